@@ -1,0 +1,225 @@
+/*
+ * lsenerf_b200.h -- C ABI of the B200-native LSENeRF per-ray hot path (liblsenerf_b200.so).
+ *
+ * Plain pointers and sizes only; every pointer is DEVICE memory unless marked [host].  All entry points
+ * enqueue work on `stream` (a cudaStream_t passed as void*) and return immediately: 0 on success, a
+ * negative code on error with a message retrievable through lse_last_error().  Nothing throws across the
+ * ABI; there is no CPU fallback.  Each function cites the reference interface it replaces (paths relative
+ * to ubc-vision/LSENeRF; "3P" = third-party kernel the reference reaches at that call site).
+ *
+ * Ragged sizes: sample-level kernels take a capacity `S_cap` and an optional device pointer `n_dev` holding
+ * the live sample count (written by lse_scan_counts); when n_dev == NULL all S_cap rows are live.  This
+ * keeps the whole step free of host synchronisation (the reference syncs with .item(),
+ * lse_grid_estimator.py:112, lse_cameras.py:360-362).
+ */
+#ifndef LSENERF_B200_H
+#define LSENERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSE_ABI_VERSION 1
+
+typedef void *lse_stream_t; /* cudaStream_t */
+
+int lse_abi_version(void);
+const char *lse_last_error(void);
+/* number of kernel launches issued through this library since load (bench.py: gpu_launches) */
+int64_t lse_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (a) ray generation
+ * ------------------------------------------------------------------------------------------------- */
+
+/* SplineCameraOptimizer.get_rgb_cameras / get_evs_cameras / get_deblur_cameras
+ * (lse_nerf/ns_camera_optimizer.py:130-197) = exp_map_to_quat_map + vectorized_generalized_interpolation +
+ * slerp + quat_map_to_mtx (lse_nerf/interpolation_utils.py:56-246).
+ *   ctrl_tangents [K,6] (t, rotvec), ctrl_ts [K], times [n]  ->  c2w [n*n_virtual,3,4]
+ *   n_virtual = 1: pose at clip(times[i]); n_virtual = 4 (deblur): (times[i]-t_offset) + t_step*k, pixel-major,
+ *   with t_offset = exp_t/2 and t_step = exp_t/(n_virtual-1) rounded to fp32 by the caller (as torch does).
+ *   dM [4,4] or NULL: right-multiply the relative event-camera transform; scale [1] or NULL scales dM[:3,3].
+ *   seg_out [n*n_virtual] int32 or NULL: the control segment chosen (bit-exact parity hook). */
+int lse_pose_interp_fwd(const float *ctrl_tangents, const float *ctrl_ts, int K, const float *times, int64_t n,
+                        int n_virtual, float t_offset, float t_step, const float *dM, const float *scale,
+                        float *c2w, int32_t *seg_out, lse_stream_t stream);
+/* backward: d_c2w [n*n_virtual,3,4] -> d_ctrl_tangents [K,6] (atomically accumulated), d_scale [1] (accumulated,
+ * may be NULL). */
+int lse_pose_interp_bwd(const float *ctrl_tangents, const float *ctrl_ts, int K, const float *times, int64_t n,
+                        int n_virtual, float t_offset, float t_step, const float *dM, const float *scale,
+                        const float *d_c2w, float *d_ctrl_tangents, float *d_scale, lse_stream_t stream);
+
+/* EdCameras._generate_rays_from_coords, perspective branch (lse_nerf/lse_cameras.py:349-395,487-493,539-561).
+ *   c2w [n,3,4], coords [n,2]=(y,x)  ->  origins [n,3], directions [n,3], pixel_area [n], dir_norm [n] */
+int lse_rays_from_c2w_fwd(const float *c2w, const float *coords, int64_t n, float fx, float fy, float cx, float cy,
+                          float *origins, float *directions, float *pixel_area, float *dir_norm,
+                          lse_stream_t stream);
+int lse_rays_from_c2w_bwd(const float *c2w, const float *coords, int64_t n, float fx, float fy, float cx, float cy,
+                          const float *d_origins, const float *d_directions, float *d_c2w, lse_stream_t stream);
+
+/* CameraOptimizer.forward + apply_to_raybundle, mode SO3xR3 (lse_nerf/ns_camera_optimizer.py:258-329):
+ *   origins += t(pose_adjustment[cam]); directions = R(pose_adjustment[cam]) @ directions.  cam_idx int64 [n]. */
+int lse_pose_delta_fwd(const float *pose_adjustment, int64_t n_cams, const int64_t *cam_idx, int64_t n,
+                       const float *origins, const float *directions, float *origins_out, float *directions_out,
+                       lse_stream_t stream);
+int lse_pose_delta_bwd(const float *pose_adjustment, int64_t n_cams, const int64_t *cam_idx, int64_t n,
+                       const float *directions, const float *d_origins_out, const float *d_directions_out,
+                       float *d_pose_adjustment, float *d_origins, float *d_directions, lse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (b) occupancy-grid marching  (3P nerfacc.grid.traverse_grids, lse_nerf/lse_grid_estimator.py:83-106)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* near = near_plane (+ jitter[r]*step_size when jitter != NULL: the stratified draw of :91-92).
+ * pass 1: counts[r] = number of samples of ray r. */
+int lse_march_count(const float *rays_o, const float *rays_d, int64_t n_rays, const uint8_t *binaries,
+                    const float *aabbs, int levels, int res, float near_plane, float far_plane,
+                    const float *jitter, float step_size, float cone_angle, int32_t *counts, lse_stream_t stream);
+/* exclusive scan of counts -> starts [n] ; total -> total_dev [1] (int32).  Also used for compaction. */
+int lse_scan_counts(const int32_t *counts, int64_t n, int32_t *starts, int32_t *total_dev, lse_stream_t stream);
+/* pass 2: writes ray_indices/t_starts/t_ends at starts[r]; rays whose samples would exceed S_cap are truncated
+ * (overflow_dev [1] int32 set to 1). */
+int lse_march_fill(const float *rays_o, const float *rays_d, int64_t n_rays, const uint8_t *binaries,
+                   const float *aabbs, int levels, int res, float near_plane, float far_plane, const float *jitter,
+                   float step_size, float cone_angle, const int32_t *starts, int64_t S_cap, int32_t *ray_indices,
+                   float *t_starts, float *t_ends, int32_t *overflow_dev, lse_stream_t stream);
+
+/* 3P nerfacc.render_visibility_from_density (lse_nerf/lse_grid_estimator.py:109-127,139-143):
+ * per ray, T = exp(-exclusive_sum(sigma*dt)), alpha = 1-exp(-sigma*dt), keep = T >= early_stop_eps &&
+ * alpha >= min(alpha_thre, *occ_mean_dev).  Writes keep [S] (uint8) and keep_counts [n_rays]. */
+int lse_visibility(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
+                   const float *t_ends, const float *sigmas, float early_stop_eps, float alpha_thre,
+                   const float *occ_mean_dev, uint8_t *keep, int32_t *keep_counts, lse_stream_t stream);
+/* stable per-ray compaction of the kept samples (ray_indices, t_starts, t_ends, h16 [S,16], sigma [S]). */
+int lse_compact(const int32_t *starts, const int32_t *counts, const int32_t *new_starts, int64_t n_rays,
+                const uint8_t *keep, const float *t_starts, const float *t_ends, const float *h16,
+                const float *sigma, int32_t *ray_indices_out, float *t_starts_out, float *t_ends_out,
+                float *h16_out, float *sigma_out, lse_stream_t stream);
+
+/* 3P nerfacc OccGridEstimator.update_every_n_steps (inherited NGP callback; lse_nerf/lsenerf.py:184-188):
+ * occs[cell] = max(occs[cell]*decay, occ[i]) for the evaluated cells, then binaries = occs > min(mean(occs), thre).
+ * cell_idx int64 [n] (global cell ids), occ [n]; occ_mean_dev [1] receives mean(occs) (the value
+ * lse_grid_estimator.py:112 reads with .item()); scratch_sum: 1 double of device scratch. */
+int lse_occ_update(float *occs, int64_t n_cells_total, const int64_t *cell_idx, const float *occ, int64_t n,
+                   float decay, float occ_thre, uint8_t *binaries, float *occ_mean_dev, double *scratch_sum,
+                   lse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (c) multiresolution hash grid (3P nerfstudio HashEncoding.pytorch_fwd semantics,
+ *     lse_nerf/lse_field.py:43-91,208,279)
+ * ------------------------------------------------------------------------------------------------- */
+/* x [S,3] in [0,1), table [L*2^log2_T, 2], scalings [L] (taken from the module buffer, never recomputed)
+ * -> out [S, 2L] level-major. */
+int lse_hashgrid_fwd(const float *x, int64_t S, const float *table, const float *scalings, int L, int log2_T,
+                     float *out, lse_stream_t stream);
+/* d_out [S,2L] -> d_table (atomically accumulated, same shape as table), d_x [S,3] (written; may be NULL). */
+int lse_hashgrid_bwd(const float *x, int64_t S, const float *table, const float *scalings, int L, int log2_T,
+                     const float *d_out, float *d_table, float *d_x, lse_stream_t stream);
+/* parity hook: the 8 table rows touched per level, idx [S,L,8] int64, corner order of pytorch_fwd. */
+int lse_hashgrid_indices(const float *x, int64_t S, const float *scalings, int L, int log2_T, int64_t *idx,
+                         lse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (c+d) field: LSEField.get_density / get_outputs (lse_nerf/lse_field.py:264-360)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+    /* hash grid */
+    const float *table; const float *scalings; int32_t levels; int32_t log2_T;
+    /* base MLP 32->64->16 (nn.Linear layout [out,in] + bias), lse_field.py:199-207 */
+    const float *W1, *b1, *W2, *b2;
+    /* colour MLP 63->64->64->3, lse_field.py:254-262 */
+    const float *W3, *b3, *W4, *b4, *W5, *b5;
+    /* appearance embedding [emb_rows,32]; emb_mode 0: row app_id[ray]; 1: row 0 (GlobalEmbedding);
+       2: zeros (eval "zero"); 3: explicit vector emb (1 row, eval "mean"/"param") */
+    const float *emb; int32_t emb_rows; int32_t emb_mode;
+    int32_t sh_shifted;        /* 1: SH evaluated on (d+1)/2 (nerfstudio torch path, lse_field.py:298) */
+    int32_t use_tensor_cores;  /* 1: tcgen05/TMEM 3xTF32 MLP kernels, 0: fp32 SIMT kernels */
+} LseFieldParams;
+
+typedef struct {
+    float *d_table;                 /* [L*T,2] accumulated */
+    float *dW1, *db1, *dW2, *db2;   /* accumulated */
+    float *dW3, *db3, *dW4, *db4, *dW5, *db5;
+    float *d_emb;                   /* [emb_rows,32] accumulated (NULL for emb_mode 2) */
+} LseFieldGrads;
+
+/* samples: position = origins[r] + directions[r] * (t0+t1)/2 with r = ray_idx ? ray_idx[i] : i; if directions ==
+ * NULL the position is origins[r] (Field.density_fn).  -> sigma [S] (density after trunc_exp * selector) and
+ * h16 [S,16] = base-MLP output (col 0 = density pre-activation, cols 1..15 = geo features). */
+int lse_field_density_fwd(const LseFieldParams *p /*[host]*/, const float *origins, const float *directions,
+                          const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap,
+                          const int32_t *n_dev, float *sigma, float *h16, lse_stream_t stream);
+/* d_sigma [S], d_h16 [S,16] (col 0 ignored; geo grads in cols 1..15) -> parameter grads, and when not NULL
+ * d_origins/d_directions [n_rays,3] (atomically accumulated per ray). */
+int lse_field_density_bwd(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                          const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                          int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                          const float *d_h16, float *d_origins, float *d_directions, lse_stream_t stream);
+/* rgb [S,3] = sigmoid(head(cat[SH16(dir), geo15, emb32])).  app_id int32 [n_rays] (per RAY) or NULL. */
+int lse_field_color_fwd(const LseFieldParams *p, const float *directions, const int32_t *ray_idx,
+                        const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb,
+                        lse_stream_t stream);
+/* d_rgb [S,3] -> d_h16 [S,16] (cols 1..15 written, col 0 zeroed), head/embedding grads, d_directions per ray. */
+int lse_field_color_bwd(const LseFieldParams *p, const LseFieldGrads *g, const float *directions,
+                        const int32_t *ray_idx, const int32_t *app_id, int64_t S_cap, const int32_t *n_dev,
+                        const float *h16, const float *d_rgb, float *d_h16, float *d_directions,
+                        lse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (e) compositing (3P nerfacc.pack_info / render_weight_from_density, nerfstudio RGB/Depth/Accumulation
+ *     renderers; lse_nerf/lsenerf.py:300-318, lse_nerf/lse_renderer.py:6-11)
+ * ------------------------------------------------------------------------------------------------- */
+/* per ray r with samples [starts[r], starts[r]+counts[r]):  w = T*alpha;  rgb_out [R,3] = sum w*rgb;
+ * acc [R] = sum w; depth_num [R] = sum w*t_mid (divide/clip on the host side of the API); weights [S] stored. */
+int lse_composite_fwd(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
+                      const float *t_ends, const float *sigma, const float *rgb, float *weights, float *rgb_out,
+                      float *acc_out, float *depth_num_out, lse_stream_t stream);
+/* d_rgb_out [R,3], d_acc [R] / d_depth_num [R] (may be NULL) -> d_sigma [S], d_rgb [S,3]. */
+int lse_composite_bwd(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
+                      const float *t_ends, const float *sigma, const float *rgb, const float *d_rgb_out,
+                      const float *d_acc, const float *d_depth_num, float *d_sigma, float *d_rgb,
+                      lse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (f) render epilogue and losses (lse_nerf/lsenerf.py:329-439, lse_nerf/intensity_mappers.py:64-87)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t use_mapping;      /* LSENeRFModelConfig.use_mapping */
+    int32_t map_mode;         /* 0 co_map, 1 evs_rgb, 2 rgb_evs */
+    int32_t rgb_mapper;       /* 0 identity, 1 gt (x^(1/2.4)), 2 powpow */
+    int32_t evs_mapper;       /* 0 none/identity, 2 powpow */
+    int32_t ev_one_dim;       /* 0 off, 1 learned (softmax weights), 2 gt gray */
+    int32_t training;
+    int32_t deblur;           /* mean over groups of 4 rays */
+    int32_t want_ev;          /* ev_out flag of get_outputs */
+} LseEpilogueCfg;
+
+/* rgb_lin [R,3] (composited) -> rgb_final [R or R/4,3], ev_linear [R,C], ev_out [R,C] (C = 1 if ev_one_dim else 3)
+ * rgb_pow / evs_pow: the Powpow coefficients [1] (or NULL); rgb_to_one_w [3] raw (pre-softmax) weights or NULL. */
+int lse_epilogue_fwd(const LseEpilogueCfg *cfg /*[host]*/, const float *rgb_lin, int64_t n_rays, const float *rgb_pow,
+                     const float *evs_pow, const float *rgb_to_one_w, float *rgb_final, float *ev_linear,
+                     float *ev_out, lse_stream_t stream);
+int lse_epilogue_bwd(const LseEpilogueCfg *cfg, const float *rgb_lin, int64_t n_rays, const float *rgb_pow,
+                     const float *evs_pow, const float *rgb_to_one_w, const float *d_rgb_final,
+                     const float *d_ev_out, float *d_rgb_lin, float *d_rgb_pow, float *d_evs_pow,
+                     float *d_rgb_to_one_w, lse_stream_t stream);
+
+/* get_loss_dict (lsenerf.py:392-439): losses[0] = MSE(col_target, col_pred);
+ * losses[1] = evs_weight * MSE(log(next+1e-6) - log(prev+1e-6), evs) with to_gray when C == 3.
+ * Also writes the gradients of each loss w.r.t. its predictions (unit upstream gradient). */
+int lse_loss_fwd(const float *col_pred, const float *col_target, int64_t n_col, const float *prev, const float *next,
+                 const float *evs, int64_t n_evs, int C, float evs_weight, float *losses, float *d_col_pred,
+                 float *d_prev, float *d_next, lse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * next-row: fused Adam over a flat fp32 arena (lse_nerf/lse_config.py:29-38)
+ * ------------------------------------------------------------------------------------------------- */
+int lse_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int step, float grad_scale, lse_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSENERF_B200_H */

@@ -1,0 +1,160 @@
+// composite.cu -- (e) alpha compositing as warp-segmented scans.
+//
+// Replaces nerfacc.pack_info / render_weight_from_density (lse_nerf/lsenerf.py:300-306) and the
+// accumulate_along_rays calls inside nerfstudio's RGB / Accumulation / Depth renderers (lsenerf.py:309-318,
+// lse_nerf/lse_renderer.py:6-11).  One warp owns one ray: lanes stride over the ray's packed samples, the exclusive
+// prefix of sigma*dt is a shuffle scan with a running carry, and the three reductions (rgb, accumulation, depth
+// numerator) are lane-private partial sums folded with one butterfly at the end -- no atomics, deterministic.
+// HBM-streaming: ~28 B read + 4 B written per sample forward.
+#include "common.cuh"
+#include "../../include/lsenerf_b200.h"
+
+namespace lse {
+
+__device__ __forceinline__ float warp_incl_scan(float v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float y = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += y;
+    }
+    return v;
+}
+
+__global__ void composite_fwd_kernel(const int32_t *__restrict__ starts, const int32_t *__restrict__ counts, int64_t n_rays,
+                                     const float *__restrict__ t_starts, const float *__restrict__ t_ends,
+                                     const float *__restrict__ sigma, const float *__restrict__ rgb,
+                                     float *__restrict__ weights, float *__restrict__ rgb_out, float *__restrict__ acc_out,
+                                     float *__restrict__ depth_num)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rays; r += n_warps) {
+        const int64_t s = starts[r];
+        const int32_t c = counts[r];
+        float carry = 0.0f, a_r = 0.0f, a_g = 0.0f, a_b = 0.0f, a_w = 0.0f, a_d = 0.0f;
+        for (int32_t k0 = 0; k0 < c; k0 += 32) {
+            const int32_t k = k0 + lane;
+            float sd = 0.0f, tm = 0.0f;
+            if (k < c) {
+                float ta = t_starts[s + k], tb = t_ends[s + k];
+                sd = sigma[s + k] * (tb - ta);
+                tm = (ta + tb) / 2.0f;
+            }
+            float inc = warp_incl_scan(sd, lane);
+            float T = expf(-(carry + (inc - sd)));
+            float alpha = 1.0f - expf(-sd);
+            float w = T * alpha;
+            if (k < c) {
+                if (weights) weights[s + k] = w;
+                const float *c3 = rgb + 3 * (s + k);
+                a_r = fmaf(w, c3[0], a_r); a_g = fmaf(w, c3[1], a_g); a_b = fmaf(w, c3[2], a_b);
+                a_w += w;
+                a_d = fmaf(w, tm, a_d);
+            }
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b); a_w = warp_sum(a_w); a_d = warp_sum(a_d);
+        if (lane == 0) {
+            rgb_out[3 * r] = a_r; rgb_out[3 * r + 1] = a_g; rgb_out[3 * r + 2] = a_b;
+            if (acc_out) acc_out[r] = a_w;
+            if (depth_num) depth_num[r] = a_d;
+        }
+    }
+}
+
+// L = sum_i w_i v_i with v_i = g_rgb . c_i + g_acc + g_dnum * tmid_i;  w_i = T_i (1 - e^{-sd_i}), T_i = e^{-sum_{j<i} sd_j}
+//   dL/dsd_i = T_{i+1} v_i - sum_{j>i} w_j v_j          (T_{i+1} = T_i e^{-sd_i})
+//   dL/dsigma_i = dt_i * dL/dsd_i ;  dL/dc_i = w_i g_rgb
+__global__ void composite_bwd_kernel(const int32_t *__restrict__ starts, const int32_t *__restrict__ counts, int64_t n_rays,
+                                     const float *__restrict__ t_starts, const float *__restrict__ t_ends,
+                                     const float *__restrict__ sigma, const float *__restrict__ rgb,
+                                     const float *__restrict__ d_rgb_out, const float *__restrict__ d_acc,
+                                     const float *__restrict__ d_dnum, float *__restrict__ d_sigma, float *__restrict__ d_rgb)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rays; r += n_warps) {
+        const int64_t s = starts[r];
+        const int32_t c = counts[r];
+        const float g0 = d_rgb_out[3 * r], g1 = d_rgb_out[3 * r + 1], g2 = d_rgb_out[3 * r + 2];
+        const float ga = d_acc ? d_acc[r] : 0.0f, gd = d_dnum ? d_dnum[r] : 0.0f;
+        // pass 1: total of w_j v_j
+        float carry = 0.0f, tot = 0.0f;
+        for (int32_t k0 = 0; k0 < c; k0 += 32) {
+            const int32_t k = k0 + lane;
+            float sd = 0.0f, v = 0.0f;
+            if (k < c) {
+                float ta = t_starts[s + k], tb = t_ends[s + k];
+                sd = sigma[s + k] * (tb - ta);
+                const float *c3 = rgb + 3 * (s + k);
+                v = g0 * c3[0] + g1 * c3[1] + g2 * c3[2] + ga + gd * ((ta + tb) / 2.0f);
+            }
+            float inc = warp_incl_scan(sd, lane);
+            float T = expf(-(carry + (inc - sd)));
+            float w = T * (1.0f - expf(-sd));
+            tot += (k < c) ? w * v : 0.0f;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        tot = warp_sum(tot);
+        // pass 2: per-sample gradients
+        carry = 0.0f;
+        float wv_carry = 0.0f;
+        for (int32_t k0 = 0; k0 < c; k0 += 32) {
+            const int32_t k = k0 + lane;
+            float sd = 0.0f, v = 0.0f, dt = 0.0f;
+            if (k < c) {
+                float ta = t_starts[s + k], tb = t_ends[s + k];
+                dt = tb - ta;
+                sd = sigma[s + k] * dt;
+                const float *c3 = rgb + 3 * (s + k);
+                v = g0 * c3[0] + g1 * c3[1] + g2 * c3[2] + ga + gd * ((ta + tb) / 2.0f);
+            }
+            float inc = warp_incl_scan(sd, lane);
+            float T = expf(-(carry + (inc - sd)));
+            float e = expf(-sd);
+            float w = T * (1.0f - e);
+            float wv = (k < c) ? w * v : 0.0f;
+            float wv_inc = warp_incl_scan(wv, lane);
+            float suffix = tot - (wv_carry + wv_inc);  // sum_{j>i} w_j v_j
+            if (k < c) {
+                d_sigma[s + k] = dt * (T * e * v - suffix);
+                float *o3 = d_rgb + 3 * (s + k);
+                o3[0] = w * g0; o3[1] = w * g1; o3[2] = w * g2;
+            }
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+            wv_carry += __shfl_sync(0xffffffffu, wv_inc, 31);
+        }
+    }
+}
+
+}  // namespace lse
+
+using namespace lse;
+
+extern "C" int lse_composite_fwd(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
+                                 const float *t_ends, const float *sigma, const float *rgb, float *weights, float *rgb_out,
+                                 float *acc_out, float *depth_num_out, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(starts && counts && t_starts && t_ends && sigma && rgb && rgb_out, "missing pointer");
+    if (n_rays <= 0) return 0;
+    int threads = 256;
+    composite_fwd_kernel<<<stride_grid(n_rays * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+        starts, counts, n_rays, t_starts, t_ends, sigma, rgb, weights, rgb_out, acc_out, depth_num_out);
+    return check_launch("lse_composite_fwd");
+}
+
+extern "C" int lse_composite_bwd(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
+                                 const float *t_ends, const float *sigma, const float *rgb, const float *d_rgb_out,
+                                 const float *d_acc, const float *d_depth_num, float *d_sigma, float *d_rgb,
+                                 lse_stream_t stream)
+{
+    LSE_CHECK_ARG(starts && counts && t_starts && t_ends && sigma && rgb && d_rgb_out && d_sigma && d_rgb, "missing pointer");
+    if (n_rays <= 0) return 0;
+    int threads = 256;
+    composite_bwd_kernel<<<stride_grid(n_rays * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+        starts, counts, n_rays, t_starts, t_ends, sigma, rgb, d_rgb_out, d_acc, d_depth_num, d_sigma, d_rgb);
+    return check_launch("lse_composite_bwd");
+}

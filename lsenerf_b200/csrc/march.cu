@@ -1,0 +1,295 @@
+// march.cu -- (b) occupancy-grid marching, visibility culling, compaction, occupancy EMA update.
+//
+// Replaces the nerfacc kernels reached at lse_nerf/lse_grid_estimator.py:93-127,139-143 and the inherited
+// OccGridEstimator.update_every_n_steps.  Two-pass ragged allocation (count -> scan -> fill) entirely on the
+// device: the live sample count stays in HBM (`total_dev`) and every downstream kernel reads it from there, so
+// a training step needs no host synchronisation.
+//
+// Kernel classes: the DDA itself is a sequential fp32 recurrence per ray (one thread per ray, bit-exact against
+// the oracle, built WITHOUT fma contraction); visibility/compaction are warp-per-ray segmented scans
+// (HBM-streaming, ~20 B per sample).
+#include "common.cuh"
+#include "math_march.cuh"
+#include "../../include/lsenerf_b200.h"
+
+namespace lse {
+
+struct CountEmit { __device__ void operator()(float, float) const {} };
+struct FillEmit {
+    float *t0, *t1; int32_t *ri; int32_t ray; int64_t base, cap; mutable int32_t k;
+    __device__ void operator()(float a, float b) const
+    {
+        int64_t p = base + k;
+        if (p < cap) { t0[p] = a; t1[p] = b; ri[p] = ray; }
+        ++k;
+    }
+};
+
+__global__ void march_count_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n_rays,
+                                   const uint8_t *__restrict__ binaries, const float *__restrict__ aabbs, int levels, int res,
+                                   float near_plane, float far_plane, const float *__restrict__ jitter, float step_size,
+                                   float cone_angle, int32_t *__restrict__ counts)
+{
+    __shared__ float s_aabb[6 * kMaxLevels];
+    for (int i = threadIdx.x; i < 6 * levels; i += blockDim.x) s_aabb[i] = aabbs[i];
+    __syncthreads();
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rays; r += (int64_t)gridDim.x * blockDim.x) {
+        float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
+        float d[3] = {rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]};
+        float nearp = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
+        counts[r] = march_ray(o, d, binaries, s_aabb, levels, res, nearp, far_plane, step_size, cone_angle, CountEmit());
+    }
+}
+
+__global__ void march_fill_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n_rays,
+                                  const uint8_t *__restrict__ binaries, const float *__restrict__ aabbs, int levels, int res,
+                                  float near_plane, float far_plane, const float *__restrict__ jitter, float step_size,
+                                  float cone_angle, const int32_t *__restrict__ starts, int64_t S_cap,
+                                  int32_t *__restrict__ ray_indices, float *__restrict__ t_starts, float *__restrict__ t_ends,
+                                  int32_t *__restrict__ overflow)
+{
+    __shared__ float s_aabb[6 * kMaxLevels];
+    for (int i = threadIdx.x; i < 6 * levels; i += blockDim.x) s_aabb[i] = aabbs[i];
+    __syncthreads();
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rays; r += (int64_t)gridDim.x * blockDim.x) {
+        float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
+        float d[3] = {rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]};
+        float nearp = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
+        FillEmit e{t_starts, t_ends, ray_indices, (int32_t)r, (int64_t)starts[r], S_cap, 0};
+        int n = march_ray(o, d, binaries, s_aabb, levels, res, nearp, far_plane, step_size, cone_angle, e);
+        if ((int64_t)starts[r] + n > S_cap && overflow) *overflow = 1;
+    }
+}
+
+// single-CTA exclusive scan (n is a ray count: 1e4 .. 1e6); 1024 threads, 4 items per thread per round.
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t *__restrict__ counts, int64_t n,
+                                                           int32_t *__restrict__ starts, int32_t *__restrict__ total)
+{
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 4096) {
+        int64_t i0 = base + 4 * (int64_t)threadIdx.x;
+        int32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < n) ? counts[i0 + j] : 0;
+        int32_t tsum = v[0] + v[1] + v[2] + v[3];
+        int32_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = warp_tot[lane];
+            int32_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += y;
+            }
+            warp_tot[lane] = winc - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        int32_t carry = carry_s;
+        int32_t excl = carry + warp_tot[wid] + (inc - tsum);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j < n) starts[i0 + j] = excl;
+            excl += v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl;  // last thread holds the running total after its 4 items
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry_s;
+}
+
+// warp per ray: transmittance scan -> keep mask + kept count
+__global__ void visibility_kernel(const int32_t *__restrict__ starts, const int32_t *__restrict__ counts, int64_t n_rays,
+                                  const float *__restrict__ t_starts, const float *__restrict__ t_ends,
+                                  const float *__restrict__ sigmas, float early_stop_eps, float alpha_thre,
+                                  const float *__restrict__ occ_mean, uint8_t *__restrict__ keep,
+                                  int32_t *__restrict__ keep_counts)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float thre = alpha_thre;
+    if (occ_mean) thre = fminf(alpha_thre, *occ_mean);
+    for (int64_t r = warp; r < n_rays; r += n_warps) {
+        const int64_t s = starts[r];
+        const int32_t c = counts[r];
+        float carry = 0.0f;
+        int32_t kept = 0;
+        for (int32_t k0 = 0; k0 < c; k0 += 32) {
+            int32_t k = k0 + lane;
+            float sd = 0.0f;
+            if (k < c) sd = sigmas[s + k] * (t_ends[s + k] - t_starts[s + k]);
+            float inc = sd;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                float y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            float excl = carry + (inc - sd);
+            float T = expf(-excl);
+            float alpha = 1.0f - expf(-sd);
+            bool vis = (k < c) && (T >= early_stop_eps) && (thre > 0.0f ? (alpha >= thre) : true);
+            if (k < c) keep[s + k] = vis ? 1 : 0;
+            kept += __popc(__ballot_sync(0xffffffffu, vis));
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) keep_counts[r] = kept;
+    }
+}
+
+__global__ void compact_kernel(const int32_t *__restrict__ starts, const int32_t *__restrict__ counts,
+                               const int32_t *__restrict__ new_starts, int64_t n_rays, const uint8_t *__restrict__ keep,
+                               const float *__restrict__ t_starts, const float *__restrict__ t_ends,
+                               const float4 *__restrict__ h16, const float *__restrict__ sigma,
+                               int32_t *__restrict__ ri_out, float *__restrict__ t0_out, float *__restrict__ t1_out,
+                               float4 *__restrict__ h16_out, float *__restrict__ sigma_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rays; r += n_warps) {
+        const int64_t s = starts[r];
+        const int32_t c = counts[r];
+        int64_t dst = new_starts[r];
+        for (int32_t k0 = 0; k0 < c; k0 += 32) {
+            int32_t k = k0 + lane;
+            bool kp = (k < c) && keep[s + k];
+            uint32_t m = __ballot_sync(0xffffffffu, kp);
+            if (kp) {
+                int64_t p = dst + __popc(m & ((1u << lane) - 1u));
+                ri_out[p] = (int32_t)r;
+                t0_out[p] = t_starts[s + k];
+                t1_out[p] = t_ends[s + k];
+                if (sigma) sigma_out[p] = sigma[s + k];
+                if (h16) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h16_out[4 * p + j] = h16[4 * (s + k) + j];
+                }
+            }
+            dst += __popc(m);
+        }
+    }
+}
+
+// ---- occupancy EMA update --------------------------------------------------------------------------------
+__global__ void occ_ema_kernel(float *__restrict__ occs, const int64_t *__restrict__ cell_idx, const float *__restrict__ occ,
+                               int64_t n, float decay)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = cell_idx[i];
+        occs[c] = fmaxf(occs[c] * decay, occ[i]);
+    }
+}
+
+__global__ void occ_sum_kernel(const float *__restrict__ occs, int64_t n, double *__restrict__ sum)
+{
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += (double)occs[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sum, acc);
+}
+
+__global__ void occ_binarize_kernel(const float *__restrict__ occs, int64_t n, const double *__restrict__ sum, float occ_thre,
+                                    uint8_t *__restrict__ binaries, float *__restrict__ occ_mean)
+{
+    float mean = (float)(*sum / (double)n);
+    float thre = fminf(mean, occ_thre);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && occ_mean) *occ_mean = mean;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        binaries[i] = occs[i] > thre ? 1 : 0;
+}
+
+}  // namespace lse
+
+using namespace lse;
+
+extern "C" int lse_march_count(const float *rays_o, const float *rays_d, int64_t n_rays, const uint8_t *binaries,
+                               const float *aabbs, int levels, int res, float near_plane, float far_plane,
+                               const float *jitter, float step_size, float cone_angle, int32_t *counts, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(levels >= 1 && levels <= kMaxLevels, "levels must be in [1,8]");
+    if (n_rays <= 0) return 0;
+    int threads = 64;  // few, long-running threads: spread rays over all SMs
+    march_count_kernel<<<stride_grid(n_rays, threads, 16), threads, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, n_rays, binaries, aabbs, levels, res, near_plane, far_plane, jitter, step_size, cone_angle, counts);
+    return check_launch("lse_march_count");
+}
+
+extern "C" int lse_scan_counts(const int32_t *counts, int64_t n, int32_t *starts, int32_t *total_dev, lse_stream_t stream)
+{
+    if (n < 0) n = 0;
+    scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, n, starts, total_dev);
+    return check_launch("lse_scan_counts");
+}
+
+extern "C" int lse_march_fill(const float *rays_o, const float *rays_d, int64_t n_rays, const uint8_t *binaries,
+                              const float *aabbs, int levels, int res, float near_plane, float far_plane, const float *jitter,
+                              float step_size, float cone_angle, const int32_t *starts, int64_t S_cap, int32_t *ray_indices,
+                              float *t_starts, float *t_ends, int32_t *overflow_dev, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(levels >= 1 && levels <= kMaxLevels, "levels must be in [1,8]");
+    if (n_rays <= 0) return 0;
+    int threads = 64;
+    march_fill_kernel<<<stride_grid(n_rays, threads, 16), threads, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, n_rays, binaries, aabbs, levels, res, near_plane, far_plane, jitter, step_size, cone_angle, starts,
+        S_cap, ray_indices, t_starts, t_ends, overflow_dev);
+    return check_launch("lse_march_fill");
+}
+
+extern "C" int lse_visibility(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
+                              const float *t_ends, const float *sigmas, float early_stop_eps, float alpha_thre,
+                              const float *occ_mean_dev, uint8_t *keep, int32_t *keep_counts, lse_stream_t stream)
+{
+    if (n_rays <= 0) return 0;
+    int threads = 256;
+    visibility_kernel<<<stride_grid(n_rays * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+        starts, counts, n_rays, t_starts, t_ends, sigmas, early_stop_eps, alpha_thre, occ_mean_dev, keep, keep_counts);
+    return check_launch("lse_visibility");
+}
+
+extern "C" int lse_compact(const int32_t *starts, const int32_t *counts, const int32_t *new_starts, int64_t n_rays,
+                           const uint8_t *keep, const float *t_starts, const float *t_ends, const float *h16,
+                           const float *sigma, int32_t *ray_indices_out, float *t_starts_out, float *t_ends_out,
+                           float *h16_out, float *sigma_out, lse_stream_t stream)
+{
+    if (n_rays <= 0) return 0;
+    int threads = 256;
+    compact_kernel<<<stride_grid(n_rays * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+        starts, counts, new_starts, n_rays, keep, t_starts, t_ends, (const float4 *)h16, sigma, ray_indices_out,
+        t_starts_out, t_ends_out, (float4 *)h16_out, sigma_out);
+    return check_launch("lse_compact");
+}
+
+extern "C" int lse_occ_update(float *occs, int64_t n_cells_total, const int64_t *cell_idx, const float *occ, int64_t n,
+                              float decay, float occ_thre, uint8_t *binaries, float *occ_mean_dev, double *scratch_sum,
+                              lse_stream_t stream)
+{
+    LSE_CHECK_ARG(scratch_sum != nullptr, "scratch_sum (1 double) required");
+    cudaStream_t st = (cudaStream_t)stream;
+    int threads = 256;
+    if (n > 0) {
+        occ_ema_kernel<<<stride_grid(n, threads), threads, 0, st>>>(occs, cell_idx, occ, n, decay);
+        int rc = check_launch("lse_occ_update/ema");
+        if (rc) return rc;
+    }
+    cudaMemsetAsync(scratch_sum, 0, sizeof(double), st);
+    occ_sum_kernel<<<stride_grid(n_cells_total, threads, 4), threads, 0, st>>>(occs, n_cells_total, scratch_sum);
+    int rc = check_launch("lse_occ_update/sum");
+    if (rc) return rc;
+    occ_binarize_kernel<<<stride_grid(n_cells_total, threads, 4), threads, 0, st>>>(occs, n_cells_total, scratch_sum, occ_thre,
+                                                                                    binaries, occ_mean_dev);
+    return check_launch("lse_occ_update/binarize");
+}
