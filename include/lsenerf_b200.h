@@ -172,10 +172,12 @@ int lse_field_color_bwd(const LseFieldParams *p, const LseFieldGrads *g, const f
  *     renderers; lse_nerf/lsenerf.py:300-318, lse_nerf/lse_renderer.py:6-11)
  * ------------------------------------------------------------------------------------------------- */
 /* per ray r with samples [starts[r], starts[r]+counts[r]):  w = T*alpha;  rgb_out [R,3] = sum w*rgb;
- * acc [R] = sum w; depth_num [R] = sum w*t_mid (divide/clip on the host side of the API); weights [S] stored. */
+ * acc [R] = sum w; depth_num [R] = sum w*t_mid; tmid_minmax [R,2] = (min,max) sample mid-point of the ray
+ * (+inf,-inf when empty) -- DepthRenderer("expected") divides by acc+1e-10 and clips to the global min/max on the
+ * host side of the API; weights [S] stored.  acc/depth_num/tmid_minmax/weights may be NULL. */
 int lse_composite_fwd(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
                       const float *t_ends, const float *sigma, const float *rgb, float *weights, float *rgb_out,
-                      float *acc_out, float *depth_num_out, lse_stream_t stream);
+                      float *acc_out, float *depth_num_out, float *tmid_minmax, lse_stream_t stream);
 /* d_rgb_out [R,3], d_acc [R] / d_depth_num [R] (may be NULL) -> d_sigma [S], d_rgb [S,3]. */
 int lse_composite_bwd(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
                       const float *t_ends, const float *sigma, const float *rgb, const float *d_rgb_out,

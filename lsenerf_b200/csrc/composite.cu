@@ -25,7 +25,7 @@ __global__ void composite_fwd_kernel(const int32_t *__restrict__ starts, const i
                                      const float *__restrict__ t_starts, const float *__restrict__ t_ends,
                                      const float *__restrict__ sigma, const float *__restrict__ rgb,
                                      float *__restrict__ weights, float *__restrict__ rgb_out, float *__restrict__ acc_out,
-                                     float *__restrict__ depth_num)
+                                     float *__restrict__ depth_num, float *__restrict__ tmid_minmax)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -60,6 +60,14 @@ __global__ void composite_fwd_kernel(const int32_t *__restrict__ starts, const i
             rgb_out[3 * r] = a_r; rgb_out[3 * r + 1] = a_g; rgb_out[3 * r + 2] = a_b;
             if (acc_out) acc_out[r] = a_w;
             if (depth_num) depth_num[r] = a_d;
+            if (tmid_minmax) {  // t is increasing along a ray: first / last sample bound the ray's mid-points
+                float lo = INFINITY, hi = -INFINITY;
+                if (c > 0) {
+                    lo = (t_starts[s] + t_ends[s]) / 2.0f;
+                    hi = (t_starts[s + c - 1] + t_ends[s + c - 1]) / 2.0f;
+                }
+                tmid_minmax[2 * r] = lo; tmid_minmax[2 * r + 1] = hi;
+            }
         }
     }
 }
@@ -136,13 +144,13 @@ using namespace lse;
 
 extern "C" int lse_composite_fwd(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
                                  const float *t_ends, const float *sigma, const float *rgb, float *weights, float *rgb_out,
-                                 float *acc_out, float *depth_num_out, lse_stream_t stream)
+                                 float *acc_out, float *depth_num_out, float *tmid_minmax, lse_stream_t stream)
 {
     LSE_CHECK_ARG(starts && counts && t_starts && t_ends && sigma && rgb && rgb_out, "missing pointer");
     if (n_rays <= 0) return 0;
     int threads = 256;
     composite_fwd_kernel<<<stride_grid(n_rays * 32, threads), threads, 0, (cudaStream_t)stream>>>(
-        starts, counts, n_rays, t_starts, t_ends, sigma, rgb, weights, rgb_out, acc_out, depth_num_out);
+        starts, counts, n_rays, t_starts, t_ends, sigma, rgb, weights, rgb_out, acc_out, depth_num_out, tmid_minmax);
     return check_launch("lse_composite_fwd");
 }
 

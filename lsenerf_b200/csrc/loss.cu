@@ -171,29 +171,18 @@ __global__ void loss_kernel(const float *__restrict__ col_pred, const float *__r
         a_rgb = fmaf(diff, diff, a_rgb);
         if (d_col) d_col[i] = -2.0f * diff * inv_rgb;
     }
-    const float inv_ev = n_evs > 0 ? 1.0f / (float)n_evs : 0.0f;
-    for (int64_t i = tid0; i < n_evs; i += stride) {
-        float pr, nx;
-        if (C == 1) { pr = prev[i]; nx = next[i]; }
-        else {
-            pr = kGray[0] * prev[3 * i] + kGray[1] * prev[3 * i + 1] + kGray[2] * prev[3 * i + 2];
-            nx = kGray[0] * next[3 * i] + kGray[1] * next[3 * i + 1] + kGray[2] * next[3 * i + 2];
-        }
+    // to_gray (utils.py:99-105) returns a 2-D [n,3] tensor unchanged, so with 3 channels the log-difference is taken
+    // per channel against the event value tiled x3 (lsenerf.py:436): element e = i*C + c compares with evs[i].
+    const int64_t nev = n_evs * C;
+    const float inv_ev = nev > 0 ? 1.0f / (float)nev : 0.0f;
+    for (int64_t e = tid0; e < nev; e += stride) {
+        float pr = prev[e], nx = next[e];
         float delta = logf(nx + kLogEps) - logf(pr + kLogEps);
-        float diff = delta - evs[i];
+        float diff = delta - evs[e / C];
         a_ev = fmaf(diff, diff, a_ev);
         float g = evs_weight * 2.0f * diff * inv_ev;
-        float gn = g / (nx + kLogEps), gp = -g / (pr + kLogEps);
-        if (C == 1) {
-            if (d_prev) d_prev[i] = gp;
-            if (d_next) d_next[i] = gn;
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (d_prev) d_prev[3 * i + c] = gp * kGray[c];
-                if (d_next) d_next[3 * i + c] = gn * kGray[c];
-            }
-        }
+        if (d_prev) d_prev[e] = -g / (pr + kLogEps);
+        if (d_next) d_next[e] = g / (nx + kLogEps);
     }
     a_rgb = warp_sum(a_rgb); a_ev = warp_sum(a_ev);
     if ((threadIdx.x & 31) == 0) {
@@ -273,7 +262,7 @@ extern "C" int lse_loss_fwd(const float *col_pred, const float *col_target, int6
     LSE_CHECK_ARG(C == 1 || C == 3, "C must be 1 or 3");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(losses, 0, 2 * sizeof(float), st);
-    int64_t n = n_col * 3 > n_evs ? n_col * 3 : n_evs;
+    int64_t n = n_col * 3 > n_evs * C ? n_col * 3 : n_evs * C;
     if (n <= 0) return 0;
     int threads = 256;
     loss_kernel<<<stride_grid(n, threads, 2), threads, 0, st>>>(col_pred, col_target, n_col, prev, next, evs, n_evs, C,

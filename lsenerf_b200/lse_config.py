@@ -1,0 +1,28 @@
+"""The four shipped experiment configurations (exp_configs/*.sh + scripts/train_evimo.sh) and the method defaults of
+lse_nerf/lse_config.py, expressed over this package's config dataclasses."""
+from __future__ import annotations
+
+from .lse_datamanager import MultiCamManagerConfig
+from .lse_embeddings import LSEEmbeddingConfig
+from .lsenerf import LSENeRFModelConfig
+from .ns_camera_optimizer import CameraOptimizerConfig
+
+TRAIN_NUM_RAYS_PER_BATCH = 3512   # lse_config.py:24
+EVAL_NUM_RAYS_PER_CHUNK = 3512    # lse_config.py:27
+
+
+def experiment(name: str, num_rays: int = TRAIN_NUM_RAYS_PER_BATCH, deblur: bool = True, cam_opt: bool = True, **model_kw):
+    """name in {"lsenerf", "lsenerf_emb", "badnerf", "badnerf_emb"} -> (MultiCamManagerConfig, LSENeRFModelConfig)."""
+    name = name.lower()
+    lse = name.startswith("lsenerf")
+    emb = "evs_emb" if name.endswith("_emb") else "global_emb"
+    loss_type = "deblur" if deblur else "linspace"
+    # scripts/train_evimo.sh:13-30 (+ train.py:295-297: deblur forces the spline RGB optimizer)
+    col = CameraOptimizerConfig(mode="SO3xR3" if cam_opt else "off", optim_type="spline", exp_t=30000)
+    evs = CameraOptimizerConfig(mode="SO3xR3" if cam_opt else "off", optim_type="ns")
+    dm = MultiCamManagerConfig(train_num_rays_per_batch=num_rays, rgb_frac=0.66 if lse else 1.0, col_cam_optimizer=col,
+                               evs_cam_optimizer=evs, rgb_loss_mode="deblur" if deblur else "mse")
+    model = LSENeRFModelConfig(use_mapping=lse, mapping_method="identity", map_mode="co_map" if lse else "None",
+                               evs_mapping_method="powpow" if lse else "None", ev_one_dim="gt", rgb_loss_type=loss_type,
+                               evs_loss_weight=1.0, embed_config=LSEEmbeddingConfig(embedding_type=emb), **model_kw)
+    return dm, model

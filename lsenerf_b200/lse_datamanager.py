@@ -1,0 +1,133 @@
+"""MultiCamManager (mirror of the hot-path part of lse_nerf/lse_datamanager.py:83-144,254-372,381-408): ray-budget
+split, pixel sampling, RGB / prev / next ray bundles, camera optimizers.  Dataset parsing and nerfstudio's
+CacheDataloader are out of scope: the manager is handed image stores directly (host tensors, like upstream where images
+stay on the CPU and only sampled pixels are copied, lse_pixel_sampler.py:28-32)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from .data_components import CameraIdxFixer
+from .lse_cameras import EdCameras
+from .lse_pixel_sampler import EvPixelSampler
+from .lse_ray_generator import ConsecRayGenerator, DeblurRayGenerator, RayGenerator
+from .ns_camera_optimizer import CameraOptimizerConfig, HardCamType
+from .utils import add_metadata, gbconfig
+
+
+@dataclass
+class MultiCamManagerConfig:
+    """lse_datamanager.py:83-144."""
+    train_num_rays_per_batch: int = 1024
+    rgb_frac: float = 0.66
+    eval_num_rays_per_batch: int = 64
+    col_cam_optimizer: CameraOptimizerConfig = field(default_factory=CameraOptimizerConfig)
+    evs_cam_optimizer: CameraOptimizerConfig = field(default_factory=CameraOptimizerConfig)
+    rgb_loss_mode: str = "mse"
+
+    def __post_init__(self):
+        self.rgb_loss_mode = self.rgb_loss_mode.lower()
+        self.update_num_batch_rays()
+
+    def update_num_batch_rays(self):
+        """:135-144."""
+        self.train_num_evs_rays_per_batch = int((1 - self.rgb_frac) * self.train_num_rays_per_batch * 0.5)
+        if self.rgb_loss_mode == "deblur":
+            self.train_num_col_rays_per_batch = int((self.train_num_rays_per_batch - self.train_num_evs_rays_per_batch * 2) * (1 / 4))
+        else:
+            self.train_num_col_rays_per_batch = self.train_num_rays_per_batch - self.train_num_evs_rays_per_batch * 2
+
+
+@dataclass
+class ImageStore:
+    """What nerfstudio's CacheDataloader hands the pixel sampler: a stacked image batch on the HOST."""
+    image: torch.Tensor          # [N,H,W,C] fp32 (pinned host memory)
+    image_idx: torch.Tensor      # [N] int64
+    appearance_id: torch.Tensor  # [N] int64
+    e_thresh: Optional[torch.Tensor] = None  # [N] (events)
+
+    def batch(self) -> Dict:
+        return {"image": self.image, "image_idx": self.image_idx, "appearance_id": self.appearance_id, "e_thresh": self.e_thresh}
+
+
+class MultiCamManager(nn.Module):
+    def __init__(self, config: MultiCamManagerConfig, col_cameras: EdCameras, evs_cameras: EdCameras, col_store: ImageStore,
+                 evs_store: ImageStore, dM: torch.Tensor, num_embd: int, device="cuda", spline_init: Optional[dict] = None,
+                 seed: Optional[int] = None) -> None:
+        super().__init__()
+        self.config = config
+        self.device = device
+        self.num_embd = num_embd
+        self.col_store, self.evs_store = col_store, evs_store
+        gen = None
+        if seed is not None:
+            gen = torch.Generator().manual_seed(seed)
+        self.train_col_pixel_sampler = EvPixelSampler(config.train_num_col_rays_per_batch, generator=gen)
+        self.train_evs_pixel_sampler = EvPixelSampler(config.train_num_evs_rays_per_batch, generator=gen)
+        # ---- setup_train, lse_datamanager.py:254-325 ------------------------------------------------------------
+        kw = dict(spline_init or {})
+        self.col_train_camera_optimizer = config.col_cam_optimizer.setup(num_cameras=col_cameras.size, device=device, dM=dM,
+                                                                         cameras=col_cameras, **kw)
+        interp = self.col_train_camera_optimizer if config.col_cam_optimizer.optim_type == "spline" else None
+        self.col_cams = col_cameras.to(device)
+        self.col_cams.set_interpolator(interp)
+        evs_interp = interp if (config.evs_cam_optimizer.optim_type == "spline" and interp is not None) else None
+        if config.evs_cam_optimizer.optim_type == "spline":
+            self.evs_train_camera_optimizer = self.col_train_camera_optimizer
+        else:
+            self.evs_train_camera_optimizer = config.evs_cam_optimizer.setup(num_cameras=evs_cameras.size, device=device)
+        self.col_ray_generator = (DeblurRayGenerator if config.rgb_loss_mode == "deblur" else RayGenerator)(self.col_cams)
+        evs_cams = evs_cameras.to(device)
+        evs_cams.set_hard_cam_type(HardCamType.EVS)
+        evs_cams.set_interpolator(evs_interp)
+        self.evs_ray_generator = ConsecRayGenerator(evs_cams)
+        self.cameraIdxFixer = CameraIdxFixer(col_cameras.times.reshape(-1), device)
+        self.to(device)
+
+    def get_train_col_rays_per_batch(self) -> int:
+        return self.config.train_num_col_rays_per_batch
+
+    def get_train_evs_rays_per_batch(self) -> int:
+        return self.config.train_num_evs_rays_per_batch
+
+    def get_train_rays_per_batch(self) -> int:
+        return self.config.train_num_rays_per_batch
+
+    def next_train(self, step: int):
+        """lse_datamanager.py:337-372 -> ((col, prev, next) bundles, {"col_batch", "evs_batch"})."""
+        self.col_train_camera_optimizer.update_mode(step)
+        self.evs_train_camera_optimizer.update_mode(step)
+        col_bundle = col_batch = prev_bundle = next_bundle = evs_batch = None
+        if self.get_train_col_rays_per_batch() > 0:
+            col_batch = self.train_col_pixel_sampler.sample(self.col_store.batch())
+            col_batch = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in col_batch.items()}
+            col_bundle = self.col_ray_generator(col_batch["indices"])
+            self.col_train_camera_optimizer.apply_to_raybundle(col_bundle)
+            col_bundle = add_metadata(col_bundle, col_batch, max_app_id=self.num_embd)
+        if self.get_train_evs_rays_per_batch() > 0:
+            evs_batch = self.train_evs_pixel_sampler.sample(self.evs_store.batch())
+            evs_batch = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in evs_batch.items()}
+            prev_bundle, next_bundle = self.evs_ray_generator(evs_batch["indices"])
+            self.evs_train_camera_optimizer.apply_to_raybundle(prev_bundle)
+            self.evs_train_camera_optimizer.apply_to_raybundle(next_bundle)
+            prev_bundle = add_metadata(prev_bundle, evs_batch, cam_id=1)
+            next_bundle = add_metadata(next_bundle, evs_batch, cam_id=1)
+        prev_bundle, next_bundle = self.cameraIdxFixer(prev_bundle), self.cameraIdxFixer(next_bundle)
+        return (col_bundle, prev_bundle, next_bundle), {"col_batch": col_batch, "evs_batch": evs_batch}
+
+    def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
+        """lse_datamanager.py:381-408."""
+        groups: Dict[str, List[nn.Parameter]] = {}
+
+        def add(params):
+            groups["camera_opt"] = groups.get("camera_opt", []) + params
+        cfg = self.config
+        if cfg.col_cam_optimizer.mode != "off" and self.get_train_col_rays_per_batch() > 0:
+            add(list(self.col_train_camera_optimizer.parameters()))
+        if cfg.evs_cam_optimizer.mode != "off" and cfg.col_cam_optimizer.mode != "spline" and self.get_train_evs_rays_per_batch() > 0:
+            if self.evs_train_camera_optimizer is not self.col_train_camera_optimizer:
+                add(list(self.evs_train_camera_optimizer.parameters()))
+        return groups

@@ -1,0 +1,97 @@
+"""LSEOccGridEstimator on the B200 marching kernels (mirror of lse_nerf/lse_grid_estimator.py and the nerfacc
+OccGridEstimator state it inherits: buffers occs / binaries / aabbs / resolution, update_every_n_steps)."""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+
+
+class LSEOccGridEstimator(nn.Module):
+    def __init__(self, roi_aabb: Tensor, resolution: int = 128, levels: int = 4) -> None:
+        super().__init__()
+        roi = torch.as_tensor(roi_aabb, dtype=torch.float32).flatten()
+        c, h = (roi[:3] + roi[3:]) / 2, (roi[3:] - roi[:3]) / 2
+        aabbs = torch.stack([torch.cat([c - h * 2**l, c + h * 2**l]) for l in range(levels)], dim=0)
+        self.levels, self.res = levels, resolution
+        self.cells_per_lvl = resolution**3
+        self.register_buffer("resolution", torch.tensor([resolution] * 3, dtype=torch.int32))
+        self.register_buffer("aabbs", aabbs)
+        self.register_buffer("occs", torch.zeros(levels * self.cells_per_lvl))
+        self.register_buffer("binaries", torch.zeros(levels, resolution, resolution, resolution, dtype=torch.bool))
+        # device copy of occs.mean(): the reference reads it with .item() every sampling() call
+        # (lse_grid_estimator.py:112); here it is refreshed by the grid-update kernel and read on the device.
+        self.register_buffer("occ_mean", torch.zeros(1), persistent=False)
+        self._mean_valid = False
+
+    def binaries_u8(self) -> Tensor:
+        return self.binaries.view(torch.uint8)
+
+    def refresh_occ_mean(self):
+        self.occ_mean.copy_(self.occs.mean().reshape(1))
+        self._mean_valid = True
+
+    def occ_mean_dev(self) -> Tensor:
+        if not self._mean_valid:
+            self.refresh_occ_mean()
+        return self.occ_mean
+
+    # ---- reference API --------------------------------------------------------------------------------------------
+    def sampling(self, rays_o: Tensor, rays_d: Tensor, sigma_fn: Optional[Callable] = None, alpha_fn: Optional[Callable] = None,
+                 near_plane: float = 0.0, far_plane: float = 1e10, t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None,
+                 render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0, stratified: bool = False,
+                 cone_angle: float = 0.0, samples_per_ray_cap: int = 1024, jitter: Optional[Tensor] = None
+                 ) -> Tuple[Tensor, Tensor, Tensor]:
+        """lse_grid_estimator.py:15-144 -> (ray_indices int64 [S], t_starts [S], t_ends [S]).  Exact-size outputs need the
+        sample count on the host, so this API-level entry synchronises once; the fused model path does not."""
+        assert t_min is None and t_max is None, "per-ray t_min/t_max are unset on the LSE path (lse_cameras.py:230-249)"
+        assert alpha_fn is None, "only sigma_fn culling is used by the reference (lsenerf.py:191-194)"
+        R = rays_o.shape[0]
+        if stratified and jitter is None:
+            jitter = torch.rand(R, device=rays_o.device)
+        m = ops.march(rays_o, rays_d, self.binaries_u8(), self.aabbs, near_plane, far_plane, render_step_size, cone_angle,
+                      jitter if stratified else None, max(1, R * samples_per_ray_cap))
+        n = int(m.total.item())
+        if int(m.overflow.item()):
+            raise RuntimeError("sample capacity exceeded: raise samples_per_ray_cap")
+        ri, t0, t1 = m.ray_indices[:n], m.t_starts[:n], m.t_ends[:n]
+        if (alpha_thre > 0.0 or early_stop_eps > 0.0) and sigma_fn is not None:
+            sig = sigma_fn(t0, t1, ri.long())
+            assert sig.shape == t0.shape, "sigmas must have shape of (N,)! Got {}".format(sig.shape)
+            sig_full = torch.zeros(m.S_cap, device=rays_o.device)
+            sig_full[:n] = sig.detach()
+            mc, _, _, _ = ops.visibility_compact(m, sig_full, None, early_stop_eps, alpha_thre, self.occ_mean_dev())
+            n2 = int(mc.total.item())
+            ri, t0, t1 = mc.ray_indices[:n2], mc.t_starts[:n2], mc.t_ends[:n2]
+        return ri.long(), t0, t1
+
+    @torch.no_grad()
+    def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
+                             warmup_steps: int = 256, n: int = 16) -> None:
+        """nerfacc OccGridEstimator.update_every_n_steps (inherited NGP callback)."""
+        if step % n != 0 or not self.training:
+            return
+        dev = self.occs.device
+        N = self.cells_per_lvl
+        idx_all, occ_all = [], []
+        for l in range(self.levels):
+            if step < warmup_steps:
+                idx = torch.arange(N, device=dev)
+            else:
+                uni = torch.randint(N, (N // 4,), device=dev)
+                occ_idx = torch.nonzero(self.binaries[l].flatten())[:, 0]
+                if occ_idx.numel() > N // 4:
+                    occ_idx = occ_idx[torch.randint(occ_idx.numel(), (N // 4,), device=dev)]
+                idx = torch.cat([uni, occ_idx], dim=0)
+            r = self.res
+            coords = torch.stack([idx // (r * r), (idx // r) % r, idx % r], dim=-1).float()
+            x = (coords + torch.rand_like(coords)) / r
+            lo, hi = self.aabbs[l, :3], self.aabbs[l, 3:]
+            occ = occ_eval_fn(lo + x * (hi - lo)).reshape(-1)
+            idx_all.append(idx + l * N); occ_all.append(occ)
+        ops.occ_update(self.occs, torch.cat(idx_all).contiguous(), torch.cat(occ_all).contiguous().float(), self.binaries_u8(),
+                       self.occ_mean, ema_decay, occ_thre)
+        self._mean_valid = True

@@ -1,0 +1,143 @@
+"""LSENeRFPipeline.get_train_loss_dict (mirror of lse_nerf/lse_pipeline.py:110-145) plus the training-step driver the
+nerfstudio Trainer provides upstream (zero_grad -> loss -> backward -> Adam)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .compat import concat_bundles
+from .lse_datamanager import MultiCamManager
+from .lsenerf import LSENeRFModel
+
+
+class LSENeRFPipeline(nn.Module):
+    def __init__(self, datamanager: MultiCamManager, model: LSENeRFModel, fuse_bundles: bool = True) -> None:
+        super().__init__()
+        self.datamanager = datamanager
+        self._model = model
+        # the three forwards of lse_pipeline.py:115-123 are independent given the same weights: issue them as ONE launch
+        # chain over the concatenated bundle (identical per-ray results), then split the outputs.
+        self.fuse_bundles = fuse_bundles
+
+    @property
+    def model(self):
+        return self._model
+
+    def get_train_loss_dict(self, step: int):
+        """lse_pipeline.py:110-145 -> (out_dict, loss_dict, metrics_dict)."""
+        bundles, batch = self.datamanager.next_train(step)
+        col_bundle, prev_bundle, next_bundle = bundles
+        col_out = prev_out = next_out = None
+        m = self._model
+        if self.fuse_bundles and col_bundle is not None and prev_bundle is not None:
+            col_out, prev_out, next_out = self._fused_forward(col_bundle, prev_bundle, next_bundle)
+        else:
+            if col_bundle is not None and len(col_bundle) > 0:
+                col_out = m(col_bundle, ev_out=False)
+            if prev_bundle is not None and len(prev_bundle) > 0:
+                prev_out = m(prev_bundle, raybd2=next_bundle, batch=batch, ev_out=True)
+                next_out = m(next_bundle, raybd2=prev_bundle, batch=batch, keep=True, ev_out=True)
+        out_dict = {"col_out": col_out, "prev_out": prev_out, "next_out": next_out}
+        metrics_dict = m.get_metrics_dict(out_dict, batch)
+        loss_dict = m.get_loss_dict(out_dict, batch, metrics_dict)
+        return out_dict, loss_dict, metrics_dict
+
+    def _fused_forward(self, col, prev, nxt):
+        m = self._model
+        big = concat_bundles([col, prev, nxt])
+        n0, n1 = len(col), len(prev)
+        raw = m.exec_get_outputs(big)
+        outs = []
+        for lo, hi, ev in ((0, n0, False), (n0, n0 + n1, True), (n0 + n1, n0 + 2 * n1, True)):
+            part = {k: v[lo:hi] for k, v in raw.items()}
+            outs.append(self._finish(part, ev))
+        return outs
+
+    def _finish(self, out, ev_out):
+        """the post-compositing half of LSENeRFModel.get_outputs applied to a slice of the fused render."""
+        m = self._model
+        c = m.config
+        cfg = m._epilogue_cfg(ev_out)
+        rgb_pow = getattr(getattr(m, "rgb_mapper", None), "pow_coeff", None)
+        evs_pow = getattr(m.evs_mapper, "pow_coeff", None)
+        w_one = m.rgb_to_one.weights.reshape(-1) if c.ev_one_dim == "learned" else None
+        lin = out["rgb"].contiguous()
+        rgb_final, ev, ev_lin = ops.epilogue(lin, cfg, rgb_pow, evs_pow, w_one)
+        out["rgb"] = rgb_final
+        if ev.numel() > 0:
+            out["ev_out"] = ev
+            out["linear"] = torch.clamp(lin.detach(), 1e-5)
+            if c.map_mode == "co_map":
+                out["ev_linear"] = ev_lin
+        return out
+
+    def get_param_groups(self) -> Dict[str, list]:
+        return {**self.datamanager.get_param_groups(), **self._model.get_param_groups()}
+
+
+@dataclass
+class OptimizerSpec:
+    """lse_config.py:29-38: Adam(lr, eps=1e-15) + ExponentialDecay(lr_final, max_steps)."""
+    lr: float
+    lr_final: float
+    max_steps: int
+    eps: float = 1e-15
+    betas: tuple = (0.9, 0.999)
+
+    def lr_at(self, step: int) -> float:
+        t = min(max(step / self.max_steps, 0.0), 1.0)
+        return math.exp(math.log(self.lr) * (1 - t) + math.log(self.lr_final) * t)
+
+
+DEFAULT_OPTIMIZERS = {"fields": OptimizerSpec(1e-2, 1e-4, 200000), "camera_opt": OptimizerSpec(1e-3, 1e-4, 5000)}
+
+
+class FusedAdam:
+    """Adam over the pipeline's parameter groups using the fused kernel (csrc/loss.cu:adam_kernel); state per tensor."""
+
+    def __init__(self, groups: Dict[str, list], specs: Dict[str, OptimizerSpec] = None) -> None:
+        self.groups = groups
+        self.specs = specs or DEFAULT_OPTIMIZERS
+        self.state = {}
+        self.step_count = 0
+
+    def zero_grad(self):
+        for ps in self.groups.values():
+            for p in ps:
+                if p.grad is not None:
+                    p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0):
+        self.step_count += 1
+        for name, ps in self.groups.items():
+            spec = self.specs[name]
+            lr = spec.lr_at(self.step_count - 1)
+            for p in ps:
+                if p.grad is None or not p.requires_grad:
+                    continue
+                st = self.state.get(p)
+                if st is None:
+                    st = self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
+                ops.adam_step(p.data, p.grad.contiguous(), st[0], st[1], lr, spec.betas[0], spec.betas[1], spec.eps,
+                              self.step_count, grad_scale)
+
+
+def train_iteration(pipeline: LSENeRFPipeline, optim: FusedAdam, step: int, world_size: int = 1):
+    """nerfstudio Trainer.train_iteration for one rank: grid update callback, zero_grad, loss, backward,
+    (gradient all-reduce over NCCL when world_size > 1), Adam."""
+    pipeline.model.update_occupancy(step)
+    optim.zero_grad()
+    _, loss_dict, metrics = pipeline.get_train_loss_dict(step)
+    loss = sum(loss_dict.values())
+    loss.backward()
+    if world_size > 1:
+        from .dist import allreduce_grads
+        allreduce_grads(optim.groups)
+    optim.step(1.0 / world_size if world_size > 1 else 1.0)
+    return loss_dict, metrics

@@ -1,0 +1,254 @@
+"""LSENeRFModel on the B200 kernels (drop-in mirror of lse_nerf/lsenerf.py:47-439).
+
+``get_outputs`` runs the whole per-bundle path -- march, density, visibility culling, colour, compositing, render
+epilogue -- as two autograd nodes over hand-written kernels with no host synchronisation; ``get_loss_dict`` is one
+more.  Eval-image visualisation / PSNR / SSIM / LPIPS (lsenerf.py:442-530) are out of scope.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+from .compat import FieldHeadNames, Frustums, RayBundle, RaySamples
+from .intensity_mappers import MAPPERS_DICT
+from .lse_embeddings import LSEEmbeddingConfig
+from .lse_field import LSEField
+from .lse_grid_estimator import LSEOccGridEstimator
+from .lse_renderer import AccumulationRenderer, DepthRenderer, LinearRenderer, RGBRenderer
+from .utils import gbconfig
+
+
+@dataclass
+class LSENeRFModelConfig:
+    """lsenerf.py:47-99 plus the InstantNGPModelConfig defaults it inherits."""
+    # InstantNGPModelConfig
+    grid_resolution: int = 128
+    grid_levels: int = 4
+    max_res: int = 2048
+    log2_hashmap_size: int = 19
+    alpha_thre: float = 0.01
+    cone_angle: float = 0.004
+    render_step_size: Optional[float] = None
+    near_plane: float = 0.05
+    far_plane: float = 1e3
+    background_color: str = "black"   # upstream default "random"; the parity build fixes black
+    disable_scene_contraction: bool = False
+    eval_num_rays_per_chunk: int = 3512
+    # LSENeRFModelConfig
+    evs_loss_weight: float = 1.0
+    emb_norm_weight: float = 1e-2
+    event_loss_type: str = "log_loss"
+    use_mapping: bool = False
+    mapping_method: str = "mlp"
+    evs_mapping_method: Optional[str] = "None"
+    ev_one_dim: object = "learned"
+    rgb_loss_type: str = "linspace"
+    use_mapper_loss: bool = False
+    mapper_loss_weight: float = 0.25
+    scaler_weight: float = 1.0
+    map_mode: str = "ev_rgb"
+    embed_config: LSEEmbeddingConfig = field(default_factory=LSEEmbeddingConfig)
+    # B200 build knobs
+    use_tensor_cores: bool = False
+    samples_per_ray_cap: int = 512
+
+    def __post_init__(self):  # lsenerf.py:86-99
+        if self.evs_mapping_method is None or str(self.evs_mapping_method).lower() == "none":
+            self.evs_mapping_method = None
+        if self.map_mode.lower() in ("none", "ev_rgb"):
+            self.map_mode = "evs_rgb"
+        if isinstance(self.ev_one_dim, str):
+            if self.ev_one_dim.lower() in ("false", "none"):
+                self.ev_one_dim = False
+            elif self.ev_one_dim.lower() == "true":
+                self.ev_one_dim = "learned"
+        if self.rgb_loss_type.lower() == "none":
+            self.rgb_loss_type = "linspace"
+
+
+class ThreeToOne(nn.Module):
+    """lsenerf.py:102-109 (softmax-weighted RGB -> 1); evaluated inside the epilogue kernel."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.weights = nn.Parameter(torch.ones(1, 3) / 3)
+
+
+class ToGrayGT(nn.Module):
+    """lsenerf.py:112-119."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.register_buffer("c2g_vec", torch.tensor([0.2989, 0.5870, 0.1140]).reshape(-1, 1))
+
+
+class LSENeRFModel(nn.Module):
+    def __init__(self, config: LSENeRFModelConfig, scene_aabb: Tensor, num_train_data: int, **kwargs) -> None:
+        super().__init__()
+        self.config = config
+        self.num_train_data = num_train_data
+        self.kwargs = kwargs
+        self.collider = None
+        self.scene_aabb = nn.Parameter(torch.as_tensor(scene_aabb, dtype=torch.float32).flatten(), requires_grad=False)
+        self.populate_modules()
+
+    @property
+    def device(self):
+        return self.scene_aabb.device
+
+    def populate_modules(self):
+        """lsenerf.py:158-228."""
+        c = self.config
+        assert c.event_loss_type.lower() == "log_loss", "enerf_norm_loss is not built into the fused loss kernel yet"
+        self.field = LSEField(aabb=self.scene_aabb.data.reshape(2, 3), num_images=self.num_train_data,
+                              log2_hashmap_size=c.log2_hashmap_size, max_res=c.max_res,
+                              spatial_distortion=not c.disable_scene_contraction, embd_config=c.embed_config,
+                              use_tensor_cores=c.use_tensor_cores)
+        if c.render_step_size is None:
+            c.render_step_size = ((self.scene_aabb[3:] - self.scene_aabb[:3]) ** 2).sum().sqrt().item() / 1000
+        self.occupancy_grid = LSEOccGridEstimator(self.scene_aabb.data, resolution=c.grid_resolution, levels=c.grid_levels)
+        self.renderer_rgb = RGBRenderer(background_color=c.background_color)
+        self.renderer_accumulation = AccumulationRenderer()
+        self.renderer_depth = DepthRenderer(method="expected")
+        if c.use_mapping:
+            init = MAPPERS_DICT.get(c.mapping_method.lower())
+            assert init is not None, f"{c.mapping_method} mapper is not supported"
+            self.rgb_mapper = init()
+            self.renderer_rgb = LinearRenderer(background_color=c.background_color)
+        self.evs_mapper = None
+        if c.evs_mapping_method is not None and c.map_mode == "co_map":
+            init = MAPPERS_DICT.get(c.evs_mapping_method.lower())
+            assert init is not None, f"{c.evs_mapping_method} mapper is not supported"
+            self.evs_mapper = init()
+        if c.ev_one_dim == "learned":
+            self.rgb_to_one = ThreeToOne()
+        elif c.ev_one_dim == "gt":
+            self.rgb_to_one = ToGrayGT()
+
+    def get_param_groups(self):
+        """lsenerf.py:231-249."""
+        c = self.config
+        groups = {"fields": list(self.field.parameters())}
+        if c.mapping_method == "gt":
+            return groups
+        if c.use_mapping:
+            groups["fields"] += list(self.rgb_mapper.parameters())
+        if c.ev_one_dim:
+            groups["fields"] += list(self.rgb_to_one.parameters())
+        if c.evs_mapping_method is not None and self.evs_mapper is not None:
+            groups["fields"] += list(self.evs_mapper.parameters())
+        if gbconfig.IS_EVAL:
+            groups["fields"] = list(self.field.embedding_appearance.parameters())
+        return groups
+
+    def init_test_params(self):
+        self.field.embedding_appearance.init_test_params()
+
+    def update_occupancy(self, step: int):
+        """Inherited NGP BEFORE_TRAIN_ITERATION callback: occ = density * render_step_size."""
+        self.occupancy_grid.update_every_n_steps(step, occ_eval_fn=lambda x: self.field.density_fn(x) * self.config.render_step_size)
+
+    # ---- forward ----------------------------------------------------------------------------------------------------
+    def forward(self, ray_bundle: RayBundle, **kwargs):
+        if self.collider is not None:
+            ray_bundle = self.collider(ray_bundle)
+        return self.get_outputs(ray_bundle, **kwargs)
+
+    def _render_opts(self) -> ops.RenderOpts:
+        c, g = self.config, self.occupancy_grid
+        return ops.RenderOpts(binaries_u8=g.binaries_u8(), aabbs=g.aabbs, occ_mean_dev=g.occ_mean_dev(), near=c.near_plane,
+                              far=c.far_plane, step=float(c.render_step_size), cone=c.cone_angle, alpha_thre=c.alpha_thre,
+                              early_stop_eps=1e-4, cull=self.training, samples_per_ray_cap=c.samples_per_ray_cap)
+
+    def exec_get_outputs(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None, opts: Optional[ops.RenderOpts] = None):
+        """lsenerf.py:278-326: sampler -> field -> weights -> renderers, as one fused autograd node."""
+        R = len(ray_bundle)
+        dev = ray_bundle.origins.device
+        fw = self.field.weights()
+        opts = opts or self._render_opts()
+        if self.training and jitter is None:  # stratified=self.training (lse_grid_estimator.py:91-92)
+            jitter = torch.rand(R, device=dev)
+        app = None
+        if fw.emb_mode == 0:
+            app = ray_bundle.metadata["appearance_id"].reshape(-1).to(torch.int32).contiguous()
+        rgb, acc, dnum, mm, nspr = ops.render_rays(fw, opts, ray_bundle.origins, ray_bundle.directions,
+                                                   jitter if self.training else None, app)
+        if not self.training and not isinstance(self.renderer_rgb, LinearRenderer):
+            rgb = torch.clamp(rgb, 0.0, 1.0)  # RGBRenderer eval clamp (nan_to_num is a no-op on sigmoid outputs)
+        return {"rgb": rgb, "accumulation": acc, "depth": ops.finalize_depth(dnum, acc, mm), "num_samples_per_ray": nspr}
+
+    def _epilogue_cfg(self, ev_out: bool):
+        c = self.config
+        return ops.epilogue_cfg(c.use_mapping, c.map_mode, getattr(getattr(self, "rgb_mapper", None), "kind", None),
+                                getattr(self.evs_mapper, "kind", None), c.ev_one_dim, self.training,
+                                c.rgb_loss_type == "deblur", ev_out)
+
+    def get_outputs(self, ray_bundle: RayBundle, ev_out=False, jitter=None, **kwargs):
+        """lsenerf.py:329-377."""
+        out = self.exec_get_outputs(ray_bundle, jitter)
+        c = self.config
+        cfg = self._epilogue_cfg(ev_out)
+        rgb_pow = getattr(getattr(self, "rgb_mapper", None), "pow_coeff", None)
+        evs_pow = getattr(self.evs_mapper, "pow_coeff", None)
+        w_one = self.rgb_to_one.weights.reshape(-1) if c.ev_one_dim == "learned" else None
+        lin = out["rgb"]
+        rgb_final, ev, ev_lin = ops.epilogue(lin, cfg, rgb_pow, evs_pow, w_one)
+        out["rgb"] = rgb_final
+        if ev.numel() > 0:
+            out["ev_out"] = ev
+            if c.map_mode == "rgb_evs":
+                out["linear"] = torch.cat([ev] * 3, dim=-1) if ev.shape[-1] == 1 else ev
+            else:
+                out["linear"] = torch.clamp(lin.detach(), 1e-5)
+            if c.map_mode == "co_map":
+                out["ev_linear"] = ev_lin
+        return out
+
+    # ---- losses -----------------------------------------------------------------------------------------------------
+    def get_metrics_dict(self, outputs, batch):
+        md = {}
+        col = outputs.get("col_out")
+        if col is not None and batch.get("col_batch") is not None:
+            img = batch["col_batch"]["image"].to(self.device)
+            mse = torch.mean((col["rgb"].detach() - img) ** 2)
+            md["col_psnr"] = -10.0 * torch.log10(mse)
+            md["col_num_samples_per_batch"] = col["num_samples_per_ray"].sum()
+        return md
+
+    def get_loss_dict(self, outputs, batch, metrics_dict=None):
+        """lsenerf.py:422-439."""
+        c = self.config
+        col_batch, evs_batch = batch["col_batch"], batch["evs_batch"]
+        col_out, prev_out, next_out = outputs["col_out"], outputs["prev_out"], outputs["next_out"]
+        col_pred = col_out["rgb"] if col_out is not None else None
+        col_img = col_batch["image"].to(self.device) if col_out is not None else None
+        prev = nxt = evs = None
+        if prev_out is not None:
+            key = "rgb" if not c.use_mapping else "ev_out"
+            prev, nxt = prev_out[key], next_out[key]
+            evs = evs_batch["image"].to(self.device)
+        l_rgb, l_ev = ops.losses(col_pred, col_img, prev, nxt, evs, c.evs_loss_weight)
+        ld = {}
+        if col_out is not None:
+            ld["rgb_loss"] = l_rgb
+        if prev_out is not None:
+            ld["event_loss"] = l_ev
+        return ld
+
+    # ---- eval rendering ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle, chunk: Optional[int] = None) -> Dict[str, Tensor]:
+        """nerfstudio Model.get_outputs_for_camera_ray_bundle (call site lse_pipeline.py:212): chunked full-frame render."""
+        chunk = chunk or self.config.eval_num_rays_per_chunk
+        H, W = camera_ray_bundle.origins.shape[:2]
+        flat = camera_ray_bundle.flatten()
+        outs: Dict[str, list] = {}
+        for i in range(0, H * W, chunk):
+            o = self.forward(flat[i:i + chunk])
+            for k, v in o.items():
+                outs.setdefault(k, []).append(v)
+        return {k: torch.cat(v).view(H, W, -1) for k, v in outs.items() if v[0].shape[0] == min(chunk, H * W) or k != "x"}

@@ -1,0 +1,615 @@
+"""torch.autograd.Function wrappers over the C ABI (include/lsenerf_b200.h).
+
+Every op runs hand-written sm_100a kernels on the current torch CUDA stream; parameters stay ordinary torch
+tensors (the library only borrows their device pointers for the duration of a call).  Shape/dtype/device checks
+live here, not in the kernels (same split as the reference, which asserts in Python: lse_cameras.py:132-217).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field as dc_field
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import P, call, stream
+
+
+def _f32(t: Tensor, name: str) -> Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _acc_grad(p: Tensor) -> Tensor:
+    """Gradient buffer the kernels accumulate into: p.grad itself (allocated zero-filled on first use)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+# =================================================================================================================
+# (a) ray generation
+# =================================================================================================================
+class _PoseInterp(torch.autograd.Function):
+    """SplineCameraOptimizer.get_*_cameras (ns_camera_optimizer.py:130-197)."""
+
+    @staticmethod
+    def forward(ctx, ctrl_tangents, scale, ctrl_ts, times, n_virtual, exp_t, dM):
+        ct = _f32(ctrl_tangents, "ctrl_tangents")
+        ts = _f32(times.reshape(-1), "times")
+        n = ts.numel()
+        t_off = float(torch.tensor(exp_t / 2, dtype=torch.float32)) if n_virtual > 1 else 0.0
+        t_step = float(torch.tensor(exp_t / (n_virtual - 1), dtype=torch.float32)) if n_virtual > 1 else 0.0
+        out = torch.empty(n * n_virtual, 3, 4, device=ct.device, dtype=torch.float32)
+        call("lse_pose_interp_fwd", P(ct), P(ctrl_ts), ct.shape[0], P(ts), n, n_virtual, t_off, t_step, P(dM),
+             P(scale) if (scale is not None and dM is not None) else None, P(out), None, stream())
+        ctx.save_for_backward(ct, ctrl_ts, ts, dM if dM is not None else ct.new_empty(0),
+                              scale if scale is not None else ct.new_empty(0))
+        ctx.meta = (n, n_virtual, t_off, t_step, dM is not None, scale is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_c2w):
+        ct, ctrl_ts, ts, dM, scale = ctx.saved_tensors
+        n, n_virtual, t_off, t_step, has_dM, has_scale = ctx.meta
+        d_ct = torch.zeros_like(ct)
+        d_scale = torch.zeros(1, device=ct.device) if (has_scale and has_dM) else None
+        call("lse_pose_interp_bwd", P(ct), P(ctrl_ts), ct.shape[0], P(ts), n, n_virtual, t_off, t_step,
+             P(dM) if has_dM else None, P(scale) if (has_scale and has_dM) else None, P(d_c2w.contiguous()), P(d_ct),
+             P(d_scale), stream())
+        return d_ct, (d_scale if has_scale else None), None, None, None, None, None
+
+
+def pose_interp(ctrl_tangents, ctrl_ts, times, n_virtual=1, exp_t=0.0, dM=None, scale=None) -> Tensor:
+    return _PoseInterp.apply(ctrl_tangents, scale, ctrl_ts, times, n_virtual, exp_t, dM)
+
+
+def pose_segments(ctrl_tangents, ctrl_ts, times) -> Tensor:
+    """parity hook: control segment index chosen for each query time."""
+    ts = _f32(times.reshape(-1), "times")
+    out = torch.empty(ts.numel(), 3, 4, device=ts.device)
+    seg = torch.empty(ts.numel(), dtype=torch.int32, device=ts.device)
+    call("lse_pose_interp_fwd", P(_f32(ctrl_tangents, "ctrl")), P(ctrl_ts), ctrl_tangents.shape[0], P(ts), ts.numel(), 1,
+         0.0, 0.0, None, None, P(out), P(seg), stream())
+    return seg
+
+
+class _RaysFromC2W(torch.autograd.Function):
+    """EdCameras._generate_rays_from_coords, perspective (lse_cameras.py:349-395,487-493,539-561)."""
+
+    @staticmethod
+    def forward(ctx, c2w, coords, fx, fy, cx, cy):
+        c2w = _f32(c2w, "c2w"); coords = _f32(coords, "coords")
+        n = coords.shape[0]
+        o = torch.empty(n, 3, device=c2w.device); d = torch.empty(n, 3, device=c2w.device)
+        area = torch.empty(n, 1, device=c2w.device); nrm = torch.empty(n, 1, device=c2w.device)
+        call("lse_rays_from_c2w_fwd", P(c2w), P(coords), n, fx, fy, cx, cy, P(o), P(d), P(area), P(nrm), stream())
+        ctx.save_for_backward(c2w, coords)
+        ctx.intr = (fx, fy, cx, cy)
+        ctx.mark_non_differentiable(area, nrm)
+        return o, d, area, nrm
+
+    @staticmethod
+    def backward(ctx, d_o, d_d, _a, _n):
+        c2w, coords = ctx.saved_tensors
+        g = torch.empty_like(c2w)
+        call("lse_rays_from_c2w_bwd", P(c2w), P(coords), coords.shape[0], *ctx.intr,
+             P(d_o.contiguous()) if d_o is not None else None, P(d_d.contiguous()) if d_d is not None else None, P(g), stream())
+        return g, None, None, None, None, None
+
+
+def rays_from_c2w(c2w, coords, fx, fy, cx, cy):
+    return _RaysFromC2W.apply(c2w, coords, float(fx), float(fy), float(cx), float(cy))
+
+
+class _PoseDelta(torch.autograd.Function):
+    """CameraOptimizer.apply_to_raybundle, SO3xR3 (ns_camera_optimizer.py:258-329)."""
+
+    @staticmethod
+    def forward(ctx, pose_adjustment, cam_idx, origins, directions):
+        pa = _f32(pose_adjustment, "pose_adjustment"); o = _f32(origins, "origins"); d = _f32(directions, "directions")
+        ci = cam_idx.reshape(-1).to(torch.int64).contiguous()
+        n = o.shape[0]
+        oo = torch.empty_like(o); dd = torch.empty_like(d)
+        call("lse_pose_delta_fwd", P(pa), pa.shape[0], P(ci), n, P(o), P(d), P(oo), P(dd), stream())
+        ctx.save_for_backward(pa, ci, d)
+        return oo, dd
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        pa, ci, d = ctx.saved_tensors
+        n = d.shape[0]
+        d_pa = torch.zeros_like(pa); d_o = torch.empty_like(d); d_d = torch.empty_like(d)
+        call("lse_pose_delta_bwd", P(pa), pa.shape[0], P(ci), n, P(d), P(g_o.contiguous()) if g_o is not None else None,
+             P(g_d.contiguous()) if g_d is not None else None, P(d_pa), P(d_o), P(d_d), stream())
+        return d_pa, None, d_o, d_d
+
+
+def pose_delta(pose_adjustment, cam_idx, origins, directions):
+    return _PoseDelta.apply(pose_adjustment, cam_idx, origins, directions)
+
+
+# =================================================================================================================
+# (b) marching
+# =================================================================================================================
+@dataclass
+class MarchResult:
+    ray_indices: Tensor   # int32 [S_cap]
+    t_starts: Tensor      # [S_cap]
+    t_ends: Tensor        # [S_cap]
+    starts: Tensor        # int32 [R]
+    counts: Tensor        # int32 [R]
+    total: Tensor         # int32 [1] device-side live count
+    overflow: Tensor      # int32 [1]
+    S_cap: int
+
+
+def scan_counts(counts: Tensor):
+    starts = torch.empty_like(counts)
+    total = torch.empty(1, dtype=torch.int32, device=counts.device)
+    call("lse_scan_counts", P(counts), counts.numel(), P(starts), P(total), stream())
+    return starts, total
+
+
+def march(rays_o, rays_d, binaries_u8, aabbs, near, far, step, cone, jitter: Optional[Tensor], S_cap: int) -> MarchResult:
+    """traverse_grids (lse_grid_estimator.py:83-106) without a host sync: capacity-bounded packed output."""
+    o = _f32(rays_o.detach(), "rays_o"); d = _f32(rays_d.detach(), "rays_d")
+    R = o.shape[0]
+    dev = o.device
+    levels, res = binaries_u8.shape[0], binaries_u8.shape[1]
+    counts = torch.empty(R, dtype=torch.int32, device=dev)
+    jit = _f32(jitter, "jitter") if jitter is not None else None
+    call("lse_march_count", P(o), P(d), R, P(binaries_u8), P(aabbs), levels, res, near, far, P(jit), step, cone, P(counts), stream())
+    starts, total = scan_counts(counts)
+    ri = torch.empty(S_cap, dtype=torch.int32, device=dev)
+    t0 = torch.empty(S_cap, device=dev); t1 = torch.empty(S_cap, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("lse_march_fill", P(o), P(d), R, P(binaries_u8), P(aabbs), levels, res, near, far, P(jit), step, cone, P(starts),
+         S_cap, P(ri), P(t0), P(t1), P(overflow), stream())
+    return MarchResult(ri, t0, t1, starts, counts, total, overflow, S_cap)
+
+
+def visibility_compact(m: MarchResult, sigma: Tensor, h16: Optional[Tensor], early_stop_eps, alpha_thre, occ_mean_dev):
+    """render_visibility_from_density + mask filter (lse_grid_estimator.py:109-143), device-side."""
+    dev = sigma.device
+    R = m.counts.numel()
+    keep = torch.empty(m.S_cap, dtype=torch.uint8, device=dev)
+    kc = torch.empty(R, dtype=torch.int32, device=dev)
+    call("lse_visibility", P(m.starts), P(m.counts), R, P(m.t_starts), P(m.t_ends), P(sigma), early_stop_eps, alpha_thre,
+         P(occ_mean_dev), P(keep), P(kc), stream())
+    ns, total = scan_counts(kc)
+    ri = torch.empty_like(m.ray_indices); t0 = torch.empty_like(m.t_starts); t1 = torch.empty_like(m.t_ends)
+    h_out = torch.empty_like(h16) if h16 is not None else None
+    s_out = torch.empty_like(sigma)
+    call("lse_compact", P(m.starts), P(m.counts), P(ns), R, P(keep), P(m.t_starts), P(m.t_ends), P(h16), P(sigma), P(ri), P(t0),
+         P(t1), P(h_out), P(s_out), stream())
+    return MarchResult(ri, t0, t1, ns, kc, total, m.overflow, m.S_cap), s_out, h_out, keep
+
+
+# =================================================================================================================
+# (c) hash grid
+# =================================================================================================================
+class _HashEncode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, scalings, log2_T):
+        x = _f32(x, "x"); table = _f32(table, "hash_table")
+        S, L = x.shape[0], scalings.numel()
+        out = torch.empty(S, 2 * L, device=x.device)
+        call("lse_hashgrid_fwd", P(x), S, P(table), P(scalings), L, log2_T, P(out), stream())
+        ctx.save_for_backward(x, table, scalings)
+        ctx.log2_T = log2_T
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, table, scalings = ctx.saved_tensors
+        S, L = x.shape[0], scalings.numel()
+        need_t, need_x = ctx.needs_input_grad[1], ctx.needs_input_grad[0]
+        d_table = torch.zeros_like(table) if need_t else None
+        d_x = torch.empty_like(x) if need_x else None
+        call("lse_hashgrid_bwd", P(x), S, P(table), P(scalings), L, ctx.log2_T, P(g.contiguous()), P(d_table), P(d_x), stream())
+        return d_x, d_table, None, None
+
+
+def hash_encode(x, table, scalings, log2_T):
+    return _HashEncode.apply(x, table, scalings, log2_T)
+
+
+def hash_indices(x, scalings, log2_T) -> Tensor:
+    x = _f32(x, "x")
+    S, L = x.shape[0], scalings.numel()
+    idx = torch.empty(S, L, 8, dtype=torch.int64, device=x.device)
+    call("lse_hashgrid_indices", P(x), S, P(scalings), L, log2_T, P(idx), stream())
+    return idx
+
+
+# =================================================================================================================
+# (c+d) field
+# =================================================================================================================
+@dataclass
+class FieldWeights:
+    """Borrowed parameter tensors of LSEField (checkpoint keys in SURVEY Appendix D)."""
+    table: Tensor
+    scalings: Tensor
+    log2_T: int
+    W1: Tensor; b1: Tensor; W2: Tensor; b2: Tensor
+    W3: Tensor; b3: Tensor; W4: Tensor; b4: Tensor; W5: Tensor; b5: Tensor
+    emb: Optional[Tensor]
+    emb_mode: int = 1          # 0 per-ray appearance id, 1 row 0, 2 zeros, 3 explicit 1-row vector
+    sh_shifted: bool = True
+    use_tensor_cores: bool = False
+
+    def tensors(self):
+        return [self.table, self.W1, self.b1, self.W2, self.b2, self.W3, self.b3, self.W4, self.b4, self.W5, self.b5]
+
+    def c_params(self) -> _lib.LseFieldParams:
+        p = _lib.LseFieldParams()
+        p.table = self.table.data_ptr(); p.scalings = self.scalings.data_ptr()
+        p.levels = self.scalings.numel(); p.log2_T = self.log2_T
+        for n in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "W5", "b5"):
+            t = getattr(self, n)
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise RuntimeError(f"{n}: need a contiguous CUDA float32 tensor")
+            setattr(p, n, t.data_ptr())
+        if self.emb is not None and self.emb_mode != 2:
+            p.emb = self.emb.data_ptr(); p.emb_rows = self.emb.shape[0]
+        else:
+            p.emb = None; p.emb_rows = 0
+        p.emb_mode = self.emb_mode
+        p.sh_shifted = 1 if self.sh_shifted else 0
+        p.use_tensor_cores = 1 if self.use_tensor_cores else 0
+        return p
+
+
+def _grads_struct(fw: FieldWeights, bufs: dict) -> _lib.LseFieldGrads:
+    g = _lib.LseFieldGrads()
+    g.d_table = bufs["table"].data_ptr() if bufs.get("table") is not None else None
+    for n in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "W5", "b5"):
+        setattr(g, "d" + n, bufs[n].data_ptr() if bufs.get(n) is not None else None)
+    g.d_emb = bufs["emb"].data_ptr() if bufs.get("emb") is not None else None
+    return g
+
+
+def field_density_raw(fw: FieldWeights, origins, directions, ray_idx, t0, t1, S_cap, n_dev):
+    """no-grad density pass -> (sigma [S_cap], h16 [S_cap,16])."""
+    dev = origins.device
+    sigma = torch.empty(S_cap, device=dev); h16 = torch.empty(S_cap, 16, device=dev)
+    cp = fw.c_params()
+    call("lse_field_density_fwd", ctypes.byref(cp), P(origins), P(directions), P(ray_idx), P(t0), P(t1), S_cap, P(n_dev),
+         P(sigma), P(h16), stream())
+    return sigma, h16
+
+
+def field_color_raw(fw: FieldWeights, directions, ray_idx, app_id, S_cap, n_dev, h16):
+    rgb = torch.empty(S_cap, 3, device=h16.device)
+    cp = fw.c_params()
+    call("lse_field_color_fwd", ctypes.byref(cp), P(directions), P(ray_idx), P(app_id), S_cap, P(n_dev), P(h16), P(rgb), stream())
+    return rgb
+
+
+_DENS_KEYS = ("table", "W1", "b1", "W2", "b2")
+_COL_KEYS = ("W3", "b3", "W4", "b4", "W5", "b5")
+
+
+class _FieldDensity(torch.autograd.Function):
+    """LSEField.get_density on explicit sample frustums (lse_field.py:264-288)."""
+
+    @staticmethod
+    def forward(ctx, origins, directions, t0, t1, fw: FieldWeights, table, W1, b1, W2, b2):
+        o = _f32(origins, "origins")
+        d = _f32(directions, "directions") if directions is not None else None
+        S = o.shape[0]
+        sigma, h16 = field_density_raw(fw, o, d, None, t0, t1, S, None)
+        ctx.fw = fw
+        ctx.save_for_backward(o, d if d is not None else o.new_empty(0), t0 if t0 is not None else o.new_empty(0),
+                              t1 if t1 is not None else o.new_empty(0), h16)
+        ctx.has = (d is not None, t0 is not None)
+        return sigma, h16
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_h16):
+        o, d, t0, t1, h16 = ctx.saved_tensors
+        has_d, has_t = ctx.has
+        fw = ctx.fw
+        S = o.shape[0]
+        bufs = {k: torch.zeros_like(getattr(fw, k)) for k in _DENS_KEYS}
+        need_o, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and has_d
+        g_o = torch.zeros_like(o) if need_o else None
+        g_d = torch.zeros_like(o) if need_d else None
+        cp = fw.c_params(); cg = _grads_struct(fw, bufs)
+        call("lse_field_density_bwd", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d) if has_d else None, None,
+             P(t0) if has_t else None, P(t1) if has_t else None, S, None, P(h16),
+             P(d_sigma.contiguous()) if d_sigma is not None else None, P(d_h16.contiguous()) if d_h16 is not None else None,
+             P(g_o), P(g_d), stream())
+        return g_o, g_d, None, None, None, bufs["table"], bufs["W1"], bufs["b1"], bufs["W2"], bufs["b2"]
+
+
+def field_density(fw: FieldWeights, origins, directions=None, t0=None, t1=None):
+    return _FieldDensity.apply(origins, directions, t0, t1, fw, fw.table, fw.W1, fw.b1, fw.W2, fw.b2)
+
+
+class _FieldColor(torch.autograd.Function):
+    """LSEField.get_outputs (lse_field.py:290-360): rgb = sigmoid(head(cat[SH, geo, emb]))."""
+
+    @staticmethod
+    def forward(ctx, directions, h16, app_id, fw: FieldWeights, W3, b3, W4, b4, W5, b5, emb):
+        d = _f32(directions, "directions"); h16 = _f32(h16, "h16")
+        S = d.shape[0]
+        rgb = field_color_raw(fw, d, None, app_id, S, None, h16)
+        ctx.fw = fw
+        ctx.save_for_backward(d, h16, app_id if app_id is not None else d.new_empty(0, dtype=torch.int32))
+        ctx.has_app = app_id is not None
+        return rgb
+
+    @staticmethod
+    def backward(ctx, d_rgb):
+        d, h16, app = ctx.saved_tensors
+        fw = ctx.fw
+        S = d.shape[0]
+        bufs = {k: torch.zeros_like(getattr(fw, k)) for k in _COL_KEYS}
+        want_emb = fw.emb is not None and fw.emb_mode in (0, 1) and ctx.needs_input_grad[10]
+        bufs["emb"] = torch.zeros_like(fw.emb) if want_emb else None
+        d_h16 = torch.empty_like(h16)
+        g_d = torch.zeros_like(d) if ctx.needs_input_grad[0] else None
+        cp = fw.c_params(); cg = _grads_struct(fw, bufs)
+        call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), None, P(app) if ctx.has_app else None, S, None,
+             P(h16), P(d_rgb.contiguous()), P(d_h16), P(g_d), stream())
+        return (g_d, d_h16, None, None, bufs["W3"], bufs["b3"], bufs["W4"], bufs["b4"], bufs["W5"], bufs["b5"], bufs["emb"])
+
+
+def field_color(fw: FieldWeights, directions, h16, app_id=None):
+    return _FieldColor.apply(directions, h16, app_id, fw, fw.W3, fw.b3, fw.W4, fw.b4, fw.W5, fw.b5, fw.emb)
+
+
+# =================================================================================================================
+# (e) compositing
+# =================================================================================================================
+class _Composite(torch.autograd.Function):
+    """pack_info + render_weight_from_density + accumulate_along_rays (lsenerf.py:300-318)."""
+
+    @staticmethod
+    def forward(ctx, sigma, rgb, t0, t1, starts, counts):
+        R = counts.numel()
+        dev = sigma.device
+        S = sigma.numel()
+        w = torch.empty(S, device=dev)
+        out = torch.empty(R, 3, device=dev); acc = torch.empty(R, 1, device=dev); dnum = torch.empty(R, 1, device=dev)
+        mm = torch.empty(R, 2, device=dev)
+        call("lse_composite_fwd", P(starts), P(counts), R, P(t0), P(t1), P(_f32(sigma, "sigma")), P(_f32(rgb, "rgb")), P(w),
+             P(out), P(acc), P(dnum), P(mm), stream())
+        ctx.save_for_backward(sigma, rgb, t0, t1, starts, counts)
+        ctx.mark_non_differentiable(w, mm)
+        return out, acc, dnum, w, mm
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_acc, g_dnum, _w, _mm):
+        sigma, rgb, t0, t1, starts, counts = ctx.saved_tensors
+        R = counts.numel()
+        d_sigma = torch.zeros_like(sigma); d_rgb = torch.zeros_like(rgb)
+        if g_rgb is None:
+            g_rgb = torch.zeros(R, 3, device=sigma.device)
+        call("lse_composite_bwd", P(starts), P(counts), R, P(t0), P(t1), P(sigma), P(rgb), P(g_rgb.contiguous()),
+             P(g_acc.contiguous()) if g_acc is not None else None, P(g_dnum.contiguous()) if g_dnum is not None else None,
+             P(d_sigma), P(d_rgb), stream())
+        return d_sigma, d_rgb, None, None, None, None
+
+
+def composite(sigma, rgb, t0, t1, starts, counts):
+    return _Composite.apply(sigma, rgb, t0, t1, starts, counts)
+
+
+def finalize_depth(dnum: Tensor, acc: Tensor, mm: Tensor) -> Tensor:
+    """DepthRenderer('expected'): depth = sum(w*t)/(acc+1e-10) clipped to [min t_mid, max t_mid] over all samples."""
+    depth = dnum / (acc + 1e-10)
+    return torch.clip(depth, mm[:, 0].min(), mm[:, 1].max())
+
+
+# =================================================================================================================
+# fused render: march -> density -> cull -> colour -> composite, one autograd node, no host sync
+# =================================================================================================================
+@dataclass
+class RenderOpts:
+    binaries_u8: Tensor
+    aabbs: Tensor
+    occ_mean_dev: Optional[Tensor]
+    near: float = 0.05
+    far: float = 1e3
+    step: float = (12.0 ** 0.5) / 1000.0
+    cone: float = 0.004
+    alpha_thre: float = 0.01
+    early_stop_eps: float = 1e-4
+    cull: bool = True                  # training: sigma_fn given (lse_grid_estimator.py:109-143)
+    samples_per_ray_cap: int = 512     # packed capacity = R * this
+    accumulate_into_grad: bool = True  # parameter grads are accumulated straight into p.grad (no 64 MiB temporaries)
+    keep_debug: bool = False
+    debug: dict = dc_field(default_factory=dict)
+
+
+class _RenderRays(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, origins, directions, jitter, app_id, fw: FieldWeights, opts: RenderOpts, *params):
+        o = _f32(origins, "origins"); d = _f32(directions, "directions")
+        R = o.shape[0]
+        S_cap = max(1, R * opts.samples_per_ray_cap)
+        m0 = march(o, d, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step, opts.cone, jitter, S_cap)
+        sigma, h16 = field_density_raw(fw, o, d, m0.ray_indices, m0.t_starts, m0.t_ends, S_cap, m0.total)
+        if opts.cull and (opts.alpha_thre > 0.0 or opts.early_stop_eps > 0.0):
+            m, sigma_c, h16_c, keep = visibility_compact(m0, sigma, h16, opts.early_stop_eps, opts.alpha_thre, opts.occ_mean_dev)
+        else:
+            m, sigma_c, h16_c, keep = m0, sigma, h16, None
+        if opts.keep_debug:
+            opts.debug.update(march0=m0, sigma0=sigma, keep=keep, march=m)
+        rgb_s = field_color_raw(fw, d, m.ray_indices, app_id, S_cap, m.total, h16_c)
+        dev = o.device
+        w = torch.empty(S_cap, device=dev)
+        out = torch.empty(R, 3, device=dev); acc = torch.empty(R, 1, device=dev); dnum = torch.empty(R, 1, device=dev)
+        mm = torch.empty(R, 2, device=dev)
+        call("lse_composite_fwd", P(m.starts), P(m.counts), R, P(m.t_starts), P(m.t_ends), P(sigma_c), P(rgb_s), P(w), P(out),
+             P(acc), P(dnum), P(mm), stream())
+        ctx.fw, ctx.opts, ctx.m, ctx.app_id = fw, opts, m, app_id
+        ctx.save_for_backward(o, d, sigma_c, h16_c, rgb_s)
+        ctx.params = params
+        nspr = m.counts
+        ctx.mark_non_differentiable(dnum, mm, nspr)
+        if opts.keep_debug:
+            opts.debug.update(weights=w, rgb_samples=rgb_s, sigma=sigma_c, h16=h16_c)
+        return out, acc, dnum, mm, nspr
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_acc, _gd, _gmm, _gn):
+        o, d, sigma, h16, rgb_s = ctx.saved_tensors
+        fw, opts, m = ctx.fw, ctx.opts, ctx.m
+        R = o.shape[0]
+        S_cap = m.S_cap
+        dev = o.device
+        if g_rgb is None:
+            g_rgb = torch.zeros(R, 3, device=dev)
+        d_sigma = torch.empty(S_cap, device=dev); d_rgb = torch.empty(S_cap, 3, device=dev)
+        call("lse_composite_bwd", P(m.starts), P(m.counts), R, P(m.t_starts), P(m.t_ends), P(sigma), P(rgb_s), P(g_rgb.contiguous()),
+             P(g_acc.contiguous()) if g_acc is not None else None, None, P(d_sigma), P(d_rgb), stream())
+        names = ("table", "W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "W5", "b5", "emb")
+        params = dict(zip(names, ctx.params))
+        bufs, ret = {}, {}
+        for k in names:
+            p = params[k]
+            if p is None or not p.requires_grad:
+                bufs[k], ret[k] = None, None
+            elif opts.accumulate_into_grad and p.is_leaf:
+                bufs[k], ret[k] = _acc_grad(p), None
+            else:
+                bufs[k] = torch.zeros_like(p); ret[k] = bufs[k]
+        for k in names[:11]:  # the kernels need every MLP gradient buffer; frozen weights get a scratch one
+            if bufs[k] is None and k != "table":
+                bufs[k] = torch.zeros_like(params[k])
+        if fw.emb_mode not in (0, 1):
+            bufs["emb"] = None
+        need_o, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_o = torch.zeros_like(o) if need_o else None
+        g_d = torch.zeros_like(d) if (need_d or need_o) else None
+        d_h16 = torch.empty(S_cap, 16, device=dev)
+        cp = fw.c_params(); cg = _grads_struct(fw, bufs)
+        call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
+             P(h16), P(d_rgb), P(d_h16), P(g_d) if need_d else None, stream())
+        call("lse_field_density_bwd", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts), P(m.t_ends),
+             S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(g_d) if need_d else None, stream())
+        return (g_o, g_d if need_d else None, None, None, None, None, *[ret[k] for k in names])
+
+
+def render_rays(fw: FieldWeights, opts: RenderOpts, origins, directions, jitter=None, app_id=None):
+    """-> (rgb [R,3], accumulation [R,1], depth_num [R,1], tmid_minmax [R,2], num_samples_per_ray [R])."""
+    params = (fw.table, fw.W1, fw.b1, fw.W2, fw.b2, fw.W3, fw.b3, fw.W4, fw.b4, fw.W5, fw.b5, fw.emb)
+    return _RenderRays.apply(origins, directions, jitter, app_id, fw, opts, *params)
+
+
+# =================================================================================================================
+# (f) epilogue + losses
+# =================================================================================================================
+MAP_MODES = {"co_map": 0, "evs_rgb": 1, "rgb_evs": 2}
+MAPPERS = {None: 0, "none": 0, "identity": 0, "gt": 1, "powpow": 2}
+ONE_DIM = {False: 0, None: 0, "learned": 1, "gt": 2}
+
+
+def epilogue_cfg(use_mapping, map_mode, rgb_mapper, evs_mapper, ev_one_dim, training, deblur, want_ev) -> _lib.LseEpilogueCfg:
+    c = _lib.LseEpilogueCfg()
+    c.use_mapping = int(bool(use_mapping)); c.map_mode = MAP_MODES[map_mode]
+    c.rgb_mapper = MAPPERS[rgb_mapper] if use_mapping or map_mode == "rgb_evs" else 0
+    c.evs_mapper = MAPPERS[evs_mapper] if map_mode == "co_map" else 0
+    c.ev_one_dim = ONE_DIM[ev_one_dim]
+    c.training = int(bool(training)); c.deblur = int(bool(deblur)); c.want_ev = int(bool(want_ev))
+    return c
+
+
+class _Epilogue(torch.autograd.Function):
+    """LSENeRFModel.get_outputs after compositing (lsenerf.py:334-375)."""
+
+    @staticmethod
+    def forward(ctx, rgb_lin, rgb_pow, evs_pow, to_one_w, cfg: _lib.LseEpilogueCfg):
+        x = _f32(rgb_lin, "rgb")
+        R = x.shape[0]
+        group = bool(cfg.deblur and cfg.training and R % 4 == 0)
+        n_out = R // 4 if group else R
+        C = 1 if cfg.ev_one_dim else 3
+        dev = x.device
+        rgb_final = torch.empty(n_out, 3, device=dev)
+        mapped = bool(cfg.use_mapping or cfg.map_mode == 2)
+        ev_branch = mapped and (cfg.map_mode == 1 or cfg.want_ev or not cfg.training)
+        ev_out = torch.empty(R, C, device=dev) if ev_branch else None
+        ev_lin = torch.empty(R, C, device=dev) if ev_branch else None
+        call("lse_epilogue_fwd", ctypes.byref(cfg), P(x), R, P(rgb_pow), P(evs_pow), P(to_one_w), P(rgb_final), P(ev_lin), P(ev_out),
+             stream())
+        ctx.cfg = cfg
+        ctx.save_for_backward(x, *(t if t is not None else x.new_empty(0) for t in (rgb_pow, evs_pow, to_one_w)))
+        ctx.has = (rgb_pow is not None, evs_pow is not None, to_one_w is not None, ev_branch)
+        if not ev_branch:
+            ev_out = x.new_empty(0); ev_lin = x.new_empty(0)
+        ctx.mark_non_differentiable(ev_lin)
+        return rgb_final, ev_out, ev_lin
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_ev, _g_lin):
+        x, rgb_pow, evs_pow, to_one_w = ctx.saved_tensors
+        h_rp, h_ep, h_w, ev_branch = ctx.has
+        R = x.shape[0]
+        d_x = torch.empty_like(x)
+        d_rp = torch.zeros_like(rgb_pow) if h_rp else None
+        d_ep = torch.zeros_like(evs_pow) if h_ep else None
+        d_w = torch.zeros_like(to_one_w) if h_w else None
+        call("lse_epilogue_bwd", ctypes.byref(ctx.cfg), P(x), R, P(rgb_pow) if h_rp else None, P(evs_pow) if h_ep else None,
+             P(to_one_w) if h_w else None, P(g_rgb.contiguous()) if g_rgb is not None else None,
+             P(g_ev.contiguous()) if (g_ev is not None and ev_branch) else None, P(d_x), P(d_rp), P(d_ep), P(d_w), stream())
+        return d_x, d_rp, d_ep, d_w, None
+
+
+def epilogue(rgb_lin, cfg, rgb_pow=None, evs_pow=None, to_one_w=None):
+    return _Epilogue.apply(rgb_lin, rgb_pow, evs_pow, to_one_w, cfg)
+
+
+class _Losses(torch.autograd.Function):
+    """get_loss_dict (lsenerf.py:392-439): rgb MSE + weighted event log-difference MSE, gradients in the same pass."""
+
+    @staticmethod
+    def forward(ctx, col_pred, col_target, prev, nxt, evs, evs_weight):
+        dev = (col_pred if col_pred is not None else prev).device
+        losses = torch.empty(2, device=dev)
+        n_col = col_pred.shape[0] if col_pred is not None else 0
+        n_evs = prev.shape[0] if prev is not None else 0
+        C = prev.shape[-1] if prev is not None else 1
+        d_col = torch.empty_like(col_pred) if col_pred is not None else None
+        d_prev = torch.empty_like(prev) if prev is not None else None
+        d_next = torch.empty_like(nxt) if nxt is not None else None
+        call("lse_loss_fwd", P(_f32(col_pred, "col_pred")) if col_pred is not None else None,
+             P(_f32(col_target, "col_target")) if col_target is not None else None, n_col,
+             P(_f32(prev, "prev")) if prev is not None else None, P(_f32(nxt, "next")) if nxt is not None else None,
+             P(_f32(evs.reshape(-1), "evs")) if evs is not None else None, n_evs, C, float(evs_weight), P(losses), P(d_col), P(d_prev),
+             P(d_next), stream())
+        ctx.save_for_backward(*(t if t is not None else losses.new_empty(0) for t in (d_col, d_prev, d_next)))
+        ctx.has = (d_col is not None, d_prev is not None)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_ev):
+        d_col, d_prev, d_next = ctx.saved_tensors
+        has_col, has_ev = ctx.has
+        return (d_col * g_rgb if has_col else None, None, d_prev * g_ev if has_ev else None, d_next * g_ev if has_ev else None,
+                None, None)
+
+
+def losses(col_pred, col_target, prev, nxt, evs, evs_weight=1.0):
+    return _Losses.apply(col_pred, col_target, prev, nxt, evs, evs_weight)
+
+
+# =================================================================================================================
+# occupancy grid update, Adam
+# =================================================================================================================
+def occ_update(occs: Tensor, cell_idx: Tensor, occ: Tensor, binaries_u8: Tensor, occ_mean_dev: Tensor, decay=0.95, occ_thre=0.01):
+    scratch = torch.zeros(1, dtype=torch.float64, device=occs.device)
+    call("lse_occ_update", P(occs), occs.numel(), P(cell_idx), P(occ), cell_idx.numel(), decay, occ_thre, P(binaries_u8.view(-1)),
+         P(occ_mean_dev), P(scratch), stream())
+
+
+def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    call("lse_adam_step", P(param), P(grad), P(exp_avg), P(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, step, grad_scale,
+         stream())

@@ -105,7 +105,15 @@ def render_samples(sd, cfg: Cfg, bundle: dict, ri, t0, t1, training: bool):
 
 
 def to_gray(img: Tensor) -> Tensor:
-    """utils.py:99-105 / ToGrayGT lsenerf.py:112-119."""
+    """utils.py:99-105, condition kept verbatim: a 2-D [n,3] tensor (every tensor on the per-ray path) is returned
+    UNCHANGED -- only >=3-D images are converted."""
+    if ((img.shape[-1] != 3) or (len(img.shape) == 2)) and (img.shape[-1] != 1):
+        return img
+    return img @ torch.tensor(GRAY).reshape(-1, 1).to(img)
+
+
+def gray_gt(img: Tensor) -> Tensor:
+    """ToGrayGT.forward, lsenerf.py:112-119."""
     return img @ torch.tensor(GRAY).reshape(-1, 1).to(img)
 
 
@@ -114,7 +122,7 @@ def rgb_to_one(sd, cfg: Cfg, x: Tensor) -> Tensor:
     if cfg.ev_one_dim == "learned":
         return torch.nn.functional.linear(x, torch.softmax(sd["rgb_to_one.weights"], dim=-1), None)
     if cfg.ev_one_dim == "gt":
-        return to_gray(x)
+        return gray_gt(x)
     return x
 
 
