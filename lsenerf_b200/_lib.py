@@ -99,8 +99,36 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_prof = None
+
+
+def profile_start():
+    """Bracket every ABI call with CUDA events on the launching stream (bench.py roofline; never on during timing)."""
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    """-> {abi_function: (calls, total_ms)}; synchronises."""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in rec:
+        c, t = out.get(name, (0, 0.0))
+        out[name] = (c + 1, t + e0.elapsed_time(e1))
+    return out
+
+
 def call(name: str, *args):
-    rc = getattr(lib(), name)(*args)
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args)
+        e1.record()
+        _prof.append((name, e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib().lse_last_error().decode()}")
 

@@ -96,20 +96,44 @@ class MultiCamManager(nn.Module):
     def get_train_rays_per_batch(self) -> int:
         return self.config.train_num_rays_per_batch
 
-    def next_train(self, step: int):
-        """lse_datamanager.py:337-372 -> ((col, prev, next) bundles, {"col_batch", "evs_batch"})."""
+    def sample_host_batches(self):
+        """The host half of next_train: uniform pixel draw + gather from the host image stacks (lse_pixel_sampler.py)."""
+        col = self.train_col_pixel_sampler.sample(self.col_store.batch()) if self.get_train_col_rays_per_batch() > 0 else None
+        evs = self.train_evs_pixel_sampler.sample(self.evs_store.batch()) if self.get_train_evs_rays_per_batch() > 0 else None
+        return col, evs
+
+    def to_device(self, batch, pinned: bool = False):
+        if batch is None:
+            return None
+        out = {}
+        for k, v in batch.items():
+            if isinstance(v, torch.Tensor):
+                if pinned and torch.cuda.is_available() and not v.is_pinned():
+                    v = v.pin_memory()
+                v = v.to(self.device, non_blocking=True)
+            out[k] = v
+        return out
+
+    @staticmethod
+    def batch_nbytes(batch) -> int:
+        return 0 if batch is None else sum(v.numel() * v.element_size() for v in batch.values() if isinstance(v, torch.Tensor))
+
+    def next_train(self, step: int, prefetched=None):
+        """lse_datamanager.py:337-372 -> ((col, prev, next) bundles, {"col_batch", "evs_batch"}).
+        prefetched: optional (col_batch, evs_batch) already resident on the device (bench: HBM-resident inputs)."""
         self.col_train_camera_optimizer.update_mode(step)
         self.evs_train_camera_optimizer.update_mode(step)
         col_bundle = col_batch = prev_bundle = next_bundle = evs_batch = None
+        if prefetched is None:
+            hc, he = self.sample_host_batches()
+            prefetched = (self.to_device(hc, True), self.to_device(he, True))
         if self.get_train_col_rays_per_batch() > 0:
-            col_batch = self.train_col_pixel_sampler.sample(self.col_store.batch())
-            col_batch = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in col_batch.items()}
+            col_batch = prefetched[0]
             col_bundle = self.col_ray_generator(col_batch["indices"])
             self.col_train_camera_optimizer.apply_to_raybundle(col_bundle)
             col_bundle = add_metadata(col_bundle, col_batch, max_app_id=self.num_embd)
         if self.get_train_evs_rays_per_batch() > 0:
-            evs_batch = self.train_evs_pixel_sampler.sample(self.evs_store.batch())
-            evs_batch = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in evs_batch.items()}
+            evs_batch = prefetched[1]
             prev_bundle, next_bundle = self.evs_ray_generator(evs_batch["indices"])
             self.evs_train_camera_optimizer.apply_to_raybundle(prev_bundle)
             self.evs_train_camera_optimizer.apply_to_raybundle(next_bundle)

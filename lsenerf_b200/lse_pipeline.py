@@ -28,9 +28,9 @@ class LSENeRFPipeline(nn.Module):
     def model(self):
         return self._model
 
-    def get_train_loss_dict(self, step: int):
+    def get_train_loss_dict(self, step: int, prefetched=None):
         """lse_pipeline.py:110-145 -> (out_dict, loss_dict, metrics_dict)."""
-        bundles, batch = self.datamanager.next_train(step)
+        bundles, batch = self.datamanager.next_train(step, prefetched)
         col_bundle, prev_bundle, next_bundle = bundles
         col_out = prev_out = next_out = None
         m = self._model
@@ -128,12 +128,12 @@ class FusedAdam:
                               self.step_count, grad_scale)
 
 
-def train_iteration(pipeline: LSENeRFPipeline, optim: FusedAdam, step: int, world_size: int = 1):
+def train_iteration(pipeline: LSENeRFPipeline, optim: FusedAdam, step: int, world_size: int = 1, prefetched=None):
     """nerfstudio Trainer.train_iteration for one rank: grid update callback, zero_grad, loss, backward,
     (gradient all-reduce over NCCL when world_size > 1), Adam."""
     pipeline.model.update_occupancy(step)
     optim.zero_grad()
-    _, loss_dict, metrics = pipeline.get_train_loss_dict(step)
+    _, loss_dict, metrics = pipeline.get_train_loss_dict(step, prefetched)
     loss = sum(loss_dict.values())
     loss.backward()
     if world_size > 1:

@@ -2,6 +2,16 @@
 
 Everything is seeded (default 96, scripts/train_evimo.sh:7).  Plain host-side torch/numpy; no kernels involved.  The
 same dictionary feeds the CUDA modules (``build_pipeline``) and -- in tests/bench only -- the CPU oracle.
+
+The scene is a ball of radius 0.5 on a thin ground slab inside the [-1,1]^3 box, seen from 64 control poses on a
+circle of radius 1.5.  Two target modes:
+  * ``targets="noise"``  : U(0,1) RGB and Poisson events (SURVEY 8d literally) -- used by the small parity tests;
+  * ``targets="analytic"``: RGB frames ray-traced from the analytic scene and event frames = quantised log-intensity
+    difference between consecutive event-camera poses, so that training is a consistent (learnable) problem.
+``bake_density=True`` additionally shapes the initial density to agree with the analytic occupancy (see
+``bake_density_prior``) so that the NGP occupancy update (every 16 steps) keeps a stationary, representative number of
+samples per ray from step 0 -- with a plain random init the first update fills the grid with fog and the work per step
+says nothing about steady-state training.
 """
 from __future__ import annotations
 
@@ -13,6 +23,10 @@ import numpy as np
 import torch
 
 from .interpolation_utils import matrix_to_tangent_vector
+
+GRAY = (0.2989, 0.5870, 0.1140)
+BALL_R = 0.5
+SLAB_Z = -0.03
 
 
 @dataclass
@@ -32,6 +46,10 @@ class SceneSpec:
     log2_hashmap_size: int = 19
     table_scale: float = 100.0       # hash table U(-1,1)*1e-3 scaled so densities vary
     e_thresh: float = 0.2
+    targets: str = "noise"           # "noise" | "analytic"
+    bake_density: bool = False
+    bake_level: int = 4              # hash level whose lattice carries the density prior (59^3 vertices < 2^19)
+    bake_gain: float = 4.5           # raw density = +-gain inside/outside -> sigma ~ 90 / 0.011
 
 
 def look_at_c2w(pos: np.ndarray) -> np.ndarray:
@@ -40,6 +58,53 @@ def look_at_c2w(pos: np.ndarray) -> np.ndarray:
     x = np.cross(up, z); x /= np.linalg.norm(x)
     y = np.cross(z, x)
     return np.concatenate([np.stack([x, y, z], axis=1), pos[:, None]], axis=1)
+
+
+def inside_solid(p: torch.Tensor) -> torch.Tensor:
+    """analytic geometry: ball of radius 0.5 at the origin + ground slab |x|,|y| <= 1, z in [SLAB_Z-0.03, SLAB_Z]."""
+    ball = (p * p).sum(-1) <= BALL_R * BALL_R
+    slab = (p[..., 0].abs() <= 1.0) & (p[..., 1].abs() <= 1.0) & (p[..., 2] <= SLAB_Z) & (p[..., 2] >= SLAB_Z - 0.03)
+    return ball | slab
+
+
+def trace_frame(c2w: torch.Tensor, H: int, W: int, intr) -> torch.Tensor:
+    """Linear radiance [H,W,3] of the analytic scene seen from one pinhole camera (same ray convention as
+    lse_cameras.py:381-395,491-493: direction (x, y, -1) in camera space, integer pixel coordinates)."""
+    fx, fy, cx, cy = intr
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    dcam = torch.stack([(xs - cx) / fx, -(ys - cy) / fy, -torch.ones_like(xs)], dim=-1)
+    d = dcam @ c2w[:3, :3].T
+    d = d / d.norm(dim=-1, keepdim=True)
+    o = c2w[:3, 3]
+    b = (d * o).sum(-1)
+    disc = b * b - ((o * o).sum() - BALL_R * BALL_R)
+    t_ball = torch.where(disc > 0, -b - torch.sqrt(disc.clamp(min=0)), torch.full_like(b, float("inf")))
+    t_ball = torch.where(t_ball > 0, t_ball, torch.full_like(b, float("inf")))
+    t_slab = torch.where(d[..., 2] < 0, (SLAB_Z - o[2]) / d[..., 2].clamp(max=-1e-9), torch.full_like(b, float("inf")))
+    ps = o + t_slab.clamp(max=1e6)[..., None] * d
+    t_slab = torch.where((ps[..., 0].abs() <= 1.0) & (ps[..., 1].abs() <= 1.0) & (t_slab > 0), t_slab, torch.full_like(b, float("inf")))
+    img = torch.zeros(H, W, 3)
+    hit_b = t_ball < t_slab
+    n = (o + t_ball.clamp(max=1e6)[..., None] * d) / BALL_R
+    img[hit_b] = (0.5 + 0.4 * n)[hit_b]
+    hit_s = (~hit_b) & torch.isfinite(t_slab)
+    checker = ((torch.floor(ps[..., 0] * 4) + torch.floor(ps[..., 1] * 4)) % 2 == 0).float()
+    img[hit_s] = (0.25 + 0.45 * checker)[hit_s][:, None].expand(-1, 3)
+    return img
+
+
+def evs_c2w_from_spline(scene: dict) -> torch.Tensor:
+    """Initial event-camera poses M_rgb(t) @ dM on the host (scipy slerp of the control poses); stored as the event
+    cameras' camera_to_worlds, which the 'ns' optimizer then refines through pose_adjustment."""
+    from scipy.spatial.transform import Rotation, Slerp
+    ts = scene["ctrl_ts"].numpy().astype(np.float64)
+    c2w = scene["col_c2w"].numpy().astype(np.float64)
+    q = scene["evs_times"].reshape(-1).numpy().astype(np.float64)
+    R = Slerp(ts, Rotation.from_matrix(c2w[:, :3, :3]))(q).as_matrix()
+    t = np.stack([np.interp(q, ts, c2w[:, i, 3]) for i in range(3)], axis=1)
+    M = np.concatenate([R, t[:, :, None]], axis=2)
+    M4 = np.concatenate([M, np.tile(np.array([[[0, 0, 0, 1.0]]]), (len(M), 1, 1))], axis=1)
+    return torch.from_numpy((M4 @ scene["dM"].numpy().astype(np.float64))[:, :3, :4].astype(np.float32))
 
 
 def make_scene(spec: SceneSpec = SceneSpec(), images: bool = True) -> dict:
@@ -61,7 +126,7 @@ def make_scene(spec: SceneSpec = SceneSpec(), images: bool = True) -> dict:
     ctrl_tangents = torch.stack([matrix_to_tangent_vector(M) for M in c2ws])
     dM = torch.eye(4)
     dM[0, 3] = spec.baseline
-    # ---- occupancy: ball of radius 0.5 + thin ground slab at level 0, replicated into the coarser levels ---------
+    # ---- occupancy: cells whose centre lies in the ball / slab, replicated into the coarser levels ---------------
     res, L = spec.grid_res, spec.grid_levels
     binaries = torch.zeros(L, res, res, res, dtype=torch.bool)
     lin = (torch.arange(res, dtype=torch.float32) + 0.5) / res
@@ -69,12 +134,11 @@ def make_scene(spec: SceneSpec = SceneSpec(), images: bool = True) -> dict:
         half = 2.0**l
         ax = -half + lin * 2 * half
         X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
-        ball = (X * X + Y * Y + Z * Z) <= 0.25
-        slab = (Z.abs() <= max(0.03, half / res)) & (X.abs() <= 1.0) & (Y.abs() <= 1.0) & (Z <= 0) if l == 0 else \
-               ((Z + 0.03).abs() <= half / res) & (X.abs() <= 1.0) & (Y.abs() <= 1.0)
+        cell = 2 * half / res
+        ball = (X * X + Y * Y + Z * Z) <= (BALL_R + 0.5 * cell) ** 2
+        slab = (X.abs() <= 1.0 + cell) & (Y.abs() <= 1.0 + cell) & ((Z - (SLAB_Z - 0.015)).abs() <= 0.015 + 0.5 * cell)
         binaries[l] = ball | slab
     occs = 0.02 * binaries.flatten().float()
-    # ---- event camera poses (n+1) from the initial spline, stored (evs_cam_optimizer.optim_type == "ns") -------------
     n_ev = spec.n_evs_frames
     evs_times = torch.linspace(0.0, spec.t_end, n_ev + 1)
     scene = dict(spec=spec, ctrl_ts=ctrl_ts, ctrl_tangents0=ctrl_tangents, dM=dM, exp_t=spec.exp_t, binaries=binaries, occs=occs,
@@ -87,19 +151,68 @@ def make_scene(spec: SceneSpec = SceneSpec(), images: bool = True) -> dict:
     scene["evs_image_idx"] = torch.arange(n_ev)
     scene["col_appearance_id"] = torch.clamp(torch.round(ctrl_ts / (spec.t_end / n_ev)).long(), 0, n_ev - 1)
     scene["evs_appearance_id"] = torch.arange(n_ev)
+    scene["evs_c2w0"] = evs_c2w_from_spline(scene)
     if images:
         H, W = spec.col_hw
-        scene["col_images"] = torch.rand(K, H, W, 3, generator=g)
-        H, W = spec.evs_hw
-        cnt = torch.poisson(torch.full((n_ev, H, W, 1), 0.5), generator=g)
-        sign = torch.where(torch.rand(n_ev, H, W, 1, generator=g) < 0.5, -1.0, 1.0)
-        scene["evs_images"] = cnt * sign * spec.e_thresh       # EventFrameDataset: evs * e_thresh (lse_dataset.py:86-88)
+        He, We = spec.evs_hw
+        if spec.targets == "analytic":
+            scene["col_images"] = torch.stack([trace_frame(scene["col_c2w"][i], H, W, scene["col_intr"]) for i in range(K)])
+            gw = torch.tensor(GRAY)
+            prev = torch.log(trace_frame(scene["evs_c2w0"][0], He, We, scene["evs_intr"]) @ gw + 1e-2)
+            frames = []
+            for i in range(n_ev):
+                cur = torch.log(trace_frame(scene["evs_c2w0"][i + 1], He, We, scene["evs_intr"]) @ gw + 1e-2)
+                frames.append(torch.trunc((cur - prev) / spec.e_thresh) * spec.e_thresh)
+                prev = cur
+            scene["evs_images"] = torch.stack(frames)[..., None].contiguous()
+        else:
+            scene["col_images"] = torch.rand(K, H, W, 3, generator=g)
+            cnt = torch.poisson(torch.full((n_ev, He, We, 1), 0.5), generator=g)
+            sign = torch.where(torch.rand(n_ev, He, We, 1, generator=g) < 0.5, -1.0, 1.0)
+            scene["evs_images"] = cnt * sign * spec.e_thresh   # EventFrameDataset: evs * e_thresh (lse_dataset.py:86-88)
     return scene
+
+
+def _vertex_rows(n: int, log2_T: int):
+    """table row (within one level) of every lattice vertex (x,y,z) in [0,n]^3, same hash as the kernels
+    (csrc/math_field.cuh: (x ^ y*2654435761 ^ z*805459861) mod 2^log2_T, evaluated here in int64)."""
+    r = torch.arange(n + 1, dtype=torch.int64)
+    X, Y, Z = torch.meshgrid(r, r, r, indexing="ij")
+    h = (X ^ (Y * 2654435761) ^ (Z * 805459861)) % (1 << log2_T)
+    return h.reshape(-1), torch.stack([X, Y, Z], dim=-1).reshape(-1, 3)
+
+
+def _bake(model, spec: SceneSpec) -> None:
+    """Shape the INITIAL density to the analytic geometry: feature 0 of hash level ``bake_level`` is set to +1 on lattice
+    vertices inside the solid and -1 outside, hidden units 0/1 of the base MLP read +-that feature and the density row of
+    the output layer reads only those two units, giving raw density ~ +-bake_gain.  Everything else keeps its random
+    init, and every value remains an ordinary trainable parameter."""
+    grid = model.field.mlp_base_grid
+    lvl = spec.bake_level
+    n = int(grid.scalings[lvl].item())
+    assert (n + 1) ** 3 < (1 << grid.log2_hashmap_size), "bake level lattice must fit the hash table"
+    rows, verts = _vertex_rows(n, grid.log2_hashmap_size)
+    # lattice vertex -> normalised x = v/n -> contracted p = 4x-2 -> world (inverse L-inf contraction, identity inside)
+    p = 4.0 * verts.float() / n - 2.0
+    m = p.abs().amax(dim=-1, keepdim=True)
+    world = torch.where(m <= 1, p, p / (m * (2 - m)).clamp(min=1e-6))
+    ins = inside_solid(world)
+    base = lvl << grid.log2_hashmap_size
+    dev = grid.hash_table.device
+    with torch.no_grad():
+        t = grid.hash_table
+        t[base + rows[~ins].to(dev), 0] = -1.0
+        t[base + rows[ins].to(dev), 0] = 1.0       # inside wins on hash collisions
+        W1, b1 = model.field.mlp_base_mlp.layers[0].weight, model.field.mlp_base_mlp.layers[0].bias
+        W2, b2 = model.field.mlp_base_mlp.layers[1].weight, model.field.mlp_base_mlp.layers[1].bias
+        W1[0:2].zero_(); b1[0:2].zero_()
+        W1[0, 2 * lvl] = 1.0; W1[1, 2 * lvl] = -1.0
+        W2[0].zero_(); W2[0, 0] = spec.bake_gain; W2[0, 1] = -spec.bake_gain; b2[0] = 0.0
 
 
 def init_model_state(model, scene: dict, seed: Optional[int] = None) -> None:
     """Seeded parameter init of SURVEY 8d on a constructed LSENeRFModel (CPU or CUDA): hash table U(-1,1)*1e-3*scale,
-    nn.Linear default init, embedding N(0,1); occupancy buffers from the scene."""
+    nn.Linear default init, embedding N(0,1); occupancy buffers from the scene; optional density prior."""
     spec: SceneSpec = scene["spec"]
     g = torch.Generator().manual_seed(spec.seed if seed is None else seed)
     with torch.no_grad():
@@ -114,20 +227,8 @@ def init_model_state(model, scene: dict, seed: Optional[int] = None) -> None:
         model.occupancy_grid.binaries.copy_(scene["binaries"].to(t.device))
         model.occupancy_grid.occs.copy_(scene["occs"].to(t.device))
         model.occupancy_grid.refresh_occ_mean()
-
-
-def evs_c2w_from_spline(scene: dict) -> torch.Tensor:
-    """Initial event-camera poses M_rgb(t) @ dM on the host (numpy slerp of the control poses); stored as the event
-    cameras' camera_to_worlds, which the 'ns' optimizer then refines through pose_adjustment."""
-    from scipy.spatial.transform import Rotation, Slerp
-    ts = scene["ctrl_ts"].numpy().astype(np.float64)
-    c2w = scene["col_c2w"].numpy().astype(np.float64)
-    q = scene["evs_times"].reshape(-1).numpy().astype(np.float64)
-    R = Slerp(ts, Rotation.from_matrix(c2w[:, :3, :3]))(q).as_matrix()
-    t = np.stack([np.interp(q, ts, c2w[:, i, 3]) for i in range(3)], axis=1)
-    M = np.concatenate([R, t[:, :, None]], axis=2)
-    M4 = np.concatenate([M, np.tile(np.array([[[0, 0, 0, 1.0]]]), (len(M), 1, 1))], axis=1)
-    return torch.from_numpy((M4 @ scene["dM"].numpy().astype(np.float64))[:, :3, :4].astype(np.float32))
+    if spec.bake_density:
+        _bake(model, spec)
 
 
 def build_pipeline(scene: dict, experiment: str = "lsenerf", num_rays: int = 8192, rgb_frac: Optional[float] = 0.5,
@@ -146,10 +247,11 @@ def build_pipeline(scene: dict, experiment: str = "lsenerf", num_rays: int = 819
     if rgb_frac is not None:
         dm_cfg.rgb_frac = rgb_frac
         dm_cfg.update_num_batch_rays()
+    dm_cfg.col_cam_optimizer.exp_t = scene["exp_t"]
     fx, fy, cx, cy = scene["col_intr"]
     col_cams = EdCameras(scene["col_c2w"].clone(), fx, fy, cx, cy, spec.col_hw[1], spec.col_hw[0], times=scene["col_times"])
     fx, fy, cx, cy = scene["evs_intr"]
-    evs_cams = EdCameras(evs_c2w_from_spline(scene), fx, fy, cx, cy, spec.evs_hw[1], spec.evs_hw[0], times=scene["evs_times"])
+    evs_cams = EdCameras(scene["evs_c2w0"].clone(), fx, fy, cx, cy, spec.evs_hw[1], spec.evs_hw[0], times=scene["evs_times"])
 
     def store(img, idx, app, thr=None):
         if pin and torch.cuda.is_available():
