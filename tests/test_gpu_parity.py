@@ -309,7 +309,11 @@ def test_train_step_parity(dev, variant):
         if gref is None:
             assert gcu.abs().max().item() == 0.0, k
             continue
-        assert rel_err(gcu, gref) < 3e-3, (k, rel_err(gcu, gref))
+        # Field / mapper / embedding gradients: 3e-3 end to end (each kernel's own backward is held to 1e-3 above).  Camera
+        # gradients are sums over ~1e5 per-sample position gradients of mixed sign (the hash grid's d/dx is piecewise
+        # constant), so both fp32 sides carry cancellation noise: 2e-2 end to end, 1e-3 per kernel in the unit tests.
+        tol = 2e-2 if "cam_opt" in k else 3e-3
+        assert rel_err(gcu, gref) < tol, (k, rel_err(gcu, gref))
         checked += 1
     assert checked >= 11
     if "cam_opt" in variant:

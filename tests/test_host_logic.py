@@ -1,0 +1,81 @@
+"""CPU: host-side mirrors of the reference's data logic (no kernels)."""
+import torch
+
+from lsenerf_b200 import utils
+from lsenerf_b200.data_components import find_closest_idxs
+from lsenerf_b200.lse_datamanager import MultiCamManagerConfig
+from lsenerf_b200.lse_pixel_sampler import EvPixelSampler
+from lsenerf_b200.lsenerf import LSENeRFModelConfig
+from lsenerf_b200.ns_camera_optimizer import CameraOptimizerConfig
+from oracle import data as OD
+
+
+def test_ray_budget_split():
+    """lse_datamanager.py:135-144 (numbers from SURVEY 5.1)."""
+    c = MultiCamManagerConfig(train_num_rays_per_batch=3512, rgb_frac=0.66)
+    assert (c.train_num_evs_rays_per_batch, c.train_num_col_rays_per_batch) == (597, 2318)
+    c = MultiCamManagerConfig(train_num_rays_per_batch=3512, rgb_frac=0.66, rgb_loss_mode="deblur")
+    assert c.train_num_col_rays_per_batch == 579
+    c = MultiCamManagerConfig(train_num_rays_per_batch=8192, rgb_frac=0.5, rgb_loss_mode="DEBLUR")
+    assert (c.train_num_evs_rays_per_batch, c.train_num_col_rays_per_batch) == (2048, 1024)
+    c = MultiCamManagerConfig(train_num_rays_per_batch=3512, rgb_frac=1.0)
+    assert (c.train_num_evs_rays_per_batch, c.train_num_col_rays_per_batch) == (0, 3512)
+    assert OD.ray_budget(8192, 0.5, True) == (2048, 1024) and OD.ray_budget(3512, 0.66, False) == (597, 2318)
+
+
+def test_pixel_sampler_bit_exact_against_oracle():
+    g1, g2 = torch.Generator().manual_seed(7), torch.Generator().manual_seed(7)
+    N, H, W = 5, 48, 64
+    imgs = torch.rand(N, H, W, 3)
+    batch = {"image": imgs, "image_idx": torch.arange(N) + 10, "appearance_id": torch.arange(N) * 2, "e_thresh": torch.rand(N)}
+    out = EvPixelSampler(300, generator=g1).sample(batch)
+    idx = OD.sample_pixels(torch.rand(300, 3, generator=g2), N, H, W)
+    ref = OD.collate(imgs, batch["image_idx"], batch["appearance_id"], batch["e_thresh"], idx)
+    for k in ("image", "indices", "appearance_id", "e_thresh"):
+        assert torch.equal(out[k], ref[k]), k
+    assert int(out["indices"][:, 0].min()) >= 10 and int(idx[:, 1].max()) < H and int(idx[:, 2].max()) < W
+
+
+def test_appearance_id_and_datashape():
+    app = torch.tensor([[0], [5], [9]])
+    ref = torch.zeros(12, 1)
+    out = utils.fix_appearance_id(app, ref, max_app_id=10)
+    assert out.reshape(3, 4).tolist() == [[0, 0, 0, 1], [3, 4, 5, 6], [7, 8, 9, 9]]          # id + {-2,-1,0,1}, clipped, pixel-major
+    assert torch.equal(out, OD.fix_appearance_id(app, 12, 10))
+    seq = utils.fix_datashape(torch.tensor([[1], [2], [3]]), ref)
+    assert seq.reshape(-1).tolist() == [1, 2, 3] * 4                                        # sequence-major (quirk B.10)
+    assert utils.fix_datashape(app, torch.zeros(3, 1)) is app
+
+
+def test_find_closest_idxs():
+    ref = torch.tensor([0.0, 10.0, 20.0, 30.0])
+    q = torch.tensor([-5.0, 4.9, 5.1, 15.0, 29.0, 100.0])
+    assert find_closest_idxs(ref, q).tolist() == [0, 0, 1, 2, 3, 3]
+    assert torch.equal(find_closest_idxs(ref, q), OD.find_closest_idxs(ref, q))
+
+
+def test_to_gray_quirk():
+    """utils.py:99-105: 2-D [n,3] tensors are returned unchanged, images are converted."""
+    x = torch.rand(7, 3)
+    assert utils.to_gray(x) is x
+    img = torch.rand(4, 5, 3)
+    assert utils.to_gray(img).shape == (4, 5, 1)
+
+
+def test_config_normalisation():
+    c = LSENeRFModelConfig(evs_mapping_method="None", map_mode="None", ev_one_dim="False", rgb_loss_type="None")
+    assert c.evs_mapping_method is None and c.map_mode == "evs_rgb" and c.ev_one_dim is False and c.rgb_loss_type == "linspace"
+    assert LSENeRFModelConfig(ev_one_dim="true").ev_one_dim == "learned"
+    o = CameraOptimizerConfig(mode="off", scheme="delayed")
+    assert o.scheme == "active" and o.delay_cnt == 1999999999
+
+
+def test_synthetic_scene_shapes():
+    from lsenerf_b200 import synthetic as syn
+    spec = syn.SceneSpec(col_hw=(24, 32), evs_hw=(24, 32), n_ctrl=6, n_evs_frames=10, grid_res=16, targets="analytic", col_f=30, evs_f=31)
+    sc = syn.make_scene(spec)
+    assert sc["col_images"].shape == (6, 24, 32, 3) and sc["evs_images"].shape == (10, 24, 32, 1)
+    assert sc["evs_c2w0"].shape == (11, 3, 4) and sc["binaries"].shape == (4, 16, 16, 16)
+    assert float(sc["col_images"].max()) <= 1.0 and float(sc["col_images"].max()) > 0.3
+    q = sc["evs_images"] / spec.e_thresh
+    assert torch.allclose(q, torch.round(q), atol=1e-4)                                      # integer event counts x threshold
