@@ -1,0 +1,149 @@
+// tc_common.cuh -- tcgen05 / TMEM / mbarrier primitives (inline PTX, sm_100a) and the 3xTF32 operand staging used by the
+// LSEField MLP kernels.
+//
+// Operand layout in shared memory (UMMA canonical K-major, no swizzle): a [rows x K] fp32 matrix is stored as K/4
+// "panels"; panel kc holds, for every row, the 16 bytes of columns 4kc..4kc+3, rows contiguous at 16-byte stride:
+//        byte offset(row, k) = (k/4) * rows*16 + row*16 + (k%4)*4
+// i.e. 8-row core matrices of 128 contiguous bytes, SBO (8-row group stride) = 128 B, LBO (next 16-byte K chunk) =
+// rows*16 B.  One tcgen05.mma.kind::tf32 consumes K = 8 (two panels).  A thread that owns row r writes one float4 per
+// panel; a warp's 32 rows are 512 contiguous bytes, so the staging stores are conflict-free STS.128.
+//
+// fp32 parity: the tensor core reads TF32 (10 explicit mantissa bits).  Every operand x is split into hi = x with the low
+// 13 mantissa bits cleared (exactly representable in TF32) and lo = x - hi (exact in fp32, |lo| < 2^-10 |x|), and each
+// product is issued as three MMAs  Ahi*Bhi + Alo*Bhi + Ahi*Blo  accumulated in fp32 in TMEM; the dropped lo*lo term and
+// the TF32 rounding of lo are O(2^-21) relative.
+#pragma once
+#include "common.cuh"
+
+namespace lse {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// bounded spin: a lost arrival traps (reported as a launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+    __syncwarp();   // reconverge before the .sync.aligned tcgen05 instructions that follow
+}
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// named barrier over `n` threads (one warpgroup); ids 1.. (0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// ---- TMEM allocation (one full warp executes these) -------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- descriptors ------------------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor kind::tf32: D = F32 (bits 4-5 = 1), A = B = TF32 (format 2 at bits 7-9 / 10-12), both K-major,
+// N>>3 at bits 17-22, M>>4 at bits 24-28
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all previously issued MMAs of this thread arrives on the mbarrier (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers: 32 lanes x 32 bit, 16 consecutive columns; thread t of warp w reads lane 32*(w%4)+t ----------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- 3xTF32 split and operand staging ---------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo)
+{
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
+// write 4 consecutive K values of row `row` (panel kc) into the hi / lo operand buffers of a `rows`-row matrix
+__device__ __forceinline__ void stage4(float *hi_buf, float *lo_buf, int rows, int kc, int row, float a, float b, float c, float d)
+{
+    float4 h, l;
+    split_tf32(a, h.x, l.x); split_tf32(b, h.y, l.y); split_tf32(c, h.z, l.z); split_tf32(d, h.w, l.w);
+    const int off = (kc * rows + row) * 4;
+    *reinterpret_cast<float4 *>(hi_buf + off) = h;
+    *reinterpret_cast<float4 *>(lo_buf + off) = l;
+}
+
+// cooperative: global row-major W[n_real][k_real] -> panel layout [K/4][N][4] (hi and lo), zero padded to N x K
+__device__ __forceinline__ void stage_weights(float *hi_buf, float *lo_buf, const float *__restrict__ W, int n_real, int k_real,
+                                              int N, int K, int tid, int nthreads)
+{
+    for (int i = tid; i < N * K; i += nthreads) {
+        const int n = i / K, k = i % K;
+        const float w = (n < n_real && k < k_real) ? W[n * k_real + k] : 0.0f;
+        float h, l;
+        split_tf32(w, h, l);
+        const int off = ((k >> 2) * N + n) * 4 + (k & 3);
+        hi_buf[off] = h; lo_buf[off] = l;
+    }
+}
+
+// issue the 3 x (K/8) MMAs of one dense layer:  D[128 x N] = A[128 x K] * W[N x K]^T   (A rows = 128)
+__device__ __forceinline__ void issue_layer(uint32_t d_tmem, const float *a_hi, const float *a_lo, const float *w_hi,
+                                            const float *w_lo, int N, int K)
+{
+    const uint32_t idesc = idesc_tf32(128, N);
+    const uint32_t a_lbo = 128 * 16, w_lbo = (uint32_t)N * 16;
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint32_t ao = ks * 2 * a_lbo, wo = ks * 2 * w_lbo;
+        const uint64_t ah = smem_desc(smem_u32(a_hi) + ao, a_lbo, 128), al = smem_desc(smem_u32(a_lo) + ao, a_lbo, 128);
+        const uint64_t wh = smem_desc(smem_u32(w_hi) + wo, w_lbo, 128), wl = smem_desc(smem_u32(w_lo) + wo, w_lbo, 128);
+        mma_tf32(d_tmem, ah, wh, idesc, acc); acc = 1;
+        mma_tf32(d_tmem, al, wh, idesc, 1);
+        mma_tf32(d_tmem, ah, wl, idesc, 1);
+    }
+}
+
+}  // namespace tc
+}  // namespace lse

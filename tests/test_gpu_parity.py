@@ -430,3 +430,34 @@ def test_full_size_properties(dev):
     enc.backward(gout)
     per_level = table.grad.view(16, -1, 2).sum(dim=1).reshape(-1)
     assert torch.allclose(per_level, gout.sum(dim=0), rtol=2e-3, atol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------- tensor-core MLPs
+@pytest.mark.parametrize("S", [1, 127, 128, 129, 5000, 70001])
+def test_tensor_core_forward_matches_fp32(dev, S):
+    """tcgen05 3xTF32 density / colour kernels against the fp32 CUDA-core kernels and the oracle (ragged tile counts)."""
+    import dataclasses
+    from lsenerf_b200 import ops
+    from oracle import field as OF
+    scene, p = _pipeline(dev, emb=True)
+    p.train()
+    fw = p._model.field.weights()
+    fw_tc = dataclasses.replace(fw, use_tensor_cores=True)
+    g = torch.Generator().manual_seed(S)
+    o = (torch.rand(S, 3, generator=g) * 2.4 - 1.2).to(dev)
+    d = torch.nn.functional.normalize(torch.randn(S, 3, generator=g), dim=-1).to(dev)
+    t0 = (torch.rand(S, generator=g) * 0.5).to(dev); t1 = t0 + 0.01
+    app = torch.randint(0, scene["num_emb"], (S,), generator=g, dtype=torch.int32).to(dev)
+    sig_a, h_a = ops.field_density_raw(fw, o, d, None, t0, t1, S, None)
+    sig_b, h_b = ops.field_density_raw(fw_tc, o, d, None, t0, t1, S, None)
+    assert rel_err(h_b, h_a) < 2e-5 and rel_err(sig_b, sig_a) < 2e-5
+    rgb_a = ops.field_color_raw(fw, d, None, app, S, None, h_a)
+    rgb_b = ops.field_color_raw(fw_tc, d, None, app, S, None, h_a)
+    assert rel_err(rgb_b, rgb_a) < 2e-5
+    sd, cfg = oracle_state(p), oracle_cfg(p)
+    pos = o.cpu() + d.cpu() * ((t0.cpu() + t1.cpu()) / 2)[:, None]
+    with torch.no_grad():
+        dens, geo = OF.density(sd, pos, cfg.scalings, cfg.log2_hashmap_size)
+        emb = OF.appearance_embedding(sd, app.cpu().long(), S, "evs_emb", True)
+        rgb_ref = OF.color(sd, d.cpu(), geo, emb)
+    assert rel_err(sig_b, dens[:, 0]) < TOL_OUT and rel_err(h_b[:, 1:], geo) < TOL_OUT and rel_err(rgb_b, rgb_ref) < TOL_OUT
