@@ -72,19 +72,24 @@ int lse_pose_delta_bwd(const float *pose_adjustment, int64_t n_cams, const int64
  * (b) occupancy-grid marching  (3P nerfacc.grid.traverse_grids, lse_nerf/lse_grid_estimator.py:83-106)
  * ------------------------------------------------------------------------------------------------- */
 
+/* Pack the byte occupancy tensor (nerfacc `binaries` [levels,res,res,res] bool) into 1 bit per cell (occ_bits,
+ * levels*res^3/32 words) plus an any-occupied mip over 8^3 superblocks (occ_mip, ceil(levels*(res/8)^3/32) words) that
+ * the marching kernels keep in shared memory.  res % 32 == 0. */
+int lse_occ_pack(const uint8_t *binaries, int levels, int res, uint32_t *occ_bits, uint32_t *occ_mip, lse_stream_t stream);
+
 /* near = near_plane (+ jitter[r]*step_size when jitter != NULL: the stratified draw of :91-92).
  * pass 1: counts[r] = number of samples of ray r. */
-int lse_march_count(const float *rays_o, const float *rays_d, int64_t n_rays, const uint8_t *binaries,
-                    const float *aabbs, int levels, int res, float near_plane, float far_plane,
+int lse_march_count(const float *rays_o, const float *rays_d, int64_t n_rays, const uint32_t *occ_bits,
+                    const uint32_t *occ_mip, const float *aabbs, int levels, int res, float near_plane, float far_plane,
                     const float *jitter, float step_size, float cone_angle, int32_t *counts, lse_stream_t stream);
 /* exclusive scan of counts -> starts [n] ; total -> total_dev [1] (int32).  Also used for compaction. */
 int lse_scan_counts(const int32_t *counts, int64_t n, int32_t *starts, int32_t *total_dev, lse_stream_t stream);
 /* pass 2: writes ray_indices/t_starts/t_ends at starts[r]; rays whose samples would exceed S_cap are truncated
  * (overflow_dev [1] int32 set to 1). */
-int lse_march_fill(const float *rays_o, const float *rays_d, int64_t n_rays, const uint8_t *binaries,
-                   const float *aabbs, int levels, int res, float near_plane, float far_plane, const float *jitter,
-                   float step_size, float cone_angle, const int32_t *starts, int64_t S_cap, int32_t *ray_indices,
-                   float *t_starts, float *t_ends, int32_t *overflow_dev, lse_stream_t stream);
+int lse_march_fill(const float *rays_o, const float *rays_d, int64_t n_rays, const uint32_t *occ_bits,
+                   const uint32_t *occ_mip, const float *aabbs, int levels, int res, float near_plane, float far_plane,
+                   const float *jitter, float step_size, float cone_angle, const int32_t *starts, int64_t S_cap,
+                   int32_t *ray_indices, float *t_starts, float *t_ends, int32_t *overflow_dev, lse_stream_t stream);
 
 /* 3P nerfacc.render_visibility_from_density (lse_nerf/lse_grid_estimator.py:109-127,139-143):
  * per ray, T = exp(-exclusive_sum(sigma*dt)), alpha = 1-exp(-sigma*dt), keep = T >= early_stop_eps &&

@@ -25,39 +25,67 @@ struct FillEmit {
     }
 };
 
-__global__ void march_count_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n_rays,
-                                   const uint8_t *__restrict__ binaries, const float *__restrict__ aabbs, int levels, int res,
-                                   float near_plane, float far_plane, const float *__restrict__ jitter, float step_size,
-                                   float cone_angle, int32_t *__restrict__ counts)
+// pack binaries (bytes) -> 1 bit per cell + any-occupied mip over 8^3 superblocks (mip must be zeroed beforehand)
+__global__ void occ_pack_kernel(const uint8_t *__restrict__ binaries, int levels, int res, uint32_t *__restrict__ bits,
+                                uint32_t *__restrict__ mip)
 {
-    __shared__ float s_aabb[6 * kMaxLevels];
-    for (int i = threadIdx.x; i < 6 * levels; i += blockDim.x) s_aabb[i] = aabbs[i];
-    __syncthreads();
-    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rays; r += (int64_t)gridDim.x * blockDim.x) {
-        float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
-        float d[3] = {rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]};
-        float nearp = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
-        counts[r] = march_ray(o, d, binaries, s_aabb, levels, res, nearp, far_plane, step_size, cone_angle, CountEmit());
+    const int64_t n_words = ((int64_t)levels * res * res * res) >> 5;
+    const int sb = res >> 3;
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(binaries + (w << 5));
+        uint4 a = src[0], b = src[1];
+        uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((v[q] >> (8 * k)) & 0xFFu) word |= 1u << (4 * q + k);
+        bits[w] = word;
+        if (word) {
+            // the 32 cells of a word share x, y and z/32; they span 4 superblocks along z
+            const int64_t cell = w << 5;
+            const int z0 = (int)(cell % res), y = (int)((cell / res) % res), x = (int)((cell / ((int64_t)res * res)) % res);
+            const int level = (int)(cell / ((int64_t)res * res * res));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if ((word >> (8 * q)) & 0xFFu) {
+                    const int m = ((level * sb + (x >> 3)) * sb + (y >> 3)) * sb + ((z0 + 8 * q) >> 3);
+                    atomicOr(mip + (m >> 5), 1u << (m & 31));
+                }
+            }
+        }
     }
 }
 
-__global__ void march_fill_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n_rays,
-                                  const uint8_t *__restrict__ binaries, const float *__restrict__ aabbs, int levels, int res,
-                                  float near_plane, float far_plane, const float *__restrict__ jitter, float step_size,
-                                  float cone_angle, const int32_t *__restrict__ starts, int64_t S_cap,
-                                  int32_t *__restrict__ ray_indices, float *__restrict__ t_starts, float *__restrict__ t_ends,
-                                  int32_t *__restrict__ overflow)
+constexpr int kMaxMipWords = 1024;  // 4 levels x 16^3 superblocks = 16384 bits = 512 words (res 128); 8 levels fit too
+
+template <bool FILL>
+__global__ void march_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n_rays,
+                             const uint32_t *__restrict__ bits, const uint32_t *__restrict__ mip, int mip_words,
+                             const float *__restrict__ aabbs, int levels, int res, float near_plane, float far_plane,
+                             const float *__restrict__ jitter, float step_size, float cone_angle,
+                             int32_t *__restrict__ counts, const int32_t *__restrict__ starts, int64_t S_cap,
+                             int32_t *__restrict__ ray_indices, float *__restrict__ t_starts, float *__restrict__ t_ends,
+                             int32_t *__restrict__ overflow)
 {
     __shared__ float s_aabb[6 * kMaxLevels];
+    __shared__ uint32_t s_mip[kMaxMipWords];
     for (int i = threadIdx.x; i < 6 * levels; i += blockDim.x) s_aabb[i] = aabbs[i];
+    for (int i = threadIdx.x; i < mip_words; i += blockDim.x) s_mip[i] = mip[i];
     __syncthreads();
+    const OccBits occ{bits, s_mip, res};
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rays; r += (int64_t)gridDim.x * blockDim.x) {
         float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
         float d[3] = {rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]};
         float nearp = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
-        FillEmit e{t_starts, t_ends, ray_indices, (int32_t)r, (int64_t)starts[r], S_cap, 0};
-        int n = march_ray(o, d, binaries, s_aabb, levels, res, nearp, far_plane, step_size, cone_angle, e);
-        if ((int64_t)starts[r] + n > S_cap && overflow) *overflow = 1;
+        if (!FILL) {
+            counts[r] = march_ray(o, d, occ, s_aabb, levels, res, nearp, far_plane, step_size, cone_angle, CountEmit());
+        } else {
+            FillEmit e{t_starts, t_ends, ray_indices, (int32_t)r, (int64_t)starts[r], S_cap, 0};
+            int n = march_ray(o, d, occ, s_aabb, levels, res, nearp, far_plane, step_size, cone_angle, e);
+            if ((int64_t)starts[r] + n > S_cap && overflow) *overflow = 1;
+        }
     }
 }
 
@@ -216,15 +244,34 @@ __global__ void occ_binarize_kernel(const float *__restrict__ occs, int64_t n, c
 
 using namespace lse;
 
-extern "C" int lse_march_count(const float *rays_o, const float *rays_d, int64_t n_rays, const uint8_t *binaries,
-                               const float *aabbs, int levels, int res, float near_plane, float far_plane,
-                               const float *jitter, float step_size, float cone_angle, int32_t *counts, lse_stream_t stream)
+extern "C" int lse_occ_pack(const uint8_t *binaries, int levels, int res, uint32_t *bits, uint32_t *mip, lse_stream_t stream)
 {
     LSE_CHECK_ARG(levels >= 1 && levels <= kMaxLevels, "levels must be in [1,8]");
+    LSE_CHECK_ARG(res % 32 == 0, "grid resolution must be a multiple of 32");
+    const int sb = res >> 3;
+    const int mip_words = (levels * sb * sb * sb + 31) / 32;
+    LSE_CHECK_ARG(mip_words <= kMaxMipWords, "occupancy mip does not fit shared memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(mip, 0, sizeof(uint32_t) * mip_words, st);
+    const int64_t n_words = ((int64_t)levels * res * res * res) >> 5;
+    occ_pack_kernel<<<stride_grid(n_words, 256, 4), 256, 0, st>>>(binaries, levels, res, bits, mip);
+    return check_launch("lse_occ_pack");
+}
+
+extern "C" int lse_march_count(const float *rays_o, const float *rays_d, int64_t n_rays, const uint32_t *occ_bits,
+                               const uint32_t *occ_mip, const float *aabbs, int levels, int res, float near_plane,
+                               float far_plane, const float *jitter, float step_size, float cone_angle, int32_t *counts,
+                               lse_stream_t stream)
+{
+    LSE_CHECK_ARG(levels >= 1 && levels <= kMaxLevels, "levels must be in [1,8]");
+    LSE_CHECK_ARG(res % 32 == 0, "grid resolution must be a multiple of 32");
     if (n_rays <= 0) return 0;
+    const int sb = res >> 3;
+    const int mip_words = (levels * sb * sb * sb + 31) / 32;
     int threads = 64;  // few, long-running threads: spread rays over all SMs
-    march_count_kernel<<<stride_grid(n_rays, threads, 16), threads, 0, (cudaStream_t)stream>>>(
-        rays_o, rays_d, n_rays, binaries, aabbs, levels, res, near_plane, far_plane, jitter, step_size, cone_angle, counts);
+    march_kernel<false><<<stride_grid(n_rays, threads, 16), threads, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, n_rays, occ_bits, occ_mip, mip_words, aabbs, levels, res, near_plane, far_plane, jitter, step_size,
+        cone_angle, counts, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
     return check_launch("lse_march_count");
 }
 
@@ -235,17 +282,21 @@ extern "C" int lse_scan_counts(const int32_t *counts, int64_t n, int32_t *starts
     return check_launch("lse_scan_counts");
 }
 
-extern "C" int lse_march_fill(const float *rays_o, const float *rays_d, int64_t n_rays, const uint8_t *binaries,
-                              const float *aabbs, int levels, int res, float near_plane, float far_plane, const float *jitter,
-                              float step_size, float cone_angle, const int32_t *starts, int64_t S_cap, int32_t *ray_indices,
-                              float *t_starts, float *t_ends, int32_t *overflow_dev, lse_stream_t stream)
+extern "C" int lse_march_fill(const float *rays_o, const float *rays_d, int64_t n_rays, const uint32_t *occ_bits,
+                              const uint32_t *occ_mip, const float *aabbs, int levels, int res, float near_plane,
+                              float far_plane, const float *jitter, float step_size, float cone_angle, const int32_t *starts,
+                              int64_t S_cap, int32_t *ray_indices, float *t_starts, float *t_ends, int32_t *overflow_dev,
+                              lse_stream_t stream)
 {
     LSE_CHECK_ARG(levels >= 1 && levels <= kMaxLevels, "levels must be in [1,8]");
+    LSE_CHECK_ARG(res % 32 == 0, "grid resolution must be a multiple of 32");
     if (n_rays <= 0) return 0;
+    const int sb = res >> 3;
+    const int mip_words = (levels * sb * sb * sb + 31) / 32;
     int threads = 64;
-    march_fill_kernel<<<stride_grid(n_rays, threads, 16), threads, 0, (cudaStream_t)stream>>>(
-        rays_o, rays_d, n_rays, binaries, aabbs, levels, res, near_plane, far_plane, jitter, step_size, cone_angle, starts,
-        S_cap, ray_indices, t_starts, t_ends, overflow_dev);
+    march_kernel<true><<<stride_grid(n_rays, threads, 16), threads, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, n_rays, occ_bits, occ_mip, mip_words, aabbs, levels, res, near_plane, far_plane, jitter, step_size,
+        cone_angle, nullptr, starts, S_cap, ray_indices, t_starts, t_ends, overflow_dev);
     return check_launch("lse_march_fill");
 }
 

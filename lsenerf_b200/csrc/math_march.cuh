@@ -30,9 +30,35 @@ LSE_HD float march_dt(float t, float cone_angle, float dt_min)
     return fminf(fmaxf(rn_mul(t, cone_angle), dt_min), 1e10f);
 }
 
-// Emit = functor (float t_start, float t_end) called once per sample in order.  Returns the sample count.
-template <class Emit>
-LSE_HD int march_ray(const float o[3], const float d[3], const uint8_t *binaries, const float *aabbs, int levels,
+// occupancy as the byte tensor nerfacc keeps (binaries [levels,res,res,res] bool)
+struct OccBytes {
+    const uint8_t *binaries; int res;
+    LSE_HD bool operator()(int level, const int cur[3]) const
+    {
+        int64_t cell = (int64_t)level * res * res * res + ((int64_t)cur[0] * res + cur[1]) * res + cur[2];
+        return binaries[cell] != 0;
+    }
+};
+
+// occupancy as 1 bit per cell (word = cell >> 5) guarded by an any-occupied mip over 8^3 superblocks: the DDA still
+// visits every cell (the fp32 tdist recurrence has to be replayed exactly) but cells of an empty superblock cost no
+// memory access at all -- the mip (levels * (res/8)^3 bits = 2 KiB for 4 x 128^3) lives in shared memory.
+struct OccBits {
+    const uint32_t *bits; const uint32_t *mip; int res;
+    LSE_HD bool operator()(int level, const int cur[3]) const
+    {
+        const int sb = res >> 3;
+        const int m = ((level * sb + (cur[0] >> 3)) * sb + (cur[1] >> 3)) * sb + (cur[2] >> 3);
+        if (!((mip[m >> 5] >> (m & 31)) & 1u)) return false;
+        const int64_t cell = (int64_t)level * res * res * res + ((int64_t)cur[0] * res + cur[1]) * res + cur[2];
+        return (bits[cell >> 5] >> (cell & 31)) & 1u;
+    }
+};
+
+// Occ  = functor (level, cur[3]) -> occupied ; Emit = functor (float t_start, float t_end) called once per sample in
+// order.  Returns the sample count.
+template <class Occ, class Emit>
+LSE_HD int march_ray(const float o[3], const float d[3], Occ occ, const float *aabbs, int levels,
                      int res, float near_plane, float far_plane, float step_size, float cone_angle, Emit emit)
 {
     const float eps = 1e-6f;
@@ -55,7 +81,6 @@ LSE_HD int march_ray(const float o[3], const float d[3], const uint8_t *binaries
 
     int n = 0;
     float t_last = near_plane;
-    const int64_t cells = (int64_t)res * res * res;
     const float resf = (float)res;
 
     for (int i = 0; i < n_ev - 1; ++i) {
@@ -95,8 +120,7 @@ LSE_HD int march_ray(const float o[3], const float d[3], const uint8_t *binaries
 
         for (;;) {
             float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), tmax);
-            int64_t cell = (int64_t)level * cells + ((int64_t)cur[0] * res + cur[1]) * res + cur[2];
-            if (!binaries[cell]) {
+            if (!occ(level, cur)) {
                 for (;;) {
                     float dt = march_dt(t_last, cone_angle, step_size);
                     if (rn_add(t_last, rn_mul(dt, 0.5f)) >= t_trav) break;
