@@ -72,7 +72,7 @@ class LSEField(nn.Module):
                  num_layers_color: int = 3, features_per_level: int = 2, hidden_dim_color: int = 64,
                  appearance_embedding_dim: int = 32, embd_config: Optional[LSEEmbeddingConfig] = None,
                  spatial_distortion=True, average_init_density: float = 1.0, implementation: str = "torch",
-                 use_tensor_cores: bool = False, **unused) -> None:
+                 use_tensor_cores: bool = True, **unused) -> None:
         super().__init__()
         assert (num_layers, hidden_dim, geo_feat_dim, num_levels, num_layers_color, hidden_dim_color) == (2, 64, 15, 16, 3, 64), \
             "the fused kernels are specialised for the shipped architecture (lse_field.py:128-140)"

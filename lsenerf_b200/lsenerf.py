@@ -53,7 +53,7 @@ class LSENeRFModelConfig:
     map_mode: str = "ev_rgb"
     embed_config: LSEEmbeddingConfig = field(default_factory=LSEEmbeddingConfig)
     # B200 build knobs
-    use_tensor_cores: bool = False
+    use_tensor_cores: bool = True
     samples_per_ray_cap: int = 512
 
     def __post_init__(self):  # lsenerf.py:86-99
