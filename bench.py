@@ -165,13 +165,19 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from lsenerf_b200 import _lib
-    from lsenerf_b200.lse_pipeline import FusedAdam, train_iteration
 
     scene, pipe = build(dev, seed=96 + rank)
     pipe.train()
     dm = pipe.datamanager
-    opt = FusedAdam(pipe.get_param_groups())
+    from lsenerf_b200.engine import ArenaAdam, GraphedStep
+    opt = ArenaAdam(pipe.get_param_groups())
     K, W = args.steps, args.warmup
+    # steady-state training: start after the occupancy grid's 256-step warm-up schedule (during warm-up every 16th step
+    # re-evaluates all 4x128^3 cells, afterwards a quarter of them + the occupied ones)
+    START = 1000
+    gs = GraphedStep(pipe, opt, world, use_graph=not args.no_graph)
+    opt.step_count = START
+    gs.capture(start_step=START)
 
     def barrier():
         if world > 1:
@@ -186,54 +192,51 @@ def run_b200(args):
         return ms
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------------
-    staged = []
-    for _ in range(K + W):
-        hc, he = dm.sample_host_batches()
-        staged.append((dm.to_device(hc, True), dm.to_device(he, True)))
+    staged = [gs.stage.pack_to_device(*dm.sample_host_batches()) for _ in range(K + W)]
     torch.cuda.synchronize()
-    step_no = 0
     for i in range(W):
-        train_iteration(pipe, opt, step_no, world, staged[i]); step_no += 1
+        gs.step(packed_dev=staged[i])
     barrier()
     clocks = ClockSampler(local); clocks.start()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        train_iteration(pipe, opt, step_no, world, staged[W + i]); step_no += 1
+        gs.step(packed_dev=staged[W + i])
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - l0
+    launches_eager = _lib.launch_count() - l0
     del staged
 
-    # ---- e2e: host image stacks -> pinned batch -> H2D -> step -> D2H loss ------------------------------------------------
-    h2d = d2h = 0
+    # ---- e2e: host image stacks -> host pixel draw + gather -> pinned batch -> H2D -> step -> D2H loss --------------------
     for _ in range(2):
-        train_iteration(pipe, opt, step_no, world); step_no += 1
+        gs.step()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(K):
-        hc, he = dm.sample_host_batches()
-        pre = (dm.to_device(hc, True), dm.to_device(he, True))
-        h2d = dm.batch_nbytes(hc) + dm.batch_nbytes(he)
-        ld, _ = train_iteration(pipe, opt, step_no, world, pre); step_no += 1
-        host_loss = torch.stack([v.detach() for v in ld.values()]).cpu()   # D2H read of the step's result
-        d2h = host_loss.numel() * host_loss.element_size()
+        host_loss = gs.step(host_batches=dm.sample_host_batches()).cpu()   # D2H read of the step's losses
     f1.record()
     barrier()
     clk = clocks.stop()
     ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+    h2d, d2h = gs.stage.nbytes, host_loss.numel() * host_loss.element_size()
 
-    # ---- per-kernel-class device time + roofline of the dominant kernel (outside the timed regions) -----------------------
+    # ---- per-kernel-class device time + roofline of the dominant kernel (eager, outside the timed regions) ----------------
+    eager = GraphedStep(pipe, opt, world, use_graph=False)
+    eager.step_no = gs.step_no
+    eager.step(); eager.step()
     _lib.profile_start()
-    n_prof = 3
+    l1 = _lib.launch_count()
+    n_prof = 4
     for _ in range(n_prof):
-        train_iteration(pipe, opt, step_no, world); step_no += 1
+        eager.step_no = 1001                      # keep the (amortised) grid update out of the per-kernel picture
+        eager.step()
+    launches = (_lib.launch_count() - l1) // n_prof * K if launches_eager == 0 or not args.no_graph else launches_eager
     prof = _lib.profile_stop()
     opts = pipe._model._render_opts(); opts.keep_debug = True
-    bundles, _ = dm.next_train(step_no)
+    bundles, _ = dm.next_train(gs.step_no)
     from lsenerf_b200.compat import concat_bundles
     with torch.no_grad():
         pipe._model.exec_get_outputs(concat_bundles(list(bundles)), None, opts)
@@ -259,7 +262,9 @@ def run_b200(args):
                 "config": {"workload": WORKLOAD, "parallelism": f"ray-sharded dp{world}, 1 grad all-reduce/step",
                            "l2": "working set per step (64 MiB table + 64 MiB grad + 128 MiB Adam state + sample buffers) exceeds the 126 MB L2; no explicit flush",
                            "samples_marched_per_step": S0, "samples_kept_per_step": S1, "capacity_overflow": overflow,
-                           "mlp": "tcgen05 3xTF32" if pipe._model.config.use_tensor_cores else "fp32 SIMT"},
+                           "mlp": "tcgen05 (3xTF32 fwd, BF16x3 bwd)" if pipe._model.config.use_tensor_cores else "fp32 SIMT",
+                           "step": "one CUDA-graph replay (zero_grad+raygen+render+loss+backward) + Adam graph" if not args.no_graph else "eager launches",
+                           "start_step": START},
                 "e2e": {"value": rays * K / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": int(launches), "clocks": clk,
@@ -283,6 +288,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

