@@ -8,6 +8,7 @@
 // Kernel classes: the DDA itself is a sequential fp32 recurrence per ray (one thread per ray, bit-exact against
 // the oracle, built WITHOUT fma contraction); visibility/compaction are warp-per-ray segmented scans
 // (HBM-streaming, ~20 B per sample).
+#include <cstdlib>
 #include "common.cuh"
 #include "math_march.cuh"
 #include "../../include/lsenerf_b200.h"
@@ -58,7 +59,13 @@ __global__ void occ_pack_kernel(const uint8_t *__restrict__ binaries, int levels
     }
 }
 
-constexpr int kMaxMipWords = 1024;  // 4 levels x 16^3 superblocks = 16384 bits = 512 words (res 128); 8 levels fit too
+constexpr int kMaxMipWords = 1024;
+static int ray_stride()   // lanes per ray (see march_kernel); LSE_MARCH_STRIDE overrides for tuning
+{
+    static int v = 0;
+    if (v == 0) { const char *e = getenv("LSE_MARCH_STRIDE"); v = e ? atoi(e) : 8; if (v < 1 || v > 32) v = 8; }
+    return v;
+}  // 4 levels x 16^3 superblocks = 16384 bits = 512 words (res 128); 8 levels fit too
 
 template <bool FILL>
 __global__ void march_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n_rays,
@@ -67,7 +74,7 @@ __global__ void march_kernel(const float *__restrict__ rays_o, const float *__re
                              const float *__restrict__ jitter, float step_size, float cone_angle,
                              int32_t *__restrict__ counts, const int32_t *__restrict__ starts, int64_t S_cap,
                              int32_t *__restrict__ ray_indices, float *__restrict__ t_starts, float *__restrict__ t_ends,
-                             int32_t *__restrict__ overflow)
+                             int32_t *__restrict__ overflow, int kRayStride)
 {
     __shared__ float s_aabb[6 * kMaxLevels];
     __shared__ uint32_t s_mip[kMaxMipWords];
@@ -75,7 +82,14 @@ __global__ void march_kernel(const float *__restrict__ rays_o, const float *__re
     for (int i = threadIdx.x; i < mip_words; i += blockDim.x) s_mip[i] = mip[i];
     __syncthreads();
     const OccBits occ{bits, s_mip, res};
-    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rays; r += (int64_t)gridDim.x * blockDim.x) {
+    // kRayStride lanes per ray: a warp marches only 32/kRayStride rays.  The rays of a warp are incoherent (random pixels of
+    // random cameras), so lanes wait on each other's data-dependent loops, and with one thread per ray the whole chip holds
+    // 256 warps (< 1 per scheduler): spreading the rays over 4x more warps cuts the divergence and lets the schedulers
+    // overlap the dependent fp32 chains of several warps.  Measured optimum between issue-bound (1 ray/warp) and
+    // latency-bound (32 rays/warp).
+    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (gtid % kRayStride != 0) return;
+    for (int64_t r = gtid / kRayStride; r < n_rays; r += ((int64_t)gridDim.x * blockDim.x) / kRayStride) {
         float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
         float d[3] = {rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]};
         float nearp = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
@@ -268,10 +282,11 @@ extern "C" int lse_march_count(const float *rays_o, const float *rays_d, int64_t
     if (n_rays <= 0) return 0;
     const int sb = res >> 3;
     const int mip_words = (levels * sb * sb * sb + 31) / 32;
-    int threads = 64;  // few, long-running threads: spread rays over all SMs
-    march_kernel<false><<<stride_grid(n_rays, threads, 16), threads, 0, (cudaStream_t)stream>>>(
+    const int kRayStride = ray_stride();
+    int threads = 128;
+    march_kernel<false><<<stride_grid(n_rays * kRayStride, threads, 16), threads, 0, (cudaStream_t)stream>>>(
         rays_o, rays_d, n_rays, occ_bits, occ_mip, mip_words, aabbs, levels, res, near_plane, far_plane, jitter, step_size,
-        cone_angle, counts, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+        cone_angle, counts, nullptr, 0, nullptr, nullptr, nullptr, nullptr, kRayStride);
     return check_launch("lse_march_count");
 }
 
@@ -293,10 +308,11 @@ extern "C" int lse_march_fill(const float *rays_o, const float *rays_d, int64_t 
     if (n_rays <= 0) return 0;
     const int sb = res >> 3;
     const int mip_words = (levels * sb * sb * sb + 31) / 32;
-    int threads = 64;
-    march_kernel<true><<<stride_grid(n_rays, threads, 16), threads, 0, (cudaStream_t)stream>>>(
+    const int kRayStride = ray_stride();
+    int threads = 128;
+    march_kernel<true><<<stride_grid(n_rays * kRayStride, threads, 16), threads, 0, (cudaStream_t)stream>>>(
         rays_o, rays_d, n_rays, occ_bits, occ_mip, mip_words, aabbs, levels, res, near_plane, far_plane, jitter, step_size,
-        cone_angle, nullptr, starts, S_cap, ray_indices, t_starts, t_ends, overflow_dev);
+        cone_angle, nullptr, starts, S_cap, ray_indices, t_starts, t_ends, overflow_dev, kRayStride);
     return check_launch("lse_march_fill");
 }
 

@@ -57,28 +57,19 @@ struct OccBits {
 
 // Occ  = functor (level, cur[3]) -> occupied ; Emit = functor (float t_start, float t_end) called once per sample in
 // order.  Returns the sample count.
-//
-// Control flow is a FLAT state machine: one loop whose every trip advances every lane by one unit of work (a few
-// empty-space steps, a few samples, or one DDA cell step).  A 32-ray warp is completely incoherent (random pixels of
-// random cameras); with nested data-dependent loops every lane waits for the longest inner loop of any lane at each
-// reconvergence point, which cost ~13x here.  The arithmetic and its order per ray are exactly those of the nested
-// formulation in oracle/nerfacc_ref.c.
 template <class Occ, class Emit>
 LSE_HD int march_ray(const float o[3], const float d[3], Occ occ, const float *aabbs, int levels,
                      int res, float near_plane, float far_plane, float step_size, float cone_angle, Emit emit)
 {
     const float eps = 1e-6f;
-    const float inv0 = rn_div(1.0f, d[0]), inv1 = rn_div(1.0f, d[1]), inv2 = rn_div(1.0f, d[2]);
+    float inv[3] = {rn_div(1.0f, d[0]), rn_div(1.0f, d[1]), rn_div(1.0f, d[2])};
     float tv[2 * kMaxLevels]; int ti[2 * kMaxLevels]; bool hits[kMaxLevels];
-    {
-        const float inv[3] = {inv0, inv1, inv2};
-        const float miss = INFINITY;
-        for (int l = 0; l < levels; ++l) {
-            float t0, t1;
-            hits[l] = slab_hit(o, inv, aabbs + 6 * l, aabbs + 6 * l + 3, t0, t1);
-            tv[l] = hits[l] ? t0 : miss;
-            tv[levels + l] = hits[l] ? t1 : miss;
-        }
+    const float miss = INFINITY;
+    for (int l = 0; l < levels; ++l) {
+        float t0, t1;
+        hits[l] = slab_hit(o, inv, aabbs + 6 * l, aabbs + 6 * l + 3, t0, t1);
+        tv[l] = hits[l] ? t0 : miss;
+        tv[levels + l] = hits[l] ? t1 : miss;
     }
     const int n_ev = 2 * levels;
     for (int i = 0; i < n_ev; ++i) ti[i] = i;
@@ -92,97 +83,67 @@ LSE_HD int march_ray(const float o[3], const float d[3], Occ occ, const float *a
     float t_last = near_plane;
     const float resf = (float)res;
 
-    // traversal state (scalars, no dynamically indexed arrays)
-    float td0 = 0.f, td1 = 0.f, td2 = 0.f, dl0 = 0.f, dl1 = 0.f, dl2 = 0.f, tmax = 0.f, t_trav = 0.f;
-    int c0 = 0, c1 = 0, c2 = 0, s0 = 0, s1 = 0, s2 = 0, v0 = 0, v1 = 0, v2 = 0, level = 0;
-    int seg = 0;           // next event pair to look at
-    int state = 0;         // 0: find + set up next segment, 1: begin cell, 2: march empty, 3: march occupied, 4: DDA step, 5: done
-    while (state != 5) {
-        if (state == 0) {
-            // ---- find the next traversable segment ------------------------------------------------------------------
-            bool found = false;
-            float tmin = 0.f;
-            while (seg < n_ev - 1 && !found) {
-                const int i = seg++;
-                const bool entering = ti[i] < levels;
-                int lv = ti[i] % levels;
-                if (!hits[lv]) continue;
-                if (!entering) {
-                    const int next_level = ti[i + 1] % levels;
-                    if (next_level <= lv) continue;
-                    lv = next_level;
-                }
-                tmin = fmaxf(tv[i], near_plane);
-                tmax = fminf(tv[i + 1], far_plane);
-                if (tmin >= tmax) continue;
-                level = lv;
-                found = true;
-            }
-            if (!found) { state = 5; continue; }
-            const float *bmin = aabbs + 6 * level, *bmax = bmin + 3;
-            float tdv[3], dlv[3]; int cv[3], sv[3], ov[3];
-            const float inv[3] = {inv0, inv1, inv2};
-#pragma unroll
-            for (int ax = 0; ax < 3; ++ax) {
-                float ext = rn_sub(bmax[ax], bmin[ax]);
-                float voxel = rn_div(ext, resf);
-                float s = rn_add(o[ax], rn_mul(d[ax], rn_add(tmin, eps)));
-                float e = rn_add(o[ax], rn_mul(d[ax], rn_sub(tmax, eps)));
-                int a0 = (int)rn_mul(rn_div(rn_sub(s, bmin[ax]), ext), resf);
-                int a1 = (int)rn_mul(rn_div(rn_sub(e, bmin[ax]), ext), resf);
-                cv[ax] = a0 < 0 ? 0 : (a0 > res - 1 ? res - 1 : a0);
-                int fin = a1 < 0 ? 0 : (a1 > res - 1 ? res - 1 : a1);
-                int idelta = d[ax] > 0.0f ? 1 : 0;
-                float edge = rn_mul((float)(cv[ax] + idelta), voxel);
-                float tm = rn_add(rn_mul(rn_add(bmin[ax], rn_sub(edge, s)), inv[ax]), tmin);
-                float sf = (d[ax] == 0.0f) ? 0.0f : (d[ax] > 0.0f ? 1.0f : -1.0f);
-                tdv[ax] = (d[ax] == 0.0f) ? tmax : tm;
-                sv[ax] = (int)sf;
-                float dl = rn_mul(rn_mul(voxel, inv[ax]), sf);
-                dlv[ax] = (d[ax] == 0.0f) ? tmax : dl;
-                ov[ax] = fin + sv[ax];
-            }
-            td0 = tdv[0]; td1 = tdv[1]; td2 = tdv[2]; dl0 = dlv[0]; dl1 = dlv[1]; dl2 = dlv[2];
-            c0 = cv[0]; c1 = cv[1]; c2 = cv[2]; s0 = sv[0]; s1 = sv[1]; s2 = sv[2]; v0 = ov[0]; v1 = ov[1]; v2 = ov[2];
-            state = 1;
+    for (int i = 0; i < n_ev - 1; ++i) {
+        bool entering = ti[i] < levels;
+        int level = ti[i] % levels;
+        if (!hits[level]) continue;
+        if (!entering) {
+            int next_level = ti[i + 1] % levels;
+            if (next_level <= level) continue;
+            level = next_level;
         }
-        if (state == 1) {
-            t_trav = fminf(fminf(td0, fminf(td1, td2)), tmax);
-            const int cur[3] = {c0, c1, c2};
-            state = occ(level, cur) ? 3 : 2;
+        float tmin = fmaxf(tv[i], near_plane);
+        float tmax = fminf(tv[i + 1], far_plane);
+        if (tmin >= tmax) continue;
+
+        const float *bmin = aabbs + 6 * level, *bmax = bmin + 3;
+        float tdist[3], delta[3]; int cur[3], stp[3], ovf[3];
+        for (int ax = 0; ax < 3; ++ax) {
+            float ext = rn_sub(bmax[ax], bmin[ax]);
+            float voxel = rn_div(ext, resf);
+            float s = rn_add(o[ax], rn_mul(d[ax], rn_add(tmin, eps)));
+            float e = rn_add(o[ax], rn_mul(d[ax], rn_sub(tmax, eps)));
+            int c0 = (int)rn_mul(rn_div(rn_sub(s, bmin[ax]), ext), resf);
+            int c1 = (int)rn_mul(rn_div(rn_sub(e, bmin[ax]), ext), resf);
+            cur[ax] = c0 < 0 ? 0 : (c0 > res - 1 ? res - 1 : c0);
+            int fin = c1 < 0 ? 0 : (c1 > res - 1 ? res - 1 : c1);
+            int idelta = d[ax] > 0.0f ? 1 : 0;
+            float edge = rn_mul((float)(cur[ax] + idelta), voxel);
+            float tm = rn_add(rn_mul(rn_add(bmin[ax], rn_sub(edge, s)), inv[ax]), tmin);
+            float sf = (d[ax] == 0.0f) ? 0.0f : (d[ax] > 0.0f ? 1.0f : -1.0f);
+            tdist[ax] = (d[ax] == 0.0f) ? tmax : tm;
+            stp[ax] = (int)sf;
+            float dl = rn_mul(rn_mul(voxel, inv[ax]), sf);
+            delta[ax] = (d[ax] == 0.0f) ? tmax : dl;
+            ovf[ax] = fin + stp[ax];
         }
-        if (state == 2) {
-            // a few empty-space steps per trip
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                if (state == 2) {
+
+        for (;;) {
+            float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), tmax);
+            if (!occ(level, cur)) {
+                for (;;) {
                     float dt = march_dt(t_last, cone_angle, step_size);
-                    if (rn_add(t_last, rn_mul(dt, 0.5f)) >= t_trav) state = 4;
-                    else t_last = rn_add(t_last, dt);
+                    if (rn_add(t_last, rn_mul(dt, 0.5f)) >= t_trav) break;
+                    t_last = rn_add(t_last, dt);
                 }
-            }
-        } else if (state == 3) {
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                if (state == 3) {
+            } else {
+                for (;;) {
                     float dt = march_dt(t_last, cone_angle, step_size);
-                    if (rn_add(t_last, rn_mul(dt, 0.5f)) >= t_trav) state = 4;
-                    else {
-                        float t_next = rn_add(t_last, dt);
-                        emit(t_last, t_next);
-                        ++n;
-                        t_last = t_next;
-                        if (t_next >= t_trav) state = 4;
-                    }
+                    if (rn_add(t_last, rn_mul(dt, 0.5f)) >= t_trav) break;
+                    float t_next = rn_add(t_last, dt);
+                    emit(t_last, t_next);
+                    ++n;
+                    t_last = t_next;
+                    if (t_next >= t_trav) break;
                 }
             }
-        }
-        if (state == 4) {
-            bool over;
-            if (td0 < td1 && td0 < td2) { c0 += s0; td0 = rn_add(td0, dl0); over = (c0 == v0); }
-            else if (td1 < td2)         { c1 += s1; td1 = rn_add(td1, dl1); over = (c1 == v1); }
-            else                        { c2 += s2; td2 = rn_add(td2, dl2); over = (c2 == v2); }
-            state = over ? 0 : 1;
+            int ax;
+            if (tdist[0] < tdist[1] && tdist[0] < tdist[2]) ax = 0;
+            else if (tdist[1] < tdist[2]) ax = 1;
+            else ax = 2;
+            cur[ax] += stp[ax];
+            tdist[ax] = rn_add(tdist[ax], delta[ax]);
+            if (cur[ax] == ovf[ax]) break;
         }
     }
     return n;
