@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -153,6 +153,46 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------- GPU arm
+def render_leg(pipe, scene, dev, rank, world, max_over_ranks, barrier, H=720, W=1280, f=1000.0, frames=3, chunk=65536):
+    """Full-frame eval render (no culling, no jitter, LinearRenderer, final clamp) of a 1280x720 camera placed on the spline,
+    with an SO3xR3 camera-optimizer delta applied to the bundle (lse_loaders.py:20-27); rows sharded over the ranks."""
+    from lsenerf_b200 import ops
+    from lsenerf_b200.compat import RayBundle
+    m = pipe._model
+    was_training = m.training
+    pipe.eval()
+    rows = (H + world - 1) // world
+    r0, r1 = rank * rows, min(H, (rank + 1) * rows)
+    ys, xs = torch.meshgrid(torch.arange(r0, r1, dtype=torch.float32, device=dev), torch.arange(W, dtype=torch.float32, device=dev), indexing="ij")
+    coords = torch.stack([ys, xs], -1).reshape(-1, 2).contiguous()
+    n = coords.shape[0]
+    co = pipe.datamanager.col_train_camera_optimizer
+    pa = torch.randn(1, 6, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) * 1e-3
+
+    def frame(t):
+        with torch.no_grad():
+            c2w = co.get_rgb_cameras(torch.tensor([t], device=dev))[0]
+            o, d, area, _ = ops.rays_from_c2w(c2w[None].expand(n, 3, 4).contiguous(), coords, f, f, W / 2.0, H / 2.0)
+            o, d = ops.pose_delta(pa, torch.zeros(n, dtype=torch.long, device=dev), o, d)
+            rb = RayBundle(o.reshape(r1 - r0, W, 3), d.reshape(r1 - r0, W, 3), area.reshape(r1 - r0, W, 1),
+                           torch.zeros(r1 - r0, W, 1, dtype=torch.long, device=dev),
+                           metadata={"appearance_id": torch.zeros(r1 - r0, W, 1, dtype=torch.long, device=dev)})
+            return m.get_outputs_for_camera_ray_bundle(rb, chunk=chunk)["rgb"]
+    frame(1.0e5)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(frames):
+        img = frame(1.0e5 + 5.0e4 * k)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / frames
+    if was_training:
+        pipe.train()
+    return {"value": H * W / (ms * 1e-3), "unit": "rays/s", "frame": f"{W}x{H}", "ms_per_frame": ms, "chunk_rays": chunk,
+            "sharding": f"{world} row blocks", "mean_rgb": float(img.mean())}
+
+
 def run_b200(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,13 +237,13 @@ def run_b200(args):
             return float(t.item())
         return ms
 
+    clocks = ClockSampler(local); clocks.start()
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------------
     staged = [gs.stage.pack_to_device(*dm.sample_host_batches()) for _ in range(K + W)]
     torch.cuda.synchronize()
     for i in range(W):
         gs.step(packed_dev=staged[i])
     barrier()
-    clocks = ClockSampler(local); clocks.start()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -249,6 +289,9 @@ def run_b200(args):
     S0, S1 = int(opts.debug["march0"].total.item()), int(opts.debug["march"].total.item())
     overflow = int(opts.debug["march0"].overflow.item())
 
+    # ---- render rays/sec: BASELINE configs[4], one 1280x720 eval frame with camera optimisation, rows sharded over ranks -------
+    render = render_leg(pipe, scene, dev, rank, world, max_over_ranks, barrier)
+
     if rank == 0:
         per_call = {k: v[1] / v[0] for k, v in prof.items()}
         per_step = {k: v[1] / n_prof for k, v in prof.items()}
@@ -277,6 +320,7 @@ def run_b200(args):
                 "roofline": {"kernel": roof_k, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                              "traffic": None, "peak_source": which, "ms_per_launch": per_call[roof_k],
                              "share_of_step": per_step[roof_k] / sum(per_step.values())},
+                "render": render,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
         if world == 1 and not args.no_cpu:
             rps, sec = time_cpu(3, 1, 1024)

@@ -251,4 +251,4 @@ class LSENeRFModel(nn.Module):
             o = self.forward(flat[i:i + chunk])
             for k, v in o.items():
                 outs.setdefault(k, []).append(v)
-        return {k: torch.cat(v).view(H, W, -1) for k, v in outs.items() if v[0].shape[0] == min(chunk, H * W) or k != "x"}
+        return {k: torch.cat(v).view(H, W, -1) for k, v in outs.items()}
