@@ -24,6 +24,36 @@ from ._lib import P, call, stream
 from .lse_pipeline import DEFAULT_OPTIMIZERS, LSENeRFPipeline, OptimizerSpec
 
 
+class _PinnedRing:
+    """N pinned host buffers used round-robin as the source of asynchronous H2D copies.  ``acquire`` returns the next slot
+    after waiting for the copy that last read it; ``upload`` enqueues the copy on the current stream and marks the slot."""
+
+    def __init__(self, shape, dtype, device, slots: int = 4) -> None:
+        self.cuda = torch.device(device).type == "cuda"
+        self.bufs = [torch.zeros(shape, dtype=dtype) for _ in range(slots)]
+        if self.cuda:
+            self.bufs = [b.pin_memory() for b in self.bufs]
+        self.events = [None] * slots
+        self.cur = -1
+
+    def acquire(self) -> torch.Tensor:
+        self.cur = (self.cur + 1) % len(self.bufs)
+        ev = self.events[self.cur]
+        if ev is not None:
+            ev.synchronize()
+        return self.bufs[self.cur]
+
+    def current(self) -> torch.Tensor:
+        return self.bufs[self.cur]
+
+    def upload(self, dst: torch.Tensor) -> None:
+        dst.copy_(self.bufs[self.cur], non_blocking=True)
+        if self.cuda:
+            ev = self.events[self.cur] or torch.cuda.Event()
+            ev.record()
+            self.events[self.cur] = ev
+
+
 class ParamArena:
     """One optimizer group flattened: params, grads and Adam moments each in one contiguous fp32 buffer."""
 
@@ -63,7 +93,9 @@ class ArenaAdam:
         self.groups = {k: a.params for k, a in self.arenas.items()}
         dev = next(iter(self.arenas.values())).data.device
         self.names = list(self.arenas.keys())
-        self.hp_host = torch.zeros(len(self.names), 4).pin_memory() if dev.type == "cuda" else torch.zeros(len(self.names), 4)
+        # ring of pinned host mirrors: the host may run several steps ahead of the device, so a slot is only rewritten after
+        # the H2D copy that read it has completed (event per slot)
+        self.hp_ring = _PinnedRing((len(self.names), 4), torch.float32, dev)
         self.hp_dev = torch.zeros(len(self.names), 4, device=dev)
         self.step_count = 0
 
@@ -74,15 +106,16 @@ class ArenaAdam:
     def set_step(self, step_count: int, grad_scale: float = 1.0) -> None:
         """refresh the device hyper-parameters for optimizer step number `step_count` (1-based)."""
         self.step_count = step_count
+        host = self.hp_ring.acquire()
         for i, name in enumerate(self.names):
             spec = self.specs[name]
             lr = spec.lr_at(step_count - 1)
             bc1 = 1.0 - spec.betas[0] ** step_count
             bc2 = 1.0 - spec.betas[1] ** step_count
-            self.hp_host[i, 0] = lr / bc1
-            self.hp_host[i, 1] = math.sqrt(bc2)
-            self.hp_host[i, 2] = grad_scale
-        self.hp_dev.copy_(self.hp_host, non_blocking=True)
+            host[i, 0] = lr / bc1
+            host[i, 1] = math.sqrt(bc2)
+            host[i, 2] = grad_scale
+        self.hp_ring.upload(self.hp_dev)
 
     @torch.no_grad()
     def apply(self) -> None:
@@ -117,9 +150,7 @@ class BatchStage:
                 if isinstance(v, torch.Tensor):
                     self.keys.append((name, k, v.shape, v.dtype, v.numel() * v.element_size()))
         self.nbytes = sum((nb + 15) // 16 * 16 for *_, nb in self.keys)
-        self.host = torch.empty(self.nbytes, dtype=torch.uint8)
-        if torch.cuda.is_available():
-            self.host = self.host.pin_memory()
+        self.ring = _PinnedRing((self.nbytes,), torch.uint8, device)
         self.dev = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
         self.has = (col_batch is not None, evs_batch is not None)
 
@@ -136,7 +167,7 @@ class BatchStage:
         return (v["col"] if self.has[0] else None, v["evs"] if self.has[1] else None)
 
     def pack_host(self, col_batch, evs_batch) -> None:
-        v = self._views(self.host)
+        v = self._views(self.ring.acquire())
         for name, b in (("col", col_batch), ("evs", evs_batch)):
             if b is not None:
                 for k, t in b.items():
@@ -144,7 +175,7 @@ class BatchStage:
                         v[name][k].copy_(t)
 
     def upload(self) -> None:
-        self.dev.copy_(self.host, non_blocking=True)
+        self.ring.upload(self.dev)
 
     def load_packed(self, packed_dev: torch.Tensor) -> None:
         """device-to-device refresh from a pre-staged packed batch (bench: inputs resident in HBM)."""
@@ -152,7 +183,7 @@ class BatchStage:
 
     def pack_to_device(self, col_batch, evs_batch) -> torch.Tensor:
         self.pack_host(col_batch, evs_batch)
-        return self.host.to(self.device, non_blocking=False).clone()
+        return self.ring.current().to(self.device, non_blocking=False).clone()
 
 
 class GraphedStep:

@@ -3,8 +3,10 @@
 Everything is seeded (default 96, scripts/train_evimo.sh:7).  Plain host-side torch/numpy; no kernels involved.  The
 same dictionary feeds the CUDA modules (``build_pipeline``) and -- in tests/bench only -- the CPU oracle.
 
-The scene is a ball of radius 0.5 on a thin ground slab inside the [-1,1]^3 box, seen from 64 control poses on a
-circle of radius 1.5.  Two target modes:
+The scene is a ball of radius 0.5 on a thin ground slab inside the [-1,1]^3 box, enclosed by a textured dome of radius 3
+(an indoor scene like EVIMOv2's: no pixel is black, which the log-intensity event loss needs -- with a black background
+the clamp at 1e-5 is an absorbing state of the optimisation), seen from 64 control poses on a circle of radius 1.5.
+Two target modes:
   * ``targets="noise"``  : U(0,1) RGB and Poisson events (SURVEY 8d literally) -- used by the small parity tests;
   * ``targets="analytic"``: RGB frames ray-traced from the analytic scene and event frames = quantised log-intensity
     difference between consecutive event-camera poses, so that training is a consistent (learnable) problem.
@@ -27,6 +29,8 @@ from .interpolation_utils import matrix_to_tangent_vector
 GRAY = (0.2989, 0.5870, 0.1140)
 BALL_R = 0.5
 SLAB_Z = -0.03
+ROOM_R = 3.0                         # inner radius of the enclosing textured dome (every ray ends on a lit surface)
+ROOM_T = 0.8                         # thickness of the dome wall carried by the occupancy grid / density prior
 
 
 @dataclass
@@ -61,10 +65,20 @@ def look_at_c2w(pos: np.ndarray) -> np.ndarray:
 
 
 def inside_solid(p: torch.Tensor) -> torch.Tensor:
-    """analytic geometry: ball of radius 0.5 at the origin + ground slab |x|,|y| <= 1, z in [SLAB_Z-0.03, SLAB_Z]."""
-    ball = (p * p).sum(-1) <= BALL_R * BALL_R
+    """analytic geometry: ball of radius 0.5 at the origin + ground slab |x|,|y| <= 1, z in [SLAB_Z-0.03, SLAB_Z] + the
+    dome wall ROOM_R <= |p| <= ROOM_R + ROOM_T."""
+    r2 = (p * p).sum(-1)
+    ball = r2 <= BALL_R * BALL_R
     slab = (p[..., 0].abs() <= 1.0) & (p[..., 1].abs() <= 1.0) & (p[..., 2] <= SLAB_Z) & (p[..., 2] >= SLAB_Z - 0.03)
-    return ball | slab
+    room = (r2 >= ROOM_R * ROOM_R) & (r2 <= (ROOM_R + ROOM_T) ** 2)
+    return ball | slab | room
+
+
+def room_colour(n: torch.Tensor) -> torch.Tensor:
+    """smooth texture of the dome as a function of the unit direction n from the origin; values in [0.2, 0.8]."""
+    a = torch.sin(5.0 * n[..., 0]) * torch.cos(4.0 * n[..., 1])
+    b = torch.sin(3.0 * n[..., 2] + 2.0 * n[..., 0])
+    return torch.stack([0.5 + 0.3 * a, 0.5 + 0.3 * b, 0.5 - 0.15 * a - 0.15 * b], dim=-1)
 
 
 def trace_frame(c2w: torch.Tensor, H: int, W: int, intr) -> torch.Tensor:
@@ -83,7 +97,8 @@ def trace_frame(c2w: torch.Tensor, H: int, W: int, intr) -> torch.Tensor:
     t_slab = torch.where(d[..., 2] < 0, (SLAB_Z - o[2]) / d[..., 2].clamp(max=-1e-9), torch.full_like(b, float("inf")))
     ps = o + t_slab.clamp(max=1e6)[..., None] * d
     t_slab = torch.where((ps[..., 0].abs() <= 1.0) & (ps[..., 1].abs() <= 1.0) & (t_slab > 0), t_slab, torch.full_like(b, float("inf")))
-    img = torch.zeros(H, W, 3)
+    t_room = -b + torch.sqrt((b * b - ((o * o).sum() - ROOM_R * ROOM_R)).clamp(min=0))   # camera is inside the dome
+    img = room_colour((o + t_room[..., None] * d) / ROOM_R)
     hit_b = t_ball < t_slab
     n = (o + t_ball.clamp(max=1e6)[..., None] * d) / BALL_R
     img[hit_b] = (0.5 + 0.4 * n)[hit_b]
@@ -93,17 +108,23 @@ def trace_frame(c2w: torch.Tensor, H: int, W: int, intr) -> torch.Tensor:
     return img
 
 
-def evs_c2w_from_spline(scene: dict) -> torch.Tensor:
-    """Initial event-camera poses M_rgb(t) @ dM on the host (scipy slerp of the control poses); stored as the event
-    cameras' camera_to_worlds, which the 'ns' optimizer then refines through pose_adjustment."""
+def spline_c2w(scene: dict, times) -> np.ndarray:
+    """RGB-camera poses [n,4,4] (fp64) at `times` on the host: scipy slerp + lerp of the control poses, times clipped to
+    the control range like ns_camera_optimizer.py:130-147."""
     from scipy.spatial.transform import Rotation, Slerp
     ts = scene["ctrl_ts"].numpy().astype(np.float64)
     c2w = scene["col_c2w"].numpy().astype(np.float64)
-    q = scene["evs_times"].reshape(-1).numpy().astype(np.float64)
+    q = np.clip(np.asarray(times, dtype=np.float64).reshape(-1), ts[0], ts[-1])
     R = Slerp(ts, Rotation.from_matrix(c2w[:, :3, :3]))(q).as_matrix()
     t = np.stack([np.interp(q, ts, c2w[:, i, 3]) for i in range(3)], axis=1)
     M = np.concatenate([R, t[:, :, None]], axis=2)
-    M4 = np.concatenate([M, np.tile(np.array([[[0, 0, 0, 1.0]]]), (len(M), 1, 1))], axis=1)
+    return np.concatenate([M, np.tile(np.array([[[0, 0, 0, 1.0]]]), (len(M), 1, 1))], axis=1)
+
+
+def evs_c2w_from_spline(scene: dict) -> torch.Tensor:
+    """Initial event-camera poses M_rgb(t) @ dM on the host; stored as the event cameras' camera_to_worlds, which the
+    'ns' optimizer then refines through pose_adjustment."""
+    M4 = spline_c2w(scene, scene["evs_times"].numpy())
     return torch.from_numpy((M4 @ scene["dM"].numpy().astype(np.float64))[:, :3, :4].astype(np.float32))
 
 
@@ -137,7 +158,9 @@ def make_scene(spec: SceneSpec = SceneSpec(), images: bool = True) -> dict:
         cell = 2 * half / res
         ball = (X * X + Y * Y + Z * Z) <= (BALL_R + 0.5 * cell) ** 2
         slab = (X.abs() <= 1.0 + cell) & (Y.abs() <= 1.0 + cell) & ((Z - (SLAB_Z - 0.015)).abs() <= 0.015 + 0.5 * cell)
-        binaries[l] = ball | slab
+        rr = torch.sqrt(X * X + Y * Y + Z * Z)
+        room = (rr >= ROOM_R - 0.87 * cell) & (rr <= ROOM_R + ROOM_T + 0.87 * cell)
+        binaries[l] = ball | slab | room
     occs = 0.02 * binaries.flatten().float()
     n_ev = spec.n_evs_frames
     evs_times = torch.linspace(0.0, spec.t_end, n_ev + 1)
@@ -156,7 +179,14 @@ def make_scene(spec: SceneSpec = SceneSpec(), images: bool = True) -> dict:
         H, W = spec.col_hw
         He, We = spec.evs_hw
         if spec.targets == "analytic":
-            scene["col_images"] = torch.stack([trace_frame(scene["col_c2w"][i], H, W, scene["col_intr"]) for i in range(K)])
+            # motion-blurred RGB frames: the mean of the scene traced at the 4 virtual poses the deblur ray generator
+            # integrates over the exposure (ns_camera_optimizer.py:184-189), so target and model quadrature agree
+            frames = []
+            for i in range(K):
+                tq = float(ctrl_ts[i]) - spec.exp_t / 2 + np.arange(4) * spec.exp_t / 3
+                Ms = torch.from_numpy(spline_c2w(scene, tq)[:, :3, :4].astype(np.float32))
+                frames.append(torch.stack([trace_frame(M, H, W, scene["col_intr"]) for M in Ms]).mean(0))
+            scene["col_images"] = torch.stack(frames)
             gw = torch.tensor(GRAY)
             prev = torch.log(trace_frame(scene["evs_c2w0"][0], He, We, scene["evs_intr"]) @ gw + 1e-2)
             frames = []
