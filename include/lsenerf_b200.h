@@ -162,6 +162,17 @@ int lse_field_density_bwd(const LseFieldParams *p, const LseFieldGrads *g, const
                           const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                           int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
                           const float *d_h16, float *d_origins, float *d_directions, lse_stream_t stream);
+/* The same backward with caller-provided scratch memory (device, `lse_field_density_bwd_workspace(S_cap)` bytes, 256-byte
+ * aligned; may be NULL when p->use_tensor_cores == 0).  With tensor cores the work is split into three launches: re-encode
+ * of the samples at full occupancy (feat [S,32] into the workspace), base-MLP backward on tcgen05, table scatter +
+ * position gradients at full occupancy.  Replaces the same reference lines as lse_field_density_bwd (autograd of
+ * lse_field.py:264-288). */
+int64_t lse_field_density_bwd_workspace(int64_t S_cap);
+int lse_field_density_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                             const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                             int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                             const float *d_h16, float *d_origins, float *d_directions, void *workspace,
+                             int64_t workspace_bytes, lse_stream_t stream);
 /* rgb [S,3] = sigmoid(head(cat[SH16(dir), geo15, emb32])).  app_id int32 [n_rays] (per RAY) or NULL. */
 int lse_field_color_fwd(const LseFieldParams *p, const float *directions, const int32_t *ray_idx,
                         const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb,

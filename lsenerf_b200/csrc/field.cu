@@ -25,10 +25,6 @@ int tc_color_fwd(const LseFieldParams &P, const float *directions, const int32_t
 int tc_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *directions, const int32_t *ray_idx,
                  const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_rgb,
                  float *d_h16, float *d_directions, cudaStream_t st);
-int tc_density_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *origins, const float *directions,
-                   const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev,
-                   const float *h16, const float *d_sigma, const float *d_h16, float *d_origins, float *d_directions,
-                   cudaStream_t st);
 }  // namespace lse
 
 using namespace lse;
@@ -65,9 +61,8 @@ extern "C" int lse_field_density_bwd(const LseFieldParams *p, const LseFieldGrad
     LSE_CHECK_ARG(g && g->dW1 && g->db1 && g->dW2 && g->db2, "gradient buffers for the base MLP missing");
     LSE_CHECK_ARG(origins && h16, "origins / h16 missing");
     if (S_cap <= 0) return 0;
-    if (p->use_tensor_cores)
-        return tc_density_bwd(*p, *g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, d_h16, d_origins,
-                              d_directions, (cudaStream_t)stream);
+    // the tensor-core backward needs scratch memory for the re-encoded features (lse_field_density_bwd_ws); without a
+    // workspace the fp32 CUDA-core kernel computes the same gradients
     return simt_density_bwd(*p, *g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, d_h16, d_origins,
                             d_directions, (cudaStream_t)stream);
 }

@@ -1,0 +1,213 @@
+// field_hash.cu -- the hash-grid halves of the tensor-core density backward, as full-occupancy CUDA-core kernels, and the
+// C-ABI entry that chains them around the base-MLP backward (field_tc_bwd.cu):
+//
+//   encode_samples   (thread = kept sample)  positions -> feat [S,32] (16 levels x 8 float2 gathers, the same arithmetic as the
+//                                            forward), dout0 = d_sigma * d(trunc_exp)/d(raw) * selector
+//   density_mlp_bwd  (tcgen05)               feat, dout0, d_h16 -> dfeat [S,32], dW1, db1, dW2, db2
+//   scatter_samples  (thread = kept sample)  dfeat -> 128 RED.ADD.V2.F32 into the table gradient; d/dx of the trilinear blend
+//                                            (re-gather) -> contraction backward -> per-ray origin / direction gradients
+//
+// Why split: the gathers and reductions are latency bound and want 64 resident warps per SM; the MLP wants 227 KiB of
+// operand staging and all of TMEM (10 warps per SM).  Fused, the 4 compute warps of a tile serialise 256 dependent memory
+// round trips per sample behind the tensor pipe.  Split, feat and dfeat cross HBM once each (256 B per kept sample).
+#include "common.cuh"
+#include "math_field.cuh"
+#include "field_common.cuh"
+#include "../../include/lsenerf_b200.h"
+
+namespace lse {
+
+int tc_density_mlp_bwd(const LseFieldParams &P, const LseFieldGrads &G, int64_t S_cap, const int32_t *n_dev, const float *feat,
+                       const float *dout0, const float *d_h16, float *dfeat, cudaStream_t st);
+int simt_density_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *origins, const float *directions,
+                     const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev,
+                     const float *h16, const float *d_sigma, const float *d_h16, float *d_origins, float *d_directions,
+                     cudaStream_t st);
+
+constexpr int HT = 256;   // threads per CTA of the hash kernels
+
+__global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, const float *__restrict__ origins,
+                                                            const float *__restrict__ directions,
+                                                            const int32_t *__restrict__ ray_idx, const float *__restrict__ t0,
+                                                            const float *__restrict__ t1, int64_t S_cap,
+                                                            const int32_t *__restrict__ n_dev, const float *__restrict__ h16,
+                                                            const float *__restrict__ d_sigma, float *__restrict__ feat,
+                                                            float *__restrict__ dout0)
+{
+    __shared__ float s_scal[NL];
+    if (threadIdx.x < NL) s_scal[threadIdx.x] = P.scalings[threadIdx.x];
+    __syncthreads();
+    const int64_t S = live_count(n_dev, S_cap);
+    const float2 *table = reinterpret_cast<const float2 *>(P.table);
+    for (int64_t i = blockIdx.x * (int64_t)HT + threadIdx.x; i < S; i += (int64_t)gridDim.x * HT) {
+        SampleGeom g;
+        load_geom(i, origins, directions, ray_idx, t0, t1, g);
+        float f[NF];
+        encode(g.x, table, s_scal, P.log2_T, f);
+        float4 *o4 = reinterpret_cast<float4 *>(feat + 32 * i);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o4[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        const float gs = d_sigma ? d_sigma[i] : 0.0f;
+        dout0[i] = g.cc.sel ? gs * expf(fminf(fmaxf(h16[16 * i], -15.0f), 15.0f)) : 0.0f;
+    }
+}
+
+// ---- warp-aggregated reductions over runs of consecutive lanes with equal keys -----------------------------------------------
+// Samples are packed ray-major and a ray crosses a (convex) grid cell once, so the lanes of a warp that fall into the same cell of
+// a coarse level are consecutive.  `heads` = ballot of run starts; returns the last lane of this lane's run.
+__device__ __forceinline__ int run_last_lane(uint32_t heads, int lane)
+{
+    const uint32_t above = heads & ~((2u << lane) - 1u);     // run starts strictly above this lane (lane 31: 2u<<31 wraps to 0 -> none)
+    return lane == 31 ? 31 : (above ? __ffs(above) - 2 : 31);
+}
+// after the call the first lane of every run holds the sum over its run
+__device__ __forceinline__ float run_sum(float v, int lane, int last)
+{
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const float t = __shfl_down_sync(0xffffffffu, v, s);
+        if (lane + s <= last) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, float *__restrict__ d_table,
+                                                             const float *__restrict__ origins, const float *__restrict__ directions,
+                                                             const int32_t *__restrict__ ray_idx, const float *__restrict__ t0,
+                                                             const float *__restrict__ t1, int64_t S_cap,
+                                                             const int32_t *__restrict__ n_dev, const float *__restrict__ dfeat,
+                                                             float *__restrict__ d_origins, float *__restrict__ d_directions)
+{
+    __shared__ float s_scal[NL];
+    if (threadIdx.x < NL) s_scal[threadIdx.x] = P.scalings[threadIdx.x];
+    __syncthreads();
+    const int64_t S = live_count(n_dev, S_cap);
+    const float2 *table = reinterpret_cast<const float2 *>(P.table);
+    const uint32_t mask = (1u << P.log2_T) - 1u;
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count: every lane of a warp takes part in the shuffles
+    for (int64_t base = blockIdx.x * (int64_t)HT + (threadIdx.x & ~31); base < S; base += (int64_t)gridDim.x * HT) {
+        const int64_t i = base + lane;
+        const bool live = i < S;
+        SampleGeom g;
+        g.cc.sel = false; g.has_dir = false; g.tmid = 0.0f; g.ray = -1 - lane;
+        g.x[0] = g.x[1] = g.x[2] = 0.0f;
+        float df[NF];
+        if (live) {
+            load_geom(i, origins, directions, ray_idx, t0, t1, g);
+            const float4 *f4 = reinterpret_cast<const float4 *>(dfeat + 32 * i);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { float4 t = f4[q]; df[4 * q] = t.x; df[4 * q + 1] = t.y; df[4 * q + 2] = t.z; df[4 * q + 3] = t.w; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NF; ++j) df[j] = 0.0f;
+        }
+        const bool want_dx = live && (d_origins != nullptr || d_directions != nullptr) && g.cc.sel;
+        float dx[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            HashCell hc;
+            hash_cell(g.x, s_scal[l], mask, hc);
+            const float gl[2] = {df[2 * l], df[2 * l + 1]};
+            if (d_table) {
+                float w[8];
+                hash_weights(hc, w);
+                float *dtl = d_table + (((size_t)l << P.log2_T) * 2);
+                // run key: the cell (floor corner) and whether each axis sits on the lattice (ceil == floor); equal keys <=> all 8
+                // corner rows equal.  Dead lanes get a key no live lane has.
+                const float sx = rn_mul(g.x[0], s_scal[l]), sy = rn_mul(g.x[1], s_scal[l]), sz = rn_mul(g.x[2], s_scal[l]);
+                const uint32_t fx = (uint32_t)(int32_t)floorf(sx), fy = (uint32_t)(int32_t)floorf(sy), fz = (uint32_t)(int32_t)floorf(sz);
+                const uint32_t onl = (ceilf(sx) == floorf(sx) ? 1u : 0u) | (ceilf(sy) == floorf(sy) ? 2u : 0u) | (ceilf(sz) == floorf(sz) ? 4u : 0u);
+                const uint32_t k0 = live ? (fx | (fy << 12) | (fz << 24)) : 0xFFFFFFFFu;
+                const uint32_t k1 = live ? ((fz >> 8) | (onl << 4)) : (uint32_t)lane;
+                const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
+                const bool head = lane == 0 || p0 != k0 || p1 != k1;
+                const uint32_t heads = __ballot_sync(0xffffffffu, head);
+                if (__popc(heads) <= 20) {          // coarse level: few cells per warp -> one reduction per run
+                    const int last = run_last_lane(heads, lane);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float a = run_sum(w[c] * gl[0], lane, last), b = run_sum(w[c] * gl[1], lane, last);
+                        if (head && live) red_add2(dtl + 2 * (size_t)hc.idx[c], a, b);
+                    }
+                } else if (live) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) red_add2(dtl + 2 * (size_t)hc.idx[c], w[c] * gl[0], w[c] * gl[1]);
+                }
+            }
+            if (want_dx) {
+                const float2 *__restrict__ tl = table + ((size_t)l << P.log2_T);
+                float F[8][2];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { float2 v = __ldg(tl + hc.idx[c]); F[c][0] = v.x; F[c][1] = v.y; }
+                float d3[3];
+                hash_blend_dx(F, hc, gl, d3);
+                const float sc = s_scal[l];
+                dx[0] = fmaf(d3[0], sc, dx[0]); dx[1] = fmaf(d3[1], sc, dx[1]); dx[2] = fmaf(d3[2], sc, dx[2]);
+            }
+        }
+        if (d_origins != nullptr || d_directions != nullptr) {
+            // per-ray gradients: one reduction per run of lanes on the same ray
+            float dp[3] = {0.0f, 0.0f, 0.0f};
+            if (want_dx) contract_normalize_bwd(g.p, g.cc, dx, dp);
+            const int32_t rkey = live ? (ray_idx ? g.ray : (int32_t)(i & 0x7fffffff)) : -1 - lane;
+            const int32_t pk = __shfl_up_sync(0xffffffffu, rkey, 1);
+            const bool head = lane == 0 || pk != rkey;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            const int last = run_last_lane(heads, lane);
+            const int64_t r = ray_idx ? (int64_t)g.ray : i;
+            const float tm = g.has_dir ? g.tmid : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float so = run_sum(dp[j], lane, last), sd = run_sum(dp[j] * tm, lane, last);
+                if (head && live) {
+                    if (d_origins) red_add(d_origins + 3 * r + j, so);
+                    if (d_directions && directions) red_add(d_directions + 3 * r + j, sd);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace lse
+
+using namespace lse;
+
+extern "C" int64_t lse_field_density_bwd_workspace(int64_t S_cap)
+{
+    // feat [S,32] + dfeat [S,32] + dout0 [S], fp32, each 256-byte aligned
+    const int64_t s = S_cap < 1 ? 1 : S_cap;
+    return ((s * 32 * 4 + 255) / 256 * 256) * 2 + (s * 4 + 255) / 256 * 256;
+}
+
+extern "C" int lse_field_density_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                                        const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                                        int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                                        const float *d_h16, float *d_origins, float *d_directions, void *workspace,
+                                        int64_t workspace_bytes, lse_stream_t stream)
+{
+    if (!p) { set_error("%s: params is NULL", __func__); return -22; }
+    LSE_CHECK_ARG(p->levels == 16 && p->log2_T >= 4 && p->log2_T <= 28 && p->table && p->scalings, "bad hash-grid parameters");
+    LSE_CHECK_ARG(p->W1 && p->b1 && p->W2 && p->b2, "base MLP weights missing");
+    LSE_CHECK_ARG(g && g->dW1 && g->db1 && g->dW2 && g->db2, "gradient buffers for the base MLP missing");
+    LSE_CHECK_ARG(origins && h16, "origins / h16 missing");
+    if (S_cap <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p->use_tensor_cores)
+        return simt_density_bwd(*p, *g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, d_h16, d_origins,
+                                d_directions, st);
+    LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
+    const int64_t fbytes = (S_cap * 32 * 4 + 255) / 256 * 256;
+    float *feat = reinterpret_cast<float *>(workspace);
+    float *dfeat = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + fbytes);
+    float *dout0 = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + 2 * fbytes);
+    const int grid = stride_grid(S_cap, HT, 8);
+    encode_samples_kernel<<<grid, HT, 0, st>>>(*p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, feat, dout0);
+    int rc = check_launch("lse_field_density_bwd_ws[encode]");
+    if (rc) return rc;
+    rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, feat, dout0, d_h16, dfeat, st);
+    if (rc) return rc;
+    scatter_samples_kernel<<<grid, HT, 0, st>>>(*p, g->d_table, origins, directions, ray_idx, t0, t1, S_cap, n_dev, dfeat, d_origins,
+                                                d_directions);
+    return check_launch("lse_field_density_bwd_ws[scatter]");
+}

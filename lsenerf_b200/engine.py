@@ -231,6 +231,7 @@ class GraphedStep:
         """one training iteration; returns the (device) loss vector.  Either a pre-staged packed device batch or host
         batches from MultiCamManager.sample_host_batches()."""
         self.pipeline.model.update_occupancy(self.step_no)       # eager, every 16th step
+        self.pipeline.model.occupancy_grid.packed()              # host-side version check; repacks only if binaries were edited
         if packed_dev is not None:
             self.stage.load_packed(packed_dev)
         else:

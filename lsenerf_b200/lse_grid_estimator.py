@@ -26,9 +26,26 @@ class LSEOccGridEstimator(nn.Module):
         # (lse_grid_estimator.py:112); here it is refreshed by the grid-update kernel and read on the device.
         self.register_buffer("occ_mean", torch.zeros(1), persistent=False)
         self._mean_valid = False
+        # bit-packed copy of `binaries` + 8^3-superblock mip read by the marching kernels; repacked when the grid changes
+        self._bits: Optional[Tensor] = None
+        self._mip: Optional[Tensor] = None
+        self._packed_key = None
 
     def binaries_u8(self) -> Tensor:
         return self.binaries.view(torch.uint8)
+
+    def packed(self, force: bool = False) -> Tuple[Tensor, Tensor]:
+        """(bits, mip) of the current `binaries`.  The tensors are persistent (CUDA-graph safe) and rewritten in place
+        whenever `binaries` was modified through torch (version counter) or by the grid-update kernel (force)."""
+        b = self.binaries
+        key = (b.data_ptr(), b._version, str(b.device))
+        if self._bits is None or self._bits.device != b.device:
+            self._bits, self._mip = ops.occ_pack_alloc(self.levels, self.res, b.device)
+            force = True
+        if force or key != self._packed_key:
+            ops.occ_pack(self.binaries_u8(), self._bits, self._mip)
+            self._packed_key = (b.data_ptr(), b._version, str(b.device))
+        return self._bits, self._mip
 
     def refresh_occ_mean(self):
         self.occ_mean.copy_(self.occs.mean().reshape(1))
@@ -53,7 +70,7 @@ class LSEOccGridEstimator(nn.Module):
         if stratified and jitter is None:
             jitter = torch.rand(R, device=rays_o.device)
         m = ops.march(rays_o, rays_d, self.binaries_u8(), self.aabbs, near_plane, far_plane, render_step_size, cone_angle,
-                      jitter if stratified else None, max(1, R * samples_per_ray_cap))
+                      jitter if stratified else None, max(1, R * samples_per_ray_cap), packed=self.packed())
         n = int(m.total.item())
         if int(m.overflow.item()):
             raise RuntimeError("sample capacity exceeded: raise samples_per_ray_cap")
@@ -95,3 +112,4 @@ class LSEOccGridEstimator(nn.Module):
         ops.occ_update(self.occs, torch.cat(idx_all).contiguous(), torch.cat(occ_all).contiguous().float(), self.binaries_u8(),
                        self.occ_mean, ema_decay, occ_thre)
         self._mean_valid = True
+        self.packed(force=True)

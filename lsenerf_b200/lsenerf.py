@@ -160,7 +160,7 @@ class LSENeRFModel(nn.Module):
 
     def _render_opts(self) -> ops.RenderOpts:
         c, g = self.config, self.occupancy_grid
-        return ops.RenderOpts(binaries_u8=g.binaries_u8(), aabbs=g.aabbs, occ_mean_dev=g.occ_mean_dev(), near=c.near_plane,
+        return ops.RenderOpts(binaries_u8=g.binaries_u8(), aabbs=g.aabbs, occ_mean_dev=g.occ_mean_dev(), occ_packed=g.packed(), near=c.near_plane,
                               far=c.far_plane, step=float(c.render_step_size), cone=c.cone_angle, alpha_thre=c.alpha_thre,
                               early_stop_eps=1e-4, cull=self.training, samples_per_ray_cap=c.samples_per_ray_cap)
 

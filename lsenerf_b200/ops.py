@@ -154,19 +154,33 @@ def scan_counts(counts: Tensor):
     return starts, total
 
 
-def march(rays_o, rays_d, binaries_u8, aabbs, near, far, step, cone, jitter: Optional[Tensor], S_cap: int) -> MarchResult:
-    """traverse_grids (lse_grid_estimator.py:83-106) without a host sync: capacity-bounded packed output."""
+def occ_pack_alloc(levels: int, res: int, dev):
+    n_cells = levels * res * res * res
+    bits = torch.empty(n_cells // 32, dtype=torch.int32, device=dev)
+    mip = torch.empty((levels * (res // 8) ** 3 + 31) // 32, dtype=torch.int32, device=dev)
+    return bits, mip
+
+
+def occ_pack(binaries_u8: Tensor, bits: Tensor, mip: Tensor) -> None:
+    """bit-pack the occupancy bytes + 8^3-superblock mip (8 MiB read) for the marching kernels."""
+    call("lse_occ_pack", P(binaries_u8), binaries_u8.shape[0], binaries_u8.shape[1], P(bits), P(mip), stream())
+
+
+def march(rays_o, rays_d, binaries_u8, aabbs, near, far, step, cone, jitter: Optional[Tensor], S_cap: int,
+          packed: Optional[tuple] = None) -> MarchResult:
+    """traverse_grids (lse_grid_estimator.py:83-106) without a host sync: capacity-bounded packed output.
+    packed: (bits, mip) from LSEOccGridEstimator.packed(); packed here from `binaries_u8` when absent."""
     o = _f32(rays_o.detach(), "rays_o"); d = _f32(rays_d.detach(), "rays_d")
     R = o.shape[0]
     dev = o.device
     levels, res = binaries_u8.shape[0], binaries_u8.shape[1]
     counts = torch.empty(R, dtype=torch.int32, device=dev)
     jit = _f32(jitter, "jitter") if jitter is not None else None
-    # bit-pack the occupancy bytes + superblock mip (8 MiB read, ~2 us) -- always fresh, binaries may be edited by anyone
-    n_cells = levels * res * res * res
-    bits = torch.empty(n_cells // 32, dtype=torch.int32, device=dev)
-    mip = torch.empty((levels * (res // 8) ** 3 + 31) // 32, dtype=torch.int32, device=dev)
-    call("lse_occ_pack", P(binaries_u8), levels, res, P(bits), P(mip), stream())
+    if packed is None:
+        bits, mip = occ_pack_alloc(levels, res, dev)
+        occ_pack(binaries_u8, bits, mip)
+    else:
+        bits, mip = packed
     call("lse_march_count", P(o), P(d), R, P(bits), P(mip), P(aabbs), levels, res, near, far, P(jit), step, cone, P(counts), stream())
     starts, total = scan_counts(counts)
     ri = torch.empty(S_cap, dtype=torch.int32, device=dev)
@@ -295,6 +309,16 @@ def field_color_raw(fw: FieldWeights, directions, ray_idx, app_id, S_cap, n_dev,
     return rgb
 
 
+def _density_bwd(fw: FieldWeights, cp, cg, o, d, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, d_h16, g_o, g_d):
+    """lse_field_density_bwd_ws: with tensor cores the library needs scratch for feat / dfeat (re-encode -> MLP -> scatter)."""
+    ws, nbytes = None, 0
+    if fw.use_tensor_cores:
+        nbytes = int(_lib.lib().lse_field_density_bwd_workspace(S_cap))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=o.device)
+    call("lse_field_density_bwd_ws", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(ray_idx), P(t0), P(t1), S_cap, P(n_dev),
+         P(h16), P(d_sigma), P(d_h16), P(g_o), P(g_d), P(ws), nbytes, stream())
+
+
 _DENS_KEYS = ("table", "W1", "b1", "W2", "b2")
 _COL_KEYS = ("W3", "b3", "W4", "b4", "W5", "b5")
 
@@ -325,10 +349,9 @@ class _FieldDensity(torch.autograd.Function):
         g_o = torch.zeros_like(o) if need_o else None
         g_d = torch.zeros_like(o) if need_d else None
         cp = fw.c_params(); cg = _grads_struct(fw, bufs)
-        call("lse_field_density_bwd", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d) if has_d else None, None,
-             P(t0) if has_t else None, P(t1) if has_t else None, S, None, P(h16),
-             P(d_sigma.contiguous()) if d_sigma is not None else None, P(d_h16.contiguous()) if d_h16 is not None else None,
-             P(g_o), P(g_d), stream())
+        _density_bwd(fw, cp, cg, o, d if has_d else None, None, t0 if has_t else None, t1 if has_t else None, S, None, h16,
+                     d_sigma.contiguous() if d_sigma is not None else None, d_h16.contiguous() if d_h16 is not None else None,
+                     g_o, g_d)
         return g_o, g_d, None, None, None, bufs["table"], bufs["W1"], bufs["b1"], bufs["W2"], bufs["b2"]
 
 
@@ -420,6 +443,7 @@ class RenderOpts:
     binaries_u8: Tensor
     aabbs: Tensor
     occ_mean_dev: Optional[Tensor]
+    occ_packed: Optional[tuple] = None  # (bits, mip) of binaries_u8 (LSEOccGridEstimator.packed()); packed per call when None
     near: float = 0.05
     far: float = 1e3
     step: float = (12.0 ** 0.5) / 1000.0
@@ -439,7 +463,7 @@ class _RenderRays(torch.autograd.Function):
         o = _f32(origins, "origins"); d = _f32(directions, "directions")
         R = o.shape[0]
         S_cap = max(1, R * opts.samples_per_ray_cap)
-        m0 = march(o, d, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step, opts.cone, jitter, S_cap)
+        m0 = march(o, d, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step, opts.cone, jitter, S_cap, opts.occ_packed)
         sigma, h16 = field_density_raw(fw, o, d, m0.ray_indices, m0.t_starts, m0.t_ends, S_cap, m0.total)
         if opts.cull and (opts.alpha_thre > 0.0 or opts.early_stop_eps > 0.0):
             m, sigma_c, h16_c, keep = visibility_compact(m0, sigma, h16, opts.early_stop_eps, opts.alpha_thre, opts.occ_mean_dev)
@@ -498,8 +522,8 @@ class _RenderRays(torch.autograd.Function):
         cp = fw.c_params(); cg = _grads_struct(fw, bufs)
         call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
              P(h16), P(d_rgb), P(d_h16), P(g_d) if need_d else None, stream())
-        call("lse_field_density_bwd", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts), P(m.t_ends),
-             S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(g_d) if need_d else None, stream())
+        _density_bwd(fw, cp, cg, o, d, m.ray_indices, m.t_starts, m.t_ends, S_cap, m.total, h16, d_sigma, d_h16, g_o,
+                     g_d if need_d else None)
         return (g_o, g_d if need_d else None, None, None, None, None, *[ret[k] for k in names])
 
 
