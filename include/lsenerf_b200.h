@@ -73,7 +73,7 @@ int lse_pose_delta_bwd(const float *pose_adjustment, int64_t n_cams, const int64
  * ------------------------------------------------------------------------------------------------- */
 
 /* Pack the byte occupancy tensor (nerfacc `binaries` [levels,res,res,res] bool) into 1 bit per cell (occ_bits,
- * levels*res^3/32 words) plus an any-occupied mip over 8^3 superblocks (occ_mip, ceil(levels*(res/8)^3/32) words) that
+ * levels*res^3/32 words; brick-major: one 64-bit word per 4x4x4 brick of cells, opaque to the caller) plus an any-occupied mip over 8^3 superblocks (occ_mip, ceil(levels*(res/8)^3/32) words) that
  * the marching kernels keep in shared memory.  res % 32 == 0. */
 int lse_occ_pack(const uint8_t *binaries, int levels, int res, uint32_t *occ_bits, uint32_t *occ_mip, lse_stream_t stream);
 
@@ -90,6 +90,22 @@ int lse_march_fill(const float *rays_o, const float *rays_d, int64_t n_rays, con
                    const uint32_t *occ_mip, const float *aabbs, int levels, int res, float near_plane, float far_plane,
                    const float *jitter, float step_size, float cone_angle, const int32_t *starts, int64_t S_cap,
                    int32_t *ray_indices, float *t_starts, float *t_ends, int32_t *overflow_dev, lse_stream_t stream);
+/* Single-pass variant of count+fill (same samples, bit for bit).  Kernel 1 (thread = ray x level segment) runs the DDA and
+ * collapses consecutive cells of equal occupancy into (bound, occupied) runs in `workspace`
+ * (`lse_march_workspace(n_rays, levels, res)` bytes); kernel 2 (thread = ray) replays the sample-step recurrence once against the
+ * runs and writes (t_start, t_end) pairs to per-ray slabs `slabs` [n_rays, max_per_ray, 2] fp32 (max_per_ray >= the longest
+ * possible ray, 1024 for the default cone/step); counts[r] = samples of ray r (clamped to max_per_ray, *overflow_dev = 1 if
+ * clamped).  lse_scan_counts + lse_march_pack then produce the packed ray-major (ray_indices, t_starts, t_ends) of
+ * lse_march_fill. */
+int64_t lse_march_workspace(int64_t n_rays, int levels, int res);
+int lse_march_single(const float *rays_o, const float *rays_d, int64_t n_rays, const uint32_t *occ_bits,
+                     const uint32_t *occ_mip, const float *aabbs, int levels, int res, float near_plane,
+                     float far_plane, const float *jitter, float step_size, float cone_angle, float *slabs,
+                     int max_per_ray, int32_t *counts, int32_t *overflow_dev, void *workspace, int64_t workspace_bytes,
+                     lse_stream_t stream);
+int lse_march_pack(const float *slabs, int max_per_ray, const int32_t *counts, const int32_t *starts, int64_t n_rays,
+                   int64_t S_cap, int32_t *ray_indices, float *t_starts, float *t_ends, int32_t *overflow_dev,
+                   lse_stream_t stream);
 
 /* 3P nerfacc.render_visibility_from_density (lse_nerf/lse_grid_estimator.py:109-127,139-143):
  * per ray, T = exp(-exclusive_sum(sigma*dt)), alpha = 1-exp(-sigma*dt), keep = T >= early_stop_eps &&

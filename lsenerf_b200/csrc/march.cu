@@ -26,35 +26,32 @@ struct FillEmit {
     }
 };
 
-// pack binaries (bytes) -> 1 bit per cell + any-occupied mip over 8^3 superblocks (mip must be zeroed beforehand)
-__global__ void occ_pack_kernel(const uint8_t *__restrict__ binaries, int levels, int res, uint32_t *__restrict__ bits,
+// pack binaries (bytes) -> 1 bit per cell, BRICK-major: one 64-bit word per 4x4x4 brick of cells (bit = (x&3)<<4 | (y&3)<<2 | z&3;
+// word index = ((level*res/4 + x/4)*res/4 + y/4)*res/4 + z/4), so a ray reads one word per ~5 visited cells instead of one per
+// cell; plus an any-occupied mip over 8^3 superblocks (mip must be zeroed beforehand)
+__global__ void occ_pack_kernel(const uint8_t *__restrict__ binaries, int levels, int res, uint64_t *__restrict__ bits,
                                 uint32_t *__restrict__ mip)
 {
-    const int64_t n_words = ((int64_t)levels * res * res * res) >> 5;
-    const int sb = res >> 3;
-    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(binaries + (w << 5));
-        uint4 a = src[0], b = src[1];
-        uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t word = 0;
+    const int rb = res >> 2, sb = res >> 3;
+    const int64_t n_bricks = (int64_t)levels * rb * rb * rb;
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_bricks; w += (int64_t)gridDim.x * blockDim.x) {
+        const int bz = (int)(w % rb), by = (int)((w / rb) % rb), bx = (int)((w / ((int64_t)rb * rb)) % rb);
+        const int level = (int)(w / ((int64_t)rb * rb * rb));
+        uint64_t word = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int dx = 0; dx < 4; ++dx)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((v[q] >> (8 * k)) & 0xFFu) word |= 1u << (4 * q + k);
+            for (int dy = 0; dy < 4; ++dy) {
+                const int64_t cell = (int64_t)level * res * res * res + ((int64_t)(4 * bx + dx) * res + (4 * by + dy)) * res + 4 * bz;
+                const uint32_t v = *reinterpret_cast<const uint32_t *>(binaries + cell);
+#pragma unroll
+                for (int dz = 0; dz < 4; ++dz)
+                    if ((v >> (8 * dz)) & 0xFFu) word |= 1ull << ((dx << 4) | (dy << 2) | dz);
+            }
         bits[w] = word;
         if (word) {
-            // the 32 cells of a word share x, y and z/32; they span 4 superblocks along z
-            const int64_t cell = w << 5;
-            const int z0 = (int)(cell % res), y = (int)((cell / res) % res), x = (int)((cell / ((int64_t)res * res)) % res);
-            const int level = (int)(cell / ((int64_t)res * res * res));
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if ((word >> (8 * q)) & 0xFFu) {
-                    const int m = ((level * sb + (x >> 3)) * sb + (y >> 3)) * sb + ((z0 + 8 * q) >> 3);
-                    atomicOr(mip + (m >> 5), 1u << (m & 31));
-                }
-            }
+            const int m = ((level * sb + (bx >> 1)) * sb + (by >> 1)) * sb + (bz >> 1);
+            atomicOr(mip + (m >> 5), 1u << (m & 31));
         }
     }
 }
@@ -81,7 +78,7 @@ __global__ void march_kernel(const float *__restrict__ rays_o, const float *__re
     for (int i = threadIdx.x; i < 6 * levels; i += blockDim.x) s_aabb[i] = aabbs[i];
     for (int i = threadIdx.x; i < mip_words; i += blockDim.x) s_mip[i] = mip[i];
     __syncthreads();
-    const OccBits occ{bits, s_mip, res};
+    const OccBits occ{reinterpret_cast<const uint64_t *>(bits), s_mip, res};
     // kRayStride lanes per ray: a warp marches only 32/kRayStride rays.  The rays of a warp are incoherent (random pixels of
     // random cameras), so lanes wait on each other's data-dependent loops, and with one thread per ray the whole chip holds
     // 256 warps (< 1 per scheduler): spreading the rays over 4x more warps cuts the divergence and lets the schedulers
@@ -99,6 +96,246 @@ __global__ void march_kernel(const float *__restrict__ rays_o, const float *__re
             FillEmit e{t_starts, t_ends, ray_indices, (int32_t)r, (int64_t)starts[r], S_cap, 0};
             int n = march_ray(o, d, occ, s_aabb, levels, res, nearp, far_plane, step_size, cone_angle, e);
             if ((int64_t)starts[r] + n > S_cap && overflow) *overflow = 1;
+        }
+    }
+}
+
+// ---- single-pass marching ------------------------------------------------------------------------------------------------------
+// The nested loops of traverse_grids (math_march.cuh:march_ray) interleave two sequential fp32 recurrences: the DDA over grid
+// cells (tdist += delta) and the sample stepping (t += clamp(t*cone, step)).  They only meet in the comparison
+// "t + dt/2 >= t_trav(cell)", and t_trav is non-decreasing along the ray, so step k is emitted iff the first visited cell
+// with t_trav > mid_k is occupied.  Consecutive cells of equal occupancy therefore collapse into one RUN bounded by the
+// t_trav of its last cell.  Two kernels, each a flat loop whose lanes stay in lockstep:
+//   march_runs_kernel  thread = (ray, level segment): the segments between the sorted box-crossing events start their DDA
+//                      from scratch, so they are independent; each writes its (bound | occupied-bit) runs to HBM.
+//   march_steps_kernel thread = ray: ONE step of the t recurrence per loop iteration against the run list, samples written to
+//                      a per-ray slab of `max_per_ray` slots (no count pass); lse_march_pack packs the slabs ray-major.
+// Both replay exactly the reference's operations on tdist and t, so (t_start, t_end) stay bit-identical.
+// a segment visits at most 3*(res-1)+1 cells, so 3*res run slots per (ray, segment) always suffice
+__host__ __device__ inline int run_cap(int res) { return 3 * res; }
+
+struct RayEvents {
+    float tv[2 * kMaxLevels]; int ti[2 * kMaxLevels]; bool hits[kMaxLevels]; float inv[3];
+};
+__device__ __forceinline__ void ray_events(const float o[3], const float d[3], const float *aabbs, int levels, RayEvents &E)
+{
+    E.inv[0] = rn_div(1.0f, d[0]); E.inv[1] = rn_div(1.0f, d[1]); E.inv[2] = rn_div(1.0f, d[2]);
+    for (int l = 0; l < levels; ++l) {
+        float t0, t1;
+        E.hits[l] = slab_hit(o, E.inv, aabbs + 6 * l, aabbs + 6 * l + 3, t0, t1);
+        E.tv[l] = E.hits[l] ? t0 : INFINITY;
+        E.tv[levels + l] = E.hits[l] ? t1 : INFINITY;
+    }
+    const int n_ev = 2 * levels;
+    for (int i = 0; i < n_ev; ++i) E.ti[i] = i;
+    for (int i = 1; i < n_ev; ++i) {  // stable insertion sort
+        float kv = E.tv[i]; int ki = E.ti[i]; int j = i - 1;
+        while (j >= 0 && E.tv[j] > kv) { E.tv[j + 1] = E.tv[j]; E.ti[j + 1] = E.ti[j]; --j; }
+        E.tv[j + 1] = kv; E.ti[j + 1] = ki;
+    }
+}
+
+constexpr int kMarchThreads = 128;
+
+__global__ void __launch_bounds__(kMarchThreads) march_runs_kernel(
+    const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n_rays, const uint32_t *__restrict__ bits,
+    const uint32_t *__restrict__ mip, int mip_words, const float *__restrict__ aabbs, int levels, int res, float near_plane,
+    float far_plane, const float *__restrict__ jitter, float step_size, uint32_t *__restrict__ runs, int32_t *__restrict__ n_runs)
+{
+    __shared__ float s_aabb[6 * kMaxLevels];
+    __shared__ uint32_t s_mip[kMaxMipWords];
+    for (int i = threadIdx.x; i < 6 * levels; i += blockDim.x) s_aabb[i] = aabbs[i];
+    for (int i = threadIdx.x; i < mip_words; i += blockDim.x) s_mip[i] = mip[i];
+    __syncthreads();
+    OccBrickCache occ{reinterpret_cast<const uint64_t *>(bits), s_mip, res, -1, 0ull};
+    const int n_slots = 2 * levels - 1, cap = run_cap(res);
+    const float eps = 1e-6f, resf = (float)res;
+    // consecutive threads = consecutive rays of the SAME segment slot: coalesced ray loads, similar trip counts in a warp
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_rays * n_slots; w += (int64_t)gridDim.x * blockDim.x) {
+        const int slot = (int)(w / n_rays);
+        const int64_t r = w % n_rays;
+        const float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
+        const float d[3] = {rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]};
+        const float nearp = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
+        RayEvents E;
+        ray_events(o, d, s_aabb, levels, E);
+        uint32_t *out = runs + (r * n_slots + slot) * (int64_t)cap;
+        int k = 0;
+        // segment `slot` = between sorted events slot and slot+1 (math_march.cuh:march_ray, outer loop body)
+        bool valid = true;
+        int lv = E.ti[slot] % levels;
+        if (!E.hits[lv]) valid = false;
+        if (valid && !(E.ti[slot] < levels)) {
+            const int next_level = E.ti[slot + 1] % levels;
+            if (next_level <= lv) valid = false;
+            lv = next_level;
+        }
+        const float tmin = fmaxf(E.tv[slot], nearp);
+        const float tmax = fminf(E.tv[slot + 1], far_plane);
+        if (tmin >= tmax) valid = false;
+        if (valid) {
+            const float *bmin = s_aabb + 6 * lv, *bmax = bmin + 3;
+            float tdist[3], delta[3]; int cur[3], stp[3], ovf[3];
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                float ext = rn_sub(bmax[ax], bmin[ax]);
+                float voxel = rn_div(ext, resf);
+                float s = rn_add(o[ax], rn_mul(d[ax], rn_add(tmin, eps)));
+                float e = rn_add(o[ax], rn_mul(d[ax], rn_sub(tmax, eps)));
+                int q0 = (int)rn_mul(rn_div(rn_sub(s, bmin[ax]), ext), resf);
+                int q1 = (int)rn_mul(rn_div(rn_sub(e, bmin[ax]), ext), resf);
+                cur[ax] = q0 < 0 ? 0 : (q0 > res - 1 ? res - 1 : q0);
+                int fin = q1 < 0 ? 0 : (q1 > res - 1 ? res - 1 : q1);
+                int idelta = d[ax] > 0.0f ? 1 : 0;
+                float edge = rn_mul((float)(cur[ax] + idelta), voxel);
+                float tm = rn_add(rn_mul(rn_add(bmin[ax], rn_sub(edge, s)), E.inv[ax]), tmin);
+                float sf = (d[ax] == 0.0f) ? 0.0f : (d[ax] > 0.0f ? 1.0f : -1.0f);
+                tdist[ax] = (d[ax] == 0.0f) ? tmax : tm;
+                stp[ax] = (int)sf;
+                float dl = rn_mul(rn_mul(voxel, E.inv[ax]), sf);
+                delta[ax] = (d[ax] == 0.0f) ? tmax : dl;
+                ovf[ax] = fin + stp[ax];
+            }
+            float td0 = tdist[0], td1 = tdist[1], td2 = tdist[2];
+            const float dl0 = delta[0], dl1 = delta[1], dl2 = delta[2];
+            int c0 = cur[0], c1 = cur[1], c2 = cur[2];
+            const int s0 = stp[0], s1 = stp[1], s2 = stp[2], v0 = ovf[0], v1 = ovf[1], v2 = ovf[2];
+            bool have_run = false, run_occ = false, more = true;
+            float run_bound = 0.0f;
+            while (more) {
+                const float t_trav = fminf(fminf(td0, fminf(td1, td2)), tmax);
+                const bool oc = occ.lookup(lv, c0, c1, c2);
+                if (have_run && oc != run_occ) {
+                    if (k < cap) out[k] = __float_as_uint(run_bound) | (run_occ ? 0x80000000u : 0u);
+                    ++k;
+                }
+                run_occ = oc; have_run = true; run_bound = t_trav;
+                const bool a0 = td0 < td1 && td0 < td2;
+                const bool a1 = !a0 && td1 < td2;
+                if (a0)      { c0 += s0; td0 = rn_add(td0, dl0); more = c0 != v0; }
+                else if (a1) { c1 += s1; td1 = rn_add(td1, dl1); more = c1 != v1; }
+                else         { c2 += s2; td2 = rn_add(td2, dl2); more = c2 != v2; }
+            }
+            if (k < cap) out[k] = __float_as_uint(run_bound) | (run_occ ? 0x80000000u : 0u);
+            ++k;
+        }
+        n_runs[r * n_slots + slot] = k <= cap ? k : -1;   // -1 cannot happen: cap >= the cells of a segment
+    }
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS) and its group bookkeeping
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kRing = 8;   // 16-byte chunks (4 runs each) in flight per ray
+
+__global__ void __launch_bounds__(kMarchThreads) march_steps_kernel(
+    int64_t n_rays, int levels, int res, float near_plane, const float *__restrict__ jitter, float step_size, float cone_angle,
+    const uint32_t *__restrict__ runs, const int32_t *__restrict__ n_runs, float2 *__restrict__ slabs, int max_per_ray,
+    int32_t *__restrict__ counts, int32_t *__restrict__ overflow, int lanes_per_ray)
+{
+    // Per-thread ring of run chunks filled by cp.async kRing chunks ahead of the consumer, so the (L2) latency of the run list
+    // never sits on the t recurrence.  The ring streams the chunks of the ray's non-empty segments back to back; layout
+    // [chunk][thread] keeps the 16-byte accesses conflict-free.  ONE flat loop per ray: every iteration either takes one step
+    // of the t recurrence or moves to the next run, so the 32 rays of a warp stay in lockstep whatever their segment structure.
+    __shared__ uint4 s_ring[kRing][kMarchThreads];
+    __shared__ int16_t s_cnt[2 * kMaxLevels][kMarchThreads];
+    const int n_slots = 2 * levels - 1, cap = run_cap(res);
+    const int tid = threadIdx.x;
+    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (gtid % lanes_per_ray != 0) return;
+    for (int64_t r = gtid / lanes_per_ray; r < n_rays; r += ((int64_t)gridDim.x * blockDim.x) / lanes_per_ray) {
+        const float nearp = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
+        const uint4 *src = reinterpret_cast<const uint4 *>(runs + r * n_slots * (int64_t)cap);   // slot s starts at chunk s*cap/4
+        const int slot_chunks = cap >> 2;
+        float2 *slab = slabs + r * (int64_t)max_per_ray;
+        for (int sl = 0; sl < n_slots; ++sl) { const int c = n_runs[r * n_slots + sl]; s_cnt[sl][tid] = (int16_t)(c > 0 ? c : 0); }
+        // producer cursor
+        int p_slot = 0, p_chunk = 0, p_n = (s_cnt[0][tid] + 3) >> 2, wr = 0;
+        auto fetch_next = [&]() {
+            while (p_slot < n_slots && p_chunk >= p_n) { ++p_slot; p_chunk = 0; p_n = p_slot < n_slots ? (s_cnt[p_slot][tid] + 3) >> 2 : 0; }
+            if (p_slot < n_slots) { cp_async16(&s_ring[wr % kRing][tid], src + p_slot * slot_chunks + p_chunk); ++p_chunk; }
+            ++wr;
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int c = 0; c < kRing; ++c) fetch_next();
+        // consumer cursor
+        int c_slot = 0, rd = 0, idx = 0, n = 0;
+        while (c_slot < n_slots && s_cnt[c_slot][tid] == 0) ++c_slot;
+        bool done = c_slot >= n_slots;
+        int cnt = done ? 0 : s_cnt[c_slot][tid];
+        cp_async_wait<kRing - 1>();
+        uint4 cur = s_ring[0][tid];
+        uint32_t e = cur.x;
+        float t_last = nearp;
+        // the warp-wide vote is the loop condition: it re-converges the lanes every iteration (and stops the compiler from
+        // re-nesting the loop into per-run inner loops, which would serialise lanes with different run lengths)
+        const uint32_t wmask = __activemask();
+        while (__any_sync(wmask, !done)) {
+            if (!done) {
+                const float bound = __uint_as_float(e & 0x7FFFFFFFu);
+                const float dt = march_dt(t_last, cone_angle, step_size);
+                const float mid = rn_add(t_last, rn_mul(dt, 0.5f));
+                const float t_next = rn_add(t_last, dt);
+                if (mid < bound) {
+                    if ((e >> 31) && n < max_per_ray) slab[n] = make_float2(t_last, t_next);
+                    n += (int)(e >> 31);
+                    t_last = t_next;
+                } else {
+                    ++idx;
+                    bool new_chunk = (idx & 3) == 0;
+                    if (idx >= cnt) {               // segment exhausted: the next non-empty one starts a fresh chunk
+                        do { ++c_slot; } while (c_slot < n_slots && s_cnt[c_slot][tid] == 0);
+                        done = c_slot >= n_slots;
+                        cnt = done ? 0 : s_cnt[c_slot][tid];
+                        idx = 0;
+                        new_chunk = true;
+                    }
+                    if (!done) {
+                        if (new_chunk) {
+                            fetch_next();           // refill the ring slot just consumed, kRing chunks ahead
+                            ++rd;
+                            cp_async_wait<kRing - 1>();
+                            cur = s_ring[rd % kRing][tid];
+                        } else {
+                            cur.x = cur.y; cur.y = cur.z; cur.z = cur.w;
+                        }
+                        e = cur.x;
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        counts[r] = n < max_per_ray ? n : max_per_ray;
+        if (n > max_per_ray && overflow) *overflow = 1;
+    }
+}
+
+// warp per ray: slab -> packed (ray_indices, t_starts, t_ends) at starts[r]
+__global__ void march_pack_kernel(const float2 *__restrict__ slabs, int max_per_ray, const int32_t *__restrict__ counts,
+                                  const int32_t *__restrict__ starts, int64_t n_rays, int64_t S_cap, int32_t *__restrict__ ray_indices,
+                                  float *__restrict__ t_starts, float *__restrict__ t_ends, int32_t *__restrict__ overflow)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rays; r += n_warps) {
+        const int64_t s = starts[r];
+        const int32_t c = counts[r];
+        if (lane == 0 && s + c > S_cap && overflow) *overflow = 1;
+        const float2 *src = slabs + r * (int64_t)max_per_ray;
+        for (int32_t k = lane; k < c; k += 32) {
+            const int64_t p = s + k;
+            if (p < S_cap) {
+                const float2 v = src[k];
+                t_starts[p] = v.x; t_ends[p] = v.y; ray_indices[p] = (int32_t)r;
+            }
         }
     }
 }
@@ -267,8 +504,8 @@ extern "C" int lse_occ_pack(const uint8_t *binaries, int levels, int res, uint32
     LSE_CHECK_ARG(mip_words <= kMaxMipWords, "occupancy mip does not fit shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(mip, 0, sizeof(uint32_t) * mip_words, st);
-    const int64_t n_words = ((int64_t)levels * res * res * res) >> 5;
-    occ_pack_kernel<<<stride_grid(n_words, 256, 4), 256, 0, st>>>(binaries, levels, res, bits, mip);
+    const int64_t n_bricks = ((int64_t)levels * res * res * res) >> 6;
+    occ_pack_kernel<<<stride_grid(n_bricks, 256, 4), 256, 0, st>>>(binaries, levels, res, reinterpret_cast<uint64_t *>(bits), mip);
     return check_launch("lse_occ_pack");
 }
 
@@ -288,6 +525,62 @@ extern "C" int lse_march_count(const float *rays_o, const float *rays_d, int64_t
         rays_o, rays_d, n_rays, occ_bits, occ_mip, mip_words, aabbs, levels, res, near_plane, far_plane, jitter, step_size,
         cone_angle, counts, nullptr, 0, nullptr, nullptr, nullptr, nullptr, kRayStride);
     return check_launch("lse_march_count");
+}
+
+static int march_lanes()   // lanes per ray of march_steps_kernel; LSE_MARCH_LANES overrides for tuning
+{
+    static int v = 0;
+    if (v == 0) { const char *e = getenv("LSE_MARCH_LANES"); v = e ? atoi(e) : 1; if (v < 1 || v > 32) v = 1; }
+    return v;
+}
+
+extern "C" int64_t lse_march_workspace(int64_t n_rays, int levels, int res)
+{
+    // runs [n_rays, 2*levels-1, 3*res] u32 + n_runs [n_rays, 2*levels-1] i32 (only the used prefix of a run list is touched)
+    const int64_t n = (n_rays < 1 ? 1 : n_rays) * (2 * levels - 1);
+    return (n * run_cap(res) * 4 + 255) / 256 * 256 + (n * 4 + 255) / 256 * 256;
+}
+
+extern "C" int lse_march_single(const float *rays_o, const float *rays_d, int64_t n_rays, const uint32_t *occ_bits,
+                                const uint32_t *occ_mip, const float *aabbs, int levels, int res, float near_plane,
+                                float far_plane, const float *jitter, float step_size, float cone_angle, float *slabs,
+                                int max_per_ray, int32_t *counts, int32_t *overflow_dev, void *workspace,
+                                int64_t workspace_bytes, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(levels >= 1 && levels <= kMaxLevels, "levels must be in [1,8]");
+    LSE_CHECK_ARG(res % 32 == 0, "grid resolution must be a multiple of 32");
+    LSE_CHECK_ARG(slabs && counts && max_per_ray > 0, "slabs / counts missing");
+    if (n_rays <= 0) return 0;
+    LSE_CHECK_ARG(workspace && workspace_bytes >= lse_march_workspace(n_rays, levels, res), "workspace missing or too small");
+    const int sb = res >> 3;
+    const int mip_words = (levels * sb * sb * sb + 31) / 32;
+    LSE_CHECK_ARG(mip_words <= kMaxMipWords, "occupancy mip does not fit shared memory");
+    const int64_t n = n_rays * (2 * levels - 1);
+    uint32_t *runs = reinterpret_cast<uint32_t *>(workspace);
+    int32_t *n_runs = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(workspace) + (n * run_cap(res) * 4 + 255) / 256 * 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    march_runs_kernel<<<stride_grid(n, kMarchThreads, 16), kMarchThreads, 0, st>>>(
+        rays_o, rays_d, n_rays, occ_bits, occ_mip, mip_words, aabbs, levels, res, near_plane, far_plane, jitter, step_size, runs,
+        n_runs);
+    int rc = check_launch("lse_march_single[runs]");
+    if (rc) return rc;
+    const int lanes = march_lanes();
+    march_steps_kernel<<<stride_grid(n_rays * lanes, kMarchThreads, 16), kMarchThreads, 0, st>>>(
+        n_rays, levels, res, near_plane, jitter, step_size, cone_angle, runs, n_runs, reinterpret_cast<float2 *>(slabs), max_per_ray,
+        counts, overflow_dev, lanes);
+    return check_launch("lse_march_single[steps]");
+}
+
+extern "C" int lse_march_pack(const float *slabs, int max_per_ray, const int32_t *counts, const int32_t *starts, int64_t n_rays,
+                              int64_t S_cap, int32_t *ray_indices, float *t_starts, float *t_ends, int32_t *overflow_dev,
+                              lse_stream_t stream)
+{
+    if (n_rays <= 0) return 0;
+    const int threads = 256;
+    march_pack_kernel<<<stride_grid(n_rays * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2 *>(slabs), max_per_ray, counts, starts, n_rays, S_cap, ray_indices, t_starts, t_ends,
+        overflow_dev);
+    return check_launch("lse_march_pack");
 }
 
 extern "C" int lse_scan_counts(const int32_t *counts, int64_t n, int32_t *starts, int32_t *total_dev, lse_stream_t stream)

@@ -40,18 +40,36 @@ struct OccBytes {
     }
 };
 
-// occupancy as 1 bit per cell (word = cell >> 5) guarded by an any-occupied mip over 8^3 superblocks: the DDA still
-// visits every cell (the fp32 tdist recurrence has to be replayed exactly) but cells of an empty superblock cost no
-// memory access at all -- the mip (levels * (res/8)^3 bits = 2 KiB for 4 x 128^3) lives in shared memory.
+// occupancy as 1 bit per cell in 64-bit words of 4x4x4 bricks (march.cu:occ_pack_kernel), guarded by an any-occupied mip over
+// 8^3 superblocks: the DDA still visits every cell (the fp32 tdist recurrence has to be replayed exactly) but cells of an empty
+// superblock cost no memory access at all -- the mip (levels * (res/8)^3 bits = 2 KiB for 4 x 128^3) lives in shared memory.
 struct OccBits {
-    const uint32_t *bits; const uint32_t *mip; int res;
+    const uint64_t *bits; const uint32_t *mip; int res;
     LSE_HD bool operator()(int level, const int cur[3]) const
     {
-        const int sb = res >> 3;
+        const int sb = res >> 3, rb = res >> 2;
         const int m = ((level * sb + (cur[0] >> 3)) * sb + (cur[1] >> 3)) * sb + (cur[2] >> 3);
         if (!((mip[m >> 5] >> (m & 31)) & 1u)) return false;
-        const int64_t cell = (int64_t)level * res * res * res + ((int64_t)cur[0] * res + cur[1]) * res + cur[2];
-        return (bits[cell >> 5] >> (cell & 31)) & 1u;
+        const int64_t brick = (((int64_t)level * rb + (cur[0] >> 2)) * rb + (cur[1] >> 2)) * rb + (cur[2] >> 2);
+        return (bits[brick] >> (((cur[0] & 3) << 4) | ((cur[1] & 3) << 2) | (cur[2] & 3))) & 1ull;
+    }
+};
+
+// the same lookup with the last brick kept in registers: consecutive DDA cells mostly stay inside one brick
+struct OccBrickCache {
+    const uint64_t *bits; const uint32_t *mip; int res;
+    int id; uint64_t word;
+    LSE_D bool lookup(int level, int x, int y, int z)
+    {
+        const int rb = res >> 2;
+        const int brick = ((level * rb + (x >> 2)) * rb + (y >> 2)) * rb + (z >> 2);
+        if (brick != id) {
+            id = brick;
+            const int sb = res >> 3;
+            const int m = ((level * sb + (x >> 3)) * sb + (y >> 3)) * sb + (z >> 3);
+            word = ((mip[m >> 5] >> (m & 31)) & 1u) ? bits[brick] : 0ull;
+        }
+        return (word >> (((x & 3) << 4) | ((y & 3) << 2) | (z & 3))) & 1ull;
     }
 };
 

@@ -166,8 +166,11 @@ def occ_pack(binaries_u8: Tensor, bits: Tensor, mip: Tensor) -> None:
     call("lse_occ_pack", P(binaries_u8), binaries_u8.shape[0], binaries_u8.shape[1], P(bits), P(mip), stream())
 
 
+MAX_SAMPLES_PER_RAY = 1024   # slab slots per ray of the single-pass march (a ray through 4 levels takes < 1000 steps)
+
+
 def march(rays_o, rays_d, binaries_u8, aabbs, near, far, step, cone, jitter: Optional[Tensor], S_cap: int,
-          packed: Optional[tuple] = None) -> MarchResult:
+          packed: Optional[tuple] = None, two_pass: bool = False) -> MarchResult:
     """traverse_grids (lse_grid_estimator.py:83-106) without a host sync: capacity-bounded packed output.
     packed: (bits, mip) from LSEOccGridEstimator.packed(); packed here from `binaries_u8` when absent."""
     o = _f32(rays_o.detach(), "rays_o"); d = _f32(rays_d.detach(), "rays_d")
@@ -181,13 +184,23 @@ def march(rays_o, rays_d, binaries_u8, aabbs, near, far, step, cone, jitter: Opt
         occ_pack(binaries_u8, bits, mip)
     else:
         bits, mip = packed
-    call("lse_march_count", P(o), P(d), R, P(bits), P(mip), P(aabbs), levels, res, near, far, P(jit), step, cone, P(counts), stream())
-    starts, total = scan_counts(counts)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
     ri = torch.empty(S_cap, dtype=torch.int32, device=dev)
     t0 = torch.empty(S_cap, device=dev); t1 = torch.empty(S_cap, device=dev)
-    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-    call("lse_march_fill", P(o), P(d), R, P(bits), P(mip), P(aabbs), levels, res, near, far, P(jit), step, cone, P(starts),
-         S_cap, P(ri), P(t0), P(t1), P(overflow), stream())
+    if two_pass:
+        call("lse_march_count", P(o), P(d), R, P(bits), P(mip), P(aabbs), levels, res, near, far, P(jit), step, cone, P(counts), stream())
+        starts, total = scan_counts(counts)
+        call("lse_march_fill", P(o), P(d), R, P(bits), P(mip), P(aabbs), levels, res, near, far, P(jit), step, cone, P(starts),
+             S_cap, P(ri), P(t0), P(t1), P(overflow), stream())
+    else:
+        # one marching pass into per-ray slabs (only the used prefix of a slab is ever touched), then a coalesced pack
+        slabs = torch.empty(R, MAX_SAMPLES_PER_RAY, 2, device=dev)
+        nws = int(_lib.lib().lse_march_workspace(R, levels, res))
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        call("lse_march_single", P(o), P(d), R, P(bits), P(mip), P(aabbs), levels, res, near, far, P(jit), step, cone, P(slabs),
+             MAX_SAMPLES_PER_RAY, P(counts), P(overflow), P(ws), nws, stream())
+        starts, total = scan_counts(counts)
+        call("lse_march_pack", P(slabs), MAX_SAMPLES_PER_RAY, P(counts), P(starts), R, S_cap, P(ri), P(t0), P(t1), P(overflow), stream())
     return MarchResult(ri, t0, t1, starts, counts, total, overflow, S_cap)
 
 
