@@ -298,8 +298,11 @@ def run_b200(args):
     clocks.start()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
+    hb = dm.sample_host_batches()
     for i in range(K):
-        host_loss = gs.step(host_batches=dm.sample_host_batches()).cpu()   # D2H read of the step's losses
+        out = gs.step(host_batches=hb)      # pack into pinned staging + H2D + graph replays, all asynchronous
+        hb = dm.sample_host_batches()       # host pixel draw + gather of the NEXT batch overlaps the device step
+        host_loss = out.cpu()               # D2H read of this step's losses (synchronises)
     f1.record()
     barrier()
     clk = clocks.stop()

@@ -84,12 +84,17 @@ class RayBundle:
         return self._map(lambda t: t.to(device))
 
 
-def concat_bundles(bundles) -> RayBundle:
-    """Concatenate flat bundles (used to issue the col/prev/next forwards of lse_pipeline.py:115-123 as one launch)."""
+def concat_bundles(bundles, fields=None, metadata_keys=None) -> RayBundle:
+    """Concatenate flat bundles (used to issue the col/prev/next forwards of lse_pipeline.py:115-123 as one launch).
+    fields / metadata_keys restrict the concatenation to what the consumer reads (every cat is a launch)."""
     def cat(name):
+        if fields is not None and name not in fields:
+            return None
         vals = [getattr(b, name) for b in bundles]
         return torch.cat(vals, dim=0) if all(v is not None for v in vals) else None
     keys = set.intersection(*[set(b.metadata.keys()) for b in bundles])
+    if metadata_keys is not None:
+        keys = keys & set(metadata_keys)
     md = {k: torch.cat([b.metadata[k] for b in bundles], dim=0) for k in keys}
     return RayBundle(cat("origins"), cat("directions"), cat("pixel_area"), cat("camera_indices"), cat("nears"), cat("fars"),
                      md, cat("times"))

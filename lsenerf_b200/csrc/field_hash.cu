@@ -60,11 +60,10 @@ __device__ __forceinline__ int run_last_lane(uint32_t heads, int lane)
     const uint32_t above = heads & ~((2u << lane) - 1u);     // run starts strictly above this lane (lane 31: 2u<<31 wraps to 0 -> none)
     return lane == 31 ? 31 : (above ? __ffs(above) - 2 : 31);
 }
-// after the call the first lane of every run holds the sum over its run
-__device__ __forceinline__ float run_sum(float v, int lane, int last)
+// after the call the first lane of every run holds the sum over its run; `max_len` (warp-uniform) = longest run of the warp
+__device__ __forceinline__ float run_sum(float v, int lane, int last, int max_len)
 {
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
+    for (int s = 1; s < max_len; s <<= 1) {
         const float t = __shfl_down_sync(0xffffffffu, v, s);
         if (lane + s <= last) v += t;
     }
@@ -92,23 +91,17 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
         SampleGeom g;
         g.cc.sel = false; g.has_dir = false; g.tmid = 0.0f; g.ray = -1 - lane;
         g.x[0] = g.x[1] = g.x[2] = 0.0f;
-        float df[NF];
-        if (live) {
-            load_geom(i, origins, directions, ray_idx, t0, t1, g);
-            const float4 *f4 = reinterpret_cast<const float4 *>(dfeat + 32 * i);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { float4 t = f4[q]; df[4 * q] = t.x; df[4 * q + 1] = t.y; df[4 * q + 2] = t.z; df[4 * q + 3] = t.w; }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NF; ++j) df[j] = 0.0f;
-        }
+        if (live) load_geom(i, origins, directions, ray_idx, t0, t1, g);
+        const float2 *df2 = reinterpret_cast<const float2 *>(dfeat + 32 * i);
         const bool want_dx = live && (d_origins != nullptr || d_directions != nullptr) && g.cc.sel;
         float dx[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
+        // the level loop stays rolled: 16 unrolled copies of this body (19 k instructions) thrash the instruction cache
+#pragma unroll 1
         for (int l = 0; l < NL; ++l) {
             HashCell hc;
             hash_cell(g.x, s_scal[l], mask, hc);
-            const float gl[2] = {df[2 * l], df[2 * l + 1]};
+            const float2 g2 = live ? __ldg(df2 + l) : make_float2(0.0f, 0.0f);
+            const float gl[2] = {g2.x, g2.y};
             if (d_table) {
                 float w[8];
                 hash_weights(hc, w);
@@ -125,9 +118,10 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
                 const uint32_t heads = __ballot_sync(0xffffffffu, head);
                 if (__popc(heads) <= 20) {          // coarse level: few cells per warp -> one reduction per run
                     const int last = run_last_lane(heads, lane);
+                    const int max_len = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last - lane + 1));
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float a = run_sum(w[c] * gl[0], lane, last), b = run_sum(w[c] * gl[1], lane, last);
+                        const float a = run_sum(w[c] * gl[0], lane, last, max_len), b = run_sum(w[c] * gl[1], lane, last, max_len);
                         if (head && live) red_add2(dtl + 2 * (size_t)hc.idx[c], a, b);
                     }
                 } else if (live) {
@@ -155,11 +149,12 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
             const bool head = lane == 0 || pk != rkey;
             const uint32_t heads = __ballot_sync(0xffffffffu, head);
             const int last = run_last_lane(heads, lane);
+            const int max_len = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last - lane + 1));
             const int64_t r = ray_idx ? (int64_t)g.ray : i;
             const float tm = g.has_dir ? g.tmid : 0.0f;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const float so = run_sum(dp[j], lane, last), sd = run_sum(dp[j] * tm, lane, last);
+                const float so = run_sum(dp[j], lane, last, max_len), sd = run_sum(dp[j] * tm, lane, last, max_len);
                 if (head && live) {
                     if (d_origins) red_add(d_origins + 3 * r + j, so);
                     if (d_directions && directions) red_add(d_directions + 3 * r + j, sd);

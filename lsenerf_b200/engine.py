@@ -193,6 +193,7 @@ class GraphedStep:
         self.pipeline, self.optim, self.world = pipeline, optim, world_size
         self.use_graph = use_graph
         dm = pipeline.datamanager
+        dm.lean = True                      # captured step: no launches for metadata the fused path never reads
         hc, he = dm.sample_host_batches()
         self.stage = BatchStage(hc, he, dm.device)
         self.stage.pack_host(hc, he); self.stage.upload()

@@ -49,7 +49,8 @@ class LSENeRFPipeline(nn.Module):
 
     def _fused_forward(self, col, prev, nxt):
         m = self._model
-        big = concat_bundles([col, prev, nxt])
+        # the fused render reads origins / directions (+ the appearance id of per-frame embeddings) only
+        big = concat_bundles([col, prev, nxt], fields=("origins", "directions"), metadata_keys=("appearance_id",))
         n0, n1 = len(col), len(prev)
         raw = m.exec_get_outputs(big)
         outs = []

@@ -42,12 +42,14 @@ def fix_appearance_id(data, ref_data, max_app_id=1000000):
     return torch.clip(data + delta, 0, max_app_id - 1).reshape(-1, 1)
 
 
-def add_metadata(ray_bundle, batch, cam_id=0, max_app_id=10000000):
-    """utils.py:182-194."""
+def add_metadata(ray_bundle, batch, cam_id=0, max_app_id=10000000, lean=False):
+    """utils.py:182-194.  lean: appearance_id only (the one entry the model reads, lse_field.py:324-327)."""
     ref = ray_bundle.camera_indices
     dev = ref.device
     app = batch["appearance_id"].to(dev)[..., None].contiguous()
     ray_bundle.metadata["appearance_id"] = fix_appearance_id(app, ref, max_app_id)
+    if lean:
+        return ray_bundle
     ray_bundle.metadata["cam_type"] = torch.full((len(ray_bundle),), cam_id, device=dev)
     ray_bundle.metadata["coords"] = fix_datashape(batch["indices"].to(dev), ref)
     return ray_bundle
