@@ -244,7 +244,15 @@ def run_b200(args):
     pipe.train()
     dm = pipe.datamanager
     from lsenerf_b200.engine import ArenaAdam, GraphedStep
-    opt = ArenaAdam(pipe.get_param_groups())
+    sym_group = None
+    if world > 1 and not args.nccl_allreduce:
+        sym_group = dist.group.WORLD
+    try:
+        opt = ArenaAdam(pipe.get_param_groups(), symmetric_group=sym_group)
+    except Exception as e:                                   # symmetric memory unavailable on this box: NCCL all-reduce path
+        if rank == 0:
+            print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce", file=sys.stderr)
+        opt = ArenaAdam(pipe.get_param_groups())
     K, W = args.steps, args.warmup
     # steady-state training: start after the occupancy grid's 256-step warm-up schedule (during warm-up every 16th step
     # re-evaluates all 4x128^3 cells, afterwards a quarter of them + the occupied ones)
@@ -256,8 +264,26 @@ def run_b200(args):
     # step 150) and then sharpens; marched ~205 and kept ~37 samples/ray are stationary from ~1000 steps on (RGB PSNR ~33 dB).
     # Time the steady state, not the transient.
     BURN_IN = args.burn_in
-    for _ in range(BURN_IN):
-        gs.step()
+    # N > 1: the model state (hence samples per ray, hence work per ray) must not depend on N, or the per-N values are not
+    # comparable.  Rank 0 alone runs the burn-in (exactly the 1-GPU trajectory: same seed, no exchange), then its weights,
+    # Adam moments and occupancy grid are broadcast; only then do the ranks draw different rays and exchange gradients.
+    if rank == 0:
+        gs.local_only = True
+        for _ in range(BURN_IN):
+            gs.step()
+        gs.local_only = False
+    if world > 1:
+        torch.cuda.synchronize()
+        og = pipe._model.occupancy_grid
+        for a in opt.arenas.values():
+            for t in (a.data, a.exp_avg, a.exp_avg_sq):
+                dist.broadcast(t, 0)
+        bin_u8 = og.binaries.view(torch.uint8)
+        for t in (og.occs, bin_u8, og.occ_mean):
+            dist.broadcast(t, 0)
+        og.packed(force=True)
+        gs.step_no = START + BURN_IN
+        opt.step_count = START + BURN_IN
 
     def barrier():
         if world > 1:
@@ -281,10 +307,15 @@ def run_b200(args):
     clocks.start()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_window:                  # ncu --profile-from-start off: capture exactly the timed steps
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(K):
         gs.step(packed_dev=staged[W + i])
     e1.record()
+    if args.profiler_window:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     clocks.pause()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -335,20 +366,46 @@ def run_b200(args):
     if rank == 0:
         per_call = {k: v[1] / v[0] for k, v in prof.items()}
         per_step = {k: v[1] / n_prof for k, v in prof.items()}
-        top = max(per_step, key=per_step.get)
-        # algorithmic bytes per sample: 1024 B gathered (+12 in, +68/128 out) for the fused
-        # density kernel over S0 marched samples; 1024 B scattered (+ re-gather 1024 B for d/dx) for its backward over S1.
-        alg = {"lse_field_density_fwd": (1024 + 12 + 68) * S0, "lse_field_density_bwd": (1024 + 1024 + 12 + 68 + 64) * S1,
-               "lse_field_color_fwd": (64 + 12) * S1, "lse_field_color_bwd": (64 + 12 + 64 + 12) * S1}
+        # ALGORITHMIC bytes / flops per sample x the live sample counts read back from the device:
+        #   density_fwd    : 1024 B gathered + 12 B (ray index, t0, t1) in + 68 B (sigma, h16) out          per MARCHED sample
+        #   density_bwd_ws : 1024 B re-gathered (encode) + 1024 B scattered + 1024 B re-gathered (d/dx) + 2 x 256 B (feat / dfeat
+        #                    round trip) + 12 + 68 + 64 B (geometry, h16 row 0, d_sigma, d_h16)                   per KEPT sample
+        #   color fwd/bwd  : the dense contraction, 16 640 flop/sample forward, 3 x that backward (recompute + dgrad + wgrad)
+        alg_bytes = {"lse_field_density_fwd": (1024 + 12 + 68) * S0, "lse_field_density_bwd_ws": (3 * 1024 + 512 + 12 + 68 + 64) * S1}
+        alg_flops = {"lse_field_color_fwd": 16640 * S1, "lse_field_color_bwd": 3 * 16640 * S1}
         hbm, which = peaks()
-        roof_k = top if top in alg else "lse_field_density_fwd"
-        dur = per_call[roof_k] * 1e-3
-        achieved = alg[roof_k] / dur / 1e9
+        try:   # kernels timed inside a long step: the sustained bf16 figure
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                pk = json.load(fh)
+            tf_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1362.4)))
+        except Exception:
+            tf_peak = 1362.4
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as fh:
+                ncu_traffic = json.load(fh)
+        except Exception:
+            ncu_traffic = {}
+
+        def roof(kname):
+            dur = per_call[kname] * 1e-3
+            tr = ncu_traffic.get(kname)
+            if kname in alg_bytes:
+                ach = alg_bytes[kname] / dur / 1e9
+                r = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
+            else:
+                ach = alg_flops[kname] / dur / 1e12
+                r = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak}
+            r.update({"traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_source": tr.get("source") if tr else None,
+                      "peak_source": which, "ms_per_launch": per_call[kname], "share_of_step": per_step[kname] / sum(per_step.values())})
+            return r
+        candidates = [k for k in list(alg_bytes) + list(alg_flops) if k in per_call]
+        roof_k = max((k for k in candidates if k in alg_bytes), key=lambda k: per_step[k])
+        rooflines = [roof(k) for k in sorted(candidates, key=lambda k: -per_step[k])]
         rays = BUDGET * world
         line = {"metric": "train rays/sec (fwd+bwd, event+RGB)", "value": rays * K / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "parallelism": f"ray-sharded dp{world}, 1 grad all-reduce/step",
+                "config": {"workload": WORKLOAD, "parallelism": f"ray-sharded dp{world}; gradient exchange: {opt.exchange_kind()}",
                            "l2": "working set per step (64 MiB table + 64 MiB grad + 128 MiB Adam state + sample buffers) exceeds the 126 MB L2; no explicit flush",
                            "samples_marched_per_step": S0, "samples_kept_per_step": S1, "capacity_overflow": overflow,
                            "mlp": "tcgen05 (3xTF32 fwd, BF16x3 bwd)" if pipe._model.config.use_tensor_cores else "fp32 SIMT",
@@ -357,9 +414,7 @@ def run_b200(args):
                 "e2e": {"value": rays * K / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": int(launches), "clocks": clk,
-                "roofline": {"kernel": roof_k, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                             "traffic": None, "peak_source": which, "ms_per_launch": per_call[roof_k],
-                             "share_of_step": per_step[roof_k] / sum(per_step.values())},
+                "roofline": roof(roof_k), "rooflines": rooflines,
                 "render": render,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
         if world == 1 and not args.no_cpu:
@@ -380,6 +435,8 @@ def main():
     ap.add_argument("--burn-in", type=int, default=1000, help="untimed training steps before the timed region")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--profiler-window", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: NCCL all-reduce + local Adam instead of the fused peer-memory kernel")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

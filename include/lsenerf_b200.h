@@ -259,6 +259,17 @@ int lse_adam_step(float *param, const float *grad, float *exp_avg, float *exp_av
 int lse_adam_step_hp(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
                      float beta2, float eps, const float *hp_dev, lse_stream_t stream);
 
+/* Multi-GPU optimizer step with the gradient exchange folded in (replaces DDP's all-reduce, lse_pipeline.py:96-97, plus the
+ * Adam step, lse_config.py:29-38).  The parameter and gradient arenas are symmetric-memory allocations of `n` floats mapped by
+ * every rank: peer_params / peer_grads [host] are `world` device pointers (this rank's own at index `rank`);
+ * param_multicast / grad_multicast are the NVSwitch multicast addresses of the two arenas (both NULL: plain peer loads /
+ * stores).  Rank r reduces slice r of the gradients over all ranks, applies Adam to it (exp_avg / exp_avg_sq are LOCAL, only
+ * the slice is touched; hp_dev as in lse_adam_step_hp with grad_scale = 1/world) and writes the new parameters into every
+ * rank's arena.  The caller brackets the call with two cross-rank barriers on the same stream. */
+int lse_adam_step_collective(void *const *peer_params, void *const *peer_grads, float *param_multicast,
+                             const float *grad_multicast, float *exp_avg, float *exp_avg_sq, int64_t n, int rank, int world,
+                             float beta1, float beta2, float eps, const float *hp_dev, lse_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

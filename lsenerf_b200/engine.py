@@ -54,10 +54,20 @@ class _PinnedRing:
             self.events[self.cur] = ev
 
 
-class ParamArena:
-    """One optimizer group flattened: params, grads and Adam moments each in one contiguous fp32 buffer."""
+def _symm_alloc(n: int, dev, group):
+    """fp32 [n] in symmetric memory, rendezvoused over `group` -> (tensor, handle) or None when unavailable."""
+    import torch.distributed._symmetric_memory as symm_mem
+    t = symm_mem.empty(n, dtype=torch.float32, device=dev)
+    t.zero_()
+    return t, symm_mem.rendezvous(t, group)
 
-    def __init__(self, params: List[nn.Parameter]) -> None:
+
+class ParamArena:
+    """One optimizer group flattened: params, grads and Adam moments each in one contiguous fp32 buffer.  With
+    `symmetric_group` the parameter and gradient buffers are symmetric-memory allocations every rank of the group maps
+    (NVLink peer pointers + the NVSwitch multicast address) for the fused exchange of csrc/adam_collective.cu."""
+
+    def __init__(self, params: List[nn.Parameter], symmetric_group=None) -> None:
         seen, uniq = set(), []
         for p in params:
             if p.requires_grad and id(p) not in seen:
@@ -69,8 +79,13 @@ class ParamArena:
             offs.append(n)
             n += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned for the float4 kernels
         self.offsets, self.numel = offs, n
-        self.data = torch.zeros(n, device=dev)
-        self.grad = torch.zeros(n, device=dev)
+        self.h_data = self.h_grad = None
+        if symmetric_group is not None:
+            self.data, self.h_data = _symm_alloc(n, dev, symmetric_group)
+            self.grad, self.h_grad = _symm_alloc(n, dev, symmetric_group)
+        else:
+            self.data = torch.zeros(n, device=dev)
+            self.grad = torch.zeros(n, device=dev)
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
         with torch.no_grad():
@@ -87,9 +102,11 @@ class ParamArena:
 class ArenaAdam:
     """Adam(lr, eps=1e-15) + exponential LR decay (lse_config.py:29-38) over ParamArenas, hyper-parameters on the device."""
 
-    def __init__(self, groups: Dict[str, List[nn.Parameter]], specs: Optional[Dict[str, OptimizerSpec]] = None) -> None:
+    def __init__(self, groups: Dict[str, List[nn.Parameter]], specs: Optional[Dict[str, OptimizerSpec]] = None,
+                 symmetric_group=None) -> None:
         self.specs = specs or DEFAULT_OPTIMIZERS
-        self.arenas = {k: ParamArena(v) for k, v in groups.items() if len(v) > 0}
+        self.symmetric = symmetric_group is not None
+        self.arenas = {k: ParamArena(v, symmetric_group) for k, v in groups.items() if len(v) > 0}
         self.groups = {k: a.params for k, a in self.arenas.items()}
         dev = next(iter(self.arenas.values())).data.device
         self.names = list(self.arenas.keys())
@@ -128,6 +145,34 @@ class ArenaAdam:
     def step(self, grad_scale: float = 1.0) -> None:
         self.set_step(self.step_count + 1, grad_scale)
         self.apply()
+
+    @torch.no_grad()
+    def apply_collective(self) -> None:
+        """Exchange + Adam as one kernel per arena over NVLink peer / multicast memory (csrc/adam_collective.cu), bracketed by
+        two symmetric-memory barriers.  Replaces allreduce() + apply() when the arenas are symmetric."""
+        import ctypes
+        assert self.symmetric, "apply_collective needs arenas allocated in symmetric memory"
+        first = self.arenas[self.names[0]]
+        first.h_grad.barrier(channel=0)                       # every rank's backward has finished writing gradients
+        for i, name in enumerate(self.names):
+            a, spec = self.arenas[name], self.specs[name]
+            W, r = a.h_data.world_size, a.h_data.rank
+            pp = (ctypes.c_void_p * W)(*[int(p) for p in a.h_data.buffer_ptrs])
+            pg = (ctypes.c_void_p * W)(*[int(p) for p in a.h_grad.buffer_ptrs])
+            mc_p, mc_g = int(a.h_data.multicast_ptr or 0), int(a.h_grad.multicast_ptr or 0)
+            use_mc = mc_p != 0 and mc_g != 0 and a.numel >= 4096       # tiny arenas: plain peer stores
+            call("lse_adam_step_collective", ctypes.cast(pp, ctypes.c_void_p), ctypes.cast(pg, ctypes.c_void_p),
+                 ctypes.c_void_p(mc_p) if use_mc else None, ctypes.c_void_p(mc_g) if use_mc else None, P(a.exp_avg),
+                 P(a.exp_avg_sq), a.numel, r, W, spec.betas[0], spec.betas[1], spec.eps, P(self.hp_dev[i]), stream())
+        first.h_data.barrier(channel=1)                       # every slice written before anybody reads weights / zeroes grads
+
+    def exchange_kind(self) -> str:
+        if not self.symmetric:
+            return "NCCL all-reduce + local Adam"
+        a = self.arenas[self.names[0]]
+        mc = int(a.h_data.multicast_ptr or 0) != 0 and int(a.h_grad.multicast_ptr or 0) != 0
+        return "fused reduce-scatter + Adam + all-gather kernel over symmetric memory (" + \
+               ("NVSwitch multimem.ld_reduce / multimem.st" if mc else "NVLink peer loads / stores") + ")"
 
     def allreduce(self) -> None:
         import torch.distributed as dist
@@ -201,6 +246,7 @@ class GraphedStep:
         self.graph_opt: Optional[torch.cuda.CUDAGraph] = None
         self.loss_out: Optional[torch.Tensor] = None
         self.step_no = 0
+        self.local_only = False     # True: step this replica alone (no exchange, grad_scale 1) -- bench burn-in on rank 0
 
     def _fwd_bwd(self) -> torch.Tensor:
         self.optim.zero_grad()
@@ -240,17 +286,25 @@ class GraphedStep:
                 host_batches = self.pipeline.datamanager.sample_host_batches()
             self.stage.pack_host(*host_batches)
             self.stage.upload()
-        self.optim.set_step(self.optim.step_count + 1, 1.0 / self.world if self.world > 1 else 1.0)
+        world = 1 if self.local_only else self.world
+        self.optim.set_step(self.optim.step_count + 1, 1.0 / world if world > 1 else 1.0)
+        fused = world > 1 and self.optim.symmetric
         if self.graph_fb is not None:
             self.graph_fb.replay()
-            if self.world > 1:
-                self.optim.allreduce()
-            self.graph_opt.replay()
+            if fused:
+                self.optim.apply_collective()
+            else:
+                if world > 1:
+                    self.optim.allreduce()
+                self.graph_opt.replay()
             out = self.loss_out
         else:
             out = self._fwd_bwd()
-            if self.world > 1:
-                self.optim.allreduce()
-            self.optim.apply()
+            if fused:
+                self.optim.apply_collective()
+            else:
+                if world > 1:
+                    self.optim.allreduce()
+                self.optim.apply()
         self.step_no += 1
         return out

@@ -527,3 +527,14 @@ def test_tensor_core_backward_matches_fp32(dev, S, emb):
     for k in ref:
         assert torch.isfinite(tc[k]).all(), k
         assert rel_err(tc[k], ref[k]) < TOL_GRAD, (k, rel_err(tc[k], ref[k]))
+
+
+def test_collective_adam_two_gpus(dev):
+    """csrc/adam_collective.cu on 2 GPUs (skipped on a single-GPU box): see tests/dist_collective_check.py."""
+    import subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29571", os.path.join(here, "dist_collective_check.py")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
