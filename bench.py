@@ -368,10 +368,13 @@ def run_b200(args):
         per_step = {k: v[1] / n_prof for k, v in prof.items()}
         # ALGORITHMIC bytes / flops per sample x the live sample counts read back from the device:
         #   density_fwd    : 1024 B gathered + 12 B (ray index, t0, t1) in + 68 B (sigma, h16) out          per MARCHED sample
-        #   density_bwd_ws : 1024 B re-gathered (encode) + 1024 B scattered + 1024 B re-gathered (d/dx) + 2 x 256 B (feat / dfeat
-        #                    round trip) + 12 + 68 + 64 B (geometry, h16 row 0, d_sigma, d_h16)                   per KEPT sample
+        #   density_bwd    : encode = 1024 B re-gathered + 128 B feat out + 20 B geometry/d_sigma; finish = 1024 B scattered + 1024 B
+        #                    re-gathered (d/dx) + 128 B feat in + 256 B dfeat round trip + 80 B                    per KEPT sample
         #   color fwd/bwd  : the dense contraction, 16 640 flop/sample forward, 3 x that backward (recompute + dgrad + wgrad)
-        alg_bytes = {"lse_field_density_fwd": (1024 + 12 + 68) * S0, "lse_field_density_bwd_ws": (3 * 1024 + 512 + 12 + 68 + 64) * S1}
+        alg_bytes = {"lse_field_density_fwd": (1024 + 12 + 68) * S0, "lse_field_density_bwd_ws": (3 * 1024 + 512 + 12 + 68 + 64) * S1,
+                     # the same backward as its two launches (the encode half runs under the colour backward on a side stream)
+                     "lse_field_density_bwd_encode": (1024 + 128 + 12 + 8) * S1,
+                     "lse_field_density_bwd_finish": (2 * 1024 + 128 + 256 + 12 + 64 + 4) * S1}
         alg_flops = {"lse_field_color_fwd": 16640 * S1, "lse_field_color_bwd": 3 * 16640 * S1}
         hbm, which = peaks()
         try:   # kernels timed inside a long step: the sustained bf16 figure

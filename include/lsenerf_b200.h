@@ -189,6 +189,17 @@ int lse_field_density_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, co
                              int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
                              const float *d_h16, float *d_origins, float *d_directions, void *workspace,
                              int64_t workspace_bytes, lse_stream_t stream);
+/* The two halves of lse_field_density_bwd_ws.  `encode` needs d_sigma but not d_h16, so it may run on a side stream
+ * concurrently with lse_field_color_bwd (which produces d_h16); join, then `finish`. */
+int lse_field_density_bwd_encode(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                                 const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                                 int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                                 void *workspace, int64_t workspace_bytes, lse_stream_t stream);
+int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                                 const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                                 int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                                 const float *d_h16, float *d_origins, float *d_directions, void *workspace,
+                                 int64_t workspace_bytes, lse_stream_t stream);
 /* rgb [S,3] = sigmoid(head(cat[SH16(dir), geo15, emb32])).  app_id int32 [n_rays] (per RAY) or NULL. */
 int lse_field_color_fwd(const LseFieldParams *p, const float *directions, const int32_t *ray_idx,
                         const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb,

@@ -175,34 +175,72 @@ extern "C" int64_t lse_field_density_bwd_workspace(int64_t S_cap)
     return ((s * 32 * 4 + 255) / 256 * 256) * 2 + (s * 4 + 255) / 256 * 256;
 }
 
-extern "C" int lse_field_density_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
-                                        const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
-                                        int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
-                                        const float *d_h16, float *d_origins, float *d_directions, void *workspace,
-                                        int64_t workspace_bytes, lse_stream_t stream)
+static int check_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins, const float *h16, const char *fn)
 {
-    if (!p) { set_error("%s: params is NULL", __func__); return -22; }
-    LSE_CHECK_ARG(p->levels == 16 && p->log2_T >= 4 && p->log2_T <= 28 && p->table && p->scalings, "bad hash-grid parameters");
-    LSE_CHECK_ARG(p->W1 && p->b1 && p->W2 && p->b2, "base MLP weights missing");
-    LSE_CHECK_ARG(g && g->dW1 && g->db1 && g->dW2 && g->db2, "gradient buffers for the base MLP missing");
-    LSE_CHECK_ARG(origins && h16, "origins / h16 missing");
+    if (!p) { set_error("%s: params is NULL", fn); return -22; }
+    if (!(p->levels == 16 && p->log2_T >= 4 && p->log2_T <= 28 && p->table && p->scalings)) { set_error("%s: bad hash-grid parameters", fn); return -22; }
+    if (!(p->W1 && p->b1 && p->W2 && p->b2)) { set_error("%s: base MLP weights missing", fn); return -22; }
+    if (!(g && g->dW1 && g->db1 && g->dW2 && g->db2)) { set_error("%s: gradient buffers for the base MLP missing", fn); return -22; }
+    if (!(origins && h16)) { set_error("%s: origins / h16 missing", fn); return -22; }
+    return 0;
+}
+
+struct BwdWs { float *feat, *dfeat, *dout0; };
+static BwdWs carve_ws(void *workspace, int64_t S_cap)
+{
+    const int64_t fbytes = (S_cap * 32 * 4 + 255) / 256 * 256;
+    char *w = reinterpret_cast<char *>(workspace);
+    return {reinterpret_cast<float *>(w), reinterpret_cast<float *>(w + fbytes), reinterpret_cast<float *>(w + 2 * fbytes)};
+}
+
+// first third of lse_field_density_bwd_ws: needs only d_sigma (not d_h16), so a caller may run it on a side stream
+// concurrently with lse_field_color_bwd (which produces d_h16) and join before lse_field_density_bwd_finish
+extern "C" int lse_field_density_bwd_encode(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                                            const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                                            int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                                            void *workspace, int64_t workspace_bytes, lse_stream_t stream)
+{
+    int rc = check_bwd_ws(p, g, origins, h16, __func__);
+    if (rc) return rc;
+    if (S_cap <= 0 || !p->use_tensor_cores) return 0;
+    LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
+    const BwdWs ws = carve_ws(workspace, S_cap);
+    encode_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, (cudaStream_t)stream>>>(*p, origins, directions, ray_idx, t0, t1, S_cap,
+                                                                                      n_dev, h16, d_sigma, ws.feat, ws.dout0);
+    return check_launch("lse_field_density_bwd_encode");
+}
+
+extern "C" int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                                            const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                                            int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                                            const float *d_h16, float *d_origins, float *d_directions, void *workspace,
+                                            int64_t workspace_bytes, lse_stream_t stream)
+{
+    int rc = check_bwd_ws(p, g, origins, h16, __func__);
+    if (rc) return rc;
     if (S_cap <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (!p->use_tensor_cores)
         return simt_density_bwd(*p, *g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, d_h16, d_origins,
                                 d_directions, st);
     LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
-    const int64_t fbytes = (S_cap * 32 * 4 + 255) / 256 * 256;
-    float *feat = reinterpret_cast<float *>(workspace);
-    float *dfeat = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + fbytes);
-    float *dout0 = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + 2 * fbytes);
-    const int grid = stride_grid(S_cap, HT, 8);
-    encode_samples_kernel<<<grid, HT, 0, st>>>(*p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, feat, dout0);
-    int rc = check_launch("lse_field_density_bwd_ws[encode]");
+    const BwdWs ws = carve_ws(workspace, S_cap);
+    rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_h16, ws.dfeat, st);
     if (rc) return rc;
-    rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, feat, dout0, d_h16, dfeat, st);
+    scatter_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, st>>>(*p, g->d_table, origins, directions, ray_idx, t0, t1, S_cap, n_dev,
+                                                                     ws.dfeat, d_origins, d_directions);
+    return check_launch("lse_field_density_bwd_finish");
+}
+
+extern "C" int lse_field_density_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                                        const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                                        int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                                        const float *d_h16, float *d_origins, float *d_directions, void *workspace,
+                                        int64_t workspace_bytes, lse_stream_t stream)
+{
+    int rc = lse_field_density_bwd_encode(p, g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, workspace,
+                                          workspace_bytes, stream);
     if (rc) return rc;
-    scatter_samples_kernel<<<grid, HT, 0, st>>>(*p, g->d_table, origins, directions, ray_idx, t0, t1, S_cap, n_dev, dfeat, d_origins,
-                                                d_directions);
-    return check_launch("lse_field_density_bwd_ws[scatter]");
+    return lse_field_density_bwd_finish(p, g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, d_h16, d_origins,
+                                        d_directions, workspace, workspace_bytes, stream);
 }

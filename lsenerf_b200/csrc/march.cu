@@ -530,7 +530,7 @@ extern "C" int lse_march_count(const float *rays_o, const float *rays_d, int64_t
 static int march_lanes()   // lanes per ray of march_steps_kernel; LSE_MARCH_LANES overrides for tuning
 {
     static int v = 0;
-    if (v == 0) { const char *e = getenv("LSE_MARCH_LANES"); v = e ? atoi(e) : 1; if (v < 1 || v > 32) v = 1; }
+    if (v == 0) { const char *e = getenv("LSE_MARCH_LANES"); v = e ? atoi(e) : 4; if (v < 1 || v > 32) v = 4; }
     return v;
 }
 

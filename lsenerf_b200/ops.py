@@ -332,6 +332,16 @@ def _density_bwd(fw: FieldWeights, cp, cg, o, d, ray_idx, t0, t1, S_cap, n_dev, 
          P(h16), P(d_sigma), P(d_h16), P(g_o), P(g_d), P(ws), nbytes, stream())
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 _DENS_KEYS = ("table", "W1", "b1", "W2", "b2")
 _COL_KEYS = ("W3", "b3", "W4", "b4", "W5", "b5")
 
@@ -533,10 +543,27 @@ class _RenderRays(torch.autograd.Function):
         g_d = torch.zeros_like(d) if (need_d or need_o) else None
         d_h16 = torch.empty(S_cap, 16, device=dev)
         cp = fw.c_params(); cg = _grads_struct(fw, bufs)
-        call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
-             P(h16), P(d_rgb), P(d_h16), P(g_d) if need_d else None, stream())
-        _density_bwd(fw, cp, cg, o, d, m.ray_indices, m.t_starts, m.t_ends, S_cap, m.total, h16, d_sigma, d_h16, g_o,
-                     g_d if need_d else None)
+        gd = g_d if need_d else None
+        if fw.use_tensor_cores:
+            # the re-encode of the kept samples (gather-bound, 256-thread CTAs, no shared memory) needs d_sigma only: it runs on a
+            # side stream under the colour backward (tensor/latency-bound, one 320-thread CTA per SM) and joins before the MLP
+            nbytes = int(_lib.lib().lse_field_density_bwd_workspace(S_cap))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            cur, side = torch.cuda.current_stream(), _side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                call("lse_field_density_bwd_encode", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
+                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(ws), nbytes, stream())
+            call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
+                 P(h16), P(d_rgb), P(d_h16), P(gd), stream())
+            cur.wait_stream(side)
+            call("lse_field_density_bwd_finish", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
+                 P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), P(ws), nbytes, stream())
+            ws.record_stream(side)
+        else:
+            call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
+                 P(h16), P(d_rgb), P(d_h16), P(gd), stream())
+            _density_bwd(fw, cp, cg, o, d, m.ray_indices, m.t_starts, m.t_ends, S_cap, m.total, h16, d_sigma, d_h16, g_o, gd)
         return (g_o, g_d if need_d else None, None, None, None, None, *[ret[k] for k in names])
 
 

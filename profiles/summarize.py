@@ -14,8 +14,8 @@ import subprocess
 import sys
 
 ABI_OF = {"density_fwd_tc_kernel": "lse_field_density_fwd", "color_fwd_tc_kernel": "lse_field_color_fwd",
-          "color_bwd_tc_kernel": "lse_field_color_bwd", "encode_samples_kernel": "lse_field_density_bwd_ws",
-          "density_mlp_bwd_tc_kernel": "lse_field_density_bwd_ws", "scatter_samples_kernel": "lse_field_density_bwd_ws"}
+          "color_bwd_tc_kernel": "lse_field_color_bwd", "encode_samples_kernel": "lse_field_density_bwd_encode",
+          "density_mlp_bwd_tc_kernel": "lse_field_density_bwd_finish", "scatter_samples_kernel": "lse_field_density_bwd_finish"}
 
 
 def short(name):
