@@ -239,6 +239,7 @@ class GraphedStep:
         self.use_graph = use_graph
         dm = pipeline.datamanager
         dm.lean = True                      # captured step: no launches for metadata the fused path never reads
+        pipeline.lean = True                # ... nor for outputs the loss never reads (depth, detached linear, metrics)
         hc, he = dm.sample_host_batches()
         self.stage = BatchStage(hc, he, dm.device)
         self.stage.pack_host(hc, he); self.stage.upload()

@@ -27,6 +27,10 @@ class LSEOccGridEstimator(nn.Module):
         self.register_buffer("occ_mean", torch.zeros(1), persistent=False)
         self._mean_valid = False
         # bit-packed copy of `binaries` + 8^3-superblock mip read by the marching kernels; repacked when the grid changes
+        # the grid update draws its cells / jitter from a private generator with a fixed seed: replicas of a multi-GPU run hold
+        # identical weights, so they derive identical grids without any exchange
+        self._gen: Optional[torch.Generator] = None
+        self.update_seed = 0x5EED
         self._bits: Optional[Tensor] = None
         self._mip: Optional[Tensor] = None
         self._packed_key = None
@@ -93,19 +97,23 @@ class LSEOccGridEstimator(nn.Module):
             return
         dev = self.occs.device
         N = self.cells_per_lvl
+        if self._gen is None or self._gen.device != dev:
+            self._gen = torch.Generator(device=dev)
+            self._gen.manual_seed(self.update_seed)
+        gen = self._gen
         idx_all, occ_all = [], []
         for l in range(self.levels):
             if step < warmup_steps:
                 idx = torch.arange(N, device=dev)
             else:
-                uni = torch.randint(N, (N // 4,), device=dev)
+                uni = torch.randint(N, (N // 4,), device=dev, generator=gen)
                 occ_idx = torch.nonzero(self.binaries[l].flatten())[:, 0]
                 if occ_idx.numel() > N // 4:
-                    occ_idx = occ_idx[torch.randint(occ_idx.numel(), (N // 4,), device=dev)]
+                    occ_idx = occ_idx[torch.randint(occ_idx.numel(), (N // 4,), device=dev, generator=gen)]
                 idx = torch.cat([uni, occ_idx], dim=0)
             r = self.res
             coords = torch.stack([idx // (r * r), (idx // r) % r, idx % r], dim=-1).float()
-            x = (coords + torch.rand_like(coords)) / r
+            x = (coords + torch.rand(coords.shape, device=dev, generator=gen)) / r
             lo, hi = self.aabbs[l, :3], self.aabbs[l, 3:]
             occ = occ_eval_fn(lo + x * (hi - lo)).reshape(-1)
             idx_all.append(idx + l * N); occ_all.append(occ)

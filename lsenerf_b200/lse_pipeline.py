@@ -23,6 +23,9 @@ class LSENeRFPipeline(nn.Module):
         # the three forwards of lse_pipeline.py:115-123 are independent given the same weights: issue them as ONE launch
         # chain over the concatenated bundle (identical per-ray results), then split the outputs.
         self.fuse_bundles = fuse_bundles
+        # lean = the captured training step: skip outputs the loss never reads (depth, detached "linear", metrics) -- each is a
+        # handful of tiny launches.  Off by default: get_train_loss_dict() then returns everything upstream returns.
+        self.lean = False
 
     @property
     def model(self):
@@ -43,7 +46,7 @@ class LSENeRFPipeline(nn.Module):
                 prev_out = m(prev_bundle, raybd2=next_bundle, batch=batch, ev_out=True)
                 next_out = m(next_bundle, raybd2=prev_bundle, batch=batch, keep=True, ev_out=True)
         out_dict = {"col_out": col_out, "prev_out": prev_out, "next_out": next_out}
-        metrics_dict = m.get_metrics_dict(out_dict, batch)
+        metrics_dict = {} if self.lean else m.get_metrics_dict(out_dict, batch)
         loss_dict = m.get_loss_dict(out_dict, batch, metrics_dict)
         return out_dict, loss_dict, metrics_dict
 
@@ -52,12 +55,10 @@ class LSENeRFPipeline(nn.Module):
         # the fused render reads origins / directions (+ the appearance id of per-frame embeddings) only
         big = concat_bundles([col, prev, nxt], fields=("origins", "directions"), metadata_keys=("appearance_id",))
         n0, n1 = len(col), len(prev)
-        raw = m.exec_get_outputs(big)
-        outs = []
-        for lo, hi, ev in ((0, n0, False), (n0, n0 + n1, True), (n0 + n1, n0 + 2 * n1, True)):
-            part = {k: v[lo:hi] for k, v in raw.items()}
-            outs.append(self._finish(part, ev))
-        return outs
+        raw = m.exec_get_outputs(big, with_depth=not self.lean)
+        # one split per tensor (its backward is a single cat, where three slices would be three zero-fills + copies + adds)
+        parts = {k: v.split([n0, n1, n1]) for k, v in raw.items() if v is not None}
+        return [self._finish({k: v[i] for k, v in parts.items()}, ev) for i, ev in enumerate((False, True, True))]
 
     def _finish(self, out, ev_out):
         """the post-compositing half of LSENeRFModel.get_outputs applied to a slice of the fused render."""
@@ -72,7 +73,8 @@ class LSENeRFPipeline(nn.Module):
         out["rgb"] = rgb_final
         if ev.numel() > 0:
             out["ev_out"] = ev
-            out["linear"] = torch.clamp(lin.detach(), 1e-5)
+            if not self.lean:
+                out["linear"] = torch.clamp(lin.detach(), 1e-5)
             if c.map_mode == "co_map":
                 out["ev_linear"] = ev_lin
         return out

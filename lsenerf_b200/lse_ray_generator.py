@@ -19,9 +19,14 @@ class RayGenerator(nn.Module):
         self.pose_optimizer = pose_optimizer
         self.register_buffer("image_coords", cameras.get_image_coords(), persistent=False)
 
+    @staticmethod
+    def _coords(y: Tensor, x: Tensor) -> Tensor:
+        """image_coords[y, x]: the table holds integer pixel coordinates (lse_cameras.py:69-73), i.e. (y, x) themselves."""
+        return torch.stack([y, x], dim=-1).to(torch.float32)
+
     def forward(self, ray_indices: Tensor) -> RayBundle:
         c, y, x = ray_indices[:, 0], ray_indices[:, 1], ray_indices[:, 2]
-        coords = self.image_coords[y, x]
+        coords = self._coords(y, x)
         return self.cameras.generate_rays(camera_indices=c.unsqueeze(-1), coords=coords)
 
 
@@ -30,7 +35,7 @@ class ConsecRayGenerator(RayGenerator):
 
     def forward(self, ray_indices: Tensor):
         c, y, x = ray_indices[:, 0], ray_indices[:, 1], ray_indices[:, 2]
-        coords = self.image_coords[y, x]
+        coords = self._coords(y, x)
         prev = self.cameras.generate_rays(camera_indices=c.unsqueeze(-1), coords=coords)
         nxt = self.cameras.generate_rays(camera_indices=c.unsqueeze(-1) + 1, coords=coords)
         return prev, nxt
@@ -45,7 +50,7 @@ class PrevNextRayGenerator(RayGenerator):
 
     def forward(self, ray_indices: Tensor):
         c, y, x = ray_indices[:, 0], ray_indices[:, 1], ray_indices[:, 2]
-        coords = self.image_coords[y, x]
+        coords = self._coords(y, x)
         return (self.prev_cameras.generate_rays(camera_indices=c.unsqueeze(-1), coords=coords),
                 self.next_cameras.generate_rays(camera_indices=c.unsqueeze(-1), coords=coords))
 
@@ -66,7 +71,7 @@ class DeblurRayGenerator(RayGenerator):
         cams.get_c2w_fn = MethodType(get_deblur_c2w, cams)
         try:
             c, y, x = ray_indices[:, 0], ray_indices[:, 1], ray_indices[:, 2]
-            coords = self.image_coords[y, x]
+            coords = self._coords(y, x)
             coords = torch.tile(coords[:, None], (1, 4, 1)).reshape(-1, coords.shape[-1])
             bundle = cams.generate_rays(camera_indices=c.unsqueeze(-1), coords=coords)
         finally:

@@ -164,7 +164,8 @@ class LSENeRFModel(nn.Module):
                               far=c.far_plane, step=float(c.render_step_size), cone=c.cone_angle, alpha_thre=c.alpha_thre,
                               early_stop_eps=1e-4, cull=self.training, samples_per_ray_cap=c.samples_per_ray_cap)
 
-    def exec_get_outputs(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None, opts: Optional[ops.RenderOpts] = None):
+    def exec_get_outputs(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None, opts: Optional[ops.RenderOpts] = None,
+                         with_depth: bool = True):
         """lsenerf.py:278-326: sampler -> field -> weights -> renderers, as one fused autograd node."""
         R = len(ray_bundle)
         dev = ray_bundle.origins.device
@@ -179,7 +180,10 @@ class LSENeRFModel(nn.Module):
                                                    jitter if self.training else None, app)
         if not self.training and not isinstance(self.renderer_rgb, LinearRenderer):
             rgb = torch.clamp(rgb, 0.0, 1.0)  # RGBRenderer eval clamp (nan_to_num is a no-op on sigmoid outputs)
-        return {"rgb": rgb, "accumulation": acc, "depth": ops.finalize_depth(dnum, acc, mm), "num_samples_per_ray": nspr}
+        out = {"rgb": rgb, "accumulation": acc, "num_samples_per_ray": nspr}
+        if with_depth:
+            out["depth"] = ops.finalize_depth(dnum, acc, mm)
+        return out
 
     def _epilogue_cfg(self, ev_out: bool):
         c = self.config
