@@ -330,10 +330,14 @@ def run_b200(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     hb = dm.sample_host_batches()
+    pending = None
     for i in range(K):
-        out = gs.step(host_batches=hb)      # pack into pinned staging + H2D + graph replays, all asynchronous
-        hb = dm.sample_host_batches()       # host pixel draw + gather of the NEXT batch overlaps the device step
-        host_loss = out.cpu()               # D2H read of this step's losses (synchronises)
+        rb = gs.step_async(host_batches=hb)     # pack into pinned staging + H2D + graph replays + D2H of the losses, all asynchronous
+        hb = dm.sample_host_batches()           # host pixel draw + gather of the NEXT batch overlaps the device step
+        if pending is not None:
+            host_loss = pending.get()           # losses of the PREVIOUS step on the host (waits for that copy only)
+        pending = rb
+    host_loss = pending.get()
     f1.record()
     barrier()
     clk = clocks.stop()

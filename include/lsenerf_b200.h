@@ -107,6 +107,14 @@ int lse_march_pack(const float *slabs, int max_per_ray, const int32_t *counts, c
                    int64_t S_cap, int32_t *ray_indices, float *t_starts, float *t_ends, int32_t *overflow_dev,
                    lse_stream_t stream);
 
+/* One generation of the early-terminating culling pass (exactly the kept set of render_visibility_from_density, lse_grid_estimator.py:
+ * 109-127, without evaluating the field behind opaque surfaces): for every ray still visible after its first `lo` samples
+ * (transmittance from depth_acc [n_rays] + sigmas over [prev_lo, lo) >= early_stop_eps) append the ids of its samples [lo, hi) to
+ * sample_list and bump *n_list_dev.  Call with prev_lo == lo == 0 for the first generation; sigmas must be zero-filled beforehand. */
+int lse_cull_generation(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
+                        const float *t_ends, const float *sigmas, float *depth_acc, int prev_lo, int lo, int hi,
+                        float early_stop_eps, int32_t *sample_list, int64_t list_cap, int32_t *n_list_dev, lse_stream_t stream);
+
 /* 3P nerfacc.render_visibility_from_density (lse_nerf/lse_grid_estimator.py:109-127,139-143):
  * per ray, T = exp(-exclusive_sum(sigma*dt)), alpha = 1-exp(-sigma*dt), keep = T >= early_stop_eps &&
  * alpha >= min(alpha_thre, *occ_mean_dev).  Writes keep [S] (uint8) and keep_counts [n_rays]. */
@@ -172,6 +180,11 @@ typedef struct {
 int lse_field_density_fwd(const LseFieldParams *p /*[host]*/, const float *origins, const float *directions,
                           const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap,
                           const int32_t *n_dev, float *sigma, float *h16, lse_stream_t stream);
+/* The same forward over an explicit list of sample ids (int32 [list_cap], live prefix *n_list_dev): thread j evaluates sample
+ * sample_list[j] and writes sigma / h16 at that sample's own slot.  Used by the early-terminating culling pass. */
+int lse_field_density_fwd_list(const LseFieldParams *p /*[host]*/, const float *origins, const float *directions,
+                               const int32_t *ray_idx, const float *t0, const float *t1, const int32_t *sample_list,
+                               int64_t list_cap, const int32_t *n_list_dev, float *sigma, float *h16, lse_stream_t stream);
 /* d_sigma [S], d_h16 [S,16] (col 0 ignored; geo grads in cols 1..15) -> parameter grads, and when not NULL
  * d_origins/d_directions [n_rays,3] (atomically accumulated per ray). */
 int lse_field_density_bwd(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,

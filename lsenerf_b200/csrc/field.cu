@@ -6,8 +6,8 @@
 
 namespace lse {
 int simt_density_fwd(const LseFieldParams &P, const float *origins, const float *directions, const int32_t *ray_idx,
-                     const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, float *sigma, float *h16,
-                     cudaStream_t st);
+                     const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, const int32_t *list, float *sigma,
+                     float *h16, cudaStream_t st);
 int simt_color_fwd(const LseFieldParams &P, const float *directions, const int32_t *ray_idx, const int32_t *app_id,
                    int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb, cudaStream_t st);
 int simt_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *directions, const int32_t *ray_idx,
@@ -18,8 +18,8 @@ int simt_density_bwd(const LseFieldParams &P, const LseFieldGrads &G, const floa
                      const float *h16, const float *d_sigma, const float *d_h16, float *d_origins, float *d_directions,
                      cudaStream_t st);
 int tc_density_fwd(const LseFieldParams &P, const float *origins, const float *directions, const int32_t *ray_idx,
-                   const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, float *sigma, float *h16,
-                   cudaStream_t st);
+                   const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, const int32_t *list, float *sigma,
+                   float *h16, cudaStream_t st);
 int tc_color_fwd(const LseFieldParams &P, const float *directions, const int32_t *ray_idx, const int32_t *app_id,
                  int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb, cudaStream_t st);
 int tc_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *directions, const int32_t *ray_idx,
@@ -47,8 +47,23 @@ extern "C" int lse_field_density_fwd(const LseFieldParams *p, const float *origi
     LSE_CHECK_ARG(p->W1 && p->b1 && p->W2 && p->b2, "base MLP weights missing");
     LSE_CHECK_ARG(origins && h16, "origins / h16 missing");
     if (S_cap <= 0) return 0;
-    if (p->use_tensor_cores) return tc_density_fwd(*p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, sigma, h16, (cudaStream_t)stream);
-    return simt_density_fwd(*p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, sigma, h16, (cudaStream_t)stream);
+    if (p->use_tensor_cores) return tc_density_fwd(*p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, nullptr, sigma, h16, (cudaStream_t)stream);
+    return simt_density_fwd(*p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, nullptr, sigma, h16, (cudaStream_t)stream);
+}
+
+extern "C" int lse_field_density_fwd_list(const LseFieldParams *p, const float *origins, const float *directions,
+                                          const int32_t *ray_idx, const float *t0, const float *t1, const int32_t *sample_list,
+                                          int64_t list_cap, const int32_t *n_list_dev, float *sigma, float *h16,
+                                          lse_stream_t stream)
+{
+    int rc = check_params(p, __func__);
+    if (rc) return rc;
+    LSE_CHECK_ARG(p->W1 && p->b1 && p->W2 && p->b2, "base MLP weights missing");
+    LSE_CHECK_ARG(origins && h16 && sample_list, "origins / h16 / sample_list missing");
+    if (list_cap <= 0) return 0;
+    if (p->use_tensor_cores)
+        return tc_density_fwd(*p, origins, directions, ray_idx, t0, t1, list_cap, n_list_dev, sample_list, sigma, h16, (cudaStream_t)stream);
+    return simt_density_fwd(*p, origins, directions, ray_idx, t0, t1, list_cap, n_list_dev, sample_list, sigma, h16, (cudaStream_t)stream);
 }
 
 extern "C" int lse_field_density_bwd(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,

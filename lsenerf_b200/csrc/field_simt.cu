@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(TS) density_fwd_kernel(LseFieldParams P, const
                                                          const float *__restrict__ directions,
                                                          const int32_t *__restrict__ ray_idx, const float *__restrict__ t0,
                                                          const float *__restrict__ t1, int64_t S_cap,
-                                                         const int32_t *__restrict__ n_dev, float *__restrict__ sigma,
-                                                         float *__restrict__ h16)
+                                                         const int32_t *__restrict__ n_dev, const int32_t *__restrict__ list,
+                                                         float *__restrict__ sigma, float *__restrict__ h16)
 {
     __shared__ __align__(16) float sW1[NH * NF];
     __shared__ __align__(16) float sW2[NO * NH];
@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(TS) density_fwd_kernel(LseFieldParams P, const
     __syncthreads();
     const int64_t S = live_count(n_dev, S_cap);
     const float2 *table = reinterpret_cast<const float2 *>(P.table);
-    for (int64_t i = blockIdx.x * (int64_t)TS + threadIdx.x; i < S; i += (int64_t)gridDim.x * TS) {
+    for (int64_t j = blockIdx.x * (int64_t)TS + threadIdx.x; j < S; j += (int64_t)gridDim.x * TS) {
+        const int64_t i = list ? (int64_t)list[j] : j;
         SampleGeom g;
         load_geom(i, origins, directions, ray_idx, t0, t1, g);
         float feat[NF];
@@ -443,10 +444,10 @@ static int persistent_grid(int64_t S_cap, int ctas_per_sm)
 }
 
 int simt_density_fwd(const LseFieldParams &P, const float *origins, const float *directions, const int32_t *ray_idx,
-                     const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, float *sigma, float *h16,
-                     cudaStream_t st)
+                     const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, const int32_t *list, float *sigma,
+                     float *h16, cudaStream_t st)
 {
-    density_fwd_kernel<<<persistent_grid(S_cap, 4), TS, 0, st>>>(P, origins, directions, ray_idx, t0, t1, S_cap, n_dev, sigma, h16);
+    density_fwd_kernel<<<persistent_grid(S_cap, 4), TS, 0, st>>>(P, origins, directions, ray_idx, t0, t1, S_cap, n_dev, list, sigma, h16);
     return check_launch("lse_field_density_fwd");
 }
 

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
                                                                     const int32_t *__restrict__ ray_idx,
                                                                     const float *__restrict__ t0, const float *__restrict__ t1,
                                                                     int64_t S_cap, const int32_t *__restrict__ n_dev,
+                                                                    const int32_t *__restrict__ list,
                                                                     float *__restrict__ sigma, float *__restrict__ h16)
 {
     extern __shared__ __align__(1024) float smem[];
@@ -103,8 +104,9 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
     const int64_t n_tiles = (S + WG - 1) / WG;
     const float2 *table = reinterpret_cast<const float2 *>(P.table);
     for (int64_t tile = (int64_t)blockIdx.x * NWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * NWG) {
-        const int64_t i = tile * WG + row;
-        const bool live = i < S;
+        const int64_t j = tile * WG + row;
+        const bool live = j < S;
+        const int64_t i = (list && live) ? (int64_t)list[j] : j;     // optional indirection: the samples to evaluate
         SampleGeom g;
         g.cc.sel = false;
         float feat[NF];
@@ -263,13 +265,14 @@ static int tc_grid(int64_t S_cap)
 }
 
 int tc_density_fwd(const LseFieldParams &P, const float *origins, const float *directions, const int32_t *ray_idx,
-                   const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, float *sigma, float *h16,
-                   cudaStream_t st)
+                   const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, const int32_t *list, float *sigma,
+                   float *h16, cudaStream_t st)
 {
     constexpr size_t smem_bytes = DensitySmem::TOTAL * sizeof(float) + kCtrlBytes;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(density_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
-    density_fwd_tc_kernel<<<tc_grid(S_cap), WG * NWG, smem_bytes, st>>>(P, origins, directions, ray_idx, t0, t1, S_cap, n_dev, sigma, h16);
+    density_fwd_tc_kernel<<<tc_grid(S_cap), WG * NWG, smem_bytes, st>>>(P, origins, directions, ray_idx, t0, t1, S_cap, n_dev, list, sigma,
+                                                                        h16);
     return check_launch("lse_field_density_fwd[tc]");
 }
 

@@ -388,6 +388,48 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t *__rest
     if (threadIdx.x == 0 && total) *total = carry_s;
 }
 
+// ---- early-terminating culling pass ------------------------------------------------------------------------------------------
+// render_visibility_from_density keeps a sample iff T >= early_stop_eps and alpha >= alpha_thre, with T = exp(-sum of sigma*dt of the
+// samples BEFORE it).  sigma >= 0, so T never increases along a ray: once it is below eps no later sample can be kept whatever
+// its density, and evaluating the field there is wasted work.  The culling pass therefore runs in generations: generation g
+// evaluates the samples [lo_g, hi_g) of every ray that is still visible after its first lo_g samples.  This kernel (warp per ray)
+// advances the ray's running optical depth over the previous generation and, if the ray is still alive, appends its sample ids for
+// this generation to a list (contiguous per ray) that the density kernel consumes through a device-side count.  Samples never
+// evaluated keep sigma = 0 (the caller zero-fills), which the visibility kernel maps to "not kept" exactly like the reference maps
+// their true density (alpha_thre > 0; the dead test carries a 0.1 % margin against the different summation order there).
+__global__ void cull_generation_kernel(const int32_t *__restrict__ starts, const int32_t *__restrict__ counts, int64_t n_rays,
+                                       const float *__restrict__ t_starts, const float *__restrict__ t_ends,
+                                       const float *__restrict__ sigmas, float *__restrict__ depth_acc, int prev_lo, int lo, int hi,
+                                       float early_stop_eps, int32_t *__restrict__ list, int64_t list_cap, int32_t *__restrict__ n_list)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rays; r += n_warps) {
+        const int64_t s = starts[r];
+        const int32_t c = counts[r];
+        if (c <= lo) continue;
+        float acc = prev_lo < lo ? depth_acc[r] : 0.0f;
+        if (prev_lo < lo) {
+            if (acc < 0.0f) continue;                         // died in an earlier generation
+            float part = 0.0f;
+            for (int32_t k = prev_lo + lane; k < lo; k += 32) part += sigmas[s + k] * (t_ends[s + k] - t_starts[s + k]);
+            acc += warp_sum(part);
+            const bool dead = early_stop_eps > 0.0f && expf(-acc) < early_stop_eps * 0.999f;
+            if (lane == 0) depth_acc[r] = dead ? -1.0f : acc;
+            if (dead) continue;
+        } else if (lane == 0) {
+            depth_acc[r] = 0.0f;
+        }
+        const int32_t n = (c < hi ? c : hi) - lo;
+        int32_t base = 0;
+        if (lane == 0) base = atomicAdd(n_list, n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int32_t k = lane; k < n; k += 32)
+            if ((int64_t)base + k < list_cap) list[base + k] = (int32_t)(s + lo + k);
+    }
+}
+
 // warp per ray: transmittance scan -> keep mask + kept count
 __global__ void visibility_kernel(const int32_t *__restrict__ starts, const int32_t *__restrict__ counts, int64_t n_rays,
                                   const float *__restrict__ t_starts, const float *__restrict__ t_ends,
@@ -607,6 +649,23 @@ extern "C" int lse_march_fill(const float *rays_o, const float *rays_d, int64_t 
         rays_o, rays_d, n_rays, occ_bits, occ_mip, mip_words, aabbs, levels, res, near_plane, far_plane, jitter, step_size,
         cone_angle, nullptr, starts, S_cap, ray_indices, t_starts, t_ends, overflow_dev, kRayStride);
     return check_launch("lse_march_fill");
+}
+
+extern "C" int lse_cull_generation(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
+                                   const float *t_ends, const float *sigmas, float *depth_acc, int prev_lo, int lo, int hi,
+                                   float early_stop_eps, int32_t *sample_list, int64_t list_cap, int32_t *n_list_dev,
+                                   lse_stream_t stream)
+{
+    LSE_CHECK_ARG(starts && counts && t_starts && t_ends && sigmas && depth_acc && sample_list && n_list_dev, "missing pointer");
+    LSE_CHECK_ARG(0 <= prev_lo && prev_lo <= lo && lo < hi, "generation bounds must satisfy 0 <= prev_lo <= lo < hi");
+    if (n_rays <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(n_list_dev, 0, sizeof(int32_t), st);
+    int threads = 256;
+    cull_generation_kernel<<<stride_grid(n_rays * 32, threads), threads, 0, st>>>(starts, counts, n_rays, t_starts, t_ends, sigmas, depth_acc,
+                                                                                  prev_lo, lo, hi, early_stop_eps, sample_list, list_cap,
+                                                                                  n_list_dev);
+    return check_launch("lse_cull_generation");
 }
 
 extern "C" int lse_visibility(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,

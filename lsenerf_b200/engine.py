@@ -231,6 +231,17 @@ class BatchStage:
         return self.ring.current().to(self.device, non_blocking=False).clone()
 
 
+class LossReadback:
+    """Handle of one step's losses on their way to the host (pinned slot + event): .get() waits for THAT copy only."""
+
+    def __init__(self, slot: torch.Tensor, event) -> None:
+        self.slot, self.event = slot, event
+
+    def get(self) -> torch.Tensor:
+        self.event.synchronize()
+        return self.slot.clone()
+
+
 class GraphedStep:
     """train_iteration (nerfstudio Trainer) as CUDA graph replays."""
 
@@ -248,6 +259,7 @@ class GraphedStep:
         self.loss_out: Optional[torch.Tensor] = None
         self.step_no = 0
         self.local_only = False     # True: step this replica alone (no exchange, grad_scale 1) -- bench burn-in on rank 0
+        self._loss_ring = None      # pinned host slots + events of step_async()
 
     def _fwd_bwd(self) -> torch.Tensor:
         self.optim.zero_grad()
@@ -309,3 +321,16 @@ class GraphedStep:
                 self.optim.apply()
         self.step_no += 1
         return out
+
+    def step_async(self, packed_dev: Optional[torch.Tensor] = None, host_batches=None) -> LossReadback:
+        """step() + an asynchronous D2H copy of the losses into a pinned slot.  The caller reads step k's losses after
+        enqueuing step k+1, so the device never idles on the host's per-step work (pack, H2D, graph launch)."""
+        out = self.step(packed_dev, host_batches)
+        if self._loss_ring is None:
+            self._loss_ring = [[torch.empty(out.shape, dtype=out.dtype).pin_memory(), torch.cuda.Event()] for _ in range(4)]
+            self._loss_i = 0
+        slot, ev = self._loss_ring[self._loss_i % 4]
+        self._loss_i += 1
+        slot.copy_(out, non_blocking=True)
+        ev.record()
+        return LossReadback(slot, ev)

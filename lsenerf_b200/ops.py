@@ -7,6 +7,7 @@ live here, not in the kernels (same split as the reference, which asserts in Pyt
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass, field as dc_field
 from typing import Optional
 
@@ -315,6 +316,33 @@ def field_density_raw(fw: FieldWeights, origins, directions, ray_idx, t0, t1, S_
     return sigma, h16
 
 
+def _cull_bounds():
+    """per-ray sample boundaries of the generations of the early-terminating culling pass (LSE_CULL_BOUNDS overrides)."""
+    env = os.environ.get("LSE_CULL_BOUNDS")
+    b = [int(x) for x in env.split(",")] if env else [40, 160]
+    return [0] + [x for x in b if x > 0] + [1 << 30]
+
+
+def field_density_culling(fw: FieldWeights, origins, directions, m: "MarchResult", early_stop_eps: float):
+    """The density pass that feeds visibility culling (lse_grid_estimator.py:109-127), evaluated in generations along the rays:
+    a ray whose transmittance has fallen below early_stop_eps after its first `lo` samples cannot keep any later sample
+    (sigma >= 0), so the field is not evaluated there; those samples keep sigma = 0, which the visibility test rejects exactly
+    like their true density.  Same kept set as evaluating every marched sample."""
+    dev = origins.device
+    S_cap, R = m.S_cap, m.counts.numel()
+    sigma = torch.zeros(S_cap, device=dev); h16 = torch.empty(S_cap, 16, device=dev)
+    depth = torch.empty(R, device=dev)
+    lst = torch.empty(S_cap, dtype=torch.int32, device=dev); n_list = torch.empty(1, dtype=torch.int32, device=dev)
+    cp = fw.c_params()
+    b = _cull_bounds()
+    for g in range(len(b) - 1):
+        call("lse_cull_generation", P(m.starts), P(m.counts), R, P(m.t_starts), P(m.t_ends), P(sigma), P(depth), b[g - 1] if g else 0,
+             b[g], b[g + 1], float(early_stop_eps), P(lst), S_cap, P(n_list), stream())
+        call("lse_field_density_fwd_list", ctypes.byref(cp), P(origins), P(directions), P(m.ray_indices), P(m.t_starts), P(m.t_ends),
+             P(lst), S_cap, P(n_list), P(sigma), P(h16), stream())
+    return sigma, h16
+
+
 def field_color_raw(fw: FieldWeights, directions, ray_idx, app_id, S_cap, n_dev, h16):
     rgb = torch.empty(S_cap, 3, device=h16.device)
     cp = fw.c_params()
@@ -475,6 +503,7 @@ class RenderOpts:
     early_stop_eps: float = 1e-4
     cull: bool = True                  # training: sigma_fn given (lse_grid_estimator.py:109-143)
     samples_per_ray_cap: int = 512     # packed capacity = R * this
+    early_terminate: bool = True       # culling pass: no field evaluation behind opaque surfaces (same kept set)
     accumulate_into_grad: bool = True  # parameter grads are accumulated straight into p.grad (no 64 MiB temporaries)
     keep_debug: bool = False
     debug: dict = dc_field(default_factory=dict)
@@ -487,8 +516,12 @@ class _RenderRays(torch.autograd.Function):
         R = o.shape[0]
         S_cap = max(1, R * opts.samples_per_ray_cap)
         m0 = march(o, d, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step, opts.cone, jitter, S_cap, opts.occ_packed)
-        sigma, h16 = field_density_raw(fw, o, d, m0.ray_indices, m0.t_starts, m0.t_ends, S_cap, m0.total)
-        if opts.cull and (opts.alpha_thre > 0.0 or opts.early_stop_eps > 0.0):
+        culling = opts.cull and (opts.alpha_thre > 0.0 or opts.early_stop_eps > 0.0)
+        if culling and opts.early_stop_eps > 0.0 and opts.early_terminate:
+            sigma, h16 = field_density_culling(fw, o, d, m0, opts.early_stop_eps)
+        else:
+            sigma, h16 = field_density_raw(fw, o, d, m0.ray_indices, m0.t_starts, m0.t_ends, S_cap, m0.total)
+        if culling:
             m, sigma_c, h16_c, keep = visibility_compact(m0, sigma, h16, opts.early_stop_eps, opts.alpha_thre, opts.occ_mean_dev)
         else:
             m, sigma_c, h16_c, keep = m0, sigma, h16, None

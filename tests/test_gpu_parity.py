@@ -324,12 +324,13 @@ def test_train_step_parity(dev, variant):
         if gref is None:
             assert gcu.abs().max().item() == 0.0, k
             continue
-        # Field / mapper / embedding gradients: 5e-3 end to end (threshold-straddling samples + atomics order) (each kernel's own backward is held to 1e-3 above).  Camera
+        # Field / mapper / embedding gradients: 1e-2 end to end (up to 5 % of the rays keep/drop a threshold-straddling sample, which
+        # moves their whole contribution; which rays do depends on the last bits of sigma; + atomics order) (each kernel's own backward is held to 1e-3 above).  Camera
         # gradients are sums over ~1e5 per-sample position gradients of mixed sign (the hash grid's d/dx is piecewise
         # constant), so both fp32 sides carry cancellation noise: 2e-2 end to end, 1e-3 per kernel in the unit tests.
         # (noise floor: 1e5 mixed-sign fp32 terms of magnitude M accumulated by atomics in arbitrary order carry ~sqrt(1e5)*6e-8*M
         # of rounding noise against a sum of ~1e-3*M -- a few 1e-2 relative on BOTH sides, different from run to run)
-        tol = 5e-2 if "cam_opt" in k else 5e-3
+        tol = 5e-2 if "cam_opt" in k else 1e-2
         assert rel_err(gcu, gref) < tol, (k, rel_err(gcu, gref))
         checked += 1
     assert checked >= 11
@@ -538,3 +539,35 @@ def test_collective_adam_two_gpus(dev):
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29571", os.path.join(here, "dist_collective_check.py")], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_early_terminating_culling_pass_keeps_the_same_samples(dev):
+    """The generation-wise culling pass (no field evaluation once a ray's transmittance is below early_stop_eps) against the
+    plain one (every marched sample evaluated): identical kept samples per ray, bit-identical render, and far fewer evaluations
+    on a scene with opaque surfaces."""
+    import dataclasses
+    from lsenerf_b200 import ops
+    spec = small_spec(grid_res=64, log2_hashmap_size=16, bake_density=True)
+    scene = syn.make_scene(spec, images=False)
+    scene["col_images"] = torch.rand(spec.n_ctrl, *spec.col_hw, 3); scene["evs_images"] = torch.zeros(spec.n_evs_frames, *spec.evs_hw, 1)
+    p = syn.build_pipeline(scene, "lsenerf", num_rays=2048, device=dev, seed=3, pin=False)
+    p.train()
+    m = p._model
+    bundles, _ = p.datamanager.next_train(0)
+    from lsenerf_b200.compat import concat_bundles
+    big = concat_bundles(list(bundles))
+    jit = torch.rand(len(big), generator=torch.Generator().manual_seed(1)).to(dev)
+    outs = {}
+    for et in (False, True):
+        opts = m._render_opts(); opts.early_terminate = et; opts.keep_debug = True
+        with torch.no_grad():
+            o = m.exec_get_outputs(big, jit, opts)
+        outs[et] = (o, opts.debug["sigma0"].clone(), opts.debug["keep"].clone(), int(opts.debug["march0"].total.item()))
+    (a, sa, ka, n), (b, sb, kb, _) = outs[False], outs[True]
+    assert n > 50000
+    assert torch.equal(a["num_samples_per_ray"], b["num_samples_per_ray"]) and torch.equal(ka[:n], kb[:n])
+    assert torch.equal(a["rgb"], b["rgb"]) and torch.equal(a["accumulation"], b["accumulation"])
+    evaluated = int((sb[:n] != 0).sum()) if False else int(((sb[:n] == sa[:n]) & (sa[:n] != 0)).sum())
+    skipped = int(((sb[:n] == 0) & (sa[:n] != 0)).sum())
+    assert skipped > 0.2 * n, (skipped, n)          # opaque ball / slab / dome: a large part of the march is never evaluated
+    assert int(ka[:n].sum()) > 1000
