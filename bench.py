@@ -312,6 +312,7 @@ def run_b200(args):
     e0.record()
     for i in range(K):
         gs.step(packed_dev=staged[W + i])
+    gs.flush()                                # the last step's field optimizer runs on the engine's side stream
     e1.record()
     if args.profiler_window:
         torch.cuda.synchronize()
@@ -338,6 +339,7 @@ def run_b200(args):
             host_loss = pending.get()           # losses of the PREVIOUS step on the host (waits for that copy only)
         pending = rb
     host_loss = pending.get()
+    gs.flush()
     f1.record()
     barrier()
     clk = clocks.stop()

@@ -110,34 +110,40 @@ class ArenaAdam:
         self.groups = {k: a.params for k, a in self.arenas.items()}
         dev = next(iter(self.arenas.values())).data.device
         self.names = list(self.arenas.keys())
-        # ring of pinned host mirrors: the host may run several steps ahead of the device, so a slot is only rewritten after
-        # the H2D copy that read it has completed (event per slot)
-        self.hp_ring = _PinnedRing((len(self.names), 4), torch.float32, dev)
+        # per-arena ring of pinned host mirrors of the 4 hyper-parameter floats: the host may run several steps ahead of the
+        # device, so a slot is only rewritten after the H2D copy that read it has completed (event per slot)
+        self.hp_rings = {n: _PinnedRing((4,), torch.float32, dev) for n in self.names}
         self.hp_dev = torch.zeros(len(self.names), 4, device=dev)
         self.step_count = 0
+        self._grad_scale = 1.0
 
-    def zero_grad(self) -> None:
-        for a in self.arenas.values():
-            a.zero_grad()
+    def zero_grad(self, only: Optional[List[str]] = None) -> None:
+        for n, a in self.arenas.items():
+            if only is None or n in only:
+                a.zero_grad()
 
-    def set_step(self, step_count: int, grad_scale: float = 1.0) -> None:
-        """refresh the device hyper-parameters for optimizer step number `step_count` (1-based)."""
-        self.step_count = step_count
-        host = self.hp_ring.acquire()
-        for i, name in enumerate(self.names):
-            spec = self.specs[name]
-            lr = spec.lr_at(step_count - 1)
-            bc1 = 1.0 - spec.betas[0] ** step_count
-            bc2 = 1.0 - spec.betas[1] ** step_count
-            host[i, 0] = lr / bc1
-            host[i, 1] = math.sqrt(bc2)
-            host[i, 2] = grad_scale
-        self.hp_ring.upload(self.hp_dev)
+    def set_step(self, step_count: int, grad_scale: float = 1.0, upload: bool = True) -> None:
+        """optimizer step number `step_count` (1-based); upload=False defers the H2D refresh to upload_hp(name) (the engine issues
+        it on the stream, and just before the launch, of each arena's optimizer kernel)."""
+        self.step_count, self._grad_scale = step_count, grad_scale
+        if upload:
+            for name in self.names:
+                self.upload_hp(name)
+
+    def upload_hp(self, name: str) -> None:
+        i, spec, step_count = self.names.index(name), self.specs[name], self.step_count
+        host = self.hp_rings[name].acquire()
+        host[0] = spec.lr_at(step_count - 1) / (1.0 - spec.betas[0] ** step_count)
+        host[1] = math.sqrt(1.0 - spec.betas[1] ** step_count)
+        host[2] = self._grad_scale
+        self.hp_rings[name].upload(self.hp_dev[i])
 
     @torch.no_grad()
-    def apply(self) -> None:
+    def apply(self, only: Optional[List[str]] = None) -> None:
         """one fused Adam launch per group, reading hp_dev (graph-capturable)."""
         for i, name in enumerate(self.names):
+            if only is not None and name not in only:
+                continue
             a, spec = self.arenas[name], self.specs[name]
             call("lse_adam_step_hp", P(a.data), P(a.grad), P(a.exp_avg), P(a.exp_avg_sq), a.numel, spec.betas[0], spec.betas[1],
                  spec.eps, P(self.hp_dev[i]), stream())
@@ -147,14 +153,17 @@ class ArenaAdam:
         self.apply()
 
     @torch.no_grad()
-    def apply_collective(self) -> None:
+    def apply_collective(self, only: Optional[List[str]] = None, channel: int = 0) -> None:
         """Exchange + Adam as one kernel per arena over NVLink peer / multicast memory (csrc/adam_collective.cu), bracketed by
-        two symmetric-memory barriers.  Replaces allreduce() + apply() when the arenas are symmetric."""
+        two symmetric-memory barriers (signal-pad channels `channel`, `channel`+1: concurrent calls on different streams must use
+        different channels).  Replaces allreduce() + apply() when the arenas are symmetric."""
         import ctypes
         assert self.symmetric, "apply_collective needs arenas allocated in symmetric memory"
-        first = self.arenas[self.names[0]]
-        first.h_grad.barrier(channel=0)                       # every rank's backward has finished writing gradients
-        for i, name in enumerate(self.names):
+        names = [n for n in self.names if only is None or n in only]
+        first = self.arenas[names[0]]
+        first.h_grad.barrier(channel=channel)                 # every rank's backward has finished writing gradients
+        for name in names:
+            i = self.names.index(name)
             a, spec = self.arenas[name], self.specs[name]
             W, r = a.h_data.world_size, a.h_data.rank
             pp = (ctypes.c_void_p * W)(*[int(p) for p in a.h_data.buffer_ptrs])
@@ -164,7 +173,7 @@ class ArenaAdam:
             call("lse_adam_step_collective", ctypes.cast(pp, ctypes.c_void_p), ctypes.cast(pg, ctypes.c_void_p),
                  ctypes.c_void_p(mc_p) if use_mc else None, ctypes.c_void_p(mc_g) if use_mc else None, P(a.exp_avg),
                  P(a.exp_avg_sq), a.numel, r, W, spec.betas[0], spec.betas[1], spec.eps, P(self.hp_dev[i]), stream())
-        first.h_data.barrier(channel=1)                       # every slice written before anybody reads weights / zeroes grads
+        first.h_data.barrier(channel=channel + 1)             # every slice written before anybody reads weights / zeroes grads
 
     def exchange_kind(self) -> str:
         if not self.symmetric:
@@ -243,7 +252,16 @@ class LossReadback:
 
 
 class GraphedStep:
-    """train_iteration (nerfstudio Trainer) as CUDA graph replays."""
+    """train_iteration (nerfstudio Trainer) as CUDA graph replays, software-pipelined across steps.
+
+    One iteration = graph A (zero the camera gradients, ray generation, occupancy-grid march: depends on the camera parameters
+    and the grid only) -> graph B (zero the field gradients, culling pass, field, compositing, losses, backward) -> the camera
+    optimizer (tiny, same stream) and the FIELD optimizer / gradient exchange on a side stream.  A of step k+1 does not read the
+    field weights, so it runs while the side stream is still streaming 16.8 M parameters through Adam (or through the fused
+    reduce-scatter + Adam + all-gather kernel); B of step k+1 waits for it.  The march is latency bound and leaves the memory
+    system idle, the optimizer is pure bandwidth: they overlap almost perfectly."""
+
+    FIELD_GROUP = "fields"
 
     def __init__(self, pipeline: LSENeRFPipeline, optim: ArenaAdam, world_size: int = 1, use_graph: bool = True) -> None:
         self.pipeline, self.optim, self.world = pipeline, optim, world_size
@@ -254,16 +272,27 @@ class GraphedStep:
         hc, he = dm.sample_host_batches()
         self.stage = BatchStage(hc, he, dm.device)
         self.stage.pack_host(hc, he); self.stage.upload()
-        self.graph_fb: Optional[torch.cuda.CUDAGraph] = None
-        self.graph_opt: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_a: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_b: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_opt: Dict[str, torch.cuda.CUDAGraph] = {}
         self.loss_out: Optional[torch.Tensor] = None
+        self.ctx: Optional[dict] = None
         self.step_no = 0
         self.local_only = False     # True: step this replica alone (no exchange, grad_scale 1) -- bench burn-in on rank 0
         self._loss_ring = None      # pinned host slots + events of step_async()
+        self.side = torch.cuda.Stream(device=dm.device) if torch.cuda.is_available() else None
+        self.ev_b = torch.cuda.Event() if self.side is not None else None
+        self.ev_opt: Optional[torch.cuda.Event] = None        # field optimizer of the previous step (side stream)
+        self.early = [n for n in optim.names if n != self.FIELD_GROUP]   # groups stepped on the main stream right after B
 
-    def _fwd_bwd(self) -> torch.Tensor:
-        self.optim.zero_grad()
-        _, loss_dict, _ = self.pipeline.get_train_loss_dict(self.step_no, self.stage.device_batches())
+    # ---- the two halves of an iteration -----------------------------------------------------------------------------------------
+    def _phase_a(self) -> None:
+        self.optim.zero_grad(only=self.early)
+        self.ctx = self.pipeline.prepare_train(self.step_no, self.stage.device_batches(), premarch=True)
+
+    def _phase_b(self) -> torch.Tensor:
+        self.optim.zero_grad(only=[self.FIELD_GROUP])
+        _, loss_dict, _ = self.pipeline.finish_train(self.ctx)
         loss = sum(loss_dict.values())
         loss.backward()
         return torch.stack([v.detach() for v in loss_dict.values()])
@@ -275,23 +304,53 @@ class GraphedStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(3):                       # warm-up on a side stream (allocator, lazy inits, attribute calls)
-                self._fwd_bwd()
+                self._phase_a(); self._phase_b()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if not self.use_graph:
             return
-        self.graph_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_fb):
-            self.loss_out = self._fwd_bwd()
-        self.graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_opt):
-            self.optim.apply()
+        self.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self._phase_a()
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+            self.loss_out = self._phase_b()
+        for name in self.optim.names:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.graph_a.pool()):
+                self.optim.apply(only=[name])
+            self.graph_opt[name] = g
+
+    def _optimize(self, names, world: int, channel: int) -> None:
+        """optimizer (+ exchange) of `names` on the current stream."""
+        for n in names:
+            self.optim.upload_hp(n)
+        if world > 1 and self.optim.symmetric:
+            self.optim.apply_collective(only=names, channel=channel)
+        else:
+            if world > 1:
+                import torch.distributed as dist
+                for n in names:
+                    dist.all_reduce(self.optim.arenas[n].grad, op=dist.ReduceOp.SUM)
+            for n in names:
+                if n in self.graph_opt:
+                    self.graph_opt[n].replay()
+                else:
+                    self.optim.apply(only=[n])
+
+    def flush(self) -> None:
+        """make the current stream wait for the field optimizer still in flight on the side stream."""
+        if self.ev_opt is not None:
+            torch.cuda.current_stream().wait_event(self.ev_opt)
 
     def step(self, packed_dev: Optional[torch.Tensor] = None, host_batches=None) -> torch.Tensor:
         """one training iteration; returns the (device) loss vector.  Either a pre-staged packed device batch or host
         batches from MultiCamManager.sample_host_batches()."""
-        self.pipeline.model.update_occupancy(self.step_no)       # eager, every 16th step
-        self.pipeline.model.occupancy_grid.packed()              # host-side version check; repacks only if binaries were edited
+        model = self.pipeline.model
+        if self.step_no % 16 == 0:
+            self.flush()                                 # the grid update evaluates the field: it needs the updated weights
+        model.update_occupancy(self.step_no)             # eager, every 16th step
+        model.occupancy_grid.packed()                    # host-side version check; repacks only if binaries were edited
         if packed_dev is not None:
             self.stage.load_packed(packed_dev)
         else:
@@ -300,25 +359,28 @@ class GraphedStep:
             self.stage.pack_host(*host_batches)
             self.stage.upload()
         world = 1 if self.local_only else self.world
-        self.optim.set_step(self.optim.step_count + 1, 1.0 / world if world > 1 else 1.0)
-        fused = world > 1 and self.optim.symmetric
-        if self.graph_fb is not None:
-            self.graph_fb.replay()
-            if fused:
-                self.optim.apply_collective()
-            else:
-                if world > 1:
-                    self.optim.allreduce()
-                self.graph_opt.replay()
+        self.optim.set_step(self.optim.step_count + 1, 1.0 / world if world > 1 else 1.0, upload=False)
+        main = torch.cuda.current_stream()
+        # A: rays + march (camera parameters and grid only) -- overlaps the previous step's field optimizer
+        if self.graph_a is not None:
+            self.graph_a.replay()
+        else:
+            self._phase_a()
+        self.flush()
+        # B: everything that reads the field weights, and the backward
+        if self.graph_b is not None:
+            self.graph_b.replay()
             out = self.loss_out
         else:
-            out = self._fwd_bwd()
-            if fused:
-                self.optim.apply_collective()
-            else:
-                if world > 1:
-                    self.optim.allreduce()
-                self.optim.apply()
+            out = self._phase_b()
+        self.ev_b.record(main)
+        if self.early:
+            self._optimize(self.early, world, channel=2)
+        self.side.wait_event(self.ev_b)
+        with torch.cuda.stream(self.side):
+            self._optimize([self.FIELD_GROUP], world, channel=0)
+            self.ev_opt = torch.cuda.Event()
+            self.ev_opt.record(self.side)
         self.step_no += 1
         return out
 

@@ -33,12 +33,42 @@ class LSENeRFPipeline(nn.Module):
 
     def get_train_loss_dict(self, step: int, prefetched=None):
         """lse_pipeline.py:110-145 -> (out_dict, loss_dict, metrics_dict)."""
+        return self.finish_train(self.prepare_train(step, prefetched))
+
+    def prepare_train(self, step: int, prefetched=None, premarch: bool = False) -> dict:
+        """First half of get_train_loss_dict: everything that depends on the camera parameters and the occupancy grid but NOT on
+        the field weights -- batch, ray bundles and (premarch=True, fused bundles) the occupancy-grid march.  The engine runs it
+        while the previous step's optimizer is still updating the field."""
         bundles, batch = self.datamanager.next_train(step, prefetched)
-        col_bundle, prev_bundle, next_bundle = bundles
+        ctx = {"bundles": bundles, "batch": batch}
+        col, prev, nxt = bundles
+        m = self._model
+        if self.fuse_bundles and col is not None and prev is not None:
+            # the three forwards of lse_pipeline.py:115-123 are independent given the weights: one launch chain over the
+            # concatenated bundle; the fused render reads origins / directions (+ the appearance id of per-frame embeddings) only
+            big = concat_bundles([col, prev, nxt], fields=("origins", "directions"), metadata_keys=("appearance_id",))
+            ctx["big"], ctx["sizes"] = big, (len(col), len(prev), len(nxt))
+            if premarch and m.training:
+                opts = m._render_opts()
+                jitter = torch.rand(len(big), device=big.origins.device)
+                S_cap = max(1, len(big) * opts.samples_per_ray_cap)
+                opts.premarched = ops.march(big.origins, big.directions, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step,
+                                            opts.cone, jitter, S_cap, opts.occ_packed)
+                ctx["opts"], ctx["jitter"] = opts, jitter
+        return ctx
+
+    def finish_train(self, ctx: dict):
+        """Second half: field evaluation, compositing, epilogue, losses."""
+        batch = ctx["batch"]
+        col_bundle, prev_bundle, next_bundle = ctx["bundles"]
         col_out = prev_out = next_out = None
         m = self._model
-        if self.fuse_bundles and col_bundle is not None and prev_bundle is not None:
-            col_out, prev_out, next_out = self._fused_forward(col_bundle, prev_bundle, next_bundle)
+        if "big" in ctx:
+            n0, n1, n2 = ctx["sizes"]
+            raw = m.exec_get_outputs(ctx["big"], ctx.get("jitter"), ctx.get("opts"), with_depth=not self.lean)
+            # one split per tensor (its backward is a single cat, where three slices would be three zero-fills + copies + adds)
+            parts = {k: v.split([n0, n1, n2]) for k, v in raw.items() if v is not None}
+            col_out, prev_out, next_out = [self._finish({k: v[i] for k, v in parts.items()}, ev) for i, ev in enumerate((False, True, True))]
         else:
             if col_bundle is not None and len(col_bundle) > 0:
                 col_out = m(col_bundle, ev_out=False)
@@ -49,16 +79,6 @@ class LSENeRFPipeline(nn.Module):
         metrics_dict = {} if self.lean else m.get_metrics_dict(out_dict, batch)
         loss_dict = m.get_loss_dict(out_dict, batch, metrics_dict)
         return out_dict, loss_dict, metrics_dict
-
-    def _fused_forward(self, col, prev, nxt):
-        m = self._model
-        # the fused render reads origins / directions (+ the appearance id of per-frame embeddings) only
-        big = concat_bundles([col, prev, nxt], fields=("origins", "directions"), metadata_keys=("appearance_id",))
-        n0, n1 = len(col), len(prev)
-        raw = m.exec_get_outputs(big, with_depth=not self.lean)
-        # one split per tensor (its backward is a single cat, where three slices would be three zero-fills + copies + adds)
-        parts = {k: v.split([n0, n1, n1]) for k, v in raw.items() if v is not None}
-        return [self._finish({k: v[i] for k, v in parts.items()}, ev) for i, ev in enumerate((False, True, True))]
 
     def _finish(self, out, ev_out):
         """the post-compositing half of LSENeRFModel.get_outputs applied to a slice of the fused render."""

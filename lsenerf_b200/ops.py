@@ -504,6 +504,7 @@ class RenderOpts:
     cull: bool = True                  # training: sigma_fn given (lse_grid_estimator.py:109-143)
     samples_per_ray_cap: int = 512     # packed capacity = R * this
     early_terminate: bool = True       # culling pass: no field evaluation behind opaque surfaces (same kept set)
+    premarched: Optional[MarchResult] = None
     accumulate_into_grad: bool = True  # parameter grads are accumulated straight into p.grad (no 64 MiB temporaries)
     keep_debug: bool = False
     debug: dict = dc_field(default_factory=dict)
@@ -515,7 +516,10 @@ class _RenderRays(torch.autograd.Function):
         o = _f32(origins, "origins"); d = _f32(directions, "directions")
         R = o.shape[0]
         S_cap = max(1, R * opts.samples_per_ray_cap)
-        m0 = march(o, d, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step, opts.cone, jitter, S_cap, opts.occ_packed)
+        m0 = opts.premarched   # marched earlier on the same rays / jitter / grid (engine: overlaps the previous step's optimizer)
+        if m0 is None:
+            m0 = march(o, d, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step, opts.cone, jitter, S_cap, opts.occ_packed)
+        assert m0.S_cap == S_cap and m0.counts.numel() == R
         culling = opts.cull and (opts.alpha_thre > 0.0 or opts.early_stop_eps > 0.0)
         if culling and opts.early_stop_eps > 0.0 and opts.early_terminate:
             sigma, h16 = field_density_culling(fw, o, d, m0, opts.early_stop_eps)

@@ -547,7 +547,7 @@ def test_early_terminating_culling_pass_keeps_the_same_samples(dev):
     on a scene with opaque surfaces."""
     import dataclasses
     from lsenerf_b200 import ops
-    spec = small_spec(grid_res=64, log2_hashmap_size=16, bake_density=True)
+    spec = small_spec(grid_res=64, log2_hashmap_size=18, bake_density=True)
     scene = syn.make_scene(spec, images=False)
     scene["col_images"] = torch.rand(spec.n_ctrl, *spec.col_hw, 3); scene["evs_images"] = torch.zeros(spec.n_evs_frames, *spec.evs_hw, 1)
     p = syn.build_pipeline(scene, "lsenerf", num_rays=2048, device=dev, seed=3, pin=False)
