@@ -505,6 +505,7 @@ class RenderOpts:
     samples_per_ray_cap: int = 512     # packed capacity = R * this
     early_terminate: bool = True       # culling pass: no field evaluation behind opaque surfaces (same kept set)
     premarched: Optional[MarchResult] = None
+    last_totals: Optional[tuple] = None  # (marched, kept) device-side sample counts of the latest render through these opts
     accumulate_into_grad: bool = True  # parameter grads are accumulated straight into p.grad (no 64 MiB temporaries)
     keep_debug: bool = False
     debug: dict = dc_field(default_factory=dict)
@@ -539,6 +540,7 @@ class _RenderRays(torch.autograd.Function):
         call("lse_composite_fwd", P(m.starts), P(m.counts), R, P(m.t_starts), P(m.t_ends), P(sigma_c), P(rgb_s), P(w), P(out),
              P(acc), P(dnum), P(mm), stream())
         ctx.fw, ctx.opts, ctx.m, ctx.app_id = fw, opts, m, app_id
+        opts.last_totals = (m0.total, m.total)
         ctx.save_for_backward(o, d, sigma_c, h16_c, rgb_s)
         ctx.params = params
         nspr = m.counts
