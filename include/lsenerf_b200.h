@@ -213,6 +213,17 @@ int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFieldGrads *g
                                  int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
                                  const float *d_h16, float *d_origins, float *d_directions, void *workspace,
                                  int64_t workspace_bytes, lse_stream_t stream);
+/* lse_field_density_bwd_finish as two calls (tensor-core path): `rays` = base-MLP backward + ray / position gradients, `table` =
+ * the hash-table gradient alone, which only the optimizer needs and which may therefore run on the optimizer's stream. */
+int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                               const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                               int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                               const float *d_h16, float *d_origins, float *d_directions, void *workspace,
+                               int64_t workspace_bytes, lse_stream_t stream);
+int lse_field_density_bwd_table(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                                const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                                int64_t S_cap, const int32_t *n_dev, void *workspace, int64_t workspace_bytes,
+                                lse_stream_t stream);
 /* rgb [S,3] = sigmoid(head(cat[SH16(dir), geo15, emb32])).  app_id int32 [n_rays] (per RAY) or NULL. */
 int lse_field_color_fwd(const LseFieldParams *p, const float *directions, const int32_t *ray_idx,
                         const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb,

@@ -103,7 +103,7 @@ extern "C" int lse_adam_step_collective(void *const *peer_params, void *const *p
     const int64_t e = b + per < n4 ? b + per : n4;
     if (e <= b) return 0;
     const int threads = 256;
-    const int grid = stride_grid(e - b, threads, 8);
+    const int grid = stride_grid(e - b, threads, 4);   // leave SM thread slots for the overlapped main-stream kernels
     if (param_multicast)
         adam_collective_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(pp, grad_multicast, param_multicast, exp_avg, exp_avg_sq,
                                                                                  b, e, rank, world, beta1, beta2, eps, hp_dev);

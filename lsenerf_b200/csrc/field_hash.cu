@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, co
                                                             const float *__restrict__ t1, int64_t S_cap,
                                                             const int32_t *__restrict__ n_dev, const float *__restrict__ h16,
                                                             const float *__restrict__ d_sigma, float *__restrict__ feat,
-                                                            float *__restrict__ dout0)
+                                                            float *__restrict__ dout0, float *__restrict__ xs)
 {
     __shared__ float s_scal[NL];
     if (threadIdx.x < NL) s_scal[threadIdx.x] = P.scalings[threadIdx.x];
@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, co
         for (int q = 0; q < 8; ++q) o4[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
         const float gs = d_sigma ? d_sigma[i] : 0.0f;
         dout0[i] = g.cc.sel ? gs * expf(fminf(fmaxf(h16[16 * i], -15.0f), 15.0f)) : 0.0f;
+        xs[3 * i] = g.x[0]; xs[3 * i + 1] = g.x[1]; xs[3 * i + 2] = g.x[2];      // grid coordinates for the deferred table scatter
     }
 }
 
@@ -75,8 +76,10 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
                                                              const int32_t *__restrict__ ray_idx, const float *__restrict__ t0,
                                                              const float *__restrict__ t1, int64_t S_cap,
                                                              const int32_t *__restrict__ n_dev, const float *__restrict__ dfeat,
-                                                             float *__restrict__ d_origins, float *__restrict__ d_directions)
+                                                             float *__restrict__ d_origins, float *__restrict__ d_directions,
+                                                             const float *__restrict__ xs)
 {
+    // xs != NULL: grid coordinates saved by encode_samples (table-only launches: the ray buffers may already belong to the next step)
     __shared__ float s_scal[NL];
     if (threadIdx.x < NL) s_scal[threadIdx.x] = P.scalings[threadIdx.x];
     __syncthreads();
@@ -91,7 +94,10 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
         SampleGeom g;
         g.cc.sel = false; g.has_dir = false; g.tmid = 0.0f; g.ray = -1 - lane;
         g.x[0] = g.x[1] = g.x[2] = 0.0f;
-        if (live) load_geom(i, origins, directions, ray_idx, t0, t1, g);
+        if (live) {
+            if (xs) { g.x[0] = xs[3 * i]; g.x[1] = xs[3 * i + 1]; g.x[2] = xs[3 * i + 2]; }
+            else load_geom(i, origins, directions, ray_idx, t0, t1, g);
+        }
         const float2 *df2 = reinterpret_cast<const float2 *>(dfeat + 32 * i);
         const bool want_dx = live && (d_origins != nullptr || d_directions != nullptr) && g.cc.sel;
         float dx[3] = {0.0f, 0.0f, 0.0f};
@@ -170,9 +176,9 @@ using namespace lse;
 
 extern "C" int64_t lse_field_density_bwd_workspace(int64_t S_cap)
 {
-    // feat [S,32] + dfeat [S,32] + dout0 [S], fp32, each 256-byte aligned
+    // feat [S,32] + dfeat [S,32] + dout0 [S] + xs [S,3], fp32, each 256-byte aligned
     const int64_t s = S_cap < 1 ? 1 : S_cap;
-    return ((s * 32 * 4 + 255) / 256 * 256) * 2 + (s * 4 + 255) / 256 * 256;
+    return ((s * 32 * 4 + 255) / 256 * 256) * 2 + (s * 4 + 255) / 256 * 256 + (s * 12 + 255) / 256 * 256;
 }
 
 static int check_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins, const float *h16, const char *fn)
@@ -185,12 +191,13 @@ static int check_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const f
     return 0;
 }
 
-struct BwdWs { float *feat, *dfeat, *dout0; };
+struct BwdWs { float *feat, *dfeat, *dout0, *xs; };
 static BwdWs carve_ws(void *workspace, int64_t S_cap)
 {
-    const int64_t fbytes = (S_cap * 32 * 4 + 255) / 256 * 256;
+    const int64_t fbytes = (S_cap * 32 * 4 + 255) / 256 * 256, obytes = (S_cap * 4 + 255) / 256 * 256;
     char *w = reinterpret_cast<char *>(workspace);
-    return {reinterpret_cast<float *>(w), reinterpret_cast<float *>(w + fbytes), reinterpret_cast<float *>(w + 2 * fbytes)};
+    return {reinterpret_cast<float *>(w), reinterpret_cast<float *>(w + fbytes), reinterpret_cast<float *>(w + 2 * fbytes),
+            reinterpret_cast<float *>(w + 2 * fbytes + obytes)};
 }
 
 // first third of lse_field_density_bwd_ws: needs only d_sigma (not d_h16), so a caller may run it on a side stream
@@ -206,7 +213,7 @@ extern "C" int lse_field_density_bwd_encode(const LseFieldParams *p, const LseFi
     LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
     const BwdWs ws = carve_ws(workspace, S_cap);
     encode_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, (cudaStream_t)stream>>>(*p, origins, directions, ray_idx, t0, t1, S_cap,
-                                                                                      n_dev, h16, d_sigma, ws.feat, ws.dout0);
+                                                                                      n_dev, h16, d_sigma, ws.feat, ws.dout0, ws.xs);
     return check_launch("lse_field_density_bwd_encode");
 }
 
@@ -228,8 +235,48 @@ extern "C" int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFi
     rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_h16, ws.dfeat, st);
     if (rc) return rc;
     scatter_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, st>>>(*p, g->d_table, origins, directions, ray_idx, t0, t1, S_cap, n_dev,
-                                                                     ws.dfeat, d_origins, d_directions);
+                                                                     ws.dfeat, d_origins, d_directions, nullptr);
     return check_launch("lse_field_density_bwd_finish");
+}
+
+// lse_field_density_bwd_finish as two calls, for callers that take the table scatter off the critical path: `rays` = base-MLP
+// backward + position / ray gradients (everything the rest of the backward pass needs), `table` = the hash-table gradient alone
+// (only the optimizer needs it; engine.GraphedStep runs it on the optimizer's side stream under the next step's ray generation).
+extern "C" int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                                          const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                                          int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
+                                          const float *d_h16, float *d_origins, float *d_directions, void *workspace,
+                                          int64_t workspace_bytes, lse_stream_t stream)
+{
+    int rc = check_bwd_ws(p, g, origins, h16, __func__);
+    if (rc) return rc;
+    LSE_CHECK_ARG(p->use_tensor_cores, "the split backward exists for the tensor-core path only");
+    if (S_cap <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
+    const BwdWs ws = carve_ws(workspace, S_cap);
+    rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_h16, ws.dfeat, st);
+    if (rc) return rc;
+    if (!d_origins && !d_directions) return 0;
+    scatter_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, st>>>(*p, nullptr, origins, directions, ray_idx, t0, t1, S_cap, n_dev,
+                                                                     ws.dfeat, d_origins, d_directions, nullptr);
+    return check_launch("lse_field_density_bwd_rays");
+}
+
+extern "C" int lse_field_density_bwd_table(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
+                                           const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
+                                           int64_t S_cap, const int32_t *n_dev, void *workspace, int64_t workspace_bytes,
+                                           lse_stream_t stream)
+{
+    if (!p || !g) { set_error("%s: params / grads missing", __func__); return -22; }
+    LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
+    if (S_cap <= 0 || !g->d_table) return 0;
+    const BwdWs ws = carve_ws(workspace, S_cap);
+    // positions come from the workspace (ws.xs): the ray buffers are not read, they may already be rewritten by the next step
+    scatter_samples_kernel<<<stride_grid(S_cap, HT, 4), HT, 0, (cudaStream_t)stream>>>(*p, g->d_table, nullptr, nullptr, nullptr, nullptr,
+                                                                                       nullptr, S_cap, n_dev, ws.dfeat, nullptr, nullptr,
+                                                                                       ws.xs);
+    return check_launch("lse_field_density_bwd_table");
 }
 
 extern "C" int lse_field_density_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,

@@ -269,11 +269,13 @@ class GraphedStep:
         dm = pipeline.datamanager
         dm.lean = True                      # captured step: no launches for metadata the fused path never reads
         pipeline.lean = True                # ... nor for outputs the loss never reads (depth, detached linear, metrics)
+        pipeline.defer_table_scatter = bool(pipeline.model.config.use_tensor_cores)
         hc, he = dm.sample_host_batches()
         self.stage = BatchStage(hc, he, dm.device)
         self.stage.pack_host(hc, he); self.stage.upload()
         self.graph_a: Optional[torch.cuda.CUDAGraph] = None
         self.graph_b: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_c: Optional[torch.cuda.CUDAGraph] = None     # deferred hash-table scatter (side stream, before the optimizer)
         self.graph_opt: Dict[str, torch.cuda.CUDAGraph] = {}
         self.loss_out: Optional[torch.Tensor] = None
         self.ctx: Optional[dict] = None
@@ -315,11 +317,19 @@ class GraphedStep:
         self.graph_b = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
             self.loss_out = self._phase_b()
+        if self._deferred() is not None:
+            self.graph_c = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_c, pool=self.graph_a.pool()):
+                ops.run_deferred_table_scatter(self._deferred())
         for name in self.optim.names:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self.graph_a.pool()):
                 self.optim.apply(only=[name])
             self.graph_opt[name] = g
+
+    def _deferred(self):
+        o = (self.ctx or {}).get("opts")
+        return o if (o is not None and o.deferred_table is not None) else None
 
     def _optimize(self, names, world: int, channel: int) -> None:
         """optimizer (+ exchange) of `names` on the current stream."""
@@ -378,6 +388,10 @@ class GraphedStep:
             self._optimize(self.early, world, channel=2)
         self.side.wait_event(self.ev_b)
         with torch.cuda.stream(self.side):
+            if self.graph_c is not None:
+                self.graph_c.replay()                    # hash-table scatter of this step (only the optimizer needs it)
+            elif self._deferred() is not None:
+                ops.run_deferred_table_scatter(self._deferred())
             self._optimize([self.FIELD_GROUP], world, channel=0)
             self.ev_opt = torch.cuda.Event()
             self.ev_opt.record(self.side)

@@ -26,6 +26,7 @@ class LSENeRFPipeline(nn.Module):
         # lean = the captured training step: skip outputs the loss never reads (depth, detached "linear", metrics) -- each is a
         # handful of tiny launches.  Off by default: get_train_loss_dict() then returns everything upstream returns.
         self.lean = False
+        self.defer_table_scatter = False   # engine: the hash-table scatter runs with the optimizer on a side stream
 
     @property
     def model(self):
@@ -50,6 +51,7 @@ class LSENeRFPipeline(nn.Module):
             ctx["big"], ctx["sizes"] = big, (len(col), len(prev), len(nxt))
             if premarch and m.training:
                 opts = m._render_opts()
+                opts.defer_table_scatter = self.defer_table_scatter
                 jitter = torch.rand(len(big), device=big.origins.device)
                 S_cap = max(1, len(big) * opts.samples_per_ray_cap)
                 opts.premarched = ops.march(big.origins, big.directions, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step,

@@ -505,6 +505,8 @@ class RenderOpts:
     samples_per_ray_cap: int = 512     # packed capacity = R * this
     early_terminate: bool = True       # culling pass: no field evaluation behind opaque surfaces (same kept set)
     premarched: Optional[MarchResult] = None
+    defer_table_scatter: bool = False  # backward leaves the hash-table scatter to run_deferred_table_scatter(opts)
+    deferred_table: Optional[tuple] = None
     last_totals: Optional[tuple] = None  # (marched, kept) device-side sample counts of the latest render through these opts
     accumulate_into_grad: bool = True  # parameter grads are accumulated straight into p.grad (no 64 MiB temporaries)
     keep_debug: bool = False
@@ -596,14 +598,30 @@ class _RenderRays(torch.autograd.Function):
             call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
                  P(h16), P(d_rgb), P(d_h16), P(gd), stream())
             cur.wait_stream(side)
-            call("lse_field_density_bwd_finish", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
-                 P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), P(ws), nbytes, stream())
+            if opts.defer_table_scatter and bufs["table"] is not None:
+                # the table gradient feeds the optimizer only: leave its scatter to the caller (engine: side stream, under the next
+                # step's ray generation); everything the rest of this backward pass needs is produced here
+                call("lse_field_density_bwd_rays", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
+                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), P(ws), nbytes, stream())
+                opts.deferred_table = (fw, bufs, o, d, m, ws, nbytes, S_cap)
+            else:
+                call("lse_field_density_bwd_finish", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
+                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), P(ws), nbytes, stream())
             ws.record_stream(side)
         else:
             call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
                  P(h16), P(d_rgb), P(d_h16), P(gd), stream())
             _density_bwd(fw, cp, cg, o, d, m.ray_indices, m.t_starts, m.t_ends, S_cap, m.total, h16, d_sigma, d_h16, g_o, gd)
         return (g_o, g_d if need_d else None, None, None, None, None, *[ret[k] for k in names])
+
+
+def run_deferred_table_scatter(opts: RenderOpts) -> None:
+    """the hash-table half of the density backward that _RenderRays.backward left out (opts.defer_table_scatter), on the current
+    stream.  Must run before the optimizer reads the table gradient."""
+    fw, bufs, o, d, m, ws, nbytes, S_cap = opts.deferred_table
+    cp = fw.c_params(); cg = _grads_struct(fw, bufs)
+    call("lse_field_density_bwd_table", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts), P(m.t_ends),
+         S_cap, P(m.total), P(ws), nbytes, stream())
 
 
 def render_rays(fw: FieldWeights, opts: RenderOpts, origins, directions, jitter=None, app_id=None):

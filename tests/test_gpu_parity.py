@@ -206,6 +206,7 @@ def test_scan_and_empty(dev):
 
 # ---------------------------------------------------------------------------------------------------- full model
 def _pipeline(dev, experiment="lsenerf", deblur=False, cam_opt=False, num_rays=768, emb=False, **kw):
+    torch.manual_seed(1234)          # the camera perturbations below draw from the global (CUDA) generator
     spec = small_spec()
     scene = syn.make_scene(spec)
     name = experiment + ("_emb" if emb else "")
@@ -305,8 +306,12 @@ def test_train_step_parity(dev, variant):
         assert rel_err(outs[k]["accumulation"][same.to(dev)], oouts[k]["accumulation"][same]) < TOL_OUT
         if "ev_out" in oouts[k]:
             assert rel_err(outs[k]["ev_out"][same.to(dev)], oouts[k]["ev_out"][same]) < TOL_OUT
+    # losses average over ALL rays, threshold-straddling ones included: 2e-4 when every ray agrees, plus a term proportional to
+    # the fraction of rays whose kept-sample count differs (their colour moves by ~alpha_thre, their log-intensity by more)
+    mism = max(float((outs[k]["num_samples_per_ray"].cpu().long() != oouts[k]["num_samples_per_ray"]).float().mean())
+               for k in ("col_out", "prev_out", "next_out"))
     for k in old:
-        assert abs(ld[k].item() - old[k].item()) <= 2e-4 * abs(old[k].item()) + 1e-7, (k, ld[k].item(), old[k].item())
+        assert abs(ld[k].item() - old[k].item()) <= (2e-4 + 0.1 * mism) * abs(old[k].item()) + 1e-7, (k, ld[k].item(), old[k].item(), mism)
     # parameter gradients
     cuda_grads = {}
     for k, v in m.named_parameters():
@@ -571,3 +576,42 @@ def test_early_terminating_culling_pass_keeps_the_same_samples(dev):
     skipped = int(((sb[:n] == 0) & (sa[:n] != 0)).sum())
     assert skipped > 0.2 * n, (skipped, n)          # opaque ball / slab / dome: a large part of the march is never evaluated
     assert int(ka[:n].sum()) > 1000
+
+
+def test_engine_pipelined_step_matches_plain_step(dev):
+    """engine.GraphedStep (prepare / finish split, pre-marched samples, deferred hash-table scatter on the side stream, CUDA graphs)
+    against the plain eager iteration on the same batch and jitter: same losses, same gradients for every parameter."""
+    from lsenerf_b200 import ops
+    from lsenerf_b200.engine import ArenaAdam, GraphedStep
+    scene, p = _pipeline(dev, deblur=True, cam_opt=True, use_tensor_cores=True)
+    p.train()
+    opt = ArenaAdam(p.get_param_groups())
+    gs = GraphedStep(p, opt, 1, use_graph=True)
+    gs.capture(start_step=1)
+    torch.manual_seed(11)
+    # plain path: one autograd pass through get_train_loss_dict on the staged batch, nothing deferred
+    p.defer_table_scatter = False
+    opt.zero_grad()
+    torch.manual_seed(5)
+    _, ld, _ = p.get_train_loss_dict(1, gs.stage.device_batches())
+    sum(ld.values()).backward()
+    torch.cuda.synchronize()
+    ref = {n: a.grad.clone() for n, a in opt.arenas.items()}
+    ref_loss = torch.stack([v.detach() for v in ld.values()])
+    # engine path, eager phases with the same RNG stream for the jitter
+    p.defer_table_scatter = True
+    torch.manual_seed(5)
+    gs._phase_a(); out = gs._phase_b()
+    assert gs._deferred() is not None
+    ops.run_deferred_table_scatter(gs._deferred())
+    torch.cuda.synchronize()
+    assert torch.allclose(out, ref_loss, rtol=1e-6, atol=1e-8)
+    for n, a in opt.arenas.items():
+        assert rel_err(a.grad, ref[n]) < 1e-4, (n, rel_err(a.grad, ref[n]))
+    assert float(ref["fields"].abs().max()) > 0
+    # and the graph replays run (weights move, losses finite)
+    w0 = opt.arenas["fields"].data.clone()
+    for _ in range(3):
+        loss = gs.step()
+    gs.flush(); torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and not torch.equal(w0, opt.arenas["fields"].data)
