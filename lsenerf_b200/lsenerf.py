@@ -103,7 +103,7 @@ class LSENeRFModel(nn.Module):
     def populate_modules(self):
         """lsenerf.py:158-228."""
         c = self.config
-        assert c.event_loss_type.lower() == "log_loss", "enerf_norm_loss is not built into the fused loss kernel yet"
+        assert c.event_loss_type.lower() in ("log_loss", "enerf_norm_loss"), f"unknown event_loss_type {c.event_loss_type}"
         self.field = LSEField(aabb=self.scene_aabb.data.reshape(2, 3), num_images=self.num_train_data,
                               log2_hashmap_size=c.log2_hashmap_size, max_res=c.max_res,
                               spatial_distortion=not c.disable_scene_contraction, embd_config=c.embed_config,
@@ -235,7 +235,21 @@ class LSENeRFModel(nn.Module):
             key = "rgb" if not c.use_mapping else "ev_out"
             prev, nxt = prev_out[key], next_out[key]
             evs = evs_batch["image"].to(self.device)
-        l_rgb, l_ev = ops.losses(col_pred, col_img, prev, nxt, evs, c.evs_loss_weight)
+        if prev is not None and c.event_loss_type.lower() == "enerf_norm_loss":
+            # lsenerf.py:406-419: both sides normalised by their batch L2 norm.  Two [n,1] norms and an MSE: plain device ops
+            # (this loss is not on any shipped config's path, scripts/train_evimo.sh defaults to log_loss).
+            from .utils import EPS, to_gray
+            l_rgb = ops.losses(col_pred, col_img, None, None, None, c.evs_loss_weight)[0] if col_pred is not None else None
+            p, n = (to_gray(prev), to_gray(nxt)) if prev.shape[-1] != 1 else (prev, nxt)
+            delta = torch.log(n + EPS) - torch.log(p + EPS)
+            n1 = torch.linalg.norm(delta, dim=0, keepdim=True) + EPS
+            tgt = evs if p.shape[-1] == 1 else torch.cat([evs] * 3, dim=-1)
+            with torch.no_grad():
+                tgt = tgt / evs_batch["e_thresh"].to(self.device)
+                n2 = torch.linalg.norm(tgt, dim=0, keepdim=True) + EPS
+            l_ev = c.evs_loss_weight * torch.nn.functional.mse_loss(delta / n1, tgt / n2)
+        else:
+            l_rgb, l_ev = ops.losses(col_pred, col_img, prev, nxt, evs, c.evs_loss_weight)
         ld = {}
         if col_out is not None:
             ld["rgb_loss"] = l_rgb

@@ -255,14 +255,15 @@ def _oracle_step(scene, p, bundles_gpu, batch_gpu, jitters, training=True):
 
 
 @pytest.mark.parametrize("variant", ["lsenerf", "lsenerf_deblur_camopt", "lsenerf_emb", "badnerf_events", "lsenerf_tc",
-                                     "lsenerf_emb_deblur_camopt_tc"])
+                                     "lsenerf_emb_deblur_camopt_tc", "lsenerf_enerf_norm_loss"])
 def test_train_step_parity(dev, variant):
     """One full training step (3 bundles, event + RGB loss, backward to every parameter) against the oracle.
     *_tc variants run the MLPs (forward and backward) on the tcgen05 3xTF32 kernels."""
     simt = dict(use_tensor_cores=False)
     kw = dict(lsenerf=dict(**simt), lsenerf_deblur_camopt=dict(deblur=True, cam_opt=True, **simt), lsenerf_emb=dict(emb=True, **simt),
               badnerf_events=dict(experiment="badnerf", deblur=False, **simt), lsenerf_tc=dict(use_tensor_cores=True),
-              lsenerf_emb_deblur_camopt_tc=dict(emb=True, deblur=True, cam_opt=True, use_tensor_cores=True))[variant]
+              lsenerf_emb_deblur_camopt_tc=dict(emb=True, deblur=True, cam_opt=True, use_tensor_cores=True),
+              lsenerf_enerf_norm_loss=dict(event_loss_type="enerf_norm_loss", **simt))[variant]
     scene, p = _pipeline(dev, **kw)
     if variant == "badnerf_events":   # BAD-NeRF flag set with the event branch on (BASELINE configs[3] (ii))
         p.datamanager.config.rgb_frac = 0.5; p.datamanager.config.update_num_batch_rays()
