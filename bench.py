@@ -386,6 +386,7 @@ def run_b200(args):
     with torch.no_grad():
         pipe._model.exec_get_outputs(concat_bundles(list(bundles)), None, opts)
     S0, S1 = int(opts.debug["march0"].total.item()), int(opts.debug["march"].total.item())
+    S_eval = int((opts.debug["sigma0"][:S0] != 0).sum().item())      # samples the early-terminating culling pass evaluated
     overflow = int(opts.debug["march0"].overflow.item())
 
     # ---- render rays/sec: BASELINE configs[4], one 1280x720 eval frame with camera optimisation, rows sharded over ranks -------
@@ -394,16 +395,25 @@ def run_b200(args):
     if rank == 0:
         per_call = {k: v[1] / v[0] for k, v in prof.items()}
         per_step = {k: v[1] / n_prof for k, v in prof.items()}
-        # ALGORITHMIC bytes / flops per sample x the live sample counts read back from the device:
-        #   density_fwd    : 1024 B gathered + 12 B (ray index, t0, t1) in + 68 B (sigma, h16) out          per MARCHED sample
-        #   density_bwd    : encode = 1024 B re-gathered + 128 B feat out + 20 B geometry/d_sigma; finish = 1024 B scattered + 1024 B
-        #                    re-gathered (d/dx) + 128 B feat in + 256 B dfeat round trip + 80 B                    per KEPT sample
-        #   color fwd/bwd  : the dense contraction, 16 640 flop/sample forward, 3 x that backward (recompute + dgrad + wgrad)
-        alg_bytes = {"lse_field_density_fwd": (1024 + 12 + 68) * S0, "lse_field_density_bwd_ws": (3 * 1024 + 512 + 12 + 68 + 64) * S1,
-                     # the same backward as its two launches (the encode half runs under the colour backward on a side stream)
-                     "lse_field_density_bwd_encode": (1024 + 128 + 12 + 8) * S1,
-                     "lse_field_density_bwd_finish": (2 * 1024 + 128 + 256 + 12 + 64 + 4) * S1}
+        # ALGORITHMIC bytes / flops per step: per-sample figures x the live sample counts read back
+        # from the device.  S0 marched, S_eval evaluated by the early-terminating culling pass, S1 kept.
+        #   density_fwd_list : 1024 B gathered + 12 B (ray index, t0, t1) in + 68 B (sigma, h16) out            per EVALUATED sample
+        #   density_bwd      : encode = 1024 B re-gathered + 128 B feat out + 12 B grid coords out + 20 B in;  rays = base-MLP backward
+        #                      (128 feat + 68 in, 128 dfeat out) + d/dx (1024 B re-gathered + 128 dfeat + 12 B in);  table = 1024 B
+        #                      scattered + 128 B dfeat + 12 B coords in                                             per KEPT sample
+        #   color fwd/bwd    : the dense contraction, 16 640 flop/sample forward, 3 x that backward (recompute + dgrad + wgrad)
+        alg_bytes = {"lse_field_density_fwd_list": (1024 + 12 + 68) * S_eval, "lse_field_density_fwd": (1024 + 12 + 68) * S0,
+                     "lse_field_density_bwd_encode": (1024 + 128 + 12 + 20) * S1,
+                     "lse_field_density_bwd_rays": (128 + 68 + 128 + 1024 + 128 + 12) * S1,
+                     "lse_field_density_bwd_table": (1024 + 128 + 12) * S1,
+                     "lse_field_density_bwd_finish": (128 + 68 + 128 + 2 * 1024 + 128 + 12) * S1}
         alg_flops = {"lse_field_color_fwd": 16640 * S1, "lse_field_color_bwd": 3 * 16640 * S1}
+        kernels_of = {"lse_field_density_fwd_list": ["density_fwd_tc_kernel"], "lse_field_density_fwd": ["density_fwd_tc_kernel"],
+                      "lse_field_density_bwd_encode": ["encode_samples_kernel"],
+                      "lse_field_density_bwd_rays": ["density_mlp_bwd_tc_kernel", "scatter_samples_kernel"],
+                      "lse_field_density_bwd_table": ["scatter_samples_kernel"],
+                      "lse_field_density_bwd_finish": ["density_mlp_bwd_tc_kernel", "scatter_samples_kernel"],
+                      "lse_field_color_fwd": ["color_fwd_tc_kernel"], "lse_field_color_bwd": ["color_bwd_tc_kernel"]}
         hbm, which = peaks()
         try:   # kernels timed inside a long step: the sustained bf16 figure
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -412,21 +422,25 @@ def run_b200(args):
         except Exception:
             tf_peak = 1362.4
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r1c_ncu_traffic.json")) as fh:
                 ncu_traffic = json.load(fh)
         except Exception:
             ncu_traffic = {}
+        calls_per_step = {k: v[0] / n_prof for k, v in prof.items()}
 
         def roof(kname):
+            """per LAUNCH of the ABI call: algorithmic work of one step / launches per step, over the mean launch duration"""
+            n_call = max(calls_per_step[kname], 1e-9)
             dur = per_call[kname] * 1e-3
-            tr = ncu_traffic.get(kname)
             if kname in alg_bytes:
-                ach = alg_bytes[kname] / dur / 1e9
+                ach = alg_bytes[kname] / n_call / dur / 1e9
                 r = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
             else:
-                ach = alg_flops[kname] / dur / 1e12
+                ach = alg_flops[kname] / n_call / dur / 1e12
                 r = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak}
-            r.update({"traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_source": tr.get("source") if tr else None,
+            tr = [ncu_traffic[k] for k in kernels_of.get(kname, []) if k in ncu_traffic]
+            r.update({"traffic": sum(t["dram_bytes_per_launch"] for t in tr) if tr else None,
+                      "traffic_source": tr[0].get("source") if tr else None, "launches_per_step": round(n_call, 2),
                       "peak_source": which, "ms_per_launch": per_call[kname], "share_of_step": per_step[kname] / sum(per_step.values())})
             return r
         candidates = [k for k in list(alg_bytes) + list(alg_flops) if k in per_call]
@@ -438,7 +452,7 @@ def run_b200(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "parallelism": f"ray-sharded dp{world}; gradient exchange: {opt.exchange_kind()}",
                            "l2": "working set per step (64 MiB table + 64 MiB grad + 128 MiB Adam state + sample buffers) exceeds the 126 MB L2; no explicit flush",
-                           "samples_marched_per_step": S0, "samples_kept_per_step": S1, "capacity_overflow": overflow,
+                           "samples_marched_per_step": S0, "samples_evaluated_by_culling_pass": S_eval, "samples_kept_per_step": S1, "capacity_overflow": overflow,
                            "mlp": "tcgen05 (3xTF32 fwd, BF16x3 bwd)" if pipe._model.config.use_tensor_cores else "fp32 SIMT",
                            "step": "one CUDA-graph replay (zero_grad+raygen+render+loss+backward) + Adam graph" if not args.no_graph else "eager launches",
                            "start_step": START, "burn_in_steps": burn_steps,

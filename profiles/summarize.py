@@ -13,9 +13,10 @@ import os
 import subprocess
 import sys
 
-ABI_OF = {"density_fwd_tc_kernel": "lse_field_density_fwd", "color_fwd_tc_kernel": "lse_field_color_fwd",
-          "color_bwd_tc_kernel": "lse_field_color_bwd", "encode_samples_kernel": "lse_field_density_bwd_encode",
-          "density_mlp_bwd_tc_kernel": "lse_field_density_bwd_finish", "scatter_samples_kernel": "lse_field_density_bwd_finish"}
+# kernels whose DRAM traffic (per launch, averaged over the captured launches) goes into <tag>_ncu_traffic.json
+TRAFFIC_KERNELS = ("density_fwd_tc_kernel", "color_fwd_tc_kernel", "color_bwd_tc_kernel", "encode_samples_kernel",
+                   "density_mlp_bwd_tc_kernel", "scatter_samples_kernel", "march_runs_kernel", "march_steps_kernel", "adam_hp_kernel",
+                   "cull_generation_kernel")
 
 
 def short(name):
@@ -75,12 +76,14 @@ def main():
                 m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
                 return float(v.replace(",", "")) * m
             d = nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum")
-            for kern, abi in ABI_OF.items():
+            for kern in TRAFFIC_KERNELS:
                 if kern in name:
-                    t = traffic.setdefault(abi, {"dram_bytes_per_launch": 0.0, "kernels": []})
+                    t = traffic.setdefault(kern, {"dram_bytes_per_launch": 0.0, "launches": 0})
                     t["dram_bytes_per_launch"] += d
-                    t["kernels"].append(kern)
-                    t["source"] = f"profiles/{tag}_kernels_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)"
+                    t["launches"] += 1
+    for t in traffic.values():
+        t["dram_bytes_per_launch"] /= max(t["launches"], 1)
+        t["source"] = f"profiles/{tag}_kernels_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches of one ncu --set full run)"
     with open(os.path.join(here, f"{tag}_ncu_traffic.json"), "w") as fh:
         json.dump(traffic, fh, indent=1)
     print(open(os.path.join(here, f"{tag}_launches_summary.txt")).read())
