@@ -279,16 +279,11 @@ __global__ void __launch_bounds__(kMarchThreads) march_steps_kernel(
         const uint32_t wmask = __activemask();
         while (__any_sync(wmask, !done)) {
             if (!done) {
-                const float bound = __uint_as_float(e & 0x7FFFFFFFu);
                 const float dt = march_dt(t_last, cone_angle, step_size);
                 const float mid = rn_add(t_last, rn_mul(dt, 0.5f));
                 const float t_next = rn_add(t_last, dt);
-                if (mid < bound) {
-                    if ((e >> 31) && n < max_per_ray) slab[n] = make_float2(t_last, t_next);
-                    n += (int)(e >> 31);
-                    t_last = t_next;
-                } else {
-                    ++idx;
+                if (mid >= __uint_as_float(e & 0x7FFFFFFFu)) {      // this run is behind us: move to the next one (at most one per
+                    ++idx;                                          // iteration; the step below is retried against it right away)
                     bool new_chunk = (idx & 3) == 0;
                     if (idx >= cnt) {               // segment exhausted: the next non-empty one starts a fresh chunk
                         do { ++c_slot; } while (c_slot < n_slots && s_cnt[c_slot][tid] == 0);
@@ -308,6 +303,11 @@ __global__ void __launch_bounds__(kMarchThreads) march_steps_kernel(
                         }
                         e = cur.x;
                     }
+                }
+                if (!done && mid < __uint_as_float(e & 0x7FFFFFFFu)) {   // one step of the t recurrence inside the current run
+                    if ((e >> 31) && n < max_per_ray) slab[n] = make_float2(t_last, t_next);
+                    n += (int)(e >> 31);
+                    t_last = t_next;
                 }
             }
         }
