@@ -79,3 +79,55 @@ def test_synthetic_scene_shapes():
     assert float(sc["col_images"].max()) <= 1.0 and float(sc["col_images"].max()) > 0.3
     q = sc["evs_images"] / spec.e_thresh
     assert torch.allclose(q, torch.round(q), atol=1e-4)                                      # integer event counts x threshold
+
+
+def test_param_arena_rehomes_parameters_as_views():
+    """engine.ParamArena: parameters keep identity, values and checkpoint keys; data / grad become views of the flat buffers."""
+    from lsenerf_b200.engine import ParamArena
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    extra = torch.nn.Parameter(torch.randn(7))
+    frozen = torch.nn.Parameter(torch.randn(4), requires_grad=False)
+    before = {k: v.clone() for k, v in lin.state_dict().items()}
+    arena = ParamArena([lin.weight, lin.bias, extra, frozen, lin.weight])       # duplicates and frozen tensors are skipped
+    assert len(arena.params) == 3 and arena.numel % 4 == 0 and all(o % 4 == 0 for o in arena.offsets)
+    for k, v in lin.state_dict().items():
+        assert torch.equal(v, before[k])
+    assert lin.weight.data_ptr() == arena.data.data_ptr() and lin.weight.grad.data_ptr() == arena.grad.data_ptr()
+    lin.weight.grad.fill_(2.0); extra.grad.fill_(3.0)
+    assert float(arena.grad.sum()) == 2.0 * 15 + 3.0 * 7
+    arena.data.zero_()
+    assert float(lin.weight.abs().sum()) == 0.0 and float(extra.abs().sum()) == 0.0
+    arena.zero_grad()
+    assert float(lin.weight.grad.abs().sum()) == 0.0
+
+
+def test_lr_schedule_and_cull_bounds(monkeypatch):
+    """lse_config.py:29-38 exponential decay; generation bounds of the early-terminating culling pass."""
+    from lsenerf_b200 import ops
+    from lsenerf_b200.lse_pipeline import DEFAULT_OPTIMIZERS
+    f = DEFAULT_OPTIMIZERS["fields"]
+    assert abs(f.lr_at(0) - 1e-2) < 1e-12 and abs(f.lr_at(200000) - 1e-4) < 1e-12 and abs(f.lr_at(100000) - 1e-3) < 1e-9
+    assert abs(DEFAULT_OPTIMIZERS["camera_opt"].lr_at(10**9) - 1e-4) < 1e-12
+    monkeypatch.delenv("LSE_CULL_BOUNDS", raising=False)
+    assert ops._cull_bounds() == [0, 40, 160, 1 << 30]
+    monkeypatch.setenv("LSE_CULL_BOUNDS", "32,96,224")
+    assert ops._cull_bounds() == [0, 32, 96, 224, 1 << 30]
+
+
+def test_ray_generator_coords_and_bundle_concat():
+    """image_coords[y, x] is (y, x) itself (lse_cameras.py:69-73); restricted concat keeps only what the fused render reads."""
+    from lsenerf_b200.compat import RayBundle, concat_bundles
+    from lsenerf_b200.lse_cameras import EdCameras
+    from lsenerf_b200.lse_ray_generator import RayGenerator
+    cams = EdCameras(torch.eye(4)[None, :3].repeat(2, 1, 1), 50.0, 50.0, 8.0, 6.0, 16, 12)
+    table = cams.get_image_coords()
+    y, x = torch.tensor([0, 5, 11]), torch.tensor([15, 0, 7])
+    assert torch.equal(RayGenerator._coords(y, x), table[y, x])
+    a = RayBundle(torch.zeros(3, 3), torch.ones(3, 3), torch.ones(3, 1), torch.zeros(3, 1, dtype=torch.long), metadata={"appearance_id": torch.zeros(3, 1), "coords": torch.zeros(3, 3)})
+    b = RayBundle(torch.ones(2, 3), torch.zeros(2, 3), torch.ones(2, 1), torch.ones(2, 1, dtype=torch.long), metadata={"appearance_id": torch.ones(2, 1), "coords": torch.ones(2, 3)})
+    full = concat_bundles([a, b])
+    assert len(full) == 5 and full.pixel_area is not None and set(full.metadata) == {"appearance_id", "coords"}
+    lean = concat_bundles([a, b], fields=("origins", "directions"), metadata_keys=("appearance_id",))
+    assert lean.pixel_area is None and lean.camera_indices is None and set(lean.metadata) == {"appearance_id"}
+    assert torch.equal(lean.origins, full.origins) and torch.equal(lean.directions, full.directions)
