@@ -203,11 +203,13 @@ int lse_field_density_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, co
                              const float *d_h16, float *d_origins, float *d_directions, void *workspace,
                              int64_t workspace_bytes, lse_stream_t stream);
 /* The two halves of lse_field_density_bwd_ws.  `encode` needs d_sigma but not d_h16, so it may run on a side stream
- * concurrently with lse_field_color_bwd (which produces d_h16); join, then `finish`. */
+ * concurrently with lse_field_color_bwd (which produces d_h16); join, then `finish`.  with_jacobian != 0: encode also stores
+ * d(features)/d(grid coordinate) (96 floats per sample) so that lse_field_density_bwd_rays(with_jacobian) computes the ray
+ * gradients without re-gathering the table; lse_field_density_bwd_finish always re-gathers. */
 int lse_field_density_bwd_encode(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                  const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                  int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
-                                 void *workspace, int64_t workspace_bytes, lse_stream_t stream);
+                                 int with_jacobian, void *workspace, int64_t workspace_bytes, lse_stream_t stream);
 int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                  const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                  int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
@@ -218,8 +220,8 @@ int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFieldGrads *g
 int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
-                               const float *d_h16, float *d_origins, float *d_directions, void *workspace,
-                               int64_t workspace_bytes, lse_stream_t stream);
+                               const float *d_h16, float *d_origins, float *d_directions, int with_jacobian,
+                               void *workspace, int64_t workspace_bytes, lse_stream_t stream);
 int lse_field_density_bwd_table(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                 const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                 int64_t S_cap, const int32_t *n_dev, void *workspace, int64_t workspace_bytes,

@@ -26,27 +26,52 @@ int simt_density_bwd(const LseFieldParams &P, const LseFieldGrads &G, const floa
 
 constexpr int HT = 256;   // threads per CTA of the hash kernels
 
+// JAC: also store d(feat)/d(grid coordinate) -- 2 features x 3 axes per level, already multiplied by the level's scale, 96 floats per
+// sample -- computed from the corner values this kernel has in registers anyway.  The position-gradient kernel then needs no
+// gathers at all: 384 B of streamed Jacobian per sample replace 1024 B of random 8-byte reads on the critical path.
+template <bool JAC>
 __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, const float *__restrict__ origins,
                                                             const float *__restrict__ directions,
                                                             const int32_t *__restrict__ ray_idx, const float *__restrict__ t0,
                                                             const float *__restrict__ t1, int64_t S_cap,
                                                             const int32_t *__restrict__ n_dev, const float *__restrict__ h16,
                                                             const float *__restrict__ d_sigma, float *__restrict__ feat,
-                                                            float *__restrict__ dout0, float *__restrict__ xs)
+                                                            float *__restrict__ dout0, float *__restrict__ xs, float *__restrict__ jac)
 {
     __shared__ float s_scal[NL];
     if (threadIdx.x < NL) s_scal[threadIdx.x] = P.scalings[threadIdx.x];
     __syncthreads();
     const int64_t S = live_count(n_dev, S_cap);
     const float2 *table = reinterpret_cast<const float2 *>(P.table);
+    const uint32_t mask = (1u << P.log2_T) - 1u;
     for (int64_t i = blockIdx.x * (int64_t)HT + threadIdx.x; i < S; i += (int64_t)gridDim.x * HT) {
         SampleGeom g;
         load_geom(i, origins, directions, ray_idx, t0, t1, g);
-        float f[NF];
-        encode(g.x, table, s_scal, P.log2_T, f);
-        float4 *o4 = reinterpret_cast<float4 *>(feat + 32 * i);
+        float2 *o2 = reinterpret_cast<float2 *>(feat) + i;                 // planes [16][S_cap] of float2, like the Jacobian below
+        // structure-of-arrays planes [48][S_cap] of float2: a warp's 32 samples write / read 256 contiguous bytes per plane
+        float2 *j2 = JAC ? reinterpret_cast<float2 *>(jac) + i : nullptr;
+#pragma unroll 4
+        for (int l = 0; l < NL; ++l) {
+            HashCell h;
+            hash_cell(g.x, s_scal[l], mask, h);
+            const float2 *__restrict__ tl = table + ((size_t)l << P.log2_T);
+            float F[8][2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) o4[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            for (int c = 0; c < 8; ++c) { float2 v = __ldg(tl + h.idx[c]); F[c][0] = v.x; F[c][1] = v.y; }
+            float o[2];
+            hash_blend(F, h, o);
+            o2[(size_t)l * S_cap] = make_float2(o[0], o[1]);
+            if (JAC) {
+                const float e0[2] = {1.0f, 0.0f}, e1[2] = {0.0f, 1.0f};
+                float d0[3], d1[3];
+                hash_blend_dx(F, h, e0, d0);
+                hash_blend_dx(F, h, e1, d1);
+                const float sc = s_scal[l];
+                j2[(size_t)(3 * l) * S_cap] = make_float2(d0[0] * sc, d0[1] * sc);
+                j2[(size_t)(3 * l + 1) * S_cap] = make_float2(d0[2] * sc, d1[0] * sc);
+                j2[(size_t)(3 * l + 2) * S_cap] = make_float2(d1[1] * sc, d1[2] * sc);
+            }
+        }
         const float gs = d_sigma ? d_sigma[i] : 0.0f;
         dout0[i] = g.cc.sel ? gs * expf(fminf(fmaxf(h16[16 * i], -15.0f), 15.0f)) : 0.0f;
         xs[3 * i] = g.x[0]; xs[3 * i + 1] = g.x[1]; xs[3 * i + 2] = g.x[2];      // grid coordinates for the deferred table scatter
@@ -98,7 +123,7 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
             if (xs) { g.x[0] = xs[3 * i]; g.x[1] = xs[3 * i + 1]; g.x[2] = xs[3 * i + 2]; }
             else load_geom(i, origins, directions, ray_idx, t0, t1, g);
         }
-        const float2 *df2 = reinterpret_cast<const float2 *>(dfeat + 32 * i);
+        const float2 *df2 = reinterpret_cast<const float2 *>(dfeat) + i;   // planes [16][S_cap]
         const bool want_dx = live && (d_origins != nullptr || d_directions != nullptr) && g.cc.sel;
         float dx[3] = {0.0f, 0.0f, 0.0f};
         // the level loop stays rolled: 16 unrolled copies of this body (19 k instructions) thrash the instruction cache
@@ -106,7 +131,7 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
         for (int l = 0; l < NL; ++l) {
             HashCell hc;
             hash_cell(g.x, s_scal[l], mask, hc);
-            const float2 g2 = live ? __ldg(df2 + l) : make_float2(0.0f, 0.0f);
+            const float2 g2 = live ? __ldg(df2 + (size_t)l * S_cap) : make_float2(0.0f, 0.0f);
             const float gl[2] = {g2.x, g2.y};
             if (d_table) {
                 float w[8];
@@ -170,15 +195,69 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
     }
 }
 
+// per-ray origin / direction gradients from the stored Jacobian: dx_j = sum_{l,f} dfeat[l][f] * J[l][f][j], contraction backward, one
+// reduction per run of lanes on the same ray.  Streams 512 B per sample, no gathers.
+__global__ void __launch_bounds__(HT) ray_grad_kernel(const float *__restrict__ origins, const float *__restrict__ directions,
+                                                      const int32_t *__restrict__ ray_idx, const float *__restrict__ t0,
+                                                      const float *__restrict__ t1, int64_t S_cap, const int32_t *__restrict__ n_dev,
+                                                      const float *__restrict__ dfeat, const float *__restrict__ jac,
+                                                      float *__restrict__ d_origins, float *__restrict__ d_directions)
+{
+    const int64_t S = live_count(n_dev, S_cap);
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = blockIdx.x * (int64_t)HT + (threadIdx.x & ~31); base < S; base += (int64_t)gridDim.x * HT) {
+        const int64_t i = base + lane;
+        const bool live = i < S;
+        SampleGeom g;
+        g.cc.sel = false; g.has_dir = false; g.tmid = 0.0f; g.ray = -1 - lane;
+        float dp[3] = {0.0f, 0.0f, 0.0f};
+        if (live) {
+            load_geom(i, origins, directions, ray_idx, t0, t1, g);
+            if (g.cc.sel) {
+                const float2 *f2 = reinterpret_cast<const float2 *>(dfeat) + i;
+                const float2 *j2 = reinterpret_cast<const float2 *>(jac) + i;      // planes [48][S_cap], see encode_samples_kernel
+                float dx[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+                for (int l = 0; l < NL; ++l) {
+                    const float2 gl = __ldg(f2 + (size_t)l * S_cap);
+                    const float2 a = __ldg(j2 + (size_t)(3 * l) * S_cap), b = __ldg(j2 + (size_t)(3 * l + 1) * S_cap),
+                                 c = __ldg(j2 + (size_t)(3 * l + 2) * S_cap);
+                    // (d0x d0y) (d0z d1x) (d1y d1z): feature 0 / feature 1 derivatives along x, y, z, already scaled
+                    dx[0] += gl.x * a.x + gl.y * b.y;
+                    dx[1] += gl.x * a.y + gl.y * c.x;
+                    dx[2] += gl.x * b.x + gl.y * c.y;
+                }
+                contract_normalize_bwd(g.p, g.cc, dx, dp);
+            }
+        }
+        const int32_t rkey = live ? (ray_idx ? g.ray : (int32_t)(i & 0x7fffffff)) : -1 - lane;
+        const int32_t pk = __shfl_up_sync(0xffffffffu, rkey, 1);
+        const bool head = lane == 0 || pk != rkey;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const int last = run_last_lane(heads, lane);
+        const int max_len = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last - lane + 1));
+        const int64_t r = ray_idx ? (int64_t)g.ray : i;
+        const float tm = g.has_dir ? g.tmid : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float so = run_sum(dp[j], lane, last, max_len), sd = run_sum(dp[j] * tm, lane, last, max_len);
+            if (head && live) {
+                if (d_origins) red_add(d_origins + 3 * r + j, so);
+                if (d_directions && directions) red_add(d_directions + 3 * r + j, sd);
+            }
+        }
+    }
+}
+
 }  // namespace lse
 
 using namespace lse;
 
 extern "C" int64_t lse_field_density_bwd_workspace(int64_t S_cap)
 {
-    // feat [S,32] + dfeat [S,32] + dout0 [S] + xs [S,3], fp32, each 256-byte aligned
+    // feat [S,32] + dfeat [S,32] + dout0 [S] + xs [S,3] + jac [S,96], fp32, each 256-byte aligned (untouched parts cost nothing)
     const int64_t s = S_cap < 1 ? 1 : S_cap;
-    return ((s * 32 * 4 + 255) / 256 * 256) * 2 + (s * 4 + 255) / 256 * 256 + (s * 12 + 255) / 256 * 256;
+    return ((s * 32 * 4 + 255) / 256 * 256) * 2 + (s * 4 + 255) / 256 * 256 + (s * 12 + 255) / 256 * 256 + (s * 96 * 4 + 255) / 256 * 256;
 }
 
 static int check_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins, const float *h16, const char *fn)
@@ -191,13 +270,14 @@ static int check_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const f
     return 0;
 }
 
-struct BwdWs { float *feat, *dfeat, *dout0, *xs; };
+struct BwdWs { float *feat, *dfeat, *dout0, *xs, *jac; };
 static BwdWs carve_ws(void *workspace, int64_t S_cap)
 {
-    const int64_t fbytes = (S_cap * 32 * 4 + 255) / 256 * 256, obytes = (S_cap * 4 + 255) / 256 * 256;
+    const int64_t fbytes = (S_cap * 32 * 4 + 255) / 256 * 256, obytes = (S_cap * 4 + 255) / 256 * 256,
+                  xbytes = (S_cap * 12 + 255) / 256 * 256;
     char *w = reinterpret_cast<char *>(workspace);
     return {reinterpret_cast<float *>(w), reinterpret_cast<float *>(w + fbytes), reinterpret_cast<float *>(w + 2 * fbytes),
-            reinterpret_cast<float *>(w + 2 * fbytes + obytes)};
+            reinterpret_cast<float *>(w + 2 * fbytes + obytes), reinterpret_cast<float *>(w + 2 * fbytes + obytes + xbytes)};
 }
 
 // first third of lse_field_density_bwd_ws: needs only d_sigma (not d_h16), so a caller may run it on a side stream
@@ -205,15 +285,19 @@ static BwdWs carve_ws(void *workspace, int64_t S_cap)
 extern "C" int lse_field_density_bwd_encode(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                             const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                             int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
-                                            void *workspace, int64_t workspace_bytes, lse_stream_t stream)
+                                            int with_jacobian, void *workspace, int64_t workspace_bytes, lse_stream_t stream)
 {
     int rc = check_bwd_ws(p, g, origins, h16, __func__);
     if (rc) return rc;
     if (S_cap <= 0 || !p->use_tensor_cores) return 0;
     LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
     const BwdWs ws = carve_ws(workspace, S_cap);
-    encode_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, (cudaStream_t)stream>>>(*p, origins, directions, ray_idx, t0, t1, S_cap,
-                                                                                      n_dev, h16, d_sigma, ws.feat, ws.dout0, ws.xs);
+    if (with_jacobian)
+        encode_samples_kernel<true><<<stride_grid(S_cap, HT, 8), HT, 0, (cudaStream_t)stream>>>(
+            *p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, ws.feat, ws.dout0, ws.xs, ws.jac);
+    else
+        encode_samples_kernel<false><<<stride_grid(S_cap, HT, 8), HT, 0, (cudaStream_t)stream>>>(
+            *p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, ws.feat, ws.dout0, ws.xs, nullptr);
     return check_launch("lse_field_density_bwd_encode");
 }
 
@@ -245,8 +329,8 @@ extern "C" int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFi
 extern "C" int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                           const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                           int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
-                                          const float *d_h16, float *d_origins, float *d_directions, void *workspace,
-                                          int64_t workspace_bytes, lse_stream_t stream)
+                                          const float *d_h16, float *d_origins, float *d_directions, int with_jacobian,
+                                          void *workspace, int64_t workspace_bytes, lse_stream_t stream)
 {
     int rc = check_bwd_ws(p, g, origins, h16, __func__);
     if (rc) return rc;
@@ -258,8 +342,12 @@ extern "C" int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFiel
     rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_h16, ws.dfeat, st);
     if (rc) return rc;
     if (!d_origins && !d_directions) return 0;
-    scatter_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, st>>>(*p, nullptr, origins, directions, ray_idx, t0, t1, S_cap, n_dev,
-                                                                     ws.dfeat, d_origins, d_directions, nullptr);
+    if (with_jacobian)     // lse_field_density_bwd_encode stored d(feat)/dx: no re-gather
+        ray_grad_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, st>>>(origins, directions, ray_idx, t0, t1, S_cap, n_dev, ws.dfeat, ws.jac,
+                                                                  d_origins, d_directions);
+    else
+        scatter_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, st>>>(*p, nullptr, origins, directions, ray_idx, t0, t1, S_cap, n_dev,
+                                                                         ws.dfeat, d_origins, d_directions, nullptr);
     return check_launch("lse_field_density_bwd_rays");
 }
 
@@ -285,7 +373,7 @@ extern "C" int lse_field_density_bwd_ws(const LseFieldParams *p, const LseFieldG
                                         const float *d_h16, float *d_origins, float *d_directions, void *workspace,
                                         int64_t workspace_bytes, lse_stream_t stream)
 {
-    int rc = lse_field_density_bwd_encode(p, g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, workspace,
+    int rc = lse_field_density_bwd_encode(p, g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, 0, workspace,
                                           workspace_bytes, stream);
     if (rc) return rc;
     return lse_field_density_bwd_finish(p, g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, d_h16, d_origins,

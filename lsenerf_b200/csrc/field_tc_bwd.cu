@@ -396,9 +396,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) density_mlp_bwd_tc_kernel(LseF
             const bool live = i < S;
             float f[NF], dout[NO];
             if (live) {
-                const float4 *f4 = reinterpret_cast<const float4 *>(feat + 32 * i);
+                const float2 *f2 = reinterpret_cast<const float2 *>(feat) + i;      // planes [16][S_cap] of float2 (field_hash.cu)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { float4 t = f4[q]; f[4 * q] = t.x; f[4 * q + 1] = t.y; f[4 * q + 2] = t.z; f[4 * q + 3] = t.w; }
+                for (int l = 0; l < NL; ++l) { const float2 t = __ldg(f2 + (size_t)l * S_cap); f[2 * l] = t.x; f[2 * l + 1] = t.y; }
                 const float4 *gh = reinterpret_cast<const float4 *>(d_h16 + 16 * i);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -432,9 +432,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) density_mlp_bwd_tc_kernel(LseF
             hs.publish_and_wait();
             read_row<NF>(trow, cden::SCR, f);                   // dfeat
             if (live) {
-                float4 *o4 = reinterpret_cast<float4 *>(dfeat + 32 * i);
+                float2 *o2 = reinterpret_cast<float2 *>(dfeat) + i;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) o4[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                for (int l = 0; l < NL; ++l) o2[(size_t)l * S_cap] = make_float2(f[2 * l], f[2 * l + 1]);
             }
         }
         if (any && (row >> 5) <= 2) {   // warps 0..2 (tcgen05.ld is warp-collective); rows 0..64 carry data

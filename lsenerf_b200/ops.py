@@ -593,16 +593,18 @@ class _RenderRays(torch.autograd.Function):
             cur, side = torch.cuda.current_stream(), _side_stream(dev)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
+                defer = bool(opts.defer_table_scatter and bufs["table"] is not None)
+                jac = int(defer and (g_o is not None or gd is not None))      # ray gradients from the stored Jacobian, no re-gather
                 call("lse_field_density_bwd_encode", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
-                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(ws), nbytes, stream())
+                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), jac, P(ws), nbytes, stream())
             call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
                  P(h16), P(d_rgb), P(d_h16), P(gd), stream())
             cur.wait_stream(side)
-            if opts.defer_table_scatter and bufs["table"] is not None:
+            if defer:
                 # the table gradient feeds the optimizer only: leave its scatter to the caller (engine: side stream, under the next
                 # step's ray generation); everything the rest of this backward pass needs is produced here
                 call("lse_field_density_bwd_rays", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
-                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), P(ws), nbytes, stream())
+                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), jac, P(ws), nbytes, stream())
                 opts.deferred_table = (fw, bufs, o, d, m, ws, nbytes, S_cap)
             else:
                 call("lse_field_density_bwd_finish", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
