@@ -398,13 +398,13 @@ def run_b200(args):
         # ALGORITHMIC bytes / flops per step: per-sample figures x the live sample counts read back
         # from the device.  S0 marched, S_eval evaluated by the early-terminating culling pass, S1 kept.
         #   density_fwd_list : 1024 B gathered + 12 B (ray index, t0, t1) in + 68 B (sigma, h16) out            per EVALUATED sample
-        #   density_bwd      : encode = 1024 B re-gathered + 128 B feat out + 12 B grid coords out + 20 B in;  rays = base-MLP backward
-        #                      (128 feat + 68 in, 128 dfeat out) + d/dx (1024 B re-gathered + 128 dfeat + 12 B in);  table = 1024 B
-        #                      scattered + 128 B dfeat + 12 B coords in                                             per KEPT sample
+        #   density_bwd      : encode = 1024 B re-gathered + 128 B feat + 384 B Jacobian + 12 B grid coords out + 20 B in;  rays =
+        #                      base-MLP backward (128 feat + 68 in, 128 dfeat out) + ray gradients (128 dfeat + 384 Jacobian + 12 B in);
+        #                      table = 1024 B scattered + 128 B dfeat + 12 B coords in                              per KEPT sample
         #   color fwd/bwd    : the dense contraction, 16 640 flop/sample forward, 3 x that backward (recompute + dgrad + wgrad)
         alg_bytes = {"lse_field_density_fwd_list": (1024 + 12 + 68) * S_eval, "lse_field_density_fwd": (1024 + 12 + 68) * S0,
-                     "lse_field_density_bwd_encode": (1024 + 128 + 12 + 20) * S1,
-                     "lse_field_density_bwd_rays": (128 + 68 + 128 + 1024 + 128 + 12) * S1,
+                     "lse_field_density_bwd_encode": (1024 + 128 + 384 + 12 + 20) * S1,
+                     "lse_field_density_bwd_rays": (128 + 68 + 128 + 128 + 384 + 12) * S1,
                      "lse_field_density_bwd_table": (1024 + 128 + 12) * S1,
                      "lse_field_density_bwd_finish": (128 + 68 + 128 + 2 * 1024 + 128 + 12) * S1}
         alg_flops = {"lse_field_color_fwd": 16640 * S1, "lse_field_color_bwd": 3 * 16640 * S1}
