@@ -306,6 +306,20 @@ def run_b200(args):
         burn_steps = int(t.item())
         gs.step_no = START + burn_steps
         opt.step_count = START + burn_steps
+        # the other ranks have never run the grid update on a grid of this size: let them do one now (caching-allocator growth,
+        # lazy kernel loading -- tens of milliseconds that would otherwise land inside the timed region and stall every rank at the
+        # next exchange barrier), then restore rank 0's grid and give every rank rank 0's update generator state
+        if rank != 0:
+            pipe._model.update_occupancy(16 * (gs.step_no // 16 + 1))
+        torch.cuda.synchronize()
+        for t in (og.occs, bin_u8, og.occ_mean):
+            dist.broadcast(t, 0)
+        og.packed(force=True)
+        gstate = og._gen.get_state().to(dev)
+        dist.broadcast(gstate, 0)
+        og._gen.set_state(gstate.cpu())
+    # the first (untimed) warm-up step performs a grid update on every rank; the next one falls inside the timed steps
+    gs.step_no = 16 * ((gs.step_no + 15) // 16)
 
     def barrier():
         if world > 1:
