@@ -314,16 +314,18 @@ class GraphedStep:
         self.graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_a):
             self._phase_a()
+        # B gets its OWN memory pool: graph C (side stream) reads B's buffers while A of the next step is already running, and
+        # inside one pool the allocator would have handed A's freed temporaries (march slabs, run lists) to B's workspace
         self.graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+        with torch.cuda.graph(self.graph_b):
             self.loss_out = self._phase_b()
         if self._deferred() is not None:
             self.graph_c = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_c, pool=self.graph_a.pool()):
+            with torch.cuda.graph(self.graph_c, pool=self.graph_b.pool()):
                 ops.run_deferred_table_scatter(self._deferred())
         for name in self.optim.names:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self.graph_a.pool()):
+            with torch.cuda.graph(g):
                 self.optim.apply(only=[name])
             self.graph_opt[name] = g
 
