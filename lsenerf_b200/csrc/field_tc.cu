@@ -99,6 +99,11 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
     const uint32_t tmem_row = tmem_wg + ((uint32_t)((warp & 3) * 32) << 16);    // lane field: this warp's 32 lanes
     float *a_hi = smem + L::A + wg * 2 * A_FLOATS, *a_lo = a_hi + A_FLOATS;
     uint32_t phase = 0;
+    // MMA issue: warp 0 of the warpgroup, one elected lane, warp-uniform operands
+    const bool issue_warp = warp_uniform((uint32_t)(row >> 5)) == 0u;
+    const uint32_t u_wg = warp_uniform((uint32_t)wg), u_sm = warp_uniform(smem_u32(smem));
+    const uint32_t u_tm = warp_uniform(tmem_base) + u_wg * TMEM_COLS_PER_WG;
+    const uint32_t u_ahi = u_sm + 4u * (L::A + u_wg * 2 * A_FLOATS), u_alo = u_ahi + 4u * A_FLOATS;
 
     const int64_t S = live_count(n_dev, S_cap);
     const int64_t n_tiles = (S + WG - 1) / WG;
@@ -123,10 +128,13 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
         fence_proxy_async();
         tc_fence_before();
         bar_sync(1 + wg, WG);
-        if (row == 0) {
-            tc_fence_after();
-            issue_layer(tmem_wg, a_hi, a_lo, smem + L::W1, smem + L::W1L, 64, 32);
-            mma_commit(mbar + wg);
+        if (issue_warp) {
+            if (elect_one_lane()) {
+                tc_fence_after();
+                issue_layer_u(u_tm, u_ahi, u_alo, u_sm + 4u * L::W1, u_sm + 4u * L::W1L, 64, 32);
+                mma_commit(mbar + wg);
+            }
+            __syncwarp();
         }
         mbar_wait(mbar + wg, phase); phase ^= 1;
         tc_fence_after();
@@ -140,10 +148,13 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
         fence_proxy_async();
         tc_fence_before();
         bar_sync(1 + wg, WG);
-        if (row == 0) {
-            tc_fence_after();
-            issue_layer(tmem_wg + 64, a_hi, a_lo, smem + L::W2, smem + L::W2L, 16, 64);
-            mma_commit(mbar + wg);
+        if (issue_warp) {
+            if (elect_one_lane()) {
+                tc_fence_after();
+                issue_layer_u(u_tm + 64, u_ahi, u_alo, u_sm + 4u * L::W2, u_sm + 4u * L::W2L, 16, 64);
+                mma_commit(mbar + wg);
+            }
+            __syncwarp();
         }
         mbar_wait(mbar + wg, phase); phase ^= 1;
         tc_fence_after();
@@ -194,6 +205,10 @@ __global__ void __launch_bounds__(WG *NWG, 1) color_fwd_tc_kernel(LseFieldParams
     const uint32_t tmem_row = tmem_wg + ((uint32_t)((warp & 3) * 32) << 16);
     float *a_hi = smem + L::A + wg * 2 * A_FLOATS, *a_lo = a_hi + A_FLOATS;
     uint32_t phase = 0;
+    const bool issue_warp = warp_uniform((uint32_t)(row >> 5)) == 0u;
+    const uint32_t u_wg = warp_uniform((uint32_t)wg), u_sm = warp_uniform(smem_u32(smem));
+    const uint32_t u_tm = warp_uniform(tmem_base) + u_wg * TMEM_COLS_PER_WG;
+    const uint32_t u_ahi = u_sm + 4u * (L::A + u_wg * 2 * A_FLOATS), u_alo = u_ahi + 4u * A_FLOATS;
 
     const int64_t S = live_count(n_dev, S_cap);
     const int64_t n_tiles = (S + WG - 1) / WG;
@@ -217,10 +232,13 @@ __global__ void __launch_bounds__(WG *NWG, 1) color_fwd_tc_kernel(LseFieldParams
             fence_proxy_async();
             tc_fence_before();
             bar_sync(1 + wg, WG);
-            if (row == 0) {
-                tc_fence_after();
-                issue_layer(tmem_wg, a_hi, a_lo, smem + (layer == 0 ? L::W3 : L::W4), smem + (layer == 0 ? L::W3L : L::W4L), 64, 64);
-                mma_commit(mbar + wg);
+            if (issue_warp) {
+                if (elect_one_lane()) {
+                    tc_fence_after();
+                    issue_layer_u(u_tm, u_ahi, u_alo, u_sm + 4u * (layer == 0 ? L::W3 : L::W4), u_sm + 4u * (layer == 0 ? L::W3L : L::W4L), 64, 64);
+                    mma_commit(mbar + wg);
+                }
+                __syncwarp();
             }
             mbar_wait(mbar + wg, phase); phase ^= 1;
             tc_fence_after();
@@ -235,10 +253,13 @@ __global__ void __launch_bounds__(WG *NWG, 1) color_fwd_tc_kernel(LseFieldParams
         fence_proxy_async();
         tc_fence_before();
         bar_sync(1 + wg, WG);
-        if (row == 0) {
-            tc_fence_after();
-            issue_layer(tmem_wg + 64, a_hi, a_lo, smem + L::W5, smem + L::W5L, 16, 64);
-            mma_commit(mbar + wg);
+        if (issue_warp) {
+            if (elect_one_lane()) {
+                tc_fence_after();
+                issue_layer_u(u_tm + 64, u_ahi, u_alo, u_sm + 4u * L::W5, u_sm + 4u * L::W5L, 16, 64);
+                mma_commit(mbar + wg);
+            }
+            __syncwarp();
         }
         mbar_wait(mbar + wg, phase); phase ^= 1;
         tc_fence_after();

@@ -134,35 +134,38 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) color_bwd_tc_kernel(LseFieldPa
 
     if (is_issuer) {
         // =================================================== MMA-issuing warp ===================================================
-        const uint32_t aP = smem_u32(bP), aQ = smem_u32(bQ), aR = smem_u32(bR);
-        const uint32_t w3 = smem_u32(sm16 + L::W3), w4 = smem_u32(sm16 + L::W4), w5 = smem_u32(sm16 + L::W5);
+        // warp-uniform operands (uniform registers feed tcgen05.mma directly instead of a per-instruction broadcast loop)
+        const uint32_t wg_u = uniform((uint32_t)wg), sm_u = uniform(smem_u32(sm16));
+        const uint32_t tmem = uniform(*tmem_slot) + wg_u * TMEM_WG;
+        const uint32_t aP = sm_u + 2u * (wg_u * L::WG + L::P), aQ = aP + 2u * BUF64, aR = aQ + 2u * BUF64;
+        const uint32_t w3 = sm_u + 2u * L::W3, w4 = sm_u + 2u * L::W4, w5 = sm_u + 2u * L::W5;
         uint32_t accum = 0;
         for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
             hs.wait_staged();                                                        // ph0: P = X0
-            if (lane == 0) { issue_fwd(tmem + ccol::SCR, aP, PIECE64, w3, 64, 64); mma_commit(hs.done); }
+            if (elect_one()) { issue_fwd(tmem + ccol::SCR, aP, PIECE64, w3, 64, 64); mma_commit(hs.done); }
             __syncwarp();
             hs.wait_staged();                                                        // ph1: Q = H1
-            if (lane == 0) { issue_fwd(tmem + ccol::SCR, aQ, PIECE64, w4, 64, 64); mma_commit(hs.done); }
+            if (elect_one()) { issue_fwd(tmem + ccol::SCR, aQ, PIECE64, w4, 64, 64); mma_commit(hs.done); }
             __syncwarp();
             hs.wait_staged();                                                        // ph2: P = H2
-            if (lane == 0) { issue_fwd(tmem + ccol::SCR, aP, PIECE64, w5, 16, 64); mma_commit(hs.done); }
+            if (elect_one()) { issue_fwd(tmem + ccol::SCR, aP, PIECE64, w5, 16, 64); mma_commit(hs.done); }
             __syncwarp();
             hs.wait_staged();                                                        // ph3: R = dO
-            if (lane == 0) {
+            if (elect_one()) {
                 issue_wgradT(tmem + ccol::A5, aP, PIECE64, aR, PIECE16, 16, accum);  // [H2|1]^T dO
                 issue_dgrad(tmem + ccol::SCR, aR, PIECE16, w5, 16, 64);              // dH2 = dO W5
                 mma_commit(hs.done);
             }
             __syncwarp();
             hs.wait_staged();                                                        // ph4: P = dA2
-            if (lane == 0) {
+            if (elect_one()) {
                 issue_wgradT(tmem + ccol::A4, aQ, PIECE64, aP, PIECE64, 64, accum);  // [H1|1]^T dA2
                 issue_dgrad(tmem + ccol::SCR, aP, PIECE64, w4, 64, 64);              // dH1 = dA2 W4
                 mma_commit(hs.done);
             }
             __syncwarp();
             hs.wait_staged();                                                        // ph5: Q = dA1, P = X0 (x[63] = 1)
-            if (lane == 0) {
+            if (elect_one()) {
                 issue_wgradT(tmem + ccol::A3, aP, PIECE64, aQ, PIECE64, 64, accum);  // X0^T dA1 (row 63 = db3)
                 issue_dgrad(tmem + ccol::SCR, aQ, PIECE64, w3, 64, 64);              // dX0 = dA1 W3
                 mma_commit(hs.done);
@@ -364,22 +367,24 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) density_mlp_bwd_tc_kernel(LseF
     bf16_t *bP = sm16 + wg * L::WG + L::P, *bQ = bP + BUF32, *bR = bQ + BUF64;
 
     if (is_issuer) {
-        const uint32_t aP = smem_u32(bP), aQ = smem_u32(bQ), aR = smem_u32(bR);
-        const uint32_t w1 = smem_u32(sm16 + L::W1), w2 = smem_u32(sm16 + L::W2);
+        const uint32_t wg_u = uniform((uint32_t)wg), sm_u = uniform(smem_u32(sm16));
+        const uint32_t tmem = uniform(*tmem_slot) + wg_u * TMEM_WG;
+        const uint32_t aP = sm_u + 2u * (wg_u * L::WG + L::P), aQ = aP + 2u * BUF32, aR = aQ + 2u * BUF64;
+        const uint32_t w1 = sm_u + 2u * L::W1, w2 = sm_u + 2u * L::W2;
         uint32_t accum = 0;
         for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
             hs.wait_staged();                                                        // ph0: P = feat, R = dOut
-            if (lane == 0) { issue_fwd(tmem + cden::SCR, aP, PIECE32, w1, 64, 32); mma_commit(hs.done); }
+            if (elect_one()) { issue_fwd(tmem + cden::SCR, aP, PIECE32, w1, 64, 32); mma_commit(hs.done); }
             __syncwarp();
             hs.wait_staged();                                                        // ph1: Q = H1
-            if (lane == 0) {
+            if (elect_one()) {
                 issue_wgradT(tmem + cden::A2, aQ, PIECE64, aR, PIECE16, 16, accum);  // [H1|1]^T dOut
                 issue_dgrad(tmem + cden::SCR, aR, PIECE16, w2, 16, 64);              // dH1 = dOut W2
                 mma_commit(hs.done);
             }
             __syncwarp();
             hs.wait_staged();                                                        // ph2: Q = dA1
-            if (lane == 0) {
+            if (elect_one()) {
                 issue_wgradT(tmem + cden::A1, aP, PIECE32, aQ, PIECE64, 64, accum);  // [feat|1]^T dA1
                 issue_dgrad(tmem + cden::SCR, aQ, PIECE64, w1, 64, 32);              // dfeat = dA1 W1
                 mma_commit(hs.done);

@@ -149,6 +149,16 @@ __device__ __forceinline__ void read_row(uint32_t tmem_row, int col0, float (&v)
     tmem_ld_wait();
 }
 
+// one lane of a converged warp (elect.sync): the compiler keeps warp-uniform operands of the guarded code in uniform registers
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// make a warp-uniform value provably uniform for the compiler
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- mbarrier handshake between a compute warpgroup and its MMA-issuing warp ---------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {

@@ -145,5 +145,30 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const float *a_hi, 
     }
 }
 
+// the same with shared-window byte addresses (pass warp-uniform values: the descriptors then live in uniform registers and every
+// tcgen05.mma is one instruction instead of a per-instruction register->uniform broadcast loop)
+__device__ __forceinline__ void issue_layer_u(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, int N, int K)
+{
+    const uint32_t idesc = idesc_tf32(128, N);
+    const uint32_t a_lbo = 128 * 16, w_lbo = (uint32_t)N * 16;
+    const uint64_t ah0 = smem_desc(a_hi, a_lbo, 128), al0 = smem_desc(a_lo, a_lbo, 128);
+    const uint64_t wh0 = smem_desc(w_hi, w_lbo, 128), wl0 = smem_desc(w_lo, w_lbo, 128);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t ao = (uint64_t)((ks * 2 * a_lbo) >> 4), wo = (uint64_t)((ks * 2 * w_lbo) >> 4);   // start-address field, 16-byte units
+        mma_tf32(d_tmem, ah0 + ao, wh0 + wo, idesc, acc); acc = 1;
+        mma_tf32(d_tmem, al0 + ao, wh0 + wo, idesc, 1);
+        mma_tf32(d_tmem, ah0 + ao, wl0 + wo, idesc, 1);
+    }
+}
+// one lane of a converged warp (elect.sync) / a warp-uniform value made provably uniform for the compiler
+__device__ __forceinline__ bool elect_one_lane()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 }  // namespace tc
 }  // namespace lse
