@@ -257,7 +257,8 @@ def run_b200(args):
     # steady-state training: start after the occupancy grid's 256-step warm-up schedule (during warm-up every 16th step
     # re-evaluates all 4x128^3 cells, afterwards a quarter of them + the occupied ones)
     START = 1000
-    gs = GraphedStep(pipe, opt, world, use_graph=not args.no_graph)
+    gs = GraphedStep(pipe, opt, world, use_graph=not args.no_graph, device_store=args.device_store)
+    sample_batches = dm.sample_rand_batches if args.device_store else dm.sample_host_batches
     opt.step_count = START
     gs.capture(start_step=START)
     # untimed burn-in: from the baked density prior the occupancy grid first grows (marched samples/ray 100 -> 320 by
@@ -335,7 +336,7 @@ def run_b200(args):
 
     clocks = ClockSampler(local)
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------------
-    staged = [gs.stage.pack_to_device(*dm.sample_host_batches()) for _ in range(K + W)]
+    staged = [gs.stage.pack_to_device(*sample_batches()) for _ in range(K + W)]
     torch.cuda.synchronize()
     for i in range(W):
         gs.step(packed_dev=staged[i])
@@ -366,11 +367,11 @@ def run_b200(args):
     clocks.start()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    hb = dm.sample_host_batches()
+    hb = sample_batches()
     pending = None
     for i in range(K):
         rb = gs.step_async(host_batches=hb)     # pack into pinned staging + H2D + graph replays + D2H of the losses, all asynchronous
-        hb = dm.sample_host_batches()           # host pixel draw + gather of the NEXT batch overlaps the device step
+        hb = sample_batches()                   # host pixel draw + gather of the NEXT batch overlaps the device step
         if pending is not None:
             host_loss = pending.get()           # losses of the PREVIOUS step on the host (waits for that copy only)
         pending = rb
@@ -383,7 +384,7 @@ def run_b200(args):
     h2d, d2h = gs.stage.nbytes, host_loss.numel() * host_loss.element_size()
 
     # ---- per-kernel-class device time + roofline of the dominant kernel (eager, outside the timed regions) ----------------
-    eager = GraphedStep(pipe, opt, world, use_graph=False)
+    eager = GraphedStep(pipe, opt, world, use_graph=False, device_store=args.device_store)
     eager.step_no = gs.step_no
     eager.step(); eager.step()
     _lib.profile_start()
@@ -466,6 +467,8 @@ def run_b200(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "parallelism": f"ray-sharded dp{world}; gradient exchange: {opt.exchange_kind()}",
                            "l2": "working set per step (64 MiB table + 64 MiB grad + 128 MiB Adam state + sample buffers) exceeds the 126 MB L2; no explicit flush",
+                           "image_store": "device-resident stacks, on-device pixel gather from host-drawn uniforms (SURVEY 8f-2)" if args.device_store
+                           else "pinned host stacks, host pixel gather (reference layout)",
                            "samples_marched_per_step": S0, "samples_evaluated_by_culling_pass": S_eval, "samples_kept_per_step": S1, "capacity_overflow": overflow,
                            "mlp": "tcgen05 (3xTF32 fwd, BF16x3 bwd)" if pipe._model.config.use_tensor_cores else "fp32 SIMT",
                            "step": "one CUDA-graph replay (zero_grad+raygen+render+loss+backward) + Adam graph" if not args.no_graph else "eager launches",
@@ -496,6 +499,7 @@ def main():
     ap.add_argument("--fixed-burn-in", action="store_true", help="stop the burn-in after exactly --burn-in steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--device-store", action="store_true", help="image / event stacks resident in HBM, pixel gather on the device (SURVEY 8f-2)")
     ap.add_argument("--profiler-window", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: NCCL all-reduce + local Adam instead of the fused peer-memory kernel")
     args = ap.parse_args()

@@ -51,6 +51,14 @@ int lse_pose_interp_bwd(const float *ctrl_tangents, const float *ctrl_ts, int K,
                         int n_virtual, float t_offset, float t_step, const float *dM, const float *scale,
                         const float *d_c2w, float *d_ctrl_tangents, float *d_scale, lse_stream_t stream);
 
+/* (a1) EvPixelSampler.collate_image_dataset_batch (lse_nerf/lse_pixel_sampler.py:6-48) on image stacks resident in
+ * HBM: rand3 [B,3] uniforms in [0,1) (drawn by the host generator, so the pick is bit-identical to the host sampler) ->
+ * (c,y,x) = floor(rand * [N,H,W]); image_out [B,C] = images[c,y,x,:]; indices [B,3] = (image_idx[c], y, x);
+ * appearance_out [B] = appearance_id[c]; e_thresh_out [B] = e_thresh[c] (both optional). */
+int lse_pixel_gather(const float *rand3, int64_t B, int64_t N, int H, int W, const float *images, int C,
+                     const int64_t *image_idx, const int64_t *appearance_id, const float *e_thresh, int64_t *indices,
+                     float *image_out, int64_t *appearance_out, float *e_thresh_out, lse_stream_t stream);
+
 /* EdCameras._generate_rays_from_coords, perspective branch (lse_nerf/lse_cameras.py:349-395,487-493,539-561).
  *   c2w [n,3,4], coords [n,2]=(y,x)  ->  origins [n,3], directions [n,3], pixel_area [n], dir_norm [n] */
 int lse_rays_from_c2w_fwd(const float *c2w, const float *coords, int64_t n, float fx, float fy, float cx, float cy,

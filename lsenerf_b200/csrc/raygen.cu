@@ -171,6 +171,48 @@ extern "C" int lse_pose_interp_bwd(const float *ctrl_tangents, const float *ctrl
     return check_launch("lse_pose_interp_bwd");
 }
 
+// ---- (a1) pixel sampling against image stacks resident in HBM ---------------------------------------------------------
+// EvPixelSampler.collate_image_dataset_batch (lse_pixel_sampler.py:6-48) + nerfstudio PixelSampler.sample_method:
+//     (c, y, x) = floor(rand(B,3) * [N,H,W]).long() ; image[c,y,x,:], e_thresh[c], appearance_id[c] ; indices[:,0] = image_idx[c]
+// The uniforms are still drawn by torch's generator on the host (bit-exact with the host sampler); only they cross PCIe.
+namespace lse {
+__global__ void pixel_gather_kernel(const float *__restrict__ rand3, int64_t B, int64_t N, int H, int W,
+                                    const float *__restrict__ images, int C, const int64_t *__restrict__ image_idx,
+                                    const int64_t *__restrict__ appearance_id, const float *__restrict__ e_thresh,
+                                    int64_t *__restrict__ indices, float *__restrict__ image_out,
+                                    int64_t *__restrict__ appearance_out, float *__restrict__ e_thresh_out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        // float32 product then floor, exactly torch.floor(rand * tensor([N,H,W]))
+        int64_t c = (int64_t)floorf(__fmul_rn(rand3[3 * i], (float)N));
+        int64_t y = (int64_t)floorf(__fmul_rn(rand3[3 * i + 1], (float)H));
+        int64_t x = (int64_t)floorf(__fmul_rn(rand3[3 * i + 2], (float)W));
+        c = c < 0 ? 0 : (c >= N ? N - 1 : c); y = y < 0 ? 0 : (y >= H ? H - 1 : y); x = x < 0 ? 0 : (x >= W ? W - 1 : x);
+        const float *px = images + (((c * H + y) * W + x) * (int64_t)C);
+        for (int k = 0; k < C; ++k) image_out[i * C + k] = px[k];
+        indices[3 * i] = image_idx ? image_idx[c] : c;
+        indices[3 * i + 1] = y;
+        indices[3 * i + 2] = x;
+        if (appearance_out) appearance_out[i] = appearance_id ? appearance_id[c] : c;
+        if (e_thresh_out && e_thresh) e_thresh_out[i] = e_thresh[c];
+    }
+}
+}  // namespace lse
+
+extern "C" int lse_pixel_gather(const float *rand3, int64_t B, int64_t N, int H, int W, const float *images, int C,
+                                const int64_t *image_idx, const int64_t *appearance_id, const float *e_thresh,
+                                int64_t *indices, float *image_out, int64_t *appearance_out, float *e_thresh_out,
+                                lse_stream_t stream)
+{
+    LSE_CHECK_ARG(rand3 && images && indices && image_out, "missing pointer");
+    LSE_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0, "bad image stack shape");
+    if (B <= 0) return 0;
+    int threads = 256;
+    lse::pixel_gather_kernel<<<lse::stride_grid(B, threads), threads, 0, (cudaStream_t)stream>>>(
+        rand3, B, N, H, W, images, C, image_idx, appearance_id, e_thresh, indices, image_out, appearance_out, e_thresh_out);
+    return lse::check_launch("lse_pixel_gather");
+}
+
 extern "C" int lse_rays_from_c2w_fwd(const float *c2w, const float *coords, int64_t n, float fx, float fy, float cx,
                                      float cy, float *origins, float *directions, float *pixel_area, float *dir_norm,
                                      lse_stream_t stream)

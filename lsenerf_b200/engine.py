@@ -263,14 +263,20 @@ class GraphedStep:
 
     FIELD_GROUP = "fields"
 
-    def __init__(self, pipeline: LSENeRFPipeline, optim: ArenaAdam, world_size: int = 1, use_graph: bool = True) -> None:
+    def __init__(self, pipeline: LSENeRFPipeline, optim: ArenaAdam, world_size: int = 1, use_graph: bool = True,
+                 device_store: bool = False) -> None:
         self.pipeline, self.optim, self.world = pipeline, optim, world_size
         self.use_graph = use_graph
         dm = pipeline.datamanager
         dm.lean = True                      # captured step: no launches for metadata the fused path never reads
         pipeline.lean = True                # ... nor for outputs the loss never reads (depth, detached linear, metrics)
         pipeline.defer_table_scatter = bool(pipeline.model.config.use_tensor_cores)
-        hc, he = dm.sample_host_batches()
+        # device_store: image stacks resident in HBM, the staged "batch" is just the [B,3] uniforms of the pixel
+        # draw and graph A starts with the gather kernel
+        self.device_store = device_store
+        if device_store:
+            dm.enable_device_store()
+        hc, he = dm.sample_rand_batches() if device_store else dm.sample_host_batches()
         self.stage = BatchStage(hc, he, dm.device)
         self.stage.pack_host(hc, he); self.stage.upload()
         self.graph_a: Optional[torch.cuda.CUDAGraph] = None
@@ -290,7 +296,10 @@ class GraphedStep:
     # ---- the two halves of an iteration -----------------------------------------------------------------------------------------
     def _phase_a(self) -> None:
         self.optim.zero_grad(only=self.early)
-        self.ctx = self.pipeline.prepare_train(self.step_no, self.stage.device_batches(), premarch=True)
+        batches = self.stage.device_batches()
+        if self.device_store:
+            batches = self.pipeline.datamanager.gather_device_batches(batches)
+        self.ctx = self.pipeline.prepare_train(self.step_no, batches, premarch=True)
 
     def _phase_b(self) -> torch.Tensor:
         self.optim.zero_grad(only=[self.FIELD_GROUP])
@@ -367,7 +376,8 @@ class GraphedStep:
             self.stage.load_packed(packed_dev)
         else:
             if host_batches is None:
-                host_batches = self.pipeline.datamanager.sample_host_batches()
+                dm = self.pipeline.datamanager
+                host_batches = dm.sample_rand_batches() if self.device_store else dm.sample_host_batches()
             self.stage.pack_host(*host_batches)
             self.stage.upload()
         world = 1 if self.local_only else self.world

@@ -105,6 +105,35 @@ class MultiCamManager(nn.Module):
         evs = self.train_evs_pixel_sampler.sample(self.evs_store.batch()) if self.get_train_evs_rays_per_batch() > 0 else None
         return col, evs
 
+    # ---- image / event stacks resident in HBM, pixel gather on the device ---------------------------------------
+    def enable_device_store(self) -> None:
+        """copy the image stacks to the device once (236 MB RGB + 157 MB events at 640x480); afterwards a step uploads only the
+        [B,3] uniforms of the pixel draw."""
+        dev = self.device
+        self._dev_store = {}
+        for name, st in (("col", self.col_store), ("evs", self.evs_store)):
+            self._dev_store[name] = dict(image=st.image.to(dev).contiguous(), image_idx=st.image_idx.to(dev).contiguous(),
+                                         appearance_id=st.appearance_id.to(dev).contiguous(),
+                                         e_thresh=st.e_thresh.to(dev).float().contiguous() if st.e_thresh is not None else None)
+
+    def sample_rand_batches(self):
+        """host half of the device-store path: just the uniforms (same generator consumption as sample_host_batches)."""
+        col = {"rand": self.train_col_pixel_sampler.draw()} if self.get_train_col_rays_per_batch() > 0 else None
+        evs = {"rand": self.train_evs_pixel_sampler.draw()} if self.get_train_evs_rays_per_batch() > 0 else None
+        return col, evs
+
+    def gather_device_batches(self, rand_batches):
+        """device half: {"rand": [B,3]} (already on the device) -> the batch dicts next_train() consumes."""
+        from . import ops
+        out = []
+        for name, rb in zip(("col", "evs"), rand_batches):
+            if rb is None:
+                out.append(None)
+                continue
+            st = self._dev_store[name]
+            out.append(ops.pixel_gather(rb["rand"], st["image"], st["image_idx"], st["appearance_id"], st["e_thresh"]))
+        return tuple(out)
+
     def to_device(self, batch, pinned: bool = False):
         if batch is None:
             return None

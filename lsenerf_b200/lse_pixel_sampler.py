@@ -17,6 +17,11 @@ class EvPixelSampler:
         r = torch.rand((batch_size, 3), device=device, generator=self.generator)
         return torch.floor(r * torch.tensor([num_images, image_height, image_width], device=device)).long()
 
+    def draw(self, batch_size: int = None) -> torch.Tensor:
+        """the [B,3] uniforms sample_method would draw (same generator, same consumption): the device-resident store gathers from
+        them on the GPU (ops.pixel_gather) and picks exactly the pixels the host path would have picked."""
+        return torch.rand((batch_size or self.num_rays_per_batch, 3), generator=self.generator)
+
     def sample(self, image_batch: Dict):
         return self.collate_image_dataset_batch(image_batch, self.num_rays_per_batch)
 

@@ -134,6 +134,27 @@ def pose_delta(pose_adjustment, cam_idx, origins, directions):
 
 
 # =================================================================================================================
+# (a1) pixel sampling on device-resident image stacks
+# =================================================================================================================
+def pixel_gather(rand3: Tensor, images: Tensor, image_idx: Tensor, appearance_id: Tensor, e_thresh: Optional[Tensor] = None) -> dict:
+    """EvPixelSampler.collate_image_dataset_batch on image stacks in HBM; rand3 [B,3] = the uniforms the host sampler would draw."""
+    r = _f32(rand3, "rand3")
+    B = r.shape[0]
+    N, H, W, C = images.shape
+    dev = images.device
+    indices = torch.empty(B, 3, dtype=torch.int64, device=dev)
+    img = torch.empty(B, C, device=dev)
+    app = torch.empty(B, dtype=torch.int64, device=dev)
+    thr = torch.empty(B, device=dev) if e_thresh is not None else None
+    call("lse_pixel_gather", P(r), B, N, H, W, P(_f32(images, "images")), C, P(image_idx), P(appearance_id), P(e_thresh), P(indices),
+         P(img), P(app), P(thr), stream())
+    out = {"image": img, "indices": indices, "appearance_id": app}
+    if thr is not None:
+        out["e_thresh"] = thr
+    return out
+
+
+# =================================================================================================================
 # (b) marching
 # =================================================================================================================
 @dataclass

@@ -616,3 +616,30 @@ def test_engine_pipelined_step_matches_plain_step(dev):
         loss = gs.step()
     gs.flush(); torch.cuda.synchronize()
     assert torch.isfinite(loss).all() and not torch.equal(w0, opt.arenas["fields"].data)
+
+
+def test_device_resident_store_picks_the_host_samplers_pixels(dev):
+    """lse_pixel_gather on device-resident stacks from the uniforms of the host generator == EvPixelSampler on the host
+    stacks, bit for bit (indices, pixel values, appearance ids, thresholds); and the engine runs a step through it."""
+    from lsenerf_b200.engine import ArenaAdam, GraphedStep
+    scene, p = _pipeline(dev, deblur=True, cam_opt=True)
+    dm = p.datamanager
+    dm.enable_device_store()
+    g_state = dm.train_col_pixel_sampler.generator.get_state()
+    host_col, host_evs = dm.sample_host_batches()
+    dm.train_col_pixel_sampler.generator.set_state(g_state)          # col and evs samplers share one generator
+    rc, re = dm.sample_rand_batches()
+    dcol, devs = dm.gather_device_batches(({"rand": rc["rand"].to(dev)}, {"rand": re["rand"].to(dev)}))
+    for host, devb in ((host_col, dcol), (host_evs, devs)):
+        for k, v in host.items():
+            if isinstance(v, torch.Tensor):
+                assert torch.equal(devb[k].cpu(), v), k
+    p.train()
+    opt = ArenaAdam(p.get_param_groups())
+    gs = GraphedStep(p, opt, 1, use_graph=True, device_store=True)
+    gs.capture(start_step=1)
+    w0 = opt.arenas["fields"].data.clone()
+    for _ in range(3):
+        loss = gs.step()
+    gs.flush(); torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and not torch.equal(w0, opt.arenas["fields"].data)
