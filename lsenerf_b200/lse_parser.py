@@ -242,3 +242,21 @@ def build_datamanager(scene: dict, config, device="cuda", seed: Optional[int] = 
         return ImageStore(img, torch.arange(n), app, torch.full((n,), float(thr)) if thr is not None else None)
     return MultiCamManager(config, c.cameras, e.cameras, store(c.images, c.appearance_ids), store(e.events, e.appearance_ids, e.e_thresh),
                            scene["dM"], scene["num_emb"], device=device, seed=seed)
+
+
+def build_pipeline(root: str, experiment: str = "lsenerf", num_rays: int = 8192, rgb_frac: Optional[float] = None, deblur: bool = True,
+                   cam_opt: bool = True, device="cuda", seed: Optional[int] = None, scale_factor: float = 1.0,
+                   scene_scale: float = 1.0, **model_kw):
+    """`ns-train lsenerf --data <root>` minus the trainer: parse a formatted scene directory and return the LSENeRFPipeline
+    (data manager with the parsed cameras / image stacks + model) for one of the shipped experiment configurations."""
+    from .lse_config import experiment as make_cfg
+    from .lse_pipeline import LSENeRFPipeline
+    from .lsenerf import LSENeRFModel
+    scene = load_scene(root, scale_factor, scene_scale)
+    dm_cfg, model_cfg = make_cfg(experiment, num_rays=num_rays, deblur=deblur, cam_opt=cam_opt, **model_kw)
+    if rgb_frac is not None:
+        dm_cfg.rgb_frac = rgb_frac
+        dm_cfg.update_num_batch_rays()
+    dm = build_datamanager(scene, dm_cfg, device=device, seed=seed, pin=str(device) != "cpu")
+    model = LSENeRFModel(model_cfg, scene["aabb"], num_train_data=scene["num_emb"]).to(device)
+    return LSENeRFPipeline(dm, model)

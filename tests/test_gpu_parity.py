@@ -643,3 +643,29 @@ def test_device_resident_store_picks_the_host_samplers_pixels(dev):
         loss = gs.step()
     gs.flush(); torch.cuda.synchronize()
     assert torch.isfinite(loss).all() and not torch.equal(w0, opt.arenas["fields"].data)
+
+
+def test_formatted_scene_directory_trains(dev, tmp_path):
+    """SURVEY 8f-3 end to end: a formatted scene directory (written from the synthetic scene) -> lse_parser.build_pipeline -> two
+    training iterations on the kernels."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_parser import write_scene
+    from lsenerf_b200 import lse_parser as LP
+    from lsenerf_b200.lse_pipeline import FusedAdam, train_iteration
+    scene = syn.make_scene(small_spec())
+    root = str(tmp_path / "scene")
+    os.makedirs(root)
+    write_scene(root, scene)
+    p = LP.build_pipeline(root, "lsenerf", num_rays=512, rgb_frac=0.5, device=dev, seed=2, log2_hashmap_size=14, grid_resolution=32)
+    syn.init_model_state(p._model, scene)
+    p.train()
+    opt = FusedAdam(p.get_param_groups())
+    w0 = p._model.field.mlp_base_grid.hash_table.detach().clone()
+    for step in range(2):
+        losses, _ = train_iteration(p, opt, step)
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v) for v in losses.values()) and set(losses) == {"rgb_loss", "event_loss"}
+    assert not torch.equal(w0, p._model.field.mlp_base_grid.hash_table.detach())
+    assert p.datamanager.col_train_camera_optimizer.ctrl_tangents.grad is not None
