@@ -138,12 +138,9 @@ def mapper(sd, kind: str | None, prefix: str, x: Tensor) -> Tensor:
     raise NotImplementedError(kind)
 
 
-def get_outputs(sd, cfg: Cfg, grid, bundle: dict, training: bool, ev_out: bool, jitter=None):
-    """LSENeRFModel.get_outputs, lsenerf.py:329-377."""
-    ri, t0, t1, info = sampling(sd, cfg, grid, bundle["origins"], bundle["directions"], training, jitter)
-    out = render_samples(sd, cfg, bundle, ri, t0, t1, training)
-    out["_sampling"] = info
-    out["_samples"] = (ri, t0, t1)
+def epilogue(sd, cfg: Cfg, out: dict, training: bool, ev_out: bool) -> dict:
+    """The part of LSENeRFModel.get_outputs after exec_get_outputs, lsenerf.py:333-377 (pinned against the reference's own
+    method by tests/golden/ref_epilogue.npz)."""
     clamp_out = torch.clamp(out["rgb"], 1e-5)
     if cfg.use_mapping or cfg.map_mode == "rgb_evs":
         if cfg.map_mode == "rgb_evs":
@@ -166,6 +163,15 @@ def get_outputs(sd, cfg: Cfg, grid, bundle: dict, training: bool, ev_out: bool, 
             out["rgb"] = out["rgb"].reshape(-1, 4, 3).mean(dim=1)
     out["rgb"] = torch.clamp(out["rgb"], 0, 1) if not training else torch.clamp(out["rgb"], 1e-5)
     return out
+
+
+def get_outputs(sd, cfg: Cfg, grid, bundle: dict, training: bool, ev_out: bool, jitter=None):
+    """LSENeRFModel.get_outputs, lsenerf.py:329-377."""
+    ri, t0, t1, info = sampling(sd, cfg, grid, bundle["origins"], bundle["directions"], training, jitter)
+    out = render_samples(sd, cfg, bundle, ri, t0, t1, training)
+    out["_sampling"] = info
+    out["_samples"] = (ri, t0, t1)
+    return epilogue(sd, cfg, out, training, ev_out)
 
 
 # ---------------------------------------------------------------------------------------------- losses

@@ -1,0 +1,266 @@
+"""Generate tests/golden/ref_*.npz by RUNNING THE REFERENCE'S OWN CODE (build container only: needs /root/reference).
+
+    python tests/golden/make_reference_golden.py
+
+nerfstudio / nerfacc / tinycudann / jax / cv2 / matplotlib are not installable here, so their modules are replaced by empty
+stand-ins (any attribute is a dummy class) -- enough for the reference's modules to IMPORT.  Every number stored below comes out
+of an unmodified function or method of /root/reference/lse_nerf that does not execute third-party code:
+
+  ref_utils.npz        utils.to_gray / fix_datashape / fix_appearance_id / add_metadata, data_components.find_closest_idxs
+  ref_mappers.npz      intensity_mappers.{GT_Mapper, IdentityMapper, Powpow}, lsenerf.{ThreeToOne, ToGrayGT}
+  ref_epilogue.npz     LSENeRFModel.get_outputs (lsenerf.py:329-377) after compositing, for every map mode / flag combination used
+  ref_losses.npz       LSENeRFModel.get_loss_dict with log_loss and enerf_norm_loss (lsenerf.py:392-439)
+  ref_spline.npz       SplineCameraOptimizer: control points from cameras, get_rgb_cameras / get_evs_cameras / get_deblur_cameras
+  ref_sampler.npz      EvPixelSampler.collate_image_dataset_batch (the base class's sample_method is third-party: the indices are inputs)
+  ref_hashenc.npz      Ed_HashEncoding.__init__: scalings, hash_offset
+  ref_parser.npz       lse_parser.cv_to_working, Color / Events dataparsers on a formatted scene written by tests/test_parser.py
+
+Nothing is copied out of the reference but numbers.
+"""
+import importlib
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import tempfile
+import types
+import typing
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, ".."))            # tests/
+sys.path.insert(0, os.path.join(HERE, "..", ".."))      # repo root
+
+STUB_ROOTS = ("nerfstudio", "nerfacc", "tinycudann", "jax", "cv2", "matplotlib", "torchmetrics", "viser", "tyro", "rich", "jaxtyping",
+              "torchtyping", "mediapy", "lpips", "wandb", "plotly")
+
+
+class _Val:
+    value = 0
+
+    def __init__(self, *a, **k): pass
+    def __call__(self, *a, **k): return self
+
+    def __getattr__(self, n):
+        if n.startswith("__"):
+            raise AttributeError(n)
+        return _Val()
+
+
+class _Meta(type):
+    def __getattr__(cls, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Val()
+
+
+class _StubModule(types.ModuleType):
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        cls = _Meta(name, (), {"__init__": lambda self, *a, **k: None, "__class_getitem__": classmethod(lambda c, k: c)})
+        setattr(self, name, cls)
+        return cls
+
+
+class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, name, path, target=None):
+        if name.split(".")[0] in STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+
+    def create_module(self, spec):
+        return _StubModule(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+def load_reference():
+    sys.meta_path.insert(0, _Finder())
+    sys.path.insert(0, "/root/reference")
+    torch.Any = typing.Any                       # data_components.py annotates with torch.Any (torch 2.0 re-exported typing.Any)
+    mods = {n: importlib.import_module("lse_nerf." + n) for n in
+            ("utils", "data_components", "intensity_mappers", "ns_camera_optimizer", "lse_pixel_sampler", "lse_field", "lse_embeddings",
+             "lse_parser")}
+    # python >= 3.11 rejects unhashable dataclass instances as field defaults; the reference targets 3.8
+    mods["lse_embeddings"].LSEEmbeddingConfig.__hash__ = lambda self: 0
+    mods["lsenerf"] = importlib.import_module("lse_nerf.lsenerf")
+    return types.SimpleNamespace(**mods)
+
+
+def T(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def main():
+    R = load_reference()
+    g = torch.Generator().manual_seed(96)
+    NS = types.SimpleNamespace
+
+    # ---------------------------------------------------------------------------------------------- utils / data_components
+    img3 = torch.rand(4, 5, 3, generator=g); flat3 = torch.rand(7, 3, generator=g); one = torch.rand(7, 1, generator=g)
+    data = torch.arange(6).reshape(3, 2); ref12 = torch.zeros(12, 1)
+    app = torch.tensor([[0], [5], [9], [3]])
+    bundle = NS(camera_indices=torch.zeros(16, 1, dtype=torch.long), metadata={}, __len__=None)
+
+    class _B:          # the two things add_metadata reads from a RayBundle: camera_indices and len()
+        def __init__(self, n): self.camera_indices = torch.zeros(n, 1, dtype=torch.long); self.metadata = {}
+        def __len__(self): return self.camera_indices.shape[0]
+    b16 = _B(16)
+    batch = {"appearance_id": torch.tensor([1, 7, 0, 9]), "indices": torch.arange(12).reshape(4, 3)}
+    R.utils.add_metadata(b16, batch, cam_id=1, max_app_id=10)
+    ref_ts = torch.tensor([0.0, 10.0, 20.0, 35.0, 50.0]); q = torch.tensor([[-3.0], [4.9], [5.1], [20.0], [27.4], [27.6], [99.0]])
+    np.savez(os.path.join(HERE, "ref_utils.npz"), img3=T(img3), gray_img3=T(R.utils.to_gray(img3)), flat3=T(flat3),
+             gray_flat3=T(R.utils.to_gray(flat3)),
+             data=T(data), datashape12=T(R.utils.fix_datashape(data, ref12)),
+             app=T(app), app16=T(R.utils.fix_appearance_id(app, torch.zeros(16, 1), 10)), app4=T(R.utils.fix_appearance_id(app, torch.zeros(4, 1), 10)),
+             md_batch_app=T(batch["appearance_id"]), md_batch_idx=T(batch["indices"]), md_app=T(b16.metadata["appearance_id"]),
+             md_cam_type=T(b16.metadata["cam_type"]), md_coords=T(b16.metadata["coords"]),
+             closest_ref=T(ref_ts), closest_q=T(q), closest_idx=T(R.data_components.find_closest_idxs(ref_ts, q)))
+
+    # ---------------------------------------------------------------------------------------------- mappers
+    x3 = torch.rand(64, 3, generator=g).clamp(min=1e-5); x1 = torch.rand(64, 1, generator=g).clamp(min=1e-5)
+    pw = R.intensity_mappers.Powpow()
+    with torch.no_grad():
+        pw.pow_coeff.fill_(0.83)
+    t31 = R.lsenerf.ThreeToOne()
+    with torch.no_grad():
+        t31.weights.copy_(torch.tensor([[0.2, 0.5, -0.1]]))
+    np.savez(os.path.join(HERE, "ref_mappers.npz"), x3=T(x3), x1=T(x1), gt3=T(R.intensity_mappers.GT_Mapper()(x3)),
+             ident3=T(R.intensity_mappers.IdentityMapper()(x3)), pow_coeff=0.83, pow1=T(pw(x1)), pow3=T(pw(x3)),
+             three_w=T(t31.weights), three=T(t31(x3)), gray_gt=T(R.lsenerf.ToGrayGT()(x3)))
+
+    # ---------------------------------------------------------------------------------------------- get_outputs epilogue
+    Model = R.lsenerf.LSENeRFModel
+    lin = torch.rand(32, 3, generator=g) * 0.9
+    lin[0] = 0.0; lin[1] = torch.tensor([1e-7, 0.5, 2e-6])       # values below the 1e-5 clamp
+    cases, store = [], {"lin": T(lin)}
+
+    def run_case(name, map_mode, use_mapping, ev_one_dim, rgb_mapper, evs_mapper, training, deblur, ev_out):
+        cfg = NS(use_mapping=use_mapping, map_mode=map_mode, ev_one_dim=ev_one_dim, rgb_loss_type="deblur" if deblur else "linspace")
+        fake = NS(config=cfg, training=training, rgb_mapper=rgb_mapper, evs_mapper=evs_mapper,
+                  rgb_to_one=t31 if ev_one_dim == "learned" else R.lsenerf.ToGrayGT(),
+                  exec_get_outputs=lambda rb: {"rgb": lin.clone(), "accumulation": torch.ones(32, 1), "depth": torch.ones(32, 1)})
+        fake.correct_evs_dim = lambda inp: Model.correct_evs_dim(fake, inp)
+        out = Model.get_outputs(fake, None, ev_out=ev_out)
+        cases.append(name)
+        for k in ("rgb", "ev_out", "ev_linear", "linear"):
+            if k in out:
+                store[f"{name}__{k}"] = T(out[k])
+    ident, gtm = R.intensity_mappers.IdentityMapper(), R.intensity_mappers.GT_Mapper()
+    for training in (True, False):
+        for deblur in (False, True):
+            for ev_out in (False, True):
+                tag = f"t{int(training)}d{int(deblur)}e{int(ev_out)}"
+                run_case(f"comap_gt_{tag}", "co_map", True, "gt", ident, pw, training, deblur, ev_out)
+                run_case(f"comap_learned_{tag}", "co_map", True, "learned", gtm, pw, training, deblur, ev_out)
+                run_case(f"evsrgb_{tag}", "evs_rgb", True, "gt", gtm, None, training, deblur, ev_out)
+                run_case(f"rgbevs_{tag}", "rgb_evs", False, "learned", pw, None, training, deblur, ev_out)
+                run_case(f"plain_{tag}", "evs_rgb", False, False, None, None, training, deblur, ev_out)
+    store["cases"] = np.array(cases)
+    np.savez(os.path.join(HERE, "ref_epilogue.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- losses
+    mse = torch.nn.MSELoss()
+    col_img, col_rgb = torch.rand(40, 3, generator=g), torch.rand(40, 3, generator=g)
+    evs_img = (torch.randint(-3, 4, (24, 1), generator=g).float() * 0.2)
+    thr = torch.full((24, 1), 0.2)
+    prev1, next1 = torch.rand(24, 1, generator=g) + 1e-3, torch.rand(24, 1, generator=g) + 1e-3
+    prev3, next3 = torch.rand(24, 3, generator=g) + 1e-3, torch.rand(24, 3, generator=g) + 1e-3
+    store = dict(col_img=T(col_img), col_rgb=T(col_rgb), evs_img=T(evs_img), e_thresh=T(thr), prev1=T(prev1), next1=T(next1),
+                 prev3=T(prev3), next3=T(next3))
+    for loss_type in ("log_loss", "enerf_norm_loss"):
+        for use_mapping, (p, n) in ((True, (prev1, next1)), (False, (prev3, next3))):
+            cfg = NS(rgb_loss_type="linspace", use_mapping=use_mapping, evs_loss_weight=0.7)
+            fake = NS(config=cfg, device="cpu", rgb_loss=mse)
+            fake.mse_loss = lambda a, b, c=None: Model.mse_loss(fake, a, b, c)
+            fake.rgb_losses_dic = {"linspace": fake.mse_loss, "deblur": fake.mse_loss}
+            fake.event_loss = (lambda e, a, b, eb, _f=getattr(Model, loss_type): _f(fake, e, a, b, eb))
+            key = "ev_out" if use_mapping else "rgb"
+            outs = {"col_out": {"rgb": col_rgb}, "prev_out": {key: p}, "next_out": {key: n}}
+            ld = Model.get_loss_dict(fake, outs, {"col_batch": {"image": col_img}, "evs_batch": {"image": evs_img, "e_thresh": thr}})
+            store[f"{loss_type}_map{int(use_mapping)}"] = np.array([float(ld["rgb_loss"]), float(ld["event_loss"])])
+    np.savez(os.path.join(HERE, "ref_losses.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- spline camera optimizer
+    from helpers import small_spec
+    from lsenerf_b200 import synthetic as syn
+    scene = syn.make_scene(small_spec(), images=False)
+    cams = NS(camera_to_worlds=scene["col_c2w"].clone(), times=scene["col_times"].clone())
+    store = dict(c2w=T(cams.camera_to_worlds), times=T(cams.times), dM=T(scene["dM"]))
+    q_times = torch.tensor([[-500.0], [0.0], [1234.5], [11428.0], [40000.0], [79999.0], [80000.0], [90000.0]])
+    for factor in (1, 2):
+        for mode in ("off", "SO3xR3"):
+            cfg = NS(control_pnt_factor=factor, exp_t=3000.0, mode=mode, scheme="none", delay_cnt=0)
+            opt = R.ns_camera_optimizer.SplineCameraOptimizer(cfg, num_cameras=len(cams.times), device="cpu", cameras=cams, dM=scene["dM"].clone())
+            with torch.no_grad():
+                opt.scale.fill_(1.3)
+            tag = f"f{factor}_{mode}"
+            store[f"{tag}__ctrl_tangents"] = T(opt.ctrl_tangents); store[f"{tag}__ctrl_ts"] = T(opt.ctrl_ts)
+            store[f"{tag}__rgb"] = T(opt.get_rgb_cameras(q_times)); store[f"{tag}__evs"] = T(opt.get_evs_cameras(q_times))
+            store[f"{tag}__deblur"] = T(opt.get_deblur_cameras(q_times))
+    store["q_times"] = T(q_times); store["scale"] = 1.3; store["exp_t"] = 3000.0
+    np.savez(os.path.join(HERE, "ref_spline.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- pixel sampler
+    N, H, W = 5, 12, 16
+    imgs = torch.rand(N, H, W, 3, generator=g)
+    idx = torch.stack([torch.randint(0, N, (50,), generator=g), torch.randint(0, H, (50,), generator=g), torch.randint(0, W, (50,), generator=g)], dim=1)
+    sampler = R.lse_pixel_sampler.EvPixelSampler.__new__(R.lse_pixel_sampler.EvPixelSampler)
+    sampler.sample_method = lambda *a, **k: idx.clone()          # nerfstudio's sample_method is third-party: the indices are inputs
+    b = {"image": imgs, "image_idx": torch.arange(N) + 10, "appearance_id": torch.arange(N) * 2, "e_thresh": torch.rand(N, generator=g)}
+    out = sampler.collate_image_dataset_batch(b, 50)
+    np.savez(os.path.join(HERE, "ref_sampler.npz"), images=T(imgs), image_idx=T(b["image_idx"]), appearance_id=T(b["appearance_id"]),
+             e_thresh=T(b["e_thresh"]), picked=T(idx), **{"out_" + k: T(v) for k, v in out.items() if isinstance(v, torch.Tensor)})
+
+    # ---------------------------------------------------------------------------------------------- hash encoding constants
+    torch.manual_seed(0)
+    enc = R.lse_field.Ed_HashEncoding(num_levels=16, min_res=16, max_res=2048, log2_hashmap_size=12, features_per_level=2, implementation="torch")
+    enc2 = R.lse_field.Ed_HashEncoding(num_levels=16, min_res=16, max_res=1024, log2_hashmap_size=12, features_per_level=2, implementation="torch")
+    np.savez(os.path.join(HERE, "ref_hashenc.npz"), scalings_2048=T(enc.scalings), hash_offset=T(enc.hash_offset), scalings_1024=T(enc2.scalings),
+             table_shape=np.array(enc.hash_table.shape), table_absmax=float(enc.hash_table.abs().max()))
+
+    # ---------------------------------------------------------------------------------------------- dataparsers on a formatted scene
+    from test_parser import write_scene
+    scene = syn.make_scene(small_spec())
+    with tempfile.TemporaryDirectory() as root:
+        write_scene(root, scene)
+        rec = []
+
+        class _Cams:         # records what the reference hands to its camera class
+            def __init__(self, **kw): self.kw = kw; rec.append(self)
+            def set_hard_cam_type(self, t): self.cam_type = t
+        R.lse_parser.Cameras = _Cams
+        R.lse_parser.SceneBox = lambda aabb: NS(aabb=aabb)
+        R.lse_parser.CameraDataparserOutputs.__init__ = lambda self, **kw: self.__dict__.update(kw)
+        R.lse_parser.EventsparserOutputs.__init__ = lambda self, **kw: self.__dict__.update(kw)
+        ccfg = NS(data=os.path.join(root, "colcam_set"), scale_factor=1.0, scene_scale=1.0, quality="clear", image_type="gamma",
+                  dataset_cls=None, use_gray=False)
+        col = R.lse_parser.Color.__new__(R.lse_parser.Color)
+        col.config = ccfg
+        R.lse_parser.CameraParser.__init__(col, ccfg); col.split_dic = {"train": "train_ids", "test": "val_ids", "val": "val_ids"}; col.scale_factor = 1.0
+        col.__class__.__init__ = lambda self, config: None          # _generate_dataparser_outputs re-inits itself on the image dir
+        col._get_img_dir = lambda *a: ccfg.data
+        co = col._generate_dataparser_outputs("train")
+        ecfg = NS(data=os.path.join(root, "ecam_set"), scale_factor=1.0, scene_scale=1.0, e_thresh=None, event_type=None, dataset_cls=None)
+        from pathlib import Path
+        ev = R.lse_parser.Events.__new__(R.lse_parser.Events)
+        ev.config = ecfg
+        R.lse_parser.CameraParser.__init__(ev, ecfg); ev.data = Path(ecfg.data); ev.scale_factor = 1.0
+        eo = ev._generate_dataparser_outputs("train")
+        M = np.random.RandomState(3).randn(4, 4); M[3] = [0, 0, 0, 1]
+        np.savez(os.path.join(HERE, "ref_parser.npz"), cv_in=M, cv_out=R.lse_parser.cv_to_working(M),
+                 col_c2w=T(co.cameras.kw["camera_to_worlds"]), col_f=float(co.cameras.kw["fx"]), col_cx=float(co.cameras.kw["cx"]),
+                 col_cy=float(co.cameras.kw["cy"]), col_w=int(co.cameras.kw["width"]), col_h=int(co.cameras.kw["height"]),
+                 col_times=T(co.cameras.kw["times"]), col_app=np.array(co.appearance_ids), dM=T(co.dM), n_col_files=len(co.image_filenames),
+                 evs_c2w=T(eo.cameras.kw["camera_to_worlds"]), evs_times=T(eo.cameras.kw["times"]), evs_app=np.array(eo.appearance_ids),
+                 events=np.asarray(eo.events), e_thresh=float(eo.e_thresh), aabb=T(co.scene_box.aabb))
+    print("wrote", sorted(f for f in os.listdir(HERE) if f.startswith("ref_")))
+
+
+if __name__ == "__main__":
+    main()

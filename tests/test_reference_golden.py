@@ -1,0 +1,230 @@
+"""Pins the oracle (oracle/*.py) and the host mirrors (lsenerf_b200/*.py) to numbers produced by the REFERENCE'S OWN CODE.
+
+tests/golden/ref_*.npz were written by tests/golden/make_reference_golden.py, which imports /root/reference/lse_nerf (third-party
+packages stubbed) and runs its unmodified functions.  Nothing here reads /root/reference.  Tolerances: integers / indices
+bit-exact; fp32 elementwise maps 1e-6 relative (same torch ops, possibly another association order); the scipy-built spline
+control points 1e-5.
+
+The GPU half (CUDA kernels against the same files) is in tests/test_gpu_parity.py::test_*_reference_golden.
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from helpers import small_spec  # noqa: E402
+
+from lsenerf_b200 import data_components, lse_parser, synthetic as syn, utils  # noqa: E402
+from lsenerf_b200.lse_pixel_sampler import EvPixelSampler  # noqa: E402
+from lsenerf_b200.ns_camera_optimizer import SplineCameraOptimizer  # noqa: E402
+from oracle import data as OD, field as OF, model as OM, poses as OP  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(a, b, rtol=1e-6, atol=1e-7):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+# ------------------------------------------------------------------------------------------------------ utils / data_components
+def test_utils_match_reference():
+    z = gold("utils")
+    for to_gray in (utils.to_gray, OM.to_gray):
+        close(to_gray(t(z["img3"])), z["gray_img3"])
+        close(to_gray(t(z["flat3"])), z["gray_flat3"], rtol=0, atol=0)          # [n,3] comes back unchanged (utils.py:101)
+    assert torch.equal(utils.fix_datashape(t(z["data"]), torch.zeros(12, 1)), t(z["datashape12"]))
+    app = t(z["app"])
+    assert torch.equal(utils.fix_appearance_id(app, torch.zeros(16, 1), 10), t(z["app16"]))
+    assert torch.equal(utils.fix_appearance_id(app, torch.zeros(4, 1), 10), t(z["app4"]))
+    assert torch.equal(OD.fix_appearance_id(app, 16, 10), t(z["app16"]))
+    assert torch.equal(OD.fix_appearance_id(app, 4, 10), t(z["app4"]))
+
+
+def test_add_metadata_matches_reference():
+    z = gold("utils")
+
+    class B:
+        def __init__(self, n): self.camera_indices = torch.zeros(n, 1, dtype=torch.long); self.metadata = {}
+        def __len__(self): return self.camera_indices.shape[0]
+    b = B(16)
+    utils.add_metadata(b, {"appearance_id": t(z["md_batch_app"]), "indices": t(z["md_batch_idx"])}, cam_id=1, max_app_id=10)
+    assert torch.equal(b.metadata["appearance_id"], t(z["md_app"]))
+    assert torch.equal(b.metadata["cam_type"], t(z["md_cam_type"]))
+    assert torch.equal(b.metadata["coords"], t(z["md_coords"]))
+    lean = utils.add_metadata(B(16), {"appearance_id": t(z["md_batch_app"])}, cam_id=1, max_app_id=10, lean=True)
+    assert torch.equal(lean.metadata["appearance_id"], t(z["md_app"])) and set(lean.metadata) == {"appearance_id"}
+
+
+def test_find_closest_idxs_matches_reference():
+    z = gold("utils")
+    ref, q = t(z["closest_ref"]), t(z["closest_q"])
+    assert torch.equal(data_components.find_closest_idxs(ref, q), t(z["closest_idx"]))
+    assert torch.equal(OD.find_closest_idxs(ref, q.reshape(-1)).reshape(-1, 1), t(z["closest_idx"]))
+
+
+# ------------------------------------------------------------------------------------------------------ mappers
+def test_mappers_match_reference():
+    z = gold("mappers")
+    x3, x1 = t(z["x3"]), t(z["x1"])
+    sd = {"rgb_mapper.pow_coeff": torch.tensor(float(z["pow_coeff"])), "rgb_to_one.weights": t(z["three_w"])}
+    close(OM.mapper(sd, "gt", "rgb_mapper", x3), z["gt3"])
+    close(OM.mapper(sd, "identity", "rgb_mapper", x3), z["ident3"], rtol=0, atol=0)
+    close(OM.mapper(sd, "powpow", "rgb_mapper", x1), z["pow1"])
+    close(OM.mapper(sd, "powpow", "rgb_mapper", x3), z["pow3"])
+    close(OM.rgb_to_one(sd, OM.Cfg(ev_one_dim="learned"), x3), z["three"])
+    close(OM.rgb_to_one(sd, OM.Cfg(ev_one_dim="gt"), x3), z["gray_gt"])
+    close(OM.gray_gt(x3), z["gray_gt"])
+    # the nn.Module mirrors launch the CUDA epilogue kernel: they are checked in tests/test_gpu_parity.py
+
+
+# ------------------------------------------------------------------------------------------------------ get_outputs epilogue
+EPILOGUE_MODES = {   # name -> (map_mode, use_mapping, ev_one_dim, rgb mapper, evs mapper); mirrors make_reference_golden.run_case calls
+    "comap_gt": ("co_map", True, "gt", "identity", "powpow"),
+    "comap_learned": ("co_map", True, "learned", "gt", "powpow"),
+    "evsrgb": ("evs_rgb", True, "gt", "gt", None),
+    "rgbevs": ("rgb_evs", False, "learned", "powpow", None),
+    "plain": ("evs_rgb", False, False, None, None),
+}
+
+
+def epilogue_cases():
+    for mode in EPILOGUE_MODES:
+        for training in (True, False):
+            for deblur in (False, True):
+                for ev_out in (False, True):
+                    yield mode, training, deblur, ev_out
+
+
+def test_golden_holds_every_epilogue_case():
+    z = gold("epilogue")
+    want = {f"{m}_t{int(tr)}d{int(d)}e{int(e)}" for m, tr, d, e in epilogue_cases()}
+    assert set(z["cases"].tolist()) == want
+
+
+@pytest.mark.parametrize("mode", list(EPILOGUE_MODES))
+def test_oracle_epilogue_matches_reference(mode):
+    z = gold("epilogue")
+    mm, use_mapping, one_dim, rgb_m, evs_m = EPILOGUE_MODES[mode]
+    pw, w = torch.tensor(0.83), torch.tensor([[0.2, 0.5, -0.1]])
+    sd = {"rgb_mapper.pow_coeff": pw, "evs_mapper.pow_coeff": pw, "rgb_to_one.weights": w}
+    for m, training, deblur, ev_out in epilogue_cases():
+        if m != mode:
+            continue
+        name = f"{mode}_t{int(training)}d{int(deblur)}e{int(ev_out)}"
+        cfg = OM.Cfg(use_mapping=use_mapping, map_mode=mm, ev_one_dim=one_dim, mapping_method=rgb_m, evs_mapping_method=evs_m,
+                     rgb_loss_type="deblur" if deblur else "linspace")
+        out = OM.epilogue(sd, cfg, {"rgb": t(z["lin"]).clone()}, training, ev_out)
+        keys = {k for k in ("rgb", "ev_out", "ev_linear", "linear") if f"{name}__{k}" in z.files}
+        assert keys == {k for k in ("rgb", "ev_out", "ev_linear", "linear") if k in out}, name
+        for k in keys:
+            close(out[k], z[f"{name}__{k}"], rtol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------------ losses
+@pytest.mark.parametrize("loss_type", ["log_loss", "enerf_norm_loss"])
+@pytest.mark.parametrize("use_mapping", [True, False])
+def test_oracle_losses_match_reference(loss_type, use_mapping):
+    z = gold("losses")
+    p, n = (t(z["prev1"]), t(z["next1"])) if use_mapping else (t(z["prev3"]), t(z["next3"]))
+    key = "ev_out" if use_mapping else "rgb"
+    cfg = OM.Cfg(use_mapping=use_mapping, event_loss_type=loss_type, evs_loss_weight=0.7)
+    ld = OM.loss_dict(cfg, {"rgb": t(z["col_rgb"])}, {key: p}, {key: n}, t(z["col_img"]), t(z["evs_img"]), t(z["e_thresh"]))
+    want = z[f"{loss_type}_map{int(use_mapping)}"]
+    close(ld["rgb_loss"], want[0], rtol=1e-6)
+    close(ld["event_loss"], want[1], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------------ spline camera optimiser
+SPLINE_TAGS = [f"f{f}_{m}" for f in (1, 2) for m in ("off", "SO3xR3")]
+
+
+@pytest.mark.parametrize("tag", SPLINE_TAGS)
+def test_control_points_match_reference(tag):
+    z = gold("spline")
+    cams = types.SimpleNamespace(camera_to_worlds=t(z["c2w"]), times=t(z["times"]))
+    tang, ts = SplineCameraOptimizer.build_control_pnts(cams, int(tag[1]))
+    close(ts, z[f"{tag}__ctrl_ts"], rtol=0, atol=0)
+    close(tang, z[f"{tag}__ctrl_tangents"], rtol=1e-5, atol=1e-6)
+    for i in range(tang.shape[0]):        # the oracle's log map on the interpolated matrices gives the same tangents
+        M = OP.quatmap_to_c2w(OP.tangents_to_quatmap(tang[i:i + 1]))[0]
+        close(OP.matrix_to_tangent(M), z[f"{tag}__ctrl_tangents"][i], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", SPLINE_TAGS)
+def test_oracle_spline_queries_match_reference(tag):
+    z = gold("spline")
+    ctrl, cts, q = t(z[f"{tag}__ctrl_tangents"]), t(z[f"{tag}__ctrl_ts"]), t(z["q_times"])
+    scale = None if tag.endswith("off") else torch.tensor([float(z["scale"])])
+    close(OP.spline_rgb_c2w(ctrl, cts, q), z[f"{tag}__rgb"], rtol=1e-5, atol=2e-6)
+    close(OP.spline_evs_c2w(ctrl, cts, q, t(z["dM"]), scale), z[f"{tag}__evs"], rtol=1e-5, atol=2e-6)
+    close(OP.spline_deblur_c2w(ctrl, cts, q, float(z["exp_t"])), z[f"{tag}__deblur"], rtol=1e-5, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------------ pixel sampler
+def test_collate_matches_reference():
+    z = gold("sampler")
+    picked = t(z["picked"])
+    batch = {"image": t(z["images"]), "image_idx": t(z["image_idx"]), "appearance_id": t(z["appearance_id"]), "e_thresh": t(z["e_thresh"])}
+    s = EvPixelSampler(50)
+    s.sample_method = lambda *a, **k: picked.clone()
+    out = s.collate_image_dataset_batch(batch, 50)
+    ora = OD.collate(batch["image"], batch["image_idx"], batch["appearance_id"], batch["e_thresh"], picked)
+    for got in (out, ora):
+        for k in ("image", "e_thresh", "appearance_id", "indices"):
+            assert torch.equal(got[k], t(z[f"out_{k}"])), k
+
+
+# ------------------------------------------------------------------------------------------------------ hash-grid constants
+def test_hash_scalings_match_reference():
+    z = gold("hashenc")
+    assert torch.equal(OF.hash_scalings(16, 16, 2048), t(z["scalings_2048"]))
+    assert torch.equal(OF.hash_scalings(16, 16, 1024), t(z["scalings_1024"]))
+    assert z["scalings_2048"][-1] == 2047.0          # the fp32 pow lands below 2048
+    from lsenerf_b200.lse_field import Ed_HashEncoding
+    enc = Ed_HashEncoding(num_levels=16, min_res=16, max_res=2048, log2_hashmap_size=12, features_per_level=2)
+    assert torch.equal(enc.scalings.cpu(), t(z["scalings_2048"]))
+    assert torch.equal(enc.hash_offset.cpu(), t(z["hash_offset"]))
+    assert list(enc.hash_table.shape) == z["table_shape"].tolist()
+    for amax in (float(enc.hash_table.detach().abs().max()), float(z["table_absmax"])):         # uniform(-1e-3, 1e-3) init
+        assert 0.99e-3 < amax <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------ dataparsers
+def test_parsers_match_reference():
+    from test_parser import write_scene
+    z = gold("parser")
+    close(lse_parser.cv_to_working(z["cv_in"]), z["cv_out"], rtol=0, atol=0)
+    scene = syn.make_scene(small_spec())
+    with tempfile.TemporaryDirectory() as root:
+        write_scene(root, scene)
+        co = lse_parser.ColorParser(os.path.join(root, "colcam_set")).parse("train")
+        eo = lse_parser.EventParser(os.path.join(root, "ecam_set")).parse()
+        aabb = lse_parser.ColorParser(os.path.join(root, "colcam_set")).scene_aabb()
+    close(co.cameras.camera_to_worlds, z["col_c2w"], rtol=1e-6, atol=1e-6)
+    close(co.cameras.fx[0, 0], z["col_f"]); close(co.cameras.cx[0, 0], z["col_cx"]); close(co.cameras.cy[0, 0], z["col_cy"])
+    assert (co.cameras.width, co.cameras.height) == (int(z["col_w"]), int(z["col_h"]))
+    close(co.times.reshape(-1), z["col_times"], rtol=0, atol=0)
+    assert co.appearance_ids.tolist() == z["col_app"].tolist()
+    assert len(co.image_filenames) == int(z["n_col_files"])
+    close(co.dM, z["dM"], rtol=1e-5, atol=1e-6)
+    close(eo.cameras.camera_to_worlds, z["evs_c2w"], rtol=1e-6, atol=1e-6)
+    close(eo.cameras.times.reshape(-1), z["evs_times"], rtol=0, atol=0)
+    assert eo.appearance_ids.tolist() == z["evs_app"].tolist()
+    assert eo.e_thresh == float(z["e_thresh"])
+    # the reference hands int8 event counts to EventFrameDataset, which multiplies by e_thresh on access (lse_dataset.py:84-87)
+    close(eo.events, z["events"].astype(np.float32) * np.float32(z["e_thresh"]), rtol=0, atol=0)
+    close(aabb.reshape(2, 3), z["aabb"], rtol=0, atol=0)
