@@ -15,6 +15,18 @@ of an unmodified function or method of /root/reference/lse_nerf that does not ex
   ref_hashenc.npz      Ed_HashEncoding.__init__: scalings, hash_offset
   ref_parser.npz       lse_parser.cv_to_working, Color / Events dataparsers on a formatted scene written by tests/test_parser.py
 
+
+"Glue" goldens -- the reference's own methods run with small FUNCTIONAL stand-ins for the third-party calls they make (the stand-ins
+are this repo's restatements in oracle/, i.e. exactly the part that stays UNPINNED; what these files pin is everything the
+reference itself does around them: argument order, shapes, index conventions, masks, tiling, camera selection):
+
+  ref_raygen.npz       EdCameras.generate_rays / _generate_rays_from_coords / get_c2w, ConsecRayGenerator, DeblurRayGenerator
+                       (stand-in: camera_utils.normalize_with_norm, one line; RayBundle as a plain record; image_coords = (y, x))
+  ref_field.npz        LSEField.get_density / get_outputs with the real EvsFrameEmbedding / GlobalEmbedding classes
+                       (stand-ins: hash grid, MLP, SH, contraction, trunc_exp from oracle/field.py; Embedding = nn.Embedding wrapper)
+  ref_sampling.npz     LSEOccGridEstimator.sampling (stand-ins: traverse_grids / render_visibility_from_density from oracle/nerfacc.py; the density
+                       behind sigma_fn uses the weights stored in ref_field.npz)
+
 Nothing is copied out of the reference but numbers.
 """
 import importlib
@@ -79,7 +91,26 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         pass
 
 
+class _Embedding(torch.nn.Module):
+    """stand-in for nerfstudio 0.3.2 field_components.embedding.Embedding: nn.Embedding(in_dim, out_dim), forward = lookup,
+    mean(dim) over the weight."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.embedding = torch.nn.Embedding(in_dim, out_dim)
+
+    def mean(self, dim=0):
+        return self.embedding.weight.mean(dim)
+
+    def forward(self, in_tensor):
+        return self.embedding(in_tensor)
+
+
 def load_reference():
+    emb_mod = _StubModule("nerfstudio.field_components.embedding")
+    emb_mod.Embedding = _Embedding
+    sys.modules["nerfstudio.field_components.embedding"] = emb_mod
     sys.meta_path.insert(0, _Finder())
     sys.path.insert(0, "/root/reference")
     torch.Any = typing.Any                       # data_components.py annotates with torch.Any (torch 2.0 re-exported typing.Any)
@@ -89,6 +120,8 @@ def load_reference():
     # python >= 3.11 rejects unhashable dataclass instances as field defaults; the reference targets 3.8
     mods["lse_embeddings"].LSEEmbeddingConfig.__hash__ = lambda self: 0
     mods["lsenerf"] = importlib.import_module("lse_nerf.lsenerf")
+    for n in ("lse_cameras", "lse_ray_generator", "lse_grid_estimator"):
+        mods[n] = importlib.import_module("lse_nerf." + n)
     return types.SimpleNamespace(**mods)
 
 
@@ -259,7 +292,195 @@ def main():
                  col_times=T(co.cameras.kw["times"]), col_app=np.array(co.appearance_ids), dM=T(co.dM), n_col_files=len(co.image_filenames),
                  evs_c2w=T(eo.cameras.kw["camera_to_worlds"]), evs_times=T(eo.cameras.kw["times"]), evs_app=np.array(eo.appearance_ids),
                  events=np.asarray(eo.events), e_thresh=float(eo.e_thresh), aabb=T(co.scene_box.aabb))
+
+    glue_goldens(R, g)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.startswith("ref_")))
+
+
+def glue_goldens(R, g):
+    from types import MethodType
+    from helpers import small_spec
+    from lsenerf_b200 import synthetic as syn
+    from oracle import field as OF, nerfacc as NA
+    NS = types.SimpleNamespace
+
+    # ---------------------------------------------------------------------------------------------- ray generation
+    class Bundle:                                   # nerfstudio RayBundle as a plain record
+        def __init__(self, **kw): self.__dict__.update(kw)
+    LC = R.lse_cameras
+    LC.RayBundle = Bundle
+    eps = float(np.finfo(float).eps * 4.0)          # nerfstudio camera_utils._EPS
+
+    def normalize_with_norm(x, dim):
+        n = torch.maximum(torch.linalg.vector_norm(x, dim=dim, keepdims=True), torch.tensor([eps]).to(x))
+        return x / n, n
+    LC.camera_utils.normalize_with_norm = normalize_with_norm
+    Ed = LC.EdCameras
+
+    class Cams:                                     # the state nerfstudio's Cameras.__init__ would leave behind + EdCameras' own methods
+        is_jagged = False
+        device = "cpu"
+        distortion_params = None
+        metadata = None
+        get_c2w = Ed.__dict__["get_c2w"]
+        generate_rays = Ed.__dict__["generate_rays"]
+        _generate_rays_from_coords = Ed.__dict__["_generate_rays_from_coords"]
+        set_interpolator = Ed.__dict__["set_interpolator"]
+        set_hard_cam_type = Ed.__dict__["set_hard_cam_type"]
+
+        def __init__(self, c2w, intr, times):
+            n = c2w.shape[0]
+            self.shape = (n,)
+            self.camera_to_worlds = c2w
+            self.fx, self.fy, self.cx, self.cy = (torch.full((n, 1), float(v)) for v in intr)
+            self.times = times.reshape(-1, 1)
+            self.camera_type = torch.zeros(n, 1, dtype=torch.long)        # == CameraType.PERSPECTIVE.value of the stand-in enum
+            self.interpolator = None
+            self.hard_cam_type = LC.HardCamType.RGB
+            self.get_c2w_fn = self.get_c2w
+
+    scene = syn.make_scene(small_spec(), images=False)
+    H, W = 48, 64
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    image_coords = torch.stack([ys, xs], dim=-1)                          # get_image_coords with EdCameras' zero pixel offset
+    col_intr = tuple(float(v) for v in scene["col_intr"]); evs_intr = tuple(float(v) for v in scene["evs_intr"])
+    col = Cams(scene["col_c2w"].clone(), col_intr, scene["col_times"].clone())
+    evs = Cams(scene["evs_c2w0"].clone(), evs_intr, scene["evs_times"].clone())
+    cfg = NS(control_pnt_factor=1, exp_t=3000.0, mode="SO3xR3", scheme="none", delay_cnt=0)
+    spl = R.ns_camera_optimizer.SplineCameraOptimizer(cfg, num_cameras=len(col.times), device="cpu",
+                                                      cameras=NS(camera_to_worlds=col.camera_to_worlds, times=col.times), dM=scene["dM"].clone())
+    with torch.no_grad():
+        spl.scale.fill_(1.3)
+        spl.ctrl_tangents.add_(0.01 * torch.randn(spl.ctrl_tangents.shape, generator=g))
+    n = 40
+    col_idx = torch.stack([torch.randint(0, len(col.times), (n,), generator=g), torch.randint(0, H, (n,), generator=g),
+                           torch.randint(0, W, (n,), generator=g)], dim=1)
+    evs_idx = torch.stack([torch.randint(0, len(evs.times) - 1, (n,), generator=g), torch.randint(0, H, (n,), generator=g),
+                           torch.randint(0, W, (n,), generator=g)], dim=1)
+    col_idx[0, 1:] = 0; col_idx[1, 1] = H - 1; col_idx[1, 2] = W - 1
+    store = dict(col_c2w=T(col.camera_to_worlds), col_times=T(col.times), col_intr=np.array(col_intr), evs_c2w=T(evs.camera_to_worlds),
+                 evs_times=T(evs.times), evs_intr=np.array(evs_intr), dM=T(scene["dM"]), ctrl_tangents=T(spl.ctrl_tangents),
+                 ctrl_ts=T(spl.ctrl_ts), scale=1.3, exp_t=3000.0, col_idx=T(col_idx), evs_idx=T(evs_idx), hw=np.array([H, W]))
+
+    def put(tag, rb):
+        for k in ("origins", "directions", "pixel_area", "camera_indices", "times"):
+            store[f"{tag}__{k}"] = T(getattr(rb, k))
+        store[f"{tag}__directions_norm"] = T(rb.metadata["directions_norm"])
+
+    def linspace(cams, idx):                        # nerfstudio RayGenerator.forward with the dummy pose optimizer the reference installs
+        return cams.generate_rays(camera_indices=idx[:, 0].unsqueeze(-1), coords=image_coords[idx[:, 1], idx[:, 2]], camera_opt_to_camera=None)
+    with torch.no_grad():
+        put("rgb_stored", linspace(col, col_idx))
+        col.set_interpolator(spl)
+        put("rgb_spline", linspace(col, col_idx))
+        DG = R.lse_ray_generator.DeblurRayGenerator
+
+        class Deblur:
+            generate_ray_bundle = DG.__dict__["generate_ray_bundle"]; forward = DG.__dict__["forward"]
+            def __init__(self, cams): self.cameras = cams; self.image_coords = image_coords
+        put("rgb_deblur", Deblur(col).forward(col_idx))
+        assert col.get_c2w_fn == col.get_c2w                      # the generator restores the pose function
+        CG = R.lse_ray_generator.ConsecRayGenerator
+        consec = NS(cameras=evs, image_coords=image_coords)
+        p, nx = CG.__dict__["forward"](consec, evs_idx)
+        put("evs_stored_prev", p); put("evs_stored_next", nx)
+        evs.set_interpolator(spl); evs.set_hard_cam_type(LC.HardCamType.EVS)
+        p, nx = CG.__dict__["forward"](consec, evs_idx)
+        put("evs_spline_prev", p); put("evs_spline_next", nx)
+    np.savez(os.path.join(HERE, "ref_raygen.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- field composition + embeddings
+    LF, LE = R.lse_field, R.lse_embeddings
+    log2_T, S = 10, 96
+    sc = OF.hash_scalings(16, 16, 2048)
+    sd = {OF.K_TABLE: (torch.rand(16 * 2**log2_T, 2, generator=g) * 2 - 1) * 0.5}
+    for prefix, dims in ((OF.K_BASE, (32, 64, 16)), (OF.K_HEAD, (16 + 15 + 32, 64, 64, 3))):
+        for i in range(len(dims) - 1):
+            sd[f"{prefix}.layers.{i}.weight"] = torch.randn(dims[i + 1], dims[i], generator=g) * (2.0 / dims[i]) ** 0.5
+            sd[f"{prefix}.layers.{i}.bias"] = torch.randn(dims[i + 1], generator=g) * 0.1
+    # spread the raw density so that both the alpha threshold and the transmittance cut of the sampling golden below bite
+    sd[f"{OF.K_BASE}.layers.1.weight"][0] *= 12.0; sd[f"{OF.K_BASE}.layers.1.bias"][0] = 2.0
+    pos = (torch.rand(S, 3, generator=g) * 2 - 1) * 1.5            # inside and outside the unit box (contraction branch)
+    pos[0] = torch.tensor([40.0, -3.0, 0.2]); pos[1] = 0.0; pos[2] = torch.tensor([1.0, 1.0, 1.0])
+    dirs = torch.nn.functional.normalize(torch.randn(S, 3, generator=g), dim=-1)
+    cam_idx = torch.randint(0, 5, (S, 1), generator=g)
+    app_id = torch.randint(0, 7, (S, 1), generator=g)
+    LF.trunc_exp = OF.trunc_exp
+    LF.shift_directions_for_tcnn = lambda d: (d + 1.0) / 2.0       # nerfstudio 0.3.2 field_components.spatial_distortions / fields.base_field
+    LF.SceneBox.get_normalized_positions = staticmethod(lambda p, aabb: (p - aabb[0]) / (aabb[1] - aabb[0]))
+
+    class Frustums:
+        def __init__(self): self.directions = dirs; self.shape = (S,)
+        def get_positions(self): return pos
+    class Samples:
+        def __init__(self): self.frustums = Frustums(); self.camera_indices = cam_idx; self.metadata = {"appearance_id": app_id.clone()}
+        def __len__(self): return S
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    store = {k.replace(".", "/"): T(v) for k, v in sd.items()}
+    store.update(pos=T(pos), dirs=T(dirs), cam_idx=T(cam_idx), app_id=T(app_id), log2_T=log2_T, aabb=T(aabb))
+    with torch.no_grad():
+        for tag, distortion in (("contract", OF.contract_inf), ("aabb", None)):
+            fake = NS(spatial_distortion=distortion, aabb=aabb, geo_feat_dim=15, average_init_density=1.0,
+                      mlp_base=lambda x: OF.mlp(OF.hash_encode(x, sd[OF.K_TABLE], sc, 2**log2_T), sd, OF.K_BASE, 2, None))
+            dens, geo = LF.LSEField.get_density(fake, Samples())
+            store[f"density_{tag}"] = T(dens); store[f"geo_{tag}"] = T(geo); store[f"locations_{tag}"] = T(fake._sample_locations)
+        geo = torch.from_numpy(store["geo_contract"])
+        for emb_type in ("global_emb", "evs_emb"):
+            for eval_mode in ("zero", "mean"):
+                ecfg = NS(emb_dim=32, eval_mode=eval_mode)
+                torch.manual_seed(7)
+                emb = LE.EMBEDDING_TYPE_DICT[emb_type](ecfg, 7, 32)
+                store[f"emb_weight_{emb_type}"] = T(emb.embedding.weight)
+                for training in (True, False):
+                    fake = NS(direction_encoding=OF.sh_deg4, embedding_appearance=emb, training=training, use_transient_embedding=False,
+                              use_semantics=False, use_pred_normals=False, geo_feat_dim=15, appearance_embedding_dim=emb.get_emb_dim(),
+                              mlp_head=lambda h: OF.mlp(h, sd, OF.K_HEAD, 3, "sigmoid"))
+                    out = LF.LSEField.get_outputs(fake, Samples(), density_embedding=geo)
+                    (rgb,) = out.values()
+                    store[f"rgb_{emb_type}_{eval_mode}_t{int(training)}"] = T(rgb)
+                    e = emb(Samples()) if training else emb.get_test_emb(Samples())
+                    store[f"emb_{emb_type}_{eval_mode}_t{int(training)}"] = T(e)
+    np.savez_compressed(os.path.join(HERE, "ref_field.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- sampling glue
+    LG = R.lse_grid_estimator
+    grid = NA.OccGrid(torch.tensor([-1.0, -1, -1, 1, 1, 1]), resolution=32, levels=2)
+    c = (grid.grid_coords.float() + 0.5) / 32 * 2 - 1
+    ball = (c.norm(dim=-1) < 0.6).view(32, 32, 32)
+    grid.binaries[0] = ball | (torch.rand(32, 32, 32, generator=g) < 0.02)
+    grid.binaries[1] = torch.rand(32, 32, 32, generator=g) < 0.05
+    grid.occs = grid.binaries.float().reshape(-1) * 0.03 + 0.001          # mean ~ 0.004: between the two alpha thresholds used below
+    Rn = 64
+    o = torch.nn.functional.normalize(torch.randn(Rn, 3, generator=g), dim=-1) * 1.8
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(Rn, 3, generator=g), dim=-1)
+    d[0] = torch.tensor([0.0, 0.0, 1.0]); o[0] = torch.tensor([0.1, 0.1, -1.7])          # axis aligned
+    d[1] = torch.nn.functional.normalize(o[1], dim=-1)                                       # pointing away: misses the ball
+
+    def traverse(rays_o, rays_d, binaries, aabbs, near_planes, far_planes, step_size, cone_angle):
+        ri, t0, t1, packed = NA.traverse_grids(rays_o, rays_d, binaries, aabbs, near_planes, far_planes, step_size, cone_angle)
+        left = torch.zeros(2 * ri.numel(), dtype=torch.bool); left[0::2] = True
+        return NS(vals=torch.stack([t0, t1], dim=1).reshape(-1), is_left=left, is_right=~left), NS(ray_indices=ri, packed_info=packed)
+    LG.traverse_grids = traverse
+    LG.render_visibility_from_density = lambda t_starts, t_ends, sigmas, packed_info, early_stop_eps, alpha_thre: \
+        NA.render_visibility_from_density(t_starts, t_ends, sigmas, packed_info, early_stop_eps, alpha_thre)
+
+    def sigma_fn(t_starts, t_ends, ray_indices):     # nerfstudio VolumetricSampler.get_sigma_fn around field.density_fn
+        positions = o[ray_indices] + d[ray_indices] * (t_starts + t_ends)[:, None] / 2.0
+        return OF.density(sd, positions, sc, log2_T)[0].squeeze(-1)
+    fake = NS(binaries=grid.binaries, aabbs=grid.aabbs, occs=grid.occs)
+    store = dict(origins=T(o), directions=T(d), binaries=T(grid.binaries), occs=T(grid.occs), aabbs=T(grid.aabbs),
+                 near=0.05, far=1e3, step=0.01, cone=0.004)
+    with torch.no_grad():
+        for tag, kw in (("eval", dict(sigma_fn=None, stratified=False, alpha_thre=0.01)),
+                        ("train", dict(sigma_fn=sigma_fn, stratified=True, alpha_thre=0.002, early_stop_eps=1e-4)),
+                        ("train_thre_above_mean", dict(sigma_fn=sigma_fn, stratified=True, alpha_thre=0.5, early_stop_eps=1e-4)),
+                        ("train_no_cull", dict(sigma_fn=sigma_fn, stratified=True, alpha_thre=0.0, early_stop_eps=0.0))):
+            torch.manual_seed(11)
+            store[f"{tag}__jitter"] = T(torch.rand(Rn))
+            torch.manual_seed(11)
+            ri, t0, t1 = LG.LSEOccGridEstimator.sampling(fake, o, d, near_plane=0.05, far_plane=1e3, render_step_size=0.01, cone_angle=0.004, **kw)
+            store[f"{tag}__ray_indices"] = T(ri); store[f"{tag}__t_starts"] = T(t0); store[f"{tag}__t_ends"] = T(t1)
+    np.savez_compressed(os.path.join(HERE, "ref_sampling.npz"), **store)
 
 
 if __name__ == "__main__":
