@@ -24,6 +24,10 @@ reference itself does around them: argument order, shapes, index conventions, ma
                        (stand-in: camera_utils.normalize_with_norm, one line; RayBundle as a plain record; image_coords = (y, x))
   ref_field.npz        LSEField.get_density / get_outputs with the real EvsFrameEmbedding / GlobalEmbedding classes
                        (stand-ins: hash grid, MLP, SH, contraction, trunc_exp from oracle/field.py; Embedding = nn.Embedding wrapper)
+  ref_next_train.npz   MultiCamManagerConfig.update_num_batch_rays and MultiCamManager.next_train (deblur colour bundle + event prev/next
+                       bundles: pixel collate -> ray generators -> camera optimizers incl. the delayed schedule -> add_metadata ->
+                       CameraIdxFixer; stand-ins: exp_map_SO3xR3 = the reference's own interpolation_utils.hom_exp_map_SO3xR3 rows 0-2,
+                       PixelSampler.sample = collate(batch, num_rays_per_batch), forced pixel picks)
   ref_sampling.npz     LSEOccGridEstimator.sampling (stand-ins: traverse_grids / render_visibility_from_density from oracle/nerfacc.py; the density
                        behind sigma_fn uses the weights stored in ref_field.npz)
 
@@ -111,6 +115,9 @@ def load_reference():
     emb_mod = _StubModule("nerfstudio.field_components.embedding")
     emb_mod.Embedding = _Embedding
     sys.modules["nerfstudio.field_components.embedding"] = emb_mod
+    dm_mod = _StubModule("nerfstudio.data.datamanagers.base_datamanager")
+    dm_mod.TDataset = typing.TypeVar("TDataset")           # lse_datamanager.py:147 subscripts Generic with it
+    sys.modules["nerfstudio.data.datamanagers.base_datamanager"] = dm_mod
     sys.meta_path.insert(0, _Finder())
     sys.path.insert(0, "/root/reference")
     torch.Any = typing.Any                       # data_components.py annotates with torch.Any (torch 2.0 re-exported typing.Any)
@@ -307,6 +314,7 @@ def glue_goldens(R, g):
     # ---------------------------------------------------------------------------------------------- ray generation
     class Bundle:                                   # nerfstudio RayBundle as a plain record
         def __init__(self, **kw): self.__dict__.update(kw)
+        def __len__(self): return self.origins.shape[0]
     LC = R.lse_cameras
     LC.RayBundle = Bundle
     eps = float(np.finfo(float).eps * 4.0)          # nerfstudio camera_utils._EPS
@@ -376,7 +384,7 @@ def glue_goldens(R, g):
         DG = R.lse_ray_generator.DeblurRayGenerator
 
         class Deblur:
-            generate_ray_bundle = DG.__dict__["generate_ray_bundle"]; forward = DG.__dict__["forward"]
+            generate_ray_bundle = DG.__dict__["generate_ray_bundle"]; forward = DG.__dict__["forward"]; __call__ = forward
             def __init__(self, cams): self.cameras = cams; self.image_coords = image_coords
         put("rgb_deblur", Deblur(col).forward(col_idx))
         assert col.get_c2w_fn == col.get_c2w                      # the generator restores the pose function
@@ -481,6 +489,72 @@ def glue_goldens(R, g):
             ri, t0, t1 = LG.LSEOccGridEstimator.sampling(fake, o, d, near_plane=0.05, far_plane=1e3, render_step_size=0.01, cone_angle=0.004, **kw)
             store[f"{tag}__ray_indices"] = T(ri); store[f"{tag}__t_starts"] = T(t0); store[f"{tag}__t_ends"] = T(t1)
     np.savez_compressed(os.path.join(HERE, "ref_sampling.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- datamanager: ray budget, next_train
+    import dataclasses
+    for mod in (R.lse_parser, R.ns_camera_optimizer):      # python >= 3.11: dataclass instances used as field defaults must be hashable
+        for v in vars(mod).values():
+            if isinstance(v, type) and dataclasses.is_dataclass(v) and v.__module__ == mod.__name__:
+                v.__hash__ = lambda self: 0
+    DM = importlib.import_module("lse_nerf.lse_datamanager")
+    IU = importlib.import_module("lse_nerf.interpolation_utils")
+    NCO = R.ns_camera_optimizer
+    NCO.exp_map_SO3xR3 = lambda tv: IU.hom_exp_map_SO3xR3(tv)[..., :3, :]
+    store = {}
+    budget = []
+    for num_rays in (8192, 4096, 1000, 7):
+        for frac in (0.5, 0.25, 0.0, 1.0, 0.33):
+            for mode in ("mse", "deblur"):
+                c = NS(rgb_frac=frac, train_num_rays_per_batch=num_rays, rgb_loss_mode=mode)
+                DM.MultiCamManagerConfig.update_num_batch_rays(c)
+                budget.append([num_rays, frac, int(mode == "deblur"), c.train_num_evs_rays_per_batch, c.train_num_col_rays_per_batch])
+    store["budget"] = np.array(budget, dtype=np.float64)
+    full = syn.make_scene(small_spec())
+    n_col, n_evs = 24, 32
+    col_pick = torch.stack([torch.randint(0, len(col.times), (n_col,), generator=g), torch.randint(0, H, (n_col,), generator=g),
+                            torch.randint(0, W, (n_col,), generator=g)], dim=1)
+    evs_pick = torch.stack([torch.randint(0, len(evs.times) - 1, (n_evs,), generator=g), torch.randint(0, H, (n_evs,), generator=g),
+                            torch.randint(0, W, (n_evs,), generator=g)], dim=1)
+    col_app = torch.tensor([0, 1, 2, 3, 4, 5, 6, 6]); evs_app = torch.arange(len(evs.times) - 1) % 7
+    col_full = {"image": full["col_images"], "image_idx": torch.arange(len(col.times)), "appearance_id": col_app}
+    evs_full = {"image": full["evs_images"], "image_idx": torch.arange(len(evs.times) - 1), "appearance_id": evs_app,
+                "e_thresh": torch.full((len(evs.times) - 1,), 0.2)}
+
+    def sampler(picks, n):
+        sm = R.lse_pixel_sampler.EvPixelSampler.__new__(R.lse_pixel_sampler.EvPixelSampler)
+        sm.sample_method = lambda *a, **k: picks.clone()
+        sm.sample = lambda batch: sm.collate_image_dataset_batch(batch, n)
+        return sm
+
+    class Consec:
+        forward = CG.__dict__["forward"]; __call__ = forward
+        def __init__(self, cams): self.cameras = cams; self.image_coords = image_coords
+    evs.set_interpolator(None); evs.set_hard_cam_type(LC.HardCamType.RGB)          # shipped configs: stored event poses + "ns" optimizer
+    ocfg = NS(mode="SO3xR3", scheme="delayed", delay_cnt=5)
+    evs_opt = NCO.CameraOptimizer(ocfg, num_cameras=len(evs.times), device="cpu")
+    with torch.no_grad():
+        evs_opt.pose_adjustment.copy_(torch.randn(len(evs.times), 6, generator=g) * 0.05)
+    fixer = R.data_components.CameraIdxFixer.__new__(R.data_components.CameraIdxFixer)
+    fixer.rgb_ts = col.times.reshape(-1)
+    store.update(col_pick=T(col_pick), evs_pick=T(evs_pick), col_app=T(col_app), evs_app=T(evs_app), pose_adjustment=T(evs_opt.pose_adjustment),
+                 num_embd=7, delay_cnt=5)
+    for step in (3, 9):
+        fake = NS(col_train_camera_optimizer=spl, evs_train_camera_optimizer=evs_opt, get_train_col_rays_per_batch=lambda: n_col,
+                  get_train_evs_rays_per_batch=lambda: n_evs, iter_col_train_dataloader=iter([col_full]), iter_evs_train_dataloader=iter([evs_full]),
+                  train_col_pixel_sampler=sampler(col_pick, n_col), train_evs_pixel_sampler=sampler(evs_pick, n_evs), col_ray_generator=Deblur(col),
+                  evs_ray_generator=Consec(evs), num_embd=7, cameraIdxFixer=fixer)
+        with torch.no_grad():
+            (cb, pb, nb), batch = DM.MultiCamManager.next_train(fake, step)
+        for name, rb in (("col", cb), ("prev", pb), ("next", nb)):
+            for k in ("origins", "directions", "camera_indices", "times"):
+                store[f"s{step}_{name}__{k}"] = T(getattr(rb, k))
+            for k, v in rb.metadata.items():
+                store[f"s{step}_{name}__md_{k}"] = T(v)
+        for bn in ("col_batch", "evs_batch"):
+            for k, v in batch[bn].items():
+                store[f"s{step}_{bn}__{k}"] = T(v)
+        store[f"s{step}_evs_opt_is_on"] = int(evs_opt.is_on)
+    np.savez_compressed(os.path.join(HERE, "ref_next_train.npz"), **store)
 
 
 if __name__ == "__main__":

@@ -893,3 +893,47 @@ def test_sampling_reference_golden(dev, tag, stratified, alpha_thre, eps):
     got, ref = key(ri, t0, t1), key(*want)
     assert len(got ^ ref) <= 0.01 * len(ref), (len(got), len(ref), len(got ^ ref))
     assert len(ref) < 0.5 * len(z["train_no_cull__ray_indices"])
+
+
+@pytest.mark.parametrize("step", [3, 9])
+def test_datamanager_next_train_reference_golden(dev, step):
+    """MultiCamManager.next_train (pixel collate, deblur / consecutive ray generators on the pose + ray kernels, the delayed "ns" pose
+    deltas, add_metadata, CameraIdxFixer) against the reference's own next_train run on the same picks."""
+    from lsenerf_b200.lse_cameras import EdCameras
+    from lsenerf_b200.lse_datamanager import ImageStore, MultiCamManager, MultiCamManagerConfig
+    from lsenerf_b200.ns_camera_optimizer import CameraOptimizerConfig
+    from test_reference_golden import next_train_scene
+    z, zr, scene = next_train_scene()
+    spec = scene["spec"]
+    cfg = MultiCamManagerConfig(train_num_rays_per_batch=160, rgb_frac=0.6, rgb_loss_mode="deblur",
+                                col_cam_optimizer=CameraOptimizerConfig(mode="SO3xR3", optim_type="spline", scheme="none", exp_t=float(zr["exp_t"])),
+                                evs_cam_optimizer=CameraOptimizerConfig(mode="SO3xR3", optim_type="ns", scheme="delayed", delay_cnt=int(z["delay_cnt"])))
+    assert (cfg.train_num_col_rays_per_batch, cfg.train_num_evs_rays_per_batch) == (24, 32)
+    fx, fy, cx, cy = scene["col_intr"]
+    col_cams = EdCameras(scene["col_c2w"].clone(), fx, fy, cx, cy, spec.col_hw[1], spec.col_hw[0], times=scene["col_times"])
+    fx, fy, cx, cy = scene["evs_intr"]
+    evs_cams = EdCameras(scene["evs_c2w0"].clone(), fx, fy, cx, cy, spec.evs_hw[1], spec.evs_hw[0], times=scene["evs_times"])
+    dm = MultiCamManager(cfg, col_cams, evs_cams, ImageStore(scene["col_images"], scene["col_image_idx"], scene["col_appearance_id"]),
+                         ImageStore(scene["evs_images"], scene["evs_image_idx"], scene["evs_appearance_id"], scene["e_thresh"]),
+                         scene["dM"], int(z["num_embd"]), device=dev,
+                         spline_init=dict(ctrl_tangents=torch.from_numpy(zr["ctrl_tangents"]), ctrl_ts=torch.from_numpy(zr["ctrl_ts"])))
+    col_pick, evs_pick = torch.from_numpy(z["col_pick"]), torch.from_numpy(z["evs_pick"])
+    dm.train_col_pixel_sampler.sample_method = lambda *a, **k: col_pick.clone()
+    dm.train_evs_pixel_sampler.sample_method = lambda *a, **k: evs_pick.clone()
+    with torch.no_grad():
+        dm.evs_train_camera_optimizer.pose_adjustment.copy_(torch.from_numpy(z["pose_adjustment"]))
+        (cb, pb, nb), batch = dm.next_train(step)
+    assert int(dm.evs_train_camera_optimizer.is_on) == int(z[f"s{step}_evs_opt_is_on"])
+    for name, rb in (("col", cb), ("prev", pb), ("next", nb)):
+        tag = f"s{step}_{name}"
+        np.testing.assert_allclose(rb.origins.cpu().numpy(), z[f"{tag}__origins"], rtol=0, atol=3e-5, err_msg=tag)
+        np.testing.assert_allclose(rb.directions.cpu().numpy(), z[f"{tag}__directions"], rtol=0, atol=1e-5, err_msg=tag)
+        np.testing.assert_array_equal(rb.camera_indices.cpu().numpy().reshape(-1), z[f"{tag}__camera_indices"].reshape(-1), err_msg=tag)
+        np.testing.assert_array_equal(rb.times.cpu().numpy().reshape(-1), z[f"{tag}__times"].reshape(-1), err_msg=tag)
+        for k in ("appearance_id", "cam_type", "coords"):
+            np.testing.assert_array_equal(rb.metadata[k].cpu().numpy(), z[f"{tag}__md_{k}"], err_msg=f"{tag} {k}")
+        np.testing.assert_allclose(rb.metadata["directions_norm"].cpu().numpy(), z[f"{tag}__md_directions_norm"], rtol=1e-5)
+    for bn in ("col_batch", "evs_batch"):
+        for k, v in batch[bn].items():
+            if isinstance(v, torch.Tensor):
+                np.testing.assert_array_equal(v.cpu().numpy(), z[f"s{step}_{bn}__{k}"], err_msg=f"{bn} {k}")

@@ -324,3 +324,45 @@ def test_oracle_sampling_matches_reference_glue(tag, training, alpha_thre, eps):
     assert torch.equal(t0, t(z[f"{tag}__t_starts"])) and torch.equal(t1, t(z[f"{tag}__t_ends"]))
     if tag == "train_thre_above_mean":
         assert abs(info["alpha_thre"] - float(z["occs"].mean())) < 1e-9            # min(alpha_thre, occs.mean()), lse_grid_estimator.py:112
+
+
+def test_ray_budget_matches_reference():
+    from lsenerf_b200.lse_datamanager import MultiCamManagerConfig
+    for num_rays, frac, deblur, n_evs, n_col in gold("next_train")["budget"]:
+        assert OD.ray_budget(int(num_rays), float(frac), bool(deblur)) == (int(n_evs), int(n_col))
+        c = MultiCamManagerConfig(train_num_rays_per_batch=int(num_rays), rgb_frac=float(frac), rgb_loss_mode="deblur" if deblur else "mse")
+        assert (c.train_num_evs_rays_per_batch, c.train_num_col_rays_per_batch) == (int(n_evs), int(n_col))
+
+
+def next_train_scene():
+    """the scene dict make_reference_golden.py fed to MultiCamManager.next_train"""
+    z, zr = gold("next_train"), gold("raygen")
+    scene = syn.make_scene(small_spec())
+    assert np.array_equal(scene["col_c2w"].numpy(), zr["col_c2w"]) and np.array_equal(scene["evs_c2w0"].numpy(), zr["evs_c2w"])
+    n_evs = scene["evs_images"].shape[0]
+    scene.update(col_appearance_id=t(z["col_app"]), evs_appearance_id=t(z["evs_app"]), e_thresh=torch.full((n_evs,), 0.2),
+                 evs_c2w=scene["evs_c2w0"], num_emb=int(z["num_embd"]))
+    return z, zr, scene
+
+
+@pytest.mark.parametrize("step", [3, 9])
+def test_oracle_next_train_matches_reference(step):
+    z, zr, scene = next_train_scene()
+    H, W = scene["spec"].col_hw
+    rand = lambda picks, n: (t(picks).float() + 0.5) / torch.tensor([n, H, W], dtype=torch.float32)
+    sd = {"col_cam_opt.ctrl_tangents": t(zr["ctrl_tangents"]), "col_cam_opt.scale": torch.tensor([float(zr["scale"])])}
+    if int(z[f"s{step}_evs_opt_is_on"]):              # "delayed" scheme: the event pose deltas switch on after delay_cnt steps
+        sd["evs_cam_opt.pose_adjustment"] = t(z["pose_adjustment"])
+    assert int(z[f"s{step}_evs_opt_is_on"]) == int(step > int(z["delay_cnt"]))
+    (col, prev, nxt), batch = OD.next_train(scene, sd, rand(z["col_pick"], scene["col_images"].shape[0]),
+                                            rand(z["evs_pick"], scene["evs_images"].shape[0]), True, int(z["num_embd"]))
+    for name, b in (("col", col), ("prev", prev), ("next", nxt)):
+        close(b["origins"], z[f"s{step}_{name}__origins"], rtol=1e-5, atol=2e-6)
+        close(b["directions"], z[f"s{step}_{name}__directions"], rtol=1e-5, atol=1e-6)
+        assert torch.equal(b["camera_indices"].reshape(-1), t(z[f"s{step}_{name}__camera_indices"]).reshape(-1)), name
+        close(b["times"].reshape(-1), z[f"s{step}_{name}__times"].reshape(-1), rtol=0, atol=0)
+        assert torch.equal(b["appearance_id"], t(z[f"s{step}_{name}__md_appearance_id"])), name
+    for bn in ("col_batch", "evs_batch"):
+        for k, v in batch[bn].items():
+            assert torch.equal(v, t(z[f"s{step}_{bn}__{k}"])), (bn, k)
+    assert np.abs(z["s9_prev__origins"] - z["s3_prev__origins"]).max() > 1e-3          # the pose delta is visible in the golden
