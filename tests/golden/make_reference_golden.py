@@ -28,6 +28,10 @@ reference itself does around them: argument order, shapes, index conventions, ma
                        bundles: pixel collate -> ray generators -> camera optimizers incl. the delayed schedule -> add_metadata ->
                        CameraIdxFixer; stand-ins: exp_map_SO3xR3 = the reference's own interpolation_utils.hom_exp_map_SO3xR3 rows 0-2,
                        PixelSampler.sample = collate(batch, num_rays_per_batch), forced pixel picks)
+  ref_train_step.npz   LSENeRFPipeline.get_train_loss_dict -> LSENeRFModel.forward / get_outputs / exec_get_outputs / get_loss_dict with the
+                       reference's LinearRenderer, mappers, GlobalEmbedding, LSEField and LSEOccGridEstimator.sampling on the bundles of
+                       ref_next_train.npz (stand-ins: VolumetricSampler, Field.forward / density_fn, RGB / depth / accumulation renderers,
+                       nerfacc.pack_info / render_weight_from_density / accumulate_along_rays from oracle/nerfacc.py)
   ref_sampling.npz     LSEOccGridEstimator.sampling (stand-ins: traverse_grids / render_visibility_from_density from oracle/nerfacc.py; the density
                        behind sigma_fn uses the weights stored in ref_field.npz)
 
@@ -111,10 +115,42 @@ class _Embedding(torch.nn.Module):
         return self.embedding(in_tensor)
 
 
+class _RGBRenderer(torch.nn.Module):
+    """stand-in for nerfstudio 0.3.2 RGBRenderer on packed samples with background_color="black": nan_to_num / clamp only outside
+    training (which is what the reference's LinearRenderer switches off, lse_renderer.py:6-11)."""
+
+    def __init__(self, background_color="black"):
+        super().__init__()
+        assert background_color == "black"
+
+    def forward(self, rgb, weights, ray_indices, num_rays):
+        from oracle import nerfacc as NA
+        if not self.training:
+            rgb = torch.nan_to_num(rgb)
+        out = NA.accumulate_along_rays(weights[..., 0], rgb, ray_indices, num_rays)
+        if not self.training:
+            torch.clamp_(out, min=0.0, max=1.0)
+        return out
+
+
 def load_reference():
     emb_mod = _StubModule("nerfstudio.field_components.embedding")
     emb_mod.Embedding = _Embedding
     sys.modules["nerfstudio.field_components.embedding"] = emb_mod
+    import enum
+    fh_mod = _StubModule("nerfstudio.field_components.field_heads")
+    fh_mod.FieldHeadNames = enum.Enum("FieldHeadNames", ["RGB", "DENSITY", "UNCERTAINTY", "TRANSIENT_RGB", "TRANSIENT_DENSITY", "SEMANTICS",
+                                                         "PRED_NORMALS"])
+    sys.modules["nerfstudio.field_components.field_heads"] = fh_mod
+    prof_mod = _StubModule("nerfstudio.utils.profiler")
+    prof_mod.time_function = lambda f: f
+    sys.modules["nerfstudio.utils.profiler"] = prof_mod
+    utils_mod = _StubModule("nerfstudio.utils")            # lse_pipeline.py does `from nerfstudio.utils import profiler`
+    utils_mod.profiler = prof_mod
+    sys.modules["nerfstudio.utils"] = utils_mod
+    rend_mod = _StubModule("nerfstudio.model_components.renderers")
+    rend_mod.RGBRenderer = _RGBRenderer
+    sys.modules["nerfstudio.model_components.renderers"] = rend_mod
     dm_mod = _StubModule("nerfstudio.data.datamanagers.base_datamanager")
     dm_mod.TDataset = typing.TypeVar("TDataset")           # lse_datamanager.py:147 subscripts Generic with it
     sys.modules["nerfstudio.data.datamanagers.base_datamanager"] = dm_mod
@@ -123,7 +159,7 @@ def load_reference():
     torch.Any = typing.Any                       # data_components.py annotates with torch.Any (torch 2.0 re-exported typing.Any)
     mods = {n: importlib.import_module("lse_nerf." + n) for n in
             ("utils", "data_components", "intensity_mappers", "ns_camera_optimizer", "lse_pixel_sampler", "lse_field", "lse_embeddings",
-             "lse_parser")}
+             "lse_parser", "lse_renderer")}
     # python >= 3.11 rejects unhashable dataclass instances as field defaults; the reference targets 3.8
     mods["lse_embeddings"].LSEEmbeddingConfig.__hash__ = lambda self: 0
     mods["lsenerf"] = importlib.import_module("lse_nerf.lsenerf")
@@ -538,13 +574,16 @@ def glue_goldens(R, g):
     fixer.rgb_ts = col.times.reshape(-1)
     store.update(col_pick=T(col_pick), evs_pick=T(evs_pick), col_app=T(col_app), evs_app=T(evs_app), pose_adjustment=T(evs_opt.pose_adjustment),
                  num_embd=7, delay_cnt=5)
-    for step in (3, 9):
+    def make_dm():
         fake = NS(col_train_camera_optimizer=spl, evs_train_camera_optimizer=evs_opt, get_train_col_rays_per_batch=lambda: n_col,
                   get_train_evs_rays_per_batch=lambda: n_evs, iter_col_train_dataloader=iter([col_full]), iter_evs_train_dataloader=iter([evs_full]),
                   train_col_pixel_sampler=sampler(col_pick, n_col), train_evs_pixel_sampler=sampler(evs_pick, n_evs), col_ray_generator=Deblur(col),
                   evs_ray_generator=Consec(evs), num_embd=7, cameraIdxFixer=fixer)
+        fake.next_train = lambda step: DM.MultiCamManager.next_train(fake, step)
+        return fake
+    for step in (3, 9):
         with torch.no_grad():
-            (cb, pb, nb), batch = DM.MultiCamManager.next_train(fake, step)
+            (cb, pb, nb), batch = make_dm().next_train(step)
         for name, rb in (("col", cb), ("prev", pb), ("next", nb)):
             for k in ("origins", "directions", "camera_indices", "times"):
                 store[f"s{step}_{name}__{k}"] = T(getattr(rb, k))
@@ -555,6 +594,92 @@ def glue_goldens(R, g):
                 store[f"s{step}_{bn}__{k}"] = T(v)
         store[f"s{step}_evs_opt_is_on"] = int(evs_opt.is_on)
     np.savez_compressed(os.path.join(HERE, "ref_next_train.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- one whole training step
+    LM = R.lsenerf
+    DM.MultiCamManagerConfig.__hash__ = lambda self: 0
+    LP = importlib.import_module("lse_nerf.lse_pipeline")
+    Model, FH = LM.LSENeRFModel, LF.FieldHeadNames
+    LM.nerfacc.pack_info = NA.pack_info
+    LM.nerfacc.render_weight_from_density = lambda t_starts, t_ends, sigmas, packed_info: NA.render_weight_from_density(t_starts, t_ends, sigmas, packed_info)
+
+    class Frustums2:
+        def __init__(self, origins, directions, starts, ends, pixel_area):
+            self.origins, self.directions, self.starts, self.ends, self.pixel_area = origins, directions, starts, ends, pixel_area
+            self.shape = origins.shape[:-1]
+        def get_positions(self): return self.origins + self.directions * (self.starts + self.ends) / 2
+    class Samples2:
+        def __init__(self, frustums, camera_indices=None): self.frustums, self.camera_indices, self.metadata, self.times = frustums, camera_indices, {}, None
+        def __len__(self): return self.frustums.origins.shape[0]
+    torch.manual_seed(3)
+    gemb = LE.GlobalEmbedding(NS(emb_dim=32, eval_mode="zero"), 7, 32)
+    field_self = NS(spatial_distortion=OF.contract_inf, aabb=aabb, geo_feat_dim=15, average_init_density=1.0, training=True,
+                    mlp_base=lambda x: OF.mlp(OF.hash_encode(x, sd[OF.K_TABLE], sc, 2**log2_T), sd, OF.K_BASE, 2, None),
+                    direction_encoding=OF.sh_deg4, embedding_appearance=gemb, use_transient_embedding=False, use_semantics=False,
+                    use_pred_normals=False, appearance_embedding_dim=32, mlp_head=lambda h: OF.mlp(h, sd, OF.K_HEAD, 3, "sigmoid"))
+
+    def field_forward(ray_samples):                  # nerfstudio Field.forward
+        density, density_embedding = LF.LSEField.get_density(field_self, ray_samples)
+        out = LF.LSEField.get_outputs(field_self, ray_samples, density_embedding=density_embedding)
+        out[FH.DENSITY] = density
+        return out
+
+    def density_fn(positions):                       # nerfstudio Field.density_fn: a zero-length frustum at each position
+        fr = Frustums2(positions, torch.ones_like(positions), torch.zeros_like(positions[..., :1]), torch.zeros_like(positions[..., :1]),
+                       torch.ones_like(positions[..., :1]))
+        return LF.LSEField.get_density(field_self, Samples2(fr))[0]
+    grid_self = NS(binaries=grid.binaries, aabbs=grid.aabbs, occs=grid.occs)
+
+    def volumetric_sampler(ray_bundle, render_step_size, near_plane, far_plane, alpha_thre, cone_angle):        # nerfstudio VolumetricSampler.forward
+        rays_o, rays_d = ray_bundle.origins.contiguous(), ray_bundle.directions.contiguous()
+
+        def sigma_fn(t_starts, t_ends, ray_indices):
+            positions = rays_o[ray_indices] + rays_d[ray_indices] * (t_starts + t_ends)[:, None] / 2.0
+            return density_fn(positions).squeeze(-1)
+        ri, t0, t1 = LG.LSEOccGridEstimator.sampling(grid_self, rays_o, rays_d, t_min=None, t_max=None, sigma_fn=sigma_fn,
+                                                     render_step_size=render_step_size, near_plane=near_plane, far_plane=far_plane,
+                                                     stratified=True, cone_angle=cone_angle, alpha_thre=alpha_thre)
+        if t0.shape[0] == 0:
+            ri = torch.zeros((1,), dtype=torch.long); t0 = torch.ones((1,)); t1 = torch.ones((1,))
+        fr = Frustums2(rays_o[ri], rays_d[ri], t0[..., None], t1[..., None], ray_bundle.pixel_area[ri])
+        return Samples2(fr, ray_bundle.camera_indices.contiguous()[ri]), ri
+
+    def depth_renderer(weights, ray_samples, ray_indices, num_rays):                                             # DepthRenderer("expected")
+        steps = (ray_samples.frustums.starts + ray_samples.frustums.ends) / 2
+        d = NA.accumulate_along_rays(weights[..., 0], steps, ray_indices, num_rays)
+        d = d / (NA.accumulate_along_rays(weights[..., 0], None, ray_indices, num_rays) + 1e-10)
+        return torch.clip(d, steps.min(), steps.max())
+    pw2 = R.intensity_mappers.Powpow()
+    with torch.no_grad():
+        pw2.pow_coeff.fill_(0.83)
+    mcfg = NS(near_plane=0.05, far_plane=1e3, render_step_size=0.01, alpha_thre=0.01, cone_angle=0.004, use_mapping=True, map_mode="co_map",
+              ev_one_dim="gt", rgb_loss_type="deblur", event_loss_type="log_loss", evs_loss_weight=0.7)
+
+    class FakeModel:
+        forward = Model.__dict__["forward"]; get_outputs = Model.__dict__["get_outputs"]; exec_get_outputs = Model.__dict__["exec_get_outputs"]
+        correct_evs_dim = Model.__dict__["correct_evs_dim"]; get_loss_dict = Model.__dict__["get_loss_dict"]
+        log_loss = Model.__dict__["log_loss"]; mse_loss = Model.__dict__["mse_loss"]
+        def __call__(self, rb, **kw): return self.forward(rb, **kw)
+        def get_metrics_dict(self, outputs, batch): return {}
+    m = FakeModel()
+    m.__dict__.update(config=mcfg, collider=None, field=field_forward, sampler=volumetric_sampler, training=True, device="cpu",
+                      renderer_rgb=R.lse_renderer.LinearRenderer(background_color="black"), renderer_depth=depth_renderer,
+                      renderer_accumulation=lambda weights, ray_indices, num_rays: NA.accumulate_along_rays(weights[..., 0], None, ray_indices, num_rays),
+                      rgb_mapper=R.intensity_mappers.IdentityMapper(), evs_mapper=pw2, rgb_to_one=LM.ToGrayGT(), rgb_loss=torch.nn.MSELoss())
+    m.rgb_losses_dic = {"linspace": m.mse_loss, "deblur": m.mse_loss}
+    m.event_loss = m.log_loss
+    pipe = NS(datamanager=make_dm(), _model=m, model=m, config=NS(datamanager=NS(camera_optimizer=None)))
+    with torch.no_grad():
+        torch.manual_seed(5)
+        jit = [torch.rand(96), torch.rand(32), torch.rand(32)]             # the three rand_like(near_planes) draws of the step, in call order
+        torch.manual_seed(5)
+        outs, losses, _ = LP.LSENeRFPipeline.get_train_loss_dict(pipe, 9)
+    store = dict(emb_weight=T(gemb.embedding.weight), pow_coeff=0.83, evs_loss_weight=0.7, alpha_thre=0.01, jitter_col=T(jit[0]), jitter_prev=T(jit[1]),
+                 jitter_next=T(jit[2]), rgb_loss=float(losses["rgb_loss"]), event_loss=float(losses["event_loss"]))
+    for name in ("col_out", "prev_out", "next_out"):
+        for k, v in outs[name].items():
+            store[f"{name}__{k}"] = T(v)
+    np.savez_compressed(os.path.join(HERE, "ref_train_step.npz"), **store)
 
 
 if __name__ == "__main__":

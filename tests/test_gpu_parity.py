@@ -895,10 +895,8 @@ def test_sampling_reference_golden(dev, tag, stratified, alpha_thre, eps):
     assert len(ref) < 0.5 * len(z["train_no_cull__ray_indices"])
 
 
-@pytest.mark.parametrize("step", [3, 9])
-def test_datamanager_next_train_reference_golden(dev, step):
-    """MultiCamManager.next_train (pixel collate, deblur / consecutive ray generators on the pose + ray kernels, the delayed "ns" pose
-    deltas, add_metadata, CameraIdxFixer) against the reference's own next_train run on the same picks."""
+def _golden_datamanager(dev):
+    """the MultiCamManager make_reference_golden.py modelled with the reference's classes (forced pixel picks)"""
     from lsenerf_b200.lse_cameras import EdCameras
     from lsenerf_b200.lse_datamanager import ImageStore, MultiCamManager, MultiCamManagerConfig
     from lsenerf_b200.ns_camera_optimizer import CameraOptimizerConfig
@@ -922,6 +920,15 @@ def test_datamanager_next_train_reference_golden(dev, step):
     dm.train_evs_pixel_sampler.sample_method = lambda *a, **k: evs_pick.clone()
     with torch.no_grad():
         dm.evs_train_camera_optimizer.pose_adjustment.copy_(torch.from_numpy(z["pose_adjustment"]))
+    return dm, z, scene
+
+
+@pytest.mark.parametrize("step", [3, 9])
+def test_datamanager_next_train_reference_golden(dev, step):
+    """MultiCamManager.next_train (pixel collate, deblur / consecutive ray generators on the pose + ray kernels, the delayed "ns" pose
+    deltas, add_metadata, CameraIdxFixer) against the reference's own next_train run on the same picks."""
+    dm, z, _ = _golden_datamanager(dev)
+    with torch.no_grad():
         (cb, pb, nb), batch = dm.next_train(step)
     assert int(dm.evs_train_camera_optimizer.is_on) == int(z[f"s{step}_evs_opt_is_on"])
     for name, rb in (("col", cb), ("prev", pb), ("next", nb)):
@@ -937,3 +944,87 @@ def test_datamanager_next_train_reference_golden(dev, step):
         for k, v in batch[bn].items():
             if isinstance(v, torch.Tensor):
                 np.testing.assert_array_equal(v.cpu().numpy(), z[f"s{step}_{bn}__{k}"], err_msg=f"{bn} {k}")
+
+
+def _golden_model(dev, tensor_cores):
+    """the CUDA model holding the weights / occupancy grid make_reference_golden.py gave the reference's model classes"""
+    from lsenerf_b200.lse_embeddings import LSEEmbeddingConfig
+    from lsenerf_b200.lsenerf import LSENeRFModel, LSENeRFModelConfig
+    from oracle import field as OF
+    from test_reference_golden import train_step_inputs
+    z, scene, sd, ocfg, grid, _, jitters = train_step_inputs()
+    mcfg = LSENeRFModelConfig(grid_resolution=32, grid_levels=2, log2_hashmap_size=ocfg.log2_hashmap_size, alpha_thre=ocfg.alpha_thre,
+                              render_step_size=ocfg.render_step_size, use_mapping=True, mapping_method="identity", map_mode="co_map",
+                              evs_mapping_method="powpow", ev_one_dim="gt", rgb_loss_type="deblur", evs_loss_weight=ocfg.evs_loss_weight,
+                              embed_config=LSEEmbeddingConfig(embedding_type="global_emb"), use_tensor_cores=tensor_cores)
+    m = LSENeRFModel(mcfg, scene["aabb"], num_train_data=7).to(dev)
+    m.train()
+    with torch.no_grad():
+        f = m.field
+        f.mlp_base_grid.hash_table.copy_(sd[OF.K_TABLE])
+        for mod, prefix, n in ((f.mlp_base_mlp, OF.K_BASE, 2), (f.mlp_head, OF.K_HEAD, 3)):
+            for i in range(n):
+                mod.layers[i].weight.copy_(sd[f"{prefix}.layers.{i}.weight"]); mod.layers[i].bias.copy_(sd[f"{prefix}.layers.{i}.bias"])
+        f.embedding_appearance.embedding.weight.copy_(sd[OF.K_EMB])
+        m.evs_mapper.pow_coeff.fill_(float(z["pow_coeff"]))
+        g = m.occupancy_grid
+        g.binaries.copy_(grid.binaries); g.occs.copy_(grid.occs); g.refresh_occ_mean()
+    return m, z, jitters
+
+
+def _check_step_outputs(dev, z, outs, ld, tol, max_mismatch):
+    mism = 0.0
+    for name, o in outs.items():
+        a, b_ = o["num_samples_per_ray"].cpu().long(), torch.from_numpy(z[f"{name}__num_samples_per_ray"])
+        same = a == b_
+        mism = max(mism, float((~same).float().mean()))
+        assert (~same).float().mean() <= max_mismatch, (name, int((~same).sum()))
+        assert int(b_.sum()) > 100
+        same_px = same.reshape(-1, 4).all(dim=1)              # deblur: every bundle here is averaged in groups of 4 (lsenerf.py:365-370)
+        G = lambda k: torch.from_numpy(z[f"{name}__{k}"])
+        assert tuple(o["rgb"].shape) == tuple(G("rgb").shape)
+        assert rel_err(o["rgb"][same_px.to(dev)], G("rgb")[same_px]) < tol, name
+        assert rel_err(o["accumulation"][same.to(dev)], G("accumulation")[same]) < tol, name
+        vis = same & (G("accumulation")[:, 0] > 0.5)
+        assert rel_err(o["depth"][vis.to(dev)], G("depth")[vis]) < max(tol, 1e-3), name
+        if name != "col_out":
+            assert rel_err(o["ev_out"][same.to(dev)], G("ev_out")[same]) < tol, name
+        else:
+            assert "ev_out" not in o
+    for k in ("rgb_loss", "event_loss"):
+        want = float(z[k])
+        assert abs(float(ld[k]) - want) <= (2 * tol + 0.1 * mism) * abs(want) + 1e-7, (k, float(ld[k]), want, mism)
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_training_step_reference_golden(dev, tensor_cores):
+    """The CUDA model (march / cull / field / composite / epilogue / losses) on the exact rays of the reference's next_train, against the
+    outputs of the reference's LSENeRFPipeline.get_train_loss_dict + LSENeRFModel glue (tests/golden/ref_train_step.npz) at the 1e-4
+    bar.  Rays whose kept-sample count differs sit on a culling threshold (fp32 densities of another device): bounded in number and
+    excluded from the 1e-4 comparison, exactly as in test_train_step_parity."""
+    from lsenerf_b200.compat import RayBundle
+    m, z, jitters = _golden_model(dev, tensor_cores)
+    zn = _ref("next_train")
+    G = lambda k: torch.from_numpy(zn[k]).to(dev)
+    bundles = [RayBundle(origins=G(f"s9_{n}__origins"), directions=G(f"s9_{n}__directions"), camera_indices=G(f"s9_{n}__camera_indices"),
+                         times=G(f"s9_{n}__times"), metadata={"appearance_id": G(f"s9_{n}__md_appearance_id")}) for n in ("col", "prev", "next")]
+    batch = {"col_batch": {"image": G("s9_col_batch__image")}, "evs_batch": {"image": G("s9_evs_batch__image"), "e_thresh": G("s9_evs_batch__e_thresh")}}
+    with torch.no_grad():
+        outs = {name: m(b, ev_out=ev, jitter=j.to(dev)) for name, b, ev, j in zip(("col_out", "prev_out", "next_out"), bundles,
+                                                                                 (False, True, True), jitters)}
+        ld = m.get_loss_dict(outs, batch)
+    _check_step_outputs(dev, z, outs, ld, TOL_OUT, 0.05)
+
+
+def test_training_step_through_cuda_datamanager_reference_golden(dev):
+    """The same step with the rays coming from the CUDA datamanager.  The fixture's hash table is random at full amplitude down to
+    1/2048 cells, so the 2e-5 the pose kernel is allowed against the reference moves a ray's opacity by up to 1e-2 (measured with the
+    oracle by perturbing its rays by that much): the bound here is that sensitivity, the 1e-4 bar is the test above."""
+    m, z, jitters = _golden_model(dev, True)
+    dm, _, _ = _golden_datamanager(dev)
+    with torch.no_grad():
+        bundles, batch = dm.next_train(9)
+        outs = {name: m(b, ev_out=ev, jitter=j.to(dev)) for name, b, ev, j in zip(("col_out", "prev_out", "next_out"), bundles,
+                                                                                 (False, True, True), jitters)}
+        ld = m.get_loss_dict(outs, batch)
+    _check_step_outputs(dev, z, outs, ld, 2e-2, 0.10)

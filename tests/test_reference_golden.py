@@ -366,3 +366,45 @@ def test_oracle_next_train_matches_reference(step):
         for k, v in batch[bn].items():
             assert torch.equal(v, t(z[f"s{step}_{bn}__{k}"])), (bn, k)
     assert np.abs(z["s9_prev__origins"] - z["s3_prev__origins"]).max() > 1e-3          # the pose delta is visible in the golden
+
+
+def train_step_inputs():
+    """everything make_reference_golden.py fed to LSENeRFPipeline.get_train_loss_dict at step 9"""
+    from oracle import nerfacc as NA
+    z, zs = gold("train_step"), gold("sampling")
+    zn, zr, scene = next_train_scene()
+    _, sd, sc, log2_T = field_state()
+    pw = torch.tensor(float(z["pow_coeff"]))
+    sd.update({OF.K_EMB: t(z["emb_weight"]), "evs_mapper.pow_coeff": pw, "rgb_mapper.pow_coeff": pw,
+               "col_cam_opt.ctrl_tangents": t(zr["ctrl_tangents"]), "col_cam_opt.scale": torch.tensor([float(zr["scale"])]),
+               "evs_cam_opt.pose_adjustment": t(zn["pose_adjustment"])})
+    grid = NA.OccGrid(torch.tensor([-1.0, -1, -1, 1, 1, 1]), resolution=32, levels=2)
+    grid.binaries, grid.occs = t(zs["binaries"]), t(zs["occs"])
+    cfg = OM.Cfg(near_plane=0.05, far_plane=1e3, render_step_size=0.01, alpha_thre=float(z["alpha_thre"]), cone_angle=0.004, early_stop_eps=1e-4,
+                 log2_hashmap_size=log2_T, use_mapping=True, mapping_method="identity", map_mode="co_map", evs_mapping_method="powpow",
+                 ev_one_dim="gt", rgb_loss_type="deblur", event_loss_type="log_loss", evs_loss_weight=float(z["evs_loss_weight"]),
+                 embedding_type="global_emb", scalings=sc)
+    H, W = scene["spec"].col_hw
+    rand = lambda picks, n: (t(picks).float() + 0.5) / torch.tensor([n, H, W], dtype=torch.float32)
+    rands = (rand(zn["col_pick"], scene["col_images"].shape[0]), rand(zn["evs_pick"], scene["evs_images"].shape[0]))
+    jitters = [t(z["jitter_col"]), t(z["jitter_prev"]), t(z["jitter_next"])]
+    return z, scene, sd, cfg, grid, rands, jitters
+
+
+def test_oracle_training_step_matches_reference_glue():
+    """One whole step -- next_train, three bundles through sampling / field / compositing / epilogue, the loss dict -- as composed by
+    the reference's pipeline and model classes."""
+    z, scene, sd, cfg, grid, rands, jitters = train_step_inputs()
+    with torch.no_grad():
+        bundles, batch = OD.next_train(scene, sd, rands[0], rands[1], True, scene["num_emb"])
+        outs, ld = OD.train_losses(sd, cfg, grid, bundles, batch, jitters)
+    for name in ("col_out", "prev_out", "next_out"):
+        assert torch.equal(outs[name]["num_samples_per_ray"], t(z[f"{name}__num_samples_per_ray"])), name
+        for k in ("rgb", "accumulation", "depth", "linear", "ev_linear", "ev_out"):
+            if f"{name}__{k}" in z.files:
+                close(outs[name][k], z[f"{name}__{k}"], rtol=2e-5, atol=2e-6)
+            else:
+                assert k not in outs[name], (name, k)
+    close(ld["rgb_loss"], float(z["rgb_loss"]), rtol=1e-5)
+    close(ld["event_loss"], float(z["event_loss"]), rtol=1e-5)
+    assert outs["prev_out"]["rgb"].shape == (8, 3)       # the deblur group mean hits every bundle whose ray count divides by 4
