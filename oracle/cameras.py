@@ -1,6 +1,7 @@
 """Oracle (test infrastructure): perspective ray generation of EdCameras and the LSE ray generators.
 
-PARITY UNPINNED for the nerfstudio-inherited arithmetic (Cameras, camera_utils.normalize_with_norm); the
+Pinned by tests/golden/ref_raygen.npz (the reference's EdCameras and ray generators run on a seeded scene; the one stand-in is
+nerfstudio's one-line camera_utils.normalize_with_norm, which stays PARITY UNPINNED); the
 LSENeRF-specific parts follow /root/reference/lse_nerf/lse_cameras.py:52-73,339-395,487-493,539-586 and
 /root/reference/lse_nerf/lse_ray_generator.py:46-147 line by line.
 """

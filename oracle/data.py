@@ -3,7 +3,8 @@
 Follows /root/reference/lse_nerf/lse_pixel_sampler.py:6-48, lse_nerf/utils.py:153-194,
 lse_nerf/data_components.py:5-29,84-90, lse_nerf/lse_datamanager.py:135-144,337-372 and
 lse_nerf/lse_pipeline.py:110-145.  ``PixelSampler.sample_method`` (nerfstudio 0.3.2) is restated as
-``floor(rand(B,3) * [N,H,W]).long()``: PARITY UNPINNED for that one line.
+``floor(rand(B,3) * [N,H,W]).long()``: PARITY UNPINNED for that one line; everything else here is pinned by
+tests/golden/ref_utils / ref_sampler / ref_next_train / ref_train_step .npz (the reference's own functions run on seeded inputs).
 """
 from __future__ import annotations
 

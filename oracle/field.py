@@ -1,6 +1,8 @@
 """Oracle (test infrastructure): LSEField on the nerfstudio torch (non-tcnn) path.
 
-PARITY UNPINNED (see oracle/__init__.py).  Restates /root/reference/lse_nerf/lse_field.py:43-91,264-360 and the
+PARITY UNPINNED for the nerfstudio arithmetic (hash encoding, MLP, SH, contraction, trunc_exp); the composition LSEField puts around
+it, the embeddings and the hash-grid constants are pinned by tests/golden/ref_field.npz / ref_hashenc.npz (see oracle/__init__.py).
+Restates /root/reference/lse_nerf/lse_field.py:43-91,264-360 and the
 nerfstudio 0.3.2 components it instantiates (HashEncoding.pytorch_fwd/hash_fn, MLP, SHEncoding,
 SceneContraction(order=inf), trunc_exp, Embedding) as functions over a state dict that uses the
 reference's checkpoint keys.

@@ -1,6 +1,8 @@
 """Oracle (test infrastructure): LSENeRFModel forward, sampler, renderers, mappers and losses on CPU torch.
 
-PARITY UNPINNED (see oracle/__init__.py).  Follows /root/reference/lse_nerf/lsenerf.py:278-439,
+Pinned (tests/golden/ref_epilogue, ref_losses, ref_mappers, ref_sampling, ref_train_step .npz): epilogue, losses, mappers and the
+composition of a whole step; PARITY UNPINNED for the nerfstudio / nerfacc arithmetic underneath (see oracle/__init__.py).
+Follows /root/reference/lse_nerf/lsenerf.py:278-439,
 lse_nerf/lse_grid_estimator.py:15-144, lse_nerf/lse_renderer.py:6-11, lse_nerf/intensity_mappers.py:27-87 and
 the nerfstudio 0.3.2 VolumetricSampler / RGBRenderer / DepthRenderer / AccumulationRenderer / MSELoss they call.
 Parameters come in a state dict with the reference's checkpoint keys.

@@ -2,7 +2,8 @@
 
 Restates /root/reference/lse_nerf/interpolation_utils.py and the pose methods of
 /root/reference/lse_nerf/ns_camera_optimizer.py as plain differentiable torch functions.
-PINNED by tests/golden/pose_*.npz (generated from the reference module itself).
+PINNED by tests/golden/pose_*.npz (generated from the reference module itself) and tests/golden/ref_spline.npz (the reference's
+SplineCameraOptimizer: control points built from cameras, rgb / event / deblur queries).
 """
 from __future__ import annotations
 
