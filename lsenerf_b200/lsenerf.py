@@ -189,7 +189,7 @@ class LSENeRFModel(nn.Module):
             rgb = torch.clamp(rgb, 0.0, 1.0)  # RGBRenderer eval clamp (nan_to_num is a no-op on sigmoid outputs)
         out = {"rgb": rgb, "accumulation": acc, "num_samples_per_ray": nspr}
         if with_depth:
-            out["depth"] = ops.finalize_depth(dnum, acc, mm)
+            out["depth"], out["num_samples_per_ray"] = ops.finalize_depth(dnum, acc, mm, nspr)
         return out
 
     def _epilogue_cfg(self, ev_out: bool):

@@ -501,10 +501,20 @@ def composite(sigma, rgb, t0, t1, starts, counts):
     return _Composite.apply(sigma, rgb, t0, t1, starts, counts)
 
 
-def finalize_depth(dnum: Tensor, acc: Tensor, mm: Tensor) -> Tensor:
-    """DepthRenderer('expected'): depth = sum(w*t)/(acc+1e-10) clipped to [min t_mid, max t_mid] over all samples."""
-    depth = dnum / (acc + 1e-10)
-    return torch.clip(depth, mm[:, 0].min(), mm[:, 1].max())
+def finalize_depth(dnum: Tensor, acc: Tensor, mm: Tensor, nspr: Optional[Tensor] = None):
+    """DepthRenderer('expected'): depth = sum(w*t)/(acc+1e-10) clipped to [min t_mid, max t_mid] over all samples.
+    A bundle that kept no sample at all gets, upstream, one zero-length sample at t = 1 on ray 0 (nerfstudio VolumetricSampler):
+    it carries no weight, but it sets the clip range to [1, 1] and counts as ray 0's sample.  With `nspr` (num_samples_per_ray)
+    given, returns (depth, nspr) with that rule applied; no host sync."""
+    lo, hi = mm[:, 0].min(), mm[:, 1].max()
+    empty = torch.isinf(lo)
+    one = torch.ones_like(lo)
+    depth = torch.clip(dnum / (acc + 1e-10), torch.where(empty, one, lo), torch.where(empty, one, hi))
+    if nspr is None:
+        return depth
+    nspr = nspr.clone()
+    nspr[:1] += empty.to(nspr.dtype)
+    return depth, nspr
 
 
 # =================================================================================================================

@@ -260,6 +260,16 @@ def main():
             outs = {"col_out": {"rgb": col_rgb}, "prev_out": {key: p}, "next_out": {key: n}}
             ld = Model.get_loss_dict(fake, outs, {"col_batch": {"image": col_img}, "evs_batch": {"image": evs_img, "e_thresh": thr}})
             store[f"{loss_type}_map{int(use_mapping)}"] = np.array([float(ld["rgb_loss"]), float(ld["event_loss"])])
+            if loss_type == "enerf_norm_loss" and use_mapping:       # (3-channel radiance: [n,3] / [n] does not broadcast -- upstream raises)
+                # what the pixel sampler really hands over: e_thresh [n] (lse_pixel_sampler.py:41-42) against evs [n,1] -> the
+                # division at lsenerf.py:417 broadcasts to [n,n]; with per-frame thresholds that changes the number
+                thr1d = 0.1 + 0.2 * torch.rand(24, generator=torch.Generator().manual_seed(1))
+                store["e_thresh_1d"] = T(thr1d)
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    ld = Model.get_loss_dict(fake, outs, {"col_batch": {"image": col_img}, "evs_batch": {"image": evs_img, "e_thresh": thr1d}})
+                store[f"{loss_type}_thr1d_map{int(use_mapping)}"] = np.array([float(ld["rgb_loss"]), float(ld["event_loss"])])
     np.savez(os.path.join(HERE, "ref_losses.npz"), **store)
 
     # ---------------------------------------------------------------------------------------------- spline camera optimizer

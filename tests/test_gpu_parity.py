@@ -734,6 +734,14 @@ def test_loss_dict_reference_golden(dev, loss_type, use_mapping):
     want = z[f"{loss_type}_map{int(use_mapping)}"]
     assert abs(float(ld["rgb_loss"]) - want[0]) <= TOL_OUT * abs(want[0])
     assert abs(float(ld["event_loss"]) - want[1]) <= TOL_OUT * abs(want[1])
+    if loss_type == "enerf_norm_loss" and use_mapping:        # e_thresh [n] as the sampler delivers it: the [n,n] broadcast of lsenerf.py:417
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ld = LSENeRFModel.get_loss_dict(fake, {"col_out": {"rgb": G("col_rgb")}, "prev_out": {key: p}, "next_out": {key: n}},
+                                            {"col_batch": {"image": G("col_img")}, "evs_batch": {"image": G("evs_img"), "e_thresh": G("e_thresh_1d")}})
+        want = z["enerf_norm_loss_thr1d_map1"]
+        assert abs(float(ld["event_loss"]) - want[1]) <= TOL_OUT * abs(want[1])
 
 
 @pytest.mark.parametrize("tag", ["f1_off", "f1_SO3xR3", "f2_off", "f2_SO3xR3"])
@@ -1028,3 +1036,49 @@ def test_training_step_through_cuda_datamanager_reference_golden(dev):
                                                                                  (False, True, True), jitters)}
         ld = m.get_loss_dict(outs, batch)
     _check_step_outputs(dev, z, outs, ld, 2e-2, 0.10)
+
+
+# ---------------------------------------------------------------------------------------------------- empty / one-sided inputs
+def test_bundle_that_keeps_no_sample(dev):
+    """Rays that miss every grid level: the reference's sampler substitutes one zero-length sample at t = 1 on ray 0 (weightless, but it
+    fixes depth = 1 and num_samples_per_ray[0] = 1); colour goes through the 1e-5 clamp of the epilogue into ev_out."""
+    from lsenerf_b200.compat import RayBundle
+    from oracle import model as OM
+    scene, p = _pipeline(dev)
+    p.train()
+    m = p._model
+    R = 64
+    g = torch.Generator().manual_seed(0)
+    o = torch.tensor([20.0, 20.0, 20.0]) + torch.rand(R, 3, generator=g)
+    d = torch.nn.functional.normalize(torch.tensor([1.0, 0.2, 0.1]) + 0.1 * torch.rand(R, 3, generator=g), dim=-1)
+    jit = torch.rand(R, generator=g)
+    with torch.no_grad():
+        out = m(RayBundle(origins=o.to(dev), directions=d.to(dev), metadata={}), ev_out=True, jitter=jit.to(dev))
+        ref = OM.get_outputs(oracle_state(p), oracle_cfg(p), oracle_grid(p), dict(origins=o, directions=d), True, True, jit)
+    assert int(ref["num_samples_per_ray"].sum()) == 1 and int(ref["num_samples_per_ray"][0]) == 1
+    assert torch.equal(out["num_samples_per_ray"].cpu().long(), ref["num_samples_per_ray"])
+    for k in ("rgb", "accumulation", "depth", "ev_out"):
+        assert torch.allclose(out[k].cpu(), ref[k], rtol=1e-6, atol=1e-7), k
+    assert float(out["accumulation"].abs().max()) == 0.0 and bool((out["depth"] == 1.0).all())
+
+
+@pytest.mark.parametrize("rgb_frac", [1.0, 0.0])
+def test_one_sided_batches(dev, rgb_frac):
+    """rgb_frac = 1 (BAD-NeRF, no event rays) and rgb_frac = 0 (events only): next_train returns None for the missing side
+    (lse_datamanager.py:344-366) and get_train_loss_dict / get_loss_dict skip it (lse_pipeline.py:114-123, lsenerf.py:426-437)."""
+    scene = syn.make_scene(small_spec())
+    p = syn.build_pipeline(scene, "lsenerf", num_rays=512, rgb_frac=rgb_frac, deblur=True, cam_opt=True, device=dev, seed=5, pin=False)
+    p.train()
+    bundles, batch = p.datamanager.next_train(0)
+    if rgb_frac == 1.0:
+        assert bundles[1] is None and bundles[2] is None and batch["evs_batch"] is None and len(bundles[0]) == 512
+    else:
+        assert bundles[0] is None and batch["col_batch"] is None and len(bundles[1]) == len(bundles[2]) == 256
+    outs, ld, _ = p.get_train_loss_dict(1)
+    assert set(ld) == ({"rgb_loss"} if rgb_frac == 1.0 else {"event_loss"})
+    assert (outs["col_out"] is None) == (rgb_frac == 0.0) and (outs["prev_out"] is None) == (rgb_frac == 1.0)
+    loss = sum(ld.values())
+    assert bool(torch.isfinite(loss)) and float(loss) > 0
+    loss.backward()
+    g = p._model.field.mlp_head.layers[2].weight.grad
+    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0

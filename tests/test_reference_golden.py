@@ -146,6 +146,15 @@ def test_oracle_losses_match_reference(loss_type, use_mapping):
     want = z[f"{loss_type}_map{int(use_mapping)}"]
     close(ld["rgb_loss"], want[0], rtol=1e-6)
     close(ld["event_loss"], want[1], rtol=1e-6)
+    if loss_type == "enerf_norm_loss" and use_mapping:
+        # e_thresh as the pixel sampler delivers it, [n]: evs [n,1] / e_thresh [n] broadcasts to [n,n] upstream (lsenerf.py:417); the
+        # column norms cancel the thresholds again, so the value equals the [n,1] case -- reproduced, not "fixed"
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ld = OM.loss_dict(cfg, {"rgb": t(z["col_rgb"])}, {key: p}, {key: n}, t(z["col_img"]), t(z["evs_img"]), t(z["e_thresh_1d"]))
+        close(ld["event_loss"], z["enerf_norm_loss_thr1d_map1"][1], rtol=1e-6)
+        close(z["enerf_norm_loss_thr1d_map1"], want, rtol=1e-6)
 
 
 # ------------------------------------------------------------------------------------------------------ spline camera optimiser
