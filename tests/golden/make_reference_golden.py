@@ -32,6 +32,8 @@ reference itself does around them: argument order, shapes, index conventions, ma
                        reference's LinearRenderer, mappers, GlobalEmbedding, LSEField and LSEOccGridEstimator.sampling on the bundles of
                        ref_next_train.npz (stand-ins: VolumetricSampler, Field.forward / density_fn, RGB / depth / accumulation renderers,
                        nerfacc.pack_info / render_weight_from_density / accumulate_along_rays from oracle/nerfacc.py)
+  ref_prevnext.npz     PrevNextRayGenerator.forward + PrevNextCamOptimizer.apply_to_raybundle (explicit prev / next camera sets, two pose-delta
+                       tables alternating by call parity; same stand-ins as ref_raygen / ref_next_train)
   ref_sampling.npz     LSEOccGridEstimator.sampling (stand-ins: traverse_grids / render_visibility_from_density from oracle/nerfacc.py; the density
                        behind sigma_fn uses the weights stored in ref_field.npz)
 
@@ -690,6 +692,32 @@ def glue_goldens(R, g):
         for k, v in outs[name].items():
             store[f"{name}__{k}"] = T(v)
     np.savez_compressed(os.path.join(HERE, "ref_train_step.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- explicit prev / next camera sets
+    g2 = torch.Generator().manual_seed(2024)          # own generator: the files above must not depend on this block
+    n_cam = len(evs.times) - 1
+    prev_cams = Cams(evs.camera_to_worlds[:-1].clone(), evs_intr, evs.times[:-1].clone())
+    next_cams = Cams(evs.camera_to_worlds[1:].clone(), evs_intr, evs.times[1:].clone())
+    PN = R.lse_ray_generator.PrevNextRayGenerator
+    pn_gen = NS(prev_cameras=prev_cams, next_cameras=next_cams, image_coords=image_coords)
+    pn_idx = torch.stack([torch.randint(0, n_cam, (n,), generator=g2), torch.randint(0, H, (n,), generator=g2),
+                          torch.randint(0, W, (n,), generator=g2)], dim=1)
+    pn_opt = NCO.PrevNextCamOptimizer(NS(mode="SO3xR3", scheme="none", delay_cnt=0), num_cameras=n_cam, device="cpu")
+    with torch.no_grad():
+        pn_opt.prev_optim.pose_adjustment.copy_(torch.randn(n_cam, 6, generator=g2) * 0.05)
+        pn_opt.next_optim.pose_adjustment.copy_(torch.randn(n_cam, 6, generator=g2) * 0.05)
+        pn_opt.next_optim.pose_adjustment[0] = 0.0                      # identity delta: the clamp branch of the angle (|w|^2 < 1e-4)
+        pb, nb = PN.__dict__["forward"](pn_gen, pn_idx)
+        store = dict(pn_idx=T(pn_idx), prev_c2w=T(prev_cams.camera_to_worlds), next_c2w=T(next_cams.camera_to_worlds), times_prev=T(prev_cams.times),
+                     times_next=T(next_cams.times), intr=np.array(evs_intr), pose_prev=T(pn_opt.prev_optim.pose_adjustment),
+                     pose_next=T(pn_opt.next_optim.pose_adjustment), hw=np.array([H, W]))
+        for name, rb in (("prev", pb), ("next", nb)):
+            store[f"raw_{name}__origins"] = T(rb.origins); store[f"raw_{name}__directions"] = T(rb.directions)
+            store[f"raw_{name}__camera_indices"] = T(rb.camera_indices); store[f"raw_{name}__times"] = T(rb.times)
+        pn_opt.apply_to_raybundle(pb); pn_opt.apply_to_raybundle(nb)    # call parity: first -> prev table, second -> next table
+        for name, rb in (("prev", pb), ("next", nb)):
+            store[f"adj_{name}__origins"] = T(rb.origins); store[f"adj_{name}__directions"] = T(rb.directions)
+    np.savez_compressed(os.path.join(HERE, "ref_prevnext.npz"), **store)
 
 
 if __name__ == "__main__":

@@ -1082,3 +1082,30 @@ def test_one_sided_batches(dev, rgb_frac):
     loss.backward()
     g = p._model.field.mlp_head.layers[2].weight.grad
     assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+
+
+def test_prev_next_camera_sets_reference_golden(dev):
+    """PrevNextRayGenerator + PrevNextCamOptimizer mirrors (ray kernel + pose-delta kernel) against the reference's classes."""
+    import types
+    from lsenerf_b200.lse_cameras import EdCameras
+    from lsenerf_b200.lse_ray_generator import PrevNextRayGenerator
+    from lsenerf_b200.ns_camera_optimizer import PrevNextCamOptimizer
+    z = _ref("prevnext")
+    H, W = (int(v) for v in z["hw"])
+    fx, fy, cx, cy = (float(v) for v in z["intr"])
+    cams = {n: EdCameras(torch.from_numpy(z[f"{n}_c2w"]), fx, fy, cx, cy, W, H, times=torch.from_numpy(z[f"times_{n}"])).to(dev) for n in ("prev", "next")}
+    idx = torch.from_numpy(z["pn_idx"]).to(dev)
+    opt = PrevNextCamOptimizer(types.SimpleNamespace(mode="SO3xR3", scheme="none", delay_cnt=0), z["prev_c2w"].shape[0], device=dev).to(dev)
+    with torch.no_grad():
+        opt.prev_optim.pose_adjustment.copy_(torch.from_numpy(z["pose_prev"])); opt.next_optim.pose_adjustment.copy_(torch.from_numpy(z["pose_next"]))
+        pb, nb = PrevNextRayGenerator(cams["prev"], cams["next"])(idx)
+        for name, rb in (("prev", pb), ("next", nb)):
+            np.testing.assert_allclose(rb.origins.cpu().numpy(), z[f"raw_{name}__origins"], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(rb.directions.cpu().numpy(), z[f"raw_{name}__directions"], rtol=0, atol=1e-5)
+            np.testing.assert_array_equal(rb.camera_indices.cpu().numpy(), z[f"raw_{name}__camera_indices"])
+            np.testing.assert_array_equal(rb.times.cpu().numpy(), z[f"raw_{name}__times"])
+        opt.apply_to_raybundle(pb); opt.apply_to_raybundle(nb)
+        for name, rb in (("prev", pb), ("next", nb)):
+            np.testing.assert_allclose(rb.origins.cpu().numpy(), z[f"adj_{name}__origins"], rtol=0, atol=2e-6)
+            np.testing.assert_allclose(rb.directions.cpu().numpy(), z[f"adj_{name}__directions"], rtol=0, atol=1e-5)
+    assert opt.cnt_call == 0

@@ -417,3 +417,19 @@ def test_oracle_training_step_matches_reference_glue():
     close(ld["rgb_loss"], float(z["rgb_loss"]), rtol=1e-5)
     close(ld["event_loss"], float(z["event_loss"]), rtol=1e-5)
     assert outs["prev_out"]["rgb"].shape == (8, 3)       # the deblur group mean hits every bundle whose ray count divides by 4
+
+
+def test_oracle_prev_next_camera_sets_match_reference():
+    """PrevNextRayGenerator + PrevNextCamOptimizer (explicit prev / next camera sets, one pose-delta table each, picked by call parity)."""
+    from oracle import cameras as OC
+    z = gold("prevnext")
+    idx, intr = t(z["pn_idx"]), tuple(z["intr"].tolist())
+    for name in ("prev", "next"):
+        o, d, _, _ = OC.rays_from_c2w(t(z[f"{name}_c2w"])[idx[:, 0]], OC.pixel_coords(idx), *intr)
+        close(o, z[f"raw_{name}__origins"], rtol=0, atol=0); close(d, z[f"raw_{name}__directions"], rtol=1e-6, atol=1e-7)
+        assert torch.equal(idx[:, :1], t(z[f"raw_{name}__camera_indices"]))
+        close(t(z[f"times_{name}"])[idx[:, 0]], z[f"raw_{name}__times"], rtol=0, atol=0)
+        o2, d2 = OP.apply_pose_adjustment(t(z[f"raw_{name}__origins"]), t(z[f"raw_{name}__directions"]), t(z[f"pose_{name}"]), idx[:, 0])
+        close(o2, z[f"adj_{name}__origins"], rtol=1e-6, atol=1e-6); close(d2, z[f"adj_{name}__directions"], rtol=1e-5, atol=1e-6)
+    sel = t(z["pn_idx"])[:, 0] == 0                       # camera 0 of the "next" table has a zero delta: rays unchanged
+    assert sel.any() and np.array_equal(z["adj_next__origins"][sel.numpy()], z["raw_next__origins"][sel.numpy()])
