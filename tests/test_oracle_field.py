@@ -64,3 +64,30 @@ def test_sh_matches_closed_form():
     assert abs(o[0].item() - 0.28209479177387814) < 1e-7
     assert abs(o[6].item() - (0.9461746957575601 * 0.64 - 0.31539156525251999)) < 1e-6
     assert abs(o[10].item() - 2.890611442640554 * 0.3 * -0.5 * 0.8) < 1e-6
+
+
+def test_sh_constants_against_scipy_real_harmonics():
+    """Independent check of the 16 restated SH polynomials / constants (nerfstudio components_from_spherical_harmonics, levels=4): on unit
+    vectors they must equal the orthonormal real spherical harmonics built from scipy's complex Y_l^m -- order m = -l..l per
+    degree, no Condon-Shortley sign.  (Pins the mathematics, i.e. guards against a mistyped constant shared by oracle and kernel;
+    the reference's own convention stays third-party, oracle/__init__.py.)"""
+    import numpy as np
+    import torch
+    from scipy.special import sph_harm_y
+    from oracle import field as OF
+    g = np.random.RandomState(0)
+    v = g.randn(500, 3); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    theta, phi = np.arccos(np.clip(v[:, 2], -1, 1)), np.arctan2(v[:, 1], v[:, 0])
+    cols = []
+    for l in range(4):
+        for m in range(-l, l + 1):
+            Y = sph_harm_y(l, abs(m), theta, phi)
+            if m == 0:
+                cols.append(Y.real)
+            elif m > 0:
+                cols.append(np.sqrt(2.0) * (-1) ** m * Y.real)
+            else:
+                cols.append(np.sqrt(2.0) * (-1) ** m * Y.imag)
+    want = np.stack(cols, axis=1)
+    got = OF.sh_deg4(torch.from_numpy(v)).numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-7)
