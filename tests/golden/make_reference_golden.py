@@ -32,6 +32,9 @@ reference itself does around them: argument order, shapes, index conventions, ma
                        reference's LinearRenderer, mappers, GlobalEmbedding, LSEField and LSEOccGridEstimator.sampling on the bundles of
                        ref_next_train.npz (stand-ins: VolumetricSampler, Field.forward / density_fn, RGB / depth / accumulation renderers,
                        nerfacc.pack_info / render_weight_from_density / accumulate_along_rays from oracle/nerfacc.py)
+  ref_eval_frame.npz   one full frame in eval mode: EdCameras.generate_rays(camera_indices=int) (all pixels, [H,W] batch shape) ->
+                       LSENeRFModel.forward with model / sampler / field in eval mode (no jitter, no culling, eval embedding, ev branch
+                       on, final clamp to [0,1]); same stand-ins as ref_train_step, image_coords = (y, x)
   ref_prevnext.npz     PrevNextRayGenerator.forward + PrevNextCamOptimizer.apply_to_raybundle (explicit prev / next camera sets, two pose-delta
                        tables alternating by call parity; same stand-ins as ref_raygen / ref_next_train)
   ref_sampling.npz     LSEOccGridEstimator.sampling (stand-ins: traverse_grids / render_visibility_from_density from oracle/nerfacc.py; the density
@@ -692,6 +695,32 @@ def glue_goldens(R, g):
         for k, v in outs[name].items():
             store[f"{name}__{k}"] = T(v)
     np.savez_compressed(os.path.join(HERE, "ref_train_step.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- one full frame, eval mode
+    Cams.get_image_coords = lambda self, index=None: image_coords          # nerfstudio Cameras.get_image_coords with EdCameras' zero offset
+    col.set_interpolator(None)
+    with torch.no_grad():
+        frame = col.generate_rays(camera_indices=3, coords=None)
+        assert frame.origins.shape == (H, W, 3)
+        flat = Bundle(origins=frame.origins.reshape(-1, 3), directions=frame.directions.reshape(-1, 3), pixel_area=frame.pixel_area.reshape(-1, 1),
+                      camera_indices=frame.camera_indices.reshape(-1, 1), times=frame.times.reshape(-1, 1),
+                      metadata={k: v.reshape(-1, v.shape[-1]) for k, v in frame.metadata.items()})
+        m.training = False; field_self.training = False
+
+        def eval_sampler(ray_bundle, render_step_size, near_plane, far_plane, alpha_thre, cone_angle):   # VolumetricSampler, not training
+            rays_o, rays_d = ray_bundle.origins.contiguous(), ray_bundle.directions.contiguous()
+            ri, t0, t1 = LG.LSEOccGridEstimator.sampling(grid_self, rays_o, rays_d, t_min=None, t_max=None, sigma_fn=None,
+                                                         render_step_size=render_step_size, near_plane=near_plane, far_plane=far_plane,
+                                                         stratified=False, cone_angle=cone_angle, alpha_thre=alpha_thre)
+            fr = Frustums2(rays_o[ri], rays_d[ri], t0[..., None], t1[..., None], ray_bundle.pixel_area[ri])
+            return Samples2(fr, ray_bundle.camera_indices.contiguous()[ri]), ri
+        m.sampler = eval_sampler
+        out = m(flat)
+    store = dict(cam_index=3, hw=np.array([H, W]), origins=T(flat.origins), directions=T(flat.directions), times=T(flat.times),
+                 camera_indices=T(flat.camera_indices))
+    for k, v in out.items():
+        store[f"out__{k}"] = T(v)
+    np.savez_compressed(os.path.join(HERE, "ref_eval_frame.npz"), **store)
 
     # ---------------------------------------------------------------------------------------------- explicit prev / next camera sets
     g2 = torch.Generator().manual_seed(2024)          # own generator: the files above must not depend on this block

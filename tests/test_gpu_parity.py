@@ -1109,3 +1109,46 @@ def test_prev_next_camera_sets_reference_golden(dev):
             np.testing.assert_allclose(rb.origins.cpu().numpy(), z[f"adj_{name}__origins"], rtol=0, atol=2e-6)
             np.testing.assert_allclose(rb.directions.cpu().numpy(), z[f"adj_{name}__directions"], rtol=0, atol=1e-5)
     assert opt.cnt_call == 0
+
+
+def test_eval_frame_reference_golden(dev):
+    """Eval rendering of one full frame against the reference's eval-mode forward (tests/golden/ref_eval_frame.npz): the camera mirror's
+    full-frame bundle, then the CUDA model on the golden's rays -- with eval_early_stop_eps = 0 the march is the reference's sample
+    set bit for bit and the outputs agree to 1e-4; with the default (1e-6) only the invisible tail of each ray is dropped, which moves
+    no output by more than a few 1e-6."""
+    from lsenerf_b200.compat import RayBundle
+    from lsenerf_b200.lse_cameras import EdCameras
+    from test_reference_golden import next_train_scene
+    z = _ref("eval_frame")
+    H, W = (int(v) for v in z["hw"])
+    _, _, scene = next_train_scene()
+    fx, fy, cx, cy = scene["col_intr"]
+    cams = EdCameras(scene["col_c2w"].clone(), fx, fy, cx, cy, W, H, times=scene["col_times"]).to(dev)
+    with torch.no_grad():
+        frame = cams.generate_rays(camera_indices=int(z["cam_index"]))
+    assert tuple(frame.origins.shape) == (H, W, 3)
+    np.testing.assert_allclose(frame.origins.reshape(-1, 3).cpu().numpy(), z["origins"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(frame.directions.reshape(-1, 3).cpu().numpy(), z["directions"], rtol=0, atol=1e-5)
+    np.testing.assert_array_equal(frame.times.reshape(-1, 1).cpu().numpy(), z["times"])
+    np.testing.assert_array_equal(frame.camera_indices.reshape(-1, 1).cpu().numpy(), z["camera_indices"])
+    m, _, _ = _golden_model(dev, True)
+    m.eval()
+    G = lambda k: torch.from_numpy(z[k]).to(dev)
+    bundle = RayBundle(origins=G("origins").reshape(H, W, 3), directions=G("directions").reshape(H, W, 3),
+                       camera_indices=G("camera_indices").reshape(H, W, 1), times=G("times").reshape(H, W, 1), metadata={})
+    want = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("out__")}
+    for eps in (0.0, 1e-6):
+        m.config.eval_early_stop_eps = eps
+        with torch.no_grad():
+            out = m.get_outputs_for_camera_ray_bundle(bundle, chunk=H * W)
+        out = {k: v.reshape(H * W, -1).cpu() for k, v in out.items()}
+        if eps == 0.0:
+            assert torch.equal(out["num_samples_per_ray"].reshape(-1).long(), want["num_samples_per_ray"])
+            for k in ("rgb", "accumulation", "linear", "ev_linear", "ev_out"):
+                assert rel_err(out[k], want[k]) < TOL_OUT, k
+            vis = want["accumulation"][:, 0] > 0.5
+            assert rel_err(out["depth"][vis], want["depth"][vis]) < 1e-3
+        else:
+            assert int(out["num_samples_per_ray"].sum()) < 0.8 * int(want["num_samples_per_ray"].sum())
+            for k in ("rgb", "accumulation", "ev_out"):
+                assert float((out[k] - want[k]).abs().max()) < 2e-5 + TOL_OUT * float(want[k].abs().max()), k

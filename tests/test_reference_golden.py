@@ -433,3 +433,22 @@ def test_oracle_prev_next_camera_sets_match_reference():
         close(o2, z[f"adj_{name}__origins"], rtol=1e-6, atol=1e-6); close(d2, z[f"adj_{name}__directions"], rtol=1e-5, atol=1e-6)
     sel = t(z["pn_idx"])[:, 0] == 0                       # camera 0 of the "next" table has a zero delta: rays unchanged
     assert sel.any() and np.array_equal(z["adj_next__origins"][sel.numpy()], z["raw_next__origins"][sel.numpy()])
+
+
+def test_oracle_eval_frame_matches_reference_glue():
+    """A full frame in eval mode: EdCameras.generate_rays(camera_indices=int) and LSENeRFModel.forward with model / sampler / field
+    not training (no jitter, no culling, eval embedding, event branch always on, final clamp to [0,1])."""
+    from oracle import cameras as OC
+    z = gold("eval_frame")
+    _, scene, sd, cfg, grid, _, _ = train_step_inputs()
+    H, W = (int(v) for v in z["hw"])
+    c = int(z["cam_index"])
+    b = OC.full_frame_bundle(scene["col_c2w"][c], H, W, scene["col_intr"], c, float(scene["col_times"][c, 0]))
+    close(b["origins"], z["origins"], rtol=0, atol=0); close(b["directions"], z["directions"], rtol=1e-6, atol=1e-7)
+    assert torch.equal(b["camera_indices"], t(z["camera_indices"])) and torch.equal(b["times"], t(z["times"]))
+    with torch.no_grad():
+        out = OM.get_outputs(sd, cfg, grid, dict(origins=t(z["origins"]), directions=t(z["directions"])), False, False, None)
+    assert torch.equal(out["num_samples_per_ray"], t(z["out__num_samples_per_ray"]))
+    for k in ("rgb", "accumulation", "depth", "linear", "ev_linear", "ev_out"):
+        close(out[k], z[f"out__{k}"], rtol=2e-5, atol=2e-6)
+    assert float(z["out__rgb"].max()) <= 1.0 and float(z["out__rgb"].min()) >= 0.0
