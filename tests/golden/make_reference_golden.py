@@ -13,7 +13,9 @@ of an unmodified function or method of /root/reference/lse_nerf that does not ex
   ref_spline.npz       SplineCameraOptimizer: control points from cameras, get_rgb_cameras / get_evs_cameras / get_deblur_cameras
   ref_sampler.npz      EvPixelSampler.collate_image_dataset_batch (the base class's sample_method is third-party: the indices are inputs)
   ref_hashenc.npz      Ed_HashEncoding.__init__: scalings, hash_offset
-  ref_parser.npz       lse_parser.cv_to_working, Color / Events dataparsers on a formatted scene written by tests/test_parser.py
+  ref_parser.npz       lse_parser.cv_to_working, Color / Events dataparsers on a formatted scene written by tests/test_parser.py, and what
+                       lse_dataset.ColorDataset / EventFrameDataset make of their outputs (uint8 frames, event frames * e_thresh; the
+                       nerfstudio InputDataset base is a stand-in: get_image = uint8 / 255, get_data = {image_idx, image})
 
 
 "Glue" goldens -- the reference's own methods run with small FUNCTIONAL stand-ins for the third-party calls they make (the stand-ins
@@ -138,7 +140,27 @@ class _RGBRenderer(torch.nn.Module):
         return out
 
 
+class _InputDataset:
+    """stand-in for nerfstudio 0.3.2 InputDataset (no alpha / mask handling): keeps the dataparser outputs, get_image = uint8 / 255,
+    get_data = {"image_idx", "image"}."""
+
+    def __init__(self, dataparser_outputs, scale_factor=1.0):
+        self._dataparser_outputs, self.scale_factor = dataparser_outputs, scale_factor
+
+    def __len__(self):
+        return len(self._dataparser_outputs.image_filenames)
+
+    def get_image(self, image_idx):
+        return torch.from_numpy(self.get_numpy_image(image_idx).astype("float32") / 255.0)
+
+    def get_data(self, image_idx):
+        return {"image_idx": image_idx, "image": self.get_image(image_idx)}
+
+
 def load_reference():
+    ds_mod = _StubModule("nerfstudio.data.datasets.base_dataset")
+    ds_mod.InputDataset = _InputDataset
+    sys.modules["nerfstudio.data.datasets.base_dataset"] = ds_mod
     emb_mod = _StubModule("nerfstudio.field_components.embedding")
     emb_mod.Embedding = _Embedding
     sys.modules["nerfstudio.field_components.embedding"] = emb_mod
@@ -343,13 +365,22 @@ def main():
         ev.config = ecfg
         R.lse_parser.CameraParser.__init__(ev, ecfg); ev.data = Path(ecfg.data); ev.scale_factor = 1.0
         eo = ev._generate_dataparser_outputs("train")
+        LD = importlib.import_module("lse_nerf.lse_dataset")
+        cds, eds = LD.ColorDataset(co), LD.EventFrameDataset(eo)
+        col_u8 = np.stack([cds.get_numpy_image(i) for i in range(len(cds))])
+        col_d0 = cds.get_data(0)
+        evs_f32 = torch.stack([eds.get_image(i) for i in range(len(eds))])
+        evs_d1 = eds.get_data(1)
         M = np.random.RandomState(3).randn(4, 4); M[3] = [0, 0, 0, 1]
-        np.savez(os.path.join(HERE, "ref_parser.npz"), cv_in=M, cv_out=R.lse_parser.cv_to_working(M),
+        np.savez_compressed(os.path.join(HERE, "ref_parser.npz"), cv_in=M, cv_out=R.lse_parser.cv_to_working(M),
                  col_c2w=T(co.cameras.kw["camera_to_worlds"]), col_f=float(co.cameras.kw["fx"]), col_cx=float(co.cameras.kw["cx"]),
                  col_cy=float(co.cameras.kw["cy"]), col_w=int(co.cameras.kw["width"]), col_h=int(co.cameras.kw["height"]),
                  col_times=T(co.cameras.kw["times"]), col_app=np.array(co.appearance_ids), dM=T(co.dM), n_col_files=len(co.image_filenames),
                  evs_c2w=T(eo.cameras.kw["camera_to_worlds"]), evs_times=T(eo.cameras.kw["times"]), evs_app=np.array(eo.appearance_ids),
-                 events=np.asarray(eo.events), e_thresh=float(eo.e_thresh), aabb=T(co.scene_box.aabb))
+                 events=np.asarray(eo.events), e_thresh=float(eo.e_thresh), aabb=T(co.scene_box.aabb),
+                 ds_col_u8=col_u8, ds_col_data0_image=T(col_d0["image"]), ds_col_data0_app=int(col_d0["appearance_id"]), ds_n_evs=len(eds),
+                 ds_evs_f32=T(evs_f32), ds_evs_data1_image=T(evs_d1["image"]), ds_evs_data1_app=int(evs_d1["appearance_id"]),
+                 ds_evs_data1_thresh=T(evs_d1["e_thresh"]))
 
     glue_goldens(R, g)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.startswith("ref_")))

@@ -237,6 +237,14 @@ def test_parsers_match_reference():
     # the reference hands int8 event counts to EventFrameDataset, which multiplies by e_thresh on access (lse_dataset.py:84-87)
     close(eo.events, z["events"].astype(np.float32) * np.float32(z["e_thresh"]), rtol=0, atol=0)
     close(aabb.reshape(2, 3), z["aabb"], rtol=0, atol=0)
+    # what the reference's ColorDataset / EventFrameDataset hand the pixel sampler (lse_dataset.py:18-88)
+    assert np.array_equal((co.images.numpy() * 255.0).round().astype(np.uint8), z["ds_col_u8"])
+    close(co.images[0], z["ds_col_data0_image"], rtol=0, atol=0)
+    assert int(co.appearance_ids[0]) == int(z["ds_col_data0_app"])
+    assert eo.events.shape[0] == int(z["ds_n_evs"])
+    close(eo.events, z["ds_evs_f32"], rtol=0, atol=0)
+    close(eo.events[1], z["ds_evs_data1_image"], rtol=0, atol=0)
+    assert int(eo.appearance_ids[1]) == int(z["ds_evs_data1_app"]) and abs(eo.e_thresh - float(z["ds_evs_data1_thresh"][0])) < 1e-7
 
 
 # ======================================================================================================================
