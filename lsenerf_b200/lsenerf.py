@@ -62,7 +62,7 @@ class LSENeRFModelConfig:
     def __post_init__(self):  # lsenerf.py:86-99
         if self.evs_mapping_method is None or str(self.evs_mapping_method).lower() == "none":
             self.evs_mapping_method = None
-        if self.map_mode.lower() in ("none", "ev_rgb"):
+        if self.map_mode.lower() == "none":      # the default "ev_rgb" is left alone, as upstream: it matches no branch of get_outputs
             self.map_mode = "evs_rgb"
         if isinstance(self.ev_one_dim, str):
             if self.ev_one_dim.lower() in ("false", "none"):

@@ -673,6 +673,10 @@ ONE_DIM = {False: 0, None: 0, "learned": 1, "gt": 2}
 
 def epilogue_cfg(use_mapping, map_mode, rgb_mapper, evs_mapper, ev_one_dim, training, deblur, want_ev) -> _lib.LseEpilogueCfg:
     c = _lib.LseEpilogueCfg()
+    if map_mode not in MAP_MODES:
+        # e.g. the upstream default "ev_rgb": none of the branches at lsenerf.py:336-363 matches, so whatever use_mapping says the
+        # output is only clamped (and "ev_out" is absent, which makes the event loss raise KeyError upstream and here alike)
+        use_mapping, map_mode = False, "evs_rgb"
     c.use_mapping = int(bool(use_mapping)); c.map_mode = MAP_MODES[map_mode]
     c.rgb_mapper = MAPPERS[rgb_mapper] if use_mapping or map_mode == "rgb_evs" else 0
     c.evs_mapper = MAPPERS[evs_mapper] if map_mode == "co_map" else 0

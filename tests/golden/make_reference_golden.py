@@ -9,6 +9,7 @@ of an unmodified function or method of /root/reference/lse_nerf that does not ex
   ref_utils.npz        utils.to_gray / fix_datashape / fix_appearance_id / add_metadata, data_components.find_closest_idxs
   ref_mappers.npz      intensity_mappers.{GT_Mapper, IdentityMapper, Powpow}, lsenerf.{ThreeToOne, ToGrayGT}
   ref_epilogue.npz     LSENeRFModel.get_outputs (lsenerf.py:329-377) after compositing, for every map mode / flag combination used
+  ref_configs.json     defaults and __post_init__ normalisation of LSENeRFModelConfig, LSEEmbeddingConfig, CameraOptimizerConfig (own fields)
   ref_losses.npz       LSENeRFModel.get_loss_dict with log_loss and enerf_norm_loss (lsenerf.py:392-439)
   ref_spline.npz       SplineCameraOptimizer: control points from cameras, get_rgb_cameras / get_evs_cameras / get_deblur_cameras
   ref_sampler.npz      EvPixelSampler.collate_image_dataset_batch (the base class's sample_method is third-party: the indices are inputs)
@@ -264,8 +265,26 @@ def main():
                 run_case(f"evsrgb_{tag}", "evs_rgb", True, "gt", gtm, None, training, deblur, ev_out)
                 run_case(f"rgbevs_{tag}", "rgb_evs", False, "learned", pw, None, training, deblur, ev_out)
                 run_case(f"plain_{tag}", "evs_rgb", False, False, None, None, training, deblur, ev_out)
+                # the config default map_mode "ev_rgb" with mapping on: no branch matches, the output is only clamped
+                run_case(f"unmatched_{tag}", "ev_rgb", True, "gt", gtm, None, training, deblur, ev_out)
     store["cases"] = np.array(cases)
     np.savez(os.path.join(HERE, "ref_epilogue.npz"), **store)
+
+    # ---------------------------------------------------------------------------------------------- config defaults / normalisation
+    import dataclasses
+    import json
+
+    def own_fields(obj, skip=("_target", "embed_config", "col_dataparser", "evs_dataparser", "collate_fn", "col_cam_optimizer", "evs_cam_optimizer")):
+        return {f.name: getattr(obj, f.name) for f in dataclasses.fields(obj) if f.name not in skip}
+    MC = R.lsenerf.LSENeRFModelConfig
+    CO = R.ns_camera_optimizer.CameraOptimizerConfig
+    cfgs = {"model_default": own_fields(MC()),
+            "model_none_strings": own_fields(MC(evs_mapping_method="None", map_mode="None", ev_one_dim="False", rgb_loss_type="None")),
+            "model_true_string": own_fields(MC(ev_one_dim="true", evs_mapping_method="powpow", map_mode="co_map")),
+            "embedding_default": own_fields(R.lse_embeddings.LSEEmbeddingConfig()),
+            "camopt_default": own_fields(CO()), "camopt_off_delayed": own_fields(CO(mode="off", scheme="delayed", delay_cnt=7)),
+            "camopt_on_delayed": own_fields(CO(mode="SO3xR3", scheme="delayed", delay_cnt=7, optim_type="spline"))}
+    json.dump(cfgs, open(os.path.join(HERE, "ref_configs.json"), "w"), indent=1, sort_keys=True)
 
     # ---------------------------------------------------------------------------------------------- losses
     mse = torch.nn.MSELoss()

@@ -98,6 +98,7 @@ EPILOGUE_MODES = {   # name -> (map_mode, use_mapping, ev_one_dim, rgb mapper, e
     "evsrgb": ("evs_rgb", True, "gt", "gt", None),
     "rgbevs": ("rgb_evs", False, "learned", "powpow", None),
     "plain": ("evs_rgb", False, False, None, None),
+    "unmatched": ("ev_rgb", True, "gt", "gt", None),       # the config default map_mode: no branch of lsenerf.py:336-363 matches
 }
 
 
@@ -460,3 +461,34 @@ def test_oracle_eval_frame_matches_reference_glue():
     for k in ("rgb", "accumulation", "depth", "linear", "ev_linear", "ev_out"):
         close(out[k], z[f"out__{k}"], rtol=2e-5, atol=2e-6)
     assert float(z["out__rgb"].max()) <= 1.0 and float(z["out__rgb"].min()) >= 0.0
+
+
+def test_config_defaults_and_normalisation_match_reference():
+    """LSENeRFModelConfig / LSEEmbeddingConfig / CameraOptimizerConfig: defaults and __post_init__ results of the reference's dataclasses
+    (own fields; the inherited InstantNGP fields are third-party)."""
+    import dataclasses
+    import json
+    from lsenerf_b200.lse_embeddings import LSEEmbeddingConfig
+    from lsenerf_b200.lsenerf import LSENeRFModelConfig
+    from lsenerf_b200.ns_camera_optimizer import CameraOptimizerConfig
+    ref = json.load(open(os.path.join(GOLD, "ref_configs.json")))
+    mine = {"model_default": LSENeRFModelConfig(),
+            "model_none_strings": LSENeRFModelConfig(evs_mapping_method="None", map_mode="None", ev_one_dim="False", rgb_loss_type="None"),
+            "model_true_string": LSENeRFModelConfig(ev_one_dim="true", evs_mapping_method="powpow", map_mode="co_map"),
+            "embedding_default": LSEEmbeddingConfig(),
+            "camopt_default": CameraOptimizerConfig(), "camopt_off_delayed": CameraOptimizerConfig(mode="off", scheme="delayed", delay_cnt=7),
+            "camopt_on_delayed": CameraOptimizerConfig(mode="SO3xR3", scheme="delayed", delay_cnt=7, optim_type="spline")}
+    assert set(ref) == set(mine)
+    for name, obj in mine.items():
+        have = {f.name for f in dataclasses.fields(obj)}
+        assert set(ref[name]) <= have, (name, set(ref[name]) - have)
+        for k, v in ref[name].items():
+            assert getattr(obj, k) == v, (name, k, getattr(obj, k), v)
+    assert ref["model_default"]["map_mode"] == "ev_rgb"
+
+
+def test_unmatched_map_mode_is_clamp_only():
+    from lsenerf_b200 import ops
+    a = ops.epilogue_cfg(True, "ev_rgb", "gt", None, "gt", True, False, True)
+    b = ops.epilogue_cfg(False, "evs_rgb", None, None, "gt", True, False, True)
+    assert all(getattr(a, f) == getattr(b, f) for f, _ in a._fields_)
