@@ -1152,3 +1152,22 @@ def test_eval_frame_reference_golden(dev):
             assert int(out["num_samples_per_ray"].sum()) < 0.8 * int(want["num_samples_per_ray"].sum())
             for k in ("rgb", "accumulation", "ev_out"):
                 assert float((out[k] - want[k]).abs().max()) < 2e-5 + TOL_OUT * float(want[k].abs().max()), k
+
+
+@pytest.mark.parametrize("rgb_frac", [1.0, 0.0])
+def test_engine_runs_one_sided_batches(dev, rgb_frac):
+    """engine.GraphedStep with one side of the batch missing (RGB-only BAD-NeRF budget / events only): the un-fused path is captured
+    and replayed, losses stay finite, weights move."""
+    from lsenerf_b200.engine import ArenaAdam, GraphedStep
+    scene = syn.make_scene(small_spec())
+    p = syn.build_pipeline(scene, "lsenerf", num_rays=512, rgb_frac=rgb_frac, deblur=True, cam_opt=True, device=dev, seed=5, pin=False)
+    p.train()
+    opt = ArenaAdam(p.get_param_groups())
+    gs = GraphedStep(p, opt, 1, use_graph=True)
+    gs.capture(start_step=1)
+    w0 = opt.arenas["fields"].data.clone()
+    for _ in range(3):
+        loss = gs.step()
+    gs.flush(); torch.cuda.synchronize()
+    assert loss.numel() == 1 and bool(torch.isfinite(loss).all()) and float(loss.sum()) > 0
+    assert not torch.equal(w0, opt.arenas["fields"].data)
