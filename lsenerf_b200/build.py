@@ -24,6 +24,10 @@ SOURCES = ["abi.cu", "raygen.cu", "march.cu", "hashgrid.cu", "field.cu", "field_
 EXTRA = {"march.cu": ["-fmad=false"]}
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+# build-time experiments (off by default; rebuild with --force after changing one): LSE_PAIR_LOADS=1 -> field_common.cuh:gather_corners
+for _flag in ("LSE_PAIR_LOADS",):
+    if os.environ.get(_flag):
+        COMMON += [f"-D{_flag}={os.environ[_flag]}"]
 
 
 def _nvcc() -> str:

@@ -105,6 +105,38 @@ __device__ __forceinline__ void load_geom(int64_t i, const float *__restrict__ o
     contract_normalize(g.p, g.x, g.cc);
 }
 
+// The 8 corner rows of one level.
+// LSE_PAIR_LOADS (build-time experiment, off by default; `LSE_PAIR_LOADS=1 python -m lsenerf_b200.build --force`): the x term enters the
+// hash unmultiplied, so the x and x+1 corners of a cell land on idx and idx ^ 1 -- the two halves of one 16-byte slot -- whenever
+// floor(x) is even.  One LDG.128 then serves both corners of such a lane: 4 loads instead of 8, the same values.  The gathers are
+// bound by L1TEX wavefronts (lines touched per warp-wide load), which this cuts by a quarter at the fine levels.
+#ifndef LSE_PAIR_LOADS
+#define LSE_PAIR_LOADS 0
+#endif
+#if LSE_PAIR_LOADS
+__device__ __forceinline__ void gather_corners(const float2 *__restrict__ tl, const HashCell &h, float (&F)[8][2])
+{
+    if ((h.idx[0] ^ h.idx[3]) == 1u) {       // == (ceil_x ^ floor_x) & mask for all four x-pairs: ceil_x = floor_x + 1, floor_x even
+        const float4 *__restrict__ tl4 = reinterpret_cast<const float4 *>(tl);
+        constexpr int PC[4] = {0, 1, 4, 5}, PF[4] = {3, 2, 7, 6};   // (ceil_x, floor_x) corner of each (y, z) combination
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t jf = h.idx[PF[q]];
+            const float4 v = __ldg(tl4 + (jf >> 1));
+            const bool odd = (jf & 1u) != 0u;
+            F[PF[q]][0] = odd ? v.z : v.x; F[PF[q]][1] = odd ? v.w : v.y;
+            F[PC[q]][0] = odd ? v.x : v.z; F[PC[q]][1] = odd ? v.y : v.w;
+        }
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float2 v = __ldg(tl + h.idx[c]);
+        F[c][0] = v.x; F[c][1] = v.y;
+    }
+}
+#endif
+
 __device__ __forceinline__ void encode(const float x[3], const float2 *__restrict__ table, const float *__restrict__ s_scal,
                                        int log2_T, float (&feat)[NF])
 {
@@ -115,11 +147,15 @@ __device__ __forceinline__ void encode(const float x[3], const float2 *__restric
         hash_cell(x, s_scal[l], mask, h);
         const float2 *__restrict__ tl = table + ((size_t)l << log2_T);
         float F[8][2];
+#if LSE_PAIR_LOADS
+        gather_corners(tl, h, F);
+#else
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float2 v = __ldg(tl + h.idx[c]);
             F[c][0] = v.x; F[c][1] = v.y;
         }
+#endif
         float o[2];
         hash_blend(F, h, o);
         feat[2 * l] = o[0]; feat[2 * l + 1] = o[1];

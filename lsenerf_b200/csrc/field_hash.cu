@@ -56,8 +56,12 @@ __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, co
             hash_cell(g.x, s_scal[l], mask, h);
             const float2 *__restrict__ tl = table + ((size_t)l << P.log2_T);
             float F[8][2];
+#if LSE_PAIR_LOADS
+            gather_corners(tl, h, F);
+#else
 #pragma unroll
             for (int c = 0; c < 8; ++c) { float2 v = __ldg(tl + h.idx[c]); F[c][0] = v.x; F[c][1] = v.y; }
+#endif
             float o[2];
             hash_blend(F, h, o);
             o2[(size_t)l * S_cap] = make_float2(o[0], o[1]);
