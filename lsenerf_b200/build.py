@@ -24,8 +24,9 @@ SOURCES = ["abi.cu", "raygen.cu", "march.cu", "hashgrid.cu", "field.cu", "field_
 EXTRA = {"march.cu": ["-fmad=false"]}
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-# build-time experiments (off by default; rebuild with --force after changing one): LSE_PAIR_LOADS=1 -> field_common.cuh:gather_corners
-for _flag in ("LSE_PAIR_LOADS",):
+# build-time experiments (off by default; rebuild with --force after changing one): LSE_PAIR_LOADS=1 -> field_common.cuh:gather_corners,
+# LSE_PAIR_REDS=1 -> field_hash.cu:scatter_samples_kernel
+for _flag in ("LSE_PAIR_LOADS", "LSE_PAIR_REDS"):
     if os.environ.get(_flag):
         COMMON += [f"-D{_flag}={os.environ[_flag]}"]
 

@@ -70,6 +70,12 @@ __device__ __forceinline__ void red_add2(float *addr, float a, float b)
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+// ... of four adjacent floats, 16-byte aligned (RED.ADD.V4.F32 on sm_90+)
+__device__ __forceinline__ void red_add4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 }  // namespace lse
 
 #define LSE_CHECK_ARG(cond, msg)                    \

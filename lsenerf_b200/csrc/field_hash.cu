@@ -25,6 +25,9 @@ int simt_density_bwd(const LseFieldParams &P, const LseFieldGrads &G, const floa
                      cudaStream_t st);
 
 constexpr int HT = 256;   // threads per CTA of the hash kernels
+#ifndef LSE_PAIR_REDS
+#define LSE_PAIR_REDS 0
+#endif
 
 // JAC: also store d(feat)/d(grid coordinate) -- 2 features x 3 axes per level, already multiplied by the level's scale, 96 floats per
 // sample -- computed from the corner values this kernel has in registers anyway.  The position-gradient kernel then needs no
@@ -151,6 +154,45 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
                 const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
                 const bool head = lane == 0 || p0 != k0 || p1 != k1;
                 const uint32_t heads = __ballot_sync(0xffffffffu, head);
+#if LSE_PAIR_REDS
+                // build-time experiment (off by default, see gather_corners in field_common.cuh): the x / x+1 corners of a cell are the
+                // two halves of one 16-byte slot when floor(x) is even -> one RED.ADD.V4.F32 instead of two RED.ADD.V2.F32.  `pair` is a
+                // function of the corner rows, hence uniform over a run of equal keys.
+                const bool pair = ((hc.idx[0] ^ hc.idx[3]) == 1u);
+                constexpr int PC[4] = {0, 1, 4, 5}, PF[4] = {3, 2, 7, 6};
+                if (__popc(heads) <= 20) {
+                    const int last = run_last_lane(heads, lane);
+                    const int max_len = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last - lane + 1));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float ac = run_sum(w[PC[q]] * gl[0], lane, last, max_len), bc = run_sum(w[PC[q]] * gl[1], lane, last, max_len);
+                        const float af = run_sum(w[PF[q]] * gl[0], lane, last, max_len), bf = run_sum(w[PF[q]] * gl[1], lane, last, max_len);
+                        if (head && live) {
+                            const uint32_t jf = hc.idx[PF[q]];
+                            if (pair) {
+                                if (jf & 1u) red_add4(dtl + 4 * (size_t)(jf >> 1), ac, bc, af, bf);
+                                else red_add4(dtl + 4 * (size_t)(jf >> 1), af, bf, ac, bc);
+                            } else {
+                                red_add2(dtl + 2 * (size_t)hc.idx[PC[q]], ac, bc);
+                                red_add2(dtl + 2 * (size_t)jf, af, bf);
+                            }
+                        }
+                    }
+                } else if (live) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float ac = w[PC[q]] * gl[0], bc = w[PC[q]] * gl[1], af = w[PF[q]] * gl[0], bf = w[PF[q]] * gl[1];
+                        const uint32_t jf = hc.idx[PF[q]];
+                        if (pair) {
+                            if (jf & 1u) red_add4(dtl + 4 * (size_t)(jf >> 1), ac, bc, af, bf);
+                            else red_add4(dtl + 4 * (size_t)(jf >> 1), af, bf, ac, bc);
+                        } else {
+                            red_add2(dtl + 2 * (size_t)hc.idx[PC[q]], ac, bc);
+                            red_add2(dtl + 2 * (size_t)jf, af, bf);
+                        }
+                    }
+                }
+#else
                 if (__popc(heads) <= 20) {          // coarse level: few cells per warp -> one reduction per run
                     const int last = run_last_lane(heads, lane);
                     const int max_len = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last - lane + 1));
@@ -163,6 +205,7 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
 #pragma unroll
                     for (int c = 0; c < 8; ++c) red_add2(dtl + 2 * (size_t)hc.idx[c], w[c] * gl[0], w[c] * gl[1]);
                 }
+#endif
             }
             if (want_dx) {
                 const float2 *__restrict__ tl = table + ((size_t)l << P.log2_T);
