@@ -13,7 +13,8 @@ import re
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblsenerf_b200.so")
+# LSE_B200_LIB: another build of the same library (lsenerf_b200.build --variant ...), for A/B runs of build-time experiments
+LIB_PATH = os.environ.get("LSE_B200_LIB") or os.path.join(HERE, "liblsenerf_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "lsenerf_b200.h")
 
 

@@ -1,6 +1,6 @@
 """Build liblsenerf_b200.so (the C-ABI library of sm_100a kernels) in-tree with nvcc.
 
-    python -m lsenerf_b200.build [--force] [--verbose]
+    python -m lsenerf_b200.build [--force] [--verbose] [--variant NAME]
 
 Each .cu is compiled to an object with ``-gencode arch=compute_100a,code=sm_100a -lineinfo`` (objects cached by
 mtime) and linked into ``lsenerf_b200/liblsenerf_b200.so``.  ``march.cu`` is compiled with ``-fmad=false``: the
@@ -46,8 +46,8 @@ def _deps_mtime() -> float:
     return m
 
 
-def _compile(src: str, force: bool, verbose: bool) -> str:
-    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+def _compile(src: str, force: bool, verbose: bool, obj_dir: str = OBJ) -> str:
+    obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
     spath = os.path.join(CSRC, src)
     newest = max(os.path.getmtime(spath), _deps_mtime())
     if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
@@ -64,17 +64,22 @@ def _compile(src: str, force: bool, verbose: bool) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJ, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """variant: build into lsenerf_b200/_obj_<variant>/ -> liblsenerf_b200_<variant>.so next to the default library (A/B runs of the
+    build-time experiments: `LSE_PAIR_LOADS=1 python -m lsenerf_b200.build --variant pair`, then `LSE_B200_LIB=.../liblsenerf_b200_pair.so`)."""
+    obj_dir = OBJ + (f"_{variant}" if variant else "")
+    lib = LIB.replace(".so", f"_{variant}.so") if variant else LIB
+    os.makedirs(obj_dir, exist_ok=True)
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, force, verbose), SOURCES))
-    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+        objs = list(ex.map(lambda s: _compile(s, force, verbose, obj_dir), SOURCES))
+    if force or not os.path.exists(lib) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
+        cmd = [_nvcc(), "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=_variant))
