@@ -457,6 +457,12 @@ def run_b200(args):
             r.update({"traffic": sum(t["dram_bytes_per_launch"] for t in tr) if tr else None,
                       "traffic_source": tr[0].get("source") if tr else None, "launches_per_step": round(n_call, 2),
                       "peak_source": which, "ms_per_launch": per_call[kname], "share_of_step": per_step[kname] / sum(per_step.values())})
+            # tensor kernels: the utilisation ncu saw in the same capture `traffic` comes from (sm__pipe_tensor_cycles_active, % of peak).
+            # `frac` counts ALGORITHMIC fp32 flops against the dense bf16 peak; the pipe itself issues 3 split MMAs per product on
+            # padded tiles, which is why it is busier than `frac` says.
+            tp = [t.get("tensor_pipe_active_pct") for t in tr if isinstance(t, dict) and t.get("tensor_pipe_active_pct")]
+            if r["bound"] == "tensor" and tp:
+                r["tensor_pipe_active_pct"] = max(tp)
             return r
         candidates = [k for k in list(alg_bytes) + list(alg_flops) if k in per_call]
         roof_k = max((k for k in candidates if k in alg_bytes), key=lambda k: per_step[k])

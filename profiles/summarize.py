@@ -78,11 +78,14 @@ def main():
             d = nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum")
             for kern in TRAFFIC_KERNELS:
                 if kern in name:
-                    t = traffic.setdefault(kern, {"dram_bytes_per_launch": 0.0, "launches": 0})
+                    t = traffic.setdefault(kern, {"dram_bytes_per_launch": 0.0, "launches": 0, "tensor_pipe_active_pct": 0.0})
                     t["dram_bytes_per_launch"] += d
                     t["launches"] += 1
+                    tp = vals.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+                    t["tensor_pipe_active_pct"] += float(tp[0].replace(",", "")) if tp else 0.0
     for t in traffic.values():
         t["dram_bytes_per_launch"] /= max(t["launches"], 1)
+        t["tensor_pipe_active_pct"] /= max(t["launches"], 1)   # sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active, mean
         t["source"] = f"profiles/{tag}_kernels_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches of one ncu --set full run)"
     with open(os.path.join(here, f"{tag}_ncu_traffic.json"), "w") as fh:
         json.dump(traffic, fh, indent=1)
