@@ -91,3 +91,33 @@ def test_sh_constants_against_scipy_real_harmonics():
     want = np.stack(cols, axis=1)
     got = OF.sh_deg4(torch.from_numpy(v)).numpy()
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-7)
+
+
+def test_x_corner_pairs_share_a_16_byte_slot():
+    """The index fact behind the LSE_PAIR_LOADS / LSE_PAIR_REDS build-time experiments (field_common.cuh:gather_corners,
+    field_hash.cu:scatter_samples_kernel): the x term enters the hash unmultiplied, so whenever (idx[0] ^ idx[3]) == 1 every
+    (ceil_x, floor_x) corner pair -- (0,3), (1,2), (4,7), (5,6) -- sits on rows j ^ 1 and j of the level's table, i.e. in the two halves of
+    the 16-byte slot j >> 1; this happens for about half of the samples at fine levels."""
+    import torch
+    from oracle import field as OF
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(20000, 3, generator=g)
+    x[:64] = torch.randint(0, 16, (64, 3), generator=g).float() / 16.0          # lattice points: ceil == floor, no pair
+    T = 2**19
+    idx, _ = OF.hash_corner_indices(x, OF.hash_scalings(), T)
+    idx = idx - (torch.arange(16) * T)[None, :, None]                              # rows inside each level's sub-table
+    assert int(idx.min()) >= 0 and int(idx.max()) < T
+    pair = (idx[..., 0] ^ idx[..., 3]) == 1
+    for c, f in ((0, 3), (1, 2), (4, 7), (5, 6)):
+        assert bool(((idx[..., c] ^ idx[..., f]) == 1)[pair].all())
+        assert bool(((idx[..., c] >> 1) == (idx[..., f] >> 1))[pair].all())
+        assert not bool(((idx[..., c] ^ idx[..., f]) == 1)[~pair].any())
+    frac = pair[:, 8:].float().mean().item()
+    assert 0.45 < frac < 0.55, frac
+    # reading the slot as 4 floats and picking halves by the row's low bit returns the rows themselves
+    table = torch.rand(T, 2, generator=g)
+    slots = table.view(T // 2, 4)
+    jf, jc = idx[..., 15, 3][pair[:, 15]], idx[..., 15, 0][pair[:, 15]]
+    v = slots[jf >> 1]
+    odd = (jf & 1).bool()[:, None]
+    assert torch.equal(torch.where(odd, v[:, 2:], v[:, :2]), table[jf]) and torch.equal(torch.where(odd, v[:, :2], v[:, 2:]), table[jc])
