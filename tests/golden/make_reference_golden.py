@@ -284,6 +284,19 @@ def main():
             "embedding_default": own_fields(R.lse_embeddings.LSEEmbeddingConfig()),
             "camopt_default": own_fields(CO()), "camopt_off_delayed": own_fields(CO(mode="off", scheme="delayed", delay_cnt=7)),
             "camopt_on_delayed": own_fields(CO(mode="SO3xR3", scheme="delayed", delay_cnt=7, optim_type="spline"))}
+    # the four shipped experiments: exp_configs/*.sh on top of the DEFAULT CONFIGS block of scripts/train_evimo.sh (plain KEY=VALUE shell)
+    import re
+
+    def shell_vars(path, start=None, stop=None):
+        text = open(path).read()
+        if start is not None:
+            text = text[text.index(start):text.index(stop)]
+        return {m.group(1): m.group(2) for m in re.finditer(r"^([A-Za-z_]+)=([^\s#]*)", text, flags=re.M)}
+    defaults = shell_vars("/root/reference/scripts/train_evimo.sh", "DEFAULT CONFIGS", "END DEFAULT CONFIGS")
+    flags = open("/root/reference/scripts/train_evimo.sh").read()
+    defaults["exp_t"] = re.search(r"col-cam-optimizer\.exp-t (\d+)", flags).group(1)
+    cfgs["experiments"] = {name: {**defaults, **shell_vars(f"/root/reference/exp_configs/{name}.sh")}
+                           for name in ("lsenerf_config", "lsenerf_emb_config", "BADNERF_config", "BADNERF_emb_config")}
     json.dump(cfgs, open(os.path.join(HERE, "ref_configs.json"), "w"), indent=1, sort_keys=True)
 
     # ---------------------------------------------------------------------------------------------- losses

@@ -492,3 +492,29 @@ def test_unmatched_map_mode_is_clamp_only():
     a = ops.epilogue_cfg(True, "ev_rgb", "gt", None, "gt", True, False, True)
     b = ops.epilogue_cfg(False, "evs_rgb", None, None, "gt", True, False, True)
     assert all(getattr(a, f) == getattr(b, f) for f, _ in a._fields_)
+
+
+def test_shipped_experiments_match_reference_scripts():
+    """lse_config.experiment(name) against the flags the reference's exp_configs/*.sh + scripts/train_evimo.sh pass to `train.py lsenerf`
+    (parsed into ref_configs.json by the generator)."""
+    import json
+    from lsenerf_b200.lse_config import experiment
+    from lsenerf_b200.lsenerf import LSENeRFModelConfig
+    ref = json.load(open(os.path.join(GOLD, "ref_configs.json")))["experiments"]
+    names = {"lsenerf": "lsenerf_config", "lsenerf_emb": "lsenerf_emb_config", "badnerf": "BADNERF_config", "badnerf_emb": "BADNERF_emb_config"}
+    for mine, theirs in names.items():
+        f = ref[theirs]
+        dm, model = experiment(mine)
+        # what the reference's dataclass makes of the same command-line strings
+        want = LSENeRFModelConfig(use_mapping=f["use_map"] == "True", mapping_method=f["mapping_method"], map_mode=f["map_mode"],
+                                  evs_mapping_method=f["evs_mapping_method"], ev_one_dim=f["ev_one"], rgb_loss_type=f["rgb_loss_fn"],
+                                  event_loss_type=f["evs_loss_fn"], evs_loss_weight=float(f["evs_w"]))
+        for k in ("use_mapping", "mapping_method", "map_mode", "evs_mapping_method", "ev_one_dim", "rgb_loss_type", "event_loss_type",
+                  "evs_loss_weight"):
+            assert getattr(model, k) == getattr(want, k), (mine, k, getattr(model, k), getattr(want, k))
+        assert model.embed_config.embedding_type == f["emb_type"]
+        assert dm.rgb_frac == float(f["rgb_frac"])
+        assert dm.rgb_loss_mode == f["rgb_loss_fn"]          # train.py:295-297 hands the rgb loss mode to the datamanager as well
+        assert (dm.col_cam_optimizer.mode, dm.col_cam_optimizer.optim_type) == (f["col_cam_opt"], f["col_cam_opt_type"])
+        assert (dm.evs_cam_optimizer.mode, dm.evs_cam_optimizer.optim_type) == (f["evs_cam_opt"], f["evs_cam_opt_type"])
+        assert dm.col_cam_optimizer.exp_t == float(f["exp_t"])
