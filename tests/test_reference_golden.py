@@ -478,7 +478,7 @@ def test_config_defaults_and_normalisation_match_reference():
             "embedding_default": LSEEmbeddingConfig(),
             "camopt_default": CameraOptimizerConfig(), "camopt_off_delayed": CameraOptimizerConfig(mode="off", scheme="delayed", delay_cnt=7),
             "camopt_on_delayed": CameraOptimizerConfig(mode="SO3xR3", scheme="delayed", delay_cnt=7, optim_type="spline")}
-    assert set(ref) == set(mine)
+    assert set(ref) - {"experiments"} == set(mine)          # "experiments": test_shipped_experiments_match_reference_scripts
     for name, obj in mine.items():
         have = {f.name for f in dataclasses.fields(obj)}
         assert set(ref[name]) <= have, (name, set(ref[name]) - have)
