@@ -25,8 +25,9 @@ EXTRA = {"march.cu": ["-fmad=false"]}
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 # build-time experiments (off by default; rebuild with --force after changing one): LSE_PAIR_LOADS=1 -> field_common.cuh:gather_corners,
-# LSE_PAIR_REDS=1 -> field_hash.cu:scatter_samples_kernel
-for _flag in ("LSE_PAIR_LOADS", "LSE_PAIR_REDS"):
+# LSE_PAIR_REDS=1 -> field_hash.cu:scatter_samples_kernel, LSE_PAIR_LANES=1 -> field_common.cuh:pairlanes_level (takes precedence over
+# LSE_PAIR_LOADS in the two kernels that use it)
+for _flag in ("LSE_PAIR_LOADS", "LSE_PAIR_REDS", "LSE_PAIR_LANES"):
     if os.environ.get(_flag):
         COMMON += [f"-D{_flag}={os.environ[_flag]}"]
 

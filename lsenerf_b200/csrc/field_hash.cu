@@ -47,6 +47,41 @@ __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, co
     const int64_t S = live_count(n_dev, S_cap);
     const float2 *table = reinterpret_cast<const float2 *>(P.table);
     const uint32_t mask = (1u << P.log2_T) - 1u;
+#if LSE_PAIR_LANES
+    // build-time experiment (field_common.cuh:pairlanes_level): two lanes per sample for the gather; warp-uniform trip count
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = blockIdx.x * (int64_t)HT + (threadIdx.x & ~31); base < S; base += (int64_t)gridDim.x * HT) {
+        const int64_t i = base + lane;
+        const bool live = i < S;
+        SampleGeom g;
+        g.cc.sel = false; g.x[0] = g.x[1] = g.x[2] = 0.0f;
+        if (live) load_geom(i, origins, directions, ray_idx, t0, t1, g);
+        float xo[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xo[k] = __shfl_xor_sync(0xffffffffu, g.x[k], 1);
+        float2 *o2 = reinterpret_cast<float2 *>(feat) + i;
+        float2 *j2 = JAC ? reinterpret_cast<float2 *>(jac) + i : nullptr;
+#pragma unroll 4
+        for (int l = 0; l < NL; ++l) {
+            float o[2], j[6];
+            pairlanes_level<JAC>(g.x, xo, table + ((size_t)l << P.log2_T), s_scal[l], mask, o, j);
+            if (live) {
+                o2[(size_t)l * S_cap] = make_float2(o[0], o[1]);
+                if (JAC) {
+                    const float sc = s_scal[l];
+                    j2[(size_t)(3 * l) * S_cap] = make_float2(j[0] * sc, j[1] * sc);
+                    j2[(size_t)(3 * l + 1) * S_cap] = make_float2(j[2] * sc, j[3] * sc);
+                    j2[(size_t)(3 * l + 2) * S_cap] = make_float2(j[4] * sc, j[5] * sc);
+                }
+            }
+        }
+        if (live) {
+            const float gs = d_sigma ? d_sigma[i] : 0.0f;
+            dout0[i] = g.cc.sel ? gs * expf(fminf(fmaxf(h16[16 * i], -15.0f), 15.0f)) : 0.0f;
+            xs[3 * i] = g.x[0]; xs[3 * i + 1] = g.x[1]; xs[3 * i + 2] = g.x[2];
+        }
+    }
+#else
     for (int64_t i = blockIdx.x * (int64_t)HT + threadIdx.x; i < S; i += (int64_t)gridDim.x * HT) {
         SampleGeom g;
         load_geom(i, origins, directions, ray_idx, t0, t1, g);
@@ -83,6 +118,7 @@ __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, co
         dout0[i] = g.cc.sel ? gs * expf(fminf(fmaxf(h16[16 * i], -15.0f), 15.0f)) : 0.0f;
         xs[3 * i] = g.x[0]; xs[3 * i + 1] = g.x[1]; xs[3 * i + 2] = g.x[2];      // grid coordinates for the deferred table scatter
     }
+#endif
 }
 
 // ---- warp-aggregated reductions over runs of consecutive lanes with equal keys -----------------------------------------------
