@@ -114,6 +114,9 @@ def test_x_corner_pairs_share_a_16_byte_slot():
         assert not bool(((idx[..., c] ^ idx[..., f]) == 1)[~pair].any())
     frac = pair[:, 8:].float().mean().item()
     assert 0.45 < frac < 0.55, frac
+    # ... and the same 128-byte line (16 rows) unless floor_x ends in four one bits: the fact behind LSE_PAIR_LANES
+    same_line = ((idx[..., 0] >> 4) == (idx[..., 3] >> 4))[64:, 8:].float().mean().item()
+    assert 0.92 < same_line < 0.95, same_line
     # reading the slot as 4 floats and picking halves by the row's low bit returns the rows themselves
     table = torch.rand(T, 2, generator=g)
     slots = table.view(T // 2, 4)
