@@ -167,6 +167,13 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
             else load_geom(i, origins, directions, ray_idx, t0, t1, g);
         }
         const float2 *df2 = reinterpret_cast<const float2 *>(dfeat) + i;   // planes [16][S_cap]
+#if LSE_PAIR_LANES
+        // build-time experiment: at the fine levels two lanes share a sample (lane parity = x face, field_common.cuh:pairlanes_level)
+        float xo[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xo[k] = __shfl_xor_sync(0xffffffffu, g.x[k], 1);
+        const bool live_o = __shfl_xor_sync(0xffffffffu, (int)live, 1) != 0;
+#endif
         const bool want_dx = live && (d_origins != nullptr || d_directions != nullptr) && g.cc.sel;
         float dx[3] = {0.0f, 0.0f, 0.0f};
         // the level loop stays rolled: 16 unrolled copies of this body (19 k instructions) thrash the instruction cache
@@ -237,10 +244,37 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
                         const float a = run_sum(w[c] * gl[0], lane, last, max_len), b = run_sum(w[c] * gl[1], lane, last, max_len);
                         if (head && live) red_add2(dtl + 2 * (size_t)hc.idx[c], a, b);
                     }
-                } else if (live) {
+                }
+#if LSE_PAIR_LANES
+                else {
+                    // both reductions of an x corner pair from adjacent lanes: 15 times out of 16 they fall into one 128-byte line
+                    const bool odd = (lane & 1) != 0;
+                    const float g0o = __shfl_xor_sync(0xffffffffu, gl[0], 1), g1o = __shfl_xor_sync(0xffffffffu, gl[1], 1);
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const bool mine = (pass == 1) == odd;
+                        const float xp[3] = {mine ? g.x[0] : xo[0], mine ? g.x[1] : xo[1], mine ? g.x[2] : xo[2]};
+                        const float ga = mine ? gl[0] : g0o, gb = mine ? gl[1] : g1o;
+                        HashCell h2;
+                        hash_cell(xp, s_scal[l], mask, h2);
+                        const float wx = odd ? h2.ox : 1.0f - h2.ox, oy = h2.oy, ny = 1.0f - h2.oy, oz = h2.oz, nz = 1.0f - h2.oz;
+                        const uint32_t j0 = odd ? h2.idx[0] : h2.idx[3], j1 = odd ? h2.idx[1] : h2.idx[2];
+                        const uint32_t j2 = odd ? h2.idx[4] : h2.idx[7], j3 = odd ? h2.idx[5] : h2.idx[6];
+                        if (mine ? live : live_o) {
+                            const float w0 = wx * oy * oz, w1 = wx * ny * oz, w2 = wx * oy * nz, w3 = wx * ny * nz;   // as hash_weights
+                            red_add2(dtl + 2 * (size_t)j0, w0 * ga, w0 * gb);
+                            red_add2(dtl + 2 * (size_t)j1, w1 * ga, w1 * gb);
+                            red_add2(dtl + 2 * (size_t)j2, w2 * ga, w2 * gb);
+                            red_add2(dtl + 2 * (size_t)j3, w3 * ga, w3 * gb);
+                        }
+                    }
+                }
+#else
+                else if (live) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) red_add2(dtl + 2 * (size_t)hc.idx[c], w[c] * gl[0], w[c] * gl[1]);
                 }
+#endif
 #endif
             }
             if (want_dx) {
