@@ -92,6 +92,11 @@ int lse_march_count(const float *rays_o, const float *rays_d, int64_t n_rays, co
                     const float *jitter, float step_size, float cone_angle, int32_t *counts, lse_stream_t stream);
 /* exclusive scan of counts -> starts [n] ; total -> total_dev [1] (int32).  Also used for compaction. */
 int lse_scan_counts(const int32_t *counts, int64_t n, int32_t *starts, int32_t *total_dev, lse_stream_t stream);
+/* The same scan against a sample capacity (the reference has none: nerfacc sizes its outputs from a host read of the count): starts are
+ * clamped to cap, counts [n] are REWRITTEN so that starts[i] + counts[i] <= cap, *total_dev = min(sum, cap), and *overflow_dev
+ * (int32, may be NULL) is set to 1 when samples were dropped.  After this call no sample-level kernel can index past `cap`. */
+int lse_scan_counts_capped(int32_t *counts, int64_t n, int64_t cap, int32_t *starts, int32_t *total_dev,
+                           int32_t *overflow_dev, lse_stream_t stream);
 /* pass 2: writes ray_indices/t_starts/t_ends at starts[r]; rays whose samples would exceed S_cap are truncated
  * (overflow_dev [1] int32 set to 1). */
 int lse_march_fill(const float *rays_o, const float *rays_d, int64_t n_rays, const uint32_t *occ_bits,
@@ -314,6 +319,18 @@ int lse_adam_step_hp(float *param, const float *grad, float *exp_avg, float *exp
 int lse_adam_step_collective(void *const *peer_params, void *const *peer_grads, float *param_multicast,
                              const float *grad_multicast, float *exp_avg, float *exp_avg_sq, int64_t n, int rank, int world,
                              float beta1, float beta2, float eps, const float *hp_dev, lse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * measurement (SURVEY 8d "L2 to be measured with a resident-set microbench")
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Random gathers of vec_bytes-byte entries (4, 8 = one float2 corner, 16) from a resident set of table_bytes (power of two):
+ * 148 * ctas_per_sm CTAs of 256 threads, 8 independent loads in flight per thread, `iters` rounds; coherent != 0 makes the lanes
+ * of a warp read 32 consecutive entries (the coarse-level pattern).  loads_out (host pointer, may be NULL) receives the number of
+ * loads issued; the caller times the launch with CUDA events: GB/s = loads * vec_bytes / t.  The denominator bench.py reports
+ * the hash-gather kernels against, next to the HBM copy peak. */
+int lse_gather_microbench(const void *table, int64_t table_bytes, int vec_bytes, int iters, int coherent, int ctas_per_sm,
+                          float *sink, int64_t *loads_out, lse_stream_t stream);
 
 #ifdef __cplusplus
 }

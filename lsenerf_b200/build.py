@@ -20,17 +20,10 @@ LIB = os.path.join(HERE, "liblsenerf_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "lsenerf_b200.h")
 
 SOURCES = ["abi.cu", "raygen.cu", "march.cu", "hashgrid.cu", "field.cu", "field_simt.cu", "field_tc.cu", "field_tc_bwd.cu", "field_hash.cu",
-           "composite.cu", "loss.cu", "adam_collective.cu"]
+           "composite.cu", "loss.cu", "adam_collective.cu", "microbench.cu"]
 EXTRA = {"march.cu": ["-fmad=false"]}
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-# build-time experiments (off by default; rebuild with --force after changing one): LSE_PAIR_LOADS=1 -> field_common.cuh:gather_corners,
-# LSE_PAIR_REDS=1 -> field_hash.cu:scatter_samples_kernel, LSE_PAIR_LANES=1 -> field_common.cuh:pairlanes_level (takes precedence over
-# LSE_PAIR_LOADS in the two kernels that use it)
-for _flag in ("LSE_PAIR_LOADS", "LSE_PAIR_REDS", "LSE_PAIR_LANES"):
-    if os.environ.get(_flag):
-        COMMON += [f"-D{_flag}={os.environ[_flag]}"]
-
+          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("NVCC_EXTRA", "").split()
 
 def _nvcc() -> str:
     for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
@@ -66,8 +59,8 @@ def _compile(src: str, force: bool, verbose: bool, obj_dir: str = OBJ) -> str:
 
 
 def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
-    """variant: build into lsenerf_b200/_obj_<variant>/ -> liblsenerf_b200_<variant>.so next to the default library (A/B runs of the
-    build-time experiments: `LSE_PAIR_LOADS=1 python -m lsenerf_b200.build --variant pair`, then `LSE_B200_LIB=.../liblsenerf_b200_pair.so`)."""
+    """variant: build into lsenerf_b200/_obj_<variant>/ -> liblsenerf_b200_<variant>.so next to the default library, for A/B runs of
+    an experimental build (`NVCC_EXTRA="-DFOO=1" python -m lsenerf_b200.build --variant foo`, then `LSE_B200_LIB=.../liblsenerf_b200_foo.so`)."""
     obj_dir = OBJ + (f"_{variant}" if variant else "")
     lib = LIB.replace(".so", f"_{variant}.so") if variant else LIB
     os.makedirs(obj_dir, exist_ok=True)

@@ -25,9 +25,6 @@ int simt_density_bwd(const LseFieldParams &P, const LseFieldGrads &G, const floa
                      cudaStream_t st);
 
 constexpr int HT = 256;   // threads per CTA of the hash kernels
-#ifndef LSE_PAIR_REDS
-#define LSE_PAIR_REDS 0
-#endif
 
 // JAC: also store d(feat)/d(grid coordinate) -- 2 features x 3 axes per level, already multiplied by the level's scale, 96 floats per
 // sample -- computed from the corner values this kernel has in registers anyway.  The position-gradient kernel then needs no
@@ -47,41 +44,6 @@ __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, co
     const int64_t S = live_count(n_dev, S_cap);
     const float2 *table = reinterpret_cast<const float2 *>(P.table);
     const uint32_t mask = (1u << P.log2_T) - 1u;
-#if LSE_PAIR_LANES
-    // build-time experiment (field_common.cuh:pairlanes_level): two lanes per sample for the gather; warp-uniform trip count
-    const int lane = threadIdx.x & 31;
-    for (int64_t base = blockIdx.x * (int64_t)HT + (threadIdx.x & ~31); base < S; base += (int64_t)gridDim.x * HT) {
-        const int64_t i = base + lane;
-        const bool live = i < S;
-        SampleGeom g;
-        g.cc.sel = false; g.x[0] = g.x[1] = g.x[2] = 0.0f;
-        if (live) load_geom(i, origins, directions, ray_idx, t0, t1, g);
-        float xo[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) xo[k] = __shfl_xor_sync(0xffffffffu, g.x[k], 1);
-        float2 *o2 = reinterpret_cast<float2 *>(feat) + i;
-        float2 *j2 = JAC ? reinterpret_cast<float2 *>(jac) + i : nullptr;
-#pragma unroll 4
-        for (int l = 0; l < NL; ++l) {
-            float o[2], j[6];
-            pairlanes_level<JAC>(g.x, xo, table + ((size_t)l << P.log2_T), s_scal[l], mask, o, j);
-            if (live) {
-                o2[(size_t)l * S_cap] = make_float2(o[0], o[1]);
-                if (JAC) {
-                    const float sc = s_scal[l];
-                    j2[(size_t)(3 * l) * S_cap] = make_float2(j[0] * sc, j[1] * sc);
-                    j2[(size_t)(3 * l + 1) * S_cap] = make_float2(j[2] * sc, j[3] * sc);
-                    j2[(size_t)(3 * l + 2) * S_cap] = make_float2(j[4] * sc, j[5] * sc);
-                }
-            }
-        }
-        if (live) {
-            const float gs = d_sigma ? d_sigma[i] : 0.0f;
-            dout0[i] = g.cc.sel ? gs * expf(fminf(fmaxf(h16[16 * i], -15.0f), 15.0f)) : 0.0f;
-            xs[3 * i] = g.x[0]; xs[3 * i + 1] = g.x[1]; xs[3 * i + 2] = g.x[2];
-        }
-    }
-#else
     for (int64_t i = blockIdx.x * (int64_t)HT + threadIdx.x; i < S; i += (int64_t)gridDim.x * HT) {
         SampleGeom g;
         load_geom(i, origins, directions, ray_idx, t0, t1, g);
@@ -94,12 +56,8 @@ __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, co
             hash_cell(g.x, s_scal[l], mask, h);
             const float2 *__restrict__ tl = table + ((size_t)l << P.log2_T);
             float F[8][2];
-#if LSE_PAIR_LOADS
-            gather_corners(tl, h, F);
-#else
 #pragma unroll
             for (int c = 0; c < 8; ++c) { float2 v = __ldg(tl + h.idx[c]); F[c][0] = v.x; F[c][1] = v.y; }
-#endif
             float o[2];
             hash_blend(F, h, o);
             o2[(size_t)l * S_cap] = make_float2(o[0], o[1]);
@@ -118,7 +76,6 @@ __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, co
         dout0[i] = g.cc.sel ? gs * expf(fminf(fmaxf(h16[16 * i], -15.0f), 15.0f)) : 0.0f;
         xs[3 * i] = g.x[0]; xs[3 * i + 1] = g.x[1]; xs[3 * i + 2] = g.x[2];      // grid coordinates for the deferred table scatter
     }
-#endif
 }
 
 // ---- warp-aggregated reductions over runs of consecutive lanes with equal keys -----------------------------------------------
@@ -167,13 +124,6 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
             else load_geom(i, origins, directions, ray_idx, t0, t1, g);
         }
         const float2 *df2 = reinterpret_cast<const float2 *>(dfeat) + i;   // planes [16][S_cap]
-#if LSE_PAIR_LANES
-        // build-time experiment: at the fine levels two lanes share a sample (lane parity = x face, field_common.cuh:pairlanes_level)
-        float xo[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) xo[k] = __shfl_xor_sync(0xffffffffu, g.x[k], 1);
-        const bool live_o = __shfl_xor_sync(0xffffffffu, (int)live, 1) != 0;
-#endif
         const bool want_dx = live && (d_origins != nullptr || d_directions != nullptr) && g.cc.sel;
         float dx[3] = {0.0f, 0.0f, 0.0f};
         // the level loop stays rolled: 16 unrolled copies of this body (19 k instructions) thrash the instruction cache
@@ -197,45 +147,6 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
                 const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
                 const bool head = lane == 0 || p0 != k0 || p1 != k1;
                 const uint32_t heads = __ballot_sync(0xffffffffu, head);
-#if LSE_PAIR_REDS
-                // build-time experiment (off by default, see gather_corners in field_common.cuh): the x / x+1 corners of a cell are the
-                // two halves of one 16-byte slot when floor(x) is even -> one RED.ADD.V4.F32 instead of two RED.ADD.V2.F32.  `pair` is a
-                // function of the corner rows, hence uniform over a run of equal keys.
-                const bool pair = ((hc.idx[0] ^ hc.idx[3]) == 1u);
-                constexpr int PC[4] = {0, 1, 4, 5}, PF[4] = {3, 2, 7, 6};
-                if (__popc(heads) <= 20) {
-                    const int last = run_last_lane(heads, lane);
-                    const int max_len = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last - lane + 1));
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float ac = run_sum(w[PC[q]] * gl[0], lane, last, max_len), bc = run_sum(w[PC[q]] * gl[1], lane, last, max_len);
-                        const float af = run_sum(w[PF[q]] * gl[0], lane, last, max_len), bf = run_sum(w[PF[q]] * gl[1], lane, last, max_len);
-                        if (head && live) {
-                            const uint32_t jf = hc.idx[PF[q]];
-                            if (pair) {
-                                if (jf & 1u) red_add4(dtl + 4 * (size_t)(jf >> 1), ac, bc, af, bf);
-                                else red_add4(dtl + 4 * (size_t)(jf >> 1), af, bf, ac, bc);
-                            } else {
-                                red_add2(dtl + 2 * (size_t)hc.idx[PC[q]], ac, bc);
-                                red_add2(dtl + 2 * (size_t)jf, af, bf);
-                            }
-                        }
-                    }
-                } else if (live) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float ac = w[PC[q]] * gl[0], bc = w[PC[q]] * gl[1], af = w[PF[q]] * gl[0], bf = w[PF[q]] * gl[1];
-                        const uint32_t jf = hc.idx[PF[q]];
-                        if (pair) {
-                            if (jf & 1u) red_add4(dtl + 4 * (size_t)(jf >> 1), ac, bc, af, bf);
-                            else red_add4(dtl + 4 * (size_t)(jf >> 1), af, bf, ac, bc);
-                        } else {
-                            red_add2(dtl + 2 * (size_t)hc.idx[PC[q]], ac, bc);
-                            red_add2(dtl + 2 * (size_t)jf, af, bf);
-                        }
-                    }
-                }
-#else
                 if (__popc(heads) <= 20) {          // coarse level: few cells per warp -> one reduction per run
                     const int last = run_last_lane(heads, lane);
                     const int max_len = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last - lane + 1));
@@ -245,37 +156,10 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
                         if (head && live) red_add2(dtl + 2 * (size_t)hc.idx[c], a, b);
                     }
                 }
-#if LSE_PAIR_LANES
-                else {
-                    // both reductions of an x corner pair from adjacent lanes: 15 times out of 16 they fall into one 128-byte line
-                    const bool odd = (lane & 1) != 0;
-                    const float g0o = __shfl_xor_sync(0xffffffffu, gl[0], 1), g1o = __shfl_xor_sync(0xffffffffu, gl[1], 1);
-#pragma unroll
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const bool mine = (pass == 1) == odd;
-                        const float xp[3] = {mine ? g.x[0] : xo[0], mine ? g.x[1] : xo[1], mine ? g.x[2] : xo[2]};
-                        const float ga = mine ? gl[0] : g0o, gb = mine ? gl[1] : g1o;
-                        HashCell h2;
-                        hash_cell(xp, s_scal[l], mask, h2);
-                        const float wx = odd ? h2.ox : 1.0f - h2.ox, oy = h2.oy, ny = 1.0f - h2.oy, oz = h2.oz, nz = 1.0f - h2.oz;
-                        const uint32_t j0 = odd ? h2.idx[0] : h2.idx[3], j1 = odd ? h2.idx[1] : h2.idx[2];
-                        const uint32_t j2 = odd ? h2.idx[4] : h2.idx[7], j3 = odd ? h2.idx[5] : h2.idx[6];
-                        if (mine ? live : live_o) {
-                            const float w0 = wx * oy * oz, w1 = wx * ny * oz, w2 = wx * oy * nz, w3 = wx * ny * nz;   // as hash_weights
-                            red_add2(dtl + 2 * (size_t)j0, w0 * ga, w0 * gb);
-                            red_add2(dtl + 2 * (size_t)j1, w1 * ga, w1 * gb);
-                            red_add2(dtl + 2 * (size_t)j2, w2 * ga, w2 * gb);
-                            red_add2(dtl + 2 * (size_t)j3, w3 * ga, w3 * gb);
-                        }
-                    }
-                }
-#else
                 else if (live) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) red_add2(dtl + 2 * (size_t)hc.idx[c], w[c] * gl[0], w[c] * gl[1]);
                 }
-#endif
-#endif
             }
             if (want_dx) {
                 const float2 *__restrict__ tl = table + ((size_t)l << P.log2_T);

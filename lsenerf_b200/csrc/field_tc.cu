@@ -115,16 +115,6 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
         SampleGeom g;
         g.cc.sel = false;
         float feat[NF];
-#if LSE_PAIR_LANES
-        // build-time experiment (field_common.cuh:encode_pairlanes): two lanes per sample for the gather, all lanes take part
-        g.x[0] = g.x[1] = g.x[2] = 0.0f;
-        if (live) load_geom(i, origins, directions, ray_idx, t0, t1, g);
-        encode_pairlanes(g.x, table, smem + L::SCAL, P.log2_T, feat);
-        if (!live) {
-#pragma unroll
-            for (int j = 0; j < NF; ++j) feat[j] = 0.0f;
-        }
-#else
         if (live) {
             load_geom(i, origins, directions, ray_idx, t0, t1, g);
             encode(g.x, table, smem + L::SCAL, P.log2_T, feat);
@@ -132,7 +122,6 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
 #pragma unroll
             for (int j = 0; j < NF; ++j) feat[j] = 0.0f;
         }
-#endif
         // ---- layer 1: [128 x 32] x W1^T -> TMEM cols [0,64) ------------------------------------------------------------------
 #pragma unroll
         for (int kc = 0; kc < NF / 4; ++kc) stage4(a_hi, a_lo, WG, kc, row, feat[4 * kc], feat[4 * kc + 1], feat[4 * kc + 2], feat[4 * kc + 3]);

@@ -341,8 +341,12 @@ __global__ void march_pack_kernel(const float2 *__restrict__ slabs, int max_per_
 }
 
 // single-CTA exclusive scan (n is a ray count: 1e4 .. 1e6); 1024 threads, 4 items per thread per round.
+// cap >= 0: capacity clamp -- starts[i] = min(exclusive sum, cap), counts_rw[i] is rewritten to min(count, cap - starts[i]) and
+// total = min(sum, cap), so that no kernel downstream can index a sample slot >= cap whatever the marched total was; *overflow
+// is set when anything was dropped.
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t *__restrict__ counts, int64_t n,
-                                                           int32_t *__restrict__ starts, int32_t *__restrict__ total)
+                                                           int32_t *__restrict__ starts, int32_t *__restrict__ total,
+                                                           int64_t cap, int32_t *__restrict__ counts_rw, int32_t *__restrict__ overflow)
 {
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t carry_s;
@@ -378,14 +382,27 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t *__rest
         int32_t excl = carry + warp_tot[wid] + (inc - tsum);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (i0 + j < n) starts[i0 + j] = excl;
+            if (i0 + j < n) {
+                if (cap >= 0) {
+                    const int32_t st = (int64_t)excl < cap ? excl : (int32_t)cap;
+                    starts[i0 + j] = st;
+                    const int64_t room = cap - st;
+                    if (counts_rw && (int64_t)v[j] > room) counts_rw[i0 + j] = (int32_t)room;
+                } else {
+                    starts[i0 + j] = excl;
+                }
+            }
             excl += v[j];
         }
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = excl;  // last thread holds the running total after its 4 items
         __syncthreads();
     }
-    if (threadIdx.x == 0 && total) *total = carry_s;
+    if (threadIdx.x == 0) {
+        const bool over = cap >= 0 && (int64_t)carry_s > cap;
+        if (total) *total = over ? (int32_t)cap : carry_s;
+        if (over && overflow) *overflow = 1;
+    }
 }
 
 // ---- early-terminating culling pass ------------------------------------------------------------------------------------------
@@ -628,8 +645,17 @@ extern "C" int lse_march_pack(const float *slabs, int max_per_ray, const int32_t
 extern "C" int lse_scan_counts(const int32_t *counts, int64_t n, int32_t *starts, int32_t *total_dev, lse_stream_t stream)
 {
     if (n < 0) n = 0;
-    scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, n, starts, total_dev);
+    scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, n, starts, total_dev, -1, nullptr, nullptr);
     return check_launch("lse_scan_counts");
+}
+
+extern "C" int lse_scan_counts_capped(int32_t *counts, int64_t n, int64_t cap, int32_t *starts, int32_t *total_dev,
+                                      int32_t *overflow_dev, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(counts && starts && cap >= 0 && cap < (int64_t)INT32_MAX, "counts / starts missing or bad capacity");
+    if (n < 0) n = 0;
+    scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, n, starts, total_dev, cap, counts, overflow_dev);
+    return check_launch("lse_scan_counts_capped");
 }
 
 extern "C" int lse_march_fill(const float *rays_o, const float *rays_d, int64_t n_rays, const uint32_t *occ_bits,

@@ -288,6 +288,7 @@ class GraphedStep:
         self.step_no = 0
         self.local_only = False     # True: step this replica alone (no exchange, grad_scale 1) -- bench burn-in on rank 0
         self._loss_ring = None      # pinned host slots + events of step_async()
+        self._ovf = None            # pinned slot + event of the capacity-overflow poll
         self.side = torch.cuda.Stream(device=dm.device) if torch.cuda.is_available() else None
         self.ev_b = torch.cuda.Event() if self.side is not None else None
         self.ev_opt: Optional[torch.cuda.Event] = None        # field optimizer of the previous step (side stream)
@@ -359,6 +360,22 @@ class GraphedStep:
                 else:
                     self.optim.apply(only=[n])
 
+    def _poll_overflow(self, model) -> None:
+        """capacity flag of the march, without a per-step sync: every 16th step an asynchronous D2H copy of the sticky device
+        flag is enqueued and the copy enqueued 16 steps earlier (long complete) is inspected."""
+        if self._ovf is None:
+            self._ovf = (torch.zeros(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+            self._ovf_pending = False
+        slot, ev = self._ovf
+        if self._ovf_pending:
+            ev.synchronize()
+            if int(slot[0]):
+                raise RuntimeError("sample capacity exceeded during the last 16 steps (samples were dropped, nothing was written out "
+                                   "of bounds): raise LSENeRFModelConfig.samples_per_ray_cap")
+        slot.copy_(model._overflow, non_blocking=True)
+        ev.record()
+        self._ovf_pending = True
+
     def flush(self) -> None:
         """make the current stream wait for the field optimizer still in flight on the side stream."""
         if self.ev_opt is not None:
@@ -370,7 +387,8 @@ class GraphedStep:
         model = self.pipeline.model
         if self.step_no % 16 == 0:
             self.flush()                                 # the grid update evaluates the field: it needs the updated weights
-        model.update_occupancy(self.step_no)             # eager, every 16th step
+            self._poll_overflow(model)
+        model.update_occupancy(self.step_no, check_overflow=False)   # eager, every 16th step
         model.occupancy_grid.packed()                    # host-side version check; repacks only if binaries were edited
         if packed_dev is not None:
             self.stage.load_packed(packed_dev)

@@ -55,7 +55,7 @@ class LSENeRFPipeline(nn.Module):
                 jitter = torch.rand(len(big), device=big.origins.device)
                 S_cap = max(1, len(big) * opts.samples_per_ray_cap)
                 opts.premarched = ops.march(big.origins, big.directions, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step,
-                                            opts.cone, jitter, S_cap, opts.occ_packed)
+                                            opts.cone, jitter, S_cap, opts.occ_packed, overflow=opts.overflow)
                 ctx["opts"], ctx["jitter"] = opts, jitter
         return ctx
 

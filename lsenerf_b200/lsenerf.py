@@ -97,6 +97,9 @@ class LSENeRFModel(nn.Module):
         self.kwargs = kwargs
         self.collider = None
         self.scene_aabb = nn.Parameter(torch.as_tensor(scene_aabb, dtype=torch.float32).flatten(), requires_grad=False)
+        # sticky device flag: set by the march when a bundle needed more than R * samples_per_ray_cap sample slots (the reference
+        # has no cap).  The kernels clamp, so nothing is read or written out of bounds; check_overflow() turns it into an error.
+        self.register_buffer("_overflow", torch.zeros(1, dtype=torch.int32), persistent=False)
         self.populate_modules()
 
     @property
@@ -151,8 +154,19 @@ class LSENeRFModel(nn.Module):
     def init_test_params(self):
         self.field.embedding_appearance.init_test_params()
 
-    def update_occupancy(self, step: int):
-        """Inherited NGP BEFORE_TRAIN_ITERATION callback: occ = density * render_step_size."""
+    def check_overflow(self) -> None:
+        """raise if any render since the last check dropped samples at the packed capacity (synchronises)."""
+        if int(self._overflow.item()):
+            self._overflow.zero_()
+            raise RuntimeError(f"sample capacity exceeded (samples_per_ray_cap={self.config.samples_per_ray_cap}): samples were "
+                               "dropped from the render; raise LSENeRFModelConfig.samples_per_ray_cap")
+
+    def update_occupancy(self, step: int, check_overflow: bool = True):
+        """Inherited NGP BEFORE_TRAIN_ITERATION callback: occ = density * render_step_size.  The eager driver also
+        checks the capacity flag here (every 16th step, next to the update's own host work); the graphed engine polls it
+        asynchronously instead (engine.GraphedStep)."""
+        if check_overflow and self.training and step % 16 == 0 and self._overflow.is_cuda:
+            self.check_overflow()
         self.occupancy_grid.update_every_n_steps(step, occ_eval_fn=lambda x: self.field.density_fn(x) * self.config.render_step_size)
 
     # ---- forward ----------------------------------------------------------------------------------------------------
@@ -169,7 +183,7 @@ class LSENeRFModel(nn.Module):
             cull, eps, thre = c.eval_early_stop_eps > 0.0, c.eval_early_stop_eps, 0.0
         return ops.RenderOpts(binaries_u8=g.binaries_u8(), aabbs=g.aabbs, occ_mean_dev=g.occ_mean_dev(), occ_packed=g.packed(), near=c.near_plane,
                               far=c.far_plane, step=float(c.render_step_size), cone=c.cone_angle, alpha_thre=thre,
-                              early_stop_eps=eps, cull=cull, samples_per_ray_cap=c.samples_per_ray_cap)
+                              early_stop_eps=eps, cull=cull, samples_per_ray_cap=c.samples_per_ray_cap, overflow=self._overflow)
 
     def exec_get_outputs(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None, opts: Optional[ops.RenderOpts] = None,
                          with_depth: bool = True):

@@ -169,10 +169,15 @@ class MarchResult:
     S_cap: int
 
 
-def scan_counts(counts: Tensor):
+def scan_counts(counts: Tensor, cap: Optional[int] = None, overflow: Optional[Tensor] = None):
+    """exclusive scan -> (starts, total_dev).  With `cap` the counts are clamped IN PLACE so that starts + counts never exceeds the
+    packed capacity (and `overflow` is raised): nothing downstream can then index past the sample buffers."""
     starts = torch.empty_like(counts)
     total = torch.empty(1, dtype=torch.int32, device=counts.device)
-    call("lse_scan_counts", P(counts), counts.numel(), P(starts), P(total), stream())
+    if cap is None:
+        call("lse_scan_counts", P(counts), counts.numel(), P(starts), P(total), stream())
+    else:
+        call("lse_scan_counts_capped", P(counts), counts.numel(), int(cap), P(starts), P(total), P(overflow), stream())
     return starts, total
 
 
@@ -192,9 +197,11 @@ MAX_SAMPLES_PER_RAY = 1024   # slab slots per ray of the single-pass march (a ra
 
 
 def march(rays_o, rays_d, binaries_u8, aabbs, near, far, step, cone, jitter: Optional[Tensor], S_cap: int,
-          packed: Optional[tuple] = None, two_pass: bool = False) -> MarchResult:
+          packed: Optional[tuple] = None, two_pass: bool = False, overflow: Optional[Tensor] = None) -> MarchResult:
     """traverse_grids (lse_grid_estimator.py:83-106) without a host sync: capacity-bounded packed output.
-    packed: (bits, mip) from LSEOccGridEstimator.packed(); packed here from `binaries_u8` when absent."""
+    packed: (bits, mip) from LSEOccGridEstimator.packed(); packed here from `binaries_u8` when absent.
+    overflow: persistent int32 [1] flag to raise (sticky) when the marched samples exceed S_cap -- the counts are clamped so that
+    no later kernel indexes past the capacity; a fresh zeroed flag is allocated when absent."""
     o = _f32(rays_o.detach(), "rays_o"); d = _f32(rays_d.detach(), "rays_d")
     R = o.shape[0]
     dev = o.device
@@ -206,12 +213,13 @@ def march(rays_o, rays_d, binaries_u8, aabbs, near, far, step, cone, jitter: Opt
         occ_pack(binaries_u8, bits, mip)
     else:
         bits, mip = packed
-    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    if overflow is None:
+        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
     ri = torch.empty(S_cap, dtype=torch.int32, device=dev)
     t0 = torch.empty(S_cap, device=dev); t1 = torch.empty(S_cap, device=dev)
     if two_pass:
         call("lse_march_count", P(o), P(d), R, P(bits), P(mip), P(aabbs), levels, res, near, far, P(jit), step, cone, P(counts), stream())
-        starts, total = scan_counts(counts)
+        starts, total = scan_counts(counts, S_cap, overflow)
         call("lse_march_fill", P(o), P(d), R, P(bits), P(mip), P(aabbs), levels, res, near, far, P(jit), step, cone, P(starts),
              S_cap, P(ri), P(t0), P(t1), P(overflow), stream())
     else:
@@ -221,7 +229,7 @@ def march(rays_o, rays_d, binaries_u8, aabbs, near, far, step, cone, jitter: Opt
         ws = torch.empty(nws, dtype=torch.uint8, device=dev)
         call("lse_march_single", P(o), P(d), R, P(bits), P(mip), P(aabbs), levels, res, near, far, P(jit), step, cone, P(slabs),
              MAX_SAMPLES_PER_RAY, P(counts), P(overflow), P(ws), nws, stream())
-        starts, total = scan_counts(counts)
+        starts, total = scan_counts(counts, S_cap, overflow)
         call("lse_march_pack", P(slabs), MAX_SAMPLES_PER_RAY, P(counts), P(starts), R, S_cap, P(ri), P(t0), P(t1), P(overflow), stream())
     return MarchResult(ri, t0, t1, starts, counts, total, overflow, S_cap)
 
@@ -536,6 +544,7 @@ class RenderOpts:
     samples_per_ray_cap: int = 512     # packed capacity = R * this
     early_terminate: bool = True       # culling pass: no field evaluation behind opaque surfaces (same kept set)
     premarched: Optional[MarchResult] = None
+    overflow: Optional[Tensor] = None  # sticky int32 [1] capacity-overflow flag of the owning model (checked at the grid update)
     defer_table_scatter: bool = False  # backward leaves the hash-table scatter to run_deferred_table_scatter(opts)
     deferred_table: Optional[tuple] = None
     last_totals: Optional[tuple] = None  # (marched, kept) device-side sample counts of the latest render through these opts
@@ -552,7 +561,8 @@ class _RenderRays(torch.autograd.Function):
         S_cap = max(1, R * opts.samples_per_ray_cap)
         m0 = opts.premarched   # marched earlier on the same rays / jitter / grid (engine: overlaps the previous step's optimizer)
         if m0 is None:
-            m0 = march(o, d, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step, opts.cone, jitter, S_cap, opts.occ_packed)
+            m0 = march(o, d, opts.binaries_u8, opts.aabbs, opts.near, opts.far, opts.step, opts.cone, jitter, S_cap, opts.occ_packed,
+                       overflow=opts.overflow)
         assert m0.S_cap == S_cap and m0.counts.numel() == R
         culling = opts.cull and (opts.alpha_thre > 0.0 or opts.early_stop_eps > 0.0)
         if culling and opts.early_stop_eps > 0.0 and opts.early_terminate:

@@ -94,8 +94,8 @@ def test_sh_constants_against_scipy_real_harmonics():
 
 
 def test_x_corner_pairs_share_a_16_byte_slot():
-    """The index fact behind the LSE_PAIR_LOADS / LSE_PAIR_REDS build-time experiments (field_common.cuh:gather_corners,
-    field_hash.cu:scatter_samples_kernel): the x term enters the hash unmultiplied, so whenever (idx[0] ^ idx[3]) == 1 every
+    """Locality of the hash (the reason coarse-in-x neighbours are cheap; the paired-load / paired-reduction / two-lanes-per-sample kernels
+    built on it were measured and removed in round 2, profiles/r2a_ab_pair_*.json): the x term enters the hash unmultiplied, so whenever (idx[0] ^ idx[3]) == 1 every
     (ceil_x, floor_x) corner pair -- (0,3), (1,2), (4,7), (5,6) -- sits on rows j ^ 1 and j of the level's table, i.e. in the two halves of
     the 16-byte slot j >> 1; this happens for about half of the samples at fine levels."""
     import torch
@@ -114,7 +114,7 @@ def test_x_corner_pairs_share_a_16_byte_slot():
         assert not bool(((idx[..., c] ^ idx[..., f]) == 1)[~pair].any())
     frac = pair[:, 8:].float().mean().item()
     assert 0.45 < frac < 0.55, frac
-    # ... and the same 128-byte line (16 rows) unless floor_x ends in four one bits: the fact behind LSE_PAIR_LANES
+    # ... and the same 128-byte line (16 rows) unless floor_x ends in four one bits
     same_line = ((idx[..., 0] >> 4) == (idx[..., 3] >> 4))[64:, 8:].float().mean().item()
     assert 0.92 < same_line < 0.95, same_line
     # reading the slot as 4 floats and picking halves by the row's low bit returns the rows themselves
@@ -124,34 +124,3 @@ def test_x_corner_pairs_share_a_16_byte_slot():
     v = slots[jf >> 1]
     odd = (jf & 1).bool()[:, None]
     assert torch.equal(torch.where(odd, v[:, 2:], v[:, :2]), table[jf]) and torch.equal(torch.where(odd, v[:, :2], v[:, 2:]), table[jc])
-
-
-def test_face_bilinear_pair_blend_equals_trilinear_encode():
-    """The arithmetic of the LSE_PAIR_LANES experiment (field_common.cuh:pairlanes_level): blend each x face bilinearly in (y, z), then
-    the two faces in x; d/dx = ceil face - floor face, d/dy and d/dz blended across the faces.  Same polynomial as the encode and
-    its autograd Jacobian (fp64)."""
-    import torch
-    from oracle import field as OF
-    torch.manual_seed(0)
-    S, T = 2000, 2**12
-    x = torch.rand(S, 3, dtype=torch.float64)
-    sc = OF.hash_scalings().double()
-    table = torch.rand(16 * T, 2, dtype=torch.float64) * 2 - 1
-    xr = x.clone().requires_grad_(True)
-    ref = OF.hash_encode(xr, table, sc, T)
-    idx, off = OF.hash_corner_indices(x, sc, T)
-    F = table[idx]
-    ox, oy, oz = off[..., 0:1], off[..., 1:2], off[..., 2:3]
-
-    def face(c0, c1, c2, c3):       # corners (ceil_y, ceil_z), (floor_y, ceil_z), (ceil_y, floor_z), (floor_y, floor_z)
-        a = F[:, :, c0] * oy + F[:, :, c1] * (1 - oy); b = F[:, :, c2] * oy + F[:, :, c3] * (1 - oy)
-        return a * oz + b * (1 - oz), (F[:, :, c0] - F[:, :, c1]) * oz + (F[:, :, c2] - F[:, :, c3]) * (1 - oz), a - b
-    gc, gyc, gzc = face(0, 1, 4, 5)
-    gf, gyf, gzf = face(3, 2, 7, 6)
-    assert torch.allclose((gc * ox + gf * (1 - ox)).reshape(S, 32), ref, rtol=0, atol=1e-13)
-    w = torch.randn(S, 32, dtype=torch.float64)
-    (ref * w).sum().backward()
-    wl = w.reshape(S, 16, 2)
-    jac = [gc - gf, gyc * ox + gyf * (1 - ox), gzc * ox + gzf * (1 - ox)]
-    grad = torch.stack([((wl * j).sum(-1) * sc[None, :]).sum(1) for j in jac], dim=-1)
-    assert torch.allclose(grad, xr.grad, rtol=1e-10, atol=1e-8)
