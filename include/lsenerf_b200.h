@@ -140,13 +140,28 @@ int lse_compact(const int32_t *starts, const int32_t *counts, const int32_t *new
                 const float *sigma, int32_t *ray_indices_out, float *t_starts_out, float *t_ends_out,
                 float *h16_out, float *sigma_out, lse_stream_t stream);
 
-/* 3P nerfacc OccGridEstimator.update_every_n_steps (inherited NGP callback; lse_nerf/lsenerf.py:184-188):
- * occs[cell] = max(occs[cell]*decay, occ[i]) for the evaluated cells, then binaries = occs > min(mean(occs), thre).
- * cell_idx int64 [n] (global cell ids), occ [n]; occ_mean_dev [1] receives mean(occs) (the value
- * lse_grid_estimator.py:112 reads with .item()); scratch_sum: 1 double of device scratch. */
-int lse_occ_update(float *occs, int64_t n_cells_total, const int64_t *cell_idx, const float *occ, int64_t n,
-                   float decay, float occ_thre, uint8_t *binaries, float *occ_mean_dev, double *scratch_sum,
-                   lse_stream_t stream);
+/* 3P nerfacc OccGridEstimator.update_every_n_steps (inherited NGP callback; grid built at lse_nerf/lsenerf.py:184-188), step 1:
+ * the cells to re-evaluate and their jittered sample points, without a host read of the occupied-cell count.
+ *   warmup_all != 0 (step < warmup_steps): every cell of every level, level-major (u_uniform / u_occupied / workspace unused);
+ *   else per level (N = res^3 cells): N/4 uniform draws floor(u_uniform[l,i]*N), then the occupied cells of `binaries` in ascending
+ *   order -- all of them if at most N/4, otherwise N/4 draws occupied[floor(u_occupied[l,i]*n_occupied)]
+ *   (nerfacc _sample_uniform_and_occupied_cells with the uniforms supplied by the caller's generator: u_* are [levels, N/4] in [0,1)).
+ * Outputs compacted level-major with the live count in *n_out_dev: cell_out [cap] int32 = level*N + cell, pos_out [cap,3] =
+ * aabb_lo + (cell coords + u_jitter[j]) / res * (aabb_hi - aabb_lo); cap = levels*N (warm-up) or levels*2*(N/4).  res % 16 == 0.
+ * workspace: lse_occ_select_workspace(levels, res) bytes. */
+int64_t lse_occ_select_workspace(int levels, int res);
+int lse_occ_select_cells(const uint8_t *binaries, int levels, int res, int warmup_all, const float *u_uniform,
+                         const float *u_occupied, const float *u_jitter, const float *aabbs, void *workspace,
+                         int64_t workspace_bytes, int32_t *cell_out, float *pos_out, int32_t *n_out_dev, lse_stream_t stream);
+/* ... step 2: occs[cell] = max(occs[cell]*decay, occ[i]*occ_scale) for the evaluated cells (live prefix *n_dev of cap; n_dev NULL =
+ * all), then binaries = occs > min(mean(occs), occ_thre).  Deterministic: a cell listed several times decays ONCE from its old value
+ * and takes the largest of its new values (the reference's indexed assignment lets an arbitrary duplicate win), and mean(occs) is a
+ * fixed-order sum -- replicas holding identical weights derive bit-identical grids.  occ_mean_dev [1] receives mean(occs) (the value
+ * lse_grid_estimator.py:112 reads with .item()).  scratch_max: int32 [n_cells_total] that the caller fills with -1 ONCE (the call
+ * leaves it at -1); scratch_partials: 1024 doubles. */
+int lse_occ_update(float *occs, int64_t n_cells_total, const int32_t *cell_idx, const float *occ, int64_t cap,
+                   const int32_t *n_dev, float occ_scale, float decay, float occ_thre, uint8_t *binaries,
+                   float *occ_mean_dev, int32_t *scratch_max, double *scratch_partials, lse_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (c) multiresolution hash grid (3P nerfstudio HashEncoding.pytorch_fwd semantics,
@@ -189,7 +204,7 @@ typedef struct {
 
 /* samples: position = origins[r] + directions[r] * (t0+t1)/2 with r = ray_idx ? ray_idx[i] : i; if directions ==
  * NULL the position is origins[r] (Field.density_fn).  -> sigma [S] (density after trunc_exp * selector) and
- * h16 [S,16] = base-MLP output (col 0 = density pre-activation, cols 1..15 = geo features). */
+ * h16 [S,16] = base-MLP output (col 0 = density pre-activation, cols 1..15 = geo features); either output may be NULL. */
 int lse_field_density_fwd(const LseFieldParams *p /*[host]*/, const float *origins, const float *directions,
                           const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap,
                           const int32_t *n_dev, float *sigma, float *h16, lse_stream_t stream);

@@ -45,7 +45,7 @@ extern "C" int lse_field_density_fwd(const LseFieldParams *p, const float *origi
     int rc = check_params(p, __func__);
     if (rc) return rc;
     LSE_CHECK_ARG(p->W1 && p->b1 && p->W2 && p->b2, "base MLP weights missing");
-    LSE_CHECK_ARG(origins && h16, "origins / h16 missing");
+    LSE_CHECK_ARG(origins && (h16 || sigma), "origins / outputs missing");
     if (S_cap <= 0) return 0;
     if (p->use_tensor_cores) return tc_density_fwd(*p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, nullptr, sigma, h16, (cudaStream_t)stream);
     return simt_density_fwd(*p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, nullptr, sigma, h16, (cudaStream_t)stream);

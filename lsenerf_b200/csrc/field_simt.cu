@@ -49,9 +49,11 @@ __global__ void __launch_bounds__(TS) density_fwd_kernel(LseFieldParams P, const
         float out[NO];
         dense_rows<NO, NH>(sW2, sb2, h1, out);
         if (sigma) sigma[i] = g.cc.sel ? expf(out[0]) : expf(out[0]) * 0.0f;
-        float4 *dst = reinterpret_cast<float4 *>(h16 + 16 * i);
+        if (h16) {
+            float4 *dst = reinterpret_cast<float4 *>(h16 + 16 * i);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+        }
     }
 }
 

@@ -165,9 +165,11 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
 #pragma unroll
             for (int j = 0; j < NO; ++j) out[j] += smem[L::B2 + j];
             if (sigma) sigma[i] = g.cc.sel ? expf(out[0]) : expf(out[0]) * 0.0f;
-            float4 *dst = reinterpret_cast<float4 *>(h16 + 16 * i);
+            if (h16) {
+                float4 *dst = reinterpret_cast<float4 *>(h16 + 16 * i);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+            }
         }
     }
     tc_fence_before();

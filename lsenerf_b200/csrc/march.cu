@@ -520,32 +520,210 @@ __global__ void compact_kernel(const int32_t *__restrict__ starts, const int32_t
     }
 }
 
-// ---- occupancy EMA update --------------------------------------------------------------------------------
-__global__ void occ_ema_kernel(float *__restrict__ occs, const int64_t *__restrict__ cell_idx, const float *__restrict__ occ,
-                               int64_t n, float decay)
+// ---- occupancy-grid update (nerfacc OccGridEstimator.update_every_n_steps) ---------------------------------------
+// Cell selection, EMA and binarisation entirely on the device, without a host read of the occupied-cell count and with a result
+// that is a pure function of the inputs (no races between duplicated cells, fixed-order mean): replicas of a multi-GPU run derive
+// bit-identical grids from identical weights.
+constexpr int kOccBlockCells = 4096;   // cells per block of the occupied-cell compaction (256 threads x 16 bytes)
+
+// pass 1: occupied cells per 4096-cell block, level-major
+__global__ void __launch_bounds__(256) occ_block_count_kernel(const uint8_t *__restrict__ binaries, int32_t *__restrict__ block_counts)
 {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t c = cell_idx[i];
-        occs[c] = fmaxf(occs[c] * decay, occ[i]);
+    __shared__ int32_t s_w[8];
+    const uint4 v = reinterpret_cast<const uint4 *>(binaries)[(int64_t)blockIdx.x * 256 + threadIdx.x];
+    // bytes are 0 / 1 (torch bool): popcount of the words counts them
+    int32_t c = __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) + __popc(v.w & 0x01010101u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        block_counts[blockIdx.x] = t;
     }
 }
 
-__global__ void occ_sum_kernel(const float *__restrict__ occs, int64_t n, double *__restrict__ sum)
+// pass 2 (one CTA per level): exclusive scan of the level's block counts in place, n_occ[level] = total
+__global__ void __launch_bounds__(1024) occ_block_scan_kernel(int32_t *__restrict__ block_counts, int blocks_per_level,
+                                                              int32_t *__restrict__ n_occ)
 {
-    double acc = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        acc += (double)occs[i];
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry_s;
+    int32_t *bc = block_counts + (int64_t)blockIdx.x * blocks_per_level;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < blocks_per_level; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int32_t v = i < blocks_per_level ? bc[i] : 0;
+        int32_t inc = v;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(sum, acc);
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = warp_tot[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += y;
+            }
+            warp_tot[lane] = winc - w;
+        }
+        __syncthreads();
+        const int32_t excl = carry_s + warp_tot[wid] + (inc - v);
+        if (i < blocks_per_level) bc[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_occ[blockIdx.x] = carry_s;
 }
 
-__global__ void occ_binarize_kernel(const float *__restrict__ occs, int64_t n, const double *__restrict__ sum, float occ_thre,
-                                    uint8_t *__restrict__ binaries, float *__restrict__ occ_mean)
+// pass 3: occ_list[level][rank] = cell id inside the level, ascending (the order of torch.nonzero)
+__global__ void __launch_bounds__(256) occ_block_fill_kernel(const uint8_t *__restrict__ binaries, const int32_t *__restrict__ block_starts,
+                                                             int blocks_per_level, int64_t cells_per_level, int32_t *__restrict__ occ_list)
 {
-    float mean = (float)(*sum / (double)n);
-    float thre = fminf(mean, occ_thre);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && occ_mean) *occ_mean = mean;
+    __shared__ int32_t s_w[8];
+    const int level = blockIdx.x / blocks_per_level, blk = blockIdx.x % blocks_per_level;
+    const uint4 v = reinterpret_cast<const uint4 *>(binaries)[(int64_t)blockIdx.x * 256 + threadIdx.x];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    int32_t c = __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) + __popc(v.w & 0x01010101u);
+    int32_t inc = c;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    int32_t off = block_starts[blockIdx.x] + (inc - c);
+    for (int q = 0; q < wid; ++q) off += s_w[q];
+    int32_t *dst = occ_list + (int64_t)level * cells_per_level;
+    const int32_t cell0 = blk * kOccBlockCells + threadIdx.x * 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if ((w[k >> 2] >> (8 * (k & 3))) & 1u) dst[off++] = cell0 + k;
+}
+
+// pass 4: the cells to re-evaluate and their jittered points, compacted level-major.
+//   warm-up: every cell of every level;
+//   else per level: N/4 uniform draws floor(u*N) followed by the occupied cells -- all of them when there are at most N/4, otherwise
+//   N/4 draws occ_list[floor(u*n_occ)] (nerfacc _sample_uniform_and_occupied_cells; the uniforms come from the caller's generator).
+// x = (cell coords + jitter) / res mapped into the level's aabb (nerfacc _update).
+__global__ void occ_select_kernel(int levels, int res, int warmup_all, const int32_t *__restrict__ n_occ,
+                                  const int32_t *__restrict__ occ_list, const float *__restrict__ u_uniform,
+                                  const float *__restrict__ u_occupied, const float *__restrict__ u_jitter,
+                                  const float *__restrict__ aabbs, int32_t *__restrict__ cell_out, float *__restrict__ pos_out,
+                                  int32_t *__restrict__ n_out)
+{
+    const int64_t N = (int64_t)res * res * res, Q = N / 4;
+    const int64_t per_level = warmup_all ? N : 2 * Q;
+    const float resf = (float)res;
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < per_level * levels; w += (int64_t)gridDim.x * blockDim.x) {
+        const int level = (int)(w / per_level);
+        const int64_t i = w % per_level;
+        int64_t base = 0, cell = -1, j = -1;
+        if (warmup_all) {
+            base = (int64_t)level * N; cell = i; j = base + i;
+        } else {
+            for (int l = 0; l < level; ++l) { const int64_t no = n_occ[l]; base += Q + (no < Q ? no : Q); }
+            const int64_t no = n_occ[level];
+            if (i < Q) {
+                int64_t c = (int64_t)(u_uniform[(int64_t)level * Q + i] * (float)N);
+                cell = c < N ? c : N - 1; j = base + i;
+            } else {
+                const int64_t k = i - Q;
+                if (no <= Q) {
+                    if (k < no) { cell = occ_list[(int64_t)level * N + k]; j = base + Q + k; }
+                } else {
+                    int64_t pick = (int64_t)(u_occupied[(int64_t)level * Q + k] * (float)no);
+                    pick = pick < no ? pick : no - 1;
+                    cell = occ_list[(int64_t)level * N + pick]; j = base + Q + k;
+                }
+            }
+        }
+        if (j >= 0) {
+            cell_out[j] = (int32_t)((int64_t)level * N + cell);
+            const int cx = (int)(cell / ((int64_t)res * res)), cy = (int)((cell / res) % res), cz = (int)(cell % res);
+            const float *lo = aabbs + 6 * level, *hi = lo + 3;
+            const float cc[3] = {(float)cx, (float)cy, (float)cz};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float x = rn_div(rn_add(cc[a], u_jitter[3 * j + a]), resf);
+                pos_out[3 * j + a] = rn_add(lo[a], rn_mul(x, rn_sub(hi[a], lo[a])));
+            }
+        }
+        if (w == 0) {
+            int64_t tot = 0;
+            if (warmup_all) tot = N * levels;
+            else for (int l = 0; l < levels; ++l) { const int64_t no = n_occ[l]; tot += Q + (no < Q ? no : Q); }
+            *n_out = (int32_t)tot;
+        }
+    }
+}
+
+// EMA pass 1: per touched cell the LARGEST newly evaluated occupancy (int-ordered atomicMax on non-negative floats; scratch holds
+// -1 = untouched).  The reference's indexed assignment lets an arbitrary duplicate win; the maximum is the order-free choice.
+__global__ void occ_scatter_max_kernel(const int32_t *__restrict__ cell_idx, const float *__restrict__ occ, int64_t cap,
+                                       const int32_t *__restrict__ n_dev, float occ_scale, int32_t *__restrict__ scratch)
+{
+    const int64_t n = live_count(n_dev, cap);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = fmaxf(occ[i] * occ_scale, 0.0f);
+        atomicMax(scratch + cell_idx[i], __float_as_int(v));
+    }
+}
+
+// EMA pass 2 over ALL cells: occs = max(occs*decay, new) where touched (each cell decays exactly once, from its old value), scratch
+// reset, and the block's partial sum of the updated occs in a fixed order
+__global__ void __launch_bounds__(256) occ_apply_sum_kernel(float *__restrict__ occs, int64_t n, float decay, int32_t *__restrict__ scratch,
+                                                            double *__restrict__ partials)
+{
+    __shared__ double s_w[8];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float o = occs[i];
+        const int32_t m = scratch[i];
+        if (m >= 0) { o = fmaxf(o * decay, __int_as_float(m)); occs[i] = o; scratch[i] = -1; }
+        acc += (double)o;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        partials[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) occ_binarize_kernel(const float *__restrict__ occs, int64_t n, const double *__restrict__ partials,
+                                                           int n_partials, float occ_thre, uint8_t *__restrict__ binaries,
+                                                           float *__restrict__ occ_mean)
+{
+    __shared__ float s_thre;
+    if (threadIdx.x < 32) {     // every block re-reduces the partials in the same fixed order
+        double t = 0.0;
+        for (int i = threadIdx.x; i < n_partials; i += 32) t += partials[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) {
+            const float mean = (float)(t / (double)n);
+            s_thre = fminf(mean, occ_thre);
+            if (blockIdx.x == 0 && occ_mean) *occ_mean = mean;
+        }
+    }
+    __syncthreads();
+    const float thre = s_thre;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         binaries[i] = occs[i] > thre ? 1 : 0;
 }
@@ -718,23 +896,64 @@ extern "C" int lse_compact(const int32_t *starts, const int32_t *counts, const i
     return check_launch("lse_compact");
 }
 
-extern "C" int lse_occ_update(float *occs, int64_t n_cells_total, const int64_t *cell_idx, const float *occ, int64_t n,
-                              float decay, float occ_thre, uint8_t *binaries, float *occ_mean_dev, double *scratch_sum,
-                              lse_stream_t stream)
+extern "C" int64_t lse_occ_select_workspace(int levels, int res)
 {
-    LSE_CHECK_ARG(scratch_sum != nullptr, "scratch_sum (1 double) required");
+    const int64_t N = (int64_t)res * res * res;
+    // occ_list [levels*N] + block counts [levels*N/4096] + n_occ [levels], int32
+    return ((int64_t)levels * N + (int64_t)levels * (N / kOccBlockCells) + levels + 64) * 4;
+}
+
+extern "C" int lse_occ_select_cells(const uint8_t *binaries, int levels, int res, int warmup_all, const float *u_uniform,
+                                    const float *u_occupied, const float *u_jitter, const float *aabbs, void *workspace,
+                                    int64_t workspace_bytes, int32_t *cell_out, float *pos_out, int32_t *n_out_dev,
+                                    lse_stream_t stream)
+{
+    LSE_CHECK_ARG(levels >= 1 && levels <= kMaxLevels, "levels must be in [1,8]");
+    LSE_CHECK_ARG(res % 16 == 0, "grid resolution must be a multiple of 16");
+    LSE_CHECK_ARG(binaries && u_jitter && aabbs && cell_out && pos_out && n_out_dev, "missing pointer");
+    LSE_CHECK_ARG(warmup_all || (u_uniform && u_occupied), "uniforms missing");
+    LSE_CHECK_ARG(warmup_all || (workspace && workspace_bytes >= lse_occ_select_workspace(levels, res)), "workspace missing or too small");
     cudaStream_t st = (cudaStream_t)stream;
-    int threads = 256;
-    if (n > 0) {
-        occ_ema_kernel<<<stride_grid(n, threads), threads, 0, st>>>(occs, cell_idx, occ, n, decay);
-        int rc = check_launch("lse_occ_update/ema");
+    const int64_t N = (int64_t)res * res * res;
+    int32_t *occ_list = nullptr, *n_occ = nullptr;
+    if (!warmup_all) {
+        const int bpl = (int)(N / kOccBlockCells);
+        occ_list = reinterpret_cast<int32_t *>(workspace);
+        int32_t *block_counts = occ_list + (int64_t)levels * N;
+        n_occ = block_counts + (int64_t)levels * bpl;
+        occ_block_count_kernel<<<levels * bpl, 256, 0, st>>>(binaries, block_counts);
+        int rc = check_launch("lse_occ_select_cells/count");
+        if (rc) return rc;
+        occ_block_scan_kernel<<<levels, 1024, 0, st>>>(block_counts, bpl, n_occ);
+        rc = check_launch("lse_occ_select_cells/scan");
+        if (rc) return rc;
+        occ_block_fill_kernel<<<levels * bpl, 256, 0, st>>>(binaries, block_counts, bpl, N, occ_list);
+        rc = check_launch("lse_occ_select_cells/fill");
         if (rc) return rc;
     }
-    cudaMemsetAsync(scratch_sum, 0, sizeof(double), st);
-    occ_sum_kernel<<<stride_grid(n_cells_total, threads, 4), threads, 0, st>>>(occs, n_cells_total, scratch_sum);
-    int rc = check_launch("lse_occ_update/sum");
+    const int64_t work = (warmup_all ? N : 2 * (N / 4)) * levels;
+    occ_select_kernel<<<stride_grid(work, 256, 8), 256, 0, st>>>(levels, res, warmup_all, n_occ, occ_list, u_uniform, u_occupied, u_jitter,
+                                                                 aabbs, cell_out, pos_out, n_out_dev);
+    return check_launch("lse_occ_select_cells/select");
+}
+
+extern "C" int lse_occ_update(float *occs, int64_t n_cells_total, const int32_t *cell_idx, const float *occ, int64_t cap,
+                              const int32_t *n_dev, float occ_scale, float decay, float occ_thre, uint8_t *binaries,
+                              float *occ_mean_dev, int32_t *scratch_max, double *scratch_partials, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(occs && binaries && scratch_max && scratch_partials, "occs / binaries / scratch missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 256;
+    if (cap > 0) {
+        LSE_CHECK_ARG(cell_idx && occ, "cell_idx / occ missing");
+        occ_scatter_max_kernel<<<stride_grid(cap, threads), threads, 0, st>>>(cell_idx, occ, cap, n_dev, occ_scale, scratch_max);
+        int rc = check_launch("lse_occ_update/scatter");
+        if (rc) return rc;
+    }
+    const int grid = kNumSMs * 4;       // fixed: the partial sums (and so the mean) do not depend on anything but the data
+    occ_apply_sum_kernel<<<grid, threads, 0, st>>>(occs, n_cells_total, decay, scratch_max, scratch_partials);
+    int rc = check_launch("lse_occ_update/apply");
     if (rc) return rc;
-    occ_binarize_kernel<<<stride_grid(n_cells_total, threads, 4), threads, 0, st>>>(occs, n_cells_total, scratch_sum, occ_thre,
-                                                                                    binaries, occ_mean_dev);
+    occ_binarize_kernel<<<grid, threads, 0, st>>>(occs, n_cells_total, scratch_partials, grid, occ_thre, binaries, occ_mean_dev);
     return check_launch("lse_occ_update/binarize");
 }

@@ -31,6 +31,7 @@ class LSEOccGridEstimator(nn.Module):
         # identical weights, so they derive identical grids without any exchange
         self._gen: Optional[torch.Generator] = None
         self.update_seed = 0x5EED
+        self._scratch: Optional[tuple] = None     # (int32 [cells] kept at -1, float64 [1024]) of the update kernels
         self._bits: Optional[Tensor] = None
         self._mip: Optional[Tensor] = None
         self._packed_key = None
@@ -92,32 +93,35 @@ class LSEOccGridEstimator(nn.Module):
     @torch.no_grad()
     def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
                              warmup_steps: int = 256, n: int = 16) -> None:
-        """nerfacc OccGridEstimator.update_every_n_steps (inherited NGP callback)."""
+        """nerfacc OccGridEstimator.update_every_n_steps (inherited NGP callback): before `warmup_steps` every cell is
+        re-evaluated, afterwards N/4 uniformly drawn cells plus the occupied ones (at most N/4 of them) per level.  Everything runs on
+        the device with no host synchronisation (the reference's `nonzero` / `len(occupied)` reads are replaced by a device-side
+        compaction), and the result is a pure function of (weights, grid, generator state).  `occ_eval_fn(x [n,3]) -> occ [n]`; when it
+        offers `.raw(positions, n_dev) -> (sigma, scale)` only the live prefix of the candidate list is evaluated."""
         if step % n != 0 or not self.training:
             return
         dev = self.occs.device
-        N = self.cells_per_lvl
+        N, L = self.cells_per_lvl, self.levels
         if self._gen is None or self._gen.device != dev:
             self._gen = torch.Generator(device=dev)
             self._gen.manual_seed(self.update_seed)
         gen = self._gen
-        idx_all, occ_all = [], []
-        for l in range(self.levels):
-            if step < warmup_steps:
-                idx = torch.arange(N, device=dev)
-            else:
-                uni = torch.randint(N, (N // 4,), device=dev, generator=gen)
-                occ_idx = torch.nonzero(self.binaries[l].flatten())[:, 0]
-                if occ_idx.numel() > N // 4:
-                    occ_idx = occ_idx[torch.randint(occ_idx.numel(), (N // 4,), device=dev, generator=gen)]
-                idx = torch.cat([uni, occ_idx], dim=0)
-            r = self.res
-            coords = torch.stack([idx // (r * r), (idx // r) % r, idx % r], dim=-1).float()
-            x = (coords + torch.rand(coords.shape, device=dev, generator=gen)) / r
-            lo, hi = self.aabbs[l, :3], self.aabbs[l, 3:]
-            occ = occ_eval_fn(lo + x * (hi - lo)).reshape(-1)
-            idx_all.append(idx + l * N); occ_all.append(occ)
-        ops.occ_update(self.occs, torch.cat(idx_all).contiguous(), torch.cat(occ_all).contiguous().float(), self.binaries_u8(),
-                       self.occ_mean, ema_decay, occ_thre)
+        warm = step < warmup_steps
+        q = N // 4
+        u_uni = u_occ = None
+        if not warm:
+            u_uni = torch.rand(L, q, device=dev, generator=gen)
+            u_occ = torch.rand(L, q, device=dev, generator=gen)
+        cap = L * (N if warm else 2 * q)
+        u_jit = torch.rand(cap, 3, device=dev, generator=gen)
+        cells, pos, n_dev = ops.occ_select_cells(self.binaries_u8(), self.aabbs, warm, u_uni, u_occ, u_jit)
+        if hasattr(occ_eval_fn, "raw"):
+            occ, scale = occ_eval_fn.raw(pos, n_dev)
+        else:
+            occ, scale = occ_eval_fn(pos).reshape(-1).float().contiguous(), 1.0
+        if self._scratch is None or self._scratch[0].device != dev:
+            self._scratch = (torch.full((L * N,), -1, dtype=torch.int32, device=dev), torch.empty(1024, dtype=torch.float64, device=dev))
+        ops.occ_update(self.occs, cells, occ, self.binaries_u8(), self.occ_mean, ema_decay, occ_thre, n_dev=n_dev, occ_scale=scale,
+                       scratch=self._scratch)
         self._mean_valid = True
         self.packed(force=True)

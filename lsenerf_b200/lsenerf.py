@@ -89,6 +89,21 @@ class ToGrayGT(nn.Module):
         self.register_buffer("c2g_vec", torch.tensor([0.2989, 0.5870, 0.1140]).reshape(-1, 1))
 
 
+class _OccEval:
+    """occ_eval_fn of the grid update: x -> density(x) * render_step_size (NGP callback).  `raw` evaluates only the live prefix of the
+    device-side candidate list (no base-MLP feature output) and leaves the scale to the update kernel."""
+
+    def __init__(self, field: LSEField, step_size: float) -> None:
+        self.field, self.step_size = field, step_size
+
+    def __call__(self, x: Tensor) -> Tensor:
+        return self.field.density_fn(x) * self.step_size
+
+    def raw(self, positions: Tensor, n_dev: Tensor):
+        sigma = ops.field_density_raw(self.field.weights(), positions, None, None, None, None, positions.shape[0], n_dev, want_h16=False)[0]
+        return sigma, self.step_size
+
+
 class LSENeRFModel(nn.Module):
     def __init__(self, config: LSENeRFModelConfig, scene_aabb: Tensor, num_train_data: int, **kwargs) -> None:
         super().__init__()
@@ -167,7 +182,7 @@ class LSENeRFModel(nn.Module):
         asynchronously instead (engine.GraphedStep)."""
         if check_overflow and self.training and step % 16 == 0 and self._overflow.is_cuda:
             self.check_overflow()
-        self.occupancy_grid.update_every_n_steps(step, occ_eval_fn=lambda x: self.field.density_fn(x) * self.config.render_step_size)
+        self.occupancy_grid.update_every_n_steps(step, occ_eval_fn=_OccEval(self.field, float(self.config.render_step_size)))
 
     # ---- forward ----------------------------------------------------------------------------------------------------
     def forward(self, ray_bundle: RayBundle, **kwargs):

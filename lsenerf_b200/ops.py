@@ -335,10 +335,10 @@ def _grads_struct(fw: FieldWeights, bufs: dict) -> _lib.LseFieldGrads:
     return g
 
 
-def field_density_raw(fw: FieldWeights, origins, directions, ray_idx, t0, t1, S_cap, n_dev):
-    """no-grad density pass -> (sigma [S_cap], h16 [S_cap,16])."""
+def field_density_raw(fw: FieldWeights, origins, directions, ray_idx, t0, t1, S_cap, n_dev, want_h16: bool = True):
+    """no-grad density pass -> (sigma [S_cap], h16 [S_cap,16] or None)."""
     dev = origins.device
-    sigma = torch.empty(S_cap, device=dev); h16 = torch.empty(S_cap, 16, device=dev)
+    sigma = torch.empty(S_cap, device=dev); h16 = torch.empty(S_cap, 16, device=dev) if want_h16 else None
     cp = fw.c_params()
     call("lse_field_density_fwd", ctypes.byref(cp), P(origins), P(directions), P(ray_idx), P(t0), P(t1), S_cap, P(n_dev),
          P(sigma), P(h16), stream())
@@ -777,10 +777,38 @@ def losses(col_pred, col_target, prev, nxt, evs, evs_weight=1.0):
 # =================================================================================================================
 # occupancy grid update, Adam
 # =================================================================================================================
-def occ_update(occs: Tensor, cell_idx: Tensor, occ: Tensor, binaries_u8: Tensor, occ_mean_dev: Tensor, decay=0.95, occ_thre=0.01):
-    scratch = torch.zeros(1, dtype=torch.float64, device=occs.device)
-    call("lse_occ_update", P(occs), occs.numel(), P(cell_idx), P(occ), cell_idx.numel(), decay, occ_thre, P(binaries_u8.view(-1)),
-         P(occ_mean_dev), P(scratch), stream())
+def occ_select_cells(binaries_u8: Tensor, aabbs: Tensor, warmup_all: bool, u_uniform: Optional[Tensor], u_occupied: Optional[Tensor],
+                     u_jitter: Tensor):
+    """nerfacc OccGridEstimator._get_all_cells / _sample_uniform_and_occupied_cells + the jittered points of _update, on the device
+    and without a host read of the occupied count -> (cell_idx int32 [cap], positions [cap,3], n_dev int32 [1])."""
+    levels, res = binaries_u8.shape[0], binaries_u8.shape[1]
+    N = res ** 3
+    cap = levels * (N if warmup_all else 2 * (N // 4))
+    dev = binaries_u8.device
+    assert u_jitter.shape == (cap, 3)
+    cells = torch.empty(cap, dtype=torch.int32, device=dev)
+    pos = torch.zeros(cap, 3, device=dev)
+    n_dev = torch.empty(1, dtype=torch.int32, device=dev)
+    ws, nws = None, 0
+    if not warmup_all:
+        assert u_uniform.shape == (levels, N // 4) and u_occupied.shape == (levels, N // 4)
+        nws = int(_lib.lib().lse_occ_select_workspace(levels, res))
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    call("lse_occ_select_cells", P(binaries_u8), levels, res, int(warmup_all), P(_f32(u_uniform, "u") if u_uniform is not None else None),
+         P(_f32(u_occupied, "u") if u_occupied is not None else None), P(_f32(u_jitter, "u_jitter")), P(aabbs), P(ws), nws, P(cells), P(pos),
+         P(n_dev), stream())
+    return cells, pos, n_dev
+
+
+def occ_update(occs: Tensor, cell_idx: Tensor, occ: Tensor, binaries_u8: Tensor, occ_mean_dev: Tensor, decay=0.95, occ_thre=0.01,
+               n_dev: Optional[Tensor] = None, occ_scale: float = 1.0, scratch: Optional[tuple] = None):
+    """EMA + binarisation of OccGridEstimator._update, deterministic (see lse_occ_update).  scratch = (int32 [n_cells] kept at -1,
+    float64 [1024]); allocated here when absent."""
+    if scratch is None:
+        scratch = (torch.full((occs.numel(),), -1, dtype=torch.int32, device=occs.device),
+                   torch.empty(1024, dtype=torch.float64, device=occs.device))
+    call("lse_occ_update", P(occs), occs.numel(), P(cell_idx.to(torch.int32)), P(_f32(occ, "occ")), cell_idx.numel(), P(n_dev), float(occ_scale),
+         decay, occ_thre, P(binaries_u8.view(-1)), P(occ_mean_dev), P(scratch[0]), P(scratch[1]), stream())
 
 
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr, beta1, beta2, eps, step, grad_scale=1.0):

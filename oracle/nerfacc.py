@@ -146,11 +146,34 @@ class OccGrid:
         lo, hi = self.aabbs[level, :3], self.aabbs[level, 3:]
         return lo + x * (hi - lo)
 
+    def select_cells(self, warmup_all: bool, u_uniform: Tensor | None = None, u_occupied: Tensor | None = None):
+        """nerfacc OccGridEstimator._get_all_cells (step < warmup_steps) / _sample_uniform_and_occupied_cells(n = cells // 4):
+        per level n uniform draws followed by the occupied cells -- all of them when there are at most n, else n draws among them.
+        nerfacc draws with torch.randint; here the uniforms u_* [levels, n] in [0,1) are supplied and a draw is floor(u * high) in
+        fp32 (the convention of the pixel sampler), so that a kernel can be given the same numbers."""
+        if warmup_all:
+            return [self.grid_indices.clone() for _ in range(self.levels)]
+        n = self.cells // 4
+        out = []
+        for l in range(self.levels):
+            uni = (u_uniform[l].float() * torch.tensor(float(self.cells))).long().clamp(max=self.cells - 1)
+            occ = torch.nonzero(self.binaries[l].flatten())[:, 0]
+            if n < len(occ):
+                pick = (u_occupied[l].float() * torch.tensor(float(len(occ)))).long().clamp(max=len(occ) - 1)
+                occ = occ[pick]
+            out.append(torch.cat([uni, occ], dim=0))
+        return out
+
     def apply_update(self, level_indices, level_occ, occ_thre=1e-2, ema_decay=0.95):
-        """occs[cell] = max(occs*decay, occ); thre = clamp(mean(occs[occs>=0]), max=occ_thre); binaries = occs>thre."""
+        """occs[cell] = max(occs*decay, occ); thre = clamp(mean(occs[occs>=0]), max=occ_thre); binaries = occs>thre.
+        A cell that is listed several times (the uniform draws are with replacement, and may repeat an occupied cell): upstream's
+        indexed assignment computes every right-hand side from the OLD value and lets an arbitrary duplicate win (CUDA index_put
+        without accumulate); this restatement takes the largest -- the one outcome that does not depend on the order."""
         for l, (idx, occ) in enumerate(zip(level_indices, level_occ)):
             cell = l * self.cells + idx
-            self.occs[cell] = torch.maximum(self.occs[cell] * ema_decay, occ)
+            new = torch.full_like(self.occs, -1.0).scatter_reduce(0, cell, occ.float(), reduce="amax", include_self=True)
+            touched = new >= 0
+            self.occs = torch.where(touched, torch.maximum(self.occs * ema_decay, new), self.occs)
         thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
         self.binaries = (self.occs > thre).view(self.binaries.shape)
         return thre

@@ -401,22 +401,6 @@ def test_adam_matches_torch(dev):
     assert rel_err(pc, pr) < 1e-5
 
 
-def test_occupancy_update(dev):
-    from lsenerf_b200 import ops
-    g = torch.Generator().manual_seed(0)
-    n = 4 * 32**3
-    occs = torch.rand(n, generator=g) * 0.02
-    idx = torch.randperm(n, generator=g)[: n // 2]
-    occ = torch.rand(n // 2, generator=g) * 0.03
-    ref = occs.clone(); ref[idx] = torch.maximum(ref[idx] * 0.95, occ)
-    thre = torch.clamp(ref.mean(), max=0.01)
-    oc = occs.to(dev); b = torch.zeros(n, dtype=torch.uint8, device=dev); mean = torch.zeros(1, device=dev)
-    ops.occ_update(oc, idx.to(dev), occ.to(dev), b, mean, 0.95, 0.01)
-    assert torch.allclose(oc.cpu(), ref)
-    assert abs(mean.item() - ref.mean().item()) < 1e-7
-    assert (b.cpu().bool() != (ref > thre)).float().mean() < 1e-5
-
-
 def test_full_size_properties(dev):
     """BASELINE-size workload (8192 rays, T = 2^19): size-independent invariants of the path."""
     spec = syn.SceneSpec(col_hw=(120, 160), evs_hw=(120, 160), col_f=125.0, evs_f=130.0)
