@@ -244,11 +244,16 @@ int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFieldGrads *g
                                  const float *d_h16, float *d_origins, float *d_directions, void *workspace,
                                  int64_t workspace_bytes, lse_stream_t stream);
 /* lse_field_density_bwd_finish as two calls (tensor-core path): `rays` = base-MLP backward + ray / position gradients, `table` =
- * the hash-table gradient alone, which only the optimizer needs and which may therefore run on the optimizer's stream. */
+ * the hash-table gradient alone, which only the optimizer needs and which may therefore run on the optimizer's stream.
+ * With with_jacobian and the ray-major packing of the samples given (starts / counts [n_rays] int32, as lse_composite_fwd takes them)
+ * the ray gradients are reduced by one warp per ray in a fixed order and WRITTEN to d_origins / d_directions [n_rays,3] (no
+ * atomics, no zero-fill needed, bit-reproducible); d_dir_samples [S,3] (optional: the per-sample direction gradients of
+ * lse_field_color_bwd(dir_per_sample = 1)) is folded into the same reduction.  starts == NULL: accumulated atomically as before. */
 int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
                                const float *d_h16, float *d_origins, float *d_directions, int with_jacobian,
+                               const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *d_dir_samples,
                                void *workspace, int64_t workspace_bytes, lse_stream_t stream);
 int lse_field_density_bwd_table(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                 const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
@@ -258,10 +263,12 @@ int lse_field_density_bwd_table(const LseFieldParams *p, const LseFieldGrads *g,
 int lse_field_color_fwd(const LseFieldParams *p, const float *directions, const int32_t *ray_idx,
                         const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb,
                         lse_stream_t stream);
-/* d_rgb [S,3] -> d_h16 [S,16] (cols 1..15 written, col 0 zeroed), head/embedding grads, d_directions per ray. */
+/* d_rgb [S,3] -> d_h16 [S,16] (cols 1..15 written, col 0 zeroed), head/embedding grads, and the direction gradient of the SH
+ * encoding: dir_per_sample == 0: accumulated atomically into d_directions [n_rays,3]; != 0: written per sample into
+ * d_directions [S,3] (to be reduced per ray by lse_field_density_bwd_rays). */
 int lse_field_color_bwd(const LseFieldParams *p, const LseFieldGrads *g, const float *directions,
                         const int32_t *ray_idx, const int32_t *app_id, int64_t S_cap, const int32_t *n_dev,
-                        const float *h16, const float *d_rgb, float *d_h16, float *d_directions,
+                        const float *h16, const float *d_rgb, float *d_h16, float *d_directions, int dir_per_sample,
                         lse_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
@@ -334,6 +341,18 @@ int lse_adam_step_hp(float *param, const float *grad, float *exp_avg, float *exp
 int lse_adam_step_collective(void *const *peer_params, void *const *peer_grads, float *param_multicast,
                              const float *grad_multicast, float *exp_avg, float *exp_avg_sq, int64_t n, int rank, int world,
                              float beta1, float beta2, float eps, const float *hp_dev, lse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * reproducible training (bench.py burn-in; tests): order-independent gradient accumulation
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Deterministic mode: every atomic fp32 accumulation whose target lies inside one of the registered ranges (the flat gradient arenas
+ * of engine.ParamArena; bases / nbytes / shadows are HOST arrays of n_ranges entries, n_ranges <= 4) goes to a 64-bit fixed-point
+ * shadow of 2 x nbytes (zero-filled by the caller) instead, whose integer sums do not depend on the order of the additions;
+ * lse_det_flush(grad, shadow, n) adds the shadow into the n fp32 gradients and clears it (run it before the optimizer).
+ * n_ranges = 0 switches the mode off.  Synchronises the device; not to be called while a stream is capturing. */
+int lse_set_deterministic(int n_ranges, const void *const *bases, const int64_t *nbytes, void *const *shadows);
+int lse_det_flush(float *grad, void *shadow, int64_t n, lse_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * measurement (SURVEY 8d "L2 to be measured with a resident-set microbench")

@@ -61,19 +61,55 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// ---- deterministic accumulation mode (lse_set_deterministic) ---------------------------------------------------------------------
+// Floating-point atomics add in arrival order, so two runs of the same training step differ in the last bits of every gradient and
+// -- training being chaotic -- in the work per ray a few thousand steps later.  In deterministic mode every fire-and-forget reduction
+// whose target lies inside a registered gradient arena goes to a 64-bit fixed-point shadow of that arena instead (value * 2^50 rounded
+// to an integer: integer addition is associative, so the sum does not depend on the order); lse_det_flush converts the shadow back
+// into the fp32 gradients before the optimizer reads them.  Resolution 2^-50 = 8.9e-16 (exact for |v| >= 2^-27), range +-8192.
+// The configuration lives in constant memory, one copy per translation unit (no relocatable device code); targets outside every
+// registered range keep the plain fp32 atomic.
+struct DetCfg {
+    int32_t n, pad;
+    unsigned long long base[4], end[4], shadow[4];
+};
+static __constant__ DetCfg c_det;
+typedef void (*det_setter_t)(const DetCfg &);
+void register_det_setter(det_setter_t fn);   // abi.cu
+namespace {
+struct DetRegistrar {
+    DetRegistrar() { register_det_setter([](const DetCfg &c) { cudaMemcpyToSymbol(c_det, &c, sizeof(DetCfg)); }); }
+};
+static DetRegistrar g_det_registrar;
+}  // namespace
+
+__device__ __forceinline__ bool det_add(float *addr, float v)
+{
+    const int n = c_det.n;
+    if (n == 0) return false;
+    const unsigned long long a = (unsigned long long)addr;
+    for (int k = 0; k < n; ++k) {
+        if (a >= c_det.base[k] && a < c_det.end[k]) {
+            unsigned long long *q = reinterpret_cast<unsigned long long *>(c_det.shadow[k] + 2ull * (a - c_det.base[k]));
+            atomicAdd(q, (unsigned long long)__float2ll_rn(v * 1125899906842624.0f));
+            return true;
+        }
+    }
+    return false;
+}
+
 // fire-and-forget fp32 reduction (RED.ADD.F32)
-__device__ __forceinline__ void red_add(float *addr, float v) { atomicAdd(addr, v); }
+__device__ __forceinline__ void red_add(float *addr, float v)
+{
+    if (det_add(addr, v)) return;
+    atomicAdd(addr, v);
+}
 
 // vectorised fire-and-forget reduction of two adjacent floats (RED.ADD.V2.F32 on sm_90+)
 __device__ __forceinline__ void red_add2(float *addr, float a, float b)
 {
+    if (det_add(addr, a)) { det_add(addr + 1, b); return; }
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
-
-// ... of four adjacent floats, 16-byte aligned (RED.ADD.V4.F32 on sm_90+)
-__device__ __forceinline__ void red_add4(float *addr, float a, float b, float c, float d)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 }  // namespace lse

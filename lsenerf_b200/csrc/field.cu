@@ -12,7 +12,7 @@ int simt_color_fwd(const LseFieldParams &P, const float *directions, const int32
                    int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb, cudaStream_t st);
 int simt_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *directions, const int32_t *ray_idx,
                    const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_rgb,
-                   float *d_h16, float *d_directions, cudaStream_t st);
+                   float *d_h16, float *d_directions, int dir_per_sample, cudaStream_t st);
 int simt_density_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *origins, const float *directions,
                      const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev,
                      const float *h16, const float *d_sigma, const float *d_h16, float *d_origins, float *d_directions,
@@ -24,7 +24,7 @@ int tc_color_fwd(const LseFieldParams &P, const float *directions, const int32_t
                  int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb, cudaStream_t st);
 int tc_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *directions, const int32_t *ray_idx,
                  const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_rgb,
-                 float *d_h16, float *d_directions, cudaStream_t st);
+                 float *d_h16, float *d_directions, int dir_per_sample, cudaStream_t st);
 }  // namespace lse
 
 using namespace lse;
@@ -97,7 +97,7 @@ extern "C" int lse_field_color_fwd(const LseFieldParams *p, const float *directi
 extern "C" int lse_field_color_bwd(const LseFieldParams *p, const LseFieldGrads *g, const float *directions,
                                    const int32_t *ray_idx, const int32_t *app_id, int64_t S_cap, const int32_t *n_dev,
                                    const float *h16, const float *d_rgb, float *d_h16, float *d_directions,
-                                   lse_stream_t stream)
+                                   int dir_per_sample, lse_stream_t stream)
 {
     if (!p) { set_error("%s: params is NULL", __func__); return -22; }
     LSE_CHECK_ARG(p->W3 && p->b3 && p->W4 && p->b4 && p->W5 && p->b5, "colour MLP weights missing");
@@ -105,7 +105,8 @@ extern "C" int lse_field_color_bwd(const LseFieldParams *p, const LseFieldGrads 
     LSE_CHECK_ARG(directions && h16 && d_rgb && d_h16, "directions / h16 / d_rgb / d_h16 missing");
     if (S_cap <= 0) return 0;
     if (p->use_tensor_cores)
-        return tc_color_bwd(*p, *g, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb, d_h16, d_directions, (cudaStream_t)stream);
-    return simt_color_bwd(*p, *g, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb, d_h16, d_directions,
+        return tc_color_bwd(*p, *g, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb, d_h16, d_directions, dir_per_sample,
+                            (cudaStream_t)stream);
+    return simt_color_bwd(*p, *g, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb, d_h16, d_directions, dir_per_sample,
                           (cudaStream_t)stream);
 }

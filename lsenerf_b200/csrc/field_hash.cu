@@ -250,6 +250,64 @@ __global__ void __launch_bounds__(HT) ray_grad_kernel(const float *__restrict__ 
     }
 }
 
+
+// The same gradients with one warp per RAY over the ray-major packed samples (starts / counts): every lane accumulates its samples in
+// a fixed order, one butterfly reduction per ray, plain stores -- no atomics and no zero-filled output, and the result does not depend
+// on scheduling (bit-reproducible training, bench.py burn-in).  d_dir_samples [S,3] (optional) = per-sample direction gradients of
+// the SH encoding written by the colour backward; they are folded into the same reduction.
+__global__ void __launch_bounds__(HT) ray_grad_packed_kernel(const float *__restrict__ origins, const float *__restrict__ directions,
+                                                             const int32_t *__restrict__ ray_idx, const float *__restrict__ t0,
+                                                             const float *__restrict__ t1, int64_t S_cap,
+                                                             const int32_t *__restrict__ starts, const int32_t *__restrict__ counts,
+                                                             int64_t n_rays, const float *__restrict__ dfeat, const float *__restrict__ jac,
+                                                             const float *__restrict__ d_dir_samples, float *__restrict__ d_origins,
+                                                             float *__restrict__ d_directions)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)HT + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * HT) >> 5;
+    for (int64_t r = warp; r < n_rays; r += n_warps) {
+        const int64_t s = starts[r];
+        const int32_t c = counts[r];
+        float ao[3] = {0.0f, 0.0f, 0.0f}, ad[3] = {0.0f, 0.0f, 0.0f};
+        for (int32_t k = lane; k < c; k += 32) {
+            const int64_t i = s + k;
+            SampleGeom g;
+            load_geom(i, origins, directions, ray_idx, t0, t1, g);
+            if (g.cc.sel) {
+                const float2 *f2 = reinterpret_cast<const float2 *>(dfeat) + i;
+                const float2 *j2 = reinterpret_cast<const float2 *>(jac) + i;      // planes [48][S_cap], see encode_samples_kernel
+                float dx[3] = {0.0f, 0.0f, 0.0f}, dp[3];
+#pragma unroll 4
+                for (int l = 0; l < NL; ++l) {
+                    const float2 gl = __ldg(f2 + (size_t)l * S_cap);
+                    const float2 a = __ldg(j2 + (size_t)(3 * l) * S_cap), b = __ldg(j2 + (size_t)(3 * l + 1) * S_cap),
+                                 cc = __ldg(j2 + (size_t)(3 * l + 2) * S_cap);
+                    dx[0] += gl.x * a.x + gl.y * b.y;
+                    dx[1] += gl.x * a.y + gl.y * cc.x;
+                    dx[2] += gl.x * b.x + gl.y * cc.y;
+                }
+                contract_normalize_bwd(g.p, g.cc, dx, dp);
+                const float tm = g.has_dir ? g.tmid : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { ao[j] += dp[j]; ad[j] += dp[j] * tm; }
+            }
+            if (d_dir_samples) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) ad[j] += d_dir_samples[3 * i + j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { ao[j] = warp_sum(ao[j]); ad[j] = warp_sum(ad[j]); }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (d_origins) d_origins[3 * r + j] = ao[j];
+                if (d_directions) d_directions[3 * r + j] = ad[j];
+            }
+        }
+    }
+}
+
 }  // namespace lse
 
 using namespace lse;
@@ -331,6 +389,7 @@ extern "C" int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFiel
                                           const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                           int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
                                           const float *d_h16, float *d_origins, float *d_directions, int with_jacobian,
+                                          const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *d_dir_samples,
                                           void *workspace, int64_t workspace_bytes, lse_stream_t stream)
 {
     int rc = check_bwd_ws(p, g, origins, h16, __func__);
@@ -343,6 +402,13 @@ extern "C" int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFiel
     rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_h16, ws.dfeat, st);
     if (rc) return rc;
     if (!d_origins && !d_directions) return 0;
+    if (with_jacobian && starts && counts) {     // ray-major packed samples: one warp per ray, no atomics, written (not accumulated)
+        ray_grad_packed_kernel<<<stride_grid(n_rays * 32, HT, 8), HT, 0, st>>>(origins, directions, ray_idx, t0, t1, S_cap, starts, counts,
+                                                                               n_rays, ws.dfeat, ws.jac, d_dir_samples, d_origins,
+                                                                               d_directions);
+        return check_launch("lse_field_density_bwd_rays");
+    }
+    LSE_CHECK_ARG(d_dir_samples == nullptr, "per-sample direction gradients need the packed (starts / counts) Jacobian path");
     if (with_jacobian)     // lse_field_density_bwd_encode stored d(feat)/dx: no re-gather
         ray_grad_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, st>>>(origins, directions, ray_idx, t0, t1, S_cap, n_dev, ws.dfeat, ws.jac,
                                                                   d_origins, d_directions);

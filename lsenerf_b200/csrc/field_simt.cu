@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(TS) color_bwd_kernel(LseFieldParams P, LseFiel
                                                        const int32_t *__restrict__ ray_idx, const int32_t *__restrict__ app_id,
                                                        int64_t S_cap, const int32_t *__restrict__ n_dev,
                                                        const float *__restrict__ h16, const float *__restrict__ d_rgb,
-                                                       float *__restrict__ d_h16, float *__restrict__ d_directions)
+                                                       float *__restrict__ d_h16, float *__restrict__ d_directions, int dir_per_sample)
 {
     extern __shared__ __align__(16) float smem[];
     float *sW3 = smem;
@@ -264,7 +264,10 @@ __global__ void __launch_bounds__(TS) color_bwd_kernel(LseFieldParams P, LseFiel
                 sh16_bwd(v, g16, dv);
                 const float sc = P.sh_shifted ? 0.5f : 1.0f;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) red_add(d_directions + 3 * (int64_t)ray + j, dv[j] * sc);
+                for (int j = 0; j < 3; ++j) {
+                    if (dir_per_sample) d_directions[3 * i + j] = dv[j] * sc;         // [S,3], reduced per ray by ray_grad_packed_kernel
+                    else red_add(d_directions + 3 * (int64_t)ray + j, dv[j] * sc);
+                }
             }
             float4 *dst = reinterpret_cast<float4 *>(d_h16 + 16 * i);
             dst[0] = make_float4(0.0f, din[16], din[17], din[18]);
@@ -464,12 +467,12 @@ int simt_color_fwd(const LseFieldParams &P, const float *directions, const int32
 
 int simt_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *directions, const int32_t *ray_idx,
                    const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_rgb,
-                   float *d_h16, float *d_directions, cudaStream_t st)
+                   float *d_h16, float *d_directions, int dir_per_sample, cudaStream_t st)
 {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(color_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColorBwdSmem); attr = true; }
     color_bwd_kernel<<<persistent_grid(S_cap, 2), TS, kColorBwdSmem, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16,
-                                                                           d_rgb, d_h16, d_directions);
+                                                                           d_rgb, d_h16, d_directions, dir_per_sample);
     return check_launch("lse_field_color_bwd");
 }
 

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) color_bwd_tc_kernel(LseFieldPa
                                                                       const int32_t *__restrict__ app_id, int64_t S_cap,
                                                                       const int32_t *__restrict__ n_dev, const float *__restrict__ h16,
                                                                       const float *__restrict__ d_rgb, float *__restrict__ d_h16,
-                                                                      float *__restrict__ d_directions)
+                                                                      float *__restrict__ d_directions, int dir_per_sample)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     using L = ColorBwdSm;
@@ -255,7 +255,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) color_bwd_tc_kernel(LseFieldPa
                     sh16_bwd(v, g16, dv);
                     const float sc = P.sh_shifted ? 0.5f : 1.0f;
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) red_add(d_directions + 3 * (int64_t)ray + j, dv[j] * sc);
+                    for (int j = 0; j < 3; ++j) {
+                    if (dir_per_sample) d_directions[3 * i + j] = dv[j] * sc;         // [S,3], reduced per ray by ray_grad_packed_kernel
+                    else red_add(d_directions + 3 * (int64_t)ray + j, dv[j] * sc);
+                }
                 }
                 float4 *dst = reinterpret_cast<float4 *>(d_h16 + 16 * i);
                 dst[0] = make_float4(0.0f, x[16], x[17], x[18]);
@@ -477,14 +480,14 @@ static int bwd_grid(int64_t S_cap)
 
 int tc_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *directions, const int32_t *ray_idx,
                  const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_rgb,
-                 float *d_h16, float *d_directions, cudaStream_t st)
+                 float *d_h16, float *d_directions, int dir_per_sample, cudaStream_t st)
 {
     constexpr size_t smem_bytes = ColorBwdSm::BYTES;
     static_assert(smem_bytes <= 232448, "colour backward exceeds the 227 KiB shared-memory limit");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(color_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
     color_bwd_tc_kernel<<<bwd_grid(S_cap), BWD_THREADS, smem_bytes, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb,
-                                                                          d_h16, d_directions);
+                                                                          d_h16, d_directions, dir_per_sample);
     return check_launch("lse_field_color_bwd[tc]");
 }
 

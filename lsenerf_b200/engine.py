@@ -116,6 +116,35 @@ class ArenaAdam:
         self.hp_dev = torch.zeros(len(self.names), 4, device=dev)
         self.step_count = 0
         self._grad_scale = 1.0
+        self.det_shadows: Optional[Dict[str, torch.Tensor]] = None
+
+    # ---- deterministic accumulation (csrc/common.cuh:det_add) -------------------------------------------------------------------
+    def enable_deterministic(self) -> None:
+        """Route every atomic gradient accumulation that targets these arenas into 64-bit fixed-point shadows (order-independent
+        integer sums); flush_deterministic(name) folds a shadow back into the fp32 gradients and must run before that arena's
+        optimizer step.  Costs 8 bytes per parameter and one extra pass; meant for reproducible runs (bench burn-in, tests)."""
+        import ctypes
+        from . import _lib
+        if self.det_shadows is None:
+            self.det_shadows = {n: torch.zeros(a.numel, dtype=torch.int64, device=a.grad.device) for n, a in self.arenas.items()}
+        k = len(self.names)
+        bases = (ctypes.c_void_p * k)(*[self.arenas[n].grad.data_ptr() for n in self.names])
+        sizes = (ctypes.c_int64 * k)(*[self.arenas[n].numel * 4 for n in self.names])
+        shadows = (ctypes.c_void_p * k)(*[self.det_shadows[n].data_ptr() for n in self.names])
+        torch.cuda.synchronize()
+        rc = _lib.lib().lse_set_deterministic(k, ctypes.cast(bases, ctypes.c_void_p), ctypes.cast(sizes, ctypes.c_void_p),
+                                              ctypes.cast(shadows, ctypes.c_void_p))
+        if rc != 0:
+            raise RuntimeError(_lib.lib().lse_last_error().decode())
+
+    def disable_deterministic(self) -> None:
+        from . import _lib
+        torch.cuda.synchronize()
+        _lib.lib().lse_set_deterministic(0, None, None, None)
+
+    def flush_deterministic(self, name: str) -> None:
+        a = self.arenas[name]
+        call("lse_det_flush", P(a.grad), P(self.det_shadows[name]), a.numel, stream())
 
     def zero_grad(self, only: Optional[List[str]] = None) -> None:
         for n, a in self.arenas.items():
@@ -264,9 +293,14 @@ class GraphedStep:
     FIELD_GROUP = "fields"
 
     def __init__(self, pipeline: LSENeRFPipeline, optim: ArenaAdam, world_size: int = 1, use_graph: bool = True,
-                 device_store: bool = False) -> None:
+                 device_store: bool = False, deterministic: bool = False) -> None:
         self.pipeline, self.optim, self.world = pipeline, optim, world_size
         self.use_graph = use_graph
+        # deterministic: the gradients of a step do not depend on the order in which the atomics land (ArenaAdam.enable_deterministic
+        # must be active while this engine steps); every optimizer launch is preceded by the flush of its arena's fixed-point shadow
+        self.deterministic = deterministic
+        if deterministic:
+            optim.enable_deterministic()
         dm = pipeline.datamanager
         dm.lean = True                      # captured step: no launches for metadata the fused path never reads
         pipeline.lean = True                # ... nor for outputs the loss never reads (depth, detached linear, metrics)
@@ -290,6 +324,7 @@ class GraphedStep:
         self._loss_ring = None      # pinned host slots + events of step_async()
         self._ovf = None            # pinned slot + event of the capacity-overflow poll
         self.side = torch.cuda.Stream(device=dm.device) if torch.cuda.is_available() else None
+        self.cap_stream = torch.cuda.Stream(device=dm.device) if torch.cuda.is_available() else None
         self.ev_b = torch.cuda.Event() if self.side is not None else None
         self.ev_opt: Optional[torch.cuda.Event] = None        # field optimizer of the previous step (side stream)
         self.early = [n for n in optim.names if n != self.FIELD_GROUP]   # groups stepped on the main stream right after B
@@ -312,32 +347,46 @@ class GraphedStep:
     def capture(self, start_step: int = 0) -> None:
         self.step_no = start_step
         self.optim.set_step(max(self.optim.step_count, 1))
-        s = torch.cuda.Stream()
+        # warm-up (allocator, lazy inits) on the SAME stream the graphs are captured on: autograd remembers the stream a node or a
+        # gradient accumulator was created on and runs its backward there, and a backward that hops to a stream outside the capture
+        # invalidates it
+        s = self.cap_stream
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(3):                       # warm-up on a side stream (allocator, lazy inits, attribute calls)
+            for _ in range(3):
                 self._phase_a(); self._phase_b()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if not self.use_graph:
+            self._clear_shadows()
             return
         self.graph_a = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_a):
+        with torch.cuda.graph(self.graph_a, stream=self.cap_stream):
             self._phase_a()
         # B gets its OWN memory pool: graph C (side stream) reads B's buffers while A of the next step is already running, and
         # inside one pool the allocator would have handed A's freed temporaries (march slabs, run lists) to B's workspace
         self.graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_b):
+        with torch.cuda.graph(self.graph_b, stream=self.cap_stream):
             self.loss_out = self._phase_b()
         if self._deferred() is not None:
             self.graph_c = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_c, pool=self.graph_b.pool()):
+            with torch.cuda.graph(self.graph_c, pool=self.graph_b.pool(), stream=self.cap_stream):
                 ops.run_deferred_table_scatter(self._deferred())
         for name in self.optim.names:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self.cap_stream):
+                if self.deterministic:
+                    self.optim.flush_deterministic(name)
                 self.optim.apply(only=[name])
             self.graph_opt[name] = g
+        self._clear_shadows()
+
+    def _clear_shadows(self) -> None:
+        """the warm-up passes of capture() accumulated into the fixed-point shadows without an optimizer step to flush them"""
+        if self.deterministic and self.optim.det_shadows is not None:
+            torch.cuda.synchronize()
+            for t in self.optim.det_shadows.values():
+                t.zero_()
 
     def _deferred(self):
         o = (self.ctx or {}).get("opts")
@@ -348,16 +397,23 @@ class GraphedStep:
         for n in names:
             self.optim.upload_hp(n)
         if world > 1 and self.optim.symmetric:
+            if self.deterministic:
+                for n in names:
+                    self.optim.flush_deterministic(n)
             self.optim.apply_collective(only=names, channel=channel)
         else:
             if world > 1:
                 import torch.distributed as dist
                 for n in names:
+                    if self.deterministic:
+                        self.optim.flush_deterministic(n)
                     dist.all_reduce(self.optim.arenas[n].grad, op=dist.ReduceOp.SUM)
             for n in names:
-                if n in self.graph_opt:
-                    self.graph_opt[n].replay()
+                if n in self.graph_opt and not (world > 1 and self.deterministic):
+                    self.graph_opt[n].replay()       # (deterministic: the captured graph starts with the flush)
                 else:
+                    if self.deterministic and world == 1:
+                        self.optim.flush_deterministic(n)
                     self.optim.apply(only=[n])
 
     def _poll_overflow(self, model) -> None:

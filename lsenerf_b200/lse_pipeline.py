@@ -89,7 +89,7 @@ class LSENeRFPipeline(nn.Module):
         cfg = m._epilogue_cfg(ev_out)
         rgb_pow = getattr(getattr(m, "rgb_mapper", None), "pow_coeff", None)
         evs_pow = getattr(m.evs_mapper, "pow_coeff", None)
-        w_one = m.rgb_to_one.weights.reshape(-1) if c.ev_one_dim == "learned" else None
+        w_one = m.rgb_to_one.weights if c.ev_one_dim == "learned" else None
         lin = out["rgb"].contiguous()
         rgb_final, ev, ev_lin = ops.epilogue(lin, cfg, rgb_pow, evs_pow, w_one)
         out["rgb"] = rgb_final

@@ -234,7 +234,7 @@ class LSENeRFModel(nn.Module):
         cfg = self._epilogue_cfg(ev_out)
         rgb_pow = getattr(getattr(self, "rgb_mapper", None), "pow_coeff", None)
         evs_pow = getattr(self.evs_mapper, "pow_coeff", None)
-        w_one = self.rgb_to_one.weights.reshape(-1) if c.ev_one_dim == "learned" else None
+        w_one = self.rgb_to_one.weights if c.ev_one_dim == "learned" else None
         lin = out["rgb"]
         rgb_final, ev, ev_lin = ops.epilogue(lin, cfg, rgb_pow, evs_pow, w_one)
         out["rgb"] = rgb_final

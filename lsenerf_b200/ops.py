@@ -31,6 +31,23 @@ def _acc_grad(p: Tensor) -> Tensor:
     return p.grad
 
 
+# Gradients of leaf parameters (camera-optimizer tensors, mapper coefficients) are accumulated by the backward kernels straight into
+# p.grad instead of into a zero-filled temporary that autograd then adds to p.grad: two launches less per tensor, and -- with the
+# engine's flat gradient arenas -- every atomic accumulation of the step lands inside an arena, which is what the deterministic
+# accumulation mode (lse_set_deterministic) keys on.  False restores pure-autograd returns.
+ACCUMULATE_PARAM_GRADS = True
+
+
+def _grad_target(p: Optional[Tensor], wanted: bool, tag: str = ""):
+    """-> (buffer the kernel accumulates into or None, value backward() returns for this input)."""
+    if p is None or not wanted:
+        return None, None
+    if ACCUMULATE_PARAM_GRADS and tag in os.environ.get("LSE_ACC_TAGS", "interp,scale,delta,epi") and p.is_leaf and p.requires_grad and p.is_contiguous() and p.dtype == torch.float32:
+        return _acc_grad(p), None
+    z = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return z, z
+
+
 # =================================================================================================================
 # (a) ray generation
 # =================================================================================================================
@@ -50,18 +67,22 @@ class _PoseInterp(torch.autograd.Function):
         ctx.save_for_backward(ct, ctrl_ts, ts, dM if dM is not None else ct.new_empty(0),
                               scale if scale is not None else ct.new_empty(0))
         ctx.meta = (n, n_virtual, t_off, t_step, dM is not None, scale is not None)
+        ctx.leaves = (ctrl_tangents, scale)
         return out
 
     @staticmethod
     def backward(ctx, d_c2w):
         ct, ctrl_ts, ts, dM, scale = ctx.saved_tensors
         n, n_virtual, t_off, t_step, has_dM, has_scale = ctx.meta
-        d_ct = torch.zeros_like(ct)
-        d_scale = torch.zeros(1, device=ct.device) if (has_scale and has_dM) else None
+        p_ct, p_scale = ctx.leaves
+        d_ct, r_ct = _grad_target(p_ct, ctx.needs_input_grad[0], "interp")
+        if d_ct is None:
+            d_ct = torch.zeros_like(ct)
+        d_scale, r_scale = _grad_target(p_scale, bool(has_scale and has_dM and ctx.needs_input_grad[1]), "scale")
         call("lse_pose_interp_bwd", P(ct), P(ctrl_ts), ct.shape[0], P(ts), n, n_virtual, t_off, t_step,
              P(dM) if has_dM else None, P(scale) if (has_scale and has_dM) else None, P(d_c2w.contiguous()), P(d_ct),
              P(d_scale), stream())
-        return d_ct, (d_scale if has_scale else None), None, None, None, None, None
+        return r_ct, r_scale, None, None, None, None, None
 
 
 def pose_interp(ctrl_tangents, ctrl_ts, times, n_virtual=1, exp_t=0.0, dM=None, scale=None) -> Tensor:
@@ -117,16 +138,20 @@ class _PoseDelta(torch.autograd.Function):
         oo = torch.empty_like(o); dd = torch.empty_like(d)
         call("lse_pose_delta_fwd", P(pa), pa.shape[0], P(ci), n, P(o), P(d), P(oo), P(dd), stream())
         ctx.save_for_backward(pa, ci, d)
+        ctx.leaf = pose_adjustment
         return oo, dd
 
     @staticmethod
     def backward(ctx, g_o, g_d):
         pa, ci, d = ctx.saved_tensors
         n = d.shape[0]
-        d_pa = torch.zeros_like(pa); d_o = torch.empty_like(d); d_d = torch.empty_like(d)
+        d_pa, r_pa = _grad_target(ctx.leaf, ctx.needs_input_grad[0], "delta")
+        if d_pa is None:
+            d_pa = torch.zeros_like(pa)
+        d_o = torch.empty_like(d); d_d = torch.empty_like(d)
         call("lse_pose_delta_bwd", P(pa), pa.shape[0], P(ci), n, P(d), P(g_o.contiguous()) if g_o is not None else None,
              P(g_d.contiguous()) if g_d is not None else None, P(d_pa), P(d_o), P(d_d), stream())
-        return d_pa, None, d_o, d_d
+        return r_pa, None, d_o, d_d
 
 
 def pose_delta(pose_adjustment, cam_idx, origins, directions):
@@ -464,7 +489,7 @@ class _FieldColor(torch.autograd.Function):
         g_d = torch.zeros_like(d) if ctx.needs_input_grad[0] else None
         cp = fw.c_params(); cg = _grads_struct(fw, bufs)
         call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), None, P(app) if ctx.has_app else None, S, None,
-             P(h16), P(d_rgb.contiguous()), P(d_h16), P(g_d), stream())
+             P(h16), P(d_rgb.contiguous()), P(d_h16), P(g_d), 0, stream())
         return (g_d, d_h16, None, None, bufs["W3"], bufs["b3"], bufs["W4"], bufs["b4"], bufs["W5"], bufs["b5"], bufs["emb"])
 
 
@@ -621,11 +646,21 @@ class _RenderRays(torch.autograd.Function):
         if fw.emb_mode not in (0, 1):
             bufs["emb"] = None
         need_o, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        g_o = torch.zeros_like(o) if need_o else None
-        g_d = torch.zeros_like(d) if (need_d or need_o) else None
         d_h16 = torch.empty(S_cap, 16, device=dev)
         cp = fw.c_params(); cg = _grads_struct(fw, bufs)
-        gd = g_d if need_d else None
+        defer = bool(fw.use_tensor_cores and opts.defer_table_scatter and bufs["table"] is not None)
+        if defer and (need_o or need_d):
+            # engine path: ray gradients from the stored Jacobian, reduced by one warp per ray in a fixed order and WRITTEN (no
+            # atomics, no zero-fill, bit-reproducible); the SH direction gradients take the same route through a per-sample buffer
+            g_o = torch.empty_like(o)
+            g_d = torch.empty_like(d)
+            dir_s = torch.empty(S_cap, 3, device=dev)
+            packed = True
+        else:
+            g_o = torch.zeros_like(o) if need_o else None
+            g_d = torch.zeros_like(d) if (need_d or need_o) else None
+            dir_s, packed = None, False
+        gd = g_d if (need_d or packed) else None
         if fw.use_tensor_cores:
             # the re-encode of the kept samples (gather-bound, 256-thread CTAs, no shared memory) needs d_sigma only: it runs on a
             # side stream under the colour backward (tensor/latency-bound, one 320-thread CTA per SM) and joins before the MLP
@@ -634,18 +669,18 @@ class _RenderRays(torch.autograd.Function):
             cur, side = torch.cuda.current_stream(), _side_stream(dev)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                defer = bool(opts.defer_table_scatter and bufs["table"] is not None)
                 jac = int(defer and (g_o is not None or gd is not None))      # ray gradients from the stored Jacobian, no re-gather
                 call("lse_field_density_bwd_encode", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
                      P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), jac, P(ws), nbytes, stream())
             call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
-                 P(h16), P(d_rgb), P(d_h16), P(gd), stream())
+                 P(h16), P(d_rgb), P(d_h16), P(dir_s if packed else gd), int(packed), stream())
             cur.wait_stream(side)
             if defer:
                 # the table gradient feeds the optimizer only: leave its scatter to the caller (engine: side stream, under the next
                 # step's ray generation); everything the rest of this backward pass needs is produced here
                 call("lse_field_density_bwd_rays", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
-                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), jac, P(ws), nbytes, stream())
+                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), jac,
+                     P(m.starts) if packed else None, P(m.counts) if packed else None, R, P(dir_s), P(ws), nbytes, stream())
                 opts.deferred_table = (fw, bufs, o, d, m, ws, nbytes, S_cap)
             else:
                 call("lse_field_density_bwd_finish", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
@@ -653,9 +688,9 @@ class _RenderRays(torch.autograd.Function):
             ws.record_stream(side)
         else:
             call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
-                 P(h16), P(d_rgb), P(d_h16), P(gd), stream())
+                 P(h16), P(d_rgb), P(d_h16), P(gd), 0, stream())
             _density_bwd(fw, cp, cg, o, d, m.ray_indices, m.t_starts, m.t_ends, S_cap, m.total, h16, d_sigma, d_h16, g_o, gd)
-        return (g_o, g_d if need_d else None, None, None, None, None, *[ret[k] for k in names])
+        return (g_o if need_o else None, g_d if need_d else None, None, None, None, None, *[ret[k] for k in names])
 
 
 def run_deferred_table_scatter(opts: RenderOpts) -> None:
@@ -716,6 +751,7 @@ class _Epilogue(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.save_for_backward(x, *(t if t is not None else x.new_empty(0) for t in (rgb_pow, evs_pow, to_one_w)))
         ctx.has = (rgb_pow is not None, evs_pow is not None, to_one_w is not None, ev_branch)
+        ctx.leaves = (rgb_pow, evs_pow, to_one_w)
         if not ev_branch:
             ev_out = x.new_empty(0); ev_lin = x.new_empty(0)
         ctx.mark_non_differentiable(ev_lin)
@@ -727,13 +763,14 @@ class _Epilogue(torch.autograd.Function):
         h_rp, h_ep, h_w, ev_branch = ctx.has
         R = x.shape[0]
         d_x = torch.empty_like(x)
-        d_rp = torch.zeros_like(rgb_pow) if h_rp else None
-        d_ep = torch.zeros_like(evs_pow) if h_ep else None
-        d_w = torch.zeros_like(to_one_w) if h_w else None
+        l_rp, l_ep, l_w = ctx.leaves
+        d_rp, r_rp = _grad_target(l_rp, h_rp and ctx.needs_input_grad[1], "epi")
+        d_ep, r_ep = _grad_target(l_ep, h_ep and ctx.needs_input_grad[2], "epi")
+        d_w, r_w = _grad_target(l_w, h_w and ctx.needs_input_grad[3], "epi")
         call("lse_epilogue_bwd", ctypes.byref(ctx.cfg), P(x), R, P(rgb_pow) if h_rp else None, P(evs_pow) if h_ep else None,
              P(to_one_w) if h_w else None, P(g_rgb.contiguous()) if g_rgb is not None else None,
              P(g_ev.contiguous()) if (g_ev is not None and ev_branch) else None, P(d_x), P(d_rp), P(d_ep), P(d_w), stream())
-        return d_x, d_rp, d_ep, d_w, None
+        return d_x, r_rp, r_ep, r_w, None
 
 
 def epilogue(rgb_lin, cfg, rgb_pow=None, evs_pow=None, to_one_w=None):

@@ -508,7 +508,7 @@ def test_tensor_core_backward_matches_fp32(dev, S, emb):
         d_h16 = torch.zeros(S_cap, 16, device=dev)
         cp, cg = w.c_params(), ops._grads_struct(w, bufs)
         call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(ri_c), P(app), S_cap, P(n_dev), P(h16), P(d_rgb),
-             P(d_h16), P(g_d), stream())
+             P(d_h16), P(g_d), 0, stream())
         ops._density_bwd(w, cp, cg, o, d, ri_c, t0_c, t1_c, S_cap, n_dev, h16, d_sigma, d_h16, g_o, g_d)
         torch.cuda.synchronize()
         out = {k: v for k, v in bufs.items() if v is not None}
