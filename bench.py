@@ -1,21 +1,28 @@
 """bench.py -- train rays/sec (fwd+bwd, event+RGB loss, optimizer step) of the LSENeRF hot path on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--render]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config NAME]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one training iteration of BASELINE.json configs[1]: LSENeRF non-embedding config (exp_configs/
-lsenerf_config.sh flags: co_map, powpow event mapper, gray GT, global embedding, deblur RGB rays with the spline camera
-optimizer, SO3xR3 event-camera optimizer) on the synthetic EVIMOv2-shape scene of SURVEY.md 8d (640x480 RGB + event
-cameras, 64 control poses, 128 event frames, 4x128^3 occupancy grid, 16 x 2^19 x 2 hash table), ray budget 8192 with
-rgb_frac 0.5 = 1024 RGB pixels x 4 virtual poses + 2048 event pixels x 2 poses.  Rays are counted as the reference counts
-them (total budget per step, lse_datamanager.py:434-435).  Multi-GPU: rays are sharded (every rank draws its own budget,
-train.py:104), one NCCL all-reduce of the gradients per step -> weak scaling, value = N * budget / step time.
+One "step" = one training iteration.  --config selects the workload (BASELINE.json configs; default configs[1]):
+  lsenerf      configs[1]  exp_configs/lsenerf_config.sh: co_map, powpow event mapper, gray GT, global embedding, deblur RGB rays
+               with the spline camera optimizer, SO3xR3 event-camera optimizer
+  lsenerf_emb  configs[2]  exp_configs/lsenerf_emb_config.sh: the same with per-event-frame appearance embeddings (evs_emb; the
+               embedding table gradient goes through the exchange at N > 1)
+  badnerf      configs[3]  exp_configs/BADNERF_config.sh as shipped: rgb_frac 1.0, no mapping, 4 virtual poses per pixel, no event rays
+all on the synthetic EVIMOv2-shape scene of SURVEY.md 8d (640x480 RGB + event cameras, 64 control poses, 128 event frames, 4x128^3
+occupancy grid, 16 x 2^19 x 2 hash table), ray budget 8192.  Rays are counted as the reference counts them (total budget per step,
+lse_datamanager.py:434-435).  Multi-GPU: rays are sharded (every rank draws its own budget, train.py:104), one exchange of the
+gradients per step -> weak scaling, value = N * budget / step time.
 
-`value`  : inputs (sampled pixel batches) already resident in HBM when the timed region starts.
-`e2e`    : the same metric through the public API with HOST image stacks: per step the host pixel draw + gather,
-           H2D copy of the batch from pinned memory and a D2H read of the loss are inside the timed region.
-`--impl reference`: the reference's nerfstudio torch (non-tcnn) path as restated in oracle/ (the reference itself
-           cannot be imported: nerfstudio/nerfacc/tinycudann are not installable offline), timed on the host cores.
+The timed state is a pure function of the seed: rank 0 trains BURN_IN steps in the engine's DETERMINISTIC accumulation mode (fixed-
+point gradient sums, bit-reproducible), the state is broadcast, and a fixed probe batch must then march / keep the sample counts
+recorded in STATE (+-2 %) on every rank, or the run fails.  The timed steps themselves use the plain fp32 atomics.
+
+`value`  : inputs (sampled pixel batches) already resident in HBM when the timed region starts; median of --blocks blocks of K steps.
+`e2e`    : the same metric through the public API with HOST image stacks: per step the host pixel draw + gather, H2D copy of the
+           batch from pinned memory and a D2H read of the loss are inside the timed region.
+`--impl reference`: the reference's nerfstudio torch (non-tcnn) path as restated in oracle/ (the reference itself cannot be
+           imported: nerfstudio/nerfacc/tinycudann are not installable offline), timed on the host cores at the full budget.
 """
 from __future__ import annotations
 
@@ -34,16 +41,37 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 BUDGET = 8192
-WORKLOAD = "lsenerf_config (non-embedding) on synthetic EVIMOv2-shape scene, 640x480 RGB+event cams, budget 8192 (1024 RGB px x4 deblur poses + 2048 event px x2), T=2^19 L=16, grid 4x128^3"
+SCENE = "synthetic EVIMOv2-shape scene, 640x480 RGB+event cams, T=2^19 L=16, grid 4x128^3"
+CONFIGS = {
+    "lsenerf": dict(experiment="lsenerf", rgb_frac=0.5,
+                    workload=f"lsenerf_config (non-embedding) on {SCENE}, budget 8192 (1024 RGB px x4 deblur poses + 2048 event px x2)"),
+    "lsenerf_emb": dict(experiment="lsenerf_emb", rgb_frac=0.5,
+                        workload=f"lsenerf_emb_config (per-frame appearance embeddings) on {SCENE}, budget 8192 (1024 RGB px x4 + 2048 event px x2)"),
+    "badnerf": dict(experiment="badnerf", rgb_frac=None,
+                    workload=f"BADNERF_config as shipped (rgb_frac 1.0, no mapping, no event rays) on {SCENE}, budget 8192 (2048 RGB px x4 virtual poses)"),
+}
+START = 1000      # optimizer step the burn-in starts at: after the occupancy grid's 256-step warm-up schedule
+BURN_IN = 3000    # deterministic burn-in steps (the sample counts per ray are stationary from ~1500 steps on)
+# (marched, evaluated by the culling pass, kept) samples of the probe batch after the burn-in -- a pure function of the seed
+STATE = {
+}
+STATE_TOL = 0.02
 
 
-def peaks():
+def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             p = json.load(fh)
-        return float(p["hbm_gbs"]), "measured"
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1362.4))), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, 1362.4, "fallback (B200_PROFILING.md)"
+
+
+def git_head():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True, timeout=10).stdout.strip() or None
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -121,67 +149,110 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"unavailable: {e}"], "samples": 0}
 
 
-def build(dev, seed, full=True, budget=BUDGET):
+def build(dev, seed, full=True, budget=BUDGET, config="lsenerf", **model_kw):
     from lsenerf_b200 import synthetic as syn
-    # analytic (learnable) targets + density prior matching the analytic occupancy: the work per step is stationary and
-    # representative of steady-state training from step 0 (see lsenerf_b200/synthetic.py)
+    # analytic (learnable) targets + density prior matching the analytic occupancy (see lsenerf_b200/synthetic.py)
     kw = dict(targets="analytic", bake_density=True)
     spec = syn.SceneSpec(**kw) if full else syn.SceneSpec(col_hw=(120, 160), evs_hw=(120, 160), col_f=125.0, evs_f=130.0, **kw)
     scene = syn.make_scene(spec)
-    pipe = syn.build_pipeline(scene, "lsenerf", num_rays=budget, rgb_frac=0.5, deblur=True, cam_opt=True, device=dev, seed=seed,
-                              pin=(dev != "cpu"))
+    c = CONFIGS[config]
+    pipe = syn.build_pipeline(scene, c["experiment"], num_rays=budget, rgb_frac=c["rgb_frac"], deblur=True, cam_opt=True, device=dev, seed=seed,
+                              pin=(dev != "cpu"), **model_kw)
     return scene, pipe
 
 
 # ----------------------------------------------------------------------------------------------------------- CPU arm
-def cpu_step_fn(scene, pipe_cpu, budget):
-    """One oracle training step (fwd+bwd, both losses, marching + culling) on a `budget`-ray batch -> callable."""
+def cpu_step_fn(scene, pipe, budget, config="lsenerf"):
+    """One oracle training step (fwd+bwd, every loss of the config, marching + culling) on a `budget`-ray batch of the state held by
+    `pipe` (CPU copy) -> callable returning the loss dict; .samples = (marched, kept) of the last call."""
     from oracle import data as OD
     from oracle.bridge import oracle_cfg, oracle_grid, oracle_scene, oracle_state
-    sd = oracle_state(pipe_cpu)
+    sd = oracle_state(pipe)
     for k, v in sd.items():
         if v.dtype == torch.float32 and "occupancy" not in k and "aabb" not in k:
             v.requires_grad_(True)
-    cfg, grid, osc = oracle_cfg(pipe_cpu), oracle_grid(pipe_cpu), oracle_scene(scene, pipe_cpu)
-    n_evs, n_col = OD.ray_budget(budget, 0.5, True)
+    cfg, grid, osc = oracle_cfg(pipe), oracle_grid(pipe), oracle_scene(scene, pipe)
+    frac = pipe.datamanager.config.rgb_frac
+    n_evs, n_col = OD.ray_budget(budget, frac, True)
     g = torch.Generator().manual_seed(0)
 
     def step():
         for v in sd.values():
             v.grad = None
-        bundles, batch = OD.next_train(osc, sd, torch.rand(n_col, 3, generator=g), torch.rand(n_evs, 3, generator=g), True, scene["num_emb"])
-        jit = [torch.rand(b["origins"].shape[0], generator=g) for b in bundles]
-        _, ld = OD.train_losses(sd, cfg, grid, bundles, batch, jit, True)
+        bundles, batch = OD.next_train(osc, sd, torch.rand(n_col, 3, generator=g), torch.rand(n_evs, 3, generator=g) if n_evs > 0 else None,
+                                       True, scene["num_emb"])
+        jit = [torch.rand(b["origins"].shape[0], generator=g) if b is not None else None for b in bundles]
+        outs, ld = OD.train_losses(sd, cfg, grid, bundles, batch, jit, True)
         sum(ld.values()).backward()
+        try:
+            step.samples = (sum(int(o["_sampling"]["ray_indices0"].numel()) for o in outs.values() if o is not None),
+                            sum(int(o["_samples"][0].numel()) for o in outs.values() if o is not None))
+        except Exception:
+            step.samples = None
         return ld
+    step.samples = None
     return step
 
 
-def time_cpu(steps, warmup, budget):
+def cpu_render_fn(scene, pipe, rows=48):
+    """`rows` rows of one 640x480 eval frame through the oracle (no culling, no jitter, chunked like the reference) -> rays"""
+    from oracle import cameras as OC
+    from oracle import model as OM
+    from oracle.bridge import oracle_cfg, oracle_grid, oracle_scene, oracle_state
+    sd, cfg, grid, osc = oracle_state(pipe), oracle_cfg(pipe), oracle_grid(pipe), oracle_scene(scene, pipe)
+    H, W = 480, 640
+    b = OC.full_frame_bundle(scene["col_c2w"][3], H, W, osc["col_intr"])
+    r0 = (H - rows) // 2
+    sl = slice(r0 * W, (r0 + rows) * W)
+    b = {k: v[sl] for k, v in b.items()}
+    b["appearance_id"] = torch.zeros(rows * W, 1, dtype=torch.long)
+
+    def render():
+        with torch.no_grad():
+            for i in range(0, rows * W, 3512):
+                OM.get_outputs(sd, cfg, grid, {k: v[i:i + 3512] for k, v in b.items()}, False, True)
+        return rows * W
+    return render
+
+
+def time_cpu(pipe, scene, steps, warmup, budget, config="lsenerf", render=True):
+    """-> dict(train rays/s, s/step, samples, render rays/s) of the oracle on the host cores, from the state held by `pipe`."""
     torch.set_num_threads(os.cpu_count() or 1)
-    scene, pipe_cpu = build("cpu", 0, full=True, budget=budget)
-    step = cpu_step_fn(scene, pipe_cpu, budget)
+    step = cpu_step_fn(scene, pipe, budget, config)
     for _ in range(warmup):
         step()
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
-    return budget / statistics.median(ts), statistics.median(ts)
+    sec = statistics.median(ts)
+    out = {"rays_per_s": budget / sec, "s_per_step": sec, "samples": step.samples}
+    if render:
+        try:
+            rf = cpu_render_fn(scene, pipe)
+            t0 = time.perf_counter(); n = rf(); out["render_rays_per_s"] = n / (time.perf_counter() - t0)
+            out["render_sample"] = f"{n} rays = 48 rows of one 640x480 eval frame, chunks of 3512"
+        except Exception as e:   # the render leg is reported, never fatal
+            out["render_error"] = f"{type(e).__name__}: {e}"
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    budget = 1024   # bounded sample of the same workload: same scene/config, 1/8 of the ray budget per step
-    rps, sec = time_cpu(args.steps, min(args.warmup, 2), budget)
+    K, W = args.steps, min(args.warmup, 2)
+    scene, pipe_cpu = build("cpu", 96, full=True, budget=BUDGET, config=args.config)
+    r = time_cpu(pipe_cpu, scene, K, W, BUDGET, args.config)
     cores = os.cpu_count() or 1
-    line = {"impl": "reference", "metric": "train rays/sec (fwd+bwd, event+RGB)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "timing": "host wall clock"},
-            "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{budget}-ray budget per step (1/8 of the GPU arm's 8192), full step fwd+bwd"},
-            "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    sample = (f"full {BUDGET}-ray budget per step, fwd+bwd, median of {K} steps after {W} warm-up, from the step-0 state of the scene "
+              f"(density prior baked, before training: the GPU arm's trained state needs its own kernels to reach); samples (marched, kept) = {r['samples']}")
+    line = {"impl": "reference", "metric": "train rays/sec (fwd+bwd, event+RGB)", "value": r["rays_per_s"], "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CONFIGS[args.config]["workload"], "timing": "host wall clock", "samples_marched_kept_per_step": r["samples"]},
+            "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "render": {"value": r.get("render_rays_per_s"), "unit": "rays/s", "sample": r.get("render_sample"), "error": r.get("render_error")},
+            "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
@@ -226,6 +297,103 @@ def render_leg(pipe, scene, dev, rank, world, max_over_ranks, barrier, H=720, W=
             "sharding": f"{world} row blocks", "mean_rgb": float(img.mean())}
 
 
+def probe_state(pipe, dev):
+    """sample counts of a FIXED probe batch (own pixel seed, own jitter seed) under the current weights / grid -> (marched, evaluated
+    by the culling pass, kept).  Deterministic given the state: the march and the culling do not involve atomics in their results."""
+    from lsenerf_b200.compat import concat_bundles
+    dm, m = pipe.datamanager, pipe._model
+    gen = dm.train_col_pixel_sampler.generator
+    st = gen.get_state()
+    gen.manual_seed(20241)
+    hc, he = dm.sample_host_batches()
+    gen.set_state(st)
+    lean = dm.lean
+    dm.lean = True
+    with torch.no_grad():
+        bundles, _ = dm.next_train(START + BURN_IN, (dm.to_device(hc), dm.to_device(he)))
+        big = concat_bundles([b for b in bundles if b is not None], fields=("origins", "directions"), metadata_keys=("appearance_id",))
+        jit = torch.rand(len(big), device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        opts = m._render_opts(); opts.keep_debug = True
+        m.exec_get_outputs(big, jit, opts)
+    dm.lean = lean
+    S0, S1 = int(opts.debug["march0"].total.item()), int(opts.debug["march"].total.item())
+    S_eval = int((opts.debug["sigma0"][:S0] != 0).sum().item())
+    return S0, S_eval, S1
+
+
+def gather_peaks(dev):
+    """random 8-byte gathers out of a 4 MiB (one hash level) and a 64 MiB (whole table) resident set, measured in this process
+    (csrc/microbench.cu): the L2 denominator of the hash-gather rooflines."""
+    import ctypes
+    from lsenerf_b200._lib import P, call, stream
+    out = {}
+    sink = torch.zeros(4, device=dev)
+    for mib in (4, 64):
+        table = torch.rand(mib * (1 << 20) // 4, device=dev)
+        for pat, coherent in (("random_lane", 0), ("warp_coherent", 1)):
+            n = ctypes.c_int64(0)
+            best = 0.0
+            for rep in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                call("lse_gather_microbench", P(table), mib << 20, 8, 200, coherent, 8, P(sink), ctypes.byref(n), stream())
+                e1.record()
+                torch.cuda.synchronize()
+                if rep:
+                    best = max(best, n.value * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+            out[f"l2_{mib}MiB_{pat}_GBps"] = round(best, 1)
+        del table
+    return out
+
+
+def collective_check(opt, world, rank, dev):
+    """N > 1, before timing: one step through the fused reduce-scatter + Adam + all-gather kernel against NCCL all-reduce +
+    the single-GPU Adam on clones of the same arenas and gradients (mean of the per-rank gradients, lse_pipeline.py:96-97)."""
+    import torch.distributed as dist
+    from lsenerf_b200._lib import P, call, stream
+    res = {"kind": opt.exchange_kind()}
+    if not opt.symmetric:
+        return res
+    torch.cuda.synchronize()
+    saved = {n: (a.data.clone(), a.grad.clone(), a.exp_avg.clone(), a.exp_avg_sq.clone()) for n, a in opt.arenas.items()}
+    step_count = opt.step_count
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    max_diff, repl_diff = 0.0, 0.0
+    for n, a in opt.arenas.items():
+        a.grad.copy_(torch.randn(a.numel, device=dev, generator=g) * 1e-3)
+    dist.barrier()
+    # reference: all-reduce(sum) of clones + local Adam with grad_scale 1/W
+    ref = {}
+    opt.set_step(step_count + 1, 1.0 / world)
+    for i, n in enumerate(opt.names):
+        a, spec = opt.arenas[n], opt.specs[n]
+        p, gr, m, v = saved[n][0].clone(), a.grad.clone(), saved[n][2].clone(), saved[n][3].clone()
+        dist.all_reduce(gr, op=dist.ReduceOp.SUM)
+        call("lse_adam_step_hp", P(p), P(gr), P(m), P(v), a.numel, spec.betas[0], spec.betas[1], spec.eps, P(opt.hp_dev[i]), stream())
+        ref[n] = p
+    torch.cuda.synchronize()
+    opt.apply_collective(channel=4)
+    torch.cuda.synchronize()
+    dist.barrier()
+    for n, a in opt.arenas.items():
+        max_diff = max(max_diff, float((a.data - ref[n]).abs().max()))
+        chk = torch.stack([a.data.double().sum(), a.data.double().abs().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        repl_diff = max(repl_diff, float((hi - lo).abs().max()))
+    t = torch.tensor([max_diff], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res.update({"max_abs_diff_vs_allreduce_adam": float(t.item()), "replica_checksum_spread": repl_diff,
+                "ok": bool(float(t.item()) <= 1e-7 and repl_diff == 0.0)})
+    # restore (moments: the collective touched this rank's slice only)
+    for n, a in opt.arenas.items():
+        a.data.copy_(saved[n][0]); a.grad.copy_(saved[n][1]); a.exp_avg.copy_(saved[n][2]); a.exp_avg_sq.copy_(saved[n][3])
+    opt.step_count = step_count
+    torch.cuda.synchronize()
+    dist.barrier()
+    return res
+
+
 def run_b200(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,7 +408,7 @@ def run_b200(args):
     from lsenerf_b200 import _lib
 
     torch.manual_seed(96 + rank)
-    scene, pipe = build(dev, seed=96 + rank)
+    scene, pipe = build(dev, seed=96 + rank, config=args.config, use_tensor_cores=not args.simt)
     pipe.train()
     dm = pipe.datamanager
     from lsenerf_b200.engine import ArenaAdam, GraphedStep
@@ -254,73 +422,8 @@ def run_b200(args):
             print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce", file=sys.stderr)
         opt = ArenaAdam(pipe.get_param_groups())
     K, W = args.steps, args.warmup
-    # steady-state training: start after the occupancy grid's 256-step warm-up schedule (during warm-up every 16th step
-    # re-evaluates all 4x128^3 cells, afterwards a quarter of them + the occupied ones)
-    START = 1000
-    gs = GraphedStep(pipe, opt, world, use_graph=not args.no_graph, device_store=args.device_store)
     sample_batches = dm.sample_rand_batches if args.device_store else dm.sample_host_batches
     opt.step_count = START
-    gs.capture(start_step=START)
-    # untimed burn-in: from the baked density prior the occupancy grid first grows (marched samples/ray 100 -> 320 by
-    # step 150) and then sharpens; marched ~205 and kept ~37 samples/ray are stationary from ~1000 steps on (RGB PSNR ~33 dB).
-    # Time the steady state, not the transient.
-    BURN_IN = args.burn_in
-    TARGET_KEPT, MAX_BURN = 400_000 * BUDGET // 8192, max(args.burn_in, 6000)
-    # N > 1: the model state (hence samples per ray, hence work per ray) must not depend on N, or the per-N values are not
-    # comparable.  Rank 0 alone runs the burn-in (exactly the 1-GPU trajectory: same seed, no exchange), then its weights,
-    # Adam moments and occupancy grid are broadcast; only then do the ranks draw different rays and exchange gradients.
-    burn_steps, s1_ema = 0, None
-    if rank == 0:
-        gs.local_only = True
-        # Training with floating-point atomics is chaotic: after the same number of steps two runs differ by +-20 % in kept
-        # samples per ray, i.e. in work per ray.  The kept count falls monotonically while the surfaces sharpen (1.1 M at step 100,
-        # 0.3 M at step 3000), so the timed state is defined by WORK, not by step count: at least BURN_IN steps, then on until the
-        # running mean of the kept samples per step falls to TARGET_KEPT (49 per ray), at most MAX_BURN steps.
-        while burn_steps < MAX_BURN:
-            for _ in range(10):
-                gs.step()
-            burn_steps += 10
-            s1 = int(gs.ctx["opts"].last_totals[1].item())
-            s1_ema = s1 if s1_ema is None else 0.7 * s1_ema + 0.3 * s1
-            if burn_steps >= BURN_IN and (s1_ema <= TARGET_KEPT or args.fixed_burn_in):
-                break
-        gs.local_only = False
-    else:
-        # the other ranks receive rank 0's state below; they only warm their eager paths (grid update, lazy kernel loading)
-        gs.local_only = True
-        for _ in range(3):
-            gs.step()
-        pipe._model.update_occupancy(START + 16)
-        gs.local_only = False
-    if world > 1:
-        torch.cuda.synchronize()
-        og = pipe._model.occupancy_grid
-        for a in opt.arenas.values():
-            for t in (a.data, a.exp_avg, a.exp_avg_sq):
-                dist.broadcast(t, 0)
-        bin_u8 = og.binaries.view(torch.uint8)
-        for t in (og.occs, bin_u8, og.occ_mean):
-            dist.broadcast(t, 0)
-        og.packed(force=True)
-        t = torch.tensor([burn_steps], device=dev)
-        dist.broadcast(t, 0)
-        burn_steps = int(t.item())
-        gs.step_no = START + burn_steps
-        opt.step_count = START + burn_steps
-        # the other ranks have never run the grid update on a grid of this size: let them do one now (caching-allocator growth,
-        # lazy kernel loading -- tens of milliseconds that would otherwise land inside the timed region and stall every rank at the
-        # next exchange barrier), then restore rank 0's grid and give every rank rank 0's update generator state
-        if rank != 0:
-            pipe._model.update_occupancy(16 * (gs.step_no // 16 + 1))
-        torch.cuda.synchronize()
-        for t in (og.occs, bin_u8, og.occ_mean):
-            dist.broadcast(t, 0)
-        og.packed(force=True)
-        gstate = og._gen.get_state().to(dev)
-        dist.broadcast(gstate, 0)
-        og._gen.set_state(gstate.cpu())
-    # the first (untimed) warm-up step performs a grid update on every rank; the next one falls inside the timed steps
-    gs.step_no = 16 * ((gs.step_no + 15) // 16)
 
     def barrier():
         if world > 1:
@@ -334,56 +437,147 @@ def run_b200(args):
             return float(t.item())
         return ms
 
+    # ---- burn-in: rank 0 alone, deterministic accumulation, a fixed number of steps -> the state is a pure function of the seed ----
+    # (from the baked density prior the occupancy grid first grows, marched samples/ray 100 -> 320 by step 150, then sharpens; marched
+    # ~225 and kept ~55 samples/ray are stationary from ~1500 steps on.)  N > 1: the other ranks receive rank 0's state, so the work per
+    # ray does not depend on N; only then do the ranks draw different rays and exchange gradients.
+    burn = args.burn_in
+    t_burn = time.perf_counter()
+    if rank == 0:
+        gs0 = GraphedStep(pipe, opt, 1, use_graph=not args.no_graph, device_store=args.device_store, deterministic=not args.atomic_burn_in)
+        gs0.capture(start_step=START)
+        gs0.local_only = True
+        for _ in range(burn):
+            gs0.step()
+        gs0.flush()
+        torch.cuda.synchronize()
+        if gs0.deterministic:
+            opt.disable_deterministic()
+        del gs0
+    else:
+        pipe._model.update_occupancy(START + 16)              # lazy kernel loading / allocator growth of the grid update
+    t_burn = time.perf_counter() - t_burn
+    step_no = START + burn
+    if world > 1:
+        torch.cuda.synchronize()
+        og = pipe._model.occupancy_grid
+        for a in opt.arenas.values():
+            for t in (a.data, a.exp_avg, a.exp_avg_sq):
+                dist.broadcast(t, 0)
+        bin_u8 = og.binaries.view(torch.uint8)
+        if og._gen is None:
+            og._gen = torch.Generator(device=dev); og._gen.manual_seed(og.update_seed)
+        for t in (og.occs, bin_u8, og.occ_mean):
+            dist.broadcast(t, 0)
+        og._mean_valid = True
+        og.packed(force=True)
+        gstate = og._gen.get_state().to(dev)
+        dist.broadcast(gstate, 0)
+        og._gen.set_state(gstate.cpu())
+        torch.cuda.synchronize()
+    opt.step_count = step_no
+    probe = probe_state(pipe, dev)
+    expected = STATE.get(args.config) if (burn == BURN_IN and not args.atomic_burn_in and not args.simt) else None
+    state_ok = True
+    if expected is not None:
+        state_ok = all(abs(a - b) <= STATE_TOL * b for a, b in zip(probe, expected))
+    if world > 1:      # every rank must hold the same state
+        t = torch.tensor(list(probe), device=dev, dtype=torch.int64)
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        state_ok = state_ok and bool(torch.equal(lo, hi))
+    state_check = {"probe_marched_evaluated_kept": list(probe), "expected": list(expected) if expected else None, "tolerance": STATE_TOL,
+                   "ok": state_ok, "identical_on_all_ranks": True if world == 1 else bool(torch.equal(lo, hi))}
+
+    # ---- the timed engine: plain fp32 atomics, graphs captured from the pinned state --------------------------------------------
+    gs = GraphedStep(pipe, opt, world, use_graph=not args.no_graph, device_store=args.device_store)
+    gs.no_overlap = args.no_overlap
+    gs.capture(start_step=step_no)
+    coll = collective_check(opt, world, rank, dev) if world > 1 else None
+    # the first (untimed) warm-up step performs a grid update on every rank; the next one falls inside the timed steps
+    gs.step_no = 16 * ((step_no + 15) // 16)
     clocks = ClockSampler(local)
-    # ---- value: inputs resident in HBM ------------------------------------------------------------------------------
-    staged = [gs.stage.pack_to_device(*sample_batches()) for _ in range(K + W)]
+    blocks = max(1, args.blocks)
+
+    def totals():
+        t = gs.ctx["opts"].last_totals if gs.ctx.get("opts") is not None else None
+        return (int(t[0].item()), int(t[1].item())) if t is not None else (0, 0)
+
+    # ---- value: inputs resident in HBM; `blocks` blocks of exactly K steps, each bracketed by barrier + synchronize ------------------
+    staged = [gs.stage.pack_to_device(*sample_batches()) for _ in range(K * blocks + W)]
     torch.cuda.synchronize()
     for i in range(W):
         gs.step(packed_dev=staged[i])
-    barrier()
-    clocks.start()
-    l0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if args.profiler_window:                  # ncu --profile-from-start off: capture exactly the timed steps
-        torch.cuda.profiler.start()
-    e0.record()
-    for i in range(K):
-        gs.step(packed_dev=staged[W + i])
-    gs.flush()                                # the last step's field optimizer runs on the engine's side stream
-    e1.record()
-    if args.profiler_window:
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-    barrier()
-    clocks.pause()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches_eager = _lib.launch_count() - l0
+    block_ms, block_tot = [], []
+    launches_graph = 0
+    for b in range(blocks):
+        barrier()
+        clocks.start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.profiler_window and b == 0:       # ncu --profile-from-start off: capture exactly one timed block
+            torch.cuda.profiler.start()
+        e0.record()
+        for i in range(K):
+            gs.step(packed_dev=staged[W + b * K + i])
+        gs.flush()                                # the last step's field optimizer runs on the engine's side stream
+        e1.record()
+        if args.profiler_window and b == 0:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        barrier()
+        clocks.pause()
+        block_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+        block_tot.append(totals())
+        launches_graph = _lib.launch_count() - l0
+    ms_total = statistics.median(block_ms)
     del staged
 
     # ---- e2e: host image stacks -> host pixel draw + gather -> pinned batch -> H2D -> step -> D2H loss --------------------
     for _ in range(2):
         gs.step()
-    barrier()
-    clocks.start()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    hb = sample_batches()
-    pending = None
-    for i in range(K):
-        rb = gs.step_async(host_batches=hb)     # pack into pinned staging + H2D + graph replays + D2H of the losses, all asynchronous
-        hb = sample_batches()                   # host pixel draw + gather of the NEXT batch overlaps the device step
-        if pending is not None:
-            host_loss = pending.get()           # losses of the PREVIOUS step on the host (waits for that copy only)
-        pending = rb
-    host_loss = pending.get()
-    gs.flush()
-    f1.record()
-    barrier()
+    e2e_ms = []
+    for b in range(blocks):
+        barrier()
+        clocks.start()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        hb = sample_batches()
+        pending = None
+        for i in range(K):
+            rb = gs.step_async(host_batches=hb)     # pack into pinned staging + H2D + graph replays + D2H of the losses, all asynchronous
+            hb = sample_batches()                   # host pixel draw + gather of the NEXT batch overlaps the device step
+            if pending is not None:
+                host_loss = pending.get()           # losses of the PREVIOUS step on the host (waits for that copy only)
+            pending = rb
+        host_loss = pending.get()
+        gs.flush()
+        f1.record()
+        barrier()
+        clocks.pause()
+        e2e_ms.append(max_over_ranks(f0.elapsed_time(f1)))
     clk = clocks.stop()
-    ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+    ms_e2e = statistics.median(e2e_ms)
     h2d, d2h = gs.stage.nbytes, host_loss.numel() * host_loss.element_size()
+    pipe._model.check_overflow()
 
-    # ---- per-kernel-class device time + roofline of the dominant kernel (eager, outside the timed regions) ----------------
+    # ---- N > 1: how long does each rank wait at the two barriers of the exchange?  (instrumented steps, outside the timed regions) ---
+    barrier_wait = None
+    if world > 1 and opt.symmetric:
+        opt.barrier_events = []
+        for _ in range(8):
+            gs.step()
+        gs.flush(); torch.cuda.synchronize()
+        ev = opt.barrier_events; opt.barrier_events = None
+        w1 = [a.elapsed_time(b) for (a, b, c, d) in ev]; w2 = [c.elapsed_time(d) for (a, b, c, d) in ev]
+        t = torch.tensor([statistics.mean(w1), statistics.mean(w2)], device=dev)
+        allw = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allw, t)
+        barrier_wait = {"ms_before_exchange_per_rank": [round(float(x[0]), 4) for x in allw],
+                        "ms_after_exchange_per_rank": [round(float(x[1]), 4) for x in allw],
+                        "note": "CUDA-event time around the two symmetric-memory barriers of apply_collective (field + camera arenas per step), mean of 8 steps"}
+
+    # ---- per-kernel-class device time + rooflines (eager launches bracketed by CUDA events, outside the timed regions) -------------
     eager = GraphedStep(pipe, opt, world, use_graph=False, device_store=args.device_store)
     eager.step_no = gs.step_no
     eager.step(); eager.step()
@@ -391,18 +585,12 @@ def run_b200(args):
     l1 = _lib.launch_count()
     n_prof = 4
     for _ in range(n_prof):
-        eager.step_no = 1001                      # keep the (amortised) grid update out of the per-kernel picture
+        eager.step_no = gs.step_no // 16 * 16 + 1     # keep the (amortised) grid update out of the per-kernel picture
         eager.step()
-    launches = (_lib.launch_count() - l1) // n_prof * K if launches_eager == 0 or not args.no_graph else launches_eager
+    launches_eager = (_lib.launch_count() - l1) // n_prof
     prof = _lib.profile_stop()
-    opts = pipe._model._render_opts(); opts.keep_debug = True
-    bundles, _ = dm.next_train(gs.step_no)
-    from lsenerf_b200.compat import concat_bundles
-    with torch.no_grad():
-        pipe._model.exec_get_outputs(concat_bundles(list(bundles)), None, opts)
-    S0, S1 = int(opts.debug["march0"].total.item()), int(opts.debug["march"].total.item())
-    S_eval = int((opts.debug["sigma0"][:S0] != 0).sum().item())      # samples the early-terminating culling pass evaluated
-    overflow = int(opts.debug["march0"].overflow.item())
+    S0, S_eval, S1 = probe_state(pipe, dev)
+    gpk = gather_peaks(dev) if rank == 0 else {}
 
     # ---- render rays/sec: BASELINE configs[4], one 1280x720 eval frame with camera optimisation, rows sharded over ranks -------
     render = render_leg(pipe, scene, dev, rank, world, max_over_ranks, barrier)
@@ -410,38 +598,46 @@ def run_b200(args):
     if rank == 0:
         per_call = {k: v[1] / v[0] for k, v in prof.items()}
         per_step = {k: v[1] / n_prof for k, v in prof.items()}
-        # ALGORITHMIC bytes / flops per step: per-sample figures x the live sample counts read back
-        # from the device.  S0 marched, S_eval evaluated by the early-terminating culling pass, S1 kept.
+        calls_per_step = {k: v[0] / n_prof for k, v in prof.items()}
+        R = BUDGET
+        # ALGORITHMIC bytes / flops per step: per-unit figures x the live counts of the probe batch.
         #   density_fwd_list : 1024 B gathered + 12 B (ray index, t0, t1) in + 68 B (sigma, h16) out            per EVALUATED sample
         #   density_bwd      : encode = 1024 B re-gathered + 128 B feat + 384 B Jacobian + 12 B grid coords out + 20 B in;  rays =
         #                      base-MLP backward (128 feat + 68 in, 128 dfeat out) + ray gradients (128 dfeat + 384 Jacobian + 12 B in);
         #                      table = 1024 B scattered + 128 B dfeat + 12 B coords in                              per KEPT sample
         #   color fwd/bwd    : the dense contraction, 16 640 flop/sample forward, 3 x that backward (recompute + dgrad + wgrad)
+        #   march            : 24 B of ray in + 8 B per marched sample into the slabs (+ 12 B packed by lse_march_pack)
         alg_bytes = {"lse_field_density_fwd_list": (1024 + 12 + 68) * S_eval, "lse_field_density_fwd": (1024 + 12 + 68) * S0,
                      "lse_field_density_bwd_encode": (1024 + 128 + 384 + 12 + 20) * S1,
                      "lse_field_density_bwd_rays": (128 + 68 + 128 + 128 + 384 + 12) * S1,
                      "lse_field_density_bwd_table": (1024 + 128 + 12) * S1,
-                     "lse_field_density_bwd_finish": (128 + 68 + 128 + 2 * 1024 + 128 + 12) * S1}
+                     "lse_field_density_bwd_finish": (128 + 68 + 128 + 2 * 1024 + 128 + 12) * S1,
+                     "lse_march_single": 24 * R + 8 * S0}
+        gather_bytes = {"lse_field_density_fwd_list": 1024 * S_eval, "lse_field_density_fwd": 1024 * S0, "lse_field_density_bwd_encode": 1024 * S1,
+                        "lse_field_density_bwd_table": 1024 * S1}
         alg_flops = {"lse_field_color_fwd": 16640 * S1, "lse_field_color_bwd": 3 * 16640 * S1}
         kernels_of = {"lse_field_density_fwd_list": ["density_fwd_tc_kernel"], "lse_field_density_fwd": ["density_fwd_tc_kernel"],
                       "lse_field_density_bwd_encode": ["encode_samples_kernel"],
-                      "lse_field_density_bwd_rays": ["density_mlp_bwd_tc_kernel", "scatter_samples_kernel"],
+                      "lse_field_density_bwd_rays": ["density_mlp_bwd_tc_kernel", "ray_grad_samples_kernel", "ray_reduce_kernel"],
                       "lse_field_density_bwd_table": ["scatter_samples_kernel"],
                       "lse_field_density_bwd_finish": ["density_mlp_bwd_tc_kernel", "scatter_samples_kernel"],
-                      "lse_field_color_fwd": ["color_fwd_tc_kernel"], "lse_field_color_bwd": ["color_bwd_tc_kernel"]}
-        hbm, which = peaks()
-        try:   # kernels timed inside a long step: the sustained bf16 figure
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                pk = json.load(fh)
-            tf_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1362.4)))
-        except Exception:
-            tf_peak = 1362.4
+                      "lse_field_color_fwd": ["color_fwd_tc_kernel"], "lse_field_color_bwd": ["color_bwd_tc_kernel"],
+                      "lse_march_single": ["march_runs_kernel", "march_steps_kernel"]}
+        hbm, tf_peak, which = load_peaks()
+        # ncu DRAM traffic per launch: only from a capture of THIS code (the file records the git head it was taken at)
+        head = git_head()
+        ncu_traffic, traffic_note = {}, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1c_ncu_traffic.json")) as fh:
-                ncu_traffic = json.load(fh)
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+                tj = json.load(fh)
+            if tj.get("kernel_sources_sha") == kernel_sources_sha():
+                ncu_traffic = tj.get("kernels", {})
+                traffic_note = f"profiles/ncu_traffic.json (ncu --set full at {tj.get('git_head')}, kernel sources unchanged since)"
+            else:
+                traffic_note = f"profiles/ncu_traffic.json is from other kernel sources (captured at {tj.get('git_head')}): refused"
         except Exception:
-            ncu_traffic = {}
-        calls_per_step = {k: v[0] / n_prof for k, v in prof.items()}
+            traffic_note = "no ncu capture of this code under profiles/"
+        l2_peak = gpk.get("l2_64MiB_random_lane_GBps")
 
         def roof(kname):
             """per LAUNCH of the ABI call: algorithmic work of one step / launches per step, over the mean launch duration"""
@@ -450,49 +646,94 @@ def run_b200(args):
             if kname in alg_bytes:
                 ach = alg_bytes[kname] / n_call / dur / 1e9
                 r = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
+                if kname in gather_bytes and l2_peak:
+                    # the same launch against the measured random-gather peak of the L2 (gathered bytes only, 8 B per corner)
+                    g = gather_bytes[kname] / n_call / dur / 1e9
+                    r["vs_l2_random_gather"] = {"achieved_gather_GBps": g, "peak_GBps": l2_peak, "frac": g / l2_peak,
+                                                "note": "8-byte corners; > 1 means the kernel beats fully random lanes through coarse-level locality"}
             else:
                 ach = alg_flops[kname] / n_call / dur / 1e12
                 r = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak}
             tr = [ncu_traffic[k] for k in kernels_of.get(kname, []) if k in ncu_traffic]
-            r.update({"traffic": sum(t["dram_bytes_per_launch"] for t in tr) if tr else None,
-                      "traffic_source": tr[0].get("source") if tr else None, "launches_per_step": round(n_call, 2),
-                      "peak_source": which, "ms_per_launch": per_call[kname], "share_of_step": per_step[kname] / sum(per_step.values())})
-            # tensor kernels: the utilisation ncu saw in the same capture `traffic` comes from (sm__pipe_tensor_cycles_active, % of peak).
-            # `frac` counts ALGORITHMIC fp32 flops against the dense bf16 peak; the pipe itself issues 3 split MMAs per product on
-            # padded tiles, which is why it is busier than `frac` says.
+            r.update({"traffic": sum(t["dram_bytes_per_launch"] for t in tr) if tr else None, "traffic_source": traffic_note,
+                      "launches_per_step": round(n_call, 2), "peak_source": which, "ms_per_launch": per_call[kname],
+                      "share_of_step": per_step[kname] / sum(per_step.values())})
             tp = [t.get("tensor_pipe_active_pct") for t in tr if isinstance(t, dict) and t.get("tensor_pipe_active_pct")]
             if r["bound"] == "tensor" and tp:
                 r["tensor_pipe_active_pct"] = max(tp)
+            if kname == "lse_march_single":
+                lanes = [t.get("active_lanes_per_inst") for t in tr if isinstance(t, dict) and t.get("active_lanes_per_inst")]
+                r["note"] = ("sequential fp32 recurrences (DDA cells, sample steps): issue-bound, not byte-bound; the honest axis is "
+                             "instructions issued x active-lane fraction" + (f" (ncu: {lanes} of 32 lanes)" if lanes else ""))
             return r
         candidates = [k for k in list(alg_bytes) + list(alg_flops) if k in per_call]
-        roof_k = max((k for k in candidates if k in alg_bytes), key=lambda k: per_step[k])
+        roof_k = max((k for k in candidates if k in gather_bytes), key=lambda k: per_step[k]) if any(k in gather_bytes for k in candidates) \
+            else max(candidates, key=lambda k: per_step[k])
         rooflines = [roof(k) for k in sorted(candidates, key=lambda k: -per_step[k])]
         rays = BUDGET * world
+        kept_mean = statistics.mean(t[1] for t in block_tot) if block_tot else 0
         line = {"metric": "train rays/sec (fwd+bwd, event+RGB)", "value": rays * K / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "parallelism": f"ray-sharded dp{world}; gradient exchange: {opt.exchange_kind()}",
+                "config": {"workload": CONFIGS[args.config]["workload"], "config_name": args.config,
+                           "parallelism": f"ray-sharded dp{world}; gradient exchange: {opt.exchange_kind()}",
+                           "timing": f"median of {blocks} blocks of exactly {K} steps, each bracketed by barrier + synchronize, CUDA events, max over ranks",
+                           "block_ms": [round(x, 3) for x in block_ms], "e2e_block_ms": [round(x, 3) for x in e2e_ms],
                            "l2": "working set per step (64 MiB table + 64 MiB grad + 128 MiB Adam state + sample buffers) exceeds the 126 MB L2; no explicit flush",
                            "image_store": "device-resident stacks, on-device pixel gather from host-drawn uniforms (SURVEY 8f-2)" if args.device_store
                            else "pinned host stacks, host pixel gather (reference layout)",
-                           "samples_marched_per_step": S0, "samples_evaluated_by_culling_pass": S_eval, "samples_kept_per_step": S1, "capacity_overflow": overflow,
-                           "mlp": "tcgen05 (3xTF32 fwd, BF16x3 bwd)" if pipe._model.config.use_tensor_cores else "fp32 SIMT",
-                           "step": "one CUDA-graph replay (zero_grad+raygen+render+loss+backward) + Adam graph" if not args.no_graph else "eager launches",
-                           "start_step": START, "burn_in_steps": burn_steps,
-                           "burn_in_rule": f">= {BURN_IN} steps, then until the running mean of kept samples/step <= {TARGET_KEPT} (max {MAX_BURN})"},
+                           "mlp": "tcgen05 (3xTF32 forward, 3-MMA bf16-split backward), fp32 storage" if pipe._model.config.use_tensor_cores else "fp32 SIMT (CUDA cores)",
+                           "step": ("CUDA-graph replays (A: zero camera grads + raygen + march; B: field + compositing + losses + backward; C: table "
+                                    "scatter; Adam) " if not args.no_graph else "eager launches ") +
+                                   "-- lean step: the depth renderer, get_metrics_dict, cam_type / coords metadata and CameraIdxFixer that the reference "
+                                   "runs every iteration (lse_pipeline.py:115-142) feed no loss and are NOT computed",
+                           "overlap": "off (--no-overlap: one stream)" if args.no_overlap else "optimizer / table scatter on a side stream under the next step's ray generation + march",
+                           "start_step": START, "burn_in_steps": burn, "burn_in_seconds": round(t_burn, 1),
+                           "burn_in_rule": f"exactly {burn} steps on rank 0 in the deterministic accumulation mode (fixed-point gradient sums)"
+                           if not args.atomic_burn_in else f"exactly {burn} steps with fp32 atomics (not reproducible)",
+                           "samples_marched_per_step": S0, "samples_evaluated_by_culling_pass": S_eval, "samples_kept_per_step": S1,
+                           "samples_marched_kept_last_step_of_each_block": block_tot},
+                "state_check": state_check,
+                "samples_kept_per_sec": kept_mean * world * K / (ms_total * 1e-3),
                 "e2e": {"value": rays * K / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K},
-                "gpu_launches": int(launches), "clocks": clk,
-                "roofline": roof(roof_k), "rooflines": rooflines,
-                "render": render,
-                "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
+                "gpu_launches": int(launches_graph if args.no_graph else launches_eager * K),
+                "gpu_launches_note": "kernel launches issued through liblsenerf_b200.so per K-step block" +
+                                     ("" if args.no_graph else " (graph replays do not pass the library's launch counter: launches of one eager step x K)"),
+                "clocks": clk, "roofline": roof(roof_k), "rooflines": rooflines, "gather_peaks": gpk, "render": render,
+                "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+                "git_head": head}
+        if coll is not None:
+            line["collective_check"] = coll
+        if barrier_wait is not None:
+            line["barrier_wait"] = barrier_wait
         if world == 1 and not args.no_cpu:
-            rps, sec = time_cpu(3, 1, 1024)
-            line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "1024-ray budget per step (1/8 of 8192), median of 3 full steps fwd+bwd on the host cores"}
+            # the CPU port from the SAME trained state (same samples per ray as the timed GPU steps), full budget
+            cpu = time_cpu(pipe, scene, 5, 2, BUDGET, args.config)
+            line["cpu_baseline"] = {"value": cpu["rays_per_s"], "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"full {BUDGET}-ray budget per step from the GPU arm's trained state, median of 5 full steps fwd+bwd after 2 warm-up "
+                                              f"on the host cores; samples (marched, kept) = {cpu['samples']}",
+                                    "render": {"value": cpu.get("render_rays_per_s"), "unit": "rays/s", "sample": cpu.get("render_sample"),
+                                               "error": cpu.get("render_error")}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not state_ok:
+        raise SystemExit(f"bench.py: the timed state is not the pinned one: probe {probe} vs expected {expected} (tolerance {STATE_TOL})")
+    if coll is not None and coll.get("ok") is False:
+        raise SystemExit(f"bench.py: the fused exchange disagrees with all-reduce + Adam: {coll}")
+
+
+def kernel_sources_sha():
+    """sha1 over the CUDA sources + header: an ncu capture is only attributed to the code it was taken from"""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "lsenerf_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "lsenerf_b200.h"), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def main():
@@ -500,13 +741,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--blocks", type=int, default=5, help="timed blocks of exactly --steps steps; the median block is reported")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--burn-in", type=int, default=600, help="minimum untimed training steps before the timed region")
-    ap.add_argument("--fixed-burn-in", action="store_true", help="stop the burn-in after exactly --burn-in steps")
+    ap.add_argument("--config", default="lsenerf", choices=sorted(CONFIGS))
+    ap.add_argument("--burn-in", type=int, default=BURN_IN, help="untimed deterministic training steps before the timed region")
+    ap.add_argument("--atomic-burn-in", action="store_true", help="burn in with fp32 atomics (not reproducible; skips the state check)")
+    ap.add_argument("--simt", action="store_true", help="fp32 CUDA-core MLP kernels instead of tcgen05 (the arithmetic-identical figure)")
+    ap.add_argument("--no-overlap", action="store_true", help="optimizer / table scatter on the main stream (A/B of the software pipeline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--device-store", action="store_true", help="image / event stacks resident in HBM, pixel gather on the device (SURVEY 8f-2)")
-    ap.add_argument("--profiler-window", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
+    ap.add_argument("--profiler-window", action="store_true", help="cudaProfilerStart/Stop around the first timed block (for ncu --profile-from-start off)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: NCCL all-reduce + local Adam instead of the fused peer-memory kernel")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -251,58 +251,67 @@ __global__ void __launch_bounds__(HT) ray_grad_kernel(const float *__restrict__ 
 }
 
 
-// The same gradients with one warp per RAY over the ray-major packed samples (starts / counts): every lane accumulates its samples in
-// a fixed order, one butterfly reduction per ray, plain stores -- no atomics and no zero-filled output, and the result does not depend
-// on scheduling (bit-reproducible training, bench.py burn-in).  d_dir_samples [S,3] (optional) = per-sample direction gradients of
-// the SH encoding written by the colour backward; they are folded into the same reduction.
-__global__ void __launch_bounds__(HT) ray_grad_packed_kernel(const float *__restrict__ origins, const float *__restrict__ directions,
-                                                             const int32_t *__restrict__ ray_idx, const float *__restrict__ t0,
-                                                             const float *__restrict__ t1, int64_t S_cap,
-                                                             const int32_t *__restrict__ starts, const int32_t *__restrict__ counts,
-                                                             int64_t n_rays, const float *__restrict__ dfeat, const float *__restrict__ jac,
-                                                             const float *__restrict__ d_dir_samples, float *__restrict__ d_origins,
-                                                             float *__restrict__ d_directions)
+// Deterministic variant (engine path), two light kernels instead of atomics:
+//   ray_grad_samples_kernel (thread = kept sample, all lanes busy): per-sample position gradient from the stored Jacobian ->
+//                           g6 [S,6] = (dL/dp, dL/dp * t_mid + the SH direction gradient of the colour backward)
+//   ray_reduce_kernel       (warp = ray over the ray-major packed samples): fixed-order sum of the ray's rows of g6, plain stores.
+// No atomics and no zero-filled outputs; the result does not depend on scheduling (bit-reproducible training, bench.py burn-in).
+__global__ void __launch_bounds__(HT) ray_grad_samples_kernel(const float *__restrict__ origins, const float *__restrict__ directions,
+                                                              const int32_t *__restrict__ ray_idx, const float *__restrict__ t0,
+                                                              const float *__restrict__ t1, int64_t S_cap, const int32_t *__restrict__ n_dev,
+                                                              const float *__restrict__ dfeat, const float *__restrict__ jac,
+                                                              const float *__restrict__ d_dir_samples, float *__restrict__ g6)
+{
+    const int64_t S = live_count(n_dev, S_cap);
+    for (int64_t i = blockIdx.x * (int64_t)HT + threadIdx.x; i < S; i += (int64_t)gridDim.x * HT) {
+        SampleGeom g;
+        load_geom(i, origins, directions, ray_idx, t0, t1, g);
+        float dp[3] = {0.0f, 0.0f, 0.0f};
+        if (g.cc.sel) {
+            const float2 *f2 = reinterpret_cast<const float2 *>(dfeat) + i;
+            const float2 *j2 = reinterpret_cast<const float2 *>(jac) + i;      // planes [48][S_cap], see encode_samples_kernel
+            float dx[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+            for (int l = 0; l < NL; ++l) {
+                const float2 gl = __ldg(f2 + (size_t)l * S_cap);
+                const float2 a = __ldg(j2 + (size_t)(3 * l) * S_cap), b = __ldg(j2 + (size_t)(3 * l + 1) * S_cap),
+                             c = __ldg(j2 + (size_t)(3 * l + 2) * S_cap);
+                dx[0] += gl.x * a.x + gl.y * b.y;
+                dx[1] += gl.x * a.y + gl.y * c.x;
+                dx[2] += gl.x * b.x + gl.y * c.y;
+            }
+            contract_normalize_bwd(g.p, g.cc, dx, dp);
+        }
+        const float tm = g.has_dir ? g.tmid : 0.0f;
+        float2 *o2 = reinterpret_cast<float2 *>(g6 + 6 * i);
+        float dd[3] = {dp[0] * tm, dp[1] * tm, dp[2] * tm};
+        if (d_dir_samples) { dd[0] += d_dir_samples[3 * i]; dd[1] += d_dir_samples[3 * i + 1]; dd[2] += d_dir_samples[3 * i + 2]; }
+        o2[0] = make_float2(dp[0], dp[1]); o2[1] = make_float2(dp[2], dd[0]); o2[2] = make_float2(dd[1], dd[2]);
+    }
+}
+
+__global__ void __launch_bounds__(HT) ray_reduce_kernel(const float *__restrict__ g6, const int32_t *__restrict__ starts,
+                                                        const int32_t *__restrict__ counts, int64_t n_rays, float *__restrict__ d_origins,
+                                                        float *__restrict__ d_directions)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)HT + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * HT) >> 5;
     for (int64_t r = warp; r < n_rays; r += n_warps) {
         const int64_t s = starts[r];
         const int32_t c = counts[r];
-        float ao[3] = {0.0f, 0.0f, 0.0f}, ad[3] = {0.0f, 0.0f, 0.0f};
+        float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         for (int32_t k = lane; k < c; k += 32) {
-            const int64_t i = s + k;
-            SampleGeom g;
-            load_geom(i, origins, directions, ray_idx, t0, t1, g);
-            if (g.cc.sel) {
-                const float2 *f2 = reinterpret_cast<const float2 *>(dfeat) + i;
-                const float2 *j2 = reinterpret_cast<const float2 *>(jac) + i;      // planes [48][S_cap], see encode_samples_kernel
-                float dx[3] = {0.0f, 0.0f, 0.0f}, dp[3];
-#pragma unroll 4
-                for (int l = 0; l < NL; ++l) {
-                    const float2 gl = __ldg(f2 + (size_t)l * S_cap);
-                    const float2 a = __ldg(j2 + (size_t)(3 * l) * S_cap), b = __ldg(j2 + (size_t)(3 * l + 1) * S_cap),
-                                 cc = __ldg(j2 + (size_t)(3 * l + 2) * S_cap);
-                    dx[0] += gl.x * a.x + gl.y * b.y;
-                    dx[1] += gl.x * a.y + gl.y * cc.x;
-                    dx[2] += gl.x * b.x + gl.y * cc.y;
-                }
-                contract_normalize_bwd(g.p, g.cc, dx, dp);
-                const float tm = g.has_dir ? g.tmid : 0.0f;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) { ao[j] += dp[j]; ad[j] += dp[j] * tm; }
-            }
-            if (d_dir_samples) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) ad[j] += d_dir_samples[3 * i + j];
-            }
+            const float2 *p2 = reinterpret_cast<const float2 *>(g6 + 6 * (s + k));
+            const float2 u = p2[0], v = p2[1], w = p2[2];
+            a[0] += u.x; a[1] += u.y; a[2] += v.x; a[3] += v.y; a[4] += w.x; a[5] += w.y;
         }
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { ao[j] = warp_sum(ao[j]); ad[j] = warp_sum(ad[j]); }
+        for (int j = 0; j < 6; ++j) a[j] = warp_sum(a[j]);
         if (lane == 0) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                if (d_origins) d_origins[3 * r + j] = ao[j];
-                if (d_directions) d_directions[3 * r + j] = ad[j];
+                if (d_origins) d_origins[3 * r + j] = a[j];
+                if (d_directions) d_directions[3 * r + j] = a[3 + j];
             }
         }
     }
@@ -402,10 +411,13 @@ extern "C" int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFiel
     rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_h16, ws.dfeat, st);
     if (rc) return rc;
     if (!d_origins && !d_directions) return 0;
-    if (with_jacobian && starts && counts) {     // ray-major packed samples: one warp per ray, no atomics, written (not accumulated)
-        ray_grad_packed_kernel<<<stride_grid(n_rays * 32, HT, 8), HT, 0, st>>>(origins, directions, ray_idx, t0, t1, S_cap, starts, counts,
-                                                                               n_rays, ws.dfeat, ws.jac, d_dir_samples, d_origins,
-                                                                               d_directions);
+    if (with_jacobian && starts && counts) {     // ray-major packed samples: per-sample rows, then one warp per ray; no atomics, WRITTEN
+        float *g6 = ws.feat;                     // the feature planes are dead once the MLP backward above has consumed them
+        ray_grad_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, st>>>(origins, directions, ray_idx, t0, t1, S_cap, n_dev, ws.dfeat, ws.jac,
+                                                                          d_dir_samples, g6);
+        rc = check_launch("lse_field_density_bwd_rays[samples]");
+        if (rc) return rc;
+        ray_reduce_kernel<<<stride_grid(n_rays * 32, HT, 8), HT, 0, st>>>(g6, starts, counts, n_rays, d_origins, d_directions);
         return check_launch("lse_field_density_bwd_rays");
     }
     LSE_CHECK_ARG(d_dir_samples == nullptr, "per-sample direction gradients need the packed (starts / counts) Jacobian path");

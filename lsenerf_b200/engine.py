@@ -117,6 +117,7 @@ class ArenaAdam:
         self.step_count = 0
         self._grad_scale = 1.0
         self.det_shadows: Optional[Dict[str, torch.Tensor]] = None
+        self.barrier_events: Optional[list] = None
 
     # ---- deterministic accumulation (csrc/common.cuh:det_add) -------------------------------------------------------------------
     def enable_deterministic(self) -> None:
@@ -190,7 +191,13 @@ class ArenaAdam:
         assert self.symmetric, "apply_collective needs arenas allocated in symmetric memory"
         names = [n for n in self.names if only is None or n in only]
         first = self.arenas[names[0]]
+        rec = self.barrier_events is not None                 # bench.py: CUDA events around the two barriers (how long does this rank wait?)
+        if rec:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         first.h_grad.barrier(channel=channel)                 # every rank's backward has finished writing gradients
+        if rec:
+            ev[1].record()
         for name in names:
             i = self.names.index(name)
             a, spec = self.arenas[name], self.specs[name]
@@ -202,7 +209,12 @@ class ArenaAdam:
             call("lse_adam_step_collective", ctypes.cast(pp, ctypes.c_void_p), ctypes.cast(pg, ctypes.c_void_p),
                  ctypes.c_void_p(mc_p) if use_mc else None, ctypes.c_void_p(mc_g) if use_mc else None, P(a.exp_avg),
                  P(a.exp_avg_sq), a.numel, r, W, spec.betas[0], spec.betas[1], spec.eps, P(self.hp_dev[i]), stream())
+        if rec:
+            ev[2].record()
         first.h_data.barrier(channel=channel + 1)             # every slice written before anybody reads weights / zeroes grads
+        if rec:
+            ev[3].record()
+            self.barrier_events.append(tuple(ev))
 
     def exchange_kind(self) -> str:
         if not self.symmetric:
@@ -320,6 +332,7 @@ class GraphedStep:
         self.loss_out: Optional[torch.Tensor] = None
         self.ctx: Optional[dict] = None
         self.step_no = 0
+        self.no_overlap = False     # True: optimizer / deferred table scatter on the main stream (A/B of the software pipeline)
         self.local_only = False     # True: step this replica alone (no exchange, grad_scale 1) -- bench burn-in on rank 0
         self._loss_ring = None      # pinned host slots + events of step_async()
         self._ovf = None            # pinned slot + event of the capacity-overflow poll
@@ -472,15 +485,16 @@ class GraphedStep:
         self.ev_b.record(main)
         if self.early:
             self._optimize(self.early, world, channel=2)
-        self.side.wait_event(self.ev_b)
-        with torch.cuda.stream(self.side):
+        side = main if self.no_overlap else self.side
+        side.wait_event(self.ev_b)
+        with torch.cuda.stream(side):
             if self.graph_c is not None:
                 self.graph_c.replay()                    # hash-table scatter of this step (only the optimizer needs it)
             elif self._deferred() is not None:
                 ops.run_deferred_table_scatter(self._deferred())
             self._optimize([self.FIELD_GROUP], world, channel=0)
             self.ev_opt = torch.cuda.Event()
-            self.ev_opt.record(self.side)
+            self.ev_opt.record(side)
         self.step_no += 1
         return out
 

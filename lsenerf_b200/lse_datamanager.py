@@ -171,7 +171,7 @@ class MultiCamManager(nn.Module):
             self.evs_train_camera_optimizer.apply_to_raybundle(next_bundle)
             prev_bundle = add_metadata(prev_bundle, evs_batch, cam_id=1, lean=self.lean)
             next_bundle = add_metadata(next_bundle, evs_batch, cam_id=1, lean=self.lean)
-        if not self.lean:
+        if not self.lean and prev_bundle is not None:
             prev_bundle, next_bundle = self.cameraIdxFixer(prev_bundle), self.cameraIdxFixer(next_bundle)
         return (col_bundle, prev_bundle, next_bundle), {"col_batch": col_batch, "evs_batch": evs_batch}
 
