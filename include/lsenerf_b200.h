@@ -134,11 +134,12 @@ int lse_cull_generation(const int32_t *starts, const int32_t *counts, int64_t n_
 int lse_visibility(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
                    const float *t_ends, const float *sigmas, float early_stop_eps, float alpha_thre,
                    const float *occ_mean_dev, uint8_t *keep, int32_t *keep_counts, lse_stream_t stream);
-/* stable per-ray compaction of the kept samples (ray_indices, t_starts, t_ends, h16 [S,16], sigma [S]). */
+/* stable per-ray compaction of the kept samples (ray_indices, t_starts, t_ends, h16 [S,16], sigma [S], and -- optional -- the base-MLP
+ * activation masks uint64 [S] of LseFieldParams.relu_mask_density). */
 int lse_compact(const int32_t *starts, const int32_t *counts, const int32_t *new_starts, int64_t n_rays,
                 const uint8_t *keep, const float *t_starts, const float *t_ends, const float *h16,
-                const float *sigma, int32_t *ray_indices_out, float *t_starts_out, float *t_ends_out,
-                float *h16_out, float *sigma_out, lse_stream_t stream);
+                const float *sigma, const unsigned long long *mask, int32_t *ray_indices_out, float *t_starts_out,
+                float *t_ends_out, float *h16_out, float *sigma_out, unsigned long long *mask_out, lse_stream_t stream);
 
 /* 3P nerfacc OccGridEstimator.update_every_n_steps (inherited NGP callback; grid built at lse_nerf/lsenerf.py:184-188), step 1:
  * the cells to re-evaluate and their jittered sample points, without a host read of the occupied-cell count.
@@ -193,6 +194,13 @@ typedef struct {
     const float *emb; int32_t emb_rows; int32_t emb_mode;
     int32_t sh_shifted;        /* 1: SH evaluated on (d+1)/2 (nerfstudio torch path, lse_field.py:298) */
     int32_t use_tensor_cores;  /* 1: tcgen05/TMEM 3xTF32 MLP kernels, 0: fp32 SIMT kernels */
+    /* Activation patterns of the tensor-core path (optional, may be NULL): the forward kernels WRITE the ReLU masks of the hidden layers
+       (bit j = unit j active), the backward kernels READ them instead of re-deriving them from their own, differently rounded
+       recomputation of the hidden layer -- a unit within rounding of zero would otherwise be differentiated as active by one pass and
+       as inactive by the other.  relu_mask_density: uint64 [S] (base MLP, written at each sample's slot; lse_compact moves it with the
+       sample); relu_mask_color: uint64 [S,2] (the two hidden layers of the colour MLP).  Ignored by the fp32 CUDA-core kernels, whose
+       backward repeats the forward arithmetic exactly. */
+    unsigned long long *relu_mask_density; unsigned long long *relu_mask_color;
 } LseFieldParams;
 
 typedef struct {

@@ -142,6 +142,12 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
         read_acc<NH>(tmem_row, 0, h1);
 #pragma unroll
         for (int j = 0; j < NH; ++j) h1[j] = fmaxf(h1[j] + smem[L::B1 + j], 0.0f);
+        if (P.relu_mask_density && live) {         // the activation pattern the backward pass differentiates (LseFieldParams)
+            unsigned long long mk = 0ull;
+#pragma unroll
+            for (int j = 0; j < NH; ++j) mk |= (unsigned long long)(h1[j] > 0.0f) << j;
+            P.relu_mask_density[i] = mk;
+        }
         // ---- layer 2: [128 x 64] x W2^T -> TMEM cols [64,80) -----------------------------------------------------------------
 #pragma unroll
         for (int kc = 0; kc < NH / 4; ++kc) stage4(a_hi, a_lo, WG, kc, row, h1[4 * kc], h1[4 * kc + 1], h1[4 * kc + 2], h1[4 * kc + 3]);
@@ -248,6 +254,12 @@ __global__ void __launch_bounds__(WG *NWG, 1) color_fwd_tc_kernel(LseFieldParams
             const float *bias = smem + (layer == 0 ? L::B3 : L::B4);
 #pragma unroll
             for (int j = 0; j < NH; ++j) x[j] = fmaxf(x[j] + bias[j], 0.0f);
+            if (P.relu_mask_color && live) {
+                unsigned long long mk = 0ull;
+#pragma unroll
+                for (int j = 0; j < NH; ++j) mk |= (unsigned long long)(x[j] > 0.0f) << j;
+                P.relu_mask_color[2 * i + layer] = mk;
+            }
         }
         // output layer -> TMEM cols [64,80)
 #pragma unroll

@@ -197,11 +197,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) color_bwd_tc_kernel(LseFieldPa
             stage_row<NI, PIECE64>(bP, row, x);                 // ph0
             hs.publish_and_wait();
             read_row<NH>(trow, ccol::SCR, x);
-            uint64_t m1 = 0, m2 = 0;
+            // activation patterns: the forward pass's own (3xTF32) when it stored them, else from this bf16x2 recomputation
+            const bool fwd_masks = P.relu_mask_color != nullptr && live;
+            uint64_t m1 = fwd_masks ? P.relu_mask_color[2 * i] : 0ull, m2 = fwd_masks ? P.relu_mask_color[2 * i + 1] : 0ull;
 #pragma unroll
             for (int j = 0; j < NH; ++j) {
                 x[j] = fmaxf(x[j] + smf[L::B3 + j], 0.0f);
-                m1 |= (uint64_t)(x[j] > 0.0f) << j;
+                if (fwd_masks) x[j] = ((m1 >> j) & 1ull) ? x[j] : 0.0f;
+                else m1 |= (uint64_t)(x[j] > 0.0f) << j;
             }
             stage_row<NH, PIECE64>(bQ, row, x);                 // ph1: Q = H1
             hs.publish_and_wait();
@@ -209,7 +212,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) color_bwd_tc_kernel(LseFieldPa
 #pragma unroll
             for (int j = 0; j < NH; ++j) {
                 x[j] = fmaxf(x[j] + smf[L::B4 + j], 0.0f);
-                m2 |= (uint64_t)(x[j] > 0.0f) << j;
+                if (fwd_masks) x[j] = ((m2 >> j) & 1ull) ? x[j] : 0.0f;
+                else m2 |= (uint64_t)(x[j] > 0.0f) << j;
             }
             stage_row<NH, PIECE64>(bP, row, x);                 // ph2: P = H2
             hs.publish_and_wait();
@@ -425,11 +429,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) density_mlp_bwd_tc_kernel(LseF
             hs.publish_and_wait();
             float h[NH];
             read_row<NH>(trow, cden::SCR, h);
-            uint64_t m1 = 0;
+            const bool fwd_masks = P.relu_mask_density != nullptr && live;
+            uint64_t m1 = fwd_masks ? P.relu_mask_density[i] : 0ull;
 #pragma unroll
             for (int j = 0; j < NH; ++j) {
                 h[j] = fmaxf(h[j] + smf[L::B1 + j], 0.0f);
-                m1 |= (uint64_t)(h[j] > 0.0f) << j;
+                if (fwd_masks) h[j] = ((m1 >> j) & 1ull) ? h[j] : 0.0f;
+                else m1 |= (uint64_t)(h[j] > 0.0f) << j;
             }
             stage_row<NH, PIECE64>(bQ, row, h);                 // ph1: Q = H1
             hs.publish_and_wait();

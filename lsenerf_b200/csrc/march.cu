@@ -490,8 +490,9 @@ __global__ void compact_kernel(const int32_t *__restrict__ starts, const int32_t
                                const int32_t *__restrict__ new_starts, int64_t n_rays, const uint8_t *__restrict__ keep,
                                const float *__restrict__ t_starts, const float *__restrict__ t_ends,
                                const float4 *__restrict__ h16, const float *__restrict__ sigma,
+                               const unsigned long long *__restrict__ mask,
                                int32_t *__restrict__ ri_out, float *__restrict__ t0_out, float *__restrict__ t1_out,
-                               float4 *__restrict__ h16_out, float *__restrict__ sigma_out)
+                               float4 *__restrict__ h16_out, float *__restrict__ sigma_out, unsigned long long *__restrict__ mask_out)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -510,6 +511,7 @@ __global__ void compact_kernel(const int32_t *__restrict__ starts, const int32_t
                 t0_out[p] = t_starts[s + k];
                 t1_out[p] = t_ends[s + k];
                 if (sigma) sigma_out[p] = sigma[s + k];
+                if (mask) mask_out[p] = mask[s + k];
                 if (h16) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) h16_out[4 * p + j] = h16[4 * (s + k) + j];
@@ -885,14 +887,14 @@ extern "C" int lse_visibility(const int32_t *starts, const int32_t *counts, int6
 
 extern "C" int lse_compact(const int32_t *starts, const int32_t *counts, const int32_t *new_starts, int64_t n_rays,
                            const uint8_t *keep, const float *t_starts, const float *t_ends, const float *h16,
-                           const float *sigma, int32_t *ray_indices_out, float *t_starts_out, float *t_ends_out,
-                           float *h16_out, float *sigma_out, lse_stream_t stream)
+                           const float *sigma, const unsigned long long *mask, int32_t *ray_indices_out, float *t_starts_out,
+                           float *t_ends_out, float *h16_out, float *sigma_out, unsigned long long *mask_out, lse_stream_t stream)
 {
     if (n_rays <= 0) return 0;
     int threads = 256;
     compact_kernel<<<stride_grid(n_rays * 32, threads), threads, 0, (cudaStream_t)stream>>>(
-        starts, counts, new_starts, n_rays, keep, t_starts, t_ends, (const float4 *)h16, sigma, ray_indices_out,
-        t_starts_out, t_ends_out, (float4 *)h16_out, sigma_out);
+        starts, counts, new_starts, n_rays, keep, t_starts, t_ends, (const float4 *)h16, sigma, mask_out ? mask : nullptr, ray_indices_out,
+        t_starts_out, t_ends_out, (float4 *)h16_out, sigma_out, mask_out);
     return check_launch("lse_compact");
 }
 

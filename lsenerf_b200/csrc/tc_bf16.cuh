@@ -63,6 +63,9 @@ __device__ __forceinline__ void mma3(uint32_t d, uint32_t idesc, uint32_t &acc, 
         acc = 1;
         mma_bf16(d, desc_adv(a0, ao), desc_adv(b1, bo), idesc, 1);
         mma_bf16(d, desc_adv(a1, ao), desc_adv(b0, bo), idesc, 1);
+#ifdef LSE_BF16_LOLO
+        mma_bf16(d, desc_adv(a1, ao), desc_adv(b1, bo), idesc, 1);
+#endif
     }
 }
 

@@ -58,6 +58,8 @@ class LSENeRFModelConfig:
     # eval rendering: samples whose transmittance is below this are not evaluated / composited (their total weight is below it;
     # the reference composites them, lsenerf.py:283-318 with sigma_fn=None).  0 = evaluate every marched sample.
     eval_early_stop_eps: float = 1e-6
+    # training: early_stop_eps handed to the sampler (VolumetricSampler -> sampling(), nerfstudio default 1e-4; lse_grid_estimator.py:29)
+    train_early_stop_eps: float = 1e-4
 
     def __post_init__(self):  # lsenerf.py:86-99
         if self.evs_mapping_method is None or str(self.evs_mapping_method).lower() == "none":
@@ -193,7 +195,7 @@ class LSENeRFModel(nn.Module):
     def _render_opts(self) -> ops.RenderOpts:
         c, g = self.config, self.occupancy_grid
         if self.training:    # sigma_fn given: visibility culling with early_stop_eps 1e-4 and alpha_thre (lse_grid_estimator.py:109-143)
-            cull, eps, thre = True, 1e-4, c.alpha_thre
+            cull, eps, thre = True, c.train_early_stop_eps, c.alpha_thre
         else:                # sigma_fn None upstream: no culling; here only the invisible tail (T < eval_early_stop_eps) is dropped
             cull, eps, thre = c.eval_early_stop_eps > 0.0, c.eval_early_stop_eps, 0.0
         return ops.RenderOpts(binaries_u8=g.binaries_u8(), aabbs=g.aabbs, occ_mean_dev=g.occ_mean_dev(), occ_packed=g.packed(), near=c.near_plane,

@@ -259,8 +259,10 @@ def march(rays_o, rays_d, binaries_u8, aabbs, near, far, step, cone, jitter: Opt
     return MarchResult(ri, t0, t1, starts, counts, total, overflow, S_cap)
 
 
-def visibility_compact(m: MarchResult, sigma: Tensor, h16: Optional[Tensor], early_stop_eps, alpha_thre, occ_mean_dev):
-    """render_visibility_from_density + mask filter (lse_grid_estimator.py:109-143), device-side."""
+def visibility_compact(m: MarchResult, sigma: Tensor, h16: Optional[Tensor], early_stop_eps, alpha_thre, occ_mean_dev,
+                       relu_mask: Optional[Tensor] = None):
+    """render_visibility_from_density + mask filter (lse_grid_estimator.py:109-143), device-side.  relu_mask (int64 [S_cap], the base
+    MLP's activation masks of the tensor-core forward) is compacted with the samples: -> (march, sigma, h16, keep[, relu_mask])."""
     dev = sigma.device
     R = m.counts.numel()
     keep = torch.empty(m.S_cap, dtype=torch.uint8, device=dev)
@@ -271,9 +273,13 @@ def visibility_compact(m: MarchResult, sigma: Tensor, h16: Optional[Tensor], ear
     ri = torch.empty_like(m.ray_indices); t0 = torch.empty_like(m.t_starts); t1 = torch.empty_like(m.t_ends)
     h_out = torch.empty_like(h16) if h16 is not None else None
     s_out = torch.empty_like(sigma)
-    call("lse_compact", P(m.starts), P(m.counts), P(ns), R, P(keep), P(m.t_starts), P(m.t_ends), P(h16), P(sigma), P(ri), P(t0),
-         P(t1), P(h_out), P(s_out), stream())
-    return MarchResult(ri, t0, t1, ns, kc, total, m.overflow, m.S_cap), s_out, h_out, keep
+    k_out = torch.empty_like(relu_mask) if relu_mask is not None else None
+    call("lse_compact", P(m.starts), P(m.counts), P(ns), R, P(keep), P(m.t_starts), P(m.t_ends), P(h16), P(sigma), P(relu_mask), P(ri), P(t0),
+         P(t1), P(h_out), P(s_out), P(k_out), stream())
+    mc = MarchResult(ri, t0, t1, ns, kc, total, m.overflow, m.S_cap)
+    if relu_mask is not None:
+        return mc, s_out, h_out, keep, k_out
+    return mc, s_out, h_out, keep
 
 
 # =================================================================================================================
@@ -332,8 +338,12 @@ class FieldWeights:
     def tensors(self):
         return [self.table, self.W1, self.b1, self.W2, self.b2, self.W3, self.b3, self.W4, self.b4, self.W5, self.b5]
 
-    def c_params(self) -> _lib.LseFieldParams:
+    def c_params(self, relu_d: Optional[Tensor] = None, relu_c: Optional[Tensor] = None) -> _lib.LseFieldParams:
+        """relu_d int64 [S] / relu_c int64 [S,2]: activation-mask buffers of the tensor-core path (written by the forward kernels,
+        read by the backward kernels, see LseFieldParams)."""
         p = _lib.LseFieldParams()
+        p.relu_mask_density = relu_d.data_ptr() if relu_d is not None else None
+        p.relu_mask_color = relu_c.data_ptr() if relu_c is not None else None
         p.table = self.table.data_ptr(); p.scalings = self.scalings.data_ptr()
         p.levels = self.scalings.numel(); p.log2_T = self.log2_T
         for n in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "W5", "b5"):
@@ -360,11 +370,19 @@ def _grads_struct(fw: FieldWeights, bufs: dict) -> _lib.LseFieldGrads:
     return g
 
 
-def field_density_raw(fw: FieldWeights, origins, directions, ray_idx, t0, t1, S_cap, n_dev, want_h16: bool = True):
+def _relu_buf(fw: "FieldWeights", S_cap: int, width: int, dev) -> Optional[Tensor]:
+    """activation-mask buffer of the tensor-core path (LseFieldParams.relu_mask_*); None for the fp32 CUDA-core kernels"""
+    if not fw.use_tensor_cores:
+        return None
+    return torch.empty((S_cap,) if width == 1 else (S_cap, width), dtype=torch.int64, device=dev)
+
+
+def field_density_raw(fw: FieldWeights, origins, directions, ray_idx, t0, t1, S_cap, n_dev, want_h16: bool = True,
+                      relu_mask: Optional[Tensor] = None):
     """no-grad density pass -> (sigma [S_cap], h16 [S_cap,16] or None)."""
     dev = origins.device
     sigma = torch.empty(S_cap, device=dev); h16 = torch.empty(S_cap, 16, device=dev) if want_h16 else None
-    cp = fw.c_params()
+    cp = fw.c_params(relu_d=relu_mask)
     call("lse_field_density_fwd", ctypes.byref(cp), P(origins), P(directions), P(ray_idx), P(t0), P(t1), S_cap, P(n_dev),
          P(sigma), P(h16), stream())
     return sigma, h16
@@ -377,7 +395,8 @@ def _cull_bounds():
     return [0] + [x for x in b if x > 0] + [1 << 30]
 
 
-def field_density_culling(fw: FieldWeights, origins, directions, m: "MarchResult", early_stop_eps: float):
+def field_density_culling(fw: FieldWeights, origins, directions, m: "MarchResult", early_stop_eps: float,
+                          relu_mask: Optional[Tensor] = None):
     """The density pass that feeds visibility culling (lse_grid_estimator.py:109-127), evaluated in generations along the rays:
     a ray whose transmittance has fallen below early_stop_eps after its first `lo` samples cannot keep any later sample
     (sigma >= 0), so the field is not evaluated there; those samples keep sigma = 0, which the visibility test rejects exactly
@@ -387,7 +406,7 @@ def field_density_culling(fw: FieldWeights, origins, directions, m: "MarchResult
     sigma = torch.zeros(S_cap, device=dev); h16 = torch.empty(S_cap, 16, device=dev)
     depth = torch.empty(R, device=dev)
     lst = torch.empty(S_cap, dtype=torch.int32, device=dev); n_list = torch.empty(1, dtype=torch.int32, device=dev)
-    cp = fw.c_params()
+    cp = fw.c_params(relu_d=relu_mask)
     b = _cull_bounds()
     for g in range(len(b) - 1):
         call("lse_cull_generation", P(m.starts), P(m.counts), R, P(m.t_starts), P(m.t_ends), P(sigma), P(depth), b[g - 1] if g else 0,
@@ -397,9 +416,9 @@ def field_density_culling(fw: FieldWeights, origins, directions, m: "MarchResult
     return sigma, h16
 
 
-def field_color_raw(fw: FieldWeights, directions, ray_idx, app_id, S_cap, n_dev, h16):
+def field_color_raw(fw: FieldWeights, directions, ray_idx, app_id, S_cap, n_dev, h16, relu_mask: Optional[Tensor] = None):
     rgb = torch.empty(S_cap, 3, device=h16.device)
-    cp = fw.c_params()
+    cp = fw.c_params(relu_c=relu_mask)
     call("lse_field_color_fwd", ctypes.byref(cp), P(directions), P(ray_idx), P(app_id), S_cap, P(n_dev), P(h16), P(rgb), stream())
     return rgb
 
@@ -436,7 +455,8 @@ class _FieldDensity(torch.autograd.Function):
         o = _f32(origins, "origins")
         d = _f32(directions, "directions") if directions is not None else None
         S = o.shape[0]
-        sigma, h16 = field_density_raw(fw, o, d, None, t0, t1, S, None)
+        ctx.relu = _relu_buf(fw, S, 1, o.device)
+        sigma, h16 = field_density_raw(fw, o, d, None, t0, t1, S, None, relu_mask=ctx.relu)
         ctx.fw = fw
         ctx.save_for_backward(o, d if d is not None else o.new_empty(0), t0 if t0 is not None else o.new_empty(0),
                               t1 if t1 is not None else o.new_empty(0), h16)
@@ -453,7 +473,7 @@ class _FieldDensity(torch.autograd.Function):
         need_o, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and has_d
         g_o = torch.zeros_like(o) if need_o else None
         g_d = torch.zeros_like(o) if need_d else None
-        cp = fw.c_params(); cg = _grads_struct(fw, bufs)
+        cp = fw.c_params(relu_d=ctx.relu); cg = _grads_struct(fw, bufs)
         _density_bwd(fw, cp, cg, o, d if has_d else None, None, t0 if has_t else None, t1 if has_t else None, S, None, h16,
                      d_sigma.contiguous() if d_sigma is not None else None, d_h16.contiguous() if d_h16 is not None else None,
                      g_o, g_d)
@@ -471,7 +491,8 @@ class _FieldColor(torch.autograd.Function):
     def forward(ctx, directions, h16, app_id, fw: FieldWeights, W3, b3, W4, b4, W5, b5, emb):
         d = _f32(directions, "directions"); h16 = _f32(h16, "h16")
         S = d.shape[0]
-        rgb = field_color_raw(fw, d, None, app_id, S, None, h16)
+        ctx.relu = _relu_buf(fw, S, 2, d.device)
+        rgb = field_color_raw(fw, d, None, app_id, S, None, h16, relu_mask=ctx.relu)
         ctx.fw = fw
         ctx.save_for_backward(d, h16, app_id if app_id is not None else d.new_empty(0, dtype=torch.int32))
         ctx.has_app = app_id is not None
@@ -487,7 +508,7 @@ class _FieldColor(torch.autograd.Function):
         bufs["emb"] = torch.zeros_like(fw.emb) if want_emb else None
         d_h16 = torch.empty_like(h16)
         g_d = torch.zeros_like(d) if ctx.needs_input_grad[0] else None
-        cp = fw.c_params(); cg = _grads_struct(fw, bufs)
+        cp = fw.c_params(relu_c=ctx.relu); cg = _grads_struct(fw, bufs)
         call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), None, P(app) if ctx.has_app else None, S, None,
              P(h16), P(d_rgb.contiguous()), P(d_h16), P(g_d), 0, stream())
         return (g_d, d_h16, None, None, bufs["W3"], bufs["b3"], bufs["W4"], bufs["b4"], bufs["W5"], bufs["b5"], bufs["emb"])
@@ -590,17 +611,24 @@ class _RenderRays(torch.autograd.Function):
                        overflow=opts.overflow)
         assert m0.S_cap == S_cap and m0.counts.numel() == R
         culling = opts.cull and (opts.alpha_thre > 0.0 or opts.early_stop_eps > 0.0)
+        # tensor-core path with a backward to come: the forward kernels record the ReLU patterns the backward differentiates
+        want_bwd = any(ctx.needs_input_grad)
+        relu_d = _relu_buf(fw, S_cap, 1, o.device) if want_bwd else None
+        relu_c = _relu_buf(fw, S_cap, 2, o.device) if want_bwd else None
         if culling and opts.early_stop_eps > 0.0 and opts.early_terminate:
-            sigma, h16 = field_density_culling(fw, o, d, m0, opts.early_stop_eps)
+            sigma, h16 = field_density_culling(fw, o, d, m0, opts.early_stop_eps, relu_mask=relu_d)
         else:
-            sigma, h16 = field_density_raw(fw, o, d, m0.ray_indices, m0.t_starts, m0.t_ends, S_cap, m0.total)
+            sigma, h16 = field_density_raw(fw, o, d, m0.ray_indices, m0.t_starts, m0.t_ends, S_cap, m0.total, relu_mask=relu_d)
         if culling:
-            m, sigma_c, h16_c, keep = visibility_compact(m0, sigma, h16, opts.early_stop_eps, opts.alpha_thre, opts.occ_mean_dev)
+            res = visibility_compact(m0, sigma, h16, opts.early_stop_eps, opts.alpha_thre, opts.occ_mean_dev, relu_mask=relu_d)
+            m, sigma_c, h16_c, keep = res[:4]
+            relu_d = res[4] if relu_d is not None else None
         else:
             m, sigma_c, h16_c, keep = m0, sigma, h16, None
         if opts.keep_debug:
             opts.debug.update(march0=m0, sigma0=sigma, keep=keep, march=m)
-        rgb_s = field_color_raw(fw, d, m.ray_indices, app_id, S_cap, m.total, h16_c)
+        rgb_s = field_color_raw(fw, d, m.ray_indices, app_id, S_cap, m.total, h16_c, relu_mask=relu_c)
+        ctx.relu = (relu_d, relu_c)
         dev = o.device
         w = torch.empty(S_cap, device=dev)
         out = torch.empty(R, 3, device=dev); acc = torch.empty(R, 1, device=dev); dnum = torch.empty(R, 1, device=dev)
@@ -647,7 +675,7 @@ class _RenderRays(torch.autograd.Function):
             bufs["emb"] = None
         need_o, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         d_h16 = torch.empty(S_cap, 16, device=dev)
-        cp = fw.c_params(); cg = _grads_struct(fw, bufs)
+        cp = fw.c_params(relu_d=ctx.relu[0], relu_c=ctx.relu[1]); cg = _grads_struct(fw, bufs)
         defer = bool(fw.use_tensor_cores and opts.defer_table_scatter and bufs["table"] is not None)
         if defer and (need_o or need_d):
             # engine path: ray gradients from the stored Jacobian, reduced by one warp per ray in a fixed order and WRITTEN (no
