@@ -320,6 +320,21 @@ int lse_epilogue_bwd(const LseEpilogueCfg *cfg, const float *rgb_lin, int64_t n_
                      const float *d_ev_out, float *d_rgb_lin, float *d_rgb_pow, float *d_evs_pow,
                      float *d_rgb_to_one_w, lse_stream_t stream);
 
+/* The learned intensity mappers MLP_Mapper (dim 1) / RGB_MLP_Mapper (dim 3), lse_nerf/intensity_mappers.py:27-62: nerfstudio
+ * MLP(in_dim = out_dim = dim, num_layers = 4, layer_width = 16, ReLU, Sigmoid), torch implementation -- four nn.Linear ([out,in] + bias).
+ * Weights are taken as given (the reference's identity_init pre-fit, :8-25, is a training recipe, not part of the path).
+ * y [n,dim] = mapper(x [n,dim]); backward: dy -> dx (written, may be NULL) and the parameter gradients (accumulated; NULL = skipped). */
+typedef struct {
+    const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4;
+    int32_t dim; int32_t pad;
+} LseMlpMapper;
+typedef struct {
+    float *dW1, *db1, *dW2, *db2, *dW3, *db3, *dW4, *db4;
+} LseMlpMapperGrads;
+int lse_mlp_mapper_fwd(const LseMlpMapper *m /*[host]*/, const float *x, int64_t n, float *y, lse_stream_t stream);
+int lse_mlp_mapper_bwd(const LseMlpMapper *m /*[host]*/, const LseMlpMapperGrads *g /*[host]*/, const float *x, const float *dy,
+                       int64_t n, float *dx, lse_stream_t stream);
+
 /* get_loss_dict (lsenerf.py:392-439): losses[0] = MSE(col_target, col_pred);
  * losses[1] = evs_weight * MSE(log(next+1e-6) - log(prev+1e-6), evs) with to_gray when C == 3.
  * Also writes the gradients of each loss w.r.t. its predictions (unit upstream gradient). */

@@ -41,7 +41,16 @@ class LseEpilogueCfg(ctypes.Structure):
                                                "training", "deblur", "want_ev")]
 
 
-_STRUCTS = {"LseFieldParams": LseFieldParams, "LseFieldGrads": LseFieldGrads, "LseEpilogueCfg": LseEpilogueCfg}
+class LseMlpMapper(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4")] + [("dim", ctypes.c_int32), ("pad", ctypes.c_int32)]
+
+
+class LseMlpMapperGrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("dW1", "db1", "dW2", "db2", "dW3", "db3", "dW4", "db4")]
+
+
+_STRUCTS = {"LseFieldParams": LseFieldParams, "LseFieldGrads": LseFieldGrads, "LseEpilogueCfg": LseEpilogueCfg,
+            "LseMlpMapper": LseMlpMapper, "LseMlpMapperGrads": LseMlpMapperGrads}
 _SCALARS = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float,
             "double": ctypes.c_double, "lse_stream_t": ctypes.c_void_p}
 

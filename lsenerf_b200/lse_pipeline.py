@@ -84,22 +84,7 @@ class LSENeRFPipeline(nn.Module):
 
     def _finish(self, out, ev_out):
         """the post-compositing half of LSENeRFModel.get_outputs applied to a slice of the fused render."""
-        m = self._model
-        c = m.config
-        cfg = m._epilogue_cfg(ev_out)
-        rgb_pow = getattr(getattr(m, "rgb_mapper", None), "pow_coeff", None)
-        evs_pow = getattr(m.evs_mapper, "pow_coeff", None)
-        w_one = m.rgb_to_one.weights if c.ev_one_dim == "learned" else None
-        lin = out["rgb"].contiguous()
-        rgb_final, ev, ev_lin = ops.epilogue(lin, cfg, rgb_pow, evs_pow, w_one)
-        out["rgb"] = rgb_final
-        if ev.numel() > 0:
-            out["ev_out"] = ev
-            if not self.lean:
-                out["linear"] = torch.clamp(lin.detach(), 1e-5)
-            if c.map_mode == "co_map":
-                out["ev_linear"] = ev_lin
-        return out
+        return self._model.render_epilogue(out, ev_out, lean=self.lean)
 
     def get_param_groups(self) -> Dict[str, list]:
         return {**self.datamanager.get_param_groups(), **self._model.get_param_groups()}

@@ -229,26 +229,74 @@ class LSENeRFModel(nn.Module):
                                 getattr(self.evs_mapper, "kind", None), c.ev_one_dim, self.training,
                                 c.rgb_loss_type == "deblur", ev_out)
 
-    def get_outputs(self, ray_bundle: RayBundle, ev_out=False, jitter=None, **kwargs):
-        """lsenerf.py:329-377."""
-        out = self.exec_get_outputs(ray_bundle, jitter)
+    def _has_mlp_mapper(self) -> bool:
+        return getattr(getattr(self, "rgb_mapper", None), "kind", None) in ("mlp", "rgb_mlp") or \
+            getattr(self.evs_mapper, "kind", None) in ("mlp", "rgb_mlp")
+
+    def correct_evs_dim(self, x: Tensor) -> Tensor:
+        """lsenerf.py:255-263 for the composed epilogue: ThreeToOne (softmax-weighted sum) | ToGrayGT | identity."""
+        c = self.config
+        if c.ev_one_dim == "learned":
+            return torch.nn.functional.linear(x, torch.softmax(self.rgb_to_one.weights, dim=-1), None)
+        if c.ev_one_dim == "gt":
+            return x @ self.rgb_to_one.c2g_vec.to(x)
+        return x
+
+    def _composed_epilogue(self, out: dict, ev_out: bool, lean: bool = False) -> dict:
+        """lsenerf.py:333-375 statement by statement, for configurations with a learned MLP mapper: the mapper runs on its own kernel
+        (csrc/mapper_mlp.cu, forward + backward), the clamps / gray / group mean around it are elementwise device ops."""
+        c = self.config
+        clamp_out = torch.clamp(out["rgb"], 1e-5)
+        if c.use_mapping or c.map_mode == "rgb_evs":
+            if c.map_mode == "rgb_evs":
+                if ev_out or not self.training:
+                    out["ev_out"] = self.rgb_mapper(self.correct_evs_dim(clamp_out))
+                    out["linear"] = torch.cat([out["ev_out"]] * 3, dim=-1) if out["ev_out"].shape[-1] == 1 else out["ev_out"]
+            elif c.map_mode == "evs_rgb":
+                out["ev_out"] = self.correct_evs_dim(clamp_out)
+                out["linear"] = clamp_out
+                out["rgb"] = self.rgb_mapper(out["linear"])
+            elif c.map_mode == "co_map":
+                out["rgb"] = self.rgb_mapper(clamp_out)
+                if ev_out or not self.training:
+                    ev_linear = self.correct_evs_dim(clamp_out)
+                    out["linear"] = clamp_out
+                    out["ev_linear"] = ev_linear
+                    out["ev_out"] = self.evs_mapper(ev_linear)
+        if c.rgb_loss_type == "deblur" and self.training and out["rgb"].shape[0] % 4 == 0:
+            out["rgb"] = out["rgb"].reshape(-1, 4, 3).mean(dim=1)
+        out["rgb"] = torch.clamp(out["rgb"], 0, 1) if not self.training else torch.clamp(out["rgb"], 1e-5)
+        if "linear" in out and c.map_mode != "rgb_evs":
+            out["linear"] = out["linear"].detach()
+        return out
+
+    def render_epilogue(self, out: dict, ev_out: bool, lean: bool = False) -> dict:
+        """The part of get_outputs after compositing (lsenerf.py:333-375): clamp, intensity mappers, RGB -> one channel, deblur group
+        mean, final clamp -- one fused kernel (csrc/loss.cu) unless a learned MLP mapper is configured."""
+        if self._has_mlp_mapper():
+            return self._composed_epilogue(out, ev_out, lean)
         c = self.config
         cfg = self._epilogue_cfg(ev_out)
         rgb_pow = getattr(getattr(self, "rgb_mapper", None), "pow_coeff", None)
         evs_pow = getattr(self.evs_mapper, "pow_coeff", None)
         w_one = self.rgb_to_one.weights if c.ev_one_dim == "learned" else None
-        lin = out["rgb"]
+        lin = out["rgb"].contiguous()
         rgb_final, ev, ev_lin = ops.epilogue(lin, cfg, rgb_pow, evs_pow, w_one)
         out["rgb"] = rgb_final
         if ev.numel() > 0:
             out["ev_out"] = ev
             if c.map_mode == "rgb_evs":
-                out["linear"] = torch.cat([ev] * 3, dim=-1) if ev.shape[-1] == 1 else ev
-            else:
+                if not lean:
+                    out["linear"] = torch.cat([ev] * 3, dim=-1) if ev.shape[-1] == 1 else ev
+            elif not lean:
                 out["linear"] = torch.clamp(lin.detach(), 1e-5)
             if c.map_mode == "co_map":
                 out["ev_linear"] = ev_lin
         return out
+
+    def get_outputs(self, ray_bundle: RayBundle, ev_out=False, jitter=None, **kwargs):
+        """lsenerf.py:329-377."""
+        return self.render_epilogue(self.exec_get_outputs(ray_bundle, jitter), ev_out)
 
     # ---- losses -----------------------------------------------------------------------------------------------------
     def get_metrics_dict(self, outputs, batch):

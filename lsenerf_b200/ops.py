@@ -805,6 +805,52 @@ def epilogue(rgb_lin, cfg, rgb_pow=None, evs_pow=None, to_one_w=None):
     return _Epilogue.apply(rgb_lin, rgb_pow, evs_pow, to_one_w, cfg)
 
 
+class _MlpMapper(torch.autograd.Function):
+    """MLP_Mapper / RGB_MLP_Mapper.forward (intensity_mappers.py:27-62): y = sigmoid(L4(relu(L3(relu(L2(relu(L1 x))))))), rows of width 1 or 3."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        shape = x.shape
+        D = params[0].shape[1]
+        xf = _f32(x.reshape(-1, D), "x")
+        if shape[-1] != D:
+            raise RuntimeError(f"mapper expects inputs of width {D}, got {tuple(shape)}")
+        m = _lib.LseMlpMapper()
+        for n, t in zip(("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4"), params):
+            setattr(m, n, _f32(t, n).data_ptr())
+        m.dim = D
+        y = torch.empty_like(xf)
+        call("lse_mlp_mapper_fwd", ctypes.byref(m), P(xf), xf.shape[0], P(y), stream())
+        ctx.save_for_backward(xf)
+        ctx.params, ctx.shape, ctx.D = params, shape, D
+        return y.reshape(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xf,) = ctx.saved_tensors
+        D = ctx.D
+        m, g = _lib.LseMlpMapper(), _lib.LseMlpMapperGrads()
+        rets = []
+        for i, (n, t) in enumerate(zip(("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4"), ctx.params)):
+            setattr(m, n, t.data_ptr())
+            buf, ret = _grad_target(t, ctx.needs_input_grad[1 + i], "epi")
+            setattr(g, "d" + n, buf.data_ptr() if buf is not None else None)
+            rets.append(ret)
+            ctx_keep = buf  # noqa: F841  (buffers live in p.grad or in `rets`)
+        m.dim = D
+        dx = torch.empty_like(xf) if ctx.needs_input_grad[0] else None
+        call("lse_mlp_mapper_bwd", ctypes.byref(m), ctypes.byref(g), P(xf), P(_f32(dy.reshape(-1, D), "dy")), xf.shape[0], P(dx), stream())
+        return (dx.reshape(ctx.shape) if dx is not None else None, *rets)
+
+
+def mlp_mapper(x: Tensor, layers) -> Tensor:
+    """layers: the four nn.Linear of the mapper's MLP."""
+    params = []
+    for l in layers:
+        params += [l.weight, l.bias]
+    return _MlpMapper.apply(x, *params)
+
+
 class _Losses(torch.autograd.Function):
     """get_loss_dict (lsenerf.py:392-439): rgb MSE + weighted event log-difference MSE, gradients in the same pass."""
 

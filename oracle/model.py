@@ -129,8 +129,11 @@ def rgb_to_one(sd, cfg: Cfg, x: Tensor) -> Tensor:
 
 
 def mapper(sd, kind: str | None, prefix: str, x: Tensor) -> Tensor:
-    """intensity_mappers.py:64-87 (identity / gt x^(1/2.4) / powpow x^gamma).  The MLP mappers need the
-    CUDA-only identity_init (intensity_mappers.py:8-25) and are outside the hot-path scope."""
+    """intensity_mappers.py:27-87: identity / gt x^(1/2.4) / powpow x^gamma / mlp = MLP_Mapper (1 -> 16 -> 16 -> 16 -> 1) /
+    rgb_mlp = RGB_MLP_Mapper (3 -> ... -> 3): nerfstudio MLP(num_layers=4, layer_width=16, ReLU, Sigmoid) torch path, state-dict keys
+    `<prefix>.mlp.layers.{0..3}.{weight,bias}`.  Weights as given (identity_init, :8-25, is a pre-fit recipe, not part of the path)."""
+    if kind in ("mlp", "rgb_mlp"):
+        return F.mlp(x, sd, f"{prefix}.mlp", 4, "sigmoid")
     if kind in (None, "identity"):
         return x
     if kind == "gt":

@@ -821,6 +821,86 @@ def test_epilogue_kernel_reference_golden(dev):
     assert checked >= 16
 
 
+@pytest.mark.parametrize("kind", ["mlp", "rgb_mlp"])
+def test_mlp_mapper_kernels_reference_golden(dev, kind):
+    """MLP_Mapper / RGB_MLP_Mapper (intensity_mappers.py:27-62) on csrc/mapper_mlp.cu against the reference's own forward and autograd:
+    outputs 1e-4, input and parameter gradients 1e-3; weights loaded by the reference's checkpoint keys."""
+    from lsenerf_b200 import intensity_mappers as IM
+    from test_reference_golden import mlp_mapper_state
+    z = _ref("mlp_mappers")
+    m = (IM.MLP_Mapper if kind == "mlp" else IM.RGB_MLP_Mapper)().to(dev)
+    sd = {k[len("rgb_mapper."):]: v for k, v in mlp_mapper_state(z, kind, None).items() if k.startswith("rgb_mapper.")}
+    m.load_state_dict(sd, strict=True)                                    # the same keys as the reference module
+    x = torch.from_numpy(z[f"{kind}__x"]).to(dev).requires_grad_(True)
+    y = m(x)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), z[f"{kind}__y"], rtol=TOL_OUT, atol=1e-7)
+    (y * torch.from_numpy(z[f"{kind}__w"]).to(dev)).sum().backward()
+    assert rel_err(x.grad, torch.from_numpy(z[f"{kind}__dx"])) < TOL_GRAD
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad, torch.from_numpy(z[f"{kind}__grad.{k}"])) < TOL_GRAD, k
+    # ragged sizes around the warp / CTA boundaries
+    for n in (1, 31, 33, 129, 1000):
+        xs = torch.rand(n, m.dim, device=dev)
+        ref = xs
+        for i, l in enumerate(m.mlp.layers):
+            ref = torch.nn.functional.linear(ref, l.weight, l.bias)
+            ref = torch.relu(ref) if i < 3 else torch.sigmoid(ref)
+        assert rel_err(m(xs), ref) < 1e-5, n
+
+
+def test_model_epilogue_with_mlp_mappers_reference_golden(dev):
+    """LSENeRFModel.render_epilogue with learned mappers in every map_mode against the reference's get_outputs (24 cases), and the
+    gradients it sends to the mapper weights and to the composited radiance against oracle autograd."""
+    from lsenerf_b200.lse_config import experiment
+    from lsenerf_b200.lsenerf import LSENeRFModel
+    from oracle import model as OM
+    from test_reference_golden import MLP_EPILOGUE_MODES, mlp_mapper_state
+    z = _ref("mlp_mappers")
+    lin = torch.from_numpy(z["lin"]).to(dev)
+    for mode, (mm, use_mapping, one_dim, rgb_m, evs_m) in MLP_EPILOGUE_MODES.items():
+        _, mc = experiment("lsenerf", log2_hashmap_size=12, grid_resolution=32, grid_levels=1)
+        mc.map_mode, mc.use_mapping, mc.ev_one_dim, mc.mapping_method, mc.evs_mapping_method = mm, use_mapping, one_dim, rgb_m, evs_m
+        model = LSENeRFModel(mc, torch.tensor([-1.0, -1, -1, 1, 1, 1]), num_train_data=4).to(dev)
+        if not use_mapping:                      # rgb_evs reads self.rgb_mapper although populate_modules only builds it under use_mapping
+            from lsenerf_b200.intensity_mappers import MAPPERS_DICT
+            model.rgb_mapper = MAPPERS_DICT[rgb_m]().to(dev)
+        sd = mlp_mapper_state(z, rgb_m, evs_m)
+        own = model.state_dict()
+        for k, v in sd.items():
+            if k in own:
+                own[k].copy_(v.reshape(own[k].shape))
+        for training in (True, False):
+            model.train(training)
+            for deblur in (False, True):
+                mc.rgb_loss_type = "deblur" if deblur else "linspace"
+                for ev_out in (False, True):
+                    name = f"{mode}_t{int(training)}d{int(deblur)}e{int(ev_out)}"
+                    out = model.render_epilogue({"rgb": lin.clone()}, ev_out)
+                    for k in ("rgb", "ev_out", "ev_linear"):
+                        if f"{name}__{k}" in z.files:
+                            np.testing.assert_allclose(out[k].detach().cpu().numpy(), z[f"{name}__{k}"], rtol=TOL_OUT, atol=1e-7, err_msg=f"{name}:{k}")
+                        else:
+                            assert k not in out, (name, k)
+        # gradients (training, deblur, ev_out): CUDA against oracle autograd
+        model.train(True); mc.rgb_loss_type = "deblur"
+        x = lin.clone().requires_grad_(True)
+        out = model.render_epilogue({"rgb": x}, True)
+        loss = (out["rgb"] ** 2).sum() + ((out["ev_out"] ** 2).sum() if "ev_out" in out else 0.0)
+        loss.backward()
+        osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        xo = torch.from_numpy(z["lin"]).clone().requires_grad_(True)
+        cfg = OM.Cfg(use_mapping=use_mapping, map_mode=mm, ev_one_dim=one_dim, mapping_method=rgb_m, evs_mapping_method=evs_m, rgb_loss_type="deblur")
+        oout = OM.epilogue(osd, cfg, {"rgb": xo}, True, True)
+        ((oout["rgb"] ** 2).sum() + ((oout["ev_out"] ** 2).sum() if "ev_out" in oout else 0.0)).backward()
+        assert rel_err(x.grad, xo.grad) < TOL_GRAD, mode
+        n = 0
+        for k, p in model.named_parameters():
+            if k in osd and osd[k].grad is not None and p.grad is not None:
+                assert rel_err(p.grad, osd[k].grad.reshape(p.grad.shape)) < TOL_GRAD, (mode, k)
+                n += 1
+        assert n >= 8, (mode, n)
+
+
 def test_mapper_modules_reference_golden(dev):
     from lsenerf_b200 import intensity_mappers as IM
     z = _ref("mappers")

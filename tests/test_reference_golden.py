@@ -135,6 +135,61 @@ def test_oracle_epilogue_matches_reference(mode):
             close(out[k], z[f"{name}__{k}"], rtol=2e-6)
 
 
+# ------------------------------------------------------------------------------------------------------ learned (MLP) mappers
+MLP_EPILOGUE_MODES = {   # mirrors make_mlp_mapper_golden.run_case: (map_mode, use_mapping, ev_one_dim, rgb mapper, evs mapper)
+    "comap": ("co_map", True, "gt", "rgb_mlp", "mlp"),
+    "evsrgb": ("evs_rgb", True, "gt", "rgb_mlp", None),
+    "rgbevs": ("rgb_evs", False, "learned", "mlp", None),
+}
+
+
+def mlp_mapper_state(z, rgb_kind, evs_kind):
+    """state dict (reference checkpoint keys) holding the golden's mapper weights under rgb_mapper.* / evs_mapper.*"""
+    sd = {"rgb_to_one.weights": t(z["to_one_w"])}
+    for prefix, kind in (("rgb_mapper", rgb_kind), ("evs_mapper", evs_kind)):
+        if kind in ("mlp", "rgb_mlp"):
+            for k in z.files:
+                if k.startswith(kind + ".mlp."):
+                    sd[f"{prefix}.{k[len(kind) + 1:]}"] = t(z[k])
+    return sd
+
+
+@pytest.mark.parametrize("kind", ["mlp", "rgb_mlp"])
+def test_oracle_mlp_mapper_matches_reference(kind):
+    """MLP_Mapper / RGB_MLP_Mapper.forward and its gradients (intensity_mappers.py:27-62), run by the reference itself"""
+    z = gold("mlp_mappers")
+    sd = {k: v.requires_grad_(True) for k, v in mlp_mapper_state(z, kind, None).items()}
+    x = t(z[f"{kind}__x"]).requires_grad_(True)
+    y = OM.mapper(sd, kind, "rgb_mapper", x)
+    close(y, z[f"{kind}__y"], rtol=2e-6)
+    (y * t(z[f"{kind}__w"])).sum().backward()
+    close(x.grad, z[f"{kind}__dx"], rtol=1e-5, atol=1e-7)
+    for i in range(4):
+        for n in ("weight", "bias"):
+            close(sd[f"rgb_mapper.mlp.layers.{i}.{n}"].grad, z[f"{kind}__grad.mlp.layers.{i}.{n}"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", list(MLP_EPILOGUE_MODES))
+def test_oracle_epilogue_with_mlp_mappers_matches_reference(mode):
+    z = gold("mlp_mappers")
+    mm, use_mapping, one_dim, rgb_m, evs_m = MLP_EPILOGUE_MODES[mode]
+    sd = mlp_mapper_state(z, rgb_m, evs_m)
+    n = 0
+    for training in (True, False):
+        for deblur in (False, True):
+            for ev_out in (False, True):
+                name = f"{mode}_t{int(training)}d{int(deblur)}e{int(ev_out)}"
+                cfg = OM.Cfg(use_mapping=use_mapping, map_mode=mm, ev_one_dim=one_dim, mapping_method=rgb_m, evs_mapping_method=evs_m,
+                             rgb_loss_type="deblur" if deblur else "linspace")
+                out = OM.epilogue(sd, cfg, {"rgb": t(z["lin"]).clone()}, training, ev_out)
+                keys = {k for k in ("rgb", "ev_out", "ev_linear", "linear") if f"{name}__{k}" in z.files}
+                assert keys == {k for k in ("rgb", "ev_out", "ev_linear", "linear") if k in out}, name
+                for k in keys:
+                    close(out[k], z[f"{name}__{k}"], rtol=2e-6)
+                n += 1
+    assert n == 8
+
+
 # ------------------------------------------------------------------------------------------------------ losses
 @pytest.mark.parametrize("loss_type", ["log_loss", "enerf_norm_loss"])
 @pytest.mark.parametrize("use_mapping", [True, False])
