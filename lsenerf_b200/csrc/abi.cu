@@ -1,6 +1,7 @@
 // abi.cu -- error reporting, launch accounting and version of the C ABI.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <vector>
 #include "common.cuh"
@@ -17,6 +18,12 @@ void set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

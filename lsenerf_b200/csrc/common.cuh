@@ -33,6 +33,7 @@ namespace lse {
 constexpr int kNumSMs = 148;  // B200
 
 void set_error(const char *fmt, ...);
+int env_int(const char *name, int dflt);     // abi.cu: integer tuning knob from the environment (read once per call site)
 void count_launch();
 int check_launch(const char *what);
 

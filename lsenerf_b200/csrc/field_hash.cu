@@ -440,7 +440,10 @@ extern "C" int lse_field_density_bwd_table(const LseFieldParams *p, const LseFie
     if (S_cap <= 0 || !g->d_table) return 0;
     const BwdWs ws = carve_ws(workspace, S_cap);
     // positions come from the workspace (ws.xs): the ray buffers are not read, they may already be rewritten by the next step
-    scatter_samples_kernel<<<stride_grid(S_cap, HT, 4), HT, 0, (cudaStream_t)stream>>>(*p, g->d_table, nullptr, nullptr, nullptr, nullptr,
+    // resident CTAs per SM: the engine runs this on the optimizer's side stream under the next step's ray generation + march, whose
+    // CTAs need registers to land in (58 registers x 256 threads x 4 CTAs would take the whole register file)
+    static const int side_ctas = env_int("LSE_SIDE_CTAS", 4);
+    scatter_samples_kernel<<<stride_grid(S_cap, HT, side_ctas), HT, 0, (cudaStream_t)stream>>>(*p, g->d_table, nullptr, nullptr, nullptr, nullptr,
                                                                                        nullptr, S_cap, n_dev, ws.dfeat, nullptr, nullptr,
                                                                                        ws.xs);
     return check_launch("lse_field_density_bwd_table");

@@ -23,7 +23,14 @@ namespace lse {
 using namespace tc;
 
 constexpr int WG = 128;           // threads per warpgroup == rows per tile
-constexpr int NWG = 2;            // warpgroups (tiles in flight) per CTA
+constexpr int NWG = 2;            // warpgroups (tiles in flight) per CTA, colour kernel
+#ifndef LSE_DENSITY_NWG
+#define LSE_DENSITY_NWG 2
+#endif
+// ... density kernel.  Measured (profiles/r2c_ab_density_nwg.json): a third tile in flight (384 threads, 168 registers) makes the
+// culling pass 26 % SLOWER (0.344 vs 0.273 ms) -- the gather is not short of warps, it sits on the L1TEX -> L2 sector rate
+// (one 32-byte sector per clock per SM for random lanes, tools/gather_peak.py), which more threads only contend for.
+constexpr int NWG_D = LSE_DENSITY_NWG;
 constexpr int A_FLOATS = WG * 64; // one [128 x 64] operand buffer
 constexpr int TMEM_COLS_PER_WG = 128;
 
@@ -37,7 +44,7 @@ struct DensitySmem {
     static constexpr int B2 = B1 + 64;                    // 16
     static constexpr int SCAL = B2 + 16;                  // 16
     static constexpr int A = SCAL + 16;                   // per warpgroup: hi, lo
-    static constexpr int TOTAL = A + NWG * 2 * A_FLOATS;
+    static constexpr int TOTAL = A + NWG_D * 2 * A_FLOATS;
 };
 struct ColorSmem {
     static constexpr int W3 = 0;                          // hi [16][64][4] = 4096
@@ -69,7 +76,8 @@ __device__ __forceinline__ void read_acc(uint32_t tmem_row_base, int col0, float
 }
 
 // ===============================================================================================================================
-__global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldParams P, const float *__restrict__ origins,
+constexpr int kDensityTmemCols = NWG_D <= 2 ? 256 : 512;    // power of two >= NWG_D * TMEM_COLS_PER_WG
+__global__ void __launch_bounds__(WG *NWG_D, 1) density_fwd_tc_kernel(LseFieldParams P, const float *__restrict__ origins,
                                                                     const float *__restrict__ directions,
                                                                     const int32_t *__restrict__ ray_idx,
                                                                     const float *__restrict__ t0, const float *__restrict__ t1,
@@ -80,15 +88,15 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
     extern __shared__ __align__(1024) float smem[];
     using L = DensitySmem;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + L::TOTAL);          // [NWG]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + NWG);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + NWG_D);
     const int tid = threadIdx.x, wg = tid / WG, row = tid % WG, warp = tid >> 5;
 
-    stage_weights(smem + L::W1, smem + L::W1L, P.W1, 64, 32, 64, 32, tid, WG * NWG);
-    stage_weights(smem + L::W2, smem + L::W2L, P.W2, 16, 64, 16, 64, tid, WG * NWG);
+    stage_weights(smem + L::W1, smem + L::W1L, P.W1, 64, 32, 64, 32, tid, WG * NWG_D);
+    stage_weights(smem + L::W2, smem + L::W2L, P.W2, 16, 64, 16, 64, tid, WG * NWG_D);
     if (tid < 64) smem[L::B1 + tid] = P.b1[tid];
     if (tid < 16) { smem[L::B2 + tid] = P.b2[tid]; smem[L::SCAL + tid] = P.scalings[tid]; }
-    if (tid < NWG) mbar_init(mbar + tid, 1);
-    if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS_PER_WG * NWG);
+    if (tid < NWG_D) mbar_init(mbar + tid, 1);
+    if (warp == 0) tmem_alloc(tmem_slot, kDensityTmemCols);
     fence_mbar_init();
     fence_proxy_async();
     tc_fence_before();
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
     const int64_t S = live_count(n_dev, S_cap);
     const int64_t n_tiles = (S + WG - 1) / WG;
     const float2 *table = reinterpret_cast<const float2 *>(P.table);
-    for (int64_t tile = (int64_t)blockIdx.x * NWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * NWG) {
+    for (int64_t tile = (int64_t)blockIdx.x * NWG_D + wg; tile < n_tiles; tile += (int64_t)gridDim.x * NWG_D) {
         const int64_t j = tile * WG + row;
         const bool live = j < S;
         const int64_t i = (list && live) ? (int64_t)list[j] : j;     // optional indirection: the samples to evaluate
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(WG *NWG, 1) density_fwd_tc_kernel(LseFieldPara
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS_PER_WG * NWG);
+    if (warp == 0) tmem_dealloc(tmem_base, kDensityTmemCols);
 }
 
 // ===============================================================================================================================
@@ -291,10 +299,10 @@ __global__ void __launch_bounds__(WG *NWG, 1) color_fwd_tc_kernel(LseFieldParams
     if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS_PER_WG * NWG);
 }
 
-static int tc_grid(int64_t S_cap)
+static int tc_grid(int64_t S_cap, int nwg = NWG)
 {
     int64_t tiles = (S_cap + WG - 1) / WG;
-    int64_t ctas = (tiles + NWG - 1) / NWG;
+    int64_t ctas = (tiles + nwg - 1) / nwg;
     if (ctas < 1) ctas = 1;
     return (int)(ctas < kNumSMs ? ctas : kNumSMs);
 }
@@ -306,7 +314,7 @@ int tc_density_fwd(const LseFieldParams &P, const float *origins, const float *d
     constexpr size_t smem_bytes = DensitySmem::TOTAL * sizeof(float) + kCtrlBytes;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(density_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
-    density_fwd_tc_kernel<<<tc_grid(S_cap), WG * NWG, smem_bytes, st>>>(P, origins, directions, ray_idx, t0, t1, S_cap, n_dev, list, sigma,
+    density_fwd_tc_kernel<<<tc_grid(S_cap, NWG_D), WG * NWG_D, smem_bytes, st>>>(P, origins, directions, ray_idx, t0, t1, S_cap, n_dev, list, sigma,
                                                                         h16);
     return check_launch("lse_field_density_fwd[tc]");
 }

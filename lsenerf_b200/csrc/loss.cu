@@ -325,7 +325,8 @@ extern "C" int lse_adam_step_hp(float *param, const float *grad, float *exp_avg,
     int threads = 256;
     // half the thread slots of an SM: the engine runs this on a side stream under the next step's ray generation / march, whose
     // CTAs need somewhere to land; 1024 threads per SM of float4 streams already saturate HBM
-    lse::adam_hp_kernel<<<lse::stride_grid((n + 3) / 4, threads, 4), threads, 0, (cudaStream_t)stream>>>(
+    static const int side_ctas = lse::env_int("LSE_SIDE_CTAS", 4);
+    lse::adam_hp_kernel<<<lse::stride_grid((n + 3) / 4, threads, side_ctas), threads, 0, (cudaStream_t)stream>>>(
         param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, hp_dev);
     return lse::check_launch("lse_adam_step_hp");
 }

@@ -136,11 +136,14 @@ __device__ __forceinline__ void ray_events(const float o[3], const float d[3], c
 }
 
 constexpr int kMarchThreads = 128;
+constexpr int kSeqCap = 1024;              // steps per ray (== the slab capacity); a ray through 4 levels takes < 1000
+constexpr int kSeqStride = kSeqCap + 4;    // t_0 .. t_K inclusive, rows 16-byte aligned
 
 __global__ void __launch_bounds__(kMarchThreads) march_runs_kernel(
     const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n_rays, const uint32_t *__restrict__ bits,
     const uint32_t *__restrict__ mip, int mip_words, const float *__restrict__ aabbs, int levels, int res, float near_plane,
-    float far_plane, const float *__restrict__ jitter, float step_size, uint32_t *__restrict__ runs, int32_t *__restrict__ n_runs)
+    float far_plane, const float *__restrict__ jitter, float step_size, float cone_angle, uint32_t *__restrict__ runs,
+    int32_t *__restrict__ n_runs, float *__restrict__ tseq, int32_t *__restrict__ n_steps)
 {
     __shared__ float s_aabb[6 * kMaxLevels];
     __shared__ uint32_t s_mip[kMaxMipWords];
@@ -151,7 +154,9 @@ __global__ void __launch_bounds__(kMarchThreads) march_runs_kernel(
     const int n_slots = 2 * levels - 1, cap = run_cap(res);
     const float eps = 1e-6f, resf = (float)res;
     // consecutive threads = consecutive rays of the SAME segment slot: coalesced ray loads, similar trip counts in a warp
-    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_rays * n_slots; w += (int64_t)gridDim.x * blockDim.x) {
+    // jobs: (ray, segment slot) for slot < n_slots, plus one job per ray (slot == n_slots) that generates the ray's step sequence -- two
+    // kinds of sequential fp32 recurrences, both latency bound, sharing one launch so that they hide each other
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_rays * (n_slots + 1); w += (int64_t)gridDim.x * blockDim.x) {
         const int slot = (int)(w / n_rays);
         const int64_t r = w % n_rays;
         const float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
@@ -159,6 +164,33 @@ __global__ void __launch_bounds__(kMarchThreads) march_runs_kernel(
         const float nearp = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
         RayEvents E;
         ray_events(o, d, s_aabb, levels, E);
+        if (slot == n_slots) {
+            // t_{k+1} = t_k + clamp(t_k * cone, step, 1e10) does not depend on the occupancy (both branches of traverse_grids advance t_last
+            // by the same dt): generate the exact fp32 sequence t_0 .. t_K once, as far as any run of this ray can reach (the exit of
+            // the outermost box it hits, or the far plane).  march_classify_kernel places whole ranges of k into runs by searching it.
+            float t_far = -INFINITY;
+            for (int i = 0; i < 2 * levels; ++i) if (E.tv[i] < INFINITY) t_far = fmaxf(t_far, E.tv[i]);
+            t_far = fminf(t_far, far_plane);
+            float t = nearp;
+            float4 *row = reinterpret_cast<float4 *>(tseq + r * (int64_t)kSeqStride);
+            int k = 0;
+            bool go = true;
+            auto advance = [&]() {          // one step of the recurrence if its midpoint is still before the end
+                const float dt = march_dt(t, cone_angle, step_size);
+                if (k >= kSeqCap || !(rn_add(t, rn_mul(dt, 0.5f)) < t_far)) go = false;
+                else { t = rn_add(t, dt); ++k; }
+            };
+            for (int blk = 0; go; ++blk) {  // 4 elements per 16-byte store; index 4*blk+q holds t_{4*blk+q}, t_K included
+                float4 v;
+                v.x = t; if (go) advance();
+                v.y = t; if (go) advance();
+                v.z = t; if (go) advance();
+                v.w = t; if (go) advance();
+                row[blk] = v;
+            }
+            n_steps[r] = k;
+            continue;
+        }
         uint32_t *out = runs + (r * n_slots + slot) * (int64_t)cap;
         int k = 0;
         // segment `slot` = between sorted events slot and slot+1 (math_march.cuh:march_ray, outer loop body)
@@ -223,97 +255,142 @@ __global__ void __launch_bounds__(kMarchThreads) march_runs_kernel(
     }
 }
 
-// 16-byte asynchronous global -> shared copy (LDGSTS) and its group bookkeeping
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+// ---- run classification against the ray's step sequence --------------------------------------------------------------------------
+// march_runs_kernel generated the ray's exact fp32 step sequence t_0 .. t_K (sequential adds, nothing but registers on the dependency
+// chain).  The warp-per-ray kernel below places whole RANGES of k into runs by searching that sequence, instead of stepping through
+// it one k at a time with 6 of 32 lanes busy (round 1's march_steps_kernel, 185 us).  Every emitted (t_start, t_end) is a pair of
+// consecutive elements of the sequential recurrence, so the samples stay bit-identical to the reference's interleaved loops.
+
+// number of steps k in [0, K) whose midpoint lies before `b`, i.e. the first step that belongs behind a run bounded by b.
+// Midpoints increase with k.  `g` = an estimate from the closed form of the recurrence (arithmetic while t * cone < step, geometric
+// afterwards; off by at most a step or two), refined by galloping + bisection on the stored sequence.
+struct SeqView {
+    const float *t; int K; float cone, step;
+    __device__ __forceinline__ bool before(int k, float b) const
+    {
+        const float tk = t[k];
+        return rn_add(tk, rn_mul(march_dt(tk, cone, step), 0.5f)) < b;
+    }
+};
+__device__ __forceinline__ int steps_before(const SeqView &s, float b, int g)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+    const int K = s.K;
+    g = g < 0 ? 0 : (g > K ? K : g);
+    int lo, hi;
+    if (g >= K || !s.before(g, b)) {            // answer <= g
+        hi = g; lo = g;
+        int w = 1;
+        while (lo > 0) {
+            const int p = lo - w > 0 ? lo - w : 0;
+            if (s.before(p, b)) { lo = p + 1; break; }
+            hi = p; lo = p; w <<= 1;
+        }
+    } else {                                    // answer >= g + 1
+        lo = g + 1; hi = lo;
+        int w = 1;
+        for (;;) {
+            if (hi >= K) { hi = K; break; }
+            if (!s.before(hi, b)) break;
+            lo = hi + 1; hi = hi + w; w <<= 1;
+        }
+        if (lo > hi) lo = hi;
+    }
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (s.before(m, b)) lo = m + 1; else hi = m;
+    }
+    return lo;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kRing = 8;   // 16-byte chunks (4 runs each) in flight per ray
-
-__global__ void __launch_bounds__(kMarchThreads) march_steps_kernel(
-    int64_t n_rays, int levels, int res, float near_plane, const float *__restrict__ jitter, float step_size, float cone_angle,
-    const uint32_t *__restrict__ runs, const int32_t *__restrict__ n_runs, float2 *__restrict__ slabs, int max_per_ray,
-    int32_t *__restrict__ counts, int32_t *__restrict__ overflow, int lanes_per_ray)
+// warp per ray: runs (all segments concatenated in order, 32 per round) x the ray's step sequence -> the samples of the occupied
+// runs, written to the ray's slab
+__global__ void __launch_bounds__(256) march_classify_kernel(int64_t n_rays, int levels, int res, float near_plane,
+                                                             const float *__restrict__ jitter, float step_size, float cone_angle,
+                                                             const uint32_t *__restrict__ runs, const int32_t *__restrict__ n_runs,
+                                                             const float *__restrict__ tseq, const int32_t *__restrict__ n_steps,
+                                                             float2 *__restrict__ slabs, int max_per_ray, int32_t *__restrict__ counts,
+                                                             int32_t *__restrict__ overflow)
 {
-    // Per-thread ring of run chunks filled by cp.async kRing chunks ahead of the consumer, so the (L2) latency of the run list
-    // never sits on the t recurrence.  The ring streams the chunks of the ray's non-empty segments back to back; layout
-    // [chunk][thread] keeps the 16-byte accesses conflict-free.  ONE flat loop per ray: every iteration either takes one step
-    // of the t recurrence or moves to the next run, so the 32 rays of a warp stay in lockstep whatever their segment structure.
-    __shared__ uint4 s_ring[kRing][kMarchThreads];
-    __shared__ int16_t s_cnt[2 * kMaxLevels][kMarchThreads];
+    constexpr uint32_t FULL = 0xffffffffu;
     const int n_slots = 2 * levels - 1, cap = run_cap(res);
-    const int tid = threadIdx.x;
-    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (gtid % lanes_per_ray != 0) return;
-    for (int64_t r = gtid / lanes_per_ray; r < n_rays; r += ((int64_t)gridDim.x * blockDim.x) / lanes_per_ray) {
-        const float nearp = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
-        const uint4 *src = reinterpret_cast<const uint4 *>(runs + r * n_slots * (int64_t)cap);   // slot s starts at chunk s*cap/4
-        const int slot_chunks = cap >> 2;
-        float2 *slab = slabs + r * (int64_t)max_per_ray;
-        for (int sl = 0; sl < n_slots; ++sl) { const int c = n_runs[r * n_slots + sl]; s_cnt[sl][tid] = (int16_t)(c > 0 ? c : 0); }
-        // producer cursor
-        int p_slot = 0, p_chunk = 0, p_n = (s_cnt[0][tid] + 3) >> 2, wr = 0;
-        auto fetch_next = [&]() {
-            while (p_slot < n_slots && p_chunk >= p_n) { ++p_slot; p_chunk = 0; p_n = p_slot < n_slots ? (s_cnt[p_slot][tid] + 3) >> 2 : 0; }
-            if (p_slot < n_slots) { cp_async16(&s_ring[wr % kRing][tid], src + p_slot * slot_chunks + p_chunk); ++p_chunk; }
-            ++wr;
-            cp_async_commit();
-        };
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float t_c = cone_angle > 0.0f ? step_size / cone_angle : INFINITY;      // dt = step while t < t_c
+    const float inv_step = 1.0f / step_size, inv_lg = cone_angle > 0.0f ? 1.0f / log1pf(cone_angle) : 0.0f;
+    for (int64_t r = warp; r < n_rays; r += n_warps) {
+        const int K = n_steps[r];
+        // lane s < n_slots: runs of segment s; exclusive prefix = position of the segment in the concatenated list
+        const int my_cnt = lane < n_slots ? max(n_runs[r * n_slots + lane], 0) : 0;
+        int pre = my_cnt;
 #pragma unroll
-        for (int c = 0; c < kRing; ++c) fetch_next();
-        // consumer cursor
-        int c_slot = 0, rd = 0, idx = 0, n = 0;
-        while (c_slot < n_slots && s_cnt[c_slot][tid] == 0) ++c_slot;
-        bool done = c_slot >= n_slots;
-        int cnt = done ? 0 : s_cnt[c_slot][tid];
-        cp_async_wait<kRing - 1>();
-        uint4 cur = s_ring[0][tid];
-        uint32_t e = cur.x;
-        float t_last = nearp;
-        // the warp-wide vote is the loop condition: it re-converges the lanes every iteration (and stops the compiler from
-        // re-nesting the loop into per-run inner loops, which would serialise lanes with different run lengths)
-        const uint32_t wmask = __activemask();
-        while (__any_sync(wmask, !done)) {
-            if (!done) {
-                const float dt = march_dt(t_last, cone_angle, step_size);
-                const float mid = rn_add(t_last, rn_mul(dt, 0.5f));
-                const float t_next = rn_add(t_last, dt);
-                if (mid >= __uint_as_float(e & 0x7FFFFFFFu)) {      // this run is behind us: move to the next one (at most one per
-                    ++idx;                                          // iteration; the step below is retried against it right away)
-                    bool new_chunk = (idx & 3) == 0;
-                    if (idx >= cnt) {               // segment exhausted: the next non-empty one starts a fresh chunk
-                        do { ++c_slot; } while (c_slot < n_slots && s_cnt[c_slot][tid] == 0);
-                        done = c_slot >= n_slots;
-                        cnt = done ? 0 : s_cnt[c_slot][tid];
-                        idx = 0;
-                        new_chunk = true;
-                    }
-                    if (!done) {
-                        if (new_chunk) {
-                            fetch_next();           // refill the ring slot just consumed, kRing chunks ahead
-                            ++rd;
-                            cp_async_wait<kRing - 1>();
-                            cur = s_ring[rd % kRing][tid];
-                        } else {
-                            cur.x = cur.y; cur.y = cur.z; cur.z = cur.w;
-                        }
-                        e = cur.x;
-                    }
-                }
-                if (!done && mid < __uint_as_float(e & 0x7FFFFFFFu)) {   // one step of the t recurrence inside the current run
-                    if ((e >> 31) && n < max_per_ray) slab[n] = make_float2(t_last, t_next);
-                    n += (int)(e >> 31);
-                    t_last = t_next;
+        for (int o = 1; o < 16; o <<= 1) { const int y = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += y; }
+        const int total = __shfl_sync(FULL, pre, 15);
+        pre -= my_cnt;
+        if (K == 0 || total == 0) { if (lane == 0) counts[r] = 0; continue; }
+        const float *ts = tseq + r * (int64_t)kSeqStride;
+        const SeqView sv{ts, K, cone_angle, step_size};
+        const float t0 = jitter ? rn_add(near_plane, rn_mul(jitter[r], step_size)) : near_plane;
+        // closed form of the recurrence: k_c arithmetic steps up to t_c, geometric growth by (1 + cone) afterwards
+        const float kc = t0 < t_c ? ceilf((fminf(t_c, 1e30f) - t0) * inv_step) : 0.0f;
+        const float tkc = t0 < t_c ? t0 + kc * step_size : t0;
+        float2 *slab = slabs + r * (int64_t)max_per_ray;
+        const uint32_t *rl = runs + r * n_slots * (int64_t)cap;
+        float carry_pm = -INFINITY;
+        int carry_u = 0, n_out = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int j = base + lane;
+            const bool valid = j < total;
+            // which segment does concatenated run j belong to?  (n_slots <= 15 lanes hold the prefix)
+            int seg = 0, segpre = 0;
+            for (int sl = 0; sl < n_slots; ++sl) {
+                const int p = __shfl_sync(FULL, pre, sl), c = __shfl_sync(FULL, my_cnt, sl);
+                if (valid && c > 0 && j >= p) { seg = sl; segpre = p; }
+            }
+            const uint32_t e = valid ? rl[seg * (int64_t)cap + (j - segpre)] : 0u;
+            // effective bound of a run = running maximum (a step never returns to an earlier run)
+            float pm = valid ? __uint_as_float(e & 0x7FFFFFFFu) : -INFINITY;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const float y = __shfl_up_sync(FULL, pm, o); if (lane >= o) pm = fmaxf(pm, y); }
+            pm = fmaxf(pm, carry_pm);
+            int u = 0;
+            if (valid) {
+                float g;                    // steps with t + dt/2 < pm, from the closed form
+                if (pm - 0.5f * step_size <= tkc || cone_angle <= 0.0f) g = ceilf((pm - 0.5f * step_size - t0) * inv_step);
+                else g = kc + ceilf(__logf(pm / (tkc * (1.0f + 0.5f * cone_angle))) * inv_lg);
+                u = steps_before(sv, pm, (int)fminf(fmaxf(g, 0.0f), (float)K));
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, u, o); if (lane >= o) u = max(u, y); }
+            u = max(u, carry_u);
+            int prev = __shfl_up_sync(FULL, u, 1);
+            if (lane == 0) prev = carry_u;
+            const int c = (valid && (e >> 31)) ? u - prev : 0;
+            int inc = c;                    // offsets of the runs' samples inside the slab
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += y; }
+            const int off = n_out + inc - c;
+            uint32_t todo = __ballot_sync(FULL, c > 0);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int k0 = __shfl_sync(FULL, prev, src), cc = __shfl_sync(FULL, c, src), o0 = __shfl_sync(FULL, off, src);
+                for (int i0 = 0; i0 < cc; i0 += 32) {
+                    const int i = i0 + lane;
+                    const float a = i <= cc ? ts[k0 + i] : 0.0f;                 // one load per element: t_end comes from the next lane
+                    float bnext = __shfl_down_sync(FULL, a, 1);
+                    if (lane == 31 && i < cc) bnext = ts[k0 + i + 1];
+                    if (i < cc && o0 + i < max_per_ray) slab[o0 + i] = make_float2(a, bnext);
                 }
             }
+            n_out += __shfl_sync(FULL, inc, 31);
+            carry_pm = __shfl_sync(FULL, pm, 31);
+            carry_u = __shfl_sync(FULL, u, 31);
         }
-        cp_async_wait<0>();
-        counts[r] = n < max_per_ray ? n : max_per_ray;
-        if (n > max_per_ray && overflow) *overflow = 1;
+        if (lane == 0) {
+            counts[r] = n_out < max_per_ray ? n_out : max_per_ray;
+            // more samples than slab slots, or a sequence cut at its capacity with every step of it already used
+            if ((n_out > max_per_ray || (K >= kSeqCap && carry_u >= K)) && overflow) *overflow = 1;
+        }
     }
 }
 
@@ -766,18 +843,13 @@ extern "C" int lse_march_count(const float *rays_o, const float *rays_d, int64_t
     return check_launch("lse_march_count");
 }
 
-static int march_lanes()   // lanes per ray of march_steps_kernel; LSE_MARCH_LANES overrides for tuning
-{
-    static int v = 0;
-    if (v == 0) { const char *e = getenv("LSE_MARCH_LANES"); v = e ? atoi(e) : 4; if (v < 1 || v > 32) v = 4; }
-    return v;
-}
-
 extern "C" int64_t lse_march_workspace(int64_t n_rays, int levels, int res)
 {
     // runs [n_rays, 2*levels-1, 3*res] u32 + n_runs [n_rays, 2*levels-1] i32 (only the used prefix of a run list is touched)
-    const int64_t n = (n_rays < 1 ? 1 : n_rays) * (2 * levels - 1);
-    return (n * run_cap(res) * 4 + 255) / 256 * 256 + (n * 4 + 255) / 256 * 256;
+    // + the step sequences [n_rays, kSeqStride] fp32 + n_steps [n_rays] i32
+    const int64_t rays = n_rays < 1 ? 1 : n_rays, n = rays * (2 * levels - 1);
+    return (n * run_cap(res) * 4 + 255) / 256 * 256 + (n * 4 + 255) / 256 * 256 + (rays * kSeqStride * 4 + 255) / 256 * 256 +
+           (rays * 4 + 255) / 256 * 256;
 }
 
 extern "C" int lse_march_single(const float *rays_o, const float *rays_d, int64_t n_rays, const uint32_t *occ_bits,
@@ -798,16 +870,18 @@ extern "C" int lse_march_single(const float *rays_o, const float *rays_d, int64_
     uint32_t *runs = reinterpret_cast<uint32_t *>(workspace);
     int32_t *n_runs = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(workspace) + (n * run_cap(res) * 4 + 255) / 256 * 256);
     cudaStream_t st = (cudaStream_t)stream;
-    march_runs_kernel<<<stride_grid(n, kMarchThreads, 16), kMarchThreads, 0, st>>>(
-        rays_o, rays_d, n_rays, occ_bits, occ_mip, mip_words, aabbs, levels, res, near_plane, far_plane, jitter, step_size, runs,
-        n_runs);
+    char *wsb = reinterpret_cast<char *>(workspace) + (n * run_cap(res) * 4 + 255) / 256 * 256 + (n * 4 + 255) / 256 * 256;
+    float *tseq = reinterpret_cast<float *>(wsb);
+    int32_t *n_steps = reinterpret_cast<int32_t *>(wsb + (n_rays * kSeqStride * 4 + 255) / 256 * 256);
+    march_runs_kernel<<<stride_grid(n + n_rays, kMarchThreads, 16), kMarchThreads, 0, st>>>(
+        rays_o, rays_d, n_rays, occ_bits, occ_mip, mip_words, aabbs, levels, res, near_plane, far_plane, jitter, step_size, cone_angle, runs,
+        n_runs, tseq, n_steps);
     int rc = check_launch("lse_march_single[runs]");
     if (rc) return rc;
-    const int lanes = march_lanes();
-    march_steps_kernel<<<stride_grid(n_rays * lanes, kMarchThreads, 16), kMarchThreads, 0, st>>>(
-        n_rays, levels, res, near_plane, jitter, step_size, cone_angle, runs, n_runs, reinterpret_cast<float2 *>(slabs), max_per_ray,
-        counts, overflow_dev, lanes);
-    return check_launch("lse_march_single[steps]");
+    march_classify_kernel<<<stride_grid(n_rays * 32, 256, 8), 256, 0, st>>>(n_rays, levels, res, near_plane, jitter, step_size, cone_angle,
+                                                                            runs, n_runs, tseq, n_steps, reinterpret_cast<float2 *>(slabs),
+                                                                            max_per_ray, counts, overflow_dev);
+    return check_launch("lse_march_single[classify]");
 }
 
 extern "C" int lse_march_pack(const float *slabs, int max_per_ray, const int32_t *counts, const int32_t *starts, int64_t n_rays,
