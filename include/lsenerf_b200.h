@@ -123,7 +123,8 @@ int lse_march_pack(const float *slabs, int max_per_ray, const int32_t *counts, c
 /* One generation of the early-terminating culling pass (exactly the kept set of render_visibility_from_density, lse_grid_estimator.py:
  * 109-127, without evaluating the field behind opaque surfaces): for every ray still visible after its first `lo` samples
  * (transmittance from depth_acc [n_rays] + sigmas over [prev_lo, lo) >= early_stop_eps) append the ids of its samples [lo, hi) to
- * sample_list and bump *n_list_dev.  Call with prev_lo == lo == 0 for the first generation; sigmas must be zero-filled beforehand. */
+ * sample_list and bump *n_list_dev.  Call with prev_lo == lo == 0 for the first generation: it also zero-fills the sigmas of every ray's samples
+ * behind `hi` (samples never evaluated keep sigma = 0, which the visibility test rejects), so the buffer needs no memset. */
 int lse_cull_generation(const int32_t *starts, const int32_t *counts, int64_t n_rays, const float *t_starts,
                         const float *t_ends, const float *sigmas, float *depth_acc, int prev_lo, int lo, int hi,
                         float early_stop_eps, int32_t *sample_list, int64_t list_cap, int32_t *n_list_dev, lse_stream_t stream);

@@ -502,6 +502,10 @@ __global__ void cull_generation_kernel(const int32_t *__restrict__ starts, const
     for (int64_t r = warp; r < n_rays; r += n_warps) {
         const int64_t s = starts[r];
         const int32_t c = counts[r];
+        if (prev_lo == lo) {                                  // first generation: samples behind it keep sigma = 0 until evaluated
+            float *z = const_cast<float *>(sigmas);
+            for (int32_t k = hi + lane; k < c; k += 32) z[s + k] = 0.0f;
+        }
         if (c <= lo) continue;
         float acc = prev_lo < lo ? depth_acc[r] : 0.0f;
         if (prev_lo < lo) {

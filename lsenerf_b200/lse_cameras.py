@@ -32,6 +32,9 @@ class EdCameras:
         self.hard_cam_type = HardCamType.RGB
         self.get_c2w_fn = self.get_c2w
         self._intr = None
+        # lean (set by MultiCamManager for the captured training step): skip the per-ray `times` / repeated `camera_indices` the fused
+        # render never reads (two index + two repeat launches per bundle)
+        self.lean = False
 
     @property
     def device(self):
@@ -97,7 +100,10 @@ class EdCameras:
         c2w, _ = self.get_c2w_fn(camera_indices)
         assert c2w.shape == (coords.shape[0], 3, 4)
         o, d, area, nrm = ops.rays_from_c2w(c2w, coords.float().contiguous(), *self.intrinsics())
-        times = self.times[camera_indices[:, 0], 0][:, None] if self.times is not None else None
-        times, cam_idx = fix_datashape(times, o), fix_datashape(camera_indices, o)
+        if self.lean:
+            times, cam_idx = None, (camera_indices if camera_indices.shape[0] == o.shape[0] else None)
+        else:
+            times = self.times[camera_indices[:, 0], 0][:, None] if self.times is not None else None
+            times, cam_idx = fix_datashape(times, o), fix_datashape(camera_indices, o)
         return RayBundle(origins=o, directions=d, pixel_area=area, camera_indices=cam_idx, times=times,
                          metadata={"directions_norm": fix_datashape(nrm.detach(), o)})

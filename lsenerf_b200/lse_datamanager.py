@@ -155,6 +155,7 @@ class MultiCamManager(nn.Module):
         prefetched: optional (col_batch, evs_batch) already resident on the device (bench: HBM-resident inputs)."""
         self.col_train_camera_optimizer.update_mode(step)
         self.evs_train_camera_optimizer.update_mode(step)
+        self.col_cams.lean = self.evs_ray_generator.cameras.lean = self.lean
         col_bundle = col_batch = prev_bundle = next_bundle = evs_batch = None
         if prefetched is None:
             hc, he = self.sample_host_batches()

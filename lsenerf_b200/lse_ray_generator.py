@@ -65,7 +65,7 @@ class DeblurRayGenerator(RayGenerator):
         def get_deblur_c2w(cameras: EdCameras, camera_indices):
             cam_ts = cameras.times[camera_indices[..., 0]].reshape(-1, 1)
             c2ws = cams.interpolator.get_deblur_cameras(cam_ts)
-            return c2ws, [camera_indices[..., 0].repeat_interleave(4)]
+            return c2ws, None      # (upstream also returns the 4x repeated camera indices; nothing on the perspective path reads them)
 
         ori_fn = cams.get_c2w_fn
         cams.get_c2w_fn = MethodType(get_deblur_c2w, cams)

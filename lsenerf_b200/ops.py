@@ -56,6 +56,7 @@ class _PoseInterp(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ctrl_tangents, scale, ctrl_ts, times, n_virtual, exp_t, dM):
+        ctx.set_materialize_grads(False)      # an output nobody differentiates arrives as None, not as a zero-filled tensor
         ct = _f32(ctrl_tangents, "ctrl_tangents")
         ts = _f32(times.reshape(-1), "times")
         n = ts.numel()
@@ -74,6 +75,8 @@ class _PoseInterp(torch.autograd.Function):
     def backward(ctx, d_c2w):
         ct, ctrl_ts, ts, dM, scale = ctx.saved_tensors
         n, n_virtual, t_off, t_step, has_dM, has_scale = ctx.meta
+        if d_c2w is None:
+            return None, None, None, None, None, None, None
         p_ct, p_scale = ctx.leaves
         d_ct, r_ct = _grad_target(p_ct, ctx.needs_input_grad[0], "interp")
         if d_ct is None:
@@ -104,6 +107,7 @@ class _RaysFromC2W(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c2w, coords, fx, fy, cx, cy):
+        ctx.set_materialize_grads(False)      # an output nobody differentiates arrives as None, not as a zero-filled tensor
         c2w = _f32(c2w, "c2w"); coords = _f32(coords, "coords")
         n = coords.shape[0]
         o = torch.empty(n, 3, device=c2w.device); d = torch.empty(n, 3, device=c2w.device)
@@ -117,6 +121,8 @@ class _RaysFromC2W(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_o, d_d, _a, _n):
         c2w, coords = ctx.saved_tensors
+        if d_o is None and d_d is None:
+            return None, None, None, None, None, None
         g = torch.empty_like(c2w)
         call("lse_rays_from_c2w_bwd", P(c2w), P(coords), coords.shape[0], *ctx.intr,
              P(d_o.contiguous()) if d_o is not None else None, P(d_d.contiguous()) if d_d is not None else None, P(g), stream())
@@ -132,6 +138,7 @@ class _PoseDelta(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pose_adjustment, cam_idx, origins, directions):
+        ctx.set_materialize_grads(False)      # an output nobody differentiates arrives as None, not as a zero-filled tensor
         pa = _f32(pose_adjustment, "pose_adjustment"); o = _f32(origins, "origins"); d = _f32(directions, "directions")
         ci = cam_idx.reshape(-1).to(torch.int64).contiguous()
         n = o.shape[0]
@@ -145,6 +152,8 @@ class _PoseDelta(torch.autograd.Function):
     def backward(ctx, g_o, g_d):
         pa, ci, d = ctx.saved_tensors
         n = d.shape[0]
+        if g_o is None and g_d is None:
+            return None, None, None, None
         d_pa, r_pa = _grad_target(ctx.leaf, ctx.needs_input_grad[0], "delta")
         if d_pa is None:
             d_pa = torch.zeros_like(pa)
@@ -403,7 +412,7 @@ def field_density_culling(fw: FieldWeights, origins, directions, m: "MarchResult
     like their true density.  Same kept set as evaluating every marched sample."""
     dev = origins.device
     S_cap, R = m.S_cap, m.counts.numel()
-    sigma = torch.zeros(S_cap, device=dev); h16 = torch.empty(S_cap, 16, device=dev)
+    sigma = torch.empty(S_cap, device=dev); h16 = torch.empty(S_cap, 16, device=dev)     # the first generation zero-fills sigma
     depth = torch.empty(R, device=dev)
     lst = torch.empty(S_cap, dtype=torch.int32, device=dev); n_list = torch.empty(1, dtype=torch.int32, device=dev)
     cp = fw.c_params(relu_d=relu_mask)
@@ -602,6 +611,7 @@ class RenderOpts:
 class _RenderRays(torch.autograd.Function):
     @staticmethod
     def forward(ctx, origins, directions, jitter, app_id, fw: FieldWeights, opts: RenderOpts, *params):
+        ctx.set_materialize_grads(False)      # an output nobody differentiates arrives as None, not as a zero-filled tensor
         o = _f32(origins, "origins"); d = _f32(directions, "directions")
         R = o.shape[0]
         S_cap = max(1, R * opts.samples_per_ray_cap)
@@ -763,6 +773,7 @@ class _Epilogue(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rgb_lin, rgb_pow, evs_pow, to_one_w, cfg: _lib.LseEpilogueCfg):
+        ctx.set_materialize_grads(False)      # an output nobody differentiates arrives as None, not as a zero-filled tensor
         x = _f32(rgb_lin, "rgb")
         R = x.shape[0]
         group = bool(cfg.deblur and cfg.training and R % 4 == 0)
@@ -790,6 +801,8 @@ class _Epilogue(torch.autograd.Function):
         x, rgb_pow, evs_pow, to_one_w = ctx.saved_tensors
         h_rp, h_ep, h_w, ev_branch = ctx.has
         R = x.shape[0]
+        if g_rgb is None and (g_ev is None or not ev_branch):
+            return None, None, None, None, None
         d_x = torch.empty_like(x)
         l_rp, l_ep, l_w = ctx.leaves
         d_rp, r_rp = _grad_target(l_rp, h_rp and ctx.needs_input_grad[1], "epi")
@@ -856,6 +869,7 @@ class _Losses(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, col_pred, col_target, prev, nxt, evs, evs_weight):
+        ctx.set_materialize_grads(False)      # an output nobody differentiates arrives as None, not as a zero-filled tensor
         dev = (col_pred if col_pred is not None else prev).device
         losses = torch.empty(2, device=dev)
         n_col = col_pred.shape[0] if col_pred is not None else 0
@@ -877,8 +891,8 @@ class _Losses(torch.autograd.Function):
     def backward(ctx, g_rgb, g_ev):
         d_col, d_prev, d_next = ctx.saved_tensors
         has_col, has_ev = ctx.has
-        return (d_col * g_rgb if has_col else None, None, d_prev * g_ev if has_ev else None, d_next * g_ev if has_ev else None,
-                None, None)
+        return (d_col * g_rgb if (has_col and g_rgb is not None) else None, None, d_prev * g_ev if (has_ev and g_ev is not None) else None,
+                d_next * g_ev if (has_ev and g_ev is not None) else None, None, None)
 
 
 def losses(col_pred, col_target, prev, nxt, evs, evs_weight=1.0):

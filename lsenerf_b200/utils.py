@@ -44,7 +44,7 @@ def fix_appearance_id(data, ref_data, max_app_id=1000000):
 
 def add_metadata(ray_bundle, batch, cam_id=0, max_app_id=10000000, lean=False):
     """utils.py:182-194.  lean: appearance_id only (the one entry the model reads, lse_field.py:324-327)."""
-    ref = ray_bundle.camera_indices
+    ref = ray_bundle.camera_indices if ray_bundle.camera_indices is not None else ray_bundle.origins
     dev = ref.device
     app = batch["appearance_id"].to(dev)[..., None].contiguous()
     ray_bundle.metadata["appearance_id"] = fix_appearance_id(app, ref, max_app_id)

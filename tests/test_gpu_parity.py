@@ -719,6 +719,7 @@ def test_engine_pipelined_step_matches_plain_step(dev):
     # engine path, eager phases with the same RNG stream for the jitter
     p.defer_table_scatter = True
     torch.manual_seed(5)
+    opt.zero_grad()                        # (step() zeroes the field gradients on the side stream after the optimizer)
     gs._phase_a(); out = gs._phase_b()
     assert gs._deferred() is not None
     ops.run_deferred_table_scatter(gs._deferred())
