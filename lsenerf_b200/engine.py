@@ -341,6 +341,7 @@ class GraphedStep:
         self.ev_b = torch.cuda.Event() if self.side is not None else None
         self.ev_opt: Optional[torch.cuda.Event] = None        # field optimizer of the previous step (side stream)
         self.early = [n for n in optim.names if n != self.FIELD_GROUP]   # groups stepped on the main stream right after B
+        self.has_field = self.FIELD_GROUP in optim.names                 # False: field frozen (camera-only optimisation, train.py:262-293)
 
     # ---- the two halves of an iteration -----------------------------------------------------------------------------------------
     def _phase_a(self) -> None:
@@ -359,6 +360,9 @@ class GraphedStep:
         return torch.stack([v.detach() for v in loss_dict.values()])
 
     def capture(self, start_step: int = 0) -> None:
+        """warm up and capture the graphs of one iteration.  No autograd graph built by an EARLIER eager pass over the same parameters
+        may still be alive (held by an output or loss tensor): autograd keeps one gradient-accumulator node per parameter alive as long
+        as any graph references it and runs it on the stream it was created on -- a stream outside the capture."""
         self.step_no = start_step
         self.optim.set_step(max(self.optim.step_count, 1))
         # warm-up (allocator, lazy inits) on the SAME stream the graphs are captured on: autograd remembers the stream a node or a
@@ -495,8 +499,9 @@ class GraphedStep:
                 self.graph_c.replay()                    # hash-table scatter of this step (only the optimizer needs it)
             elif self._deferred() is not None:
                 ops.run_deferred_table_scatter(self._deferred())
-            self._optimize([self.FIELD_GROUP], world, channel=0)
-            self.optim.zero_grad(only=[self.FIELD_GROUP])
+            if self.has_field:
+                self._optimize([self.FIELD_GROUP], world, channel=0)
+                self.optim.zero_grad(only=[self.FIELD_GROUP])
             self.ev_opt = torch.cuda.Event()
             self.ev_opt.record(side)
         self.step_no += 1

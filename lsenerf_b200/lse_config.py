@@ -11,9 +11,15 @@ TRAIN_NUM_RAYS_PER_BATCH = 3512   # lse_config.py:24
 EVAL_NUM_RAYS_PER_CHUNK = 3512    # lse_config.py:27
 
 
-def experiment(name: str, num_rays: int = TRAIN_NUM_RAYS_PER_BATCH, deblur: bool = True, cam_opt: bool = True, **model_kw):
-    """name in {"lsenerf", "lsenerf_emb", "badnerf", "badnerf_emb"} -> (MultiCamManagerConfig, LSENeRFModelConfig)."""
+def experiment(name: str, num_rays: int = TRAIN_NUM_RAYS_PER_BATCH, deblur: bool = True, cam_opt: bool = True,
+               eval_camopt: bool = False, **model_kw):
+    """name in {"lsenerf", "lsenerf_emb", "badnerf", "badnerf_emb"} -> (MultiCamManagerConfig, LSENeRFModelConfig).
+    eval_camopt: the overrides train.py:modify_config applies for `--is_eval True` (scripts/eval.sh, train.py:262-293): RGB rays only
+    (rgb_frac 1), linspace / mse loss without deblur, the RGB camera optimizer forced to SO3xR3 / "ns" / active -- the camera-only
+    optimisation that precedes the full-frame eval renders (BASELINE configs[4])."""
     name = name.lower()
+    if eval_camopt:
+        deblur, cam_opt = False, True
     lse = name.startswith("lsenerf")
     emb = "evs_emb" if name.endswith("_emb") else "global_emb"
     loss_type = "deblur" if deblur else "linspace"
@@ -25,4 +31,9 @@ def experiment(name: str, num_rays: int = TRAIN_NUM_RAYS_PER_BATCH, deblur: bool
     model = LSENeRFModelConfig(use_mapping=lse, mapping_method="identity", map_mode="co_map" if lse else "None",
                                evs_mapping_method="powpow" if lse else "None", ev_one_dim="gt", rgb_loss_type=loss_type,
                                evs_loss_weight=1.0, embed_config=LSEEmbeddingConfig(embedding_type=emb), **model_kw)
+    if eval_camopt:
+        dm.col_cam_optimizer = CameraOptimizerConfig(mode="SO3xR3", optim_type="ns", scheme="active")
+        dm.evs_cam_optimizer = CameraOptimizerConfig(mode="off", optim_type="ns")
+        dm.rgb_frac = 1.0
+        dm.update_num_batch_rays()
     return dm, model

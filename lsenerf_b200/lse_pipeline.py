@@ -42,13 +42,14 @@ class LSENeRFPipeline(nn.Module):
         while the previous step's optimizer is still updating the field."""
         bundles, batch = self.datamanager.next_train(step, prefetched)
         ctx = {"bundles": bundles, "batch": batch}
-        col, prev, nxt = bundles
         m = self._model
-        if self.fuse_bundles and col is not None and prev is not None:
-            # the three forwards of lse_pipeline.py:115-123 are independent given the weights: one launch chain over the
+        live = [(i, b) for i, b in enumerate(bundles) if b is not None and len(b) > 0]
+        if self.fuse_bundles and live:
+            # the (up to) three forwards of lse_pipeline.py:115-123 are independent given the weights: one launch chain over the
             # concatenated bundle; the fused render reads origins / directions (+ the appearance id of per-frame embeddings) only
-            big = concat_bundles([col, prev, nxt], fields=("origins", "directions"), metadata_keys=("appearance_id",))
-            ctx["big"], ctx["sizes"] = big, (len(col), len(prev), len(nxt))
+            big = live[0][1] if len(live) == 1 else concat_bundles([b for _, b in live], fields=("origins", "directions"),
+                                                                    metadata_keys=("appearance_id",))
+            ctx["big"], ctx["live"] = big, [(i, len(b)) for i, b in live]
             if premarch and m.training:
                 opts = m._render_opts()
                 opts.defer_table_scatter = self.defer_table_scatter
@@ -63,21 +64,22 @@ class LSENeRFPipeline(nn.Module):
         """Second half: field evaluation, compositing, epilogue, losses."""
         batch = ctx["batch"]
         col_bundle, prev_bundle, next_bundle = ctx["bundles"]
-        col_out = prev_out = next_out = None
+        outs = [None, None, None]
         m = self._model
         if "big" in ctx:
-            n0, n1, n2 = ctx["sizes"]
             raw = m.exec_get_outputs(ctx["big"], ctx.get("jitter"), ctx.get("opts"), with_depth=not self.lean)
-            # one split per tensor (its backward is a single cat, where three slices would be three zero-fills + copies + adds)
-            parts = {k: v.split([n0, n1, n2]) for k, v in raw.items() if v is not None}
-            col_out, prev_out, next_out = [self._finish({k: v[i] for k, v in parts.items()}, ev) for i, ev in enumerate((False, True, True))]
+            idx, sizes = [i for i, _ in ctx["live"]], [n for _, n in ctx["live"]]
+            # one split per tensor (its backward is a single cat, where separate slices would be zero-fills + copies + adds)
+            parts = {k: (v.split(sizes) if len(sizes) > 1 else (v,)) for k, v in raw.items() if v is not None}
+            for j, i in enumerate(idx):
+                outs[i] = self._finish({k: v[j] for k, v in parts.items()}, i > 0)       # bundle 0 = RGB, 1 / 2 = event prev / next
         else:
             if col_bundle is not None and len(col_bundle) > 0:
-                col_out = m(col_bundle, ev_out=False)
+                outs[0] = m(col_bundle, ev_out=False)
             if prev_bundle is not None and len(prev_bundle) > 0:
-                prev_out = m(prev_bundle, raybd2=next_bundle, batch=batch, ev_out=True)
-                next_out = m(next_bundle, raybd2=prev_bundle, batch=batch, keep=True, ev_out=True)
-        out_dict = {"col_out": col_out, "prev_out": prev_out, "next_out": next_out}
+                outs[1] = m(prev_bundle, raybd2=next_bundle, batch=batch, ev_out=True)
+                outs[2] = m(next_bundle, raybd2=prev_bundle, batch=batch, keep=True, ev_out=True)
+        out_dict = {"col_out": outs[0], "prev_out": outs[1], "next_out": outs[2]}
         metrics_dict = {} if self.lean else m.get_metrics_dict(out_dict, batch)
         loss_dict = m.get_loss_dict(out_dict, batch, metrics_dict)
         return out_dict, loss_dict, metrics_dict

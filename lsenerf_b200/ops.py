@@ -686,8 +686,11 @@ class _RenderRays(torch.autograd.Function):
         need_o, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         d_h16 = torch.empty(S_cap, 16, device=dev)
         cp = fw.c_params(relu_d=ctx.relu[0], relu_c=ctx.relu[1]); cg = _grads_struct(fw, bufs)
-        defer = bool(fw.use_tensor_cores and opts.defer_table_scatter and bufs["table"] is not None)
-        if defer and (need_o or need_d):
+        # engine path (tensor cores): ray gradients from the stored Jacobian; the table scatter itself is deferred to the caller -- or
+        # absent when the table is frozen (camera-only optimisation, train.py:262-293)
+        jacpath = bool(fw.use_tensor_cores and opts.defer_table_scatter)
+        defer = jacpath and bufs["table"] is not None
+        if jacpath and (need_o or need_d):
             # engine path: ray gradients from the stored Jacobian, reduced by one warp per ray in a fixed order and WRITTEN (no
             # atomics, no zero-fill, bit-reproducible); the SH direction gradients take the same route through a per-sample buffer
             g_o = torch.empty_like(o)
@@ -707,19 +710,19 @@ class _RenderRays(torch.autograd.Function):
             cur, side = torch.cuda.current_stream(), _side_stream(dev)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                jac = int(defer and (g_o is not None or gd is not None))      # ray gradients from the stored Jacobian, no re-gather
+                jac = int(jacpath and (g_o is not None or gd is not None))    # ray gradients from the stored Jacobian, no re-gather
                 call("lse_field_density_bwd_encode", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
                      P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), jac, P(ws), nbytes, stream())
             call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
                  P(h16), P(d_rgb), P(d_h16), P(dir_s if packed else gd), int(packed), stream())
             cur.wait_stream(side)
-            if defer:
+            if jacpath:
                 # the table gradient feeds the optimizer only: leave its scatter to the caller (engine: side stream, under the next
                 # step's ray generation); everything the rest of this backward pass needs is produced here
                 call("lse_field_density_bwd_rays", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
                      P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), jac,
                      P(m.starts) if packed else None, P(m.counts) if packed else None, R, P(dir_s), P(ws), nbytes, stream())
-                opts.deferred_table = (fw, bufs, o, d, m, ws, nbytes, S_cap)
+                opts.deferred_table = (fw, bufs, o, d, m, ws, nbytes, S_cap) if defer else None
             else:
                 call("lse_field_density_bwd_finish", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
                      P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), P(d_h16), P(g_o), P(gd), P(ws), nbytes, stream())

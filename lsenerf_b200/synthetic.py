@@ -263,7 +263,7 @@ def init_model_state(model, scene: dict, seed: Optional[int] = None) -> None:
 
 def build_pipeline(scene: dict, experiment: str = "lsenerf", num_rays: int = 8192, rgb_frac: Optional[float] = 0.5,
                    deblur: bool = False, cam_opt: bool = False, device="cuda", seed: Optional[int] = None,
-                   pin: bool = True, **model_kw):
+                   pin: bool = True, eval_camopt: bool = False, **model_kw):
     """Construct datamanager + model + pipeline for one of the shipped experiment configurations on a synthetic scene."""
     from .lse_cameras import EdCameras
     from .lse_config import experiment as make_cfg
@@ -271,10 +271,10 @@ def build_pipeline(scene: dict, experiment: str = "lsenerf", num_rays: int = 819
     from .lse_pipeline import LSENeRFPipeline
     from .lsenerf import LSENeRFModel
     spec: SceneSpec = scene["spec"]
-    dm_cfg, model_cfg = make_cfg(experiment, num_rays=num_rays, deblur=deblur, cam_opt=cam_opt,
+    dm_cfg, model_cfg = make_cfg(experiment, num_rays=num_rays, deblur=deblur, cam_opt=cam_opt, eval_camopt=eval_camopt,
                                  log2_hashmap_size=spec.log2_hashmap_size, grid_resolution=spec.grid_res,
                                  grid_levels=spec.grid_levels, **model_kw)
-    if rgb_frac is not None:
+    if rgb_frac is not None and not eval_camopt:
         dm_cfg.rgb_frac = rgb_frac
         dm_cfg.update_num_batch_rays()
     dm_cfg.col_cam_optimizer.exp_t = scene["exp_t"]

@@ -1369,3 +1369,67 @@ def test_engine_runs_one_sided_batches(dev, rgb_frac):
     gs.flush(); torch.cuda.synchronize()
     assert loss.numel() == 1 and bool(torch.isfinite(loss).all()) and float(loss.sum()) > 0
     assert not torch.equal(w0, opt.arenas["fields"].data)
+
+
+# ---------------------------------------------------------------------------------------------------- camera-only optimisation
+def test_camera_only_optimisation_pass(dev):
+    """BASELINE configs[4] / SURVEY 3.4: the eval-time camera optimisation (train.py:262-293, lse_trainer.py:47-66) -- RGB rays only, plain
+    MSE, SO3xR3 "ns" optimizer on the RGB cameras, the `fields` group dropped: weights frozen, dL/d(origin, direction) flows through
+    compositing, both MLPs, SH and the hash grid's input positions into pose_adjustment alone.  Gradient against oracle autograd
+    (1e-3), nothing else receives one, and a few engine steps pull a perturbed camera back."""
+    from lsenerf_b200 import lse_trainer
+    from lsenerf_b200.engine import ArenaAdam, GraphedStep
+    torch.manual_seed(1234)
+    scene = syn.make_scene(small_spec(targets="analytic", bake_density=True, log2_hashmap_size=16, bake_level=2))
+    p = syn.build_pipeline(scene, "lsenerf", num_rays=1024, device=dev, seed=3, pin=False, eval_camopt=True)
+    dm = p.datamanager
+    assert dm.get_train_evs_rays_per_batch() == 0 and dm.config.rgb_loss_mode == "mse"
+    groups = lse_trainer.setup_param_groups(p, is_eval=True)
+    assert list(groups) == ["camera_opt"] and len(groups["camera_opt"]) == 1
+    co = dm.col_train_camera_optimizer
+    assert groups["camera_opt"][0] is co.pose_adjustment
+    assert not any(q.requires_grad for q in p._model.parameters())
+    with torch.no_grad():
+        co.pose_adjustment.normal_(0, 3e-3)
+    p.train()
+    # ---- one backward pass against the oracle
+    m = p._model
+    m.config.alpha_thre = 0.0; m.config.train_early_stop_eps = 0.0          # fixed sample set on both sides
+    bundles, batch = dm.next_train(0)
+    assert bundles[1] is None and bundles[2] is None
+    g = torch.Generator().manual_seed(31)
+    jit = torch.rand(len(bundles[0]), generator=g).to(dev)
+    out = m(bundles[0], ev_out=False, jitter=jit)
+    ld = m.get_loss_dict({"col_out": out, "prev_out": None, "next_out": None}, batch)
+    sum(ld.values()).backward()
+    assert all(q.grad is None or float(q.grad.abs().max()) == 0.0 for q in m.parameters())
+    from oracle import cameras as OC, data as OD, model as OM, poses as OPo
+    sd, cfg, grid, osc = oracle_state(p), oracle_cfg(p), oracle_grid(p), oracle_scene(scene, p)
+    cfg.alpha_thre = 0.0; cfg.early_stop_eps = 0.0
+    pa = co.pose_adjustment.detach().cpu().clone().requires_grad_(True)
+    idx = batch["col_batch"]["indices"].cpu()
+    c, y, x = idx[:, 0], idx[:, 1], idx[:, 2]
+    o0, d0, _, _ = OC.rays_from_c2w(osc["col_c2w"][c] if "col_c2w" in osc else scene["col_c2w"][c], torch.stack([y, x], -1).float(), *osc["col_intr"])
+    oo, dd = OPo.apply_pose_adjustment(o0, d0, pa, c[:, None])
+    assert rel_err(bundles[0].origins, oo) < 1e-5 and rel_err(bundles[0].directions, dd) < 1e-5
+    ob = dict(origins=oo + (bundles[0].origins.detach().cpu() - oo).detach(), directions=dd + (bundles[0].directions.detach().cpu() - dd).detach(),
+              appearance_id=OD.fix_appearance_id(batch["col_batch"]["appearance_id"].cpu(), oo.shape[0], osc["num_emb"]))
+    oout = OM.get_outputs(sd, cfg, grid, ob, True, False, jit.cpu())
+    old = OM.loss_dict(cfg, oout, None, None, batch["col_batch"]["image"].cpu(), None, None)
+    sum(old.values()).backward()
+    assert abs(ld["rgb_loss"].item() - old["rgb_loss"].item()) <= TOL_OUT * abs(old["rgb_loss"].item())
+    assert float(pa.grad.abs().max()) > 0
+    assert rel_err(co.pose_adjustment.grad, pa.grad) < TOL_GRAD, rel_err(co.pose_adjustment.grad, pa.grad)
+    # ---- the engine runs the camera-only iterations (no field optimizer, no table scatter) and reduces the loss
+    del out, ld, bundles, batch            # no autograd graph of an eager pass may be alive while the engine captures (engine.capture)
+    import gc; gc.collect()
+    m.config.alpha_thre = 0.01; m.config.train_early_stop_eps = 1e-4
+    opt = ArenaAdam(groups)
+    gs = GraphedStep(p, opt, 1, use_graph=True)
+    assert not gs.has_field
+    gs.capture(start_step=0)
+    w0 = {k: v.detach().clone() for k, v in m.state_dict().items() if v.dtype == torch.float32}
+    losses = [float(gs.step()[0]) for _ in range(150)]
+    gs.flush(); torch.cuda.synchronize()
+    assert all(torch.equal(v, m.state_dict()[k]) for k, v in w0.items() if "occupancy" not in k and "_overflow" not in k)       # field frozen
+    assert sum(losses[-20:]) < 0.9 * sum(losses[:20]), (losses[:3], losses[-3:])        # (an untrained field: the loss floor is high)
