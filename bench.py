@@ -9,6 +9,8 @@ One "step" = one training iteration.  --config selects the workload (BASELINE.js
   lsenerf_emb  configs[2]  exp_configs/lsenerf_emb_config.sh: the same with per-event-frame appearance embeddings (evs_emb; the
                embedding table gradient goes through the exchange at N > 1)
   badnerf      configs[3]  exp_configs/BADNERF_config.sh as shipped: rgb_frac 1.0, no mapping, 4 virtual poses per pixel, no event rays
+  eval_camopt  configs[4]  scripts/eval.sh: camera-only optimisation iterations (field frozen, gradients through field + hash grid into the
+               SO3xR3 camera deltas) from the trained state, then the 1280x720 full-frame render with the optimised delta applied
 all on the synthetic EVIMOv2-shape scene of SURVEY.md 8d (640x480 RGB + event cameras, 64 control poses, 128 event frames, 4x128^3
 occupancy grid, 16 x 2^19 x 2 hash table), ray budget 8192.  Rays are counted as the reference counts them (total budget per step,
 lse_datamanager.py:434-435).  Multi-GPU: rays are sharded (every rank draws its own budget, train.py:104), one exchange of the
@@ -49,6 +51,9 @@ CONFIGS = {
                         workload=f"lsenerf_emb_config (per-frame appearance embeddings) on {SCENE}, budget 8192 (1024 RGB px x4 + 2048 event px x2)"),
     "badnerf": dict(experiment="badnerf", rgb_frac=None,
                     workload=f"BADNERF_config as shipped (rgb_frac 1.0, no mapping, no event rays) on {SCENE}, budget 8192 (2048 RGB px x4 virtual poses)"),
+    "eval_camopt": dict(experiment="lsenerf", rgb_frac=0.5, eval_camopt=True,
+                        workload=f"eval-time camera optimisation (train.py:262-293: field frozen, SO3xR3 'ns' deltas on the RGB cameras, 8192 RGB rays, MSE) "
+                                 f"from the trained lsenerf_config state on {SCENE}, followed by the 1280x720 render"),
 }
 START = 1000      # optimizer step the burn-in starts at: after the occupancy grid's 256-step warm-up schedule
 BURN_IN = 3000    # deterministic burn-in steps (the sample counts per ray are stationary from ~1500 steps on)
@@ -149,7 +154,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"unavailable: {e}"], "samples": 0}
 
 
-def build(dev, seed, full=True, budget=BUDGET, config="lsenerf", **model_kw):
+def build(dev, seed, full=True, budget=BUDGET, config="lsenerf", eval_camopt=False, **model_kw):
     from lsenerf_b200 import synthetic as syn
     # analytic (learnable) targets + density prior matching the analytic occupancy (see lsenerf_b200/synthetic.py)
     kw = dict(targets="analytic", bake_density=True)
@@ -157,7 +162,7 @@ def build(dev, seed, full=True, budget=BUDGET, config="lsenerf", **model_kw):
     scene = syn.make_scene(spec)
     c = CONFIGS[config]
     pipe = syn.build_pipeline(scene, c["experiment"], num_rays=budget, rgb_frac=c["rgb_frac"], deblur=True, cam_opt=True, device=dev, seed=seed,
-                              pin=(dev != "cpu"), **model_kw)
+                              pin=(dev != "cpu"), eval_camopt=eval_camopt, **model_kw)
     return scene, pipe
 
 
@@ -271,13 +276,19 @@ def render_leg(pipe, scene, dev, rank, world, max_over_ranks, barrier, H=720, W=
     coords = torch.stack([ys, xs], -1).reshape(-1, 2).contiguous()
     n = coords.shape[0]
     co = pipe.datamanager.col_train_camera_optimizer
-    pa = torch.randn(1, 6, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) * 1e-3
+    cams = pipe.datamanager.col_cams
+    spline = hasattr(co, "get_rgb_cameras")
+    # the SO3xR3 delta applied to the full-frame bundle (lse_loaders.py:20-27): the optimizer's own deltas after the camera-only
+    # iterations (eval_camopt), else a fixed small one
+    pa = co.pose_adjustment.detach() if hasattr(co, "pose_adjustment") else \
+        torch.randn(1, 6, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) * 1e-3
 
     def frame(t):
         with torch.no_grad():
-            c2w = co.get_rgb_cameras(torch.tensor([t], device=dev))[0]
+            cam = int(t / 1.0e4) % pa.shape[0]
+            c2w = co.get_rgb_cameras(torch.tensor([t], device=dev))[0] if spline else cams.camera_to_worlds[cam % cams.size]
             o, d, area, _ = ops.rays_from_c2w(c2w[None].expand(n, 3, 4).contiguous(), coords, f, f, W / 2.0, H / 2.0)
-            o, d = ops.pose_delta(pa, torch.zeros(n, dtype=torch.long, device=dev), o, d)
+            o, d = ops.pose_delta(pa, torch.full((n,), cam, dtype=torch.long, device=dev), o, d)
             rb = RayBundle(o.reshape(r1 - r0, W, 3), d.reshape(r1 - r0, W, 3), area.reshape(r1 - r0, W, 1),
                            torch.zeros(r1 - r0, W, 1, dtype=torch.long, device=dev),
                            metadata={"appearance_id": torch.zeros(r1 - r0, W, 1, dtype=torch.long, device=dev)})
@@ -489,6 +500,25 @@ def run_b200(args):
     state_check = {"probe_marched_evaluated_kept": list(probe), "expected": list(expected) if expected else None, "tolerance": STATE_TOL,
                    "ok": state_ok, "identical_on_all_ranks": True if world == 1 else bool(torch.equal(lo, hi))}
 
+    if CONFIGS[args.config].get("eval_camopt"):
+        # configs[4]: the trained field is frozen and handed to the eval pipeline; only its (zero-initialised) camera deltas train
+        from lsenerf_b200 import lse_trainer
+        _, pipe2 = build(dev, seed=96 + rank, config=args.config, eval_camopt=True, use_tensor_cores=not args.simt)
+        pipe2._model.load_state_dict(pipe._model.state_dict())
+        pipe2._model.occupancy_grid._gen = pipe._model.occupancy_grid._gen
+        pipe2._model.occupancy_grid.refresh_occ_mean()
+        pipe2._model.occupancy_grid.packed(force=True)
+        pipe2.train()
+        groups = lse_trainer.setup_param_groups(pipe2, is_eval=True)
+        del opt
+        pipe, dm = pipe2, pipe2.datamanager
+        sample_batches = dm.sample_rand_batches if args.device_store else dm.sample_host_batches
+        try:
+            opt = ArenaAdam(groups, symmetric_group=sym_group)
+        except Exception:
+            opt = ArenaAdam(groups)
+        opt.step_count = 0
+        step_no = 0
     # ---- the timed engine: plain fp32 atomics, graphs captured from the pinned state --------------------------------------------
     gs = GraphedStep(pipe, opt, world, use_graph=not args.no_graph, device_store=args.device_store)
     gs.no_overlap = args.no_overlap
