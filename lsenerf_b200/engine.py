@@ -116,6 +116,13 @@ class ArenaAdam:
         self.hp_dev = torch.zeros(len(self.names), 4, device=dev)
         self.step_count = 0
         self._grad_scale = 1.0
+        # The fused exchange (apply_collective) SHARDS the Adam moments: rank r updates exp_avg / exp_avg_sq only inside its 1/W slice
+        # of every arena, the rest of its moment buffers goes stale.  `_sharded` records that this has happened: from then on the plain
+        # apply() would read stale moments for (W-1)/W of the parameters, so it is refused until gather_moments() has re-assembled them.
+        self._sharded = False
+        self.group = symmetric_group
+        if symmetric_group is not None:
+            self.sync_from_rank0()
         self.det_shadows: Optional[Dict[str, torch.Tensor]] = None
         self.barrier_events: Optional[list] = None
 
@@ -147,6 +154,55 @@ class ArenaAdam:
         a = self.arenas[name]
         call("lse_det_flush", P(a.grad), P(self.det_shadows[name]), a.numel, stream())
 
+    # ---- replicas: initial state, sharded moments, checkpoints --------------------------------------------------------------------
+    def sync_from_rank0(self) -> None:
+        """every replica starts from rank 0's parameters and moments (the reference's DDP wrapper broadcasts the module state at
+        construction, lse_pipeline.py:96-97): with the fused exchange a rank's slice is otherwise overwritten by its owner's
+        differently initialised weights."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        for a in self.arenas.values():
+            for t in (a.data, a.exp_avg, a.exp_avg_sq):
+                dist.broadcast(t, 0, group=self.group)
+
+    def _slice(self, a: "ParamArena", rank: int, world: int):
+        """the [lo, hi) element range of rank `rank` in adam_collective.cu: n4 = numel/4 float4s split evenly, the remainder to the last rank"""
+        n4 = a.numel // 4                       # arenas are padded to a multiple of 4 floats
+        per = (n4 + world - 1) // world
+        lo = min(rank * per, n4)
+        return lo * 4, min(lo + per, n4) * 4
+
+    @torch.no_grad()
+    def gather_moments(self) -> None:
+        """re-assemble the full Adam moments on every rank from the owners' slices (after apply_collective steps); afterwards the state
+        is a complete replica again (checkpointing, switching to the all-reduce path, single-rank continuation)."""
+        if not self._sharded:
+            return
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        for a in self.arenas.values():
+            for buf in (a.exp_avg, a.exp_avg_sq):
+                for r in range(world):
+                    lo, hi = self._slice(a, r, world)
+                    if hi > lo:
+                        dist.broadcast(buf[lo:hi], dist.get_global_rank(self.group, r) if self.group is not None else r, group=self.group)
+        self._sharded = False
+
+    def state_dict(self) -> dict:
+        """complete optimizer state (moments gathered first when they are sharded): {"step", "arenas": {name: {exp_avg, exp_avg_sq}}}"""
+        self.gather_moments()
+        return {"step": self.step_count,
+                "arenas": {n: {"exp_avg": a.exp_avg.clone(), "exp_avg_sq": a.exp_avg_sq.clone()} for n, a in self.arenas.items()}}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd: dict) -> None:
+        self.step_count = int(sd["step"])
+        for n, st in sd["arenas"].items():
+            a = self.arenas[n]
+            a.exp_avg.copy_(st["exp_avg"]); a.exp_avg_sq.copy_(st["exp_avg_sq"])
+        self._sharded = False
+
     def zero_grad(self, only: Optional[List[str]] = None) -> None:
         for n, a in self.arenas.items():
             if only is None or n in only:
@@ -171,6 +227,9 @@ class ArenaAdam:
     @torch.no_grad()
     def apply(self, only: Optional[List[str]] = None) -> None:
         """one fused Adam launch per group, reading hp_dev (graph-capturable)."""
+        if self._sharded:
+            raise RuntimeError("the Adam moments are sharded by the fused exchange (apply_collective): call gather_moments() before "
+                               "stepping a replica on its own")
         for i, name in enumerate(self.names):
             if only is not None and name not in only:
                 continue
@@ -189,6 +248,7 @@ class ArenaAdam:
         different channels).  Replaces allreduce() + apply() when the arenas are symmetric."""
         import ctypes
         assert self.symmetric, "apply_collective needs arenas allocated in symmetric memory"
+        self._sharded = True
         names = [n for n in self.names if only is None or n in only]
         first = self.arenas[names[0]]
         rec = self.barrier_events is not None                 # bench.py: CUDA events around the two barriers (how long does this rank wait?)
@@ -308,6 +368,13 @@ class GraphedStep:
                  device_store: bool = False, deterministic: bool = False) -> None:
         self.pipeline, self.optim, self.world = pipeline, optim, world_size
         self.use_graph = use_graph
+        for co in (pipeline.datamanager.col_train_camera_optimizer, pipeline.datamanager.evs_train_camera_optimizer):
+            # CameraOptimizerConfig(scheme="delayed") switches the optimizer on at step delay_cnt (ns_camera_optimizer.py:245-256): that
+            # changes the parameter groups and the captured launch sequence in mid-training, which flat arenas and graphs cannot follow
+            if getattr(co, "is_on", True) is False:
+                raise NotImplementedError("GraphedStep captures a fixed launch sequence over fixed parameter arenas: a camera optimizer "
+                                          "with scheme='delayed' that is still off would never turn on.  Train eagerly "
+                                          "(lse_pipeline.train_iteration) until delay_cnt, or use scheme='active'.")
         # deterministic: the gradients of a step do not depend on the order in which the atomics land (ArenaAdam.enable_deterministic
         # must be active while this engine steps); every optimizer launch is preceded by the flush of its arena's fixed-point shadow
         self.deterministic = deterministic

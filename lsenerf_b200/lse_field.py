@@ -31,6 +31,7 @@ class Ed_HashEncoding(nn.Module):
         assert interpolation is None or interpolation == "Linear"
         self.in_dim = 3
         self.num_levels = num_levels
+        self.max_res = max_res
         self.features_per_level = features_per_level
         self.log2_hashmap_size = log2_hashmap_size
         self.hash_table_size = 2**log2_hashmap_size

@@ -36,6 +36,11 @@ class LSEOccGridEstimator(nn.Module):
         self._mip: Optional[Tensor] = None
         self._packed_key = None
 
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._mean_valid = False          # occ_mean is derived (non-persistent): recompute it from the loaded occs on next use
+        self._packed_key = None
+
     def binaries_u8(self) -> Tensor:
         return self.binaries.view(torch.uint8)
 

@@ -168,6 +168,33 @@ class LSENeRFModel(nn.Module):
             groups["fields"] = list(self.field.embedding_appearance.parameters())
         return groups
 
+    def load_reference_state_dict(self, state_dict: dict, strict: bool = True):
+        """Load the `_model.*` part of a checkpoint written by the reference.  Its module tree holds a few entries this one does not:
+        the hash grid and base MLP a second time under `field.mlp_base.0.*` / `field.mlp_base.1.*` (the nn.Sequential alias,
+        lse_field.py:208), the scalar buffers `field.max_res / num_levels / log2_hashmap_size` (lse_field.py:158-160), and the occupancy
+        grid a second time under `sampler.occupancy_grid.*` (VolumetricSampler holds the estimator, lsenerf.py:191-194).  Aliases are
+        checked against their twins and dropped, the scalars against this model's configuration; everything else must match
+        (strict) exactly as nn.Module.load_state_dict would demand."""
+        sd = {}
+        f = self.field.mlp_base_grid
+        scalars = {"field.max_res": f.max_res, "field.num_levels": f.num_levels, "field.log2_hashmap_size": f.log2_hashmap_size}
+        alias = (("field.mlp_base.0.", "field.mlp_base_grid."), ("field.mlp_base.1.", "field.mlp_base_mlp."),
+                 ("sampler.occupancy_grid.", "occupancy_grid."))
+        state_dict = {(k[len("_model."):] if k.startswith("_model.") else k): v for k, v in state_dict.items()}
+        for k, v in state_dict.items():
+            if k in scalars:
+                if int(v) != int(scalars[k]):
+                    raise RuntimeError(f"checkpoint {k} = {int(v)} but this model was built with {int(scalars[k])}")
+                continue
+            twin = next((new + k[len(old):] for old, new in alias if k.startswith(old)), None)
+            if twin is not None:
+                if twin in state_dict and not torch.equal(torch.as_tensor(state_dict[twin]).cpu(), torch.as_tensor(v).cpu()):
+                    raise RuntimeError(f"checkpoint alias {k} disagrees with {twin}")
+                sd.setdefault(twin, v)
+                continue
+            sd[k] = v
+        return self.load_state_dict(sd, strict=strict)
+
     def init_test_params(self):
         self.field.embedding_appearance.init_test_params()
 

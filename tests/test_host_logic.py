@@ -131,3 +131,58 @@ def test_ray_generator_coords_and_bundle_concat():
     lean = concat_bundles([a, b], fields=("origins", "directions"), metadata_keys=("appearance_id",))
     assert lean.pixel_area is None and lean.camera_indices is None and set(lean.metadata) == {"appearance_id"}
     assert torch.equal(lean.origins, full.origins) and torch.equal(lean.directions, full.directions)
+
+
+def test_collective_slices_tile_the_arena():
+    """ArenaAdam._slice restates the slice arithmetic of csrc/adam_collective.cu (gather_moments re-assembles the sharded Adam moments
+    from it): the ranks' slices are disjoint, ordered and cover the arena."""
+    from types import SimpleNamespace
+    from lsenerf_b200.engine import ArenaAdam
+    for numel in (4, 8, 4096, 16787468, 1234568):
+        for world in (1, 2, 3, 4, 8):
+            a = SimpleNamespace(numel=numel)
+            edges = [ArenaAdam._slice(None, a, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == numel
+            for (lo, hi), (lo2, _) in zip(edges, edges[1:]):
+                assert lo <= hi == lo2
+            n4, per = numel // 4, (numel // 4 + world - 1) // world
+            for r, (lo, hi) in enumerate(edges):         # the kernel's own expressions
+                b = min(r * per, n4)
+                assert (lo, hi) == (4 * b, 4 * min(b + per, n4))
+
+
+def test_reference_checkpoint_keys_load():
+    """a state dict with the reference's key list (aliases under field.mlp_base.N / sampler.occupancy_grid, scalar buffers) loads
+    strictly through LSENeRFModel.load_reference_state_dict; a mismatching alias or scalar is refused"""
+    import pytest
+    import torch
+    from lsenerf_b200.lse_config import experiment
+    from lsenerf_b200.lsenerf import LSENeRFModel
+    _, mc = experiment("lsenerf_emb", log2_hashmap_size=10, grid_resolution=32, grid_levels=2)
+    src = LSENeRFModel(mc, torch.tensor([-1.0, -1, -1, 1, 1, 1]), num_train_data=5)
+    with torch.no_grad():
+        src.occupancy_grid.occs.uniform_(0, 0.02)
+        src.occupancy_grid.binaries.copy_(torch.rand(2, 32, 32, 32) < 0.3)
+    own = src.state_dict()
+    ref = {"_model." + k: v.clone() for k, v in own.items()}
+    for k, v in own.items():                               # the reference's extra entries
+        if k.startswith("field.mlp_base_grid."):
+            ref["_model.field.mlp_base.0." + k[len("field.mlp_base_grid."):]] = v.clone()
+        if k.startswith("field.mlp_base_mlp."):
+            ref["_model.field.mlp_base.1." + k[len("field.mlp_base_mlp."):]] = v.clone()
+        if k.startswith("occupancy_grid."):
+            ref["_model.sampler.occupancy_grid." + k[len("occupancy_grid."):]] = v.clone()
+    ref["_model.field.max_res"] = torch.tensor(2048); ref["_model.field.num_levels"] = torch.tensor(16)
+    ref["_model.field.log2_hashmap_size"] = torch.tensor(10)
+    dst = LSENeRFModel(mc, torch.tensor([-1.0, -1, -1, 1, 1, 1]), num_train_data=5)
+    dst.occupancy_grid._mean_valid = True
+    res = dst.load_reference_state_dict(ref, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert all(torch.equal(v, dst.state_dict()[k]) for k, v in own.items())
+    assert dst.occupancy_grid._mean_valid is False          # the derived mean is recomputed from the loaded occs
+    bad = dict(ref); bad["_model.field.log2_hashmap_size"] = torch.tensor(19)
+    with pytest.raises(RuntimeError, match="log2_hashmap_size"):
+        dst.load_reference_state_dict(bad)
+    bad = dict(ref); bad["_model.field.mlp_base.1.layers.0.bias"] = ref["_model.field.mlp_base.1.layers.0.bias"] + 1
+    with pytest.raises(RuntimeError, match="alias"):
+        dst.load_reference_state_dict(bad)
