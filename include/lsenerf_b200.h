@@ -59,13 +59,17 @@ int lse_pixel_gather(const float *rand3, int64_t B, int64_t N, int H, int W, con
                      const int64_t *image_idx, const int64_t *appearance_id, const float *e_thresh, int64_t *indices,
                      float *image_out, int64_t *appearance_out, float *e_thresh_out, lse_stream_t stream);
 
-/* EdCameras._generate_rays_from_coords, perspective branch (lse_nerf/lse_cameras.py:349-395,487-493,539-561).
- *   c2w [n,3,4], coords [n,2]=(y,x)  ->  origins [n,3], directions [n,3], pixel_area [n], dir_norm [n] */
+/* EdCameras._generate_rays_from_coords, perspective branch (lse_nerf/lse_cameras.py:349-414,487-493,539-561).
+ *   c2w [n,3,4], coords [n,2]=(y,x)  ->  origins [n,3], directions [n,3], pixel_area [n], dir_norm [n]
+ *   distortion: NULL, or 6 floats (k1,k2,k3,k4,p1,p2) -- the OpenCV lens model the scene files carry (lse_parser.py:187-198): the
+ *   pixel and its two +1 px neighbours are undistorted by nerfstudio's radial_and_tangential_undistort (10 Newton steps,
+ *   lse_cameras.py:397-414) before they become directions. */
 int lse_rays_from_c2w_fwd(const float *c2w, const float *coords, int64_t n, float fx, float fy, float cx, float cy,
-                          float *origins, float *directions, float *pixel_area, float *dir_norm,
+                          const float *distortion, float *origins, float *directions, float *pixel_area, float *dir_norm,
                           lse_stream_t stream);
 int lse_rays_from_c2w_bwd(const float *c2w, const float *coords, int64_t n, float fx, float fy, float cx, float cy,
-                          const float *d_origins, const float *d_directions, float *d_c2w, lse_stream_t stream);
+                          const float *distortion, const float *d_origins, const float *d_directions, float *d_c2w,
+                          lse_stream_t stream);
 
 /* CameraOptimizer.forward + apply_to_raybundle, mode SO3xR3 (lse_nerf/ns_camera_optimizer.py:258-329):
  *   origins += t(pose_adjustment[cam]); directions = R(pose_adjustment[cam]) @ directions.  cam_idx int64 [n]. */
@@ -75,6 +79,16 @@ int lse_pose_delta_fwd(const float *pose_adjustment, int64_t n_cams, const int64
 int lse_pose_delta_bwd(const float *pose_adjustment, int64_t n_cams, const int64_t *cam_idx, int64_t n,
                        const float *directions, const float *d_origins_out, const float *d_directions_out,
                        float *d_pose_adjustment, float *d_origins, float *d_directions, lse_stream_t stream);
+
+/* The same application with the [n_cams,3,4] correction matrices given explicitly (CameraOptimizer mode "SE3",
+ * lse_nerf/ns_camera_optimizer.py:276-277: nerfstudio exp_map_SE3 of the pose table is evaluated per CAMERA by the host mirror, these
+ * kernels apply it per RAY): origins += M[cam][:,3]; directions = M[cam][:,:3] @ directions.  Backward: d_mats [n_cams,3,4]
+ * accumulated atomically, d_origins / d_directions written. */
+int lse_apply_delta_fwd(const float *mats, int64_t n_cams, const int64_t *cam_idx, int64_t n, const float *origins,
+                        const float *directions, float *origins_out, float *directions_out, lse_stream_t stream);
+int lse_apply_delta_bwd(const float *mats, int64_t n_cams, const int64_t *cam_idx, int64_t n, const float *directions,
+                        const float *d_origins_out, const float *d_directions_out, float *d_mats, float *d_origins,
+                        float *d_directions, lse_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (b) occupancy-grid marching  (3P nerfacc.grid.traverse_grids, lse_nerf/lse_grid_estimator.py:83-106)

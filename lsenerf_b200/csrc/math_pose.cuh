@@ -239,15 +239,42 @@ LSE_HD void cam_dir(const float *c2w, float px, float py, float v[3], float &nrm
     for (int i = 0; i < 3; ++i) d[i] = v[i] / nrm;
 }
 
+// 3P nerfstudio camera_utils.radial_and_tangential_undistort (call site lse_nerf/lse_cameras.py:397-414): the undistorted normalised
+// image coordinate (x, y) whose OpenCV distortion (k1, k2, k3, k4 radial, p1, p2 tangential; dist = [k1,k2,k3,k4,p1,p2]) gives (xd, yd),
+// by 10 Newton steps from (xd, yd); a step is skipped where |det J| <= 1e-3.
+LSE_HD void undistort_one(float &x, float &y, const float dist[6])
+{
+    const float k1 = dist[0], k2 = dist[1], k3 = dist[2], k4 = dist[3], p1 = dist[4], p2 = dist[5];
+    const float xd = x, yd = y;
+    for (int it = 0; it < 10; ++it) {
+        const float r = x * x + y * y;
+        const float d = 1.0f + r * (k1 + r * (k2 + r * (k3 + r * k4)));
+        const float fx = d * x + 2.0f * p1 * x * y + p2 * (r + 2.0f * x * x) - xd;
+        const float fy = d * y + 2.0f * p2 * x * y + p1 * (r + 2.0f * y * y) - yd;
+        const float d_r = k1 + r * (2.0f * k2 + r * (3.0f * k3 + r * 4.0f * k4));
+        const float d_x = 2.0f * x * d_r, d_y = 2.0f * y * d_r;
+        const float fx_x = d + d_x * x + 2.0f * p1 * y + 6.0f * p2 * x;
+        const float fx_y = d_y * x + 2.0f * p1 * x + 2.0f * p2 * y;
+        const float fy_x = d_x * y + 2.0f * p2 * y + 2.0f * p1 * x;
+        const float fy_y = d + d_y * y + 2.0f * p2 * x + 6.0f * p1 * y;
+        const float den = fy_x * fx_y - fx_x * fy_y;
+        const bool ok = fabsf(den) > 1e-3f;
+        x += ok ? (fx * fy_y - fy * fx_y) / den : 0.0f;
+        y += ok ? (fy * fx_x - fx * fy_x) / den : 0.0f;
+    }
+}
+
 LSE_HD void rays_from_c2w_one(const float *c2w, float y, float x, float fx, float fy, float cx, float cy,
-                              float o[3], float d[3], float &pixel_area, float &dnorm)
+                              float o[3], float d[3], float &pixel_area, float &dnorm, const float *dist = nullptr)
 {
     float px = (x - cx) / fx, py = -(y - cy) / fy;
     float px1 = (x - cx + 1.0f) / fx, py1 = -(y - cy + 1.0f) / fy;
+    float pxa = px, pya = py, pxb = px1, pyb = py, pxc = px, pyc = py1;      // centre, +1 px in x, +1 px in y
+    if (dist) { undistort_one(pxa, pya, dist); undistort_one(pxb, pyb, dist); undistort_one(pxc, pyc, dist); }
     float v[3], n1, n2, d1[3], d2[3];
-    cam_dir(c2w, px, py, v, dnorm, d);
-    cam_dir(c2w, px1, py, v, n1, d1);
-    cam_dir(c2w, px, py1, v, n2, d2);
+    cam_dir(c2w, pxa, pya, v, dnorm, d);
+    cam_dir(c2w, pxb, pyb, v, n1, d1);
+    cam_dir(c2w, pxc, pyc, v, n2, d2);
     float dx = sqrtf((d[0] - d1[0]) * (d[0] - d1[0]) + (d[1] - d1[1]) * (d[1] - d1[1]) + (d[2] - d1[2]) * (d[2] - d1[2]));
     float dy = sqrtf((d[0] - d2[0]) * (d[0] - d2[0]) + (d[1] - d2[1]) * (d[1] - d2[1]) + (d[2] - d2[2]) * (d[2] - d2[2]));
     pixel_area = dx * dy;
@@ -257,9 +284,10 @@ LSE_HD void rays_from_c2w_one(const float *c2w, float y, float x, float fx, floa
 // gradient of (origins, directions) w.r.t. c2w; pixel_area / dir_norm carry no gradient (the sampler replaces
 // pixel_area by ones and directions_norm is detached, lse_cameras.py:568-571).
 LSE_HD void rays_from_c2w_one_bwd(const float *c2w, float y, float x, float fx, float fy, float cx, float cy,
-                                  const float d_o[3], const float d_d[3], float d_c2w[12])
+                                  const float d_o[3], const float d_d[3], float d_c2w[12], const float *dist = nullptr)
 {
     float px = (x - cx) / fx, py = -(y - cy) / fy;
+    if (dist) undistort_one(px, py, dist);
     float v[3], nrm, d[3];
     cam_dir(c2w, px, py, v, nrm, d);
     float raw = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);

@@ -60,16 +60,18 @@ __global__ void pose_interp_bwd_kernel(const float *__restrict__ ctrl_tangents, 
 }
 
 __global__ void rays_from_c2w_fwd_kernel(const float *__restrict__ c2w, const float *__restrict__ coords, int64_t n,
-                                         float fx, float fy, float cx, float cy, float *__restrict__ origins,
-                                         float *__restrict__ directions, float *__restrict__ pixel_area,
-                                         float *__restrict__ dir_norm)
+                                         float fx, float fy, float cx, float cy, const float *__restrict__ distortion,
+                                         float *__restrict__ origins, float *__restrict__ directions,
+                                         float *__restrict__ pixel_area, float *__restrict__ dir_norm)
 {
+    float dist[6];
+    if (distortion) { for (int j = 0; j < 6; ++j) dist[j] = distortion[j]; }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float M[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) M[j] = c2w[12 * i + j];
         float o[3], d[3], area, nrm;
-        rays_from_c2w_one(M, coords[2 * i], coords[2 * i + 1], fx, fy, cx, cy, o, d, area, nrm);
+        rays_from_c2w_one(M, coords[2 * i], coords[2 * i + 1], fx, fy, cx, cy, o, d, area, nrm, distortion ? dist : nullptr);
 #pragma unroll
         for (int j = 0; j < 3; ++j) { origins[3 * i + j] = o[j]; directions[3 * i + j] = d[j]; }
         if (pixel_area) pixel_area[i] = area;
@@ -78,16 +80,18 @@ __global__ void rays_from_c2w_fwd_kernel(const float *__restrict__ c2w, const fl
 }
 
 __global__ void rays_from_c2w_bwd_kernel(const float *__restrict__ c2w, const float *__restrict__ coords, int64_t n,
-                                         float fx, float fy, float cx, float cy, const float *__restrict__ d_o,
-                                         const float *__restrict__ d_d, float *__restrict__ d_c2w)
+                                         float fx, float fy, float cx, float cy, const float *__restrict__ distortion,
+                                         const float *__restrict__ d_o, const float *__restrict__ d_d, float *__restrict__ d_c2w)
 {
+    float dist[6];
+    if (distortion) { for (int j = 0; j < 6; ++j) dist[j] = distortion[j]; }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float M[12], go[3], gd[3], g[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) M[j] = c2w[12 * i + j];
 #pragma unroll
         for (int j = 0; j < 3; ++j) { go[j] = d_o ? d_o[3 * i + j] : 0.0f; gd[j] = d_d ? d_d[3 * i + j] : 0.0f; }
-        rays_from_c2w_one_bwd(M, coords[2 * i], coords[2 * i + 1], fx, fy, cx, cy, go, gd, g);
+        rays_from_c2w_one_bwd(M, coords[2 * i], coords[2 * i + 1], fx, fy, cx, cy, go, gd, g, distortion ? dist : nullptr);
 #pragma unroll
         for (int j = 0; j < 12; ++j) d_c2w[12 * i + j] = g[j];
     }
@@ -138,6 +142,51 @@ __global__ void pose_delta_bwd_kernel(const float *__restrict__ pa, int64_t n_ca
         if (d_d) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) d_d[3 * i + j] = dd[j];
+        }
+    }
+}
+
+// CameraOptimizer.apply_to_raybundle with the correction matrices given explicitly (mode SE3: exp_map_SE3 of the [n_cams,6] table is
+// evaluated per CAMERA upstream of this kernel; per ray only origins += t[cam], directions = R[cam] d remains)
+__global__ void apply_delta_fwd_kernel(const float *__restrict__ mats, int64_t n_cams, const int64_t *__restrict__ cam_idx, int64_t n,
+                                       const float *__restrict__ origins, const float *__restrict__ directions,
+                                       float *__restrict__ o_out, float *__restrict__ d_out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = cam_idx[i];
+        c = c < 0 ? 0 : (c >= n_cams ? n_cams - 1 : c);
+        const float *M = mats + 12 * c;
+        const float d[3] = {directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            o_out[3 * i + r] = origins[3 * i + r] + M[4 * r + 3];
+            d_out[3 * i + r] = M[4 * r] * d[0] + M[4 * r + 1] * d[1] + M[4 * r + 2] * d[2];
+        }
+    }
+}
+
+__global__ void apply_delta_bwd_kernel(const float *__restrict__ mats, int64_t n_cams, const int64_t *__restrict__ cam_idx, int64_t n,
+                                       const float *__restrict__ directions, const float *__restrict__ g_o,
+                                       const float *__restrict__ g_d, float *__restrict__ d_mats, float *__restrict__ d_o,
+                                       float *__restrict__ d_d)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = cam_idx[i];
+        c = c < 0 ? 0 : (c >= n_cams ? n_cams - 1 : c);
+        const float *M = mats + 12 * c;
+        const float d[3] = {directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]};
+        float go[3], gd[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { go[r] = g_o ? g_o[3 * i + r] : 0.0f; gd[r] = g_d ? g_d[3 * i + r] : 0.0f; }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (d_mats) {
+                red_add(d_mats + 12 * c + 4 * r + 3, go[r]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) red_add(d_mats + 12 * c + 4 * r + k, gd[r] * d[k]);
+            }
+            if (d_o) d_o[3 * i + r] = go[r];
+            if (d_d) d_d[3 * i + r] = M[r] * gd[0] + M[4 + r] * gd[1] + M[8 + r] * gd[2];      // R^T g
         }
     }
 }
@@ -214,24 +263,24 @@ extern "C" int lse_pixel_gather(const float *rand3, int64_t B, int64_t N, int H,
 }
 
 extern "C" int lse_rays_from_c2w_fwd(const float *c2w, const float *coords, int64_t n, float fx, float fy, float cx,
-                                     float cy, float *origins, float *directions, float *pixel_area, float *dir_norm,
-                                     lse_stream_t stream)
+                                     float cy, const float *distortion, float *origins, float *directions, float *pixel_area,
+                                     float *dir_norm, lse_stream_t stream)
 {
     if (n <= 0) return 0;
     int threads = 256;
     rays_from_c2w_fwd_kernel<<<stride_grid(n, threads), threads, 0, (cudaStream_t)stream>>>(
-        c2w, coords, n, fx, fy, cx, cy, origins, directions, pixel_area, dir_norm);
+        c2w, coords, n, fx, fy, cx, cy, distortion, origins, directions, pixel_area, dir_norm);
     return check_launch("lse_rays_from_c2w_fwd");
 }
 
 extern "C" int lse_rays_from_c2w_bwd(const float *c2w, const float *coords, int64_t n, float fx, float fy, float cx,
-                                     float cy, const float *d_origins, const float *d_directions, float *d_c2w,
-                                     lse_stream_t stream)
+                                     float cy, const float *distortion, const float *d_origins, const float *d_directions,
+                                     float *d_c2w, lse_stream_t stream)
 {
     if (n <= 0) return 0;
     int threads = 256;
     rays_from_c2w_bwd_kernel<<<stride_grid(n, threads), threads, 0, (cudaStream_t)stream>>>(
-        c2w, coords, n, fx, fy, cx, cy, d_origins, d_directions, d_c2w);
+        c2w, coords, n, fx, fy, cx, cy, distortion, d_origins, d_directions, d_c2w);
     return check_launch("lse_rays_from_c2w_bwd");
 }
 
@@ -256,4 +305,25 @@ extern "C" int lse_pose_delta_bwd(const float *pose_adjustment, int64_t n_cams, 
         pose_adjustment, n_cams, cam_idx, n, directions, d_origins_out, d_directions_out, d_pose_adjustment, d_origins,
         d_directions);
     return check_launch("lse_pose_delta_bwd");
+}
+
+extern "C" int lse_apply_delta_fwd(const float *mats, int64_t n_cams, const int64_t *cam_idx, int64_t n, const float *origins,
+                                   const float *directions, float *origins_out, float *directions_out, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(mats && cam_idx && origins && directions && origins_out && directions_out && n_cams > 0, "missing pointer");
+    if (n <= 0) return 0;
+    apply_delta_fwd_kernel<<<stride_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(mats, n_cams, cam_idx, n, origins, directions, origins_out,
+                                                                                   directions_out);
+    return check_launch("lse_apply_delta_fwd");
+}
+
+extern "C" int lse_apply_delta_bwd(const float *mats, int64_t n_cams, const int64_t *cam_idx, int64_t n, const float *directions,
+                                   const float *d_origins_out, const float *d_directions_out, float *d_mats, float *d_origins,
+                                   float *d_directions, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(mats && cam_idx && directions && n_cams > 0, "missing pointer");
+    if (n <= 0) return 0;
+    apply_delta_bwd_kernel<<<stride_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(mats, n_cams, cam_idx, n, directions, d_origins_out,
+                                                                                   d_directions_out, d_mats, d_origins, d_directions);
+    return check_launch("lse_apply_delta_bwd");
 }

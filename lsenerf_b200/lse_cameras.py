@@ -1,6 +1,6 @@
 """EdCameras (mirror of lse_nerf/lse_cameras.py, perspective path): pose lookup / interpolation hook and pinhole ray
-generation on csrc/raygen.cu.  Distortion, fisheye, equirect and ODS branches are out of scope (the datasets are
-undistorted perspective, lse_parser.py:198-199)."""
+generation on csrc/raygen.cu, with the OpenCV radial / tangential lens model of the scene files (lse_cameras.py:397-414,
+lse_parser.py:187-198; one coefficient set per camera rig).  Fisheye, equirect and ODS branches are out of scope."""
 from __future__ import annotations
 
 from types import MethodType
@@ -17,7 +17,7 @@ from .utils import fix_datashape
 
 class EdCameras:
     def __init__(self, camera_to_worlds: Tensor, fx, fy, cx, cy, width: int, height: int, times: Optional[Tensor] = None,
-                 metadata=None):
+                 metadata=None, distortion_params: Optional[Tensor] = None):
         n = camera_to_worlds.shape[0]
 
         def col(v):
@@ -28,6 +28,10 @@ class EdCameras:
         self.width, self.height = int(width), int(height)
         self.times = times.reshape(-1, 1).float() if times is not None else None
         self.metadata = metadata
+        # (k1,k2,k3,k4,p1,p2), lse_parser.py:189; None (or all zero) = no distortion, as upstream (lse_parser.py:198)
+        dp = torch.as_tensor(distortion_params, dtype=torch.float32).reshape(-1) if distortion_params is not None else None
+        assert dp is None or dp.numel() == 6, "one (k1,k2,k3,k4,p1,p2) set for the rig"
+        self.distortion_params = dp if (dp is not None and bool((dp != 0).any())) else None
         self.interpolator = None
         self.hard_cam_type = HardCamType.RGB
         self.get_c2w_fn = self.get_c2w
@@ -48,7 +52,7 @@ class EdCameras:
         return self.size
 
     def to(self, device):
-        for k in ("camera_to_worlds", "fx", "fy", "cx", "cy", "times"):
+        for k in ("camera_to_worlds", "fx", "fy", "cx", "cy", "times", "distortion_params"):
             v = getattr(self, k)
             if v is not None:
                 setattr(self, k, v.to(device))
@@ -99,7 +103,7 @@ class EdCameras:
         """lse_cameras.py:257-586, perspective branch."""
         c2w, _ = self.get_c2w_fn(camera_indices)
         assert c2w.shape == (coords.shape[0], 3, 4)
-        o, d, area, nrm = ops.rays_from_c2w(c2w, coords.float().contiguous(), *self.intrinsics())
+        o, d, area, nrm = ops.rays_from_c2w(c2w, coords.float().contiguous(), *self.intrinsics(), self.distortion_params)
         if self.lean:
             times, cam_idx = None, (camera_indices if camera_indices.shape[0] == o.shape[0] else None)
         else:

@@ -18,8 +18,8 @@ Layout of a formatted scene (EVIMOv2 / LSENeRF data, README of the reference):
     <scene>/ecam_set/scene.json               {"e_thresh": c}            (optional, default 0.2)
     <scene>/ecam_set/eimgs/eimgs_1x.npy       [N,H,W] accumulated event counts
 
-Distorted cameras (non-zero radial / tangential coefficients) are rejected: the datasets are undistorted perspective
-(lse_parser.py:198-199) and the ray kernels implement the pinhole branch only.
+Lens coefficients (radial k1..k3, tangential p1, p2; lse_parser.py:187-198) are handed to the ray kernel, which undistorts the pixel
+coordinates as upstream does (lse_cameras.py:397-414); they must agree across the frames of a camera.
 """
 from __future__ import annotations
 
@@ -107,14 +107,20 @@ class CameraParser:
                 times.append(float(d["t"]))
         c2w[:, :3, 3] *= self.scale_factor
         d0 = data[0]
-        dist = list(d0.get("radial_distortion", [0, 0, 0])) + list(d0.get("tangential_distortion", [0, 0]))
-        if any(abs(float(x)) > 0 for x in dist):
-            raise NotImplementedError("distorted cameras are outside the pinhole ray path (lse_cameras.py:397-414)")
+
+        def lens(d):   # lse_parser.py:187-189: (k1, k2, k3, 0, p1, p2)
+            k = [float(x) for x in d.get("radial_distortion", [0, 0, 0])]
+            p = [float(x) for x in d.get("tangential_distortion", [0, 0])]
+            return k + [0.0] + p
+        dist = lens(d0)
+        if any(lens(d) != dist for d in data):
+            raise NotImplementedError("per-frame lens coefficients: the ray kernel takes one (k1,k2,k3,k4,p1,p2) set per camera rig")
         cx, cy = d0["principal_point"]
         w, h = d0["image_size"]
         t = torch.tensor(times, dtype=torch.float32) if times else None
         cams = EdCameras(torch.from_numpy(c2w[:, :3, :4].astype(np.float32)), float(d0["focal_length"]), float(d0["focal_length"]),
-                         float(cx), float(cy), int(w), int(h), times=t)
+                         float(cx), float(cy), int(w), int(h), times=t,
+                         distortion_params=torch.tensor(dist) if any(x != 0.0 for x in dist) else None)   # None if all zero, :198
         cams.set_hard_cam_type(cam_type)
         return ParsedCameras(cams, w2c_cv, t)
 

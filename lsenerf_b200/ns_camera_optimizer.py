@@ -102,8 +102,32 @@ class SplineCameraOptimizer(nn.Module, _Schedule):
             param_groups["camera_opt"] = list(self.parameters())
 
 
+def exp_map_SE3(tangent: Tensor) -> Tensor:
+    """nerfstudio lie_groups.exp_map_SE3 (ns_camera_optimizer.py:276-277) on the [n_cams, 6] pose table: a handful of elementwise device
+    ops over n_cams rows, differentiated by autograd; the per-ray work is csrc/raygen.cu:apply_delta_*."""
+    lin, ang = tangent[:, :3].reshape(-1, 3, 1), tangent[:, 3:].reshape(-1, 3, 1)
+    theta = torch.linalg.norm(ang, dim=1).unsqueeze(1)
+    theta2, theta3 = theta**2, theta**3
+    near = theta < 1e-2
+    one = torch.ones(1, dtype=tangent.dtype, device=tangent.device)
+    theta_nz, theta2_nz, theta3_nz = torch.where(near, one, theta), torch.where(near, one, theta2), torch.where(near, one, theta3)
+    sine = theta.sin()
+    cosine = torch.where(near, 8 / (4 + theta2) - 1, theta.cos())
+    sine_by_theta = torch.where(near, 0.5 * cosine + 0.5, sine / theta_nz)
+    omc = torch.where(near, 0.5 * sine_by_theta, (1 - cosine) / theta2_nz)
+    R = omc * ang @ ang.transpose(1, 2) + cosine.reshape(-1, 1, 1) * torch.eye(3, dtype=tangent.dtype, device=tangent.device)[None]
+    temp = sine_by_theta.reshape(-1, 1) * ang.reshape(-1, 3)
+    zero = torch.zeros_like(temp[:, 0])
+    R = R + torch.stack([zero, -temp[:, 2], temp[:, 1], temp[:, 2], zero, -temp[:, 0], -temp[:, 1], temp[:, 0], zero], dim=1).reshape(-1, 3, 3)
+    sbt = torch.where(near, 1 - theta2 / 6, sine_by_theta)
+    omc = torch.where(near, 0.5 - theta2 / 24, omc)
+    tms = torch.where(near, 1.0 / 6 - theta2 / 120, (theta - sine) / theta3_nz)
+    t = sbt * lin + omc * torch.cross(ang, lin, dim=1) + tms * (ang @ (ang.transpose(1, 2) @ lin))
+    return torch.cat([R, t], dim=2)
+
+
 class CameraOptimizer(nn.Module, _Schedule):
-    """ns_camera_optimizer.py:214-366, mode SO3xR3 (SE3 is unused by every shipped config)."""
+    """ns_camera_optimizer.py:214-366, modes SO3xR3 (every shipped config) and SE3."""
 
     def __init__(self, config, num_cameras: int, device="cpu", non_trainable_camera_indices=None, **kwargs) -> None:
         super().__init__()
@@ -113,7 +137,7 @@ class CameraOptimizer(nn.Module, _Schedule):
         assert non_trainable_camera_indices is None
         if config.mode == "off":
             pass
-        elif config.mode == "SO3xR3":
+        elif config.mode in ("SO3xR3", "SE3"):
             self.pose_adjustment = nn.Parameter(torch.zeros((num_cameras, 6), device=device))
         else:
             raise NotImplementedError(f"camera optimizer mode {config.mode}")
@@ -126,6 +150,8 @@ class CameraOptimizer(nn.Module, _Schedule):
         if self.config.mode == "off":
             return torch.eye(4, device=idx.device)[None, :3, :4].tile(n, 1, 1)
         dev = self.pose_adjustment.device
+        if self.config.mode == "SE3":
+            return exp_map_SE3(self.pose_adjustment[idx, :])
         cols = []
         zero = torch.zeros(n, 3, device=dev)
         for k in range(3):
@@ -138,8 +164,12 @@ class CameraOptimizer(nn.Module, _Schedule):
         """:322-329: origins += t, directions = R @ d (left-applied to the world-space ray)."""
         if self.config.mode != "off":
             shape = raybundle.origins.shape
-            o, d = ops.pose_delta(self.pose_adjustment, raybundle.camera_indices.reshape(-1), raybundle.origins.reshape(-1, 3),
-                                  raybundle.directions.reshape(-1, 3))
+            if self.config.mode == "SE3":
+                o, d = ops.apply_delta(exp_map_SE3(self.pose_adjustment), raybundle.camera_indices.reshape(-1),
+                                       raybundle.origins.reshape(-1, 3), raybundle.directions.reshape(-1, 3))
+            else:
+                o, d = ops.pose_delta(self.pose_adjustment, raybundle.camera_indices.reshape(-1), raybundle.origins.reshape(-1, 3),
+                                      raybundle.directions.reshape(-1, 3))
             raybundle.origins, raybundle.directions = o.reshape(shape), d.reshape(shape)
 
     def get_loss_dict(self, loss_dict: dict, prefix="") -> None:

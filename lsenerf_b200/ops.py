@@ -106,13 +106,14 @@ class _RaysFromC2W(torch.autograd.Function):
     """EdCameras._generate_rays_from_coords, perspective (lse_cameras.py:349-395,487-493,539-561)."""
 
     @staticmethod
-    def forward(ctx, c2w, coords, fx, fy, cx, cy):
+    def forward(ctx, c2w, coords, fx, fy, cx, cy, distortion=None):
         ctx.set_materialize_grads(False)      # an output nobody differentiates arrives as None, not as a zero-filled tensor
         c2w = _f32(c2w, "c2w"); coords = _f32(coords, "coords")
+        ctx.dist = _f32(distortion.reshape(6), "distortion") if distortion is not None else None
         n = coords.shape[0]
         o = torch.empty(n, 3, device=c2w.device); d = torch.empty(n, 3, device=c2w.device)
         area = torch.empty(n, 1, device=c2w.device); nrm = torch.empty(n, 1, device=c2w.device)
-        call("lse_rays_from_c2w_fwd", P(c2w), P(coords), n, fx, fy, cx, cy, P(o), P(d), P(area), P(nrm), stream())
+        call("lse_rays_from_c2w_fwd", P(c2w), P(coords), n, fx, fy, cx, cy, P(ctx.dist), P(o), P(d), P(area), P(nrm), stream())
         ctx.save_for_backward(c2w, coords)
         ctx.intr = (fx, fy, cx, cy)
         ctx.mark_non_differentiable(area, nrm)
@@ -122,15 +123,16 @@ class _RaysFromC2W(torch.autograd.Function):
     def backward(ctx, d_o, d_d, _a, _n):
         c2w, coords = ctx.saved_tensors
         if d_o is None and d_d is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         g = torch.empty_like(c2w)
-        call("lse_rays_from_c2w_bwd", P(c2w), P(coords), coords.shape[0], *ctx.intr,
+        call("lse_rays_from_c2w_bwd", P(c2w), P(coords), coords.shape[0], *ctx.intr, P(ctx.dist),
              P(d_o.contiguous()) if d_o is not None else None, P(d_d.contiguous()) if d_d is not None else None, P(g), stream())
-        return g, None, None, None, None, None
+        return g, None, None, None, None, None, None
 
 
-def rays_from_c2w(c2w, coords, fx, fy, cx, cy):
-    return _RaysFromC2W.apply(c2w, coords, float(fx), float(fy), float(cx), float(cy))
+def rays_from_c2w(c2w, coords, fx, fy, cx, cy, distortion: Optional[Tensor] = None):
+    """distortion: None or 6 floats (k1,k2,k3,k4,p1,p2) on the device (lse_cameras.py:397-414)."""
+    return _RaysFromC2W.apply(c2w, coords, float(fx), float(fy), float(cx), float(cy), distortion)
 
 
 class _PoseDelta(torch.autograd.Function):
@@ -165,6 +167,35 @@ class _PoseDelta(torch.autograd.Function):
 
 def pose_delta(pose_adjustment, cam_idx, origins, directions):
     return _PoseDelta.apply(pose_adjustment, cam_idx, origins, directions)
+
+
+class _ApplyDelta(torch.autograd.Function):
+    """CameraOptimizer.apply_to_raybundle with explicit per-camera [3,4] corrections (mode SE3, ns_camera_optimizer.py:276-277,322-329)."""
+
+    @staticmethod
+    def forward(ctx, mats, cam_idx, origins, directions):
+        ctx.set_materialize_grads(False)
+        M = _f32(mats, "mats"); o = _f32(origins, "origins"); d = _f32(directions, "directions")
+        ci = cam_idx.reshape(-1).to(torch.int64).contiguous()
+        oo = torch.empty_like(o); dd = torch.empty_like(d)
+        call("lse_apply_delta_fwd", P(M), M.shape[0], P(ci), o.shape[0], P(o), P(d), P(oo), P(dd), stream())
+        ctx.save_for_backward(M, ci, d)
+        return oo, dd
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        M, ci, d = ctx.saved_tensors
+        if g_o is None and g_d is None:
+            return None, None, None, None
+        d_M = torch.zeros_like(M) if ctx.needs_input_grad[0] else None
+        d_o = torch.empty_like(d); d_d = torch.empty_like(d)
+        call("lse_apply_delta_bwd", P(M), M.shape[0], P(ci), d.shape[0], P(d), P(g_o.contiguous()) if g_o is not None else None,
+             P(g_d.contiguous()) if g_d is not None else None, P(d_M), P(d_o), P(d_d), stream())
+        return d_M, None, d_o, d_d
+
+
+def apply_delta(mats, cam_idx, origins, directions):
+    return _ApplyDelta.apply(mats, cam_idx, origins, directions)
 
 
 # =================================================================================================================

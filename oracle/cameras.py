@@ -16,7 +16,32 @@ from . import poses
 _NORM_EPS = float(np.finfo(float).eps * 4.0)  # nerfstudio camera_utils._EPS
 
 
-def rays_from_c2w(c2w: Tensor, coords_yx: Tensor, fx: float, fy: float, cx: float, cy: float):
+def radial_and_tangential_undistort(coords: Tensor, dist: Tensor, eps: float = 1e-3, max_iterations: int = 10) -> Tensor:
+    """nerfstudio 0.3.2 camera_utils.radial_and_tangential_undistort (called at lse_cameras.py:408-411) [3P, restated]: Newton
+    iterations from the distorted point for the (x, y) whose OpenCV distortion (k1,k2,k3,k4,p1,p2) reproduces `coords`; a step is
+    taken only where |det J| > eps."""
+    k1, k2, k3, k4, p1, p2 = [dist[..., i] for i in range(6)]
+    xd, yd = coords[..., 0], coords[..., 1]
+    x, y = xd, yd
+    for _ in range(max_iterations):
+        r = x * x + y * y
+        d = 1.0 + r * (k1 + r * (k2 + r * (k3 + r * k4)))
+        fx = d * x + 2 * p1 * x * y + p2 * (r + 2 * x * x) - xd
+        fy = d * y + 2 * p2 * x * y + p1 * (r + 2 * y * y) - yd
+        d_r = k1 + r * (2.0 * k2 + r * (3.0 * k3 + r * 4.0 * k4))
+        d_x, d_y = 2.0 * x * d_r, 2.0 * y * d_r
+        fx_x = d + d_x * x + 2.0 * p1 * y + 6.0 * p2 * x
+        fx_y = d_y * x + 2.0 * p1 * x + 2.0 * p2 * y
+        fy_x = d_x * y + 2.0 * p2 * y + 2.0 * p1 * x
+        fy_y = d + d_y * y + 2.0 * p2 * x + 6.0 * p1 * y
+        den = fy_x * fx_y - fx_x * fy_y
+        ok = den.abs() > eps
+        x = x + torch.where(ok, (fx * fy_y - fy * fx_y) / den, torch.zeros_like(den))
+        y = y + torch.where(ok, (fy * fx_x - fx * fy_x) / den, torch.zeros_like(den))
+    return torch.stack([x, y], dim=-1)
+
+
+def rays_from_c2w(c2w: Tensor, coords_yx: Tensor, fx: float, fy: float, cx: float, cy: float, distortion: Tensor | None = None):
     """EdCameras._generate_rays_from_coords, perspective branch (lse_cameras.py:349-395,487-493,539-561).
 
     c2w [R,3,4]; coords_yx [R,2] = (y, x) integer-valued floats (no +0.5, lse_cameras.py:69-73); intrinsics of
@@ -28,6 +53,8 @@ def rays_from_c2w(c2w: Tensor, coords_yx: Tensor, fx: float, fy: float, cx: floa
     c1 = torch.stack([(x - cx + 1) / fx, -(y - cy) / fy], -1)
     c2 = torch.stack([(x - cx) / fx, -(y - cy + 1) / fy], -1)
     cs = torch.stack([c0, c1, c2], dim=0)  # [3,R,2]
+    if distortion is not None and bool((distortion != 0).any()):       # lse_cameras.py:397-414
+        cs = radial_and_tangential_undistort(cs, distortion.reshape(6).to(cs))
     dcam = torch.cat([cs, -torch.ones_like(cs[..., :1])], dim=-1)  # (x, y, -1)
     R = c2w[..., :3, :3]
     dw = torch.sum(dcam[..., None, :] * R, dim=-1)  # [3,R,3]

@@ -148,10 +148,40 @@ def spline_deblur_c2w(ctrl_tangents: Tensor, ctrl_ts: Tensor, cam_ts: Tensor, ex
 
 # ---- CameraOptimizer ("ns", SO3xR3) (ns_camera_optimizer.py:258-329) ---------------------------------------
 
-def apply_pose_adjustment(origins: Tensor, directions: Tensor, pose_adjustment: Tensor, cam_idx: Tensor):
+def exp_map_se3(tangent: Tensor) -> Tensor:
+    """nerfstudio 0.3.2 lie_groups.exp_map_SE3 (called at ns_camera_optimizer.py:276-277) [3P, restated; derived from Theseus]:
+    tangent [n,6] = (v, omega) -> [n,3,4] with R = Rodrigues(omega) and t = V(omega) v, series expansions below |omega| = 1e-2."""
+    lin = tangent[:, :3].reshape(-1, 3, 1)
+    ang = tangent[:, 3:].reshape(-1, 3, 1)
+    theta = torch.linalg.norm(ang, dim=1).unsqueeze(1)
+    theta2, theta3 = theta**2, theta**3
+    near = theta < 1e-2
+    one = torch.ones(1, dtype=tangent.dtype, device=tangent.device)
+    theta_nz, theta2_nz, theta3_nz = torch.where(near, one, theta), torch.where(near, one, theta2), torch.where(near, one, theta3)
+    sine = theta.sin()
+    cosine = torch.where(near, 8 / (4 + theta2) - 1, theta.cos())
+    sine_by_theta = torch.where(near, 0.5 * cosine + 0.5, sine / theta_nz)
+    omc_by_theta2 = torch.where(near, 0.5 * sine_by_theta, (1 - cosine) / theta2_nz)
+    ret = torch.zeros(tangent.shape[0], 3, 4, dtype=tangent.dtype, device=tangent.device)
+    R = omc_by_theta2 * ang @ ang.transpose(1, 2)
+    R = R + cosine.reshape(-1, 1, 1) * torch.eye(3, dtype=tangent.dtype, device=tangent.device)[None]
+    temp = sine_by_theta.reshape(-1, 1) * ang.reshape(-1, 3)
+    zero = torch.zeros_like(temp[:, 0])
+    skew = torch.stack([zero, -temp[:, 2], temp[:, 1], temp[:, 2], zero, -temp[:, 0], -temp[:, 1], temp[:, 0], zero], dim=1).reshape(-1, 3, 3)
+    R = R + skew
+    sine_by_theta = torch.where(near, 1 - theta2 / 6, sine_by_theta)
+    omc_by_theta2 = torch.where(near, 0.5 - theta2 / 24, omc_by_theta2)
+    tms_by_theta3 = torch.where(near, 1.0 / 6 - theta2 / 120, (theta - sine) / theta3_nz)
+    t = sine_by_theta * lin + omc_by_theta2 * torch.cross(ang, lin, dim=1) + tms_by_theta3 * (ang @ (ang.transpose(1, 2) @ lin))
+    ret[:, :, :3] = R
+    ret[:, :, 3:] = t
+    return ret
+
+
+def apply_pose_adjustment(origins: Tensor, directions: Tensor, pose_adjustment: Tensor, cam_idx: Tensor, mode: str = "SO3xR3"):
     """apply_to_raybundle, ns_camera_optimizer.py:322-329: origins += t_delta; directions = R_delta @ d
     (left-applied to the world-space ray, quirk 7 of SURVEY Appendix B)."""
-    D = exp_map_so3xr3(pose_adjustment[cam_idx.reshape(-1).long()])
+    D = (exp_map_se3 if mode == "SE3" else exp_map_so3xr3)(pose_adjustment[cam_idx.reshape(-1).long()])
     o = origins + D[:, :3, 3]
     d = torch.bmm(D[:, :3, :3], directions[..., None])[..., 0]
     return o, d

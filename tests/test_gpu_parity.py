@@ -1371,6 +1371,37 @@ def test_engine_runs_one_sided_batches(dev, rgb_frac):
     assert not torch.equal(w0, opt.arenas["fields"].data)
 
 
+def test_lens_distortion_in_the_ray_kernel(dev):
+    """lse_cameras.py:397-414: radial / tangential undistortion of the pixel and its two neighbours inside
+    lse_rays_from_c2w_fwd/bwd against the oracle's restatement of nerfstudio's Newton iteration: rays 1e-5, pixel area 1e-4, c2w gradient
+    1e-3; and EdCameras carries the coefficients through generate_rays."""
+    from lsenerf_b200 import ops
+    from lsenerf_b200.lse_cameras import EdCameras
+    from oracle import cameras as OC
+    g = torch.Generator().manual_seed(3)
+    n = 3000
+    c2w = torch.randn(n, 3, 4, generator=g)
+    coords = torch.stack([torch.randint(0, 480, (n,), generator=g), torch.randint(0, 640, (n,), generator=g)], -1).float()
+    intr = (500.0, 505.0, 320.0, 240.0)
+    dist = torch.tensor([-0.12, 0.05, -0.01, 0.0, 0.002, -0.003])
+    cr = c2w.clone().requires_grad_(True)
+    o_r, d_r, a_r, n_r = OC.rays_from_c2w(cr, coords, *intr, distortion=dist)
+    o_p, d_p, _, _ = OC.rays_from_c2w(c2w, coords, *intr)
+    assert float((d_r - d_p).abs().max()) > 1e-3                      # the lens model matters at this field of view
+    cc = c2w.to(dev).requires_grad_(True)
+    o, d, a, nn_ = ops.rays_from_c2w(cc, coords.to(dev), *intr, dist.to(dev))
+    assert rel_err(o, o_r) < 1e-6 and rel_err(d, d_r) < 1e-5 and rel_err(a, a_r) < TOL_OUT and rel_err(nn_, n_r) < 1e-5
+    wo, wd = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+    ((o_r * wo).sum() + (d_r * wd).sum()).backward()
+    ((o * wo.to(dev)).sum() + (d * wd.to(dev)).sum()).backward()
+    assert rel_err(cc.grad, cr.grad) < TOL_GRAD
+    cams = EdCameras(c2w[:4, :, :], *intr, 640, 480, distortion_params=dist).to(dev)
+    rb = cams.generate_rays(torch.tensor([[1], [2]], device=dev), coords[:2].to(dev))
+    ref = OC.rays_from_c2w(c2w[1:3], coords[:2], *intr, distortion=dist)
+    assert rel_err(rb.directions, ref[1]) < 1e-5
+    assert EdCameras(c2w[:4], *intr, 640, 480, distortion_params=torch.zeros(6)).distortion_params is None     # lse_parser.py:198
+
+
 # ---------------------------------------------------------------------------------------------------- camera-only optimisation
 def test_camera_only_optimisation_pass(dev):
     """BASELINE configs[4] / SURVEY 3.4: the eval-time camera optimisation (train.py:262-293, lse_trainer.py:47-66) -- RGB rays only, plain
@@ -1433,3 +1464,31 @@ def test_camera_only_optimisation_pass(dev):
     gs.flush(); torch.cuda.synchronize()
     assert all(torch.equal(v, m.state_dict()[k]) for k, v in w0.items() if "occupancy" not in k and "_overflow" not in k)       # field frozen
     assert sum(losses[-20:]) < 0.9 * sum(losses[:20]), (losses[:3], losses[-3:])        # (an untrained field: the loss floor is high)
+
+
+def test_se3_camera_optimizer_mode(dev):
+    """CameraOptimizerConfig(mode="SE3") (ns_camera_optimizer.py:276-277): exp_map_SE3 of the pose table + per-ray application on
+    csrc/raygen.cu:apply_delta_* against the oracle's restatement of nerfstudio's exp_map_SE3: rays 1e-5, pose gradient 1e-3; rotations
+    on both sides of the series threshold |omega| = 1e-2."""
+    from lsenerf_b200.compat import RayBundle
+    from lsenerf_b200.ns_camera_optimizer import CameraOptimizer, CameraOptimizerConfig
+    from oracle import poses as OPo
+    g = torch.Generator().manual_seed(8)
+    n_cam, n = 6, 2000
+    co = CameraOptimizer(CameraOptimizerConfig(mode="SE3"), n_cam, device=dev).to(dev)
+    pa = torch.randn(n_cam, 6, generator=g) * 0.05
+    pa[0, 3:] = torch.tensor([2e-3, -1e-3, 3e-3]); pa[1] = 0.0           # below the series threshold / exactly zero
+    with torch.no_grad():
+        co.pose_adjustment.copy_(pa)
+    o = torch.randn(n, 3, generator=g); d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    ci = torch.randint(0, n_cam, (n, 1), generator=g)
+    par = pa.clone().requires_grad_(True)
+    o_r, d_r = OPo.apply_pose_adjustment(o, d, par, ci, mode="SE3")
+    rb = RayBundle(o.to(dev), d.to(dev), None, ci.to(dev))
+    co.apply_to_raybundle(rb)
+    assert rel_err(rb.origins, o_r) < 1e-5 and rel_err(rb.directions, d_r) < 1e-5
+    wo, wd = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+    ((o_r * wo).sum() + (d_r * wd).sum()).backward()
+    ((rb.origins * wo.to(dev)).sum() + (rb.directions * wd.to(dev)).sum()).backward()
+    assert rel_err(co.pose_adjustment.grad, par.grad) < TOL_GRAD
+    assert rel_err(co(torch.arange(n_cam, device=dev)), OPo.exp_map_se3(pa)) < 1e-5

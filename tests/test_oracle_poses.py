@@ -59,3 +59,22 @@ def test_product_tangent_init_matches_reference_formula():
     g = _load("pose_gen_data_seed0")
     mine = torch.stack([matrix_to_tangent_vector(M) for M in g["w2cs"]])
     assert np.abs(mine.numpy() - g["tangents"]).max() < 1e-5
+
+
+def test_undistort_inverts_the_opencv_lens_model():
+    """oracle/cameras.py:radial_and_tangential_undistort (nerfstudio camera_utils, called at lse_cameras.py:408-411): distorting its
+    result with the forward OpenCV model gives the input back, and zero coefficients leave coordinates untouched."""
+    import torch
+    from oracle import cameras as OC
+    g = torch.Generator().manual_seed(0)
+    xy = (torch.rand(500, 2, generator=g, dtype=torch.float64) - 0.5) * 1.2
+    dist = torch.tensor([-0.12, 0.05, -0.01, 0.0, 0.002, -0.003], dtype=torch.float64)
+    u = OC.radial_and_tangential_undistort(xy, dist)
+    x, y = u[:, 0], u[:, 1]
+    r = x * x + y * y
+    d = 1.0 + r * (dist[0] + r * (dist[1] + r * (dist[2] + r * dist[3])))
+    xd = d * x + 2 * dist[4] * x * y + dist[5] * (r + 2 * x * x)
+    yd = d * y + 2 * dist[5] * x * y + dist[4] * (r + 2 * y * y)
+    assert torch.allclose(torch.stack([xd, yd], -1), xy, atol=1e-9)
+    assert torch.equal(OC.radial_and_tangential_undistort(xy, torch.zeros(6, dtype=torch.float64)), xy)
+    assert float((u - xy).abs().max()) > 1e-3

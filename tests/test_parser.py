@@ -97,13 +97,24 @@ def test_formatted_scene_roundtrip(tmp_path):
     assert int(col_b["indices"][:, 0].max()) < K and int(evs_b["indices"][:, 0].max()) < n
 
 
-def test_distorted_cameras_are_rejected(tmp_path):
+def test_lens_coefficients_reach_the_cameras(tmp_path):
+    """lse_parser.py:187-198: (k1,k2,k3,0,p1,p2) of the camera JSONs become EdCameras.distortion_params (None when all zero);
+    frames of one camera that disagree are refused (the ray kernel takes one set per rig)."""
     import pytest
+    import torch
     d = str(tmp_path / "colcam_set"); os.makedirs(os.path.join(d, "camera"))
-    cam = _cam_json(np.eye(4)[:3], 10.0, 2.0, 2.0, 4, 4, 0.0)
-    cam["radial_distortion"] = [0.1, 0.0, 0.0]
-    json.dump(cam, open(os.path.join(d, "camera", "000000.json"), "w"))
-    json.dump({"000000": {"appearance_id": 0}}, open(os.path.join(d, "metadata.json"), "w"))
+    meta = {}
+    for i in range(2):
+        cam = _cam_json(np.eye(4)[:3], 10.0, 2.0, 2.0, 4, 4, float(i))
+        cam["radial_distortion"] = [0.1, -0.02, 0.003]; cam["tangential_distortion"] = [0.001, -0.002]
+        json.dump(cam, open(os.path.join(d, "camera", f"{i:06d}.json"), "w"))
+        meta[f"{i:06d}"] = {"appearance_id": i}
+    json.dump(meta, open(os.path.join(d, "metadata.json"), "w"))
+    p = LP.CameraParser(d)
+    cams = p.format_camera(p.cam_data_json, 0).cameras
+    assert torch.allclose(cams.distortion_params, torch.tensor([0.1, -0.02, 0.003, 0.0, 0.001, -0.002]))
+    cam["radial_distortion"] = [0.2, 0.0, 0.0]
+    json.dump(cam, open(os.path.join(d, "camera", "000001.json"), "w"))
     p = LP.CameraParser(d)
     with pytest.raises(NotImplementedError):
         p.format_camera(p.cam_data_json, 0)
