@@ -84,6 +84,46 @@ class LSENeRFPipeline(nn.Module):
         loss_dict = m.get_loss_dict(out_dict, batch, metrics_dict)
         return out_dict, loss_dict, metrics_dict
 
+    @torch.no_grad()
+    def get_average_eval_image_metrics(self, cameras, images, appearance_ids=None, camera_opt=None, log_dir=None, lpips_fn=None,
+                                       chunk=None) -> dict:
+        """lse_pipeline.py:185-233 with the eval loader of lse_loaders.py:8-27 folded in: for every eval image build the [H,W] bundle of
+        its camera, apply the (eval-optimised) camera deltas, fill metadata["appearance_id"], render in chunks, score against the image
+        and time it (num_rays_per_sec / fps as upstream, :209-218); per-image PNGs + eval_metrics.json / eval_mean.json when log_dir is
+        given (LSEWriter).  cameras: EdCameras; images [N,H,W,3]."""
+        from time import perf_counter
+
+        from .lse_writer import LSEWriter
+        was_training = self.training
+        self.eval()
+        writer = LSEWriter(log_dir) if log_dir is not None else None
+        m, dev = self._model, self._model.device
+        cameras.lean = False
+        per_image = []
+        for i in range(images.shape[0]):
+            torch.cuda.synchronize()
+            t0 = perf_counter()
+            rb = cameras.generate_rays(camera_indices=i)
+            if camera_opt is not None:
+                camera_opt.apply_to_raybundle(rb)
+            app = int(appearance_ids[i]) if appearance_ids is not None else 0
+            rb.metadata["appearance_id"] = torch.full(rb.camera_indices.shape, app, device=dev)
+            out = m.get_outputs_for_camera_ray_bundle(rb, chunk=chunk)
+            metrics, imgs = m.get_image_metrics_and_images(out, {"image": images[i]}, lpips_fn)
+            torch.cuda.synchronize()
+            H, W = rb.origins.shape[:2]
+            metrics["num_rays_per_sec"] = H * W / (perf_counter() - t0)
+            metrics["fps"] = metrics["num_rays_per_sec"] / (H * W)
+            per_image.append(metrics)
+            if writer is not None:
+                writer.log_images(imgs)
+        if writer is not None:
+            writer.log_metrics(per_image)
+        if was_training:
+            self.train()
+        return {k: (float(sum(x[k] for x in per_image if x[k] is not None) / max(1, sum(x[k] is not None for x in per_image)))
+                    if any(x[k] is not None for x in per_image) else None) for k in per_image[0]}
+
     def _finish(self, out, ev_out):
         """the post-compositing half of LSENeRFModel.get_outputs applied to a slice of the fused render."""
         return self._model.render_epilogue(out, ev_out, lean=self.lean)

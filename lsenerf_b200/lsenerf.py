@@ -370,6 +370,12 @@ class LSENeRFModel(nn.Module):
             ld["event_loss"] = l_ev
         return ld
 
+    @torch.no_grad()
+    def get_image_metrics_and_images(self, outputs, batch, lpips_fn=None):
+        """lsenerf.py:476-530 (psnr / ssim / optional lpips + the eval visualisations)."""
+        from .lse_metrics import image_metrics_and_images
+        return image_metrics_and_images(outputs, batch, self.device, lpips_fn)
+
     # ---- eval rendering ---------------------------------------------------------------------------------------------
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle, chunk: Optional[int] = None) -> Dict[str, Tensor]:

@@ -186,3 +186,47 @@ def test_reference_checkpoint_keys_load():
     bad = dict(ref); bad["_model.field.mlp_base.1.layers.0.bias"] = ref["_model.field.mlp_base.1.layers.0.bias"] + 1
     with pytest.raises(RuntimeError, match="alias"):
         dst.load_reference_state_dict(bad)
+
+
+def test_psnr_ssim_restatements():
+    """lse_metrics.psnr / ssim (the torchmetrics functions nerfstudio wires into get_image_metrics_and_images, lsenerf.py:513-515): known
+    answers -- identical images, a constant offset, and SSIM against a direct (slow) evaluation of its definition."""
+    import torch
+    from lsenerf_b200 import lse_metrics as LM
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand(1, 3, 24, 30, generator=g, dtype=torch.float64)
+    assert float(LM.ssim(a, a)) == 1.0
+    b = (a + 0.1).clamp(0, 1)
+    mse = ((a - b) ** 2).mean()
+    assert abs(float(LM.psnr(b, a)) - float(10 * torch.log10(1.0 / mse))) < 1e-9
+    # direct definition: gaussian-weighted local moments on the reflect-padded images, borders cropped
+    k, sig, pad = 11, 1.5, 5
+    d = torch.arange(-5, 6, dtype=torch.float64)
+    w = torch.exp(-(d / sig) ** 2 / 2); w = w / w.sum(); w2 = w[:, None] * w[None, :]
+    P = torch.nn.functional.pad(a, (pad,) * 4, mode="reflect"); T = torch.nn.functional.pad(b, (pad,) * 4, mode="reflect")
+    L = float(max(a.max() - a.min(), b.max() - b.min())); c1, c2 = (0.01 * L) ** 2, (0.03 * L) ** 2
+    vals = []
+    H, W = P.shape[-2:]
+    for c in range(3):
+        for y in range(pad, H - k + 1 - pad):
+            for x in range(pad, W - k + 1 - pad):
+                p, t = P[0, c, y:y + k, x:x + k], T[0, c, y:y + k, x:x + k]
+                mp, mt = (w2 * p).sum(), (w2 * t).sum()
+                spp, stt, spt = (w2 * p * p).sum() - mp**2, (w2 * t * t).sum() - mt**2, (w2 * p * t).sum() - mp * mt
+                vals.append(((2 * mp * mt + c1) * (2 * spt + c2)) / ((mp**2 + mt**2 + c1) * (spp + stt + c2)))
+    assert abs(float(LM.ssim(a, b)) - float(torch.stack(vals).mean())) < 1e-10
+
+
+def test_writer_layout(tmp_path):
+    import os
+    """LSEWriter (lse_writer.py:16-77): eval_results/<key>/NNN.png, comb_imgs, eval_metrics.json / eval_mean.json"""
+    import json
+    import torch
+    from lsenerf_b200.lse_writer import LSEWriter
+    w = LSEWriter(str(tmp_path))
+    w.log_images({"img": torch.rand(8, 20, 3), "accumulation": torch.rand(8, 10, 3), "err_map": torch.rand(8, 10, 3), "ev_out": torch.rand(8, 10, 1)})
+    mean = w.log_metrics([{"psnr": 20.0, "ssim": 0.5, "lpips": None}, {"psnr": 30.0, "ssim": 0.7, "lpips": None}])
+    assert os.path.exists(tmp_path / "eval_results" / "img" / "000.png") and os.path.exists(tmp_path / "eval_results" / "comb_imgs" / "000.png")
+    assert not os.path.exists(tmp_path / "eval_results" / "accumulation")
+    assert mean == {"psnr": 25.0, "ssim": 0.6, "lpips": None}
+    assert json.load(open(tmp_path / "eval_metrics.json"))["psnr"] == [20.0, 30.0]
