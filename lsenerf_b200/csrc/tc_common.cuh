@@ -97,12 +97,54 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- A operand in TMEM ("TS" form): D[tmem] (+)= A[tmem] * B[smem]^T ------------------------------------------------------------
+// A is read with M along the 128 lanes and K along the columns (one 32-bit column per tf32 element, 8 columns per K = 8 step), i.e. in
+// the layout a thread-per-row epilogue writes with tcgen05.st: a hidden layer goes accumulator -> registers (bias, ReLU, hi/lo split)
+// -> TMEM without touching shared memory, which otherwise carries 64 KB of staging stores and 4 KB of A reads per MMA.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> TMEM: 32 consecutive columns of this thread's lane (the mirror image of tmem_ld)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+                   "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+                   "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- 3xTF32 split and operand staging ---------------------------------------------------------------------------------
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo)
 {
     hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
     lo = x - hi;
 }
+
+// this thread's activation row v[0..K) -> hi / lo pieces at TMEM columns col_hi / col_lo of its lane
+template <int K>
+__device__ __forceinline__ void stage_tmem(uint32_t tmem_row, int col_hi, int col_lo, const float (&v)[K])
+{
+#pragma unroll
+    for (int c = 0; c < K; c += 32) {
+        uint32_t h[32], l[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float hi, lo;
+            split_tf32(v[c + j], hi, lo);
+            h[j] = __float_as_uint(hi); l[j] = __float_as_uint(lo);
+        }
+        tmem_st32(tmem_row + col_hi + c, h);
+        tmem_st32(tmem_row + col_lo + c, l);
+    }
+    tmem_st_wait();
+}
+
 
 // write 4 consecutive K values of row `row` (panel kc) into the hi / lo operand buffers of a `rows`-row matrix
 __device__ __forceinline__ void stage4(float *hi_buf, float *lo_buf, int rows, int kc, int row, float a, float b, float c, float d)
@@ -159,6 +201,21 @@ __device__ __forceinline__ void issue_layer_u(uint32_t d_tmem, uint32_t a_hi, ui
         mma_tf32(d_tmem, ah0 + ao, wh0 + wo, idesc, acc); acc = 1;
         mma_tf32(d_tmem, al0 + ao, wh0 + wo, idesc, 1);
         mma_tf32(d_tmem, ah0 + ao, wl0 + wo, idesc, 1);
+    }
+}
+// the same layer with the activations in TMEM (columns a_hi / a_lo of the tile's lanes), weights in shared memory
+__device__ __forceinline__ void issue_layer_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, int N, int K)
+{
+    const uint32_t idesc = idesc_tf32(128, N);
+    const uint32_t w_lbo = (uint32_t)N * 16;
+    const uint64_t wh0 = smem_desc(w_hi, w_lbo, 128), wl0 = smem_desc(w_lo, w_lbo, 128);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t wo = (uint64_t)((ks * 2 * w_lbo) >> 4);
+        const uint32_t ao = (uint32_t)(ks * 8);                  // 8 tf32 columns per K step
+        mma_tf32_ts(d_tmem, a_hi + ao, wh0 + wo, idesc, acc); acc = 1;
+        mma_tf32_ts(d_tmem, a_lo + ao, wh0 + wo, idesc, 1);
+        mma_tf32_ts(d_tmem, a_hi + ao, wl0 + wo, idesc, 1);
     }
 }
 // one lane of a converged warp (elect.sync) / a warp-uniform value made provably uniform for the compiler
