@@ -404,6 +404,15 @@ int lse_det_flush(float *grad, void *shadow, int64_t n, lse_stream_t stream);
 int lse_gather_microbench(const void *table, int64_t table_bytes, int vec_bytes, int iters, int coherent, int ctas_per_sm,
                           float *sink, int64_t *loads_out, lse_stream_t stream);
 
+/* Issue-to-completion clocks of `n_mma` tcgen05.mma instructions (M = 128, N columns) issued round-robin over `n_acc` TMEM
+ * accumulators by one elected thread (n_issuers = 2: two warps, one accumulator set each) on ONE CTA; best of `reps`.
+ * mode 0: bf16, A / B K-major in shared memory; 1: bf16, A / B MN-major (the weight-gradient form); 2: tf32, A in tensor memory;
+ * 3: tf32, A / B in shared memory.  cycles_out (device, 2 int64 per issuer): {first issue -> completion observed, first -> last
+ * issue}.  n_acc = 1 is one dependent chain (every instruction accumulates into the previous one's columns): the figure the
+ * 64-wide MLP layers of field_tc*.cu are bounded by. */
+int lse_mma_chain_microbench(int mode, int n_mma, int n_acc, int N, int n_issuers, int reps, int64_t *cycles_out,
+                             lse_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

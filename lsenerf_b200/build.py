@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "liblsenerf_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "lsenerf_b200.h")
 
 SOURCES = ["abi.cu", "raygen.cu", "march.cu", "hashgrid.cu", "field.cu", "field_simt.cu", "field_tc.cu", "field_tc_bwd.cu", "field_hash.cu",
-           "composite.cu", "loss.cu", "mapper_mlp.cu", "adam_collective.cu", "microbench.cu"]
+           "composite.cu", "loss.cu", "mapper_mlp.cu", "adam_collective.cu", "microbench.cu", "microbench_mma.cu"]
 EXTRA = {"march.cu": ["-fmad=false"]}
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("NVCC_EXTRA", "").split()

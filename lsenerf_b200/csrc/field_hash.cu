@@ -150,10 +150,22 @@ __global__ void __launch_bounds__(HT) scatter_samples_kernel(LseFieldParams P, f
                 if (__popc(heads) <= 20) {          // coarse level: few cells per warp -> one reduction per run
                     const int last = run_last_lane(heads, lane);
                     const int max_len = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last - lane + 1));
+                    // all 16 products in ONE shuffle tree: the loop control, the run predicate and the convergence check are paid once
+                    // per step instead of once per value and step (the kernel is issue bound: 76 % issue slots busy, r2e capture)
+                    float v[16];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float a = run_sum(w[c] * gl[0], lane, last, max_len), b = run_sum(w[c] * gl[1], lane, last, max_len);
-                        if (head && live) red_add2(dtl + 2 * (size_t)hc.idx[c], a, b);
+                    for (int c = 0; c < 8; ++c) { v[2 * c] = w[c] * gl[0]; v[2 * c + 1] = w[c] * gl[1]; }
+                    for (int s = 1; s < max_len; s <<= 1) {
+                        const bool in_run = lane + s <= last;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const float t = __shfl_down_sync(0xffffffffu, v[k], s);
+                            if (in_run) v[k] += t;
+                        }
+                    }
+                    if (head && live) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) red_add2(dtl + 2 * (size_t)hc.idx[c], v[2 * c], v[2 * c + 1]);
                     }
                 }
                 else if (live) {

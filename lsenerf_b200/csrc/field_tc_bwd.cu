@@ -321,6 +321,357 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) color_bwd_tc_kernel(LseFieldPa
 }
 
 // ===============================================================================================================================
+// colour MLP backward, 8 compute warps per tile
+// ===============================================================================================================================
+// What the 4-warp kernel above is bound by (profiles/r2e_*, ncu source view): neither the tensor pipe (18 % active) nor shared
+// memory (31 %).  Its 128 compute threads each carry a 64-channel row through tcgen05.ld -> bias / ReLU / mask -> hi/lo split ->
+// 16 STS.128 per phase at one dependent instruction every ~8 clocks (2 warps per scheduler), 26 k of the 44 k clocks a tile takes;
+// the other 18 k are spent waiting on MMA chains that both tiles of the CTA issue at the same moment (they contend for the pipe and
+// so fall into lock step).  Small MMAs cost what their operands cost to fetch from shared memory: 48 clocks at N = 64, 39 at N = 16
+// (tools/mma_chain.py), dependent or not, i.e. 6.2 k clocks per tile.  This kernel therefore
+//   * puts 8 warps on a tile: warp w reads TMEM lanes 32 (w % 4) .. + 31 -- the quarter its position in the CTA allows -- and the
+//     column half w / 4, so a thread owns 32 channels of its sample's row (half the dependent chain, half the registers, twice the
+//     warps per scheduler);
+//   * takes the weight gradients off the critical path: per phase the data-gradient MMAs are issued first and committed to `done`
+//     (what the compute warps wait for), the weight-gradient MMAs follow and commit to `free`, which a compute thread only waits for
+//     before it overwrites an operand buffer -- after its tcgen05.ld, masking and splitting;
+//   * builds the descriptors of a phase when the phase is issued (the 4-warp kernel keeps ~130 precomputed descriptors in registers
+//     and local memory and reloads 40 of them per phase on the critical path);
+//   * recomputes the input row X0 for the last phase BEFORE waiting for the previous one, so its loads hide behind the MMAs.
+constexpr int TG = 256;                           // compute threads per tile (8 warps)
+constexpr int NTG = 2;                            // tiles in flight per CTA
+constexpr int BWD8_THREADS = TG * NTG + 32 * NTG;
+
+struct Handshake8 {
+    uint64_t *full, *done, *free_;
+    uint32_t fph, dph, rph;
+    __device__ __forceinline__ void wait_staged() { mbar_wait(full, fph); fph ^= 1; tc_fence_after(); }      // issuing warp
+    __device__ __forceinline__ void publish() { signal_staged(full); }                                       // compute thread
+    __device__ __forceinline__ void wait_done() { mbar_wait(done, dph); dph ^= 1; tc_fence_after(); }
+    __device__ __forceinline__ void wait_free() { mbar_wait(free_, rph); rph ^= 1; }
+};
+
+// a value the compiler cannot hoist out of the tile loop: descriptors derived from it are built where they are used
+__device__ __forceinline__ uint32_t opaque(uint32_t v)
+{
+    uint32_t r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+// channels [32 hf, 32 hf + 32) of the colour-MLP input row (field_common.cuh color_input); channel 63 is the ones column of the
+// transposed weight gradient (W3's padded column 63 is zero)
+__device__ __forceinline__ void color_input_half(const LseFieldParams &P, const float dir[3], const float *__restrict__ h16row,
+                                                 const int32_t *__restrict__ app_id, int32_t ray, int hf, float (&x)[32])
+{
+    const float *erow = nullptr;
+    if (!(P.emb_mode == 2 || P.emb == nullptr)) {
+        int64_t er = 0;
+        if (P.emb_mode == 0 && app_id) {
+            er = app_id[ray];
+            er = er < 0 ? 0 : (er >= P.emb_rows ? P.emb_rows - 1 : er);
+        }
+        erow = P.emb + er * NE;
+    }
+    if (hf == 0) {
+        float v[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v[j] = P.sh_shifted ? (dir[j] + 1.0f) / 2.0f : dir[j];
+        float sh[16];
+        sh16(v, sh);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = sh[j];
+        const float4 *h4 = reinterpret_cast<const float4 *>(h16row);
+        float hv[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float4 t = h4[q]; hv[4 * q] = t.x; hv[4 * q + 1] = t.y; hv[4 * q + 2] = t.z; hv[4 * q + 3] = t.w; }
+#pragma unroll
+        for (int j = 0; j < 15; ++j) x[16 + j] = hv[1 + j];
+        x[31] = erow ? __ldg(erow) : 0.0f;
+    } else {
+        if (erow) {
+            const float4 *e4 = reinterpret_cast<const float4 *>(erow);
+            float e[NE];
+#pragma unroll
+            for (int q = 0; q < NE / 4; ++q) { const float4 t = __ldg(e4 + q); e[4 * q] = t.x; e[4 * q + 1] = t.y; e[4 * q + 2] = t.z; e[4 * q + 3] = t.w; }
+#pragma unroll
+            for (int j = 0; j < 31; ++j) x[j] = e[1 + j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 31; ++j) x[j] = 0.0f;
+        }
+        x[31] = 1.0f;
+    }
+}
+
+// this thread's 32 channels (panels 4 hf .. 4 hf + 3) of row `row` -> hi / lo pieces
+template <int PIECE>
+__device__ __forceinline__ void stage_half(bf16_t *buf, int row, int hf, const float (&v)[32])
+{
+#pragma unroll
+    for (int pn = 0; pn < 4; ++pn) stage8(buf, PIECE, 4 * hf + pn, row, &v[8 * pn]);
+}
+
+__global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc8_kernel(LseFieldParams P, LseFieldGrads G, const float *__restrict__ directions,
+                                                                        const int32_t *__restrict__ ray_idx,
+                                                                        const int32_t *__restrict__ app_id, int64_t S_cap,
+                                                                        const int32_t *__restrict__ n_dev, const float *__restrict__ h16,
+                                                                        const float *__restrict__ d_rgb, float *__restrict__ d_h16,
+                                                                        float *__restrict__ d_directions, int dir_per_sample)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    using L = ColorBwdSm;
+    static_assert(NTG == NWGB, "the shared-memory carve-up is per tile in flight");
+    bf16_t *sm16 = reinterpret_cast<bf16_t *>(smem_raw);
+    float *smf = reinterpret_cast<float *>(smem_raw);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smf + L::FEND);        // [tile group][full, done, free]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 3 * NTG);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_issuer = tid >= TG * NTG;
+    const int tg = is_issuer ? warp - 8 * NTG : tid / TG;                // tile group
+    const int q = warp & 3, hf = (warp >> 2) & 1;                        // TMEM lane quarter, column half
+    const int row = 32 * q + lane;
+
+    stage_weights(sm16 + L::W3, P.W3, 64, 63, 64, 64, tid, BWD8_THREADS);
+    stage_weights(sm16 + L::W4, P.W4, 64, 64, 64, 64, tid, BWD8_THREADS);
+    stage_weights(sm16 + L::W5, P.W5, 3, 64, 16, 64, tid, BWD8_THREADS);
+    if (tid < 64) { smf[L::B3 + tid] = P.b3[tid]; smf[L::B4 + tid] = P.b4[tid]; }
+    if (tid < 16) smf[L::B5 + tid] = tid < 3 ? P.b5[tid] : 0.0f;
+    if (!is_issuer && hf == 0) {
+        init_bias_panel<64>(sm16 + tg * L::WG + L::P, row);
+        init_bias_panel<64>(sm16 + tg * L::WG + L::Q, row);
+    }
+    if (tid < NTG) { mbar_init(mbar + 3 * tid, TG); mbar_init(mbar + 3 * tid + 1, 1); mbar_init(mbar + 3 * tid + 2, 1); }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_mbar_init();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot + tg * TMEM_WG;
+    Handshake8 hs{mbar + 3 * tg, mbar + 3 * tg + 1, mbar + 3 * tg + 2, 0u, 0u, 0u};
+
+    const int64_t S = live_count(n_dev, S_cap);
+    const int64_t n_tiles = (S + WGT - 1) / WGT;
+    const int64_t tile0 = (int64_t)blockIdx.x * NTG + tg, tstep = (int64_t)gridDim.x * NTG;
+    bf16_t *bP = sm16 + tg * L::WG + L::P, *bQ = bP + BUF64, *bR = bQ + BUF64;
+
+    if (is_issuer) {
+        // =================================================== MMA-issuing warp ===================================================
+        const uint32_t tg_u = uniform((uint32_t)tg), sm_u = uniform(smem_u32(sm16));
+        const uint32_t tm = uniform(*tmem_slot) + tg_u * TMEM_WG;
+        uint32_t accum = 0;
+        for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
+#pragma unroll 1
+            for (int ph = 0; ph < 6; ++ph) {
+                hs.wait_staged();
+                if (elect_one()) {
+                    const uint32_t base = opaque(sm_u);
+                    const uint32_t aP = base + 2u * (tg_u * L::WG + L::P), aQ = aP + 2u * BUF64, aR = aQ + 2u * BUF64;
+                    const uint32_t w3 = base + 2u * L::W3, w4 = base + 2u * L::W4, w5 = base + 2u * L::W5;
+                    switch (ph) {
+                    case 0: issue_fwd(tm + ccol::SCR, aP, PIECE64, w3, 64, 64); mma_commit(hs.done); break;          // P = X0
+                    case 1: issue_fwd(tm + ccol::SCR, aQ, PIECE64, w4, 64, 64); mma_commit(hs.done); break;          // Q = H1
+                    case 2: issue_fwd(tm + ccol::SCR, aP, PIECE64, w5, 16, 64); mma_commit(hs.done); break;          // P = H2
+                    case 3:                                                                                          // R = dO
+                        issue_dgrad(tm + ccol::SCR, aR, PIECE16, w5, 16, 64);                // dH2 = dO W5
+                        mma_commit(hs.done);
+                        issue_wgradT(tm + ccol::A5, aP, PIECE64, aR, PIECE16, 16, accum);    // [H2|1]^T dO
+                        break;
+                    case 4:                                                                                          // P = dA2
+                        issue_dgrad(tm + ccol::SCR, aP, PIECE64, w4, 64, 64);                // dH1 = dA2 W4
+                        mma_commit(hs.done);
+                        issue_wgradT(tm + ccol::A4, aQ, PIECE64, aP, PIECE64, 64, accum);    // [H1|1]^T dA2
+                        break;
+                    default:                                                                                         // Q = dA1, P = X0
+                        issue_dgrad(tm + ccol::SCR, aQ, PIECE64, w3, 64, 64);                // dX0 = dA1 W3
+                        mma_commit(hs.done);
+                        issue_wgradT(tm + ccol::A3, aP, PIECE64, aQ, PIECE64, 64, accum);    // X0^T dA1 (row 63 = db3)
+                        break;
+                    }
+                    mma_commit(hs.free_);          // every MMA of this phase has read its operands
+                }
+                __syncwarp();
+            }
+            accum = 1;
+        }
+    } else {
+        // =================================================== compute warps =======================================================
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * hf);     // this warp's lanes, this half's columns
+        const float *b3 = smf + L::B3 + 32 * hf, *b4 = smf + L::B4 + 32 * hf;
+        bool any = false;
+        for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
+            any = true;
+            const int64_t i = tile * WGT + row;
+            const bool live = i < S;
+            int32_t ray = 0;
+            float dir[3] = {0.0f, 0.0f, 1.0f};
+            float x[32];
+            if (live) {
+                ray = ray_idx ? ray_idx[i] : (int32_t)i;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dir[j] = directions[3 * (int64_t)ray + j];
+                color_input_half(P, dir, h16 + 16 * i, app_id, ray, hf, x);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+            }
+            stage_half<PIECE64>(bP, row, hf, x);                // ph0: P = X0 (P, Q are free: end of the previous tile)
+            hs.publish();
+            // activation patterns: the forward pass's own (3xTF32) when it stored them, else from this bf16x2 recomputation
+            const bool fwd_masks = P.relu_mask_color != nullptr && live;
+            const uint32_t *mk32 = reinterpret_cast<const uint32_t *>(P.relu_mask_color);
+            uint32_t m1 = fwd_masks ? mk32[4 * i + hf] : 0u, m2 = fwd_masks ? mk32[4 * i + 2 + hf] : 0u;
+            float g3[3] = {0.0f, 0.0f, 0.0f};
+            if (live && hf == 0) { g3[0] = d_rgb[3 * i]; g3[1] = d_rgb[3 * i + 1]; g3[2] = d_rgb[3 * i + 2]; }
+            hs.wait_done();
+            read_row<32>(trow, ccol::SCR, x);
+            hs.wait_free();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                x[j] = fmaxf(x[j] + b3[j], 0.0f);
+                if (fwd_masks) x[j] = ((m1 >> j) & 1u) ? x[j] : 0.0f;
+                else m1 |= (uint32_t)(x[j] > 0.0f) << j;
+            }
+            stage_half<PIECE64>(bQ, row, hf, x);                // ph1: Q = H1
+            hs.publish();
+            hs.wait_done();
+            read_row<32>(trow, ccol::SCR, x);
+            hs.wait_free();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                x[j] = fmaxf(x[j] + b4[j], 0.0f);
+                if (fwd_masks) x[j] = ((m2 >> j) & 1u) ? x[j] : 0.0f;
+                else m2 |= (uint32_t)(x[j] > 0.0f) << j;
+            }
+            stage_half<PIECE64>(bP, row, hf, x);                // ph2: P = H2
+            hs.publish();
+            hs.wait_done();
+            if (hf == 0) {                                      // warp-uniform: the output layer is 16 columns wide
+                float dO[16];
+                read_row<16>(trow, ccol::SCR, dO);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float g = 0.0f;
+                    if (c < 3 && live) {
+                        const float sg = sigmoidf(dO[c] + smf[L::B5 + c]);
+                        g = g3[c] * sg * (1.0f - sg);
+                    }
+                    dO[c] = g;
+                }
+                hs.wait_free();
+                stage_row<16, PIECE16>(bR, row, dO);            // ph3: R = dO
+            } else {
+                hs.wait_free();
+            }
+            hs.publish();
+            hs.wait_done();
+            read_row<32>(trow, ccol::SCR, x);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = ((m2 >> j) & 1u) ? x[j] : 0.0f;        // dA2
+            hs.wait_free();                                     // the weight gradient of layer 5 has read P = H2
+            stage_half<PIECE64>(bP, row, hf, x);                // ph4: P = dA2
+            hs.publish();
+            float x0[32];                                       // the input row again, loaded behind the MMAs of phase 4
+            if (live) {
+                color_input_half(P, dir, h16 + 16 * i, app_id, ray, hf, x0);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x0[j] = 0.0f;
+            }
+            hs.wait_done();
+            read_row<32>(trow, ccol::SCR, x);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = ((m1 >> j) & 1u) ? x[j] : 0.0f;        // dA1
+            hs.wait_free();                                     // the weight gradient of layer 4 has read Q = H1 and P = dA2
+            stage_half<PIECE64>(bQ, row, hf, x);                // ph5: Q = dA1, P = X0
+            stage_half<PIECE64>(bP, row, hf, x0);
+            hs.publish();
+            hs.wait_done();
+            read_row<32>(trow, ccol::SCR, x);                   // this half of dX0
+            if (live) {
+                if (hf == 0) {
+                    if (d_directions) {
+                        float v[3], g16[16], dv[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) v[j] = P.sh_shifted ? (dir[j] + 1.0f) / 2.0f : dir[j];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) g16[j] = x[j];
+                        sh16_bwd(v, g16, dv);
+                        const float sc = P.sh_shifted ? 0.5f : 1.0f;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            if (dir_per_sample) d_directions[3 * i + j] = dv[j] * sc;     // [S,3], reduced per ray by lse_field_density_bwd_rays
+                            else red_add(d_directions + 3 * (int64_t)ray + j, dv[j] * sc);
+                        }
+                    }
+                    float4 *dst = reinterpret_cast<float4 *>(d_h16 + 16 * i);
+                    dst[0] = make_float4(0.0f, x[16], x[17], x[18]);
+                    dst[1] = make_float4(x[19], x[20], x[21], x[22]);
+                    dst[2] = make_float4(x[23], x[24], x[25], x[26]);
+                    dst[3] = make_float4(x[27], x[28], x[29], x[30]);
+                }
+                if (G.d_emb && P.emb_mode == 0 && app_id) {
+                    int64_t er = app_id[ray];
+                    er = er < 0 ? 0 : (er >= P.emb_rows ? P.emb_rows - 1 : er);
+                    if (hf == 0) {
+                        red_add(G.d_emb + er * NE, x[31]);                                 // embedding channel 0 = input channel 31
+                    } else {                                                               // channels 32 + j = embedding channel j + 1
+                        red_add(G.d_emb + er * NE + 1, x[0]);
+#pragma unroll
+                        for (int e = 2; e < NE; e += 2) red_add2(G.d_emb + er * NE + e, x[e - 1], x[e]);
+                    }
+                }
+            }
+            hs.wait_free();                                     // the weight gradient of layer 3 has read P and Q: the next tile may stage
+        }
+        // ---- flush this tile group's TMEM-resident accumulators: lane k of the accumulator = input channel k -------------------------
+        const bool shared_emb = G.d_emb && (P.emb_mode == 1 || (P.emb_mode == 0 && !app_id));
+        float *s_db3 = smf + L::DB3 + tg * 64;
+        if (any && q <= 2) {        // whole warps (tcgen05.ld is warp-collective); lanes 0..64 carry data
+            float v[32];
+            read_row<32>(trow, ccol::A3, v);
+            if (row < 63) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) red_add(G.dW3 + (32 * hf + j) * 63 + row, v[j]);
+            } else if (row == 63) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { red_add(G.db3 + 32 * hf + j, v[j]); s_db3[32 * hf + j] = v[j]; }
+            }
+            read_row<32>(trow, ccol::A4, v);
+            if (row < 64) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) red_add(G.dW4 + (32 * hf + j) * 64 + row, v[j]);
+            } else if (row == 64) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) red_add(G.db4 + 32 * hf + j, v[j]);
+            }
+            if (hf == 0) {
+                float b[16];
+                read_row<16>(trow, ccol::A5, b);
+                if (row < 64) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) red_add(G.dW5 + j * 64 + row, b[j]);
+                } else if (row == 64) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) red_add(G.db5 + j, b[j]);
+                }
+            }
+        }
+        tc_fence_before();
+        bar_sync(1 + tg, TG);
+        if (any && shared_emb && hf == 0 && row < NE) {        // d_emb[e] = sum_j db3[j] W3[j][31+e]
+            float acc = 0.0f;
+            for (int j = 0; j < 64; ++j) acc = fmaf(s_db3[j], P.W3[j * 63 + 31 + row], acc);
+            red_add(G.d_emb + row, acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
+// ===============================================================================================================================
 // density (base) MLP backward: feat [S,32], dout [S,16] -> dfeat [S,32], dW1, db1, dW2, db2
 // ===============================================================================================================================
 struct DensityBwdSm {
@@ -476,6 +827,168 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) density_mlp_bwd_tc_kernel(LseF
     if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
+// The same kernel with 8 compute warps per tile, the data gradients committed ahead of the weight gradients and descriptors built at
+// issue time (see color_bwd_tc8_kernel): a thread owns 16 of the 32 feature channels and 32 of the 64 hidden channels of its sample.
+__global__ void __launch_bounds__(BWD8_THREADS, 1) density_mlp_bwd_tc8_kernel(LseFieldParams P, LseFieldGrads G, int64_t S_cap,
+                                                                              const int32_t *__restrict__ n_dev,
+                                                                              const float *__restrict__ feat,
+                                                                              const float *__restrict__ dout0,
+                                                                              const float *__restrict__ d_h16,
+                                                                              float *__restrict__ dfeat)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    using L = DensityBwdSm;
+    bf16_t *sm16 = reinterpret_cast<bf16_t *>(smem_raw);
+    float *smf = reinterpret_cast<float *>(smem_raw);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smf + L::FEND);        // [tile group][full, done, free]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 3 * NTG);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_issuer = tid >= TG * NTG;
+    const int tg = is_issuer ? warp - 8 * NTG : tid / TG;
+    const int q = warp & 3, hf = (warp >> 2) & 1;
+    const int row = 32 * q + lane;
+
+    stage_weights(sm16 + L::W1, P.W1, 64, 32, 64, 32, tid, BWD8_THREADS);
+    stage_weights(sm16 + L::W2, P.W2, 16, 64, 16, 64, tid, BWD8_THREADS);
+    for (int i = tid; i < 4096; i += BWD8_THREADS) sm16[L::PAD + i] = 0;
+    if (tid < 64) smf[L::B1 + tid] = P.b1[tid];
+    if (!is_issuer && hf == 0) {
+        init_bias_panel<32>(sm16 + tg * L::WG + L::P, row);
+        init_bias_panel<64>(sm16 + tg * L::WG + L::Q, row);
+    }
+    if (tid < NTG) { mbar_init(mbar + 3 * tid, TG); mbar_init(mbar + 3 * tid + 1, 1); mbar_init(mbar + 3 * tid + 2, 1); }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_mbar_init();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot + tg * TMEM_WG;
+    Handshake8 hs{mbar + 3 * tg, mbar + 3 * tg + 1, mbar + 3 * tg + 2, 0u, 0u, 0u};
+
+    const int64_t S = live_count(n_dev, S_cap);
+    const int64_t n_tiles = (S + WGT - 1) / WGT;
+    const int64_t tile0 = (int64_t)blockIdx.x * NTG + tg, tstep = (int64_t)gridDim.x * NTG;
+    bf16_t *bP = sm16 + tg * L::WG + L::P, *bQ = bP + BUF32, *bR = bQ + BUF64;
+
+    if (is_issuer) {
+        const uint32_t tg_u = uniform((uint32_t)tg), sm_u = uniform(smem_u32(sm16));
+        const uint32_t tm = uniform(*tmem_slot) + tg_u * TMEM_WG;
+        uint32_t accum = 0;
+        for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
+#pragma unroll 1
+            for (int ph = 0; ph < 3; ++ph) {
+                hs.wait_staged();
+                if (elect_one()) {
+                    const uint32_t base = opaque(sm_u);
+                    const uint32_t aP = base + 2u * (tg_u * L::WG + L::P), aQ = aP + 2u * BUF32, aR = aQ + 2u * BUF64;
+                    const uint32_t w1 = base + 2u * L::W1, w2 = base + 2u * L::W2;
+                    if (ph == 0) {                                                           // P = feat, R = dOut
+                        issue_fwd(tm + cden::SCR, aP, PIECE32, w1, 64, 32);
+                        mma_commit(hs.done);
+                    } else if (ph == 1) {                                                    // Q = H1
+                        issue_dgrad(tm + cden::SCR, aR, PIECE16, w2, 16, 64);                // dH1 = dOut W2
+                        mma_commit(hs.done);
+                        issue_wgradT(tm + cden::A2, aQ, PIECE64, aR, PIECE16, 16, accum);    // [H1|1]^T dOut
+                    } else {                                                                 // Q = dA1
+                        issue_dgrad(tm + cden::SCR, aQ, PIECE64, w1, 64, 32);                // dfeat = dA1 W1
+                        mma_commit(hs.done);
+                        issue_wgradT(tm + cden::A1, aP, PIECE32, aQ, PIECE64, 64, accum);    // [feat|1]^T dA1
+                    }
+                    mma_commit(hs.free_);
+                }
+                __syncwarp();
+            }
+            accum = 1;
+        }
+    } else {
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        const float *b1 = smf + L::B1 + 32 * hf;
+        bool any = false;
+        for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
+            any = true;
+            const int64_t i = tile * WGT + row;
+            const bool live = i < S;
+            float f[16], dout[8];
+            if (live) {
+                const float2 *f2 = reinterpret_cast<const float2 *>(feat) + i;      // planes [16][S_cap] of float2 (field_hash.cu)
+#pragma unroll
+                for (int l = 0; l < 8; ++l) { const float2 t = __ldg(f2 + (size_t)(8 * hf + l) * S_cap); f[2 * l] = t.x; f[2 * l + 1] = t.y; }
+                const float4 *gh = reinterpret_cast<const float4 *>(d_h16 + 16 * i + 8 * hf);
+#pragma unroll
+                for (int qq = 0; qq < 2; ++qq) {
+                    const float4 t = d_h16 ? gh[qq] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    dout[4 * qq] = t.x; dout[4 * qq + 1] = t.y; dout[4 * qq + 2] = t.z; dout[4 * qq + 3] = t.w;
+                }
+                if (hf == 0) dout[0] = dout0[i];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dout[j] = 0.0f;
+            }
+#pragma unroll
+            for (int pn = 0; pn < 2; ++pn) stage8(bP, PIECE32, 2 * hf + pn, row, &f[8 * pn]);     // ph0: P = feat, R = dOut
+            stage8(bR, PIECE16, hf, row, dout);
+            hs.publish();
+            const bool fwd_masks = P.relu_mask_density != nullptr && live;
+            uint32_t m1 = fwd_masks ? reinterpret_cast<const uint32_t *>(P.relu_mask_density)[2 * i + hf] : 0u;
+            float h[32];
+            hs.wait_done();
+            read_row<32>(tlane + 32 * hf, cden::SCR, h);
+            hs.wait_free();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                h[j] = fmaxf(h[j] + b1[j], 0.0f);
+                if (fwd_masks) h[j] = ((m1 >> j) & 1u) ? h[j] : 0.0f;
+                else m1 |= (uint32_t)(h[j] > 0.0f) << j;
+            }
+            stage_half<PIECE64>(bQ, row, hf, h);                // ph1: Q = H1
+            hs.publish();
+            hs.wait_done();
+            read_row<32>(tlane + 32 * hf, cden::SCR, h);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = ((m1 >> j) & 1u) ? h[j] : 0.0f;        // dA1
+            hs.wait_free();                                     // the weight gradient of layer 2 has read Q = H1 and R
+            stage_half<PIECE64>(bQ, row, hf, h);                // ph2: Q = dA1
+            hs.publish();
+            hs.wait_done();
+            read_row<16>(tlane + 16 * hf, cden::SCR, f);        // this half of dfeat
+            if (live) {
+                float2 *o2 = reinterpret_cast<float2 *>(dfeat) + i;
+#pragma unroll
+                for (int l = 0; l < 8; ++l) o2[(size_t)(8 * hf + l) * S_cap] = make_float2(f[2 * l], f[2 * l + 1]);
+            }
+            hs.wait_free();                                     // the weight gradient of layer 1 has read P and Q
+        }
+        if (any && q <= 2) {        // whole warps (tcgen05.ld is warp-collective); lanes 0..64 carry data
+            float v[32];
+            read_row<32>(tlane + 32 * hf, cden::A1, v);
+            if (row < 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) red_add(G.dW1 + (32 * hf + j) * 32 + row, v[j]);
+            } else if (row == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) red_add(G.db1 + 32 * hf + j, v[j]);
+            }
+            if (hf == 0) {
+                float b[16];
+                read_row<16>(tlane, cden::A2, b);
+                if (row < 64) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) red_add(G.dW2 + j * 64 + row, b[j]);
+                } else if (row == 64) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) red_add(G.db2 + j, b[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
 static int bwd_grid(int64_t S_cap)
 {
     int64_t tiles = (S_cap + WGT - 1) / WGT;
@@ -490,6 +1003,14 @@ int tc_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *d
 {
     constexpr size_t smem_bytes = ColorBwdSm::BYTES;
     static_assert(smem_bytes <= 232448, "colour backward exceeds the 227 KiB shared-memory limit");
+    static const int eight = env_int("LSE_COLOR_BWD8", 1);
+    if (eight) {       // 8 compute warps per tile; LSE_COLOR_BWD8=0 selects the 4-warp kernel
+        static bool attr8 = false;
+        if (!attr8) { cudaFuncSetAttribute(color_bwd_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr8 = true; }
+        color_bwd_tc8_kernel<<<bwd_grid(S_cap), BWD8_THREADS, smem_bytes, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb,
+                                                                                 d_h16, d_directions, dir_per_sample);
+        return check_launch("lse_field_color_bwd[tc8]");
+    }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(color_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
     color_bwd_tc_kernel<<<bwd_grid(S_cap), BWD_THREADS, smem_bytes, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb,
@@ -502,6 +1023,13 @@ int tc_density_mlp_bwd(const LseFieldParams &P, const LseFieldGrads &G, int64_t 
 {
     constexpr size_t smem_bytes = DensityBwdSm::BYTES;
     static_assert(smem_bytes <= 232448, "density backward exceeds the 227 KiB shared-memory limit");
+    static const int eight = env_int("LSE_DENSITY_BWD8", 1);
+    if (eight) {       // 8 compute warps per tile; LSE_DENSITY_BWD8=0 selects the 4-warp kernel
+        static bool attr8 = false;
+        if (!attr8) { cudaFuncSetAttribute(density_mlp_bwd_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr8 = true; }
+        density_mlp_bwd_tc8_kernel<<<bwd_grid(S_cap), BWD8_THREADS, smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_h16, dfeat);
+        return check_launch("lse_field_density_mlp_bwd[tc8]");
+    }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(density_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
     density_mlp_bwd_tc_kernel<<<bwd_grid(S_cap), BWD_THREADS, smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_h16, dfeat);

@@ -160,13 +160,24 @@ __device__ __forceinline__ void stage4(float *hi_buf, float *lo_buf, int rows, i
 __device__ __forceinline__ void stage_weights(float *hi_buf, float *lo_buf, const float *__restrict__ W, int n_real, int k_real,
                                               int N, int K, int tid, int nthreads)
 {
-    for (int i = tid; i < N * K; i += nthreads) {
-        const int n = i / K, k = i % K;
-        const float w = (n < n_real && k < k_real) ? W[n * k_real + k] : 0.0f;
-        float h, l;
-        split_tf32(w, h, l);
-        const int off = ((k >> 2) * N + n) * 4 + (k & 3);
-        hi_buf[off] = h; lo_buf[off] = l;
+    // batches of 8 independent loads (one trip to L2 per batch instead of one per element: the prologue is serial time on every SM)
+    for (int i0 = tid; i0 < N * K; i0 += 8 * nthreads) {
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * nthreads, n = i / K, k = i % K;
+            w[u] = (i < N * K && n < n_real && k < k_real) ? __ldg(W + n * k_real + k) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * nthreads, n = i / K, k = i % K;
+            if (i < N * K) {
+                float h, l;
+                split_tf32(w[u], h, l);
+                const int off = ((k >> 2) * N + n) * 4 + (k & 3);
+                hi_buf[off] = h; lo_buf[off] = l;
+            }
+        }
     }
 }
 
