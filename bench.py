@@ -625,6 +625,36 @@ def run_b200(args):
     # ---- render rays/sec: BASELINE configs[4], one 1280x720 eval frame with camera optimisation, rows sharded over ranks -------
     render = render_leg(pipe, scene, dev, rank, world, max_over_ranks, barrier)
 
+    # ---- the arithmetic-identical figure: the same steps on the fp32 CUDA-core MLP kernels (no tensor cores, no bf16-split backward), one
+    #      block from the state the timed blocks left behind (N = 1 only; it goes last because it keeps training the shared weights) ----
+    simt = None
+    if world == 1 and pipe._model.config.use_tensor_cores and not args.no_simt_leg:
+        m = pipe._model
+        m.config.use_tensor_cores = m.field.use_tensor_cores = False
+        try:
+            gss = GraphedStep(pipe, opt, 1, use_graph=not args.no_graph, device_store=args.device_store)
+            gss.capture(start_step=gs.step_no)
+            gss.step_no = 16 * ((gs.step_no + 15) // 16) + 1
+            stg = [gss.stage.pack_to_device(*sample_batches()) for _ in range(K + W)]
+            for i in range(W):
+                gss.step(packed_dev=stg[i])
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(K):
+                gss.step(packed_dev=stg[W + i])
+            gss.flush()
+            s1.record()
+            torch.cuda.synchronize()
+            ms_simt = s0.elapsed_time(s1)
+            simt = {"value": BUDGET * K / (ms_simt * 1e-3), "unit": "rays/s", "ms_per_step": ms_simt / K,
+                    "note": f"one block of {K} steps with use_tensor_cores = False: every MLP contraction in fp32 FMA on the CUDA cores"}
+            del gss, stg
+        except Exception as e:                                 # a reported extra, never a reason to lose the bench line
+            simt = {"error": f"{type(e).__name__}: {e}"}
+        m.config.use_tensor_cores = m.field.use_tensor_cores = True
+        pipe.defer_table_scatter = True                        # what GraphedStep set for the tensor-core path
+
     if rank == 0:
         per_call = {k: v[1] / v[0] for k, v in prof.items()}
         per_step = {k: v[1] / n_prof for k, v in prof.items()}
@@ -652,7 +682,7 @@ def run_b200(args):
                       "lse_field_density_bwd_table": ["scatter_samples_kernel"],
                       "lse_field_density_bwd_finish": ["density_mlp_bwd_tc_kernel", "scatter_samples_kernel"],
                       "lse_field_color_fwd": ["color_fwd_tc_kernel"], "lse_field_color_bwd": ["color_bwd_tc_kernel"],
-                      "lse_march_single": ["march_runs_kernel", "march_steps_kernel"]}
+                      "lse_march_single": ["march_runs_kernel", "march_classify_kernel", "march_pack_kernel"]}
         hbm, tf_peak, which = load_peaks()
         # ncu DRAM traffic per launch: only from a capture of THIS code (the file records the git head it was taken at)
         head = git_head()
@@ -733,6 +763,8 @@ def run_b200(args):
                 "clocks": clk, "roofline": roof(roof_k), "rooflines": rooflines, "gather_peaks": gpk, "render": render,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
                 "git_head": head}
+        if simt is not None:
+            line["value_simt_fp32"] = simt
         if coll is not None:
             line["collective_check"] = coll
         if barrier_wait is not None:
@@ -779,6 +811,7 @@ def main():
     ap.add_argument("--simt", action="store_true", help="fp32 CUDA-core MLP kernels instead of tcgen05 (the arithmetic-identical figure)")
     ap.add_argument("--no-overlap", action="store_true", help="optimizer / table scatter on the main stream (A/B of the software pipeline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-simt-leg", action="store_true", help="skip the extra block on the fp32 CUDA-core MLP kernels (value_simt_fp32)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--device-store", action="store_true", help="image / event stacks resident in HBM, pixel gather on the device (SURVEY 8f-2)")
     ap.add_argument("--profiler-window", action="store_true", help="cudaProfilerStart/Stop around the first timed block (for ncu --profile-from-start off)")

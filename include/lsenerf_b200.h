@@ -216,6 +216,10 @@ typedef struct {
        sample); relu_mask_color: uint64 [S,2] (the two hidden layers of the colour MLP).  Ignored by the fp32 CUDA-core kernels, whose
        backward repeats the forward arithmetic exactly. */
     unsigned long long *relu_mask_density; unsigned long long *relu_mask_color;
+    /* rgb [S,3] as lse_field_color_fwd wrote it (optional, may be NULL; read by the tensor-core lse_field_color_bwd only): the
+       derivative of the output sigmoid is rgb (1 - rgb), so the backward pass need not recompute the output layer -- one MMA phase
+       and one tensor-memory round trip less per tile.  NULL: recomputed. */
+    const float *rgb_fwd;
 } LseFieldParams;
 
 typedef struct {

@@ -1,12 +1,17 @@
 // field_tc_bwd.cu -- backward of the LSEField MLPs on tcgen05 tensor cores (BF16x2 split operands, tc_bf16.cuh).
 //
-// CTA = 2 compute warpgroups (128 threads each, thread = sample = TMEM lane) + 2 MMA-issuing warps (one per warpgroup),
-// one CTA per SM, persistent over 128-sample tiles.  A warpgroup owns its operand buffers, TMEM columns and a pair of
-// mbarriers: the compute threads stage a layer's operands (fp32 -> hi/lo bf16 panels, STS.128), fence to the async proxy and
-// arrive on `full`; the issuing warp waits, one lane issues the tcgen05.mma chain of that phase and commits to `done`; the
-// compute threads wait on `done` and read their accumulator row back with tcgen05.ld.  While one warpgroup waits on the
-// tensor core the other one stages, so the tensor pipe and the CUDA cores overlap; nobody but the issuing lane spends
-// time building descriptors.
+// CTA = 2 tiles in flight x 8 compute warps + 2 MMA-issuing warps (576 threads), one CTA per SM, persistent over 128-sample tiles.
+// Compute warp w of a tile reads the TMEM lanes 32 (w % 4) .. + 31 -- the quarter its position in the CTA allows -- and the column
+// half w / 4: a thread owns one sample and 32 of the 64 channels of its row.  A tile owns its operand buffers, 256 TMEM columns and
+// three mbarriers:
+//   full : the compute threads have staged a phase's operands (fp32 -> hi/lo bf16 panels, STS.128, fence to the async proxy)
+//   done : the issuing warp's elected lane has issued the phase's CRITICAL MMAs (forward recompute / data gradient) and committed
+//          them; the compute threads wait on it and read their accumulator rows back with tcgen05.ld
+//   free : the phase's weight-gradient MMAs, issued behind the commit to `done`, have read their operands too; a compute thread waits
+//          on it only right before it overwrites an operand buffer, i.e. after its tcgen05.ld, masking and hi/lo split
+// so the weight gradients (two thirds of the MMAs of a backward phase) run under the compute warps' work instead of in front of it.
+// Descriptors are built when a phase is issued (an opaque base per phase keeps the compiler from hoisting ~130 descriptors into
+// registers and local memory).
 //
 // Every contraction is a tcgen05.mma on ONE shared-memory layout (see tc_bf16.cuh):
 //   forward / recompute  D[s,j]  = sum_k X[s,k] W[j,k]        A = X  K-major,   B = W  K-major
@@ -15,10 +20,18 @@
 //                                                             B = dY MN-major, K = the tile's 128 samples
 // The transposed weight gradient keeps the accumulator N = out-channels (16..64 TMEM columns) and makes the bias gradient
 // the extra accumulator row fed by the ones panel.  Accumulators live in TMEM for the whole kernel and are flushed with one
-// atomicAdd per entry per warpgroup at the end.  The shared appearance-embedding gradient is W3[:,31:63]^T db3 (the
+// atomicAdd per entry per tile slot at the end.  The shared appearance-embedding gradient is W3[:,31:63]^T db3 (the
 // embedding enters every sample identically), evaluated at the flush from the accumulated bias gradient.
 //
-// Kernels:  color_bwd_tc   : h16, d_rgb -> d_h16, d_directions, dW3..5, db3..5, d_emb            (6 MMA phases per tile)
+// What bounds these kernels (profiles/r2e_*, r2h_* ncu source views; tools/mma_chain.py): a small tcgen05.mma costs what its
+// operands cost to fetch from shared memory -- 48 clocks at N = 64, 39 at N = 16, dependent on its predecessor or not -- i.e. 6.2 k
+// clocks of tensor pipe per colour tile, and two tiles in flight (80 KB of operand panels each) are what shared memory holds, so
+// the length of a tile's dependent chain decides: tcgen05.ld -> bias / ReLU / mask -> hi/lo split -> STS -> fence -> MMAs, 6 times
+// per colour tile (5 when the forward pass's rgb is available).  The first version of this file ran that chain on 4 warps per
+// tile with every MMA of a phase in front of the next tcgen05.ld: 44 k clocks per tile pair, tensor pipe 18 % active, 0.288 ms;
+// this one: 0.21 ms.
+//
+// Kernels:  color_bwd_tc   : h16, d_rgb -> d_h16, d_directions, dW3..5, db3..5, d_emb            (6 | 5 MMA phases per tile)
 //           density_mlp_bwd: feat, dout -> dfeat, dW1, db1, dW2, db2                              (3 MMA phases per tile)
 // The hash-grid halves of the density backward (re-encode of the kept samples, table scatter, position gradients) are
 // full-occupancy CUDA-core kernels in field_hash.cu; lse_field_density_bwd_ws chains the three.
@@ -33,10 +46,11 @@ namespace lse {
 
 using namespace tcb;
 
-constexpr int WGT = 128;                          // threads per compute warpgroup == samples per tile
-constexpr int NWGB = 2;                           // compute warpgroups per CTA
-constexpr int BWD_THREADS = WGT * NWGB + 32 * NWGB;
-constexpr int TMEM_WG = 256;                      // TMEM columns per warpgroup
+constexpr int WGT = 128;                          // samples per tile == TMEM lanes
+constexpr int TG = 256;                           // compute threads per tile (8 warps: lane quarter x column half)
+constexpr int NTG = 2;                            // tiles in flight per CTA
+constexpr int BWD8_THREADS = TG * NTG + 32 * NTG; // + one MMA-issuing warp per tile
+constexpr int TMEM_WG = 256;                      // TMEM columns per tile
 
 constexpr int PIECE64 = piece_elems(64), PIECE32 = piece_elems(32), PIECE16 = 2 * PANEL;
 constexpr int BUF64 = 2 * PIECE64, BUF32 = 2 * PIECE32, BUF16 = 2 * PIECE16;
@@ -64,284 +78,18 @@ __device__ __forceinline__ void issue_wgradT(uint32_t d, uint32_t x_addr, int x_
     mma3(d, idesc_bf16(N, true, true), acc, desc_mn(x_addr, 128), x_piece * 2, kstep_mn, desc_mn(g_addr, 128), g_piece * 2, kstep_mn, 8);
 }
 
-struct Handshake {
-    uint64_t *full, *done;
-    uint32_t fph, dph;
-    // issuing warp: wait until the compute warpgroup has staged the next phase
-    __device__ __forceinline__ void wait_staged() { mbar_wait(full, fph); fph ^= 1; tc_fence_after(); }
-    // compute thread: publish operands, then wait for the MMAs of this phase
-    __device__ __forceinline__ void publish_and_wait()
-    {
-        signal_staged(full);
-        mbar_wait(done, dph); dph ^= 1;
-        tc_fence_after();
-    }
+struct ColorBwdSm {   // bf16-element offsets
+    static constexpr int P = 0, Q = P + BUF64, R = Q + BUF64, WG = R + BUF16;      // per tile in flight
+    static constexpr int W3 = NTG * WG, W4 = W3 + 2 * 64 * 64, W5 = W4 + 2 * 64 * 64, END16 = W5 + 2 * 16 * 64;
+    static constexpr int F32 = END16 / 2;                                           // float offset of the fp32 block
+    static constexpr int B3 = F32, B4 = B3 + 64, B5 = B4 + 64, DB3 = B5 + 16, FEND = DB3 + NTG * 64;
+    static constexpr size_t BYTES = (size_t)FEND * 4 + 128;      // + mbarriers [tile][full, done, free] and the TMEM base
 };
+namespace ccol { constexpr int SCR = 0, A3 = 64, A4 = 128, A5 = 192; }
 
 // ===============================================================================================================================
 // colour MLP backward
 // ===============================================================================================================================
-struct ColorBwdSm {   // bf16-element offsets
-    static constexpr int P = 0, Q = P + BUF64, R = Q + BUF64, WG = R + BUF16;      // per warpgroup
-    static constexpr int W3 = NWGB * WG, W4 = W3 + 2 * 64 * 64, W5 = W4 + 2 * 64 * 64, END16 = W5 + 2 * 16 * 64;
-    static constexpr int F32 = END16 / 2;                                           // float offset of the fp32 block
-    static constexpr int B3 = F32, B4 = B3 + 64, B5 = B4 + 64, DB3 = B5 + 16, FEND = DB3 + NWGB * 64;
-    static constexpr size_t BYTES = (size_t)FEND * 4 + 64;
-};
-namespace ccol { constexpr int SCR = 0, A3 = 64, A4 = 128, A5 = 192; }
-
-__global__ void __launch_bounds__(BWD_THREADS, 1) color_bwd_tc_kernel(LseFieldParams P, LseFieldGrads G, const float *__restrict__ directions,
-                                                                      const int32_t *__restrict__ ray_idx,
-                                                                      const int32_t *__restrict__ app_id, int64_t S_cap,
-                                                                      const int32_t *__restrict__ n_dev, const float *__restrict__ h16,
-                                                                      const float *__restrict__ d_rgb, float *__restrict__ d_h16,
-                                                                      float *__restrict__ d_directions, int dir_per_sample)
-{
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    using L = ColorBwdSm;
-    bf16_t *sm16 = reinterpret_cast<bf16_t *>(smem_raw);
-    float *smf = reinterpret_cast<float *>(smem_raw);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smf + L::FEND);        // [wg][full, done]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 2 * NWGB);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_issuer = tid >= WGT * NWGB;
-    const int wg = is_issuer ? warp - 4 * NWGB : tid / WGT;
-    const int row = tid % WGT;
-
-    stage_weights(sm16 + L::W3, P.W3, 64, 63, 64, 64, tid, BWD_THREADS);
-    stage_weights(sm16 + L::W4, P.W4, 64, 64, 64, 64, tid, BWD_THREADS);
-    stage_weights(sm16 + L::W5, P.W5, 3, 64, 16, 64, tid, BWD_THREADS);
-    if (tid < 64) { smf[L::B3 + tid] = P.b3[tid]; smf[L::B4 + tid] = P.b4[tid]; }
-    if (tid < 16) smf[L::B5 + tid] = tid < 3 ? P.b5[tid] : 0.0f;
-    if (!is_issuer) {
-        init_bias_panel<64>(sm16 + wg * L::WG + L::P, row);
-        init_bias_panel<64>(sm16 + wg * L::WG + L::Q, row);
-    }
-    if (tid < NWGB) { mbar_init(mbar + 2 * tid, WGT); mbar_init(mbar + 2 * tid + 1, 1); }
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
-    fence_mbar_init();
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot + wg * TMEM_WG;
-    Handshake hs{mbar + 2 * wg, mbar + 2 * wg + 1, 0u, 0u};
-
-    const int64_t S = live_count(n_dev, S_cap);
-    const int64_t n_tiles = (S + WGT - 1) / WGT;
-    const int64_t tile0 = (int64_t)blockIdx.x * NWGB + wg, tstep = (int64_t)gridDim.x * NWGB;
-    bf16_t *bP = sm16 + wg * L::WG + L::P, *bQ = bP + BUF64, *bR = bQ + BUF64;
-
-    if (is_issuer) {
-        // =================================================== MMA-issuing warp ===================================================
-        // warp-uniform operands (uniform registers feed tcgen05.mma directly instead of a per-instruction broadcast loop)
-        const uint32_t wg_u = uniform((uint32_t)wg), sm_u = uniform(smem_u32(sm16));
-        const uint32_t tmem = uniform(*tmem_slot) + wg_u * TMEM_WG;
-        const uint32_t aP = sm_u + 2u * (wg_u * L::WG + L::P), aQ = aP + 2u * BUF64, aR = aQ + 2u * BUF64;
-        const uint32_t w3 = sm_u + 2u * L::W3, w4 = sm_u + 2u * L::W4, w5 = sm_u + 2u * L::W5;
-        uint32_t accum = 0;
-        for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
-            hs.wait_staged();                                                        // ph0: P = X0
-            if (elect_one()) { issue_fwd(tmem + ccol::SCR, aP, PIECE64, w3, 64, 64); mma_commit(hs.done); }
-            __syncwarp();
-            hs.wait_staged();                                                        // ph1: Q = H1
-            if (elect_one()) { issue_fwd(tmem + ccol::SCR, aQ, PIECE64, w4, 64, 64); mma_commit(hs.done); }
-            __syncwarp();
-            hs.wait_staged();                                                        // ph2: P = H2
-            if (elect_one()) { issue_fwd(tmem + ccol::SCR, aP, PIECE64, w5, 16, 64); mma_commit(hs.done); }
-            __syncwarp();
-            hs.wait_staged();                                                        // ph3: R = dO
-            if (elect_one()) {
-                issue_wgradT(tmem + ccol::A5, aP, PIECE64, aR, PIECE16, 16, accum);  // [H2|1]^T dO
-                issue_dgrad(tmem + ccol::SCR, aR, PIECE16, w5, 16, 64);              // dH2 = dO W5
-                mma_commit(hs.done);
-            }
-            __syncwarp();
-            hs.wait_staged();                                                        // ph4: P = dA2
-            if (elect_one()) {
-                issue_wgradT(tmem + ccol::A4, aQ, PIECE64, aP, PIECE64, 64, accum);  // [H1|1]^T dA2
-                issue_dgrad(tmem + ccol::SCR, aP, PIECE64, w4, 64, 64);              // dH1 = dA2 W4
-                mma_commit(hs.done);
-            }
-            __syncwarp();
-            hs.wait_staged();                                                        // ph5: Q = dA1, P = X0 (x[63] = 1)
-            if (elect_one()) {
-                issue_wgradT(tmem + ccol::A3, aP, PIECE64, aQ, PIECE64, 64, accum);  // X0^T dA1 (row 63 = db3)
-                issue_dgrad(tmem + ccol::SCR, aQ, PIECE64, w3, 64, 64);              // dX0 = dA1 W3
-                mma_commit(hs.done);
-            }
-            __syncwarp();
-            accum = 1;
-        }
-    } else {
-        // =================================================== compute warpgroup ==================================================
-        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        bool any = false;
-        for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
-            any = true;
-            const int64_t i = tile * WGT + row;
-            const bool live = i < S;
-            int32_t ray = 0;
-            float dir[3] = {0.0f, 0.0f, 1.0f};
-            float x[NI];
-            if (live) {
-                ray = ray_idx ? ray_idx[i] : (int32_t)i;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) dir[j] = directions[3 * (int64_t)ray + j];
-                color_input(P, dir, h16 + 16 * i, app_id, ray, x);
-                x[63] = 1.0f;                                   // W3's padded column 63 is zero; row 63 of dW3^T = db3
-            } else {
-#pragma unroll
-                for (int j = 0; j < NI; ++j) x[j] = 0.0f;
-            }
-            stage_row<NI, PIECE64>(bP, row, x);                 // ph0
-            hs.publish_and_wait();
-            read_row<NH>(trow, ccol::SCR, x);
-            // activation patterns: the forward pass's own (3xTF32) when it stored them, else from this bf16x2 recomputation
-            const bool fwd_masks = P.relu_mask_color != nullptr && live;
-            uint64_t m1 = fwd_masks ? P.relu_mask_color[2 * i] : 0ull, m2 = fwd_masks ? P.relu_mask_color[2 * i + 1] : 0ull;
-#pragma unroll
-            for (int j = 0; j < NH; ++j) {
-                x[j] = fmaxf(x[j] + smf[L::B3 + j], 0.0f);
-                if (fwd_masks) x[j] = ((m1 >> j) & 1ull) ? x[j] : 0.0f;
-                else m1 |= (uint64_t)(x[j] > 0.0f) << j;
-            }
-            stage_row<NH, PIECE64>(bQ, row, x);                 // ph1: Q = H1
-            hs.publish_and_wait();
-            read_row<NH>(trow, ccol::SCR, x);
-#pragma unroll
-            for (int j = 0; j < NH; ++j) {
-                x[j] = fmaxf(x[j] + smf[L::B4 + j], 0.0f);
-                if (fwd_masks) x[j] = ((m2 >> j) & 1ull) ? x[j] : 0.0f;
-                else m2 |= (uint64_t)(x[j] > 0.0f) << j;
-            }
-            stage_row<NH, PIECE64>(bP, row, x);                 // ph2: P = H2
-            hs.publish_and_wait();
-            float dO[16];
-            read_row<16>(trow, ccol::SCR, dO);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                float g = 0.0f;
-                if (c < 3 && live) {
-                    const float s = sigmoidf(dO[c] + smf[L::B5 + c]);
-                    g = d_rgb[3 * i + c] * s * (1.0f - s);
-                }
-                dO[c] = g;
-            }
-            stage_row<16, PIECE16>(bR, row, dO);                // ph3
-            hs.publish_and_wait();
-            read_row<NH>(trow, ccol::SCR, x);
-#pragma unroll
-            for (int j = 0; j < NH; ++j) x[j] = ((m2 >> j) & 1ull) ? x[j] : 0.0f;      // dA2
-            stage_row<NH, PIECE64>(bP, row, x);                 // ph4: P = dA2 (H2 consumed)
-            hs.publish_and_wait();
-            read_row<NH>(trow, ccol::SCR, x);
-#pragma unroll
-            for (int j = 0; j < NH; ++j) x[j] = ((m1 >> j) & 1ull) ? x[j] : 0.0f;      // dA1
-            stage_row<NH, PIECE64>(bQ, row, x);                 // ph5: Q = dA1 (H1 consumed), P = X0 again
-            if (live) {
-                color_input(P, dir, h16 + 16 * i, app_id, ray, x);
-                x[63] = 1.0f;
-            } else {
-#pragma unroll
-                for (int j = 0; j < NI; ++j) x[j] = 0.0f;
-            }
-            stage_row<NI, PIECE64>(bP, row, x);
-            hs.publish_and_wait();
-            read_row<NI>(trow, ccol::SCR, x);                   // dX0
-            if (live) {
-                if (d_directions) {
-                    float v[3], g16[16], dv[3];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) v[j] = P.sh_shifted ? (dir[j] + 1.0f) / 2.0f : dir[j];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) g16[j] = x[j];
-                    sh16_bwd(v, g16, dv);
-                    const float sc = P.sh_shifted ? 0.5f : 1.0f;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                    if (dir_per_sample) d_directions[3 * i + j] = dv[j] * sc;         // [S,3], reduced per ray by ray_grad_packed_kernel
-                    else red_add(d_directions + 3 * (int64_t)ray + j, dv[j] * sc);
-                }
-                }
-                float4 *dst = reinterpret_cast<float4 *>(d_h16 + 16 * i);
-                dst[0] = make_float4(0.0f, x[16], x[17], x[18]);
-                dst[1] = make_float4(x[19], x[20], x[21], x[22]);
-                dst[2] = make_float4(x[23], x[24], x[25], x[26]);
-                dst[3] = make_float4(x[27], x[28], x[29], x[30]);
-                if (G.d_emb && P.emb_mode == 0 && app_id) {
-                    int64_t er = app_id[ray];
-                    er = er < 0 ? 0 : (er >= P.emb_rows ? P.emb_rows - 1 : er);
-#pragma unroll
-                    for (int e = 0; e < NE; e += 2) red_add2(G.d_emb + er * NE + e, x[31 + e], x[32 + e]);
-                }
-            }
-        }
-        // ---- flush this warpgroup's TMEM-resident accumulators: lane k of the accumulator = input channel k -----------------------
-        const bool shared_emb = G.d_emb && (P.emb_mode == 1 || (P.emb_mode == 0 && !app_id));
-        float *s_db3 = smf + L::DB3 + wg * 64;
-        if (any && (row >> 5) <= 2) {   // warps 0..2 (tcgen05.ld is warp-collective); rows 0..64 carry data
-            float v[64], b[16];
-            read_row<64>(trow, ccol::A3, v);
-            if (row < 63) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) red_add(G.dW3 + j * 63 + row, v[j]);
-            } else if (row == 63) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) { red_add(G.db3 + j, v[j]); s_db3[j] = v[j]; }
-            }
-            read_row<64>(trow, ccol::A4, v);
-            if (row < 64) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) red_add(G.dW4 + j * 64 + row, v[j]);
-            } else if (row == 64) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) red_add(G.db4 + j, v[j]);
-            }
-            read_row<16>(trow, ccol::A5, b);
-            if (row < 64) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) red_add(G.dW5 + j * 64 + row, b[j]);
-            } else if (row == 64) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) red_add(G.db5 + j, b[j]);
-            }
-        }
-        tc_fence_before();
-        bar_sync(1 + wg, WGT);
-        if (any && shared_emb && row < NE) {        // d_emb[e] = sum_j db3[j] W3[j][31+e]
-            float acc = 0.0f;
-            for (int j = 0; j < 64; ++j) acc = fmaf(s_db3[j], P.W3[j * 63 + 31 + row], acc);
-            red_add(G.d_emb + row, acc);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(*tmem_slot, 512);
-}
-
-// ===============================================================================================================================
-// colour MLP backward, 8 compute warps per tile
-// ===============================================================================================================================
-// What the 4-warp kernel above is bound by (profiles/r2e_*, ncu source view): neither the tensor pipe (18 % active) nor shared
-// memory (31 %).  Its 128 compute threads each carry a 64-channel row through tcgen05.ld -> bias / ReLU / mask -> hi/lo split ->
-// 16 STS.128 per phase at one dependent instruction every ~8 clocks (2 warps per scheduler), 26 k of the 44 k clocks a tile takes;
-// the other 18 k are spent waiting on MMA chains that both tiles of the CTA issue at the same moment (they contend for the pipe and
-// so fall into lock step).  Small MMAs cost what their operands cost to fetch from shared memory: 48 clocks at N = 64, 39 at N = 16
-// (tools/mma_chain.py), dependent or not, i.e. 6.2 k clocks per tile.  This kernel therefore
-//   * puts 8 warps on a tile: warp w reads TMEM lanes 32 (w % 4) .. + 31 -- the quarter its position in the CTA allows -- and the
-//     column half w / 4, so a thread owns 32 channels of its sample's row (half the dependent chain, half the registers, twice the
-//     warps per scheduler);
-//   * takes the weight gradients off the critical path: per phase the data-gradient MMAs are issued first and committed to `done`
-//     (what the compute warps wait for), the weight-gradient MMAs follow and commit to `free`, which a compute thread only waits for
-//     before it overwrites an operand buffer -- after its tcgen05.ld, masking and splitting;
-//   * builds the descriptors of a phase when the phase is issued (the 4-warp kernel keeps ~130 precomputed descriptors in registers
-//     and local memory and reloads 40 of them per phase on the critical path);
-//   * recomputes the input row X0 for the last phase BEFORE waiting for the previous one, so its loads hide behind the MMAs.
-constexpr int TG = 256;                           // compute threads per tile (8 warps)
-constexpr int NTG = 2;                            // tiles in flight per CTA
-constexpr int BWD8_THREADS = TG * NTG + 32 * NTG;
-
 struct Handshake8 {
     uint64_t *full, *done, *free_;
     uint32_t fph, dph, rph;
@@ -412,7 +160,7 @@ __device__ __forceinline__ void stage_half(bf16_t *buf, int row, int hf, const f
     for (int pn = 0; pn < 4; ++pn) stage8(buf, PIECE, 4 * hf + pn, row, &v[8 * pn]);
 }
 
-__global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc8_kernel(LseFieldParams P, LseFieldGrads G, const float *__restrict__ directions,
+__global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldParams P, LseFieldGrads G, const float *__restrict__ directions,
                                                                         const int32_t *__restrict__ ray_idx,
                                                                         const int32_t *__restrict__ app_id, int64_t S_cap,
                                                                         const int32_t *__restrict__ n_dev, const float *__restrict__ h16,
@@ -421,7 +169,6 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc8_kernel(LseField
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     using L = ColorBwdSm;
-    static_assert(NTG == NWGB, "the shared-memory carve-up is per tile in flight");
     bf16_t *sm16 = reinterpret_cast<bf16_t *>(smem_raw);
     float *smf = reinterpret_cast<float *>(smem_raw);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smf + L::FEND);        // [tile group][full, done, free]
@@ -461,9 +208,11 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc8_kernel(LseField
         const uint32_t tg_u = uniform((uint32_t)tg), sm_u = uniform(smem_u32(sm16));
         const uint32_t tm = uniform(*tmem_slot) + tg_u * TMEM_WG;
         uint32_t accum = 0;
+        const bool skip_out = P.rgb_fwd != nullptr;
         for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
 #pragma unroll 1
             for (int ph = 0; ph < 6; ++ph) {
+                if (ph == 2 && skip_out) continue;     // the output layer is not recomputed: H2 and dO are staged together for phase 3
                 hs.wait_staged();
                 if (elect_one()) {
                     const uint32_t base = opaque(sm_u);
@@ -545,24 +294,38 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc8_kernel(LseField
                 else m2 |= (uint32_t)(x[j] > 0.0f) << j;
             }
             stage_half<PIECE64>(bP, row, hf, x);                // ph2: P = H2
-            hs.publish();
-            hs.wait_done();
-            if (hf == 0) {                                      // warp-uniform: the output layer is 16 columns wide
-                float dO[16];
-                read_row<16>(trow, ccol::SCR, dO);
+            if (P.rgb_fwd != nullptr) {
+                // sigmoid' = rgb (1 - rgb) from the forward pass's output: no output-layer phase; dO joins H2 in phase 3
+                if (hf == 0) {
+                    float dO[16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float g = 0.0f;
-                    if (c < 3 && live) {
-                        const float sg = sigmoidf(dO[c] + smf[L::B5 + c]);
-                        g = g3[c] * sg * (1.0f - sg);
+                    for (int c = 0; c < 16; ++c) dO[c] = 0.0f;
+                    if (live) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { const float sg = P.rgb_fwd[3 * i + c]; dO[c] = g3[c] * sg * (1.0f - sg); }
                     }
-                    dO[c] = g;
+                    stage_row<16, PIECE16>(bR, row, dO);        // R was last read by the previous tile's phase 3
                 }
-                hs.wait_free();
-                stage_row<16, PIECE16>(bR, row, dO);            // ph3: R = dO
             } else {
-                hs.wait_free();
+                hs.publish();
+                hs.wait_done();
+                if (hf == 0) {                                  // warp-uniform: the output layer is 16 columns wide
+                    float dO[16];
+                    read_row<16>(trow, ccol::SCR, dO);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        float g = 0.0f;
+                        if (c < 3 && live) {
+                            const float sg = sigmoidf(dO[c] + smf[L::B5 + c]);
+                            g = g3[c] * sg * (1.0f - sg);
+                        }
+                        dO[c] = g;
+                    }
+                    hs.wait_free();
+                    stage_row<16, PIECE16>(bR, row, dO);        // ph3: R = dO
+                } else {
+                    hs.wait_free();
+                }
             }
             hs.publish();
             hs.wait_done();
@@ -672,164 +435,23 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc8_kernel(LseField
 }
 
 // ===============================================================================================================================
-// density (base) MLP backward: feat [S,32], dout [S,16] -> dfeat [S,32], dW1, db1, dW2, db2
+// density (base) MLP backward: feat [S,32], dout [S,16] -> dfeat [S,32], dW1, db1, dW2, db2 (3 MMA phases per tile; a thread owns 16 of
+// the 32 feature channels and 32 of the 64 hidden channels of its sample)
 // ===============================================================================================================================
+// NT tiles in flight: 64 KB of operand panels and 144 TMEM columns per tile, so THREE tiles fit next to the weights (the colour kernel's
+// 80 KB tiles stop at two) -- 24 compute warps + 3 issuing warps at 72 registers
+template <int NT>
 struct DensityBwdSm {
     static constexpr int P = 0, Q = P + BUF32, R = Q + BUF64, WG = R + BUF16;
-    static constexpr int W1 = NWGB * WG, W2 = W1 + 2 * 64 * 32, PAD = W2 + 2 * 16 * 64, END16 = PAD + 4096;
+    static constexpr int W1 = NT * WG, W2 = W1 + 2 * 64 * 32, PAD = W2 + 2 * 16 * 64, END16 = PAD + 4096;
     static constexpr int F32 = END16 / 2;
     static constexpr int B1 = F32, FEND = B1 + 64;
-    static constexpr size_t BYTES = (size_t)FEND * 4 + 64;
+    static constexpr size_t BYTES = (size_t)FEND * 4 + 128;      // + mbarriers [tile][full, done, free] and the TMEM base
 };
 namespace cden { constexpr int SCR = 0, A1 = 64, A2 = 128; }
 
-__global__ void __launch_bounds__(BWD_THREADS, 1) density_mlp_bwd_tc_kernel(LseFieldParams P, LseFieldGrads G, int64_t S_cap,
-                                                                            const int32_t *__restrict__ n_dev,
-                                                                            const float *__restrict__ feat,
-                                                                            const float *__restrict__ dout0,
-                                                                            const float *__restrict__ d_h16,
-                                                                            float *__restrict__ dfeat)
-{
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    using L = DensityBwdSm;
-    bf16_t *sm16 = reinterpret_cast<bf16_t *>(smem_raw);
-    float *smf = reinterpret_cast<float *>(smem_raw);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smf + L::FEND);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 2 * NWGB);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_issuer = tid >= WGT * NWGB;
-    const int wg = is_issuer ? warp - 4 * NWGB : tid / WGT;
-    const int row = tid % WGT;
-
-    stage_weights(sm16 + L::W1, P.W1, 64, 32, 64, 32, tid, BWD_THREADS);
-    stage_weights(sm16 + L::W2, P.W2, 16, 64, 16, 64, tid, BWD_THREADS);
-    for (int i = tid; i < 4096; i += BWD_THREADS) sm16[L::PAD + i] = 0;
-    if (tid < 64) smf[L::B1 + tid] = P.b1[tid];
-    if (!is_issuer) {
-        init_bias_panel<32>(sm16 + wg * L::WG + L::P, row);
-        init_bias_panel<64>(sm16 + wg * L::WG + L::Q, row);
-    }
-    if (tid < NWGB) { mbar_init(mbar + 2 * tid, WGT); mbar_init(mbar + 2 * tid + 1, 1); }
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
-    fence_mbar_init();
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot + wg * TMEM_WG;
-    Handshake hs{mbar + 2 * wg, mbar + 2 * wg + 1, 0u, 0u};
-
-    const int64_t S = live_count(n_dev, S_cap);
-    const int64_t n_tiles = (S + WGT - 1) / WGT;
-    const int64_t tile0 = (int64_t)blockIdx.x * NWGB + wg, tstep = (int64_t)gridDim.x * NWGB;
-    bf16_t *bP = sm16 + wg * L::WG + L::P, *bQ = bP + BUF32, *bR = bQ + BUF64;
-
-    if (is_issuer) {
-        const uint32_t wg_u = uniform((uint32_t)wg), sm_u = uniform(smem_u32(sm16));
-        const uint32_t tmem = uniform(*tmem_slot) + wg_u * TMEM_WG;
-        const uint32_t aP = sm_u + 2u * (wg_u * L::WG + L::P), aQ = aP + 2u * BUF32, aR = aQ + 2u * BUF64;
-        const uint32_t w1 = sm_u + 2u * L::W1, w2 = sm_u + 2u * L::W2;
-        uint32_t accum = 0;
-        for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
-            hs.wait_staged();                                                        // ph0: P = feat, R = dOut
-            if (elect_one()) { issue_fwd(tmem + cden::SCR, aP, PIECE32, w1, 64, 32); mma_commit(hs.done); }
-            __syncwarp();
-            hs.wait_staged();                                                        // ph1: Q = H1
-            if (elect_one()) {
-                issue_wgradT(tmem + cden::A2, aQ, PIECE64, aR, PIECE16, 16, accum);  // [H1|1]^T dOut
-                issue_dgrad(tmem + cden::SCR, aR, PIECE16, w2, 16, 64);              // dH1 = dOut W2
-                mma_commit(hs.done);
-            }
-            __syncwarp();
-            hs.wait_staged();                                                        // ph2: Q = dA1
-            if (elect_one()) {
-                issue_wgradT(tmem + cden::A1, aP, PIECE32, aQ, PIECE64, 64, accum);  // [feat|1]^T dA1
-                issue_dgrad(tmem + cden::SCR, aQ, PIECE64, w1, 64, 32);              // dfeat = dA1 W1
-                mma_commit(hs.done);
-            }
-            __syncwarp();
-            accum = 1;
-        }
-    } else {
-        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        bool any = false;
-        for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
-            any = true;
-            const int64_t i = tile * WGT + row;
-            const bool live = i < S;
-            float f[NF], dout[NO];
-            if (live) {
-                const float2 *f2 = reinterpret_cast<const float2 *>(feat) + i;      // planes [16][S_cap] of float2 (field_hash.cu)
-#pragma unroll
-                for (int l = 0; l < NL; ++l) { const float2 t = __ldg(f2 + (size_t)l * S_cap); f[2 * l] = t.x; f[2 * l + 1] = t.y; }
-                const float4 *gh = reinterpret_cast<const float4 *>(d_h16 + 16 * i);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 t = d_h16 ? gh[q] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    dout[4 * q] = t.x; dout[4 * q + 1] = t.y; dout[4 * q + 2] = t.z; dout[4 * q + 3] = t.w;
-                }
-                dout[0] = dout0[i];
-            } else {
-#pragma unroll
-                for (int j = 0; j < NF; ++j) f[j] = 0.0f;
-#pragma unroll
-                for (int j = 0; j < NO; ++j) dout[j] = 0.0f;
-            }
-            stage_row<NF, PIECE32>(bP, row, f);                 // ph0
-            stage_row<NO, PIECE16>(bR, row, dout);
-            hs.publish_and_wait();
-            float h[NH];
-            read_row<NH>(trow, cden::SCR, h);
-            const bool fwd_masks = P.relu_mask_density != nullptr && live;
-            uint64_t m1 = fwd_masks ? P.relu_mask_density[i] : 0ull;
-#pragma unroll
-            for (int j = 0; j < NH; ++j) {
-                h[j] = fmaxf(h[j] + smf[L::B1 + j], 0.0f);
-                if (fwd_masks) h[j] = ((m1 >> j) & 1ull) ? h[j] : 0.0f;
-                else m1 |= (uint64_t)(h[j] > 0.0f) << j;
-            }
-            stage_row<NH, PIECE64>(bQ, row, h);                 // ph1: Q = H1
-            hs.publish_and_wait();
-            read_row<NH>(trow, cden::SCR, h);
-#pragma unroll
-            for (int j = 0; j < NH; ++j) h[j] = ((m1 >> j) & 1ull) ? h[j] : 0.0f;       // dA1
-            stage_row<NH, PIECE64>(bQ, row, h);                 // ph2: Q = dA1 (H1 consumed)
-            hs.publish_and_wait();
-            read_row<NF>(trow, cden::SCR, f);                   // dfeat
-            if (live) {
-                float2 *o2 = reinterpret_cast<float2 *>(dfeat) + i;
-#pragma unroll
-                for (int l = 0; l < NL; ++l) o2[(size_t)l * S_cap] = make_float2(f[2 * l], f[2 * l + 1]);
-            }
-        }
-        if (any && (row >> 5) <= 2) {   // warps 0..2 (tcgen05.ld is warp-collective); rows 0..64 carry data
-            float v[64], b[16];
-            read_row<64>(trow, cden::A1, v);
-            if (row < 32) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) red_add(G.dW1 + j * 32 + row, v[j]);
-            } else if (row == 32) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) red_add(G.db1 + j, v[j]);
-            }
-            read_row<16>(trow, cden::A2, b);
-            if (row < 64) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) red_add(G.dW2 + j * 64 + row, b[j]);
-            } else if (row == 64) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) red_add(G.db2 + j, b[j]);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(*tmem_slot, 512);
-}
-
-// The same kernel with 8 compute warps per tile, the data gradients committed ahead of the weight gradients and descriptors built at
-// issue time (see color_bwd_tc8_kernel): a thread owns 16 of the 32 feature channels and 32 of the 64 hidden channels of its sample.
-__global__ void __launch_bounds__(BWD8_THREADS, 1) density_mlp_bwd_tc8_kernel(LseFieldParams P, LseFieldGrads G, int64_t S_cap,
+template <int NT>
+__global__ void __launch_bounds__(NT *(TG + 32), 1) density_mlp_bwd_tc_kernel(LseFieldParams P, LseFieldGrads G, int64_t S_cap,
                                                                               const int32_t *__restrict__ n_dev,
                                                                               const float *__restrict__ feat,
                                                                               const float *__restrict__ dout0,
@@ -837,43 +459,45 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) density_mlp_bwd_tc8_kernel(Ls
                                                                               float *__restrict__ dfeat)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    using L = DensityBwdSm;
+    using L = DensityBwdSm<NT>;
+    constexpr int NTHREADS = NT * (TG + 32);
+    constexpr int TM = NT == 2 ? 256 : 160;        // TMEM columns per tile (144 used)
     bf16_t *sm16 = reinterpret_cast<bf16_t *>(smem_raw);
     float *smf = reinterpret_cast<float *>(smem_raw);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smf + L::FEND);        // [tile group][full, done, free]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 3 * NTG);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 3 * NT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_issuer = tid >= TG * NTG;
-    const int tg = is_issuer ? warp - 8 * NTG : tid / TG;
+    const bool is_issuer = tid >= TG * NT;
+    const int tg = is_issuer ? warp - 8 * NT : tid / TG;
     const int q = warp & 3, hf = (warp >> 2) & 1;
     const int row = 32 * q + lane;
 
-    stage_weights(sm16 + L::W1, P.W1, 64, 32, 64, 32, tid, BWD8_THREADS);
-    stage_weights(sm16 + L::W2, P.W2, 16, 64, 16, 64, tid, BWD8_THREADS);
-    for (int i = tid; i < 4096; i += BWD8_THREADS) sm16[L::PAD + i] = 0;
+    stage_weights(sm16 + L::W1, P.W1, 64, 32, 64, 32, tid, NTHREADS);
+    stage_weights(sm16 + L::W2, P.W2, 16, 64, 16, 64, tid, NTHREADS);
+    for (int i = tid; i < 4096; i += NTHREADS) sm16[L::PAD + i] = 0;
     if (tid < 64) smf[L::B1 + tid] = P.b1[tid];
     if (!is_issuer && hf == 0) {
         init_bias_panel<32>(sm16 + tg * L::WG + L::P, row);
         init_bias_panel<64>(sm16 + tg * L::WG + L::Q, row);
     }
-    if (tid < NTG) { mbar_init(mbar + 3 * tid, TG); mbar_init(mbar + 3 * tid + 1, 1); mbar_init(mbar + 3 * tid + 2, 1); }
+    if (tid < NT) { mbar_init(mbar + 3 * tid, TG); mbar_init(mbar + 3 * tid + 1, 1); mbar_init(mbar + 3 * tid + 2, 1); }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     fence_mbar_init();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot + tg * TMEM_WG;
+    const uint32_t tmem = *tmem_slot + tg * TM;
     Handshake8 hs{mbar + 3 * tg, mbar + 3 * tg + 1, mbar + 3 * tg + 2, 0u, 0u, 0u};
 
     const int64_t S = live_count(n_dev, S_cap);
     const int64_t n_tiles = (S + WGT - 1) / WGT;
-    const int64_t tile0 = (int64_t)blockIdx.x * NTG + tg, tstep = (int64_t)gridDim.x * NTG;
+    const int64_t tile0 = (int64_t)blockIdx.x * NT + tg, tstep = (int64_t)gridDim.x * NT;
     bf16_t *bP = sm16 + tg * L::WG + L::P, *bQ = bP + BUF32, *bR = bQ + BUF64;
 
     if (is_issuer) {
         const uint32_t tg_u = uniform((uint32_t)tg), sm_u = uniform(smem_u32(sm16));
-        const uint32_t tm = uniform(*tmem_slot) + tg_u * TMEM_WG;
+        const uint32_t tm = uniform(*tmem_slot) + tg_u * TM;
         uint32_t accum = 0;
         for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
 #pragma unroll 1
@@ -989,10 +613,10 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) density_mlp_bwd_tc8_kernel(Ls
     if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
-static int bwd_grid(int64_t S_cap)
+static int bwd_grid(int64_t S_cap, int nt = NTG)
 {
     int64_t tiles = (S_cap + WGT - 1) / WGT;
-    int64_t ctas = (tiles + NWGB - 1) / NWGB;
+    int64_t ctas = (tiles + nt - 1) / nt;
     if (ctas < 1) ctas = 1;
     return (int)(ctas < kNumSMs ? ctas : kNumSMs);
 }
@@ -1003,17 +627,9 @@ int tc_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *d
 {
     constexpr size_t smem_bytes = ColorBwdSm::BYTES;
     static_assert(smem_bytes <= 232448, "colour backward exceeds the 227 KiB shared-memory limit");
-    static const int eight = env_int("LSE_COLOR_BWD8", 1);
-    if (eight) {       // 8 compute warps per tile; LSE_COLOR_BWD8=0 selects the 4-warp kernel
-        static bool attr8 = false;
-        if (!attr8) { cudaFuncSetAttribute(color_bwd_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr8 = true; }
-        color_bwd_tc8_kernel<<<bwd_grid(S_cap), BWD8_THREADS, smem_bytes, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb,
-                                                                                 d_h16, d_directions, dir_per_sample);
-        return check_launch("lse_field_color_bwd[tc8]");
-    }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(color_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
-    color_bwd_tc_kernel<<<bwd_grid(S_cap), BWD_THREADS, smem_bytes, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb,
+    color_bwd_tc_kernel<<<bwd_grid(S_cap), BWD8_THREADS, smem_bytes, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb,
                                                                           d_h16, d_directions, dir_per_sample);
     return check_launch("lse_field_color_bwd[tc]");
 }
@@ -1021,18 +637,19 @@ int tc_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *d
 int tc_density_mlp_bwd(const LseFieldParams &P, const LseFieldGrads &G, int64_t S_cap, const int32_t *n_dev, const float *feat,
                        const float *dout0, const float *d_h16, float *dfeat, cudaStream_t st)
 {
-    constexpr size_t smem_bytes = DensityBwdSm::BYTES;
-    static_assert(smem_bytes <= 232448, "density backward exceeds the 227 KiB shared-memory limit");
-    static const int eight = env_int("LSE_DENSITY_BWD8", 1);
-    if (eight) {       // 8 compute warps per tile; LSE_DENSITY_BWD8=0 selects the 4-warp kernel
-        static bool attr8 = false;
-        if (!attr8) { cudaFuncSetAttribute(density_mlp_bwd_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr8 = true; }
-        density_mlp_bwd_tc8_kernel<<<bwd_grid(S_cap), BWD8_THREADS, smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_h16, dfeat);
-        return check_launch("lse_field_density_mlp_bwd[tc8]");
+    static const int nt = env_int("LSE_DENSITY_BWD_TILES", 3);      // tiles in flight per CTA (2 | 3)
+    if (nt == 2) {
+        constexpr size_t smem_bytes = DensityBwdSm<2>::BYTES;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(density_mlp_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
+        density_mlp_bwd_tc_kernel<2><<<bwd_grid(S_cap, 2), 2 * (TG + 32), smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_h16, dfeat);
+    } else {
+        constexpr size_t smem_bytes = DensityBwdSm<3>::BYTES;
+        static_assert(smem_bytes <= 232448, "density backward exceeds the 227 KiB shared-memory limit");
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(density_mlp_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
+        density_mlp_bwd_tc_kernel<3><<<bwd_grid(S_cap, 3), 3 * (TG + 32), smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_h16, dfeat);
     }
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(density_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
-    density_mlp_bwd_tc_kernel<<<bwd_grid(S_cap), BWD_THREADS, smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_h16, dfeat);
     return check_launch("lse_field_density_mlp_bwd[tc]");
 }
 

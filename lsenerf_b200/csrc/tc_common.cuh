@@ -1,12 +1,12 @@
-// tc_common.cuh -- tcgen05 / TMEM / mbarrier primitives (inline PTX, sm_100a) and the 3xTF32 operand staging used by the
-// LSEField MLP kernels.
+// tc_common.cuh -- tcgen05 / TMEM / mbarrier primitives (inline PTX, sm_100a) and the 3xTF32 operand handling of the forward
+// LSEField MLP kernels (field_tc.cu).
 //
-// Operand layout in shared memory (UMMA canonical K-major, no swizzle): a [rows x K] fp32 matrix is stored as K/4
-// "panels"; panel kc holds, for every row, the 16 bytes of columns 4kc..4kc+3, rows contiguous at 16-byte stride:
+// Weights (B operand) in shared memory, UMMA canonical K-major, no swizzle: a [rows x K] fp32 matrix is stored as K/4 "panels";
+// panel kc holds, for every row, the 16 bytes of columns 4kc..4kc+3, rows contiguous at 16-byte stride:
 //        byte offset(row, k) = (k/4) * rows*16 + row*16 + (k%4)*4
-// i.e. 8-row core matrices of 128 contiguous bytes, SBO (8-row group stride) = 128 B, LBO (next 16-byte K chunk) =
-// rows*16 B.  One tcgen05.mma.kind::tf32 consumes K = 8 (two panels).  A thread that owns row r writes one float4 per
-// panel; a warp's 32 rows are 512 contiguous bytes, so the staging stores are conflict-free STS.128.
+// i.e. 8-row core matrices of 128 contiguous bytes, SBO (8-row group stride) = 128 B, LBO (next 16-byte K chunk) = rows*16 B.
+// Activations (A operand) in TENSOR MEMORY: M along the 128 lanes, K along the columns, one 32-bit column per tf32 element --
+// the layout a thread-per-row epilogue writes with tcgen05.st.  One tcgen05.mma.kind::tf32 consumes K = 8.
 //
 // fp32 parity: the tensor core reads TF32 (10 explicit mantissa bits).  Every operand x is split into hi = x with the low
 // 13 mantissa bits cleared (exactly representable in TF32) and lo = x - hi (exact in fp32, |lo| < 2^-10 |x|), and each
@@ -117,6 +117,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
                    "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
                    "r"(r[30]), "r"(r[31]) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- 3xTF32 split and operand staging ---------------------------------------------------------------------------------
@@ -126,34 +132,22 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo)
     lo = x - hi;
 }
 
-// this thread's activation row v[0..K) -> hi / lo pieces at TMEM columns col_hi / col_lo of its lane
+// a 16- or 32-channel slice of this thread's activation row (8 warps per tile: a thread owns half of its sample's channels) -> hi / lo
+// pieces at TMEM columns col_hi / col_lo of its lane (the caller's columns already point at the slice)
 template <int K>
-__device__ __forceinline__ void stage_tmem(uint32_t tmem_row, int col_hi, int col_lo, const float (&v)[K])
+__device__ __forceinline__ void stage_tmem_slice(uint32_t tmem_row, int col_hi, int col_lo, const float (&v)[K])
 {
+    static_assert(K == 16 || K == 32, "slice of 16 or 32 channels");
+    uint32_t h[K], l[K];
 #pragma unroll
-    for (int c = 0; c < K; c += 32) {
-        uint32_t h[32], l[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float hi, lo;
-            split_tf32(v[c + j], hi, lo);
-            h[j] = __float_as_uint(hi); l[j] = __float_as_uint(lo);
-        }
-        tmem_st32(tmem_row + col_hi + c, h);
-        tmem_st32(tmem_row + col_lo + c, l);
+    for (int j = 0; j < K; ++j) {
+        float hi, lo;
+        split_tf32(v[j], hi, lo);
+        h[j] = __float_as_uint(hi); l[j] = __float_as_uint(lo);
     }
+    if constexpr (K == 32) { tmem_st32(tmem_row + col_hi, h); tmem_st32(tmem_row + col_lo, l); }
+    else { tmem_st16(tmem_row + col_hi, h); tmem_st16(tmem_row + col_lo, l); }
     tmem_st_wait();
-}
-
-
-// write 4 consecutive K values of row `row` (panel kc) into the hi / lo operand buffers of a `rows`-row matrix
-__device__ __forceinline__ void stage4(float *hi_buf, float *lo_buf, int rows, int kc, int row, float a, float b, float c, float d)
-{
-    float4 h, l;
-    split_tf32(a, h.x, l.x); split_tf32(b, h.y, l.y); split_tf32(c, h.z, l.z); split_tf32(d, h.w, l.w);
-    const int off = (kc * rows + row) * 4;
-    *reinterpret_cast<float4 *>(hi_buf + off) = h;
-    *reinterpret_cast<float4 *>(lo_buf + off) = l;
 }
 
 // cooperative: global row-major W[n_real][k_real] -> panel layout [K/4][N][4] (hi and lo), zero padded to N x K
@@ -181,40 +175,9 @@ __device__ __forceinline__ void stage_weights(float *hi_buf, float *lo_buf, cons
     }
 }
 
-// issue the 3 x (K/8) MMAs of one dense layer:  D[128 x N] = A[128 x K] * W[N x K]^T   (A rows = 128)
-__device__ __forceinline__ void issue_layer(uint32_t d_tmem, const float *a_hi, const float *a_lo, const float *w_hi,
-                                            const float *w_lo, int N, int K)
-{
-    const uint32_t idesc = idesc_tf32(128, N);
-    const uint32_t a_lbo = 128 * 16, w_lbo = (uint32_t)N * 16;
-    uint32_t acc = 0;
-    for (int ks = 0; ks < K / 8; ++ks) {
-        const uint32_t ao = ks * 2 * a_lbo, wo = ks * 2 * w_lbo;
-        const uint64_t ah = smem_desc(smem_u32(a_hi) + ao, a_lbo, 128), al = smem_desc(smem_u32(a_lo) + ao, a_lbo, 128);
-        const uint64_t wh = smem_desc(smem_u32(w_hi) + wo, w_lbo, 128), wl = smem_desc(smem_u32(w_lo) + wo, w_lbo, 128);
-        mma_tf32(d_tmem, ah, wh, idesc, acc); acc = 1;
-        mma_tf32(d_tmem, al, wh, idesc, 1);
-        mma_tf32(d_tmem, ah, wl, idesc, 1);
-    }
-}
-
-// the same with shared-window byte addresses (pass warp-uniform values: the descriptors then live in uniform registers and every
-// tcgen05.mma is one instruction instead of a per-instruction register->uniform broadcast loop)
-__device__ __forceinline__ void issue_layer_u(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, int N, int K)
-{
-    const uint32_t idesc = idesc_tf32(128, N);
-    const uint32_t a_lbo = 128 * 16, w_lbo = (uint32_t)N * 16;
-    const uint64_t ah0 = smem_desc(a_hi, a_lbo, 128), al0 = smem_desc(a_lo, a_lbo, 128);
-    const uint64_t wh0 = smem_desc(w_hi, w_lbo, 128), wl0 = smem_desc(w_lo, w_lbo, 128);
-    uint32_t acc = 0;
-    for (int ks = 0; ks < K / 8; ++ks) {
-        const uint64_t ao = (uint64_t)((ks * 2 * a_lbo) >> 4), wo = (uint64_t)((ks * 2 * w_lbo) >> 4);   // start-address field, 16-byte units
-        mma_tf32(d_tmem, ah0 + ao, wh0 + wo, idesc, acc); acc = 1;
-        mma_tf32(d_tmem, al0 + ao, wh0 + wo, idesc, 1);
-        mma_tf32(d_tmem, ah0 + ao, wl0 + wo, idesc, 1);
-    }
-}
-// the same layer with the activations in TMEM (columns a_hi / a_lo of the tile's lanes), weights in shared memory
+// issue the 3 x (K/8) MMAs of one dense layer, D[128 x N] = A[128 x K] * W[N x K]^T: activations in TMEM (columns a_hi / a_lo of the
+// tile's lanes), weights in shared memory.  Pass warp-uniform values: the descriptors then live in uniform registers and every
+// tcgen05.mma is one instruction instead of a per-instruction register->uniform broadcast loop
 __device__ __forceinline__ void issue_layer_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, int N, int K)
 {
     const uint32_t idesc = idesc_tf32(128, N);

@@ -378,12 +378,13 @@ class FieldWeights:
     def tensors(self):
         return [self.table, self.W1, self.b1, self.W2, self.b2, self.W3, self.b3, self.W4, self.b4, self.W5, self.b5]
 
-    def c_params(self, relu_d: Optional[Tensor] = None, relu_c: Optional[Tensor] = None) -> _lib.LseFieldParams:
+    def c_params(self, relu_d: Optional[Tensor] = None, relu_c: Optional[Tensor] = None, rgb_fwd: Optional[Tensor] = None) -> _lib.LseFieldParams:
         """relu_d int64 [S] / relu_c int64 [S,2]: activation-mask buffers of the tensor-core path (written by the forward kernels,
-        read by the backward kernels, see LseFieldParams)."""
+        read by the backward kernels, see LseFieldParams); rgb_fwd [S,3]: the colour forward's output, for its backward."""
         p = _lib.LseFieldParams()
         p.relu_mask_density = relu_d.data_ptr() if relu_d is not None else None
         p.relu_mask_color = relu_c.data_ptr() if relu_c is not None else None
+        p.rgb_fwd = rgb_fwd.data_ptr() if rgb_fwd is not None else None
         p.table = self.table.data_ptr(); p.scalings = self.scalings.data_ptr()
         p.levels = self.scalings.numel(); p.log2_T = self.log2_T
         for n in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "W5", "b5"):
@@ -716,7 +717,7 @@ class _RenderRays(torch.autograd.Function):
             bufs["emb"] = None
         need_o, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         d_h16 = torch.empty(S_cap, 16, device=dev)
-        cp = fw.c_params(relu_d=ctx.relu[0], relu_c=ctx.relu[1]); cg = _grads_struct(fw, bufs)
+        cp = fw.c_params(relu_d=ctx.relu[0], relu_c=ctx.relu[1], rgb_fwd=rgb_s); cg = _grads_struct(fw, bufs)
         # engine path (tensor cores): ray gradients from the stored Jacobian; the table scatter itself is deferred to the caller -- or
         # absent when the table is frozen (camera-only optimisation, train.py:262-293)
         jacpath = bool(fw.use_tensor_cores and opts.defer_table_scatter)

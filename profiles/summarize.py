@@ -15,8 +15,9 @@ import sys
 
 # kernels whose DRAM traffic (per launch, averaged over the captured launches) goes into <tag>_ncu_traffic.json
 TRAFFIC_KERNELS = ("density_fwd_tc_kernel", "color_fwd_tc_kernel", "color_bwd_tc_kernel", "encode_samples_kernel",
-                   "density_mlp_bwd_tc_kernel", "scatter_samples_kernel", "march_runs_kernel", "march_steps_kernel", "adam_hp_kernel",
-                   "cull_generation_kernel")
+                   "density_mlp_bwd_tc_kernel", "scatter_samples_kernel", "ray_grad_samples_kernel", "ray_reduce_kernel",
+                   "march_runs_kernel", "march_classify_kernel", "march_pack_kernel", "adam_hp_kernel", "cull_generation_kernel",
+                   "compact_kernel", "visibility_kernel", "composite_fwd_kernel", "composite_bwd_kernel")
 
 
 def short(name):
@@ -78,17 +79,34 @@ def main():
             d = nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum")
             for kern in TRAFFIC_KERNELS:
                 if kern in name:
-                    t = traffic.setdefault(kern, {"dram_bytes_per_launch": 0.0, "launches": 0, "tensor_pipe_active_pct": 0.0})
+                    t = traffic.setdefault(kern, {"dram_bytes_per_launch": 0.0, "launches": 0, "tensor_pipe_active_pct": 0.0,
+                                                  "active_lanes_per_inst": 0.0, "warps_active_pct": 0.0})
                     t["dram_bytes_per_launch"] += d
                     t["launches"] += 1
-                    tp = vals.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
-                    t["tensor_pipe_active_pct"] += float(tp[0].replace(",", "")) if tp else 0.0
-    for t in traffic.values():
-        t["dram_bytes_per_launch"] /= max(t["launches"], 1)
-        t["tensor_pipe_active_pct"] /= max(t["launches"], 1)   # sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active, mean
+
+                    def num(key):
+                        v = vals.get(key)
+                        return float(v[0].replace(",", "")) if v and v[0] not in ("", "n/a") else 0.0
+                    t["tensor_pipe_active_pct"] += num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+                    t["active_lanes_per_inst"] += num("smsp__thread_inst_executed_per_inst_executed.ratio")
+                    t["warps_active_pct"] += num("sm__warps_active.avg.pct_of_peak_sustained_active")
+    for t in traffic.values():       # means over the captured launches
+        for k in ("dram_bytes_per_launch", "tensor_pipe_active_pct", "active_lanes_per_inst", "warps_active_pct"):
+            t[k] /= max(t["launches"], 1)
         t["source"] = f"profiles/{tag}_kernels_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches of one ncu --set full run)"
     with open(os.path.join(here, f"{tag}_ncu_traffic.json"), "w") as fh:
         json.dump(traffic, fh, indent=1)
+    # the file bench.py reads for `roofline.traffic`: tagged with the kernel sources the capture was taken from (written next to the
+    # capture by tools/profile_round.sh ON the GPU box), so a later code change makes bench.py refuse it instead of misattributing it
+    sha_file = os.path.join(os.path.dirname(os.path.abspath(rep)), f"{tag}_sources_sha.txt")
+    if os.path.exists(sha_file):
+        sha = open(sha_file).read().split()[0]
+        # the GPU box has no .git: the commit is the local one, provided its sources still hash to what was captured
+        sys.path.insert(0, os.path.dirname(here))
+        import bench
+        head = (bench.git_head() or "unknown") if bench.kernel_sources_sha() == sha else "a state between commits"
+        with open(os.path.join(here, "ncu_traffic.json"), "w") as fh:
+            json.dump({"tag": tag, "kernel_sources_sha": sha, "git_head": head, "kernels": traffic}, fh, indent=1)
     print(open(os.path.join(here, f"{tag}_launches_summary.txt")).read())
     print(json.dumps(traffic, indent=1))
 

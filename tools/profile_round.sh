@@ -9,8 +9,9 @@ TAG=${1:-rX}
 MODE=${2:-all}      # all | list (bench + launch list only)
 OUT=gpurun_out
 mkdir -p $OUT
-HOT='regex:density_fwd_tc_kernel|color_fwd_tc_kernel|color_bwd_tc_kernel|encode_samples_kernel|density_mlp_bwd_tc_kernel|scatter_samples_kernel|ray_grad_samples_kernel|ray_reduce_kernel|march_runs_kernel|march_steps_kernel|march_tseq_kernel|march_classify_kernel|march_emit_kernel|adam_hp_kernel|cull_generation_kernel|composite_fwd_kernel|composite_bwd_kernel|compact_kernel|visibility_kernel'
+HOT='regex:density_fwd_tc_kernel|color_fwd_tc_kernel|color_bwd_tc_kernel|encode_samples_kernel|density_mlp_bwd_tc_kernel|scatter_samples_kernel|ray_grad_samples_kernel|ray_reduce_kernel|march_runs_kernel|march_classify_kernel|march_pack_kernel|ray_grad_samples_kernel|ray_reduce_kernel|adam_hp_kernel|cull_generation_kernel|composite_fwd_kernel|composite_bwd_kernel|compact_kernel|visibility_kernel'
 
+python -c "import bench, subprocess; print(bench.kernel_sources_sha(), bench.git_head() or 'snapshot')" > $OUT/${TAG}_sources_sha.txt
 python bench.py > $OUT/${TAG}_bench_1gpu.json 2> $OUT/${TAG}_bench_1gpu.err || { echo "bench failed"; tail -5 $OUT/${TAG}_bench_1gpu.err; exit 1; }
 tail -c 400 $OUT/${TAG}_bench_1gpu.json; echo
 
