@@ -409,6 +409,7 @@ class GraphedStep:
         self.ev_opt: Optional[torch.cuda.Event] = None        # field optimizer of the previous step (side stream)
         self.early = [n for n in optim.names if n != self.FIELD_GROUP]   # groups stepped on the main stream right after B
         self.has_field = self.FIELD_GROUP in optim.names                 # False: field frozen (camera-only optimisation, train.py:262-293)
+        self._one = None
 
     # ---- the two halves of an iteration -----------------------------------------------------------------------------------------
     def _phase_a(self) -> None:
@@ -421,10 +422,24 @@ class GraphedStep:
     def _phase_b(self) -> torch.Tensor:
         # the field gradients are zeroed on the side stream right after the optimizer consumed them (step()): 67 MB of memset off the
         # critical path; B waits for that stream anyway
-        _, loss_dict, _ = self.pipeline.finish_train(self.ctx)
-        loss = sum(loss_dict.values())
+        m = self.pipeline.model
+        m._loss_vec = None
+        m.unit_loss_seed = True       # scoped to this call: only here is it known that the seeds are 1
+        try:
+            _, loss_dict, _ = self.pipeline.finish_train(self.ctx)
+        finally:
+            m.unit_loss_seed = False
+        vals = list(loss_dict.values())
+        if m._loss_vec is not None and len(vals) == 2:
+            # both losses come out of ONE kernel that already wrote their gradients (ops._Losses, unit seeds): no sum, no ones_like, no
+            # seed multiplies, and the [rgb_loss, event_loss] vector the host reads is the kernel's own output
+            if self._one is None:
+                self._one = torch.ones((), device=vals[0].device)
+            torch.autograd.backward(vals, [self._one, self._one])
+            return m._loss_vec
+        loss = sum(vals)
         loss.backward()
-        return torch.stack([v.detach() for v in loss_dict.values()])
+        return torch.stack([v.detach() for v in vals])
 
     def capture(self, start_step: int = 0) -> None:
         """warm up and capture the graphs of one iteration.  No autograd graph built by an EARLIER eager pass over the same parameters

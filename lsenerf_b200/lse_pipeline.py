@@ -70,9 +70,20 @@ class LSENeRFPipeline(nn.Module):
             raw = m.exec_get_outputs(ctx["big"], ctx.get("jitter"), ctx.get("opts"), with_depth=not self.lean)
             idx, sizes = [i for i, _ in ctx["live"]], [n for _, n in ctx["live"]]
             # one split per tensor (its backward is a single cat, where separate slices would be zero-fills + copies + adds)
-            parts = {k: (v.split(sizes) if len(sizes) > 1 else (v,)) for k, v in raw.items() if v is not None}
-            for j, i in enumerate(idx):
-                outs[i] = self._finish({k: v[j] for k, v in parts.items()}, i > 0)       # bundle 0 = RGB, 1 / 2 = event prev / next
+            if self.lean and idx == [0, 1, 2] and sizes[1] == sizes[2] and sizes[1] % 4 == 0 and not m._has_mlp_mapper():
+                # the two event bundles share one epilogue configuration and sit next to each other: ONE epilogue launch (and one in the
+                # backward pass) over both, halves handed out as views.  Deblur groups are 4 consecutive rays (lsenerf.py:365-370), so
+                # with a bundle size divisible by 4 no group straddles the seam and the per-bundle results are unchanged.
+                parts = {k: v.split([sizes[0], 2 * sizes[1]]) for k, v in raw.items() if v is not None}
+                outs[0] = self._finish({k: v[0] for k, v in parts.items()}, False)
+                ev = self._finish({k: v[1] for k, v in parts.items()}, True)
+                halves = {k: v.split(v.shape[0] // 2) for k, v in ev.items() if isinstance(v, torch.Tensor) and v.shape[0] % 2 == 0 and v.shape[0] > 0}
+                outs[1] = {k: v[0] for k, v in halves.items()}
+                outs[2] = {k: v[1] for k, v in halves.items()}
+            else:
+                parts = {k: (v.split(sizes) if len(sizes) > 1 else (v,)) for k, v in raw.items() if v is not None}
+                for j, i in enumerate(idx):
+                    outs[i] = self._finish({k: v[j] for k, v in parts.items()}, i > 0)   # bundle 0 = RGB, 1 / 2 = event prev / next
         else:
             if col_bundle is not None and len(col_bundle) > 0:
                 outs[0] = m(col_bundle, ev_out=False)

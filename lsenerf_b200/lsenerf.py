@@ -362,7 +362,9 @@ class LSENeRFModel(nn.Module):
                 n2 = torch.linalg.norm(tgt, dim=0, keepdim=True) + EPS
             l_ev = c.evs_loss_weight * torch.nn.functional.mse_loss(delta / n1, tgt / n2)
         else:
-            l_rgb, l_ev = ops.losses(col_pred, col_img, prev, nxt, evs, c.evs_loss_weight)
+            # unit_loss_seed (set by engine.GraphedStep): the caller backpropagates exactly rgb_loss + event_loss with seeds of 1
+            l_rgb, l_ev, self._loss_vec = ops.losses(col_pred, col_img, prev, nxt, evs, c.evs_loss_weight,
+                                                     unit_seed=getattr(self, "unit_loss_seed", False), with_vec=True)
         ld = {}
         if col_out is not None:
             ld["rgb_loss"] = l_rgb
