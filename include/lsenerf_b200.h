@@ -257,14 +257,22 @@ int lse_field_density_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, co
                              int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
                              const float *d_h16, float *d_origins, float *d_directions, void *workspace,
                              int64_t workspace_bytes, lse_stream_t stream);
-/* The two halves of lse_field_density_bwd_ws.  `encode` needs d_sigma but not d_h16, so it may run on a side stream
- * concurrently with lse_field_color_bwd (which produces d_h16); join, then `finish`.  with_jacobian != 0: encode also stores
+/* The two halves of lse_field_density_bwd_ws.  `encode` re-gathers the features of the kept samples and needs nothing from the
+ * backward pass (d_sigma is ignored and may be NULL: `finish` / `rays` apply it), so it may run on a side stream as soon as the
+ * kept samples exist -- during the forward pass -- and be joined before `finish`.  with_jacobian != 0: encode also stores
  * d(features)/d(grid coordinate) (96 floats per sample) so that lse_field_density_bwd_rays(with_jacobian) computes the ray
  * gradients without re-gathering the table; lse_field_density_bwd_finish always re-gathers. */
 int lse_field_density_bwd_encode(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                  const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                  int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
                                  int with_jacobian, void *workspace, int64_t workspace_bytes, lse_stream_t stream);
+/* lse_field_density_bwd_encode as a BACKGROUND launch for a side stream: at most ctas_per_sm (1..8) resident CTAs per SM, so the
+ * kernels of the main stream keep their registers and issue slots (the gathers saturate the L1TEX sector rate with far fewer than
+ * 64 warps per SM).  Writes no gradient and reads nothing of the backward pass. */
+int lse_field_density_bwd_encode_bg(const LseFieldParams *p, const float *origins, const float *directions,
+                                    const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap,
+                                    const int32_t *n_dev, const float *h16, int with_jacobian, void *workspace,
+                                    int64_t workspace_bytes, int ctas_per_sm, lse_stream_t stream);
 int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                  const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                  int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,

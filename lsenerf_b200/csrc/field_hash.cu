@@ -2,7 +2,7 @@
 // C-ABI entry that chains them around the base-MLP backward (field_tc_bwd.cu):
 //
 //   encode_samples   (thread = kept sample)  positions -> feat [S,32] (16 levels x 8 float2 gathers, the same arithmetic as the
-//                                            forward), dout0 = d_sigma * d(trunc_exp)/d(raw) * selector
+//                                            forward), dout0 = d(trunc_exp)/d(raw) * selector (times d_sigma in the MLP kernel)
 //   density_mlp_bwd  (tcgen05)               feat, dout0, d_h16 -> dfeat [S,32], dW1, db1, dW2, db2
 //   scatter_samples  (thread = kept sample)  dfeat -> 128 RED.ADD.V2.F32 into the table gradient; d/dx of the trilinear blend
 //                                            (re-gather) -> contraction backward -> per-ray origin / direction gradients
@@ -18,7 +18,7 @@
 namespace lse {
 
 int tc_density_mlp_bwd(const LseFieldParams &P, const LseFieldGrads &G, int64_t S_cap, const int32_t *n_dev, const float *feat,
-                       const float *dout0, const float *d_h16, float *dfeat, cudaStream_t st);
+                       const float *dout0, const float *d_sigma, const float *d_h16, float *dfeat, cudaStream_t st);
 int simt_density_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *origins, const float *directions,
                      const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev,
                      const float *h16, const float *d_sigma, const float *d_h16, float *d_origins, float *d_directions,
@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(HT) encode_samples_kernel(LseFieldParams P, co
                 j2[(size_t)(3 * l + 2) * S_cap] = make_float2(d1[1] * sc, d1[2] * sc);
             }
         }
-        const float gs = d_sigma ? d_sigma[i] : 0.0f;
-        dout0[i] = g.cc.sel ? gs * expf(fminf(fmaxf(h16[16 * i], -15.0f), 15.0f)) : 0.0f;
+        // d(sigma)/d(raw density) = d(trunc_exp) * selector; the base-MLP backward multiplies it by d_sigma (this kernel needs nothing
+        // from the backward pass, so a caller may run it during the FORWARD pass, right after the samples are compacted)
+        dout0[i] = g.cc.sel ? expf(fminf(fmaxf(h16[16 * i], -15.0f), 15.0f)) : 0.0f;
         xs[3 * i] = g.x[0]; xs[3 * i + 1] = g.x[1]; xs[3 * i + 2] = g.x[2];      // grid coordinates for the deferred table scatter
     }
 }
@@ -340,12 +341,13 @@ extern "C" int64_t lse_field_density_bwd_workspace(int64_t S_cap)
     return ((s * 32 * 4 + 255) / 256 * 256) * 2 + (s * 4 + 255) / 256 * 256 + (s * 12 + 255) / 256 * 256 + (s * 96 * 4 + 255) / 256 * 256;
 }
 
-static int check_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins, const float *h16, const char *fn)
+static int check_bwd_ws(const LseFieldParams *p, const LseFieldGrads *g, const float *origins, const float *h16, const char *fn,
+                        bool need_grads = true)
 {
     if (!p) { set_error("%s: params is NULL", fn); return -22; }
     if (!(p->levels == 16 && p->log2_T >= 4 && p->log2_T <= 28 && p->table && p->scalings)) { set_error("%s: bad hash-grid parameters", fn); return -22; }
     if (!(p->W1 && p->b1 && p->W2 && p->b2)) { set_error("%s: base MLP weights missing", fn); return -22; }
-    if (!(g && g->dW1 && g->db1 && g->dW2 && g->db2)) { set_error("%s: gradient buffers for the base MLP missing", fn); return -22; }
+    if (need_grads && !(g && g->dW1 && g->db1 && g->dW2 && g->db2)) { set_error("%s: gradient buffers for the base MLP missing", fn); return -22; }
     if (!(origins && h16)) { set_error("%s: origins / h16 missing", fn); return -22; }
     return 0;
 }
@@ -360,23 +362,50 @@ static BwdWs carve_ws(void *workspace, int64_t S_cap)
             reinterpret_cast<float *>(w + 2 * fbytes + obytes), reinterpret_cast<float *>(w + 2 * fbytes + obytes + xbytes)};
 }
 
-// first third of lse_field_density_bwd_ws: needs only d_sigma (not d_h16), so a caller may run it on a side stream
-// concurrently with lse_field_color_bwd (which produces d_h16) and join before lse_field_density_bwd_finish
+// first third of lse_field_density_bwd_ws: needs NOTHING from the backward pass (d_sigma is accepted for ABI stability and ignored: the
+// base-MLP backward applies it), so a caller may run it on a side stream as soon as the kept samples exist -- under the colour forward,
+// compositing and losses -- and join before lse_field_density_bwd_finish / _rays
+static int encode_launch(const LseFieldParams *p, const LseFieldGrads *g, const float *origins, const float *directions,
+                         const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, const float *h16,
+                         const float *d_sigma, int with_jacobian, void *workspace, int64_t workspace_bytes, int ctas_per_sm,
+                         lse_stream_t stream, const char *fn);
+
 extern "C" int lse_field_density_bwd_encode(const LseFieldParams *p, const LseFieldGrads *g, const float *origins,
                                             const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                             int64_t S_cap, const int32_t *n_dev, const float *h16, const float *d_sigma,
                                             int with_jacobian, void *workspace, int64_t workspace_bytes, lse_stream_t stream)
 {
-    int rc = check_bwd_ws(p, g, origins, h16, __func__);
+    return encode_launch(p, g, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, with_jacobian, workspace, workspace_bytes,
+                         8, stream, __func__);
+}
+
+// the same launch confined to `ctas_per_sm` resident CTAs per SM (1..8): a background launch for a side stream, leaving registers
+// and issue slots to the kernels of the main stream (the gathers saturate the L1TEX sector rate with far fewer than 64 warps per SM)
+extern "C" int lse_field_density_bwd_encode_bg(const LseFieldParams *p, const float *origins, const float *directions,
+                                               const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap,
+                                               const int32_t *n_dev, const float *h16, int with_jacobian, void *workspace,
+                                               int64_t workspace_bytes, int ctas_per_sm, lse_stream_t stream)
+{
+    LSE_CHECK_ARG(ctas_per_sm >= 1 && ctas_per_sm <= 8, "ctas_per_sm in 1..8");
+    return encode_launch(p, nullptr, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, nullptr, with_jacobian, workspace,
+                         workspace_bytes, ctas_per_sm, stream, __func__);
+}
+
+static int encode_launch(const LseFieldParams *p, const LseFieldGrads *g, const float *origins, const float *directions,
+                         const int32_t *ray_idx, const float *t0, const float *t1, int64_t S_cap, const int32_t *n_dev, const float *h16,
+                         const float *d_sigma, int with_jacobian, void *workspace, int64_t workspace_bytes, int ctas_per_sm,
+                         lse_stream_t stream, const char *__func__name)
+{
+    int rc = check_bwd_ws(p, g, origins, h16, __func__name, false);      // writes no gradient: `g` may be NULL
     if (rc) return rc;
     if (S_cap <= 0 || !p->use_tensor_cores) return 0;
-    LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
+    if (!(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap))) { set_error("%s: workspace missing or too small", __func__name); return -22; }
     const BwdWs ws = carve_ws(workspace, S_cap);
     if (with_jacobian)
-        encode_samples_kernel<true><<<stride_grid(S_cap, HT, 8), HT, 0, (cudaStream_t)stream>>>(
+        encode_samples_kernel<true><<<stride_grid(S_cap, HT, ctas_per_sm), HT, 0, (cudaStream_t)stream>>>(
             *p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, ws.feat, ws.dout0, ws.xs, ws.jac);
     else
-        encode_samples_kernel<false><<<stride_grid(S_cap, HT, 8), HT, 0, (cudaStream_t)stream>>>(
+        encode_samples_kernel<false><<<stride_grid(S_cap, HT, ctas_per_sm), HT, 0, (cudaStream_t)stream>>>(
             *p, origins, directions, ray_idx, t0, t1, S_cap, n_dev, h16, d_sigma, ws.feat, ws.dout0, ws.xs, nullptr);
     return check_launch("lse_field_density_bwd_encode");
 }
@@ -396,7 +425,7 @@ extern "C" int lse_field_density_bwd_finish(const LseFieldParams *p, const LseFi
                                 d_directions, st);
     LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
     const BwdWs ws = carve_ws(workspace, S_cap);
-    rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_h16, ws.dfeat, st);
+    rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_sigma, d_h16, ws.dfeat, st);
     if (rc) return rc;
     scatter_samples_kernel<<<stride_grid(S_cap, HT, 8), HT, 0, st>>>(*p, g->d_table, origins, directions, ray_idx, t0, t1, S_cap, n_dev,
                                                                      ws.dfeat, d_origins, d_directions, nullptr);
@@ -420,7 +449,7 @@ extern "C" int lse_field_density_bwd_rays(const LseFieldParams *p, const LseFiel
     cudaStream_t st = (cudaStream_t)stream;
     LSE_CHECK_ARG(workspace && workspace_bytes >= lse_field_density_bwd_workspace(S_cap), "workspace missing or too small");
     const BwdWs ws = carve_ws(workspace, S_cap);
-    rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_h16, ws.dfeat, st);
+    rc = tc_density_mlp_bwd(*p, *g, S_cap, n_dev, ws.feat, ws.dout0, d_sigma, d_h16, ws.dfeat, st);
     if (rc) return rc;
     if (!d_origins && !d_directions) return 0;
     if (with_jacobian && starts && counts) {     // ray-major packed samples: per-sample rows, then one warp per ray; no atomics, WRITTEN

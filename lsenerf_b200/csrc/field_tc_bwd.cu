@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(NT *(TG + 32), 1) density_mlp_bwd_tc_kernel(Ls
                                                                               const int32_t *__restrict__ n_dev,
                                                                               const float *__restrict__ feat,
                                                                               const float *__restrict__ dout0,
+                                                                              const float *__restrict__ d_sigma,
                                                                               const float *__restrict__ d_h16,
                                                                               float *__restrict__ dfeat)
 {
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(NT *(TG + 32), 1) density_mlp_bwd_tc_kernel(Ls
                     const float4 t = d_h16 ? gh[qq] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     dout[4 * qq] = t.x; dout[4 * qq + 1] = t.y; dout[4 * qq + 2] = t.z; dout[4 * qq + 3] = t.w;
                 }
-                if (hf == 0) dout[0] = dout0[i];
+                if (hf == 0) dout[0] = d_sigma ? d_sigma[i] * dout0[i] : 0.0f;      // dL/d(raw density), see encode_samples_kernel
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = 0.0f;
@@ -635,20 +636,20 @@ int tc_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *d
 }
 
 int tc_density_mlp_bwd(const LseFieldParams &P, const LseFieldGrads &G, int64_t S_cap, const int32_t *n_dev, const float *feat,
-                       const float *dout0, const float *d_h16, float *dfeat, cudaStream_t st)
+                       const float *dout0, const float *d_sigma, const float *d_h16, float *dfeat, cudaStream_t st)
 {
     static const int nt = env_int("LSE_DENSITY_BWD_TILES", 3);      // tiles in flight per CTA (2 | 3)
     if (nt == 2) {
         constexpr size_t smem_bytes = DensityBwdSm<2>::BYTES;
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(density_mlp_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
-        density_mlp_bwd_tc_kernel<2><<<bwd_grid(S_cap, 2), 2 * (TG + 32), smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_h16, dfeat);
+        density_mlp_bwd_tc_kernel<2><<<bwd_grid(S_cap, 2), 2 * (TG + 32), smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_sigma, d_h16, dfeat);
     } else {
         constexpr size_t smem_bytes = DensityBwdSm<3>::BYTES;
         static_assert(smem_bytes <= 232448, "density backward exceeds the 227 KiB shared-memory limit");
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(density_mlp_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
-        density_mlp_bwd_tc_kernel<3><<<bwd_grid(S_cap, 3), 3 * (TG + 32), smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_h16, dfeat);
+        density_mlp_bwd_tc_kernel<3><<<bwd_grid(S_cap, 3), 3 * (TG + 32), smem_bytes, st>>>(P, G, S_cap, n_dev, feat, dout0, d_sigma, d_h16, dfeat);
     }
     return check_launch("lse_field_density_mlp_bwd[tc]");
 }

@@ -638,6 +638,11 @@ class RenderOpts:
     accumulate_into_grad: bool = True  # parameter grads are accumulated straight into p.grad (no 64 MiB temporaries)
     keep_debug: bool = False
     debug: dict = dc_field(default_factory=dict)
+    grad_mode: bool = True    # set by render_rays(): torch.is_grad_enabled() at the call (forward() itself always runs with it off)
+
+
+_ENCODE_BG_CTAS = int(os.environ.get("LSE_ENCODE_BG_CTAS", "4"))    # resident CTAs per SM of the background re-encode (profiles/r2q_*: 1 -> 1.53,
+                                                                      # 2 -> 1.450, 4 -> 1.439 ms per step; under the colour backward: 1.444)
 
 
 class _RenderRays(torch.autograd.Function):
@@ -654,7 +659,7 @@ class _RenderRays(torch.autograd.Function):
         assert m0.S_cap == S_cap and m0.counts.numel() == R
         culling = opts.cull and (opts.alpha_thre > 0.0 or opts.early_stop_eps > 0.0)
         # tensor-core path with a backward to come: the forward kernels record the ReLU patterns the backward differentiates
-        want_bwd = any(ctx.needs_input_grad)
+        want_bwd = any(ctx.needs_input_grad) and opts.grad_mode    # needs_input_grad ignores torch.no_grad(): eval renders set it too
         relu_d = _relu_buf(fw, S_cap, 1, o.device) if want_bwd else None
         relu_c = _relu_buf(fw, S_cap, 2, o.device) if want_bwd else None
         if culling and opts.early_stop_eps > 0.0 and opts.early_terminate:
@@ -669,9 +674,28 @@ class _RenderRays(torch.autograd.Function):
             m, sigma_c, h16_c, keep = m0, sigma, h16, None
         if opts.keep_debug:
             opts.debug.update(march0=m0, sigma0=sigma, keep=keep, march=m)
+        dev = o.device
         rgb_s = field_color_raw(fw, d, m.ray_indices, app_id, S_cap, m.total, h16_c, relu_mask=relu_c)
         ctx.relu = (relu_d, relu_c)
-        dev = o.device
+        ctx.bwd_ws = None
+        if want_bwd and fw.use_tensor_cores and opts.grad_mode:
+            # the first third of the density backward -- re-gather of the kept samples' features (+ the Jacobian for ray gradients) --
+            # needs nothing from the backward pass: it is launched HERE on a side stream, behind the colour MLP (whose CTAs take the
+            # whole register file) and confined to a few CTAs per SM, so that it runs under compositing, epilogue, losses and the
+            # head of the colour backward, and is joined in backward() before the base-MLP backward
+            jacpath = bool(opts.defer_table_scatter)
+            jac = int(jacpath and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]))
+            nbytes = int(_lib.lib().lse_field_density_bwd_workspace(S_cap))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            cur, side = torch.cuda.current_stream(), _side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                cpe = fw.c_params()
+                call("lse_field_density_bwd_encode_bg", ctypes.byref(cpe), P(o), P(d), P(m.ray_indices), P(m.t_starts), P(m.t_ends), S_cap,
+                     P(m.total), P(h16_c), jac, P(ws), nbytes, _ENCODE_BG_CTAS, stream())
+            for t in (ws, o, d, m.ray_indices, m.t_starts, m.t_ends, m.total, h16_c):
+                t.record_stream(side)     # should this graph die without a backward pass, the allocator still waits for the side stream
+            ctx.bwd_ws = (ws, nbytes, jac)
         w = torch.empty(S_cap, device=dev)
         out = torch.empty(R, 3, device=dev); acc = torch.empty(R, 1, device=dev); dnum = torch.empty(R, 1, device=dev)
         mm = torch.empty(R, 2, device=dev)
@@ -735,16 +759,10 @@ class _RenderRays(torch.autograd.Function):
             dir_s, packed = None, False
         gd = g_d if (need_d or packed) else None
         if fw.use_tensor_cores:
-            # the re-encode of the kept samples (gather-bound, 256-thread CTAs, no shared memory) needs d_sigma only: it runs on a
-            # side stream under the colour backward (tensor/latency-bound, one 320-thread CTA per SM) and joins before the MLP
-            nbytes = int(_lib.lib().lse_field_density_bwd_workspace(S_cap))
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            # the re-encode of the kept samples (features + Jacobian into the workspace) was started by forward() on the side stream
+            ws, nbytes, jac = ctx.bwd_ws
+            assert jac == int(jacpath and (g_o is not None or gd is not None))    # ray gradients from the stored Jacobian, no re-gather
             cur, side = torch.cuda.current_stream(), _side_stream(dev)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                jac = int(jacpath and (g_o is not None or gd is not None))    # ray gradients from the stored Jacobian, no re-gather
-                call("lse_field_density_bwd_encode", ctypes.byref(cp), ctypes.byref(cg), P(o), P(d), P(m.ray_indices), P(m.t_starts),
-                     P(m.t_ends), S_cap, P(m.total), P(h16), P(d_sigma), jac, P(ws), nbytes, stream())
             call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(m.ray_indices), P(ctx.app_id), S_cap, P(m.total),
                  P(h16), P(d_rgb), P(d_h16), P(dir_s if packed else gd), int(packed), stream())
             cur.wait_stream(side)
@@ -778,6 +796,7 @@ def run_deferred_table_scatter(opts: RenderOpts) -> None:
 def render_rays(fw: FieldWeights, opts: RenderOpts, origins, directions, jitter=None, app_id=None):
     """-> (rgb [R,3], accumulation [R,1], depth_num [R,1], tmid_minmax [R,2], num_samples_per_ray [R])."""
     params = (fw.table, fw.W1, fw.b1, fw.W2, fw.b2, fw.W3, fw.b3, fw.W4, fw.b4, fw.W5, fw.b5, fw.emb)
+    opts.grad_mode = torch.is_grad_enabled()
     return _RenderRays.apply(origins, directions, jitter, app_id, fw, opts, *params)
 
 
