@@ -220,6 +220,11 @@ typedef struct {
        derivative of the output sigmoid is rgb (1 - rgb), so the backward pass need not recompute the output layer -- one MMA phase
        and one tensor-memory round trip less per tile.  NULL: recomputed. */
     const float *rgb_fwd;
+    /* Hidden activations of the colour MLP (optional, may be NULL; tensor-core kernels only): lse_field_color_fwd WRITES, per 128-sample
+       tile, the two hidden layers as the bf16 hi/lo operand panels of the backward kernel (64 KB per tile, lse_field_color_act_bytes);
+       lse_field_color_bwd then loads them straight into shared memory (cp.async.bulk) instead of recomputing them: two MMA phases,
+       two tensor-memory round trips and the operand staging of both hidden layers less per tile.  Requires rgb_fwd in the backward. */
+    void *color_act;
 } LseFieldParams;
 
 typedef struct {
@@ -294,6 +299,8 @@ int lse_field_density_bwd_table(const LseFieldParams *p, const LseFieldGrads *g,
                                 const float *directions, const int32_t *ray_idx, const float *t0, const float *t1,
                                 int64_t S_cap, const int32_t *n_dev, void *workspace, int64_t workspace_bytes,
                                 lse_stream_t stream);
+/* bytes of LseFieldParams.color_act for a capacity of S_cap samples */
+int64_t lse_field_color_act_bytes(int64_t S_cap);
 /* rgb [S,3] = sigmoid(head(cat[SH16(dir), geo15, emb32])).  app_id int32 [n_rays] (per RAY) or NULL. */
 int lse_field_color_fwd(const LseFieldParams *p, const float *directions, const int32_t *ray_idx,
                         const int32_t *app_id, int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb,

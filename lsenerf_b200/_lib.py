@@ -26,7 +26,7 @@ class LseFieldParams(ctypes.Structure):
                 ("W5", ctypes.c_void_p), ("b5", ctypes.c_void_p),
                 ("emb", ctypes.c_void_p), ("emb_rows", ctypes.c_int32), ("emb_mode", ctypes.c_int32),
                 ("sh_shifted", ctypes.c_int32), ("use_tensor_cores", ctypes.c_int32),
-                ("relu_mask_density", ctypes.c_void_p), ("relu_mask_color", ctypes.c_void_p), ("rgb_fwd", ctypes.c_void_p)]
+                ("relu_mask_density", ctypes.c_void_p), ("relu_mask_color", ctypes.c_void_p), ("rgb_fwd", ctypes.c_void_p), ("color_act", ctypes.c_void_p)]
 
 
 class LseFieldGrads(ctypes.Structure):

@@ -21,6 +21,7 @@
 #include "math_field.cuh"
 #include "field_common.cuh"
 #include "tc_common.cuh"
+#include "tc_bf16.cuh"
 #include "../../include/lsenerf_b200.h"
 
 namespace lse {
@@ -311,6 +312,15 @@ __global__ void __launch_bounds__(TG8 *NWG, 1) color_fwd_tc_kernel(LseFieldParam
                     for (int k = 0; k < 32; ++k) mk |= (uint32_t)(x[k] > 0.0f) << k;
                     reinterpret_cast<uint32_t *>(P.relu_mask_color)[4 * i + 2 * layer + hf] = mk;
                 }
+                if (P.color_act) {
+                    // this hidden layer as the backward kernel's operand panels (tc_bf16.cuh): per tile [layer][hi | lo][panel 0..7][row][8]
+                    // bf16, i.e. exactly the 2 x 16 KB the backward copies into its P / Q buffers; a warp's 32 rows write 512
+                    // contiguous bytes per panel.  Rows past the live count are written too (finite values; their gradients are zero).
+                    tcb::bf16_t *dst = reinterpret_cast<tcb::bf16_t *>(P.color_act) + (size_t)tile * (2 * 2 * 8 * tcb::PANEL) +
+                                       (size_t)layer * (2 * 8 * tcb::PANEL);
+#pragma unroll
+                    for (int pn = 0; pn < 4; ++pn) tcb::stage8(dst, 8 * tcb::PANEL, 4 * hf + pn, row, &x[8 * pn]);
+                }
             }
         }
         if (hf == 0) {
@@ -347,6 +357,14 @@ int tc_density_fwd(const LseFieldParams &P, const float *origins, const float *d
     density_fwd_tc_kernel<<<tc_grid(S_cap), TG8 * NWG, smem_bytes, st>>>(P, origins, directions, ray_idx, t0, t1, S_cap, n_dev, list, sigma, h16);
     return check_launch("lse_field_density_fwd[tc]");
 }
+
+}  // namespace lse
+extern "C" int64_t lse_field_color_act_bytes(int64_t S_cap)
+{
+    const int64_t tiles = ((S_cap < 1 ? 1 : S_cap) + lse::WG - 1) / lse::WG;
+    return tiles * (2 * 2 * 8 * lse::tcb::PANEL) * (int64_t)sizeof(lse::tcb::bf16_t);       // 64 KB per 128-sample tile
+}
+namespace lse {
 
 int tc_color_fwd(const LseFieldParams &P, const float *directions, const int32_t *ray_idx, const int32_t *app_id,
                  int64_t S_cap, const int32_t *n_dev, const float *h16, float *rgb, cudaStream_t st)

@@ -99,6 +99,17 @@ struct Handshake8 {
     __device__ __forceinline__ void wait_free() { mbar_wait(free_, rph); rph ^= 1; }
 };
 
+// global -> shared bulk copy (async proxy, no registers), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
 // a value the compiler cannot hoist out of the tile loop: descriptors derived from it are built where they are used
 __device__ __forceinline__ uint32_t opaque(uint32_t v)
 {
@@ -109,8 +120,9 @@ __device__ __forceinline__ uint32_t opaque(uint32_t v)
 
 // channels [32 hf, 32 hf + 32) of the colour-MLP input row (field_common.cuh color_input); channel 63 is the ones column of the
 // transposed weight gradient (W3's padded column 63 is zero)
-__device__ __forceinline__ void color_input_half(const LseFieldParams &P, const float dir[3], const float *__restrict__ h16row,
-                                                 const int32_t *__restrict__ app_id, int32_t ray, int hf, float (&x)[32])
+// hv: the sample's h16 row (read by hf == 0 only), already in registers
+__device__ __forceinline__ void color_input_half_hv(const LseFieldParams &P, const float dir[3], const float (&hv)[16],
+                                                    const int32_t *__restrict__ app_id, int32_t ray, int hf, float (&x)[32])
 {
     const float *erow = nullptr;
     if (!(P.emb_mode == 2 || P.emb == nullptr)) {
@@ -129,10 +141,6 @@ __device__ __forceinline__ void color_input_half(const LseFieldParams &P, const 
         sh16(v, sh);
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = sh[j];
-        const float4 *h4 = reinterpret_cast<const float4 *>(h16row);
-        float hv[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const float4 t = h4[q]; hv[4 * q] = t.x; hv[4 * q + 1] = t.y; hv[4 * q + 2] = t.z; hv[4 * q + 3] = t.w; }
 #pragma unroll
         for (int j = 0; j < 15; ++j) x[16 + j] = hv[1 + j];
         x[31] = erow ? __ldg(erow) : 0.0f;
@@ -151,6 +159,19 @@ __device__ __forceinline__ void color_input_half(const LseFieldParams &P, const 
         x[31] = 1.0f;
     }
 }
+__device__ __forceinline__ void load_h16_row(const float *__restrict__ h16row, float (&hv)[16])
+{
+    const float4 *h4 = reinterpret_cast<const float4 *>(h16row);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float4 t = h4[q]; hv[4 * q] = t.x; hv[4 * q + 1] = t.y; hv[4 * q + 2] = t.z; hv[4 * q + 3] = t.w; }
+}
+__device__ __forceinline__ void color_input_half(const LseFieldParams &P, const float dir[3], const float *__restrict__ h16row,
+                                                 const int32_t *__restrict__ app_id, int32_t ray, int hf, float (&x)[32])
+{
+    float hv[16];
+    if (hf == 0) load_h16_row(h16row, hv);
+    color_input_half_hv(P, dir, hv, app_id, ray, hf, x);
+}
 
 // this thread's 32 channels (panels 4 hf .. 4 hf + 3) of row `row` -> hi / lo pieces
 template <int PIECE>
@@ -160,6 +181,48 @@ __device__ __forceinline__ void stage_half(bf16_t *buf, int row, int hf, const f
     for (int pn = 0; pn < 4; ++pn) stage8(buf, PIECE, 4 * hf + pn, row, &v[8 * pn]);
 }
 
+// what a compute thread does with its half of dX0: SH direction gradient, d_h16 row, per-frame embedding gradient
+__device__ __forceinline__ void color_bwd_outputs(const LseFieldParams &P, const LseFieldGrads &G, bool live, int hf, int64_t i, int32_t ray,
+                                                  const float (&dir)[3], const int32_t *__restrict__ app_id, const float (&x)[32],
+                                                  float *__restrict__ d_h16, float *__restrict__ d_directions, int dir_per_sample)
+{
+    if (live) {
+        if (hf == 0) {
+            if (d_directions) {
+                float v[3], g16[16], dv[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) v[j] = P.sh_shifted ? (dir[j] + 1.0f) / 2.0f : dir[j];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) g16[j] = x[j];
+                sh16_bwd(v, g16, dv);
+                const float sc = P.sh_shifted ? 0.5f : 1.0f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (dir_per_sample) d_directions[3 * i + j] = dv[j] * sc;     // [S,3], reduced per ray by lse_field_density_bwd_rays
+                    else red_add(d_directions + 3 * (int64_t)ray + j, dv[j] * sc);
+                }
+            }
+            float4 *dst = reinterpret_cast<float4 *>(d_h16 + 16 * i);
+            dst[0] = make_float4(0.0f, x[16], x[17], x[18]);
+            dst[1] = make_float4(x[19], x[20], x[21], x[22]);
+            dst[2] = make_float4(x[23], x[24], x[25], x[26]);
+            dst[3] = make_float4(x[27], x[28], x[29], x[30]);
+        }
+        if (G.d_emb && P.emb_mode == 0 && app_id) {
+            int64_t er = app_id[ray];
+            er = er < 0 ? 0 : (er >= P.emb_rows ? P.emb_rows - 1 : er);
+            if (hf == 0) {
+                red_add(G.d_emb + er * NE, x[31]);                                 // embedding channel 0 = input channel 31
+            } else {                                                               // channels 32 + j = embedding channel j + 1
+                red_add(G.d_emb + er * NE + 1, x[0]);
+#pragma unroll
+                for (int e = 2; e < NE; e += 2) red_add2(G.d_emb + er * NE + e, x[e - 1], x[e]);
+            }
+        }
+    }
+}
+
+template <bool STASH>
 __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldParams P, LseFieldGrads G, const float *__restrict__ directions,
                                                                         const int32_t *__restrict__ ray_idx,
                                                                         const int32_t *__restrict__ app_id, int64_t S_cap,
@@ -171,8 +234,8 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldP
     using L = ColorBwdSm;
     bf16_t *sm16 = reinterpret_cast<bf16_t *>(smem_raw);
     float *smf = reinterpret_cast<float *>(smem_raw);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smf + L::FEND);        // [tile group][full, done, free]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 3 * NTG);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smf + L::FEND);        // [tile group][full, done, free, loaded]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 4 * NTG);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool is_issuer = tid >= TG * NTG;
     const int tg = is_issuer ? warp - 8 * NTG : tid / TG;                // tile group
@@ -188,7 +251,7 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldP
         init_bias_panel<64>(sm16 + tg * L::WG + L::P, row);
         init_bias_panel<64>(sm16 + tg * L::WG + L::Q, row);
     }
-    if (tid < NTG) { mbar_init(mbar + 3 * tid, TG); mbar_init(mbar + 3 * tid + 1, 1); mbar_init(mbar + 3 * tid + 2, 1); }
+    if (tid < NTG) { mbar_init(mbar + 4 * tid, TG); mbar_init(mbar + 4 * tid + 1, 1); mbar_init(mbar + 4 * tid + 2, 1); mbar_init(mbar + 4 * tid + 3, 1); }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     fence_mbar_init();
     fence_proxy_async();
@@ -196,7 +259,10 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldP
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot + tg * TMEM_WG;
-    Handshake8 hs{mbar + 3 * tg, mbar + 3 * tg + 1, mbar + 3 * tg + 2, 0u, 0u, 0u};
+    Handshake8 hs{mbar + 4 * tg, mbar + 4 * tg + 1, mbar + 4 * tg + 2, 0u, 0u, 0u};
+    uint64_t *ld_bar = mbar + 4 * tg + 3;
+    // hidden activations stashed by the forward pass (LseFieldParams.color_act): no recompute, 3 phases per tile
+    constexpr bool stash = STASH;      // launcher: P.color_act, P.rgb_fwd and P.relu_mask_color all given
 
     const int64_t S = live_count(n_dev, S_cap);
     const int64_t n_tiles = (S + WGT - 1) / WGT;
@@ -209,11 +275,28 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldP
         const uint32_t tm = uniform(*tmem_slot) + tg_u * TMEM_WG;
         uint32_t accum = 0;
         const bool skip_out = P.rgb_fwd != nullptr;
+        uint32_t n_free = 0, ld_ph = 0;      // commits to `free` so far; parity of the next load completion
         for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
+            if constexpr (stash) {
+                // P and Q are free once the previous tile's last weight gradient has read them; then 4 bulk copies bring this tile's
+                // H2 (-> P) and H1 (-> Q) panels, hi and lo piece each 16 KB, written by the forward kernel in exactly this layout
+                if (n_free) mbar_wait(hs.free_, (n_free - 1) & 1u);
+                if (elect_one()) {
+                    const bf16_t *src = reinterpret_cast<const bf16_t *>(P.color_act) + (size_t)tile * (4 * 8 * PANEL);
+                    const uint32_t aP = smem_u32(bP), aQ = smem_u32(bQ), piece = 2u * PIECE64, half = 16384u;
+                    mbar_expect_tx(ld_bar, 4 * half);
+                    bulk_g2s(aQ, src, half, ld_bar);                                   // layer 0 (H1): hi, lo
+                    bulk_g2s(aQ + piece, src + 8 * PANEL, half, ld_bar);
+                    bulk_g2s(aP, src + 16 * PANEL, half, ld_bar);                      // layer 1 (H2): hi, lo
+                    bulk_g2s(aP + piece, src + 24 * PANEL, half, ld_bar);
+                }
+                __syncwarp();
+            }
 #pragma unroll 1
-            for (int ph = 0; ph < 6; ++ph) {
+            for (int ph = stash ? 3 : 0; ph < 6; ++ph) {
                 if (ph == 2 && skip_out) continue;     // the output layer is not recomputed: H2 and dO are staged together for phase 3
                 hs.wait_staged();
+                if (stash && ph == 3) { mbar_wait(ld_bar, ld_ph); ld_ph ^= 1; }      // the panels have landed (async proxy: no fence)
                 if (elect_one()) {
                     const uint32_t base = opaque(sm_u);
                     const uint32_t aP = base + 2u * (tg_u * L::WG + L::P), aQ = aP + 2u * BUF64, aR = aQ + 2u * BUF64;
@@ -240,6 +323,7 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldP
                     }
                     mma_commit(hs.free_);          // every MMA of this phase has read its operands
                 }
+                ++n_free;
                 __syncwarp();
             }
             accum = 1;
@@ -260,6 +344,55 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldP
                 ray = ray_idx ? ray_idx[i] : (int32_t)i;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) dir[j] = directions[3 * (int64_t)ray + j];
+            }
+            // activation patterns: the forward pass's own (3xTF32) when it stored them, else from this bf16x2 recomputation
+            const bool fwd_masks = P.relu_mask_color != nullptr && live;
+            const uint32_t *mk32 = reinterpret_cast<const uint32_t *>(P.relu_mask_color);
+            uint32_t m1 = fwd_masks ? mk32[4 * i + hf] : 0u, m2 = fwd_masks ? mk32[4 * i + 2 + hf] : 0u;
+            float g3[3] = {0.0f, 0.0f, 0.0f};
+            if (live && hf == 0) { g3[0] = d_rgb[3 * i]; g3[1] = d_rgb[3 * i + 1]; g3[2] = d_rgb[3 * i + 2]; }
+            if constexpr (stash) {
+                // ---- H1 / H2 arrive from the forward pass's stash (issuing warp, bulk copies): phases 3, 4, 5 only --------------------
+                if (hf == 0) {
+                    float dO[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) dO[c] = 0.0f;
+                    if (live) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { const float sg = P.rgb_fwd[3 * i + c]; dO[c] = g3[c] * sg * (1.0f - sg); }
+                    }
+                    stage_row<16, PIECE16>(bR, row, dO);        // R was last read by the previous tile's phase 3
+                }
+                hs.publish();                                   // ph3: R = dO (P = H2, Q = H1 loaded)
+                hs.wait_done();
+                read_row<32>(trow, ccol::SCR, x);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = ((m2 >> j) & 1u) ? x[j] : 0.0f;        // dA2
+                hs.wait_free();                                 // the weight gradient of layer 5 has read P = H2
+                stage_half<PIECE64>(bP, row, hf, x);            // ph4: P = dA2
+                hs.publish();
+                float hv[16];                                   // the sample's h16 row, loaded behind the MMAs of phase 4 (the rest of the
+                if (live && hf == 0) load_h16_row(h16 + 16 * i, hv);   // input row is arithmetic and an L1-resident embedding row)
+                hs.wait_done();
+                read_row<32>(trow, ccol::SCR, x);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = ((m1 >> j) & 1u) ? x[j] : 0.0f;        // dA1
+                hs.wait_free();                                 // the weight gradient of layer 4 has read Q = H1 and P = dA2
+                stage_half<PIECE64>(bQ, row, hf, x);            // ph5: Q = dA1, P = X0
+                if (live) {
+                    color_input_half_hv(P, dir, hv, app_id, ray, hf, x);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+                }
+                stage_half<PIECE64>(bP, row, hf, x);
+                hs.publish();
+                hs.wait_done();
+                read_row<32>(trow, ccol::SCR, x);               // this half of dX0
+                color_bwd_outputs(P, G, live, hf, i, ray, dir, app_id, x, d_h16, d_directions, dir_per_sample);
+                hs.wait_free();                                 // the weight gradient of layer 3 has read P and Q: the next tile's panels may land
+            } else {
+            if (live) {
                 color_input_half(P, dir, h16 + 16 * i, app_id, ray, hf, x);
             } else {
 #pragma unroll
@@ -267,12 +400,6 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldP
             }
             stage_half<PIECE64>(bP, row, hf, x);                // ph0: P = X0 (P, Q are free: end of the previous tile)
             hs.publish();
-            // activation patterns: the forward pass's own (3xTF32) when it stored them, else from this bf16x2 recomputation
-            const bool fwd_masks = P.relu_mask_color != nullptr && live;
-            const uint32_t *mk32 = reinterpret_cast<const uint32_t *>(P.relu_mask_color);
-            uint32_t m1 = fwd_masks ? mk32[4 * i + hf] : 0u, m2 = fwd_masks ? mk32[4 * i + 2 + hf] : 0u;
-            float g3[3] = {0.0f, 0.0f, 0.0f};
-            if (live && hf == 0) { g3[0] = d_rgb[3 * i]; g3[1] = d_rgb[3 * i + 1]; g3[2] = d_rgb[3 * i + 2]; }
             hs.wait_done();
             read_row<32>(trow, ccol::SCR, x);
             hs.wait_free();
@@ -352,41 +479,9 @@ __global__ void __launch_bounds__(BWD8_THREADS, 1) color_bwd_tc_kernel(LseFieldP
             hs.publish();
             hs.wait_done();
             read_row<32>(trow, ccol::SCR, x);                   // this half of dX0
-            if (live) {
-                if (hf == 0) {
-                    if (d_directions) {
-                        float v[3], g16[16], dv[3];
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) v[j] = P.sh_shifted ? (dir[j] + 1.0f) / 2.0f : dir[j];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) g16[j] = x[j];
-                        sh16_bwd(v, g16, dv);
-                        const float sc = P.sh_shifted ? 0.5f : 1.0f;
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            if (dir_per_sample) d_directions[3 * i + j] = dv[j] * sc;     // [S,3], reduced per ray by lse_field_density_bwd_rays
-                            else red_add(d_directions + 3 * (int64_t)ray + j, dv[j] * sc);
-                        }
-                    }
-                    float4 *dst = reinterpret_cast<float4 *>(d_h16 + 16 * i);
-                    dst[0] = make_float4(0.0f, x[16], x[17], x[18]);
-                    dst[1] = make_float4(x[19], x[20], x[21], x[22]);
-                    dst[2] = make_float4(x[23], x[24], x[25], x[26]);
-                    dst[3] = make_float4(x[27], x[28], x[29], x[30]);
-                }
-                if (G.d_emb && P.emb_mode == 0 && app_id) {
-                    int64_t er = app_id[ray];
-                    er = er < 0 ? 0 : (er >= P.emb_rows ? P.emb_rows - 1 : er);
-                    if (hf == 0) {
-                        red_add(G.d_emb + er * NE, x[31]);                                 // embedding channel 0 = input channel 31
-                    } else {                                                               // channels 32 + j = embedding channel j + 1
-                        red_add(G.d_emb + er * NE + 1, x[0]);
-#pragma unroll
-                        for (int e = 2; e < NE; e += 2) red_add2(G.d_emb + er * NE + e, x[e - 1], x[e]);
-                    }
-                }
-            }
+            color_bwd_outputs(P, G, live, hf, i, ray, dir, app_id, x, d_h16, d_directions, dir_per_sample);
             hs.wait_free();                                     // the weight gradient of layer 3 has read P and Q: the next tile may stage
+            }   // !stash
         }
         // ---- flush this tile group's TMEM-resident accumulators: lane k of the accumulator = input channel k -------------------------
         const bool shared_emb = G.d_emb && (P.emb_mode == 1 || (P.emb_mode == 0 && !app_id));
@@ -628,10 +723,17 @@ int tc_color_bwd(const LseFieldParams &P, const LseFieldGrads &G, const float *d
 {
     constexpr size_t smem_bytes = ColorBwdSm::BYTES;
     static_assert(smem_bytes <= 232448, "colour backward exceeds the 227 KiB shared-memory limit");
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(color_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
-    color_bwd_tc_kernel<<<bwd_grid(S_cap), BWD8_THREADS, smem_bytes, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb,
-                                                                          d_h16, d_directions, dir_per_sample);
+    if (P.color_act != nullptr && P.rgb_fwd != nullptr && P.relu_mask_color != nullptr) {     // hidden activations from the forward's stash
+        static bool attr_s = false;
+        if (!attr_s) { cudaFuncSetAttribute(color_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr_s = true; }
+        color_bwd_tc_kernel<true><<<bwd_grid(S_cap), BWD8_THREADS, smem_bytes, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb,
+                                                                                      d_h16, d_directions, dir_per_sample);
+    } else {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(color_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); attr = true; }
+        color_bwd_tc_kernel<false><<<bwd_grid(S_cap), BWD8_THREADS, smem_bytes, st>>>(P, G, directions, ray_idx, app_id, S_cap, n_dev, h16, d_rgb,
+                                                                                       d_h16, d_directions, dir_per_sample);
+    }
     return check_launch("lse_field_color_bwd[tc]");
 }
 

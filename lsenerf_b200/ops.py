@@ -378,13 +378,15 @@ class FieldWeights:
     def tensors(self):
         return [self.table, self.W1, self.b1, self.W2, self.b2, self.W3, self.b3, self.W4, self.b4, self.W5, self.b5]
 
-    def c_params(self, relu_d: Optional[Tensor] = None, relu_c: Optional[Tensor] = None, rgb_fwd: Optional[Tensor] = None) -> _lib.LseFieldParams:
+    def c_params(self, relu_d: Optional[Tensor] = None, relu_c: Optional[Tensor] = None, rgb_fwd: Optional[Tensor] = None,
+                 color_act: Optional[Tensor] = None) -> _lib.LseFieldParams:
         """relu_d int64 [S] / relu_c int64 [S,2]: activation-mask buffers of the tensor-core path (written by the forward kernels,
         read by the backward kernels, see LseFieldParams); rgb_fwd [S,3]: the colour forward's output, for its backward."""
         p = _lib.LseFieldParams()
         p.relu_mask_density = relu_d.data_ptr() if relu_d is not None else None
         p.relu_mask_color = relu_c.data_ptr() if relu_c is not None else None
         p.rgb_fwd = rgb_fwd.data_ptr() if rgb_fwd is not None else None
+        p.color_act = color_act.data_ptr() if color_act is not None else None     # hidden activations of the colour MLP, see the header
         p.table = self.table.data_ptr(); p.scalings = self.scalings.data_ptr()
         p.levels = self.scalings.numel(); p.log2_T = self.log2_T
         for n in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "W5", "b5"):
@@ -457,9 +459,17 @@ def field_density_culling(fw: FieldWeights, origins, directions, m: "MarchResult
     return sigma, h16
 
 
-def field_color_raw(fw: FieldWeights, directions, ray_idx, app_id, S_cap, n_dev, h16, relu_mask: Optional[Tensor] = None):
+def color_act_buf(fw: "FieldWeights", S_cap: int, dev) -> Optional[Tensor]:
+    """stash for the colour MLP's hidden activations (LseFieldParams.color_act); None for the fp32 CUDA-core kernels"""
+    if not fw.use_tensor_cores:
+        return None
+    return torch.empty(int(_lib.lib().lse_field_color_act_bytes(S_cap)), dtype=torch.uint8, device=dev)
+
+
+def field_color_raw(fw: FieldWeights, directions, ray_idx, app_id, S_cap, n_dev, h16, relu_mask: Optional[Tensor] = None,
+                    color_act: Optional[Tensor] = None):
     rgb = torch.empty(S_cap, 3, device=h16.device)
-    cp = fw.c_params(relu_c=relu_mask)
+    cp = fw.c_params(relu_c=relu_mask, color_act=color_act)
     call("lse_field_color_fwd", ctypes.byref(cp), P(directions), P(ray_idx), P(app_id), S_cap, P(n_dev), P(h16), P(rgb), stream())
     return rgb
 
@@ -641,6 +651,7 @@ class RenderOpts:
     grad_mode: bool = True    # set by render_rays(): torch.is_grad_enabled() at the call (forward() itself always runs with it off)
 
 
+_COLOR_ACT_STASH = os.environ.get("LSE_COLOR_ACT_STASH", "1") != "0"     # colour backward from the forward's stashed hidden activations
 _ENCODE_BG_CTAS = int(os.environ.get("LSE_ENCODE_BG_CTAS", "4"))    # resident CTAs per SM of the background re-encode (profiles/r2q_*: 1 -> 1.53,
                                                                       # 2 -> 1.450, 4 -> 1.439 ms per step; under the colour backward: 1.444)
 
@@ -675,7 +686,8 @@ class _RenderRays(torch.autograd.Function):
         if opts.keep_debug:
             opts.debug.update(march0=m0, sigma0=sigma, keep=keep, march=m)
         dev = o.device
-        rgb_s = field_color_raw(fw, d, m.ray_indices, app_id, S_cap, m.total, h16_c, relu_mask=relu_c)
+        ctx.color_act = color_act_buf(fw, S_cap, dev) if (want_bwd and _COLOR_ACT_STASH) else None
+        rgb_s = field_color_raw(fw, d, m.ray_indices, app_id, S_cap, m.total, h16_c, relu_mask=relu_c, color_act=ctx.color_act)
         ctx.relu = (relu_d, relu_c)
         ctx.bwd_ws = None
         if want_bwd and fw.use_tensor_cores and opts.grad_mode:
@@ -741,7 +753,7 @@ class _RenderRays(torch.autograd.Function):
             bufs["emb"] = None
         need_o, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         d_h16 = torch.empty(S_cap, 16, device=dev)
-        cp = fw.c_params(relu_d=ctx.relu[0], relu_c=ctx.relu[1], rgb_fwd=rgb_s); cg = _grads_struct(fw, bufs)
+        cp = fw.c_params(relu_d=ctx.relu[0], relu_c=ctx.relu[1], rgb_fwd=rgb_s, color_act=ctx.color_act); cg = _grads_struct(fw, bufs)
         # engine path (tensor cores): ray gradients from the stored Jacobian; the table scatter itself is deferred to the caller -- or
         # absent when the table is frozen (camera-only optimisation, train.py:262-293)
         jacpath = bool(fw.use_tensor_cores and opts.defer_table_scatter)

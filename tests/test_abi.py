@@ -38,4 +38,4 @@ def test_no_cpu_fallback():
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.LseEpilogueCfg) == 8 * 4
     assert ctypes.sizeof(_lib.LseFieldGrads) == 12 * 8
-    assert ctypes.sizeof(_lib.LseFieldParams) == 2 * 8 + 2 * 4 + 10 * 8 + 8 + 4 * 4 + 3 * 8
+    assert ctypes.sizeof(_lib.LseFieldParams) == 2 * 8 + 2 * 4 + 10 * 8 + 8 + 4 * 4 + 4 * 8

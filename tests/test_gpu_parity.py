@@ -582,8 +582,9 @@ def test_tensor_core_forward_matches_fp32(dev, S):
     from oracle import field as OF
     scene, p = _pipeline(dev, emb=True)
     p.train()
-    fw = p._model.field.weights()
+    fw = dataclasses.replace(p._model.field.weights(), use_tensor_cores=False)     # the model default is the tensor-core path
     fw_tc = dataclasses.replace(fw, use_tensor_cores=True)
+    assert not fw.use_tensor_cores and fw_tc.use_tensor_cores
     g = torch.Generator().manual_seed(S)
     o = (torch.rand(S, 3, generator=g) * 2.4 - 1.2).to(dev)
     d = torch.nn.functional.normalize(torch.randn(S, 3, generator=g), dim=-1).to(dev)
@@ -613,8 +614,9 @@ def test_tensor_core_backward_matches_fp32(dev, S, emb):
     from lsenerf_b200 import ops
     scene, p = _pipeline(dev, emb=emb)
     p.train()
-    fw = p._model.field.weights()
+    fw = dataclasses.replace(p._model.field.weights(), use_tensor_cores=False)     # the model default is the tensor-core path
     fw_tc = dataclasses.replace(fw, use_tensor_cores=True)
+    assert not fw.use_tensor_cores and fw_tc.use_tensor_cores
     g = torch.Generator().manual_seed(S + 7)
     R = max(1, S // 40)
     o = (torch.rand(R, 3, generator=g) * 2.4 - 1.2).to(dev)
@@ -633,15 +635,18 @@ def test_tensor_core_backward_matches_fp32(dev, S, emb):
     import ctypes
     from lsenerf_b200._lib import P, call, stream
 
-    rgb_fwd = ops.field_color_raw(fw_tc, d, ri_c, app, S_cap, n_dev, h16)
+    relu_c = torch.zeros(S_cap, 2, dtype=torch.int64, device=dev)
+    act = ops.color_act_buf(fw_tc, S_cap, dev)
+    rgb_fwd = ops.field_color_raw(fw_tc, d, ri_c, app, S_cap, n_dev, h16, relu_mask=relu_c, color_act=act)
 
-    def run(w, rgb=None):
+    def run(w, rgb=None, stash=False, fwd_masks=False, d_rgb=d_rgb, d_sigma=d_sigma):
         keys = ("table", "W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "W5", "b5")
         bufs = {k: torch.zeros_like(getattr(w, k)) for k in keys}
         bufs["emb"] = torch.zeros_like(w.emb) if w.emb is not None and w.emb_mode in (0, 1) else None
         g_o, g_d = torch.zeros_like(o), torch.zeros_like(d)
         d_h16 = torch.zeros(S_cap, 16, device=dev)
-        cp, cg = w.c_params(rgb_fwd=rgb), ops._grads_struct(w, bufs)
+        cp = w.c_params(rgb_fwd=rgb, relu_c=relu_c if (stash or fwd_masks) else None, color_act=act if stash else None)
+        cg = ops._grads_struct(w, bufs)
         call("lse_field_color_bwd", ctypes.byref(cp), ctypes.byref(cg), P(d), P(ri_c), P(app), S_cap, P(n_dev), P(h16), P(d_rgb),
              P(d_h16), P(g_d), 0, stream())
         ops._density_bwd(w, cp, cg, o, d, ri_c, t0_c, t1_c, S_cap, n_dev, h16, d_sigma, d_h16, g_o, g_d)
@@ -649,12 +654,45 @@ def test_tensor_core_backward_matches_fp32(dev, S, emb):
         out = {k: v for k, v in bufs.items() if v is not None}
         out.update(d_h16=d_h16[:S], g_o=g_o, g_d=g_d)
         return out
-    # tensor-core path twice: output layer recomputed (6 MMA phases per tile) / sigmoid' taken from the forward pass's rgb (5 phases)
-    ref, tc, tc5 = run(fw), run(fw_tc), run(fw_tc, rgb_fwd)
+
+    # the tensor-core colour backward in its forms: output layer recomputed (6 MMA phases per tile) / sigmoid' from the forward pass's
+    # rgb (5 phases) / the same on the ReLU patterns the forward pass recorded / hidden activations from the forward pass's stash as well
+    # (3 phases, the training path)
+    variants = {"recompute": {}, "rgb_fwd": dict(rgb=rgb_fwd), "recorded_patterns": dict(rgb=rgb_fwd, fwd_masks=True),
+                "stash": dict(rgb=rgb_fwd, stash=True)}
+
+    # Pass 1 finds the samples that sit on a ReLU boundary.  A hidden unit within rounding of zero is on in one arithmetic and off in
+    # another (fp32 FMA chain / 3xTF32 / bf16x2), which changes that sample's gradient by a FINITE amount whatever the precision of either
+    # side -- about one sample in 5 000 for the bf16x2 recomputation, one in 50 000 for the recorded 3xTF32 patterns.  They are found
+    # through the per-sample d_h16 rows (colour MLP) and the per-ray gradients (base MLP), must be rare, and are switched off
+    # (d_rgb = d_sigma = 0 removes a sample from every gradient) for ...
+    ref = run(fw)
+    first = {n: run(fw_tc, **kw) for n, kw in variants.items()}
+    flip = torch.zeros(S, dtype=torch.bool, device=dev)
+    flips = {}
+    for n, got in first.items():
+        rows = (got["d_h16"] - ref["d_h16"]).abs().amax(1) > TOL_GRAD * ref["d_h16"].abs().max()
+        rays = ((got["g_o"] - ref["g_o"]).abs().amax(1) > TOL_GRAD * ref["g_o"].abs().max()) | \
+               ((got["g_d"] - ref["g_d"]).abs().amax(1) > TOL_GRAD * ref["g_d"].abs().max())
+        flips[n] = (int(rows.sum()), int(rays.sum()))
+        flip |= rows | rays[ri.long()]
+    assert flips["recompute"][0] <= 2 + S // 1000 and flips["stash"][0] <= 2 + S // 5000, flips
+    assert float(flip.float().mean()) <= 0.05 or S < 200, (flips, float(flip.float().mean()))
+    # ... pass 2: every parameter, embedding, hash-table, per-sample and per-ray gradient of every form within 1e-3 of the fp32 kernels
+    d_rgb2, d_sigma2 = d_rgb.clone(), d_sigma.clone()
+    d_rgb2[:S][flip] = 0.0
+    d_sigma2[:S][flip] = 0.0
+    ref = run(fw, d_rgb=d_rgb2, d_sigma=d_sigma2)
+    second = {n: run(fw_tc, d_rgb=d_rgb2, d_sigma=d_sigma2, **kw) for n, kw in variants.items()}
+    for n, got in second.items():
+        for k in ref:
+            assert torch.isfinite(got[k]).all(), (n, k)
+            assert rel_err(got[k], ref[k]) < TOL_GRAD, (n, k, rel_err(got[k], ref[k]), flips)
+    # the stash itself: same recorded patterns, same arithmetic downstream -> the 5-phase kernel's result up to the bf16x2 rounding of
+    # ITS recomputed activations (the stash holds the forward pass's 3xTF32 ones), with every sample switched on
     for k in ref:
-        for got in (tc, tc5):
-            assert torch.isfinite(got[k]).all(), k
-            assert rel_err(got[k], ref[k]) < TOL_GRAD, (k, rel_err(got[k], ref[k]))
+        e = rel_err(first["stash"][k], first["recorded_patterns"][k])
+        assert e < 5e-5, ("stash vs recorded patterns", k, e)
 
 
 def test_collective_adam_two_gpus(dev):
