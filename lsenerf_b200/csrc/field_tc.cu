@@ -319,7 +319,14 @@ __global__ void __launch_bounds__(TG8 *NWG, 1) color_fwd_tc_kernel(LseFieldParam
                     tcb::bf16_t *dst = reinterpret_cast<tcb::bf16_t *>(P.color_act) + (size_t)tile * (2 * 2 * 8 * tcb::PANEL) +
                                        (size_t)layer * (2 * 8 * tcb::PANEL);
 #pragma unroll
-                    for (int pn = 0; pn < 4; ++pn) tcb::stage8(dst, 8 * tcb::PANEL, 4 * hf + pn, row, &x[8 * pn]);
+                    for (int pn = 0; pn < 4; ++pn) {       // streaming stores: 0.2 GB per step that must not evict the hash table from L2
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) tcb::split2(x[8 * pn + 2 * qq], x[8 * pn + 2 * qq + 1], h[qq], l[qq]);
+                        const int off = (4 * hf + pn) * tcb::PANEL + row * 8;
+                        __stcs(reinterpret_cast<uint4 *>(dst + off), make_uint4(h[0], h[1], h[2], h[3]));
+                        __stcs(reinterpret_cast<uint4 *>(dst + 8 * tcb::PANEL + off), make_uint4(l[0], l[1], l[2], l[3]));
+                    }
                 }
             }
         }
