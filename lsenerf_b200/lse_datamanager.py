@@ -88,6 +88,7 @@ class MultiCamManager(nn.Module):
         # lean = skip the bundle metadata nothing on the fused training path reads (cam_type, coords, nearest-RGB-frame camera
         # index of the event rays): ~25 tiny launches per step.  Off by default: next_train() then returns what upstream returns.
         self.lean = False
+        self.want_app_id = True      # lean only: False when the model's field reads no per-frame appearance id (set by the pipeline)
         self.to(device)
 
     def get_train_col_rays_per_batch(self) -> int:
@@ -164,14 +165,14 @@ class MultiCamManager(nn.Module):
             col_batch = prefetched[0]
             col_bundle = self.col_ray_generator(col_batch["indices"])
             self.col_train_camera_optimizer.apply_to_raybundle(col_bundle)
-            col_bundle = add_metadata(col_bundle, col_batch, max_app_id=self.num_embd, lean=self.lean)
+            col_bundle = add_metadata(col_bundle, col_batch, max_app_id=self.num_embd, lean=self.lean, want_app_id=self.want_app_id)
         if self.get_train_evs_rays_per_batch() > 0:
             evs_batch = prefetched[1]
             prev_bundle, next_bundle = self.evs_ray_generator(evs_batch["indices"])
             self.evs_train_camera_optimizer.apply_to_raybundle(prev_bundle)
             self.evs_train_camera_optimizer.apply_to_raybundle(next_bundle)
-            prev_bundle = add_metadata(prev_bundle, evs_batch, cam_id=1, lean=self.lean)
-            next_bundle = add_metadata(next_bundle, evs_batch, cam_id=1, lean=self.lean)
+            prev_bundle = add_metadata(prev_bundle, evs_batch, cam_id=1, lean=self.lean, want_app_id=self.want_app_id)
+            next_bundle = add_metadata(next_bundle, evs_batch, cam_id=1, lean=self.lean, want_app_id=self.want_app_id)
         if not self.lean and prev_bundle is not None:
             prev_bundle, next_bundle = self.cameraIdxFixer(prev_bundle), self.cameraIdxFixer(next_bundle)
         return (col_bundle, prev_bundle, next_bundle), {"col_batch": col_batch, "evs_batch": evs_batch}

@@ -22,6 +22,10 @@ class RayGenerator(nn.Module):
     @staticmethod
     def _coords(y: Tensor, x: Tensor) -> Tensor:
         """image_coords[y, x]: the table holds integer pixel coordinates (lse_cameras.py:69-73), i.e. (y, x) themselves."""
+        if y.dim() == 1 and x.dim() == 1 and y._base is not None and y._base is x._base and \
+                y.storage_offset() + 1 == x.storage_offset() and y.stride() == x.stride() and y.shape == x.shape:
+            # (y, x) are adjacent columns of the sampler's [B,3] index tensor: one strided convert instead of a stack + a convert
+            return torch.as_strided(y, (y.shape[0], 2), (y.stride(0), 1)).to(torch.float32)
         return torch.stack([y, x], dim=-1).to(torch.float32)
 
     def forward(self, ray_indices: Tensor) -> RayBundle:

@@ -42,8 +42,11 @@ def fix_appearance_id(data, ref_data, max_app_id=1000000):
     return torch.clip(data + delta, 0, max_app_id - 1).reshape(-1, 1)
 
 
-def add_metadata(ray_bundle, batch, cam_id=0, max_app_id=10000000, lean=False):
-    """utils.py:182-194.  lean: appearance_id only (the one entry the model reads, lse_field.py:324-327)."""
+def add_metadata(ray_bundle, batch, cam_id=0, max_app_id=10000000, lean=False, want_app_id=True):
+    """utils.py:182-194.  lean: appearance_id only (the one entry the model reads, lse_field.py:324-327) -- and not even that when the
+    caller knows the field has no per-frame embedding (want_app_id=False: five tiny launches per bundle)."""
+    if lean and not want_app_id:
+        return ray_bundle
     ref = ray_bundle.camera_indices if ray_bundle.camera_indices is not None else ray_bundle.origins
     dev = ref.device
     app = batch["appearance_id"].to(dev)[..., None].contiguous()

@@ -18,6 +18,6 @@ tail -c 400 $OUT/${TAG}_bench_1gpu.json; echo
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --no-cpu --steps 16 --warmup 3 --blocks 1 --profiler-window > $OUT/${TAG}_ncu_launches.log 2>&1 || echo "ncu launch list failed"
 [ "$MODE" = "list" ] && exit 0
-ncu --set full --clock-control none --import-source on --profile-from-start off -k "$HOT" -c 80 -f -o $OUT/${TAG}_full \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k "$HOT" -c 24 -f -o $OUT/${TAG}_full \
     python bench.py --no-cpu --steps 2 --warmup 3 --blocks 1 --profiler-window > $OUT/${TAG}_ncu_full.log 2>&1 || echo "ncu full capture failed"
 ls -la $OUT | tail -8
