@@ -610,32 +610,16 @@ def run_b200(args):
                         "ms_after_exchange_per_rank": [round(float(x[1]), 4) for x in allw],
                         "note": "CUDA-event time around the two symmetric-memory barriers of apply_collective (field + camera arenas per step), mean of 8 steps"}
 
-    # ---- per-kernel-class device time + rooflines (eager launches bracketed by CUDA events, outside the timed regions) -------------
-    eager = GraphedStep(pipe, opt, world, use_graph=False, device_store=args.device_store)
-    eager.step_no = gs.step_no
-    eager.step(); eager.step()
-    _lib.profile_start()
-    l1 = _lib.launch_count()
-    n_prof = 4
-    for _ in range(n_prof):
-        eager.step_no = gs.step_no // 16 * 16 + 1     # keep the (amortised) grid update out of the per-kernel picture
-        eager.step()
-    launches_eager = (_lib.launch_count() - l1) // n_prof
-    prof = _lib.profile_stop()
-    S0, S_eval, S1 = probe_state(pipe, dev)
-    gpk = gather_peaks(dev) if rank == 0 else {}
-
-    # ---- render rays/sec: BASELINE configs[4], one 1280x720 eval frame with camera optimisation, rows sharded over ranks -------
-    render = render_leg(pipe, scene, dev, rank, world, max_over_ranks, barrier)
-
     # ---- the arithmetic-identical figure: the same steps on the fp32 CUDA-core MLP kernels (no tensor cores, no bf16-split backward), one
-    #      block from the state the timed blocks left behind (N = 1 only; it goes last because it keeps training the shared weights) ----
+    #      block from the state the timed blocks left behind (N = 1 only; captured BEFORE any eager pass and on the first engine's streams: autograd runs a
+    #      parameter's gradient accumulator on the stream it was created on, and a backward that hops to a stream outside a capture invalidates it) ----
     simt = None
     if world == 1 and pipe._model.config.use_tensor_cores and not args.no_simt_leg:
         m = pipe._model
         m.config.use_tensor_cores = m.field.use_tensor_cores = False
         try:
             gss = GraphedStep(pipe, opt, 1, use_graph=not args.no_graph, device_store=args.device_store)
+            gss.cap_stream, gss.side = gs.cap_stream, gs.side
             gss.capture(start_step=gs.step_no)
             gss.step_no = 16 * ((gs.step_no + 15) // 16) + 1
             stg = [gss.stage.pack_to_device(*sample_batches()) for _ in range(K + W)]
@@ -657,6 +641,24 @@ def run_b200(args):
             simt = {"error": f"{type(e).__name__}: {e}"}
         m.config.use_tensor_cores = m.field.use_tensor_cores = True
         pipe.defer_table_scatter = True                        # what GraphedStep set for the tensor-core path
+
+    # ---- per-kernel-class device time + rooflines (eager launches bracketed by CUDA events, outside the timed regions) -------------
+    eager = GraphedStep(pipe, opt, world, use_graph=False, device_store=args.device_store)
+    eager.step_no = gs.step_no
+    eager.step(); eager.step()
+    _lib.profile_start()
+    l1 = _lib.launch_count()
+    n_prof = 4
+    for _ in range(n_prof):
+        eager.step_no = gs.step_no // 16 * 16 + 1     # keep the (amortised) grid update out of the per-kernel picture
+        eager.step()
+    launches_eager = (_lib.launch_count() - l1) // n_prof
+    prof = _lib.profile_stop()
+    S0, S_eval, S1 = probe_state(pipe, dev)
+    gpk = gather_peaks(dev) if rank == 0 else {}
+
+    # ---- render rays/sec: BASELINE configs[4], one 1280x720 eval frame with camera optimisation, rows sharded over ranks -------
+    render = render_leg(pipe, scene, dev, rank, world, max_over_ranks, barrier)
 
     if rank == 0:
         per_call = {k: v[1] / v[0] for k, v in prof.items()}
