@@ -4,6 +4,7 @@ CacheDataloader are out of scope: the manager is handed image stores directly (h
 stay on the CPU and only sampled pixels are copied, lse_pixel_sampler.py:28-32)."""
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -88,6 +89,8 @@ class MultiCamManager(nn.Module):
         # lean = skip the bundle metadata nothing on the fused training path reads (cam_type, coords, nearest-RGB-frame camera
         # index of the event rays): ~25 tiny launches per step.  Off by default: next_train() then returns what upstream returns.
         self.lean = False
+        self.fork_raygen = os.environ.get("LSE_RAYGEN_FORK", "1") != "0"
+        self._fork_stream = None
         self.want_app_id = True      # lean only: False when the model's field reads no per-frame appearance id (set by the pipeline)
         self.to(device)
 
@@ -161,18 +164,32 @@ class MultiCamManager(nn.Module):
         if prefetched is None:
             hc, he = self.sample_host_batches()
             prefetched = (self.to_device(hc, True), self.to_device(he, True))
-        if self.get_train_col_rays_per_batch() > 0:
+        has_col, has_evs = self.get_train_col_rays_per_batch() > 0, self.get_train_evs_rays_per_batch() > 0
+        # lean (the captured step): the RGB and the event chains are independent strings of ~10 tiny launches each -- run them as two
+        # branches (fork / join on a second stream, inside the capture) so that the graph's critical path holds one of them, not both
+        fork = self.lean and self.fork_raygen and has_col and has_evs and torch.cuda.is_available()
+        cur = torch.cuda.current_stream() if fork else None
+        if fork:
+            if self._fork_stream is None:
+                self._fork_stream = torch.cuda.Stream(device=self.device)
+            self._fork_stream.wait_stream(cur)
+        if has_col:
             col_batch = prefetched[0]
             col_bundle = self.col_ray_generator(col_batch["indices"])
             self.col_train_camera_optimizer.apply_to_raybundle(col_bundle)
             col_bundle = add_metadata(col_bundle, col_batch, max_app_id=self.num_embd, lean=self.lean, want_app_id=self.want_app_id)
-        if self.get_train_evs_rays_per_batch() > 0:
+        if has_evs:
             evs_batch = prefetched[1]
-            prev_bundle, next_bundle = self.evs_ray_generator(evs_batch["indices"])
-            self.evs_train_camera_optimizer.apply_to_raybundle(prev_bundle)
-            self.evs_train_camera_optimizer.apply_to_raybundle(next_bundle)
-            prev_bundle = add_metadata(prev_bundle, evs_batch, cam_id=1, lean=self.lean, want_app_id=self.want_app_id)
-            next_bundle = add_metadata(next_bundle, evs_batch, cam_id=1, lean=self.lean, want_app_id=self.want_app_id)
+            with torch.cuda.stream(self._fork_stream if fork else torch.cuda.current_stream() if torch.cuda.is_available() else None):
+                prev_bundle, next_bundle = self.evs_ray_generator(evs_batch["indices"])
+                self.evs_train_camera_optimizer.apply_to_raybundle(prev_bundle)
+                self.evs_train_camera_optimizer.apply_to_raybundle(next_bundle)
+                prev_bundle = add_metadata(prev_bundle, evs_batch, cam_id=1, lean=self.lean, want_app_id=self.want_app_id)
+                next_bundle = add_metadata(next_bundle, evs_batch, cam_id=1, lean=self.lean, want_app_id=self.want_app_id)
+            if fork:
+                cur.wait_stream(self._fork_stream)
+                for b in (prev_bundle, next_bundle):
+                    b.origins.record_stream(cur); b.directions.record_stream(cur)
         if not self.lean and prev_bundle is not None:
             prev_bundle, next_bundle = self.cameraIdxFixer(prev_bundle), self.cameraIdxFixer(next_bundle)
         return (col_bundle, prev_bundle, next_bundle), {"col_batch": col_batch, "evs_batch": evs_batch}
