@@ -211,15 +211,46 @@ __device__ __forceinline__ void color_bwd_outputs(const LseFieldParams &P, const
             dst[2] = make_float4(x[23], x[24], x[25], x[26]);
             dst[3] = make_float4(x[27], x[28], x[29], x[30]);
         }
-        if (G.d_emb && P.emb_mode == 0 && app_id) {
-            int64_t er = app_id[ray];
+    }
+    if (G.d_emb && P.emb_mode == 0 && app_id) {      // warp-uniform: every lane of the warp is here (dead lanes included)
+        // Per-frame embeddings: 32 gradient channels per sample onto a few hundred table rows.  The samples of a warp are consecutive
+        // samples of one or two rays, i.e. one or two rows: sum each run of equal rows in a shuffle tree and let the run head issue the
+        // reductions -- up to 32x fewer same-address atomics (0.37 -> see profiles/ for the lsenerf_emb config; they were serialising in L2).
+        const int lane = threadIdx.x & 31;
+        int64_t er = -1 - lane;                                                    // dead lanes: keys no live lane has
+        if (live) {
+            er = app_id[ray];
             er = er < 0 ? 0 : (er >= P.emb_rows ? P.emb_rows - 1 : er);
-            if (hf == 0) {
-                red_add(G.d_emb + er * NE, x[31]);                                 // embedding channel 0 = input channel 31
-            } else {                                                               // channels 32 + j = embedding channel j + 1
-                red_add(G.d_emb + er * NE + 1, x[0]);
+        }
+        const int64_t prev = __shfl_up_sync(0xffffffffu, er, 1);
+        const bool head = lane == 0 || prev != er;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const uint32_t above = heads & ~((2u << lane) - 1u);                       // run starts strictly above this lane
+        const int last = lane == 31 ? 31 : (above ? __ffs(above) - 2 : 31);
+        const int max_len = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last - lane + 1));
+        if (hf == 0) {                                                             // embedding channel 0 = input channel 31
+            float v = x[31];
+            for (int s = 1; s < max_len; s <<= 1) {
+                const float t = __shfl_down_sync(0xffffffffu, v, s);
+                if (lane + s <= last) v += t;
+            }
+            if (head && live) red_add(G.d_emb + er * NE, v);
+        } else {                                                                   // input channels 32 + j = embedding channel j + 1
+            float v[32];
 #pragma unroll
-                for (int e = 2; e < NE; e += 2) red_add2(G.d_emb + er * NE + e, x[e - 1], x[e]);
+            for (int j = 0; j < 32; ++j) v[j] = x[j];
+            for (int s = 1; s < max_len; s <<= 1) {
+                const bool in_run = lane + s <= last;
+#pragma unroll
+                for (int j = 0; j < 31; ++j) {
+                    const float t = __shfl_down_sync(0xffffffffu, v[j], s);
+                    if (in_run) v[j] += t;
+                }
+            }
+            if (head && live) {
+                red_add(G.d_emb + er * NE + 1, v[0]);
+#pragma unroll
+                for (int e = 2; e < NE; e += 2) red_add2(G.d_emb + er * NE + e, v[e - 1], v[e]);
             }
         }
     }
