@@ -124,6 +124,14 @@ def test_ray_generator_coords_and_bundle_concat():
     table = cams.get_image_coords()
     y, x = torch.tensor([0, 5, 11]), torch.tensor([15, 0, 7])
     assert torch.equal(RayGenerator._coords(y, x), table[y, x])
+    # columns of the sampler's [B,3] (camera, y, x) index tensor take the one-launch strided path: same values, contiguous result
+    idx = torch.tensor([[1, 0, 15], [0, 5, 0], [1, 11, 7], [0, 3, 3]])
+    got = RayGenerator._coords(idx[:, 1], idx[:, 2])
+    assert got.is_contiguous() and got.dtype == torch.float32 and torch.equal(got, table[idx[:, 1], idx[:, 2]])
+    sub = idx[1:]                      # a view with a storage offset
+    assert torch.equal(RayGenerator._coords(sub[:, 1], sub[:, 2]), table[sub[:, 1], sub[:, 2]])
+    # swapped columns are not adjacent in the expected order: the stack path
+    assert torch.equal(RayGenerator._coords(idx[:, 2], idx[:, 1]), torch.stack([idx[:, 2], idx[:, 1]], -1).float())
     a = RayBundle(torch.zeros(3, 3), torch.ones(3, 3), torch.ones(3, 1), torch.zeros(3, 1, dtype=torch.long), metadata={"appearance_id": torch.zeros(3, 1), "coords": torch.zeros(3, 3)})
     b = RayBundle(torch.ones(2, 3), torch.zeros(2, 3), torch.ones(2, 1), torch.ones(2, 1, dtype=torch.long), metadata={"appearance_id": torch.ones(2, 1), "coords": torch.ones(2, 3)})
     full = concat_bundles([a, b])
@@ -131,6 +139,20 @@ def test_ray_generator_coords_and_bundle_concat():
     lean = concat_bundles([a, b], fields=("origins", "directions"), metadata_keys=("appearance_id",))
     assert lean.pixel_area is None and lean.camera_indices is None and set(lean.metadata) == {"appearance_id"}
     assert torch.equal(lean.origins, full.origins) and torch.equal(lean.directions, full.directions)
+
+
+def test_lean_metadata_skips_appearance_ids_only_when_told():
+    """add_metadata(lean, want_app_id=False) leaves the bundle untouched (the field reads no per-frame embedding); every other
+    combination still fills appearance_id exactly as utils.py:172-194 does."""
+    from lsenerf_b200.compat import RayBundle
+    mk = lambda: RayBundle(torch.zeros(8, 3), torch.ones(8, 3), torch.ones(8, 1), None, metadata={})
+    batch = {"appearance_id": torch.tensor([3, 0]), "indices": torch.zeros(2, 3, dtype=torch.long)}
+    assert "appearance_id" not in utils.add_metadata(mk(), batch, lean=True, want_app_id=False).metadata
+    ref = utils.add_metadata(mk(), batch, max_app_id=5).metadata
+    for kw in (dict(lean=True), dict(lean=True, want_app_id=True), dict(lean=False, want_app_id=False)):
+        got = utils.add_metadata(mk(), batch, max_app_id=5, **kw).metadata
+        assert torch.equal(got["appearance_id"], ref["appearance_id"])
+    assert ref["appearance_id"].reshape(-1).tolist() == [1, 2, 3, 4, 0, 0, 0, 1]      # id + {-2,-1,0,1} clipped to [0, 4], pixel-major
 
 
 def test_collective_slices_tile_the_arena():
