@@ -459,11 +459,19 @@ def field_density_culling(fw: FieldWeights, origins, directions, m: "MarchResult
     return sigma, h16
 
 
-def color_act_buf(fw: "FieldWeights", S_cap: int, dev) -> Optional[Tensor]:
-    """stash for the colour MLP's hidden activations (LseFieldParams.color_act); None for the fp32 CUDA-core kernels"""
+_COLOR_ACT_MAX_BYTES = int(os.environ.get("LSE_COLOR_ACT_MAX_BYTES", str(8 << 30)))
+
+
+def color_act_buf(fw: "FieldWeights", S_cap: int, dev, max_bytes: Optional[int] = None) -> Optional[Tensor]:
+    """stash for the colour MLP's hidden activations (LseFieldParams.color_act); None for the fp32 CUDA-core kernels -- and None when
+    the CAPACITY (512 B per sample slot, live or not) would exceed max_bytes: the backward then recomputes the hidden layers (a
+    full-frame gradient pass has a capacity of 1.6e8 sample slots, which is 80 GB of stash for a few GB of live samples)."""
     if not fw.use_tensor_cores:
         return None
-    return torch.empty(int(_lib.lib().lse_field_color_act_bytes(S_cap)), dtype=torch.uint8, device=dev)
+    nbytes = int(_lib.lib().lse_field_color_act_bytes(S_cap))
+    if max_bytes is not None and nbytes > max_bytes:
+        return None
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
 
 def field_color_raw(fw: FieldWeights, directions, ray_idx, app_id, S_cap, n_dev, h16, relu_mask: Optional[Tensor] = None,
@@ -686,7 +694,7 @@ class _RenderRays(torch.autograd.Function):
         if opts.keep_debug:
             opts.debug.update(march0=m0, sigma0=sigma, keep=keep, march=m)
         dev = o.device
-        ctx.color_act = color_act_buf(fw, S_cap, dev) if (want_bwd and _COLOR_ACT_STASH) else None
+        ctx.color_act = color_act_buf(fw, S_cap, dev, _COLOR_ACT_MAX_BYTES) if (want_bwd and _COLOR_ACT_STASH) else None
         rgb_s = field_color_raw(fw, d, m.ray_indices, app_id, S_cap, m.total, h16_c, relu_mask=relu_c, color_act=ctx.color_act)
         ctx.relu = (relu_d, relu_c)
         ctx.bwd_ws = None
