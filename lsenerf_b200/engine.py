@@ -14,10 +14,17 @@ step, one optimizer kernel per tensor).  Here:
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
 from torch import nn
+
+# Resident CTAs per SM of the deferred table scatter (lse_field_density_bwd_table reads LSE_SIDE_CTAS at its first launch; the library's
+# own default is 4).  The scatter runs on this engine's side stream UNDER the next step's ray generation + march, whose CTAs need
+# registers to land in: at 63 registers x 256 threads, four scatter CTAs hold the whole register file of an SM and the march waits for
+# them.  Measured on one box (profiles/r3h_*): 2 -> 1.277, 3 -> 1.252, 4 -> 1.360, 6 -> 1.260, 8 -> 1.336 ms per step.
+os.environ.setdefault("LSE_SIDE_CTAS", "3")
 
 from . import ops
 from ._lib import P, call, stream
