@@ -36,6 +36,10 @@ class EvsFrameEmbedding(nn.Module):
         self.test_emb = nn.Embedding(1, self.out_dim).to(self.embedding.weight.device)
         self.test_emb.weight = nn.Parameter(self.embedding.weight[21:22].detach().clone())
 
+    def reads_appearance_id(self, training: bool) -> bool:
+        """does the field look up a row per ray (kernel_mode 0)?  Asked once per step by the lean data path; launches nothing."""
+        return bool(training and not gbconfig.IS_EVAL)
+
     def kernel_mode(self, training: bool):
         """-> (emb_mode, table) for LseFieldParams: 0 per-ray id, 1 row 0, 2 zeros, 3 explicit row."""
         if training and not gbconfig.IS_EVAL:
@@ -60,6 +64,9 @@ class GlobalEmbedding(EvsFrameEmbedding):
 
     def __init__(self, config, num_imgs, num_dims=None) -> None:
         super().__init__(config, 1, num_dims)
+
+    def reads_appearance_id(self, training: bool) -> bool:
+        return False
 
     def kernel_mode(self, training: bool):
         return 1, self.embedding.weight

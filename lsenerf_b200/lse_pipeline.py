@@ -40,7 +40,8 @@ class LSENeRFPipeline(nn.Module):
         """First half of get_train_loss_dict: everything that depends on the camera parameters and the occupancy grid but NOT on
         the field weights -- batch, ray bundles and (premarch=True, fused bundles) the occupancy-grid march.  The engine runs it
         while the previous step's optimizer is still updating the field."""
-        self.datamanager.want_app_id = self._model.field.weights().emb_mode == 0      # only a per-frame embedding reads appearance ids
+        f = self._model.field                                                           # only a per-frame embedding reads appearance ids
+        self.datamanager.want_app_id = f.embedding_appearance.reads_appearance_id(f.training)
         bundles, batch = self.datamanager.next_train(step, prefetched)
         ctx = {"bundles": bundles, "batch": batch}
         m = self._model

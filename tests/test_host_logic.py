@@ -155,6 +155,23 @@ def test_lean_metadata_skips_appearance_ids_only_when_told():
     assert ref["appearance_id"].reshape(-1).tolist() == [1, 2, 3, 4, 0, 0, 0, 1]      # id + {-2,-1,0,1} clipped to [0, 4], pixel-major
 
 
+def test_reads_appearance_id_agrees_with_kernel_mode():
+    """the launch-free question the lean data path asks per step == (kernel_mode(...)[0] == 0), for both embedding types, train / eval
+    and the global eval switch"""
+    from lsenerf_b200.lse_embeddings import LSEEmbeddingConfig
+    from lsenerf_b200.utils import gbconfig
+    was = gbconfig.IS_EVAL
+    try:
+        for kind in ("global_emb", "evs_emb"):
+            emb = LSEEmbeddingConfig(embedding_type=kind, eval_mode="zero").setup(num_imgs=5, num_dims=32)
+            for is_eval in (False, True):
+                gbconfig.IS_EVAL = is_eval
+                for training in (False, True):
+                    assert emb.reads_appearance_id(training) == (emb.kernel_mode(training)[0] == 0), (kind, is_eval, training)
+    finally:
+        gbconfig.IS_EVAL = was
+
+
 def test_collective_slices_tile_the_arena():
     """ArenaAdam._slice restates the slice arithmetic of csrc/adam_collective.cu (gather_moments re-assembles the sharded Adam moments
     from it): the ranks' slices are disjoint, ordered and cover the arena."""
